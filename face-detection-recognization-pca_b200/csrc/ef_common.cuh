@@ -1,0 +1,86 @@
+// Shared helpers for libeigenfaces_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+
+#include "../../include/eigenfaces_b200.h"
+
+namespace ef {
+
+extern std::atomic<int64_t> g_launches;
+void set_error_detail(const char* what, cudaError_t e);
+
+#define EF_CUDA(call)                                   \
+  do {                                                  \
+    cudaError_t e__ = (call);                           \
+    if (e__ != cudaSuccess) {                           \
+      ::ef::set_error_detail(#call, e__);               \
+      return EF_ERR_CUDA;                               \
+    }                                                   \
+  } while (0)
+
+#define EF_TRY(call)              \
+  do {                            \
+    int s__ = (call);             \
+    if (s__ != EF_OK) return s__; \
+  } while (0)
+
+// Every kernel launch of the library goes through this macro so that ef_launch_count() is exact.
+#define EF_LAUNCH(kernel, grid, block, smem, stream, ...)                 \
+  do {                                                                    \
+    kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);           \
+    ::ef::g_launches.fetch_add(1, std::memory_order_relaxed);             \
+    cudaError_t e__ = cudaPeekAtLastError();                              \
+    if (e__ != cudaSuccess) {                                             \
+      ::ef::set_error_detail(#kernel, e__);                               \
+      return EF_ERR_CUDA;                                                 \
+    }                                                                     \
+  } while (0)
+
+static inline cudaStream_t as_stream(ef_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
+static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+int sm_count();  // cached SM count of the current device (148 on B200)
+
+// Simple RAII device buffer for the host-side orchestration code.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  DevBuf() = default;
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    bytes = 0;
+  }
+  int ensure(size_t n) {
+    if (n <= bytes) return EF_OK;
+    release();
+    cudaError_t e = cudaMalloc(&p, n);
+    if (e != cudaSuccess) {
+      set_error_detail("cudaMalloc", e);
+      p = nullptr;
+      return EF_ERR_NOMEM;
+    }
+    bytes = n;
+    return EF_OK;
+  }
+  template <class T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ---------------------------------------------------------------------------------------------- device
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+}  // namespace ef

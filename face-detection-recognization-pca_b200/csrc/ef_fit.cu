@@ -1,0 +1,351 @@
+// PCA fit orchestration (host entry points): Gen-1 manual_pca and Gen-2 StandardScaler + PCA(full).
+//
+//   ef_fit_gen1_host   useless/train.py:56-128   mean, centre, Gram (N<D) or covariance, eigh, back-projection,
+//                                                column normalisation, descending sort, top-k, projection
+//   ef_fit_gen2_host   train-v5.py:349-385       pixel mean, StandardScaler.fit_transform, PCA(k).fit_transform
+//                                                (solver "full": SVD of the centred matrix, svd_flip, U*S)
+// Everything numeric runs on the device in float64; the host only sequences launches and does O(n) bookkeeping on
+// the eigenvalue vector.
+#include <climits>
+#include <cmath>
+#include <vector>
+
+#include "ef_common.cuh"
+#include "ef_internal.cuh"
+
+namespace {
+
+__global__ void mean_from_colsum_kernel(const long long* __restrict__ colsum, int D, long long N,
+                                        double* __restrict__ mean) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < D) mean[d] = (double)colsum[d] / (double)N;   // np.mean: exact integer sum, one division
+}
+
+// sklearn _incremental_mean_and_var (first batch): per column, sequential over rows like np.sum(axis=0).
+__global__ void scaler_var_kernel(const uint8_t* __restrict__ X, int64_t ldx, int64_t N, int D,
+                                  const double* __restrict__ mean, double* __restrict__ var,
+                                  double* __restrict__ scale) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const double T = mean[d];
+  double corr = 0.0, s2 = 0.0;
+  for (int64_t n = 0; n < N; ++n) {
+    const double t = (double)X[n * ldx + d] - T;
+    corr += t;
+    s2 += t * t;
+  }
+  const double nn = (double)N;
+  double v = (s2 - corr * corr / nn) / nn;
+  var[d] = v;
+  const double eps = 2.220446049250313e-16;
+  const double nme = nn * T * eps;
+  const bool constant = v <= nn * eps * v + nme * nme;
+  double sc = sqrt(v);
+  if (constant || sc == 0.0) sc = 1.0;
+  scale[d] = sc;
+}
+
+// column means of a float64 matrix, sequential over rows (np.mean(axis=0) order), then subtract in place
+__global__ void colmean_center_kernel(double* __restrict__ Z, int64_t ldz, int64_t N, int D,
+                                      double* __restrict__ mean_out) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  double s = 0.0;
+  for (int64_t n = 0; n < N; ++n) s += Z[n * ldz + d];
+  const double m = s / (double)N;
+  mean_out[d] = m;
+  for (int64_t n = 0; n < N; ++n) Z[n * ldz + d] -= m;
+}
+
+// E [D][k] row-major: divide every column by its 2-norm (useless/train.py:94-95). One CTA per column.
+__global__ void colnorm_kernel(double* __restrict__ E, int D, int k) {
+  __shared__ double red[8];
+  const int c = blockIdx.x;
+  double s = 0.0;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const double v = E[(int64_t)d * k + c];
+    s = fma(v, v, s);
+  }
+  s = ef::warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  double tot = 0.0;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+  const double nrm = sqrt(tot);
+  for (int d = threadIdx.x; d < D; d += blockDim.x) E[(int64_t)d * k + c] = E[(int64_t)d * k + c] / nrm;
+}
+
+// Vt [k][D] row-major: normalise every row, then sklearn svd_flip(u_based_decision=False): make the entry of
+// largest magnitude (first occurrence) positive.  sign[c] receives +-1.  One CTA per row.
+__global__ void rownorm_flip_kernel(double* __restrict__ Vt, int k, int D, double* __restrict__ sign) {
+  __shared__ double red[8];
+  __shared__ double bestv[8];
+  __shared__ int besti[8];
+  const int c = blockIdx.x;
+  double* row = Vt + (int64_t)c * D;
+  double s = 0.0, bv = -1.0;
+  int bi = INT_MAX;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const double v = row[d];
+    s = fma(v, v, s);
+    const double a = fabs(v);
+    if (a > bv) { bv = a; bi = d; }
+  }
+  s = ef::warp_sum(s);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double v2 = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int i2 = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (v2 > bv || (v2 == bv && i2 < bi)) { bv = v2; bi = i2; }
+  }
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[w] = s; bestv[w] = bv; besti[w] = bi; }
+  __syncthreads();
+  double tot = 0.0;
+  bv = -1.0; bi = INT_MAX;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+    tot += red[i];
+    if (bestv[i] > bv || (bestv[i] == bv && besti[i] < bi)) { bv = bestv[i]; bi = besti[i]; }
+  }
+  const double nrm = sqrt(tot);
+  const double sg = (bi != INT_MAX && row[bi] < 0.0) ? -1.0 : 1.0;
+  __syncthreads();
+  const double f = (nrm > 0.0) ? sg / nrm : sg;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) row[d] = row[d] * f;
+  if (threadIdx.x == 0) sign[c] = sg;
+}
+
+// features[n][c] = sign[c] * U[c][n] * S[c]   (U rows are eigenvectors of the N x N Gram)
+__global__ void features_kernel(const double* __restrict__ U, int N, int k, const double* __restrict__ S,
+                                const double* __restrict__ sign, double* __restrict__ F) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)N * k) return;
+  const int n = (int)(e / k), c = (int)(e % k);
+  F[e] = sign[c] * U[(int64_t)c * N + n] * S[c];
+}
+
+// E[d][c] = V[c][d] for c < k  (V rows of length D)
+__global__ void rows_to_cols_kernel(const double* __restrict__ V, int D, int k, double* __restrict__ E) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)D * k) return;
+  const int d = (int)(e / k), c = (int)(e % k);
+  E[e] = V[(int64_t)c * D + d];
+}
+
+struct Timer {
+  cudaEvent_t a = nullptr, b = nullptr;
+  ~Timer() {
+    if (a) cudaEventDestroy(a);
+    if (b) cudaEventDestroy(b);
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+int ef_fit_gen1_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_t k, double* eigenfaces,
+                     double* mean, double* projected, double* eigenvalues, ef_fit_info_t* info) {
+  if (!X || !eigenfaces || !mean || !projected || !eigenvalues || N < 2 || D <= 0 || ldx < D) return EF_ERR_INVALID;
+  const bool snapshot = N < D;                                 // useless/train.py:82
+  const int n = snapshot ? N : D;
+  if (n > 4096) return EF_ERR_UNSUPPORTED;
+  if (k <= 0) k = std::min(N - 1, D);                          // :111-112
+  k = std::min(k, n);                                          // :114
+  int dev_count = 0;
+  EF_CUDA(cudaGetDeviceCount(&dev_count));
+  cudaStream_t st = nullptr;
+  EF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
+  Timer tm;
+  EF_CUDA(cudaEventCreate(&tm.a));
+  EF_CUDA(cudaEventCreate(&tm.b));
+
+  ef::DevBuf dX, dsum, dmean, dZ, dA, dwork, devals, devecs, dE, dP;
+  const int64_t ldxd = ef::round_up(D, 16);
+  EF_TRY(dX.ensure((size_t)N * ldxd));
+  EF_TRY(dsum.ensure(sizeof(int64_t) * D));
+  EF_TRY(dmean.ensure(sizeof(double) * D));
+  EF_TRY(dZ.ensure(sizeof(double) * (size_t)N * D));
+  EF_TRY(dA.ensure(sizeof(double) * (size_t)n * n));
+  EF_TRY(dwork.ensure(ef_eigh_work_bytes(n)));
+  EF_TRY(devals.ensure(sizeof(double) * n));
+  EF_TRY(devecs.ensure(sizeof(double) * (size_t)n * n));
+  EF_TRY(dE.ensure(sizeof(double) * (size_t)D * k));
+  EF_TRY(dP.ensure(sizeof(double) * (size_t)N * k));
+  EF_CUDA(cudaMemcpy2DAsync(dX.p, ldxd, X, ldx, D, N, cudaMemcpyHostToDevice, st));
+  EF_CUDA(cudaEventRecord(tm.a, st));
+
+  // mean face, centred data
+  EF_TRY(ef_colsum_u8_device(dX.as<uint8_t>(), ldxd, N, D, dsum.as<int64_t>(), st));
+  EF_LAUNCH(mean_from_colsum_kernel, (unsigned)ef::ceil_div(D, 256), 256, 0, st, dsum.as<long long>(), D, (long long)N,
+            dmean.as<double>());
+  EF_TRY(ef_standardize_u8_device(dX.as<uint8_t>(), ldxd, N, D, dmean.as<double>(), nullptr, nullptr, dZ.as<double>(), D, st));
+  const double alpha = 1.0 / (double)(N - 1);
+  double* Z = dZ.as<double>();
+  if (snapshot) {
+    // cov = Xc Xc^T / (N-1)                                                                   :84
+    EF_TRY(ef_dgemm_device(N, N, D, alpha, Z, D, 1, Z, 1, D, 0.0, dA.as<double>(), N, st));
+  } else {
+    // cov = Xc^T Xc / (N-1)                                                                   :99
+    EF_TRY(ef_dgemm_device(D, D, N, alpha, Z, 1, D, Z, D, 1, 0.0, dA.as<double>(), D, st));
+  }
+  int sweeps = 0;
+  double off = 0.0;
+  const int est = ef_eigh_jacobi_device(dA.as<double>(), n, devals.as<double>(), devecs.as<double>(), dwork.p, 0, 0.0,
+                                        &sweeps, &off, st);
+  if (est != EF_OK) return est;
+  double* E = dE.as<double>();
+  if (snapshot) {
+    // eigenfaces = Xc^T V (top-k columns), then column normalisation                          :91-95
+    EF_TRY(ef_dgemm_device(D, k, N, 1.0, Z, 1, D, devecs.as<double>(), 1, N, 0.0, E, k, st));
+    EF_LAUNCH(colnorm_kernel, k, 256, 0, st, E, D, k);
+  } else {
+    // eigenvectors of the covariance are the eigenfaces: E[d][c] = evecs[c][d]
+    EF_LAUNCH(rows_to_cols_kernel, (unsigned)ef::ceil_div((int64_t)D * k, 256), 256, 0, st, devecs.as<double>(), D, k, E);
+  }
+  // projected_data = Xc E                                                                      :122
+  EF_TRY(ef_dgemm_device(N, k, D, 1.0, Z, D, 1, E, k, 1, 0.0, dP.as<double>(), k, st));
+  EF_CUDA(cudaEventRecord(tm.b, st));
+
+  std::vector<double> Eh((size_t)D * k);
+  EF_CUDA(cudaMemcpyAsync(Eh.data(), E, sizeof(double) * Eh.size(), cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(mean, dmean.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(projected, dP.p, sizeof(double) * (size_t)N * k, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(eigenvalues, devals.p, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaStreamSynchronize(st));
+  for (int c = 0; c < k; ++c)
+    for (int d = 0; d < D; ++d) eigenfaces[(size_t)c * D + d] = Eh[(size_t)d * k + c];   // Fortran order [D][k]
+  if (info) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, tm.a, tm.b);
+    info->sweeps = sweeps;
+    info->branch = snapshot ? 0 : 1;
+    info->off_norm = off;
+    info->gpu_ms = ms;
+  }
+  return EF_OK;
+}
+
+int ef_fit_gen2_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_t k, const ef_gen2_fit_t* out,
+                     ef_fit_info_t* info) {
+  if (!X || !out || N < 2 || D <= 0 || ldx < D || k <= 0) return EF_ERR_INVALID;
+  if (!out->mean_face || !out->scaler_mean || !out->scaler_var || !out->scaler_scale || !out->pca_mean ||
+      !out->components || !out->explained_variance || !out->explained_variance_ratio || !out->singular_values ||
+      !out->noise_variance || !out->features)
+    return EF_ERR_INVALID;
+  const bool snapshot = N <= D;
+  const int n = snapshot ? N : D;
+  if (n > 4096) return EF_ERR_UNSUPPORTED;
+  if (k > n) return EF_ERR_INVALID;      // sklearn: n_components must be <= min(n_samples, n_features)
+  cudaStream_t st = nullptr;
+  EF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
+  Timer tm;
+  EF_CUDA(cudaEventCreate(&tm.a));
+  EF_CUDA(cudaEventCreate(&tm.b));
+
+  ef::DevBuf dX, dsum, dmean, dvar, dscale, dpm, dZ, dA, dwork, devals, devecs, dVt, dS, dsign, dF;
+  const int64_t ldxd = ef::round_up(D, 16);
+  EF_TRY(dX.ensure((size_t)N * ldxd));
+  EF_TRY(dsum.ensure(sizeof(int64_t) * D));
+  EF_TRY(dmean.ensure(sizeof(double) * D));
+  EF_TRY(dvar.ensure(sizeof(double) * D));
+  EF_TRY(dscale.ensure(sizeof(double) * D));
+  EF_TRY(dpm.ensure(sizeof(double) * D));
+  EF_TRY(dZ.ensure(sizeof(double) * (size_t)N * D));
+  EF_TRY(dA.ensure(sizeof(double) * (size_t)n * n));
+  EF_TRY(dwork.ensure(ef_eigh_work_bytes(n)));
+  EF_TRY(devals.ensure(sizeof(double) * n));
+  EF_TRY(devecs.ensure(sizeof(double) * (size_t)n * n));
+  EF_TRY(dVt.ensure(sizeof(double) * (size_t)k * D));
+  EF_TRY(dS.ensure(sizeof(double) * n));
+  EF_TRY(dsign.ensure(sizeof(double) * k));
+  EF_TRY(dF.ensure(sizeof(double) * (size_t)N * k));
+  EF_CUDA(cudaMemcpy2DAsync(dX.p, ldxd, X, ldx, D, N, cudaMemcpyHostToDevice, st));
+  EF_CUDA(cudaEventRecord(tm.a, st));
+
+  // pixel mean (:366) == StandardScaler.mean_ ; var_, scale_ (:370)
+  EF_TRY(ef_colsum_u8_device(dX.as<uint8_t>(), ldxd, N, D, dsum.as<int64_t>(), st));
+  EF_LAUNCH(mean_from_colsum_kernel, (unsigned)ef::ceil_div(D, 256), 256, 0, st, dsum.as<long long>(), D, (long long)N,
+            dmean.as<double>());
+  EF_LAUNCH(scaler_var_kernel, (unsigned)ef::ceil_div(D, 128), 128, 0, st, dX.as<uint8_t>(), ldxd, (int64_t)N, D,
+            dmean.as<double>(), dvar.as<double>(), dscale.as<double>());
+  double* Z = dZ.as<double>();
+  EF_TRY(ef_standardize_u8_device(dX.as<uint8_t>(), ldxd, N, D, dmean.as<double>(), dscale.as<double>(), nullptr, Z, D, st));
+  // PCA: centre (mean_ of the standardised data is ~1e-16 but sklearn subtracts it), :373
+  EF_LAUNCH(colmean_center_kernel, (unsigned)ef::ceil_div(D, 128), 128, 0, st, Z, (int64_t)D, (int64_t)N, D,
+            dpm.as<double>());
+  if (snapshot) {
+    EF_TRY(ef_dgemm_device(N, N, D, 1.0, Z, D, 1, Z, 1, D, 0.0, dA.as<double>(), N, st));      // Zc Zc^T = U S^2 U^T
+  } else {
+    EF_TRY(ef_dgemm_device(D, D, N, 1.0, Z, 1, D, Z, D, 1, 0.0, dA.as<double>(), D, st));      // Zc^T Zc = V S^2 V^T
+  }
+  int sweeps = 0;
+  double off = 0.0;
+  const int est = ef_eigh_jacobi_device(dA.as<double>(), n, devals.as<double>(), devecs.as<double>(), dwork.p, 0, 0.0,
+                                        &sweeps, &off, st);
+  if (est != EF_OK) return est;
+  // O(n) host bookkeeping on the eigenvalues: S = sqrt(lambda), explained variance, ratio, noise variance
+  std::vector<double> lam(n);
+  EF_CUDA(cudaMemcpyAsync(lam.data(), devals.p, sizeof(double) * n, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaStreamSynchronize(st));
+  std::vector<double> S(n), ev(n);
+  double total = 0.0;
+  for (int i = 0; i < n; ++i) {
+    const double l = lam[i] > 0.0 ? lam[i] : 0.0;
+    S[i] = std::sqrt(l);
+    ev[i] = l / (double)(N - 1);
+    total += ev[i];
+  }
+  EF_CUDA(cudaMemcpyAsync(dS.p, S.data(), sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  double* Vt = dVt.as<double>();
+  if (snapshot) {
+    // Vt[c][:] = u_c^T Zc / S_c, evaluated as the normalised row (unit norm also when S_c ~ 0)
+    EF_TRY(ef_dgemm_device(k, D, N, 1.0, devecs.as<double>(), N, 1, Z, D, 1, 0.0, Vt, D, st));
+  } else {
+    EF_CUDA(cudaMemcpyAsync(Vt, devecs.p, sizeof(double) * (size_t)k * D, cudaMemcpyDeviceToDevice, st));
+  }
+  EF_LAUNCH(rownorm_flip_kernel, k, 256, 0, st, Vt, k, D, dsign.as<double>());
+  if (snapshot) {
+    EF_LAUNCH(features_kernel, (unsigned)ef::ceil_div((int64_t)N * k, 256), 256, 0, st, devecs.as<double>(), N, k,
+              dS.as<double>(), dsign.as<double>(), dF.as<double>());
+  } else {
+    // U S = Zc V
+    EF_TRY(ef_dgemm_device(N, k, D, 1.0, Z, D, 1, Vt, 1, D, 0.0, dF.as<double>(), k, st));
+  }
+  EF_CUDA(cudaEventRecord(tm.b, st));
+
+  EF_CUDA(cudaMemcpyAsync(out->mean_face, dmean.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(out->scaler_mean, dmean.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(out->scaler_var, dvar.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(out->scaler_scale, dscale.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(out->pca_mean, dpm.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(out->components, Vt, sizeof(double) * (size_t)k * D, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(out->features, dF.p, sizeof(double) * (size_t)N * k, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaStreamSynchronize(st));
+  for (int i = 0; i < k; ++i) {
+    out->explained_variance[i] = ev[i];
+    out->explained_variance_ratio[i] = total > 0.0 ? ev[i] / total : 0.0;
+    out->singular_values[i] = S[i];
+  }
+  double noise = 0.0;
+  if (k < std::min(N, D)) {
+    // sklearn: mean of the discarded explained variances (over min(N, D) - k entries)
+    const int m = std::min(N, D);
+    for (int i = k; i < m; ++i) noise += (i < n ? ev[i] : 0.0);
+    noise /= (double)(m - k);
+  }
+  *out->noise_variance = noise;
+  if (info) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, tm.a, tm.b);
+    info->sweeps = sweeps;
+    info->branch = snapshot ? 0 : 1;
+    info->off_norm = off;
+    info->gpu_ms = ms;
+  }
+  return EF_OK;
+}
+
+}  // extern "C"

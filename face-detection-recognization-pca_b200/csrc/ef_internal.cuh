@@ -1,0 +1,32 @@
+// Internal (non-ABI) entry points shared between the translation units of libeigenfaces_b200.
+#pragma once
+#include <algorithm>
+
+#include "ef_common.cuh"
+
+namespace ef {
+
+// ef_project.cu -- CUDA-core exact-integer projection
+int project_dp4a(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int32_t* acc,
+                 int ld_acc, cudaStream_t stream);
+int project_finalize(const int32_t* acc, int ld_acc, int B, int k, int kq, int S, const int32_t* col_exp,
+                     const double* bias, double* proj, int64_t ldp, const double* sumsq, double c0, double* resid2,
+                     cudaStream_t stream);
+int row_sumsq(const uint8_t* X, int64_t ldx, int B, int D, const double* qq, double* out, cudaStream_t stream);
+
+// ef_project_tc.cu -- tcgen05 kind::i8 projection (same integers as project_dp4a)
+bool project_tc_supported(int B, int D, int NC);
+int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int32_t* acc,
+               int ld_acc, cudaStream_t stream);
+
+// ef_match.cu
+// Gallery preparation: gn[j][:] = g[j][:] / |g_j| (COSINE_SK), copy + norms (COSINE_G1), copy (L2).
+int gallery_prepare(const double* g, int64_t ldg, int64_t n, int k, int metric, double* gp, int64_t ldgp, double* gnorm,
+                    cudaStream_t stream);
+size_t match_work_bytes(int B, int64_t n);
+int match(const double* p, int64_t ldp, int B, int k, const double* gp, int64_t ldgp, const double* gnorm, int64_t n,
+          int64_t index_base, int metric, double* out_score, int64_t* out_index, void* work, cudaStream_t stream);
+int label_lookup(const double* score, const int64_t* index, int B, const int32_t* labels, int metric, double threshold,
+                 int32_t* out_index32, int32_t* out_label, cudaStream_t stream);
+
+}  // namespace ef

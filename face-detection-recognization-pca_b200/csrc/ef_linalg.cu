@@ -1,0 +1,524 @@
+// Float64 / exact-integer linear-algebra building blocks of the PCA fit.
+//
+//   ef_standardize_u8_device   X -> (X - mean) / scale - shift         (useless/train.py:74, StandardScaler.transform)
+//   ef_dgemm_device            strided float64 GEMM                     (np.dot at useless/train.py:84,91,122)
+//   ef_eigh_jacobi_device      one-sided Jacobi eigensolver             (np.linalg.eigh at useless/train.py:88,103)
+//   ef_colsum_u8_device        exact column sums                        (np.mean at useless/train.py:70, train-v5.py:366)
+//   ef_gram_u8_device          exact integer Gram X X^T / X^T X         (useless/train.py:84 / :99 before centring)
+//   ef_gram_center_device      integer Gram -> centred float64 matrix
+#include <climits>
+
+#include "ef_common.cuh"
+#include "ef_internal.cuh"
+
+namespace {
+
+// ------------------------------------------------------------------------------------------ standardize
+__global__ void standardize_kernel(const uint8_t* __restrict__ X, int64_t ldx, int64_t N, int D,
+                                   const double* __restrict__ mean, const double* __restrict__ scale,
+                                   const double* __restrict__ shift, double* __restrict__ Z, int64_t ldz) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const double m = mean ? mean[d] : 0.0;
+  const double s = scale ? scale[d] : 1.0;
+  const double t = shift ? shift[d] : 0.0;
+  for (int64_t n = blockIdx.y; n < N; n += gridDim.y) {
+    double v = (double)X[n * ldx + d] - m;   // X -= mean_
+    if (scale) v = v / s;                    // X /= scale_   (IEEE division, second rounding like sklearn)
+    if (shift) v = v - t;
+    Z[n * ldz + d] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ dgemm
+// C[m][n] = alpha * sum_k A(m,k) B(k,n) + beta * C[m][n]; T x T tile per CTA, (T/16)^2 outputs per thread.
+template <int T>
+__global__ void __launch_bounds__(256)
+dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int64_t sam, int64_t sak,
+             const double* __restrict__ Bm, int64_t sbk, int64_t sbn, double beta, double* __restrict__ C,
+             int64_t ldc) {
+  constexpr int KC = 16;
+  constexpr int R = T / 16;
+  __shared__ double As[KC][T + 1];
+  __shared__ double Bs[KC][T + 1];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * T, n0 = blockIdx.x * T;
+  double acc[R][R];
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < R; ++j) acc[i][j] = 0.0;
+  const bool a_k_contig = (sak == 1);
+  const bool b_n_contig = (sbn == 1);
+
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    for (int e = tid; e < T * KC; e += 256) {
+      int mm, kk;
+      if (a_k_contig) { mm = e / KC; kk = e % KC; } else { mm = e % T; kk = e / T; }
+      const int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < M && k < K) ? A[(int64_t)m * sam + (int64_t)k * sak] : 0.0;
+    }
+    for (int e = tid; e < T * KC; e += 256) {
+      int nn, kk;
+      if (b_n_contig) { nn = e % T; kk = e / T; } else { nn = e / KC; kk = e % KC; }
+      const int n = n0 + nn, k = k0 + kk;
+      Bs[kk][nn] = (n < N && k < K) ? Bm[(int64_t)k * sbk + (int64_t)n * sbn] : 0.0;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      double av[R], bv[R];
+#pragma unroll
+      for (int i = 0; i < R; ++i) av[i] = As[kk][ty * R + i];
+#pragma unroll
+      for (int j = 0; j < R; ++j) bv[j] = Bs[kk][tx * R + j];
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int m = m0 + ty * R + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < R; ++j) {
+      const int n = n0 + tx * R + j;
+      if (n >= N) continue;
+      double v = alpha * acc[i][j];
+      if (beta != 0.0) v += beta * C[(int64_t)m * ldc + n];
+      C[(int64_t)m * ldc + n] = v;
+    }
+  }
+}
+
+// ----------------------------------------------------------------------------------------------- Jacobi
+// One-sided (Hestenes) Jacobi on the symmetric matrix A: the rows of Bt start as the columns of A, the rows of
+// Vt as the identity; plane rotations applied to row pairs of both drive the rows of Bt = (A V)^T to mutual
+// orthogonality, at which point the rows of Vt are the eigenvectors and lambda_i = v_i . b_i.
+// All n/2 disjoint pairs of a round (round-robin tournament) are rotated concurrently, one CTA per pair; a
+// grid-wide barrier separates rounds (cooperative launch guarantees co-residency).  The matrices stay L2 resident
+// (n <= 4096: 2 x 128 MB worst case, the shipped sizes 178..590 are 0.5-5.6 MB) and are accessed with .cg so that
+// no stale L1 line is read after another SM rotated the row.
+struct JacobiCtl {
+  unsigned int barrier;        // monotonically increasing arrival counter
+  unsigned int abort_flag;     // set when a spin timed out
+  unsigned long long off_bits; // max |cos| of the current sweep (bits of a non-negative double)
+  int sweeps;
+  int converged;
+  double off_final;
+};
+
+__device__ __forceinline__ bool grid_barrier(JacobiCtl* ctl, unsigned int target) {
+  __syncthreads();
+  bool ok = true;
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(&ctl->barrier, 1u);
+    long long spins = 0;
+    while (true) {
+      unsigned int v;
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(&ctl->barrier));
+      if (v >= target) break;
+      if (++spins > (1ll << 24)) {
+        unsigned int a;
+        asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(a) : "l"(&ctl->abort_flag));
+        if (a || spins > (1ll << 28)) { atomicExch(&ctl->abort_flag, 1u); ok = false; break; }
+      }
+    }
+    __threadfence();
+  }
+  ok = __syncthreads_and(ok);
+  return ok;
+}
+
+__device__ __forceinline__ double block_sum3(double a, double b, double c, double* red, double& ob, double& oc) {
+  // reduces three values across the CTA; result broadcast to all threads
+  a = ef::warp_sum(a);
+  b = ef::warp_sum(b);
+  c = ef::warp_sum(c);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+  __syncthreads();
+  if (lane == 0) { red[warp * 3 + 0] = a; red[warp * 3 + 1] = b; red[warp * 3 + 2] = c; }
+  __syncthreads();
+  double sa = 0.0, sb = 0.0, sc = 0.0;
+  for (int w = 0; w < nw; ++w) { sa += red[w * 3 + 0]; sb += red[w * 3 + 1]; sc += red[w * 3 + 2]; }
+  ob = sb;
+  oc = sc;
+  return sa;
+}
+
+__global__ void __launch_bounds__(128)
+jacobi_kernel(double* __restrict__ Bt, double* __restrict__ Vt, int n, int ld, JacobiCtl* ctl, int max_sweeps,
+              double tol) {
+  __shared__ double red[3 * 4];
+  const int np = (n + 1) / 2;
+  const int players = 2 * np;
+  const int tid = threadIdx.x;
+  unsigned int target = 0;
+  const double rot_tol = tol * 0.125;
+
+  for (int sweep = 0; sweep < max_sweeps; ++sweep) {
+    double local_off = 0.0;
+    for (int round = 0; round < players - 1; ++round) {
+      for (int pair = blockIdx.x; pair < np; pair += gridDim.x) {
+        int a, b;
+        if (pair == 0) { a = players - 1; b = round; }
+        else { a = (round + pair) % (players - 1); b = (round - pair + players - 1) % (players - 1); }
+        if (a >= n || b >= n) continue;   // the dummy player of an odd n
+        const int p = min(a, b), q = max(a, b);
+        double* bp = Bt + (int64_t)p * ld;
+        double* bq = Bt + (int64_t)q * ld;
+        double alpha = 0.0, beta = 0.0, gamma = 0.0;
+        for (int i = tid; i < n; i += blockDim.x) {
+          const double x = __ldcg(bp + i), y = __ldcg(bq + i);
+          alpha = fma(x, x, alpha);
+          beta = fma(y, y, beta);
+          gamma = fma(x, y, gamma);
+        }
+        alpha = block_sum3(alpha, beta, gamma, red, beta, gamma);
+        const double denom = sqrt(alpha) * sqrt(beta);
+        if (!(denom > 0.0)) continue;
+        const double off = fabs(gamma) / denom;
+        local_off = fmax(local_off, off);
+        if (off <= rot_tol) continue;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = copysign(1.0, zeta) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + t * t);
+        const double s = c * t;
+        double* vp = Vt + (int64_t)p * ld;
+        double* vq = Vt + (int64_t)q * ld;
+        for (int i = tid; i < n; i += blockDim.x) {
+          const double x = __ldcg(bp + i), y = __ldcg(bq + i);
+          __stcg(bp + i, c * x - s * y);
+          __stcg(bq + i, s * x + c * y);
+          const double u = __ldcg(vp + i), v = __ldcg(vq + i);
+          __stcg(vp + i, c * u - s * v);
+          __stcg(vq + i, s * u + c * v);
+        }
+      }
+      target += gridDim.x;
+      if (!grid_barrier(ctl, target)) return;
+    }
+    // sweep-level convergence test (same decision in every CTA)
+    if (tid == 0) atomicMax(&ctl->off_bits, (unsigned long long)__double_as_longlong(local_off));
+    target += gridDim.x;
+    if (!grid_barrier(ctl, target)) return;
+    unsigned long long bits;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(bits) : "l"(&ctl->off_bits));
+    const double off = __longlong_as_double((long long)bits);
+    target += gridDim.x;
+    if (!grid_barrier(ctl, target)) return;   // everyone has read off_bits before it is reset
+    if (blockIdx.x == 0 && tid == 0) {
+      ctl->sweeps = sweep + 1;
+      ctl->off_final = off;
+      ctl->converged = off <= tol;
+      if (off > tol) atomicExch(&ctl->off_bits, 0ull);
+    }
+    if (off <= tol) return;
+    target += gridDim.x;
+    if (!grid_barrier(ctl, target)) return;   // reset visible before the next sweep's atomicMax
+  }
+}
+
+__global__ void jacobi_init_kernel(double* __restrict__ Vt, int n, int ld, JacobiCtl* ctl) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e == 0) {
+    ctl->barrier = 0;
+    ctl->abort_flag = 0;
+    ctl->off_bits = 0;
+    ctl->sweeps = 0;
+    ctl->converged = 0;
+    ctl->off_final = 0.0;
+  }
+  if (e >= (int64_t)n * ld) return;
+  const int r = (int)(e / ld), c = (int)(e % ld);
+  Vt[e] = (r == c) ? 1.0 : 0.0;
+}
+
+// lambda_i = v_i . b_i ; one warp per row
+__global__ void jacobi_rayleigh_kernel(const double* __restrict__ Bt, const double* __restrict__ Vt, int n, int ld,
+                                       double* __restrict__ lam) {
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  double s = 0.0;
+  for (int i = lane; i < n; i += 32) s = fma(Vt[(int64_t)row * ld + i], Bt[(int64_t)row * ld + i], s);
+  s = ef::warp_sum(s);
+  if (lane == 0) lam[row] = s;
+}
+
+// rank by counting (descending, ties -> lower original index first) and scatter rows
+__global__ void jacobi_sort_kernel(const double* __restrict__ lam, const double* __restrict__ Vt, int n, int ld,
+                                   double* __restrict__ evals, double* __restrict__ evecs) {
+  const int row = blockIdx.x;
+  const double li = lam[row];
+  __shared__ int rank_s;
+  if (threadIdx.x == 0) rank_s = 0;
+  __syncthreads();
+  int cnt = 0;
+  for (int j = threadIdx.x; j < n; j += blockDim.x) {
+    const double lj = lam[j];
+    if (lj > li || (lj == li && j < row)) ++cnt;
+  }
+  atomicAdd(&rank_s, cnt);
+  __syncthreads();
+  const int r = rank_s;
+  if (threadIdx.x == 0) evals[r] = li;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) evecs[(int64_t)r * n + i] = Vt[(int64_t)row * ld + i];
+}
+
+// ------------------------------------------------------------------------------------- integer reductions
+__global__ void colsum_u8_kernel(const uint8_t* __restrict__ X, int64_t ldx, int64_t N, int D,
+                                 unsigned long long* __restrict__ out) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  unsigned long long s = 0;
+  for (int64_t n = blockIdx.y; n < N; n += gridDim.y) s += X[n * ldx + d];
+  if (gridDim.y == 1) out[d] = s; else atomicAdd(out + d, s);
+}
+
+// Exact integer Gram, 64 x 64 outputs per CTA, 4 x 4 per thread, dp4a on K-packed words.
+// side 0: rows of X are the vectors (K = pixels, contiguous); side 1: columns of X are the vectors (K = rows,
+// bytes transposed through shared memory).
+__global__ void __launch_bounds__(256)
+gram_u8_kernel(const uint8_t* __restrict__ X, int64_t ldx, int64_t N, int D, int d0, int d1, int side, int n_out,
+               int64_t k_per_split, unsigned long long* __restrict__ G) {
+  constexpr int T = 64, KB = 64, LDS = KB + 16;
+  __shared__ __align__(16) uint8_t As[T][LDS];
+  __shared__ __align__(16) uint8_t Bs[T][LDS];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int i0 = blockIdx.y * T, j0 = blockIdx.x * T;
+  const int64_t K = side == 0 ? (int64_t)(d1 - d0) : N;
+  const int64_t kb = (int64_t)blockIdx.z * k_per_split;
+  const int64_t ke = min(K, kb + k_per_split);
+  unsigned long long acc64[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc64[i][j] = 0;
+
+  for (int64_t kc = kb; kc < ke; kc += 16384) {   // u32 partial sums stay below 2^32: 16384 * 255^2 < 2^31
+    unsigned acc[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[i][j] = 0;
+    const int64_t kce = min(ke, kc + 16384);
+    for (int64_t k0 = kc; k0 < kce; k0 += KB) {
+      __syncthreads();
+      for (int e = tid; e < T * KB; e += 256) {
+        int v, kk;
+        if (side == 0) { v = e / KB; kk = e % KB; } else { v = e % T; kk = e / T; }
+        const int64_t k = k0 + kk;
+        uint8_t a = 0, b = 0;
+        if (k < kce) {
+          if (side == 0) {
+            if (i0 + v < n_out) a = X[(int64_t)(i0 + v) * ldx + d0 + k];
+            if (j0 + v < n_out) b = X[(int64_t)(j0 + v) * ldx + d0 + k];
+          } else {
+            if (i0 + v < n_out) a = X[k * ldx + i0 + v];
+            if (j0 + v < n_out) b = X[k * ldx + j0 + v];
+          }
+        }
+        As[v][kk] = a;
+        Bs[v][kk] = b;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kw = 0; kw < KB / 4; ++kw) {
+        unsigned av[4], bv[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) av[i] = *reinterpret_cast<const unsigned*>(&As[ty * 4 + i][kw * 4]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) bv[j] = *reinterpret_cast<const unsigned*>(&Bs[tx + 16 * j][kw * 4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = __dp4a(av[i], bv[j], acc[i][j]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc64[i][j] += acc[i][j];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = i0 + ty * 4 + i;
+    if (r >= n_out) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = j0 + tx + 16 * j;
+      if (c < n_out) atomicAdd(G + (int64_t)r * n_out + c, acc64[i][j]);
+    }
+  }
+}
+
+__global__ void gram_rowsum_kernel(const long long* __restrict__ G, int n, long long* __restrict__ rowsum,
+                                   unsigned long long* __restrict__ grand) {
+  // one warp per row: exact int64 row sums (values < 2^63 for every supported shape)
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n) return;
+  long long s = 0;
+  for (int j = lane; j < n; j += 32) s += G[(int64_t)row * n + j];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) {
+    rowsum[row] = s;
+    atomicAdd(grand, (unsigned long long)s);
+  }
+}
+
+// Centring with an EXACT integer numerator and a single rounding:
+//  side 0 (double centring of X X^T):  n^2 Gc[i][j] = n^2 G[i][j] - n (r_i + r_j) + g,  r = row sums, g = grand sum
+//  side 1 (X^T X with column sums s): N Gc[a][b]   = N G[a][b] - s_a s_b
+__global__ void gram_center_kernel(const long long* __restrict__ G, int n, int side,
+                                   const long long* __restrict__ rowsum, const long long* __restrict__ grand_sum,
+                                   const long long* __restrict__ colsum, long long Nrows, double alpha,
+                                   double* __restrict__ C) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)n * n) return;
+  const int i = (int)(e / n), j = (int)(e % n);
+  double v;
+  if (side == 0) {
+    const long long nn = (long long)n;
+    const long long num = nn * nn * G[e] - nn * (rowsum[i] + rowsum[j]) + *grand_sum;
+    v = (double)num / ((double)nn * (double)nn);
+  } else {
+    const long long num = Nrows * G[e] - colsum[i] * colsum[j];
+    v = (double)num / (double)Nrows;
+  }
+  C[e] = v * alpha;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ef_standardize_u8_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, const double* mean,
+                             const double* scale, const double* shift, double* Z, int64_t ldz, ef_stream_t stream) {
+  if (!X || !Z || N < 0 || D <= 0 || ldx < D || ldz < D) return EF_ERR_INVALID;
+  if (N == 0) return EF_OK;
+  dim3 grid((unsigned)ef::ceil_div(D, 256), (unsigned)std::min<int64_t>(N, 64));
+  EF_LAUNCH(standardize_kernel, grid, 256, 0, ef::as_stream(stream), X, ldx, N, D, mean, scale, shift, Z, ldz);
+  return EF_OK;
+}
+
+int ef_dgemm_device(int32_t M, int32_t N, int32_t K, double alpha, const double* A, int64_t sam, int64_t sak,
+                    const double* B, int64_t sbk, int64_t sbn, double beta, double* C, int64_t ldc,
+                    ef_stream_t stream) {
+  if (!A || !B || !C || M < 0 || N < 0 || K < 0 || ldc < N) return EF_ERR_INVALID;
+  if (M == 0 || N == 0) return EF_OK;
+  cudaStream_t st = ef::as_stream(stream);
+  const int64_t tiles64 = ef::ceil_div(M, 64) * ef::ceil_div(N, 64);
+  if (tiles64 >= ef::sm_count()) {
+    dim3 grid((unsigned)ef::ceil_div(N, 64), (unsigned)ef::ceil_div(M, 64));
+    EF_LAUNCH(dgemm_kernel<64>, grid, 256, 0, st, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc);
+  } else {
+    dim3 grid((unsigned)ef::ceil_div(N, 32), (unsigned)ef::ceil_div(M, 32));
+    EF_LAUNCH(dgemm_kernel<32>, grid, 256, 0, st, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc);
+  }
+  return EF_OK;
+}
+
+size_t ef_eigh_work_bytes(int32_t n) {
+  if (n <= 0) return 0;
+  // Vt [n][n] + lambda [n] + control block
+  return sizeof(double) * ((size_t)n * n + (size_t)n) + 256;
+}
+
+int ef_eigh_jacobi_device(double* A, int32_t n, double* evals, double* evecs, void* work, int32_t max_sweeps,
+                          double tol, int32_t* sweeps_used, double* off_norm, ef_stream_t stream) {
+  if (!A || !evals || !evecs || !work || n <= 0) return EF_ERR_INVALID;
+  if (n > 4096) return EF_ERR_UNSUPPORTED;
+  cudaStream_t st = ef::as_stream(stream);
+  if (max_sweeps <= 0) max_sweeps = 40;
+  if (!(tol > 0.0)) tol = 1e-14;
+  double* Vt = reinterpret_cast<double*>(work);
+  double* lam = Vt + (size_t)n * n;
+  JacobiCtl* ctl = reinterpret_cast<JacobiCtl*>(reinterpret_cast<char*>(work) +
+                                                ef::round_up(sizeof(double) * ((size_t)n * n + n), 128));
+  EF_LAUNCH(jacobi_init_kernel, (unsigned)ef::ceil_div((int64_t)n * n, 256), 256, 0, st, Vt, n, n, ctl);
+  if (n > 1) {
+    int per_sm = 0;
+    EF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_kernel, 128, 0));
+    if (per_sm < 1) return EF_ERR_UNSUPPORTED;
+    const int np = (n + 1) / 2;
+    int grid = std::min(np, per_sm * ef::sm_count());
+    int ld = n;
+    void* args[] = {&A, &Vt, &n, &ld, &ctl, &max_sweeps, &tol};
+    EF_CUDA(cudaLaunchCooperativeKernel((const void*)jacobi_kernel, dim3(grid), dim3(128), args, 0, st));
+    ef::g_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+  EF_LAUNCH(jacobi_rayleigh_kernel, (unsigned)ef::ceil_div((int64_t)n * 32, 256), 256, 0, st, A, Vt, n, n, lam);
+  EF_LAUNCH(jacobi_sort_kernel, n, 128, 0, st, lam, Vt, n, n, evals, evecs);
+  if (sweeps_used || off_norm) {
+    JacobiCtl h;
+    EF_CUDA(cudaMemcpyAsync(&h, ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+    EF_CUDA(cudaStreamSynchronize(st));
+    if (sweeps_used) *sweeps_used = h.sweeps;
+    if (off_norm) *off_norm = h.off_final;
+    if (h.abort_flag) return EF_ERR_CUDA;
+    if (n > 1 && !h.converged) return EF_ERR_NOCONVERGE;
+  }
+  return EF_OK;
+}
+
+int ef_colsum_u8_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int64_t* out, ef_stream_t stream) {
+  if (!X || !out || N < 0 || D <= 0 || ldx < D) return EF_ERR_INVALID;
+  cudaStream_t st = ef::as_stream(stream);
+  EF_CUDA(cudaMemsetAsync(out, 0, sizeof(int64_t) * (size_t)D, st));
+  if (N == 0) return EF_OK;
+  dim3 grid((unsigned)ef::ceil_div(D, 128), (unsigned)std::min<int64_t>(ef::ceil_div(N, 64), 64));
+  EF_LAUNCH(colsum_u8_kernel, grid, 128, 0, st, X, ldx, N, D, reinterpret_cast<unsigned long long*>(out));
+  return EF_OK;
+}
+
+int ef_gram_u8_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int32_t d0, int32_t d1, int32_t side,
+                      int64_t* G, ef_stream_t stream) {
+  if (!X || !G || N < 0 || D <= 0 || ldx < D || d0 < 0 || d1 > D || d0 > d1 || (side != 0 && side != 1))
+    return EF_ERR_INVALID;
+  const int64_t n_out = side == 0 ? N : D;
+  const int64_t K = side == 0 ? (d1 - d0) : N;
+  if (n_out == 0 || K == 0) return EF_OK;
+  if (n_out > 65536) return EF_ERR_UNSUPPORTED;
+  const int64_t tiles = ef::ceil_div(n_out, 64) * ef::ceil_div(n_out, 64);
+  int64_t splits = ef::ceil_div(2 * (int64_t)ef::sm_count(), tiles);
+  const int64_t max_splits = ef::ceil_div(K, 256);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int64_t per = ef::round_up(ef::ceil_div(K, splits), 64);
+  splits = ef::ceil_div(K, per);
+  dim3 grid((unsigned)ef::ceil_div(n_out, 64), (unsigned)ef::ceil_div(n_out, 64), (unsigned)splits);
+  EF_LAUNCH(gram_u8_kernel, grid, 256, 0, ef::as_stream(stream), X, ldx, N, D, d0, d1, side, (int)n_out, per,
+            reinterpret_cast<unsigned long long*>(G));
+  return EF_OK;
+}
+
+int ef_gram_center_device(const int64_t* G, int32_t n, int32_t side, const int64_t* colsum, int64_t N, double alpha,
+                          double* C, void* work, ef_stream_t stream) {
+  if (!G || !C || n <= 0 || (side != 0 && side != 1)) return EF_ERR_INVALID;
+  if (side == 1 && (!colsum || N <= 0)) return EF_ERR_INVALID;
+  if (side == 0 && !work) return EF_ERR_INVALID;
+  cudaStream_t st = ef::as_stream(stream);
+  long long* rowsum = reinterpret_cast<long long*>(work);
+  long long* grand = rowsum ? rowsum + n : nullptr;
+  if (side == 0) {
+    EF_CUDA(cudaMemsetAsync(grand, 0, sizeof(long long), st));
+    EF_LAUNCH(gram_rowsum_kernel, (unsigned)ef::ceil_div((int64_t)n * 32, 256), 256, 0, st,
+              reinterpret_cast<const long long*>(G), n, rowsum, reinterpret_cast<unsigned long long*>(grand));
+  }
+  EF_LAUNCH(gram_center_kernel, (unsigned)ef::ceil_div((int64_t)n * n, 256), 256, 0, st,
+            reinterpret_cast<const long long*>(G), n, side, rowsum, grand, reinterpret_cast<const long long*>(colsum),
+            (long long)N, alpha, C);
+  return EF_OK;
+}
+
+size_t ef_gram_center_work_bytes(int32_t n) { return n > 0 ? sizeof(int64_t) * ((size_t)n + 2) : 0; }
+
+}  // extern "C"

@@ -1,0 +1,383 @@
+// Recognition model handle: device-resident sliced basis + prepared gallery, and the batch recognition entry
+// points (host buffers and device buffers).
+//
+// ef_model_create does the one-time model preparation that the reference redoes per crop
+// (scan-template-v4.py:265-266 re-validates and re-centres on every call; sklearn cosine_similarity re-normalises
+// the whole gallery on every call, :274):
+//   W_eff[d][c] = basis[d][c] / scale[d]            effective projection matrix
+//   t[d]        = mean[d] + pca_mean[d] * scale[d]  so that features = (x - t) . W_eff
+//   digit planes of W_eff (see ef_project.cu), bias[c] = t . W~[:,c] in float64
+//   residual column u[d] = t[d] / scale[d]^2, c0 = sum t^2 / scale^2, qq[d] = 1 / scale[d]^2
+#include <cmath>
+#include <vector>
+
+#include "ef_common.cuh"
+#include "ef_internal.cuh"
+
+struct ef_model {
+  int D = 0, k = 0, kq = 0, S = 0, NC = 0, metric = 0;
+  int64_t n_gallery = 0;
+  int64_t ldw = 0;
+  bool with_residual = false, has_scale = false;
+  double c0 = 0.0;
+  ef::DevBuf wq, col_exp, bias, qq, gp, gnorm, labels;
+  // workspaces (sized by reserve)
+  int reserved = 0;
+  ef::DevBuf acc, proj, sumsq, score, index64, match_work;
+  // host-path staging
+  int host_reserved = 0;
+  ef::DevBuf x_dev, resid_dev, index32_dev, label_dev, frames_dev, boxes_dev, bad_dev;
+  int64_t x_ld = 0;
+  cudaStream_t stream = nullptr;   // owned, used by the host entry points
+  int ld_acc = 0;
+  bool use_tc = true;
+  // optional per-kernel timing (bench roofline): event pairs around the projection kernel of every call
+  bool timing = false;
+  std::vector<cudaEvent_t> ev_a, ev_b;
+  bool last_used_tc = false;
+};
+
+namespace {
+
+int check_desc(const ef_model_desc_t* d) {
+  if (!d || !d->basis || !d->mean || !d->gallery) return EF_ERR_INVALID;
+  if (d->D <= 0 || d->k <= 0 || d->n_gallery <= 0 || d->gallery_ld < d->k) return EF_ERR_INVALID;
+  if (d->metric < EF_METRIC_COSINE_SK || d->metric > EF_METRIC_L2) return EF_ERR_INVALID;
+  if (d->n_slices < 0 || d->n_slices > 8) return EF_ERR_INVALID;
+  // int32 accumulators: D * 255 * 64 must stay below 2^31
+  if ((int64_t)d->D * 255 * 64 >= (1ll << 31)) return EF_ERR_UNSUPPORTED;
+  return EF_OK;
+}
+
+// Signed 7-bit digit planes of one column, exact in float64: r_0 = w / 2^e in [-1, 1];
+// q_s = rint(r_s * 2^(7s+6)), r_{s+1} = r_s - q_s * 2^-(7s+6), |r_{s+1}| <= 2^-(7s+7).
+void slice_column(const std::vector<double>& w, int D, int S, int e, int8_t* planes, int64_t plane_stride,
+                  std::vector<double>& wq_value) {
+  for (int d = 0; d < D; ++d) {
+    double r = std::ldexp(w[d], -e);
+    double acc = 0.0;
+    for (int s = 0; s < S; ++s) {
+      const int sh = 7 * s + 6;
+      double q = std::nearbyint(std::ldexp(r, sh));
+      if (q > 64.0) q = 64.0;
+      if (q < -64.0) q = -64.0;
+      planes[(int64_t)s * plane_stride + d] = (int8_t)q;
+      const double part = std::ldexp(q, -sh);
+      r -= part;
+      acc += part;
+    }
+    wq_value[d] = std::ldexp(acc, e);   // W~[d]: exact (the partial sums nest inside 53 bits for S <= 7, and
+                                        // differ from the true sum by < 2^-53 relative for S = 8)
+  }
+}
+
+int upload(ef::DevBuf& buf, const void* src, size_t bytes) {
+  EF_TRY(buf.ensure(bytes ? bytes : 16));
+  if (bytes) EF_CUDA(cudaMemcpy(buf.p, src, bytes, cudaMemcpyHostToDevice));
+  return EF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
+  if (!out) return EF_ERR_INVALID;
+  *out = nullptr;
+  EF_TRY(check_desc(desc));
+  int dev_count = 0;
+  EF_CUDA(cudaGetDeviceCount(&dev_count));
+  if (dev_count <= 0) return EF_ERR_CUDA;
+
+  ef_model* m = new (std::nothrow) ef_model();
+  if (!m) return EF_ERR_NOMEM;
+  const int D = desc->D, k = desc->k;
+  m->D = D;
+  m->k = k;
+  m->S = desc->n_slices == 0 ? 8 : desc->n_slices;
+  m->with_residual = desc->with_residual != 0;
+  m->has_scale = desc->scale != nullptr;
+  m->kq = k + (m->with_residual ? 1 : 0);
+  m->NC = m->S * m->kq;
+  m->metric = desc->metric;
+  m->n_gallery = desc->n_gallery;
+  m->ldw = ef::round_up(D, 128);
+  const int nc_pad = (int)ef::round_up(m->NC, 16);
+  m->ld_acc = nc_pad;
+
+  // ---- host-side preparation (float64, exact digit extraction)
+  std::vector<double> t(D), inv_s(D, 1.0);
+  for (int d = 0; d < D; ++d) {
+    const double s = desc->scale ? desc->scale[d] : 1.0;
+    const double pm = desc->pca_mean ? desc->pca_mean[d] : 0.0;
+    t[d] = desc->mean[d] + pm * s;
+  }
+  std::vector<int8_t> wq((size_t)nc_pad * m->ldw, 0);
+  std::vector<int32_t> col_exp(m->kq, 0);
+  std::vector<double> bias(m->kq, 0.0), col(D), colq(D);
+  for (int c = 0; c < m->kq; ++c) {
+    if (c < k) {
+      for (int d = 0; d < D; ++d) {
+        const double b = desc->basis[(int64_t)d * desc->basis_stride_d + (int64_t)c * desc->basis_stride_k];
+        col[d] = desc->scale ? b / desc->scale[d] : b;
+      }
+    } else {
+      for (int d = 0; d < D; ++d) {
+        const double s = desc->scale ? desc->scale[d] : 1.0;
+        col[d] = desc->scale ? t[d] / (s * s) : t[d];
+      }
+    }
+    double mx = 0.0;
+    for (int d = 0; d < D; ++d) {
+      if (!std::isfinite(col[d])) { delete m; return EF_ERR_INVALID; }
+      mx = std::fmax(mx, std::fabs(col[d]));
+    }
+    int e = 0;
+    if (mx > 0.0) {
+      std::frexp(mx, &e);            // mx = f * 2^e, f in [0.5, 1)  ->  |col| / 2^e < 1
+    }
+    col_exp[c] = e;
+    // plane s of column c is row (s * kq + c) of wq
+    slice_column(col, D, m->S, e, wq.data() + (int64_t)c * m->ldw, (int64_t)m->kq * m->ldw, colq);
+    if (c < k) {
+      long double b = 0.0L;
+      for (int d = 0; d < D; ++d) b += (long double)t[d] * (long double)colq[d];
+      bias[c] = (double)b;
+    }
+  }
+  if (m->with_residual) {
+    long double c0 = 0.0L;
+    for (int d = 0; d < D; ++d) {
+      const double s = desc->scale ? desc->scale[d] : 1.0;
+      c0 += (long double)t[d] * (long double)t[d] / ((long double)s * (long double)s);
+    }
+    m->c0 = (double)c0;
+    if (desc->scale) {
+      std::vector<double> qq(D);
+      for (int d = 0; d < D; ++d) qq[d] = 1.0 / (desc->scale[d] * desc->scale[d]);
+      int st = upload(m->qq, qq.data(), sizeof(double) * D);
+      if (st != EF_OK) { delete m; return st; }
+    }
+  }
+
+  int st = upload(m->wq, wq.data(), wq.size());
+  if (st == EF_OK) st = upload(m->col_exp, col_exp.data(), sizeof(int32_t) * col_exp.size());
+  if (st == EF_OK) st = upload(m->bias, bias.data(), sizeof(double) * bias.size());
+  if (st == EF_OK && desc->labels) st = upload(m->labels, desc->labels, sizeof(int32_t) * (size_t)desc->n_gallery);
+  // gallery: upload raw (compacted to ld = k), prepare on the device
+  ef::DevBuf raw;
+  if (st == EF_OK) {
+    std::vector<double> g((size_t)desc->n_gallery * k);
+    for (int64_t j = 0; j < desc->n_gallery; ++j)
+      memcpy(&g[(size_t)j * k], desc->gallery + j * desc->gallery_ld, sizeof(double) * k);
+    st = upload(raw, g.data(), sizeof(double) * g.size());
+  }
+  if (st == EF_OK) st = m->gp.ensure(sizeof(double) * (size_t)desc->n_gallery * k);
+  if (st == EF_OK) st = m->gnorm.ensure(sizeof(double) * (size_t)desc->n_gallery);
+  if (st == EF_OK) {
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { ef::set_error_detail("cudaStreamCreate", e); st = EF_ERR_CUDA; }
+  }
+  if (st == EF_OK)
+    st = ef::gallery_prepare(raw.as<double>(), k, desc->n_gallery, k, m->metric, m->gp.as<double>(), k,
+                             m->gnorm.as<double>(), m->stream);
+  if (st == EF_OK) {
+    cudaError_t e = cudaStreamSynchronize(m->stream);
+    if (e != cudaSuccess) { ef::set_error_detail("gallery_prepare", e); st = EF_ERR_CUDA; }
+  }
+  if (st != EF_OK) { ef_model_destroy(m); return st; }
+  *out = m;
+  return EF_OK;
+}
+
+void ef_model_destroy(ef_model_t* m) {
+  if (!m) return;
+  if (m->stream) cudaStreamDestroy(m->stream);
+  for (cudaEvent_t e : m->ev_a) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->ev_b) cudaEventDestroy(e);
+  delete m;
+}
+
+int ef_model_dims(const ef_model_t* m, int32_t* D, int32_t* k, int32_t* n_gallery, int32_t* n_slices) {
+  if (!m) return EF_ERR_INVALID;
+  if (D) *D = m->D;
+  if (k) *k = m->k;
+  if (n_gallery) *n_gallery = (int32_t)m->n_gallery;
+  if (n_slices) *n_slices = m->S;
+  return EF_OK;
+}
+
+int ef_model_set_tensor_cores(ef_model_t* m, int32_t enable) {
+  if (!m) return EF_ERR_INVALID;
+  m->use_tc = enable != 0;
+  return EF_OK;
+}
+
+int ef_model_kernel_timing(ef_model_t* m, int32_t enable) {
+  if (!m) return EF_ERR_INVALID;
+  for (cudaEvent_t e : m->ev_a) cudaEventDestroy(e);
+  for (cudaEvent_t e : m->ev_b) cudaEventDestroy(e);
+  m->ev_a.clear();
+  m->ev_b.clear();
+  m->timing = enable != 0;
+  return EF_OK;
+}
+
+int ef_model_kernel_timing_read(ef_model_t* m, int32_t* n_calls, double* project_ms_mean, int32_t* used_tensor_cores) {
+  if (!m || !n_calls || !project_ms_mean) return EF_ERR_INVALID;
+  double tot = 0.0;
+  int n = 0;
+  for (size_t i = 0; i < m->ev_a.size(); ++i) {
+    float ms = 0.f;
+    EF_CUDA(cudaEventSynchronize(m->ev_b[i]));
+    EF_CUDA(cudaEventElapsedTime(&ms, m->ev_a[i], m->ev_b[i]));
+    tot += ms;
+    ++n;
+  }
+  *n_calls = n;
+  *project_ms_mean = n ? tot / n : 0.0;
+  if (used_tensor_cores) *used_tensor_cores = m->last_used_tc ? 1 : 0;
+  return EF_OK;
+}
+
+int ef_model_reserve(ef_model_t* m, int32_t max_batch) {
+  if (!m || max_batch <= 0) return EF_ERR_INVALID;
+  if (max_batch <= m->reserved) return EF_OK;
+  const size_t B = (size_t)max_batch;
+  EF_TRY(m->acc.ensure(sizeof(int32_t) * B * m->ld_acc));
+  EF_TRY(m->proj.ensure(sizeof(double) * B * m->k));
+  EF_TRY(m->sumsq.ensure(sizeof(double) * B));
+  EF_TRY(m->score.ensure(sizeof(double) * B));
+  EF_TRY(m->index64.ensure(sizeof(int64_t) * B));
+  EF_TRY(m->match_work.ensure(ef::match_work_bytes(max_batch, m->n_gallery) + 16));
+  m->reserved = max_batch;
+  return EF_OK;
+}
+
+int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
+                              const ef_result_t* out, ef_stream_t stream) {
+  if (!m || !x || !out || B < 0 || ldx < m->D) return EF_ERR_INVALID;
+  if ((ldx & 15) || (reinterpret_cast<uintptr_t>(x) & 15)) return EF_ERR_INVALID;
+  if (out->resid2 && !m->with_residual) return EF_ERR_INVALID;
+  if (B == 0) return EF_OK;
+  EF_TRY(ef_model_reserve(m, B));
+  cudaStream_t st = ef::as_stream(stream);
+  int32_t* acc = m->acc.as<int32_t>();
+  // 1. exact integer digit-plane dot products
+  cudaEvent_t ea = nullptr, eb = nullptr;
+  if (m->timing && m->ev_a.size() < 4096) {
+    EF_CUDA(cudaEventCreate(&ea));
+    EF_CUDA(cudaEventCreate(&eb));
+    m->ev_a.push_back(ea);
+    m->ev_b.push_back(eb);
+    EF_CUDA(cudaEventRecord(ea, st));
+  }
+  m->last_used_tc = m->use_tc && ef::project_tc_supported(B, m->D, m->NC);
+  if (m->last_used_tc) {
+    EF_TRY(ef::project_tc(x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, acc, m->ld_acc, st));
+  } else {
+    EF_TRY(ef::project_dp4a(x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, acc, m->ld_acc, st));
+  }
+  if (eb) EF_CUDA(cudaEventRecord(eb, st));
+  // 2. residual ingredients
+  const bool want_resid = out->resid2 != nullptr;
+  if (want_resid) EF_TRY(ef::row_sumsq(x, ldx, B, m->D, m->has_scale ? m->qq.as<double>() : nullptr,
+                                       m->sumsq.as<double>(), st));
+  // 3. planes -> float64 features (+ residual)
+  double* proj = out->proj ? out->proj : m->proj.as<double>();
+  EF_TRY(ef::project_finalize(acc, m->ld_acc, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(), m->bias.as<double>(),
+                              proj, m->k, m->sumsq.as<double>(), m->c0, want_resid ? out->resid2 : nullptr, st));
+  // 4. nearest gallery row
+  if (!out->score || !out->index) return EF_ERR_INVALID;
+  EF_TRY(ef::match(proj, m->k, B, m->k, m->gp.as<double>(), m->k, m->gnorm.as<double>(), m->n_gallery, 0, m->metric,
+                   out->score, m->index64.as<int64_t>(), m->match_work.p, st));
+  // 5. threshold + label
+  EF_TRY(ef::label_lookup(out->score, m->index64.as<int64_t>(), B, m->labels.p ? m->labels.as<int32_t>() : nullptr,
+                          m->metric, threshold, out->index, out->label, st));
+  return EF_OK;
+}
+
+static int host_reserve(ef_model_t* m, int32_t B) {
+  EF_TRY(ef_model_reserve(m, B));
+  if (B <= m->host_reserved) return EF_OK;
+  m->x_ld = ef::round_up(m->D, 128);
+  EF_TRY(m->x_dev.ensure((size_t)B * m->x_ld));
+  EF_TRY(m->resid_dev.ensure(sizeof(double) * (size_t)B));
+  EF_TRY(m->index32_dev.ensure(sizeof(int32_t) * (size_t)B));
+  EF_TRY(m->label_dev.ensure(sizeof(int32_t) * (size_t)B));
+  EF_TRY(m->bad_dev.ensure(16));
+  m->host_reserved = B;
+  return EF_OK;
+}
+
+static int copy_results_back(ef_model_t* m, int32_t B, const ef_result_t* out, const ef_result_t& dev) {
+  cudaStream_t st = m->stream;
+  if (out->proj) EF_CUDA(cudaMemcpyAsync(out->proj, dev.proj, sizeof(double) * (size_t)B * m->k, cudaMemcpyDeviceToHost, st));
+  if (out->score) EF_CUDA(cudaMemcpyAsync(out->score, dev.score, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (out->index) EF_CUDA(cudaMemcpyAsync(out->index, dev.index, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (out->label) EF_CUDA(cudaMemcpyAsync(out->label, dev.label, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  if (out->resid2) EF_CUDA(cudaMemcpyAsync(out->resid2, dev.resid2, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaStreamSynchronize(st));
+  return EF_OK;
+}
+
+int ef_model_recognize_host(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
+                            const ef_result_t* out) {
+  if (!m || !x || !out || B < 0 || ldx < m->D) return EF_ERR_INVALID;
+  if (out->resid2 && !m->with_residual) return EF_ERR_INVALID;
+  if (B == 0) return EF_OK;
+  EF_TRY(host_reserve(m, B));
+  cudaStream_t st = m->stream;
+  if (ldx == m->x_ld) {
+    EF_CUDA(cudaMemcpyAsync(m->x_dev.p, x, (size_t)B * ldx, cudaMemcpyHostToDevice, st));
+  } else {
+    EF_CUDA(cudaMemcpy2DAsync(m->x_dev.p, m->x_ld, x, ldx, m->D, B, cudaMemcpyHostToDevice, st));
+  }
+  ef_result_t dev;
+  dev.proj = out->proj ? m->proj.as<double>() : nullptr;
+  dev.score = m->score.as<double>();
+  dev.index = m->index32_dev.as<int32_t>();
+  dev.label = m->label_dev.as<int32_t>();
+  dev.resid2 = out->resid2 ? m->resid_dev.as<double>() : nullptr;
+  EF_TRY(ef_model_recognize_device(m, m->x_dev.as<uint8_t>(), m->x_ld, B, threshold, &dev, st));
+  return copy_results_back(m, B, out, dev);
+}
+
+int ef_model_recognize_boxes_device(ef_model_t* m, const uint8_t* frames, int64_t frame_stride, int32_t pitch,
+                                    int32_t width, int32_t height, int32_t channels, int32_t n_frames,
+                                    const ef_box_t* boxes, int32_t n_boxes, int32_t dw, int32_t dh, double threshold,
+                                    const ef_result_t* out, ef_stream_t stream) {
+  if (!m || !out || n_boxes < 0) return EF_ERR_INVALID;
+  if ((int64_t)dw * dh != m->D) return EF_ERR_INVALID;
+  if (n_boxes == 0) return EF_OK;
+  EF_TRY(host_reserve(m, n_boxes));
+  EF_TRY(ef_preprocess(frames, frame_stride, pitch, width, height, channels, n_frames, boxes, n_boxes, dw, dh,
+                       m->x_dev.as<uint8_t>(), m->x_ld, nullptr, stream));
+  return ef_model_recognize_device(m, m->x_dev.as<uint8_t>(), m->x_ld, n_boxes, threshold, out, stream);
+}
+
+int ef_model_recognize_boxes_host(ef_model_t* m, const uint8_t* frames, int64_t frame_stride, int32_t pitch,
+                                  int32_t width, int32_t height, int32_t channels, int32_t n_frames,
+                                  const ef_box_t* boxes, int32_t n_boxes, int32_t dw, int32_t dh, double threshold,
+                                  const ef_result_t* out) {
+  if (!m || !frames || !boxes || !out || n_boxes < 0 || n_frames <= 0) return EF_ERR_INVALID;
+  if (n_boxes == 0) return EF_OK;
+  EF_TRY(host_reserve(m, n_boxes));
+  const size_t frame_bytes = (size_t)frame_stride * n_frames;
+  EF_TRY(m->frames_dev.ensure(frame_bytes));
+  EF_TRY(m->boxes_dev.ensure(sizeof(ef_box_t) * (size_t)n_boxes));
+  cudaStream_t st = m->stream;
+  EF_CUDA(cudaMemcpyAsync(m->frames_dev.p, frames, frame_bytes, cudaMemcpyHostToDevice, st));
+  EF_CUDA(cudaMemcpyAsync(m->boxes_dev.p, boxes, sizeof(ef_box_t) * (size_t)n_boxes, cudaMemcpyHostToDevice, st));
+  ef_result_t dev;
+  dev.proj = out->proj ? m->proj.as<double>() : nullptr;
+  dev.score = m->score.as<double>();
+  dev.index = m->index32_dev.as<int32_t>();
+  dev.label = m->label_dev.as<int32_t>();
+  dev.resid2 = out->resid2 ? m->resid_dev.as<double>() : nullptr;
+  EF_TRY(ef_model_recognize_boxes_device(m, m->frames_dev.as<uint8_t>(), frame_stride, pitch, width, height, channels,
+                                         n_frames, m->boxes_dev.as<ef_box_t>(), n_boxes, dw, dh, threshold, &dev, st));
+  return copy_results_back(m, n_boxes, out, dev);
+}
+
+}  // extern "C"

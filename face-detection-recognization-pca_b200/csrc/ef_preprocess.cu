@@ -1,0 +1,147 @@
+// K1: crop preprocess, bit-exact with OpenCV's BGR2GRAY + INTER_LINEAR resize on uint8.
+//
+// Replaces cv2.cvtColor + cv2.resize + .flatten() at scan-template-v4.py:257-263, train-v5.py:329-332 and
+// useless/scan.py:248-252 for a whole batch of detection boxes.  HBM-bound byte work: one CTA walks crops,
+// coefficient tables live in shared memory, the source ROI is read through L1 (each source pixel is needed by
+// at most two destination rows / columns), the destination row is written coalesced.
+//
+// Fixed-point spec (the same one oracle/preprocess.py states and tests pin against cv2):
+//   gray = (3735 B + 19235 G + 9798 R + 2^14) >> 15
+//   scale = 1 / (dst / src) (double); f = float((d + .5) scale - .5); s = floor f; f -= s
+//   x: clamp s into [0, w-1] zeroing f when clamped; y: weights from the unclamped f, rows clipped
+//   a = rint(f * 2048) (float32, half-even); H = s0 * a0 + s1 * a1
+//   out = (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2
+//   src == 2 dst on both axes -> 2x2 box (a + b + c + d + 2) >> 2 ; src == dst -> copy
+#include "ef_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kMaxSide = 1024;  // largest dw / dh the shared-memory tables are sized for
+
+__device__ __forceinline__ int gray_at(const uint8_t* __restrict__ row, int x, int channels) {
+  if (channels == 1) return row[x];
+  const uint8_t* p = row + 3 * x;
+  return (3735 * p[0] + 19235 * p[1] + 9798 * p[2] + (1 << 14)) >> 15;
+}
+
+// One axis of OpenCV's coefficient table, computed with explicitly rounded (never fused) operations.
+__device__ __forceinline__ void axis_coeff(int d, int src, int dst, bool clamp_frac, int& s0, int& s1, int& w0,
+                                           int& w1) {
+  const double inv_scale = __ddiv_rn((double)dst, (double)src);
+  const double scale = __ddiv_rn(1.0, inv_scale);
+  const double fd = __dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
+  float f = __double2float_rn(fd);
+  const float fl = floorf(f);
+  int s = (int)fl;
+  f = __fsub_rn(f, fl);
+  if (clamp_frac) {
+    if (s < 0) { s = 0; f = 0.f; }
+    if (s >= src - 1) { s = src - 1; f = 0.f; }
+  }
+  w0 = __float2int_rn(__fmul_rn(__fsub_rn(1.f, f), 2048.f));
+  w1 = __float2int_rn(__fmul_rn(f, 2048.f));
+  s0 = min(max(s, 0), src - 1);
+  s1 = min(max(s + 1, 0), src - 1);
+}
+
+__global__ void __launch_bounds__(kThreads)
+preprocess_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int pitch, int width, int height,
+                  int channels, int n_frames, const ef_box_t* __restrict__ boxes, int n_boxes, int dw, int dh,
+                  uint8_t* __restrict__ out, int64_t out_stride, int* __restrict__ bad_boxes) {
+  extern __shared__ int tab[];
+  int* xs0 = tab;
+  int* xs1 = xs0 + dw;
+  int* xa0 = xs1 + dw;
+  int* xa1 = xa0 + dw;
+  int* ys0 = xa1 + dw;
+  int* ys1 = ys0 + dh;
+  int* yb0 = ys1 + dh;
+  int* yb1 = yb0 + dh;
+  const int tid = threadIdx.x;
+  const int npix = dw * dh;
+
+  for (int b = blockIdx.x; b < n_boxes; b += gridDim.x) {
+    const ef_box_t box = boxes[b];
+    uint8_t* __restrict__ o = out + (int64_t)b * out_stride;
+    const bool ok = box.frame >= 0 && box.frame < n_frames && box.w > 0 && box.h > 0 && box.x >= 0 && box.y >= 0 &&
+                    box.x + box.w <= width && box.y + box.h <= height;
+    if (!ok) {
+      for (int i = tid; i < npix; i += kThreads) o[i] = 0;
+      if (tid == 0 && bad_boxes) atomicAdd(bad_boxes, 1);
+      continue;
+    }
+    const uint8_t* __restrict__ src =
+        frames + (int64_t)box.frame * frame_stride + (int64_t)box.y * pitch + (int64_t)box.x * channels;
+    const int w = box.w, h = box.h;
+
+    if (w == dw && h == dh) {
+      // cv2.resize returns a copy when the size already matches.
+      const bool vec = channels == 1 && (dw % 16 == 0) && (pitch % 16 == 0) &&
+                       ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(o) & 15) == 0);
+      if (vec) {
+        const int per_row = dw / 16;
+        for (int i = tid; i < per_row * dh; i += kThreads) {
+          const int y = i / per_row, xv = i - y * per_row;
+          const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)y * pitch) + xv);
+          reinterpret_cast<uint4*>(o + (int64_t)y * dw)[xv] = v;
+        }
+      } else {
+        for (int i = tid; i < npix; i += kThreads) {
+          const int y = i / dw, x = i - y * dw;
+          o[i] = (uint8_t)gray_at(src + (int64_t)y * pitch, x, channels);
+        }
+      }
+    } else if (w == 2 * dw && h == 2 * dh) {
+      // OpenCV switches INTER_LINEAR to INTER_AREA for an exact 2x decimation.
+      for (int i = tid; i < npix; i += kThreads) {
+        const int y = i / dw, x = i - y * dw;
+        const uint8_t* r0 = src + (int64_t)(2 * y) * pitch;
+        const uint8_t* r1 = r0 + pitch;
+        const int s = gray_at(r0, 2 * x, channels) + gray_at(r0, 2 * x + 1, channels) +
+                      gray_at(r1, 2 * x, channels) + gray_at(r1, 2 * x + 1, channels);
+        o[i] = (uint8_t)((s + 2) >> 2);
+      }
+    } else {
+      for (int d = tid; d < dw + dh; d += kThreads) {
+        if (d < dw) {
+          axis_coeff(d, w, dw, true, xs0[d], xs1[d], xa0[d], xa1[d]);
+        } else {
+          const int e = d - dw;
+          axis_coeff(e, h, dh, false, ys0[e], ys1[e], yb0[e], yb1[e]);
+        }
+      }
+      __syncthreads();
+      for (int i = tid; i < npix; i += kThreads) {
+        const int y = i / dw, x = i - y * dw;
+        const uint8_t* r0 = src + (int64_t)ys0[y] * pitch;
+        const uint8_t* r1 = src + (int64_t)ys1[y] * pitch;
+        const int x0 = xs0[x], x1 = xs1[x], a0 = xa0[x], a1 = xa1[x];
+        const int h0 = gray_at(r0, x0, channels) * a0 + gray_at(r0, x1, channels) * a1;
+        const int h1 = gray_at(r1, x0, channels) * a0 + gray_at(r1, x1, channels) * a1;
+        const int v = (((yb0[y] * (h0 >> 4)) >> 16) + ((yb1[y] * (h1 >> 4)) >> 16) + 2) >> 2;
+        o[i] = (uint8_t)min(max(v, 0), 255);
+      }
+      __syncthreads();  // tables are rewritten by the next crop
+    }
+  }
+}
+
+}  // namespace
+
+extern "C" int ef_preprocess(const uint8_t* frames, int64_t frame_stride, int32_t pitch, int32_t width,
+                             int32_t height, int32_t channels, int32_t n_frames, const ef_box_t* boxes,
+                             int32_t n_boxes, int32_t dw, int32_t dh, uint8_t* out, int64_t out_stride,
+                             int32_t* bad_boxes, ef_stream_t stream) {
+  if (!frames || !boxes || !out) return EF_ERR_INVALID;
+  if (n_boxes < 0 || width <= 0 || height <= 0 || n_frames <= 0 || dw <= 0 || dh <= 0) return EF_ERR_INVALID;
+  if (channels != 1 && channels != 3) return EF_ERR_INVALID;
+  if (pitch < width * channels || out_stride < (int64_t)dw * dh) return EF_ERR_INVALID;
+  if (dw > kMaxSide || dh > kMaxSide) return EF_ERR_UNSUPPORTED;
+  if (n_boxes == 0) return EF_OK;
+  const int grid = (int)(n_boxes < (int64_t)ef::sm_count() * 8 ? n_boxes : ef::sm_count() * 8);
+  const size_t smem = sizeof(int) * 4 * (size_t)(dw + dh);
+  EF_LAUNCH(preprocess_kernel, grid, kThreads, smem, ef::as_stream(stream), frames, frame_stride, pitch, width,
+            height, channels, n_frames, boxes, n_boxes, dw, dh, out, out_stride, bad_boxes);
+  return EF_OK;
+}

@@ -1,0 +1,253 @@
+"""Batched recognition engine and PCA fit on top of the C ABI (host-side mirror, no arithmetic here).
+
+`Recognizer` wraps one ef_model handle: a model dict of either reference generation goes in once, batches of
+crops go through `recognize` (host numpy buffers, copies inside) or `recognize_device` (torch CUDA tensors,
+zero-copy).  `fit_gen1` / `fit_gen2` wrap the device PCA fits.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import METRIC_COSINE_G1, METRIC_COSINE_SK, METRIC_L2, Box, FitInfo, Gen2Fit, ModelDesc, Result, check
+
+
+def _f64(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class RecognitionResult:
+    """Arrays for a batch: features [B,k], score [B], index [B], label [B], resid2 [B] or None."""
+    __slots__ = ("features", "score", "index", "label", "resid2")
+
+    def __init__(self, features, score, index, label, resid2):
+        self.features, self.score, self.index, self.label, self.resid2 = features, score, index, label, resid2
+
+
+class Recognizer:
+    """Device-resident recognition model.
+
+    basis: [D, k] (any strides; the Gen-1 pickle stores it Fortran-ordered) or, with basis_is_components=True,
+    sklearn's components_ [k, D].  mean [D]; scale / pca_mean [D] or None; gallery [Ng, k]; labels [Ng] or None.
+    """
+
+    def __init__(self, basis, mean, gallery, *, scale=None, pca_mean=None, labels=None, metric=METRIC_COSINE_G1,
+                 basis_is_components=False, n_slices=0, with_residual=True):
+        L = _lib.lib()
+        basis = np.asarray(basis)
+        if basis.dtype != np.float64:
+            basis = basis.astype(np.float64)           # float32 pickles upcast exactly (numpy does the same)
+        if basis_is_components:
+            basis = basis.T                             # view [D, k]
+        if basis.ndim != 2:
+            raise ValueError("basis must be 2-D")
+        D, k = basis.shape
+        if not (basis.flags["C_CONTIGUOUS"] or basis.flags["F_CONTIGUOUS"]):
+            basis = np.asfortranarray(basis)
+        sd, sk = basis.strides[0] // 8, basis.strides[1] // 8
+        self._keep = [basis, _f64(mean), _f64(gallery)]
+        mean_a, gal = self._keep[1], self._keep[2]
+        if mean_a.shape != (D,) or gal.ndim != 2 or gal.shape[1] != k:
+            raise ValueError(f"shape mismatch: basis {basis.shape}, mean {mean_a.shape}, gallery {gal.shape}")
+        scale_a = _f64(scale) if scale is not None else None
+        pm_a = _f64(pca_mean) if pca_mean is not None else None
+        lab_a = np.ascontiguousarray(np.asarray(labels, dtype=np.int32)) if labels is not None else None
+        desc = ModelDesc(D=D, k=k, basis=_ptr(basis), basis_stride_d=sd, basis_stride_k=sk, mean=_ptr(mean_a),
+                         scale=_ptr(scale_a), pca_mean=_ptr(pm_a), gallery=_ptr(gal), gallery_ld=k,
+                         n_gallery=gal.shape[0], labels=_ptr(lab_a), metric=metric, n_slices=n_slices,
+                         with_residual=1 if with_residual else 0)
+        handle = C.c_void_p()
+        check(L.ef_model_create(C.byref(handle), C.byref(desc)), "ef_model_create")
+        self._h, self._L = handle, L
+        self.D, self.k, self.n_gallery, self.metric = D, k, gal.shape[0], metric
+        self.with_residual = with_residual
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._L.ef_model_destroy(self._h)
+            self._h = None
+
+    __del__ = close
+
+    def reserve(self, max_batch):
+        check(self._L.ef_model_reserve(self._h, int(max_batch)), "ef_model_reserve")
+
+    def use_tensor_cores(self, enable=True):
+        check(self._L.ef_model_set_tensor_cores(self._h, 1 if enable else 0), "ef_model_set_tensor_cores")
+
+    def kernel_timing(self, enable=True):
+        check(self._L.ef_model_kernel_timing(self._h, 1 if enable else 0), "ef_model_kernel_timing")
+
+    def kernel_timing_read(self):
+        """(calls, mean projection-kernel milliseconds, used_tensor_cores) since kernel_timing(True)."""
+        n, ms, tc = C.c_int32(), C.c_double(), C.c_int32()
+        check(self._L.ef_model_kernel_timing_read(self._h, C.byref(n), C.byref(ms), C.byref(tc)),
+              "ef_model_kernel_timing_read")
+        return n.value, ms.value, bool(tc.value)
+
+    # ------------------------------------------------------------------ host buffers (numpy in, numpy out)
+    def recognize(self, crops, threshold=0.7, want_features=True, want_residual=None):
+        """crops: uint8 [B, D] (row pitch arbitrary).  Copies in, runs K2, copies results out (synchronous)."""
+        x = np.asarray(crops)
+        if x.dtype != np.uint8 or x.ndim != 2 or x.shape[1] != self.D:
+            raise ValueError(f"crops must be uint8 [B, {self.D}], got {x.dtype} {x.shape}")
+        if x.strides[1] != 1:
+            x = np.ascontiguousarray(x)
+        B = x.shape[0]
+        want_residual = self.with_residual if want_residual is None else want_residual
+        feats = np.empty((B, self.k), dtype=np.float64) if want_features else None
+        score = np.empty(B, dtype=np.float64)
+        index = np.empty(B, dtype=np.int32)
+        label = np.empty(B, dtype=np.int32)
+        resid = np.empty(B, dtype=np.float64) if want_residual else None
+        res = Result(_ptr(feats), _ptr(score), _ptr(index), _ptr(label), _ptr(resid))
+        check(self._L.ef_model_recognize_host(self._h, _ptr(x), x.strides[0], B, float(threshold), C.byref(res)),
+              "ef_model_recognize_host")
+        return RecognitionResult(feats, score, index, label, resid)
+
+    def recognize_boxes(self, frames, boxes, side, threshold=0.7, want_features=True, want_residual=None):
+        """frames: uint8 [F, H, W] gray or [F, H, W, 3] BGR (or a single frame); boxes: int [B, 4] (x, y, w, h) or
+        [B, 5] (frame, x, y, w, h).  K1 + K2 through host buffers."""
+        fr = np.ascontiguousarray(frames)
+        if fr.dtype != np.uint8:
+            raise ValueError("frames must be uint8")
+        if fr.ndim == 2 or (fr.ndim == 3 and fr.shape[2] == 3):
+            fr = fr[None]
+        channels = 3 if fr.ndim == 4 else 1
+        F, H, W = fr.shape[:3]
+        bx = np.asarray(boxes, dtype=np.int32).reshape(-1, np.asarray(boxes).shape[-1])
+        if bx.shape[1] == 4:
+            bx = np.concatenate([np.zeros((len(bx), 1), np.int32), bx], axis=1)
+        bx = np.ascontiguousarray(bx)
+        B = len(bx)
+        if side * side != self.D:
+            raise ValueError("side*side must equal the model dimension")
+        want_residual = self.with_residual if want_residual is None else want_residual
+        feats = np.empty((B, self.k), dtype=np.float64) if want_features else None
+        score = np.empty(B, dtype=np.float64)
+        index = np.empty(B, dtype=np.int32)
+        label = np.empty(B, dtype=np.int32)
+        resid = np.empty(B, dtype=np.float64) if want_residual else None
+        res = Result(_ptr(feats), _ptr(score), _ptr(index), _ptr(label), _ptr(resid))
+        check(self._L.ef_model_recognize_boxes_host(self._h, _ptr(fr), H * W * channels, W * channels, W, H, channels,
+                                                    F, _ptr(bx), B, side, side, float(threshold), C.byref(res)),
+              "ef_model_recognize_boxes_host")
+        return RecognitionResult(feats, score, index, label, resid)
+
+    # ------------------------------------------------------------------ device buffers (torch CUDA tensors)
+    def recognize_device(self, x, threshold=0.7, out=None, want_residual=None):
+        """x: torch uint8 CUDA tensor [B, ldx>=D] with 16-byte aligned rows.  Enqueues on torch's current stream and
+        returns a dict of CUDA tensors (features, score, index, label, resid2)."""
+        import torch
+        if not (x.is_cuda and x.dtype == torch.uint8 and x.dim() == 2 and x.stride(1) == 1):
+            raise ValueError("x must be a 2-D uint8 CUDA tensor with unit inner stride")
+        B = x.shape[0]
+        want_residual = self.with_residual if want_residual is None else want_residual
+        if out is None:
+            out = {
+                "features": torch.empty((B, self.k), dtype=torch.float64, device=x.device),
+                "score": torch.empty(B, dtype=torch.float64, device=x.device),
+                "index": torch.empty(B, dtype=torch.int32, device=x.device),
+                "label": torch.empty(B, dtype=torch.int32, device=x.device),
+                "resid2": torch.empty(B, dtype=torch.float64, device=x.device) if want_residual else None,
+            }
+        res = Result(out["features"].data_ptr(), out["score"].data_ptr(), out["index"].data_ptr(),
+                     out["label"].data_ptr(), out["resid2"].data_ptr() if out.get("resid2") is not None else None)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        check(self._L.ef_model_recognize_device(self._h, x.data_ptr(), x.stride(0), B, float(threshold), C.byref(res),
+                                                C.c_void_p(stream)), "ef_model_recognize_device")
+        return out
+
+    def recognize_boxes_device(self, frames, boxes, side, threshold=0.7, out=None, want_residual=None):
+        """frames: torch uint8 CUDA [F, H, W] / [F, H, W, 3]; boxes: torch int32 CUDA [B, 5] (frame, x, y, w, h)."""
+        import torch
+        channels = 3 if frames.dim() == 4 else 1
+        F, H, W = frames.shape[:3]
+        B = boxes.shape[0]
+        want_residual = self.with_residual if want_residual is None else want_residual
+        if out is None:
+            dev = frames.device
+            out = {
+                "features": torch.empty((B, self.k), dtype=torch.float64, device=dev),
+                "score": torch.empty(B, dtype=torch.float64, device=dev),
+                "index": torch.empty(B, dtype=torch.int32, device=dev),
+                "label": torch.empty(B, dtype=torch.int32, device=dev),
+                "resid2": torch.empty(B, dtype=torch.float64, device=dev) if want_residual else None,
+            }
+        res = Result(out["features"].data_ptr(), out["score"].data_ptr(), out["index"].data_ptr(),
+                     out["label"].data_ptr(), out["resid2"].data_ptr() if out.get("resid2") is not None else None)
+        stream = torch.cuda.current_stream(frames.device).cuda_stream
+        check(self._L.ef_model_recognize_boxes_device(
+            self._h, frames.data_ptr(), frames.stride(0), frames.stride(1), W, H, channels, F, boxes.data_ptr(), B,
+            side, side, float(threshold), C.byref(res), C.c_void_p(stream)), "ef_model_recognize_boxes_device")
+        return out
+
+
+def preprocess_device(frames, boxes, side, out=None):
+    """K1 alone on torch CUDA tensors: returns uint8 [B, ld] with ld = side*side rounded up to 128."""
+    import torch
+    channels = 3 if frames.dim() == 4 else 1
+    F, H, W = frames.shape[:3]
+    B = boxes.shape[0]
+    ld = (side * side + 127) // 128 * 128
+    if out is None:
+        out = torch.zeros((B, ld), dtype=torch.uint8, device=frames.device)
+    stream = torch.cuda.current_stream(frames.device).cuda_stream
+    check(_lib.lib().ef_preprocess(frames.data_ptr(), frames.stride(0), frames.stride(1), W, H, channels, F,
+                                   boxes.data_ptr(), B, side, side, out.data_ptr(), out.stride(0), None,
+                                   C.c_void_p(stream)), "ef_preprocess")
+    return out
+
+
+def _check_u8(X):
+    X = np.asarray(X)
+    if X.dtype != np.uint8:
+        Xi = np.rint(X)
+        if not (np.array_equal(Xi, X) and Xi.min() >= 0 and Xi.max() <= 255):
+            raise ValueError("the device PCA fit takes 8-bit pixel data (integral values in [0, 255])")
+        X = Xi.astype(np.uint8)
+    if X.ndim != 2:
+        raise ValueError("data matrix must be [N, D]")
+    return np.ascontiguousarray(X)
+
+
+def fit_gen1(X, n_components=None):
+    """Device manual_pca (useless/train.py:56-128).  Returns (eigenfaces [D,k] F-order, mean, projected, eigenvalues, info)."""
+    X = _check_u8(X)
+    N, D = X.shape
+    n = N if N < D else D
+    k = min(N - 1, D) if n_components is None else int(n_components)
+    k = min(k, n)
+    eigenfaces = np.empty((D, k), dtype=np.float64, order="F")
+    mean = np.empty(D, dtype=np.float64)
+    projected = np.empty((N, k), dtype=np.float64)
+    eigenvalues = np.empty(k, dtype=np.float64)
+    info = FitInfo()
+    check(_lib.lib().ef_fit_gen1_host(_ptr(X), X.strides[0], N, D, k, _ptr(eigenfaces), _ptr(mean), _ptr(projected),
+                                      _ptr(eigenvalues), C.byref(info)), "ef_fit_gen1_host")
+    return eigenfaces, mean, projected, eigenvalues, {"sweeps": info.sweeps, "branch": info.branch,
+                                                      "off_norm": info.off_norm, "gpu_ms": info.gpu_ms}
+
+
+def fit_gen2(X, n_components):
+    """Device StandardScaler + PCA(full) (train-v5.py:349-385).  Returns a dict of float64 arrays + info."""
+    X = _check_u8(X)
+    N, D = X.shape
+    k = int(n_components)
+    out = {
+        "mean_face": np.empty(D), "scaler_mean": np.empty(D), "scaler_var": np.empty(D), "scaler_scale": np.empty(D),
+        "pca_mean": np.empty(D), "components": np.empty((k, D)), "explained_variance": np.empty(k),
+        "explained_variance_ratio": np.empty(k), "singular_values": np.empty(k), "noise_variance": np.empty(1),
+        "features": np.empty((N, k)),
+    }
+    g = Gen2Fit(**{name: _ptr(arr) for name, arr in out.items()})
+    info = FitInfo()
+    check(_lib.lib().ef_fit_gen2_host(_ptr(X), X.strides[0], N, D, k, C.byref(g), C.byref(info)), "ef_fit_gen2_host")
+    out["noise_variance"] = float(out["noise_variance"][0])
+    out["info"] = {"sweeps": info.sweeps, "branch": info.branch, "off_norm": info.off_norm, "gpu_ms": info.gpu_ms}
+    return out

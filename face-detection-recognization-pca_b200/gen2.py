@@ -1,0 +1,347 @@
+"""Gen-2 ("sklearn PCA") interface of the reference, backed by the B200 engine.
+
+  MultiFaceTrainer        train-v5.py:13-505   (train_pca_model :349-385, save_model :438-467, load_model :469-505)
+  MultiModelFaceScanner   scan-template-v4.py:10-319 (extract_face_features :253-268, recognize_face_with_model
+                          :270-287, recognize_face_all_models :289-319)
+The pickles written by save_model hold genuine fitted sklearn PCA / StandardScaler objects, so the reference's own
+scan-template-v4.py loads them and calls .transform on them; the pickles the reference wrote load here.
+"""
+import glob
+import json
+import os
+import pickle
+from datetime import datetime
+
+import numpy as np
+
+from . import engine
+from ._lib import METRIC_COSINE_SK
+
+_CACHE = {}
+
+
+def _sklearn_objects(fit, n_samples):
+    """Populate real sklearn estimators with the device fit (what pickle consumers call .transform on)."""
+    from sklearn.decomposition import PCA
+    from sklearn.preprocessing import StandardScaler
+    k, D = fit["components"].shape
+    pca = PCA(n_components=k)
+    pca.components_ = fit["components"]
+    pca.mean_ = fit["pca_mean"]
+    pca.explained_variance_ = fit["explained_variance"]
+    pca.explained_variance_ratio_ = fit["explained_variance_ratio"]
+    pca.singular_values_ = fit["singular_values"]
+    pca.n_components_ = k
+    pca.n_samples_ = n_samples
+    pca.n_features_in_ = D
+    pca.noise_variance_ = fit["noise_variance"]
+    pca._fit_svd_solver = "full"
+    scaler = StandardScaler()
+    scaler.mean_ = fit["scaler_mean"]
+    scaler.var_ = fit["scaler_var"]
+    scaler.scale_ = fit["scaler_scale"]
+    scaler.n_samples_seen_ = np.int64(n_samples)
+    scaler.n_features_in_ = D
+    return pca, scaler
+
+
+def _model_arrays(model_data):
+    pca = model_data.get('pca', model_data.get('pca_model'))   # the shipped pickle uses 'pca_model' 
+    scaler = model_data['scaler']
+    return pca, scaler
+
+
+def recognizer_for(model_data, n_slices=0):
+    """Device model for a Gen-2 model dict (cached per dict object)."""
+    key = (id(model_data), n_slices)
+    hit = _CACHE.get(key)
+    if hit is not None and hit[0] is model_data:
+        return hit[1]
+    pca, scaler = _model_arrays(model_data)
+    rec = engine.Recognizer(pca.components_, scaler.mean_, model_data['face_features'], scale=scaler.scale_,
+                            pca_mean=pca.mean_, labels=model_data['face_labels'], metric=METRIC_COSINE_SK,
+                            basis_is_components=True, n_slices=n_slices, with_residual=True)
+    _CACHE[key] = (model_data, rec)
+    return rec
+
+
+class MultiFaceTrainer:
+    def __init__(self, n_components=50):
+        self.n_components = n_components
+        self.pca = None
+        self.scaler = None
+        self.face_images = []
+        self.face_features = []
+        self.face_labels = []
+        self.face_info = []
+        self.is_trained = False
+        self.mean_face = None
+        self.eigenfaces = None
+        self.face_shape = (64, 64)
+        self.person_id_map = {}
+        self.fit_info = None
+
+    def load_face_images_from_json(self, json_path, person_dir):
+        """train-v5.py:276-347: host JPEG decode, then gray + resize of all crops in one K1 launch."""
+        import cv2
+        print(f"Loading face data from {json_path}")
+        if not os.path.exists(json_path):
+            print(f"Error: JSON file {json_path} not found!")
+            return 0
+        with open(json_path, 'r', encoding='utf-8') as f:
+            data = json.load(f)
+        faces_data = data['faces']
+        print(f"Found {len(faces_data)} faces in JSON")
+        images, valid = [], []
+        for i, face_info in enumerate(faces_data):
+            if 'image_filename' in face_info:
+                image_path = os.path.join(person_dir, face_info['image_filename'])
+            elif 'image_path' in face_info:
+                image_path = face_info['image_path']
+            else:
+                image_path = os.path.join(
+                    person_dir, f"face_{face_info.get('face_id', i)}_frame_{face_info.get('frame_number', i)}.jpg")
+            if not os.path.exists(image_path):
+                print(f"Warning: Image {image_path} not found, skipping...")
+                continue
+            img = cv2.imread(image_path)
+            if img is None:
+                print(f"Warning: Could not read image {image_path}, skipping...")
+                continue
+            images.append(img)
+            valid.append(face_info)
+        self.face_images = preprocess_images(images, self.face_shape[0]) if images else np.zeros((0, 4096), np.uint8)
+        print(f"Successfully loaded {len(images)} face images")
+        self.face_info = valid
+        self.face_labels = np.zeros(len(images), dtype=int)
+        self.person_id_map = {os.path.basename(person_dir): 0}
+        return len(images)
+
+    def train_pca_model(self):
+        if len(self.face_images) == 0:
+            print("Error: No face images loaded!")
+            return False
+        if len(self.face_labels) == 0:
+            print("Error: No face labels assigned!")
+            return False
+        X = np.asarray(self.face_images)
+        print(f"\nTraining PCA model with {len(X)} faces...")
+        print(f"Original feature dimension: {X.shape[1]}")
+        print(f"Reducing to {self.n_components} components")
+        fit = engine.fit_gen2(X, self.n_components)
+        self.mean_face = fit["mean_face"]
+        print(f"Mean face calculated with shape: {self.mean_face.shape}")
+        self.pca, self.scaler = _sklearn_objects(fit, len(X))
+        self.eigenfaces = self.pca.components_
+        print(f"Generated {len(self.eigenfaces)} eigenfaces")
+        print(f"PCA explained variance ratio: {self.pca.explained_variance_ratio_.sum():.3f}")
+        print(f"Reduced feature dimension: {fit['features'].shape[1]}")
+        self.face_features = fit["features"]
+        self.fit_info = fit["info"]
+        self.is_trained = True
+        return True
+
+    def save_eigenfaces(self, output_dir):
+        """train-v5.py:387-436: mean face + first 10 eigenfaces as min-max normalised JPEGs + model-info JSON."""
+        if not self.is_trained:
+            print("Error: Model not trained yet!")
+            return False
+        import cv2
+        os.makedirs(output_dir, exist_ok=True)
+        mean_img = cv2.normalize(self.mean_face.reshape(self.face_shape), None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8U)
+        cv2.imwrite(os.path.join(output_dir, "multi_person_mean_face.jpg"), mean_img)
+        n_save = min(10, len(self.eigenfaces))
+        for i in range(n_save):
+            ef = cv2.normalize(self.eigenfaces[i].reshape(self.face_shape), None, 0, 255, cv2.NORM_MINMAX, dtype=cv2.CV_8U)
+            cv2.imwrite(os.path.join(output_dir, f"multi_person_eigenface_{i + 1:02d}.jpg"), ef)
+        model_info = {
+            'training_date': datetime.now().isoformat(),
+            'total_faces': len(self.face_images),
+            'total_persons': len(self.person_id_map),
+            'person_id_map': self.person_id_map,
+            'n_components': self.n_components,
+            'explained_variance_ratio': float(self.pca.explained_variance_ratio_.sum()),
+            'face_shape': self.face_shape,
+            'eigenfaces_saved': n_save,
+        }
+        with open(os.path.join(output_dir, "multi_person_model_info.json"), 'w', encoding='utf-8') as f:
+            json.dump(model_info, f, indent=2, ensure_ascii=False)
+        return True
+
+    def save_model(self, model_path):
+        if not self.is_trained:
+            print("Error: Model not trained yet!")
+            return False
+        model_data = {
+            'pca': self.pca,
+            'scaler': self.scaler,
+            'face_features': self.face_features,
+            'face_labels': self.face_labels,
+            'face_info': self.face_info,
+            'person_id_map': self.person_id_map,
+            'n_components': self.n_components,
+            'mean_face': self.mean_face,
+            'eigenfaces': self.eigenfaces,
+            'face_shape': self.face_shape,
+            'training_date': datetime.now().isoformat(),
+        }
+        with open(model_path, 'wb') as f:
+            pickle.dump(model_data, f)
+        print(f"Model saved to {model_path}")
+        return True
+
+    def load_model(self, model_path):
+        if not os.path.exists(model_path):
+            print(f"Error: Model file {model_path} not found!")
+            return False
+        with open(model_path, 'rb') as f:
+            model_data = pickle.load(f)
+        self.pca = model_data['pca']
+        self.scaler = model_data['scaler']
+        self.face_features = model_data['face_features']
+        self.face_labels = model_data['face_labels']
+        self.face_info = model_data['face_info']
+        self.person_id_map = model_data['person_id_map']
+        self.n_components = model_data['n_components']
+        self.mean_face = model_data.get('mean_face', None)
+        self.eigenfaces = model_data.get('eigenfaces', None)
+        self.face_shape = model_data.get('face_shape', (64, 64))
+        self.is_trained = True
+        print(f"Model loaded from {model_path}")
+        return True
+
+
+def preprocess_images(images, side):
+    """Gray + resize a list of variable-size uint8 images (BGR or gray) to [B, side*side] with ONE K1 launch:
+    the images are packed into one padded canvas per image (host), boxes name the valid region."""
+    import torch
+    from . import engine as _e
+    H = max(im.shape[0] for im in images)
+    W = max(im.shape[1] for im in images)
+    color = any(im.ndim == 3 for im in images)
+    canvas = np.zeros((len(images), H, W, 3) if color else (len(images), H, W), dtype=np.uint8)
+    boxes = np.zeros((len(images), 5), dtype=np.int32)
+    for i, im in enumerate(images):
+        if color and im.ndim == 2:
+            raise ValueError("mixing gray and BGR images in one batch is not supported")
+        canvas[i, :im.shape[0], :im.shape[1]] = im
+        boxes[i] = (i, 0, 0, im.shape[1], im.shape[0])
+    dev = torch.device("cuda", torch.cuda.current_device())
+    out = _e.preprocess_device(torch.from_numpy(canvas).to(dev), torch.from_numpy(boxes).to(dev), side)
+    return out[:, :side * side].cpu().numpy()
+
+
+class MultiModelFaceScanner:
+    def __init__(self):
+        self.models = {}
+
+    def load_all_models(self, model_pattern="faces/lock_version/*/face_model.pkl"):
+        """scan-template-v4.py:17-74 without the template images (detection stays on the host, out of scope)."""
+        model_paths = glob.glob(model_pattern)
+        if not model_paths:
+            print(f"No models found matching pattern: {model_pattern}")
+            return False
+        print(f"Found {len(model_paths)} model(s):")
+        for model_path in model_paths:
+            person_name = os.path.basename(os.path.dirname(model_path))
+            try:
+                with open(model_path, 'rb') as f:
+                    model_data = pickle.load(f)
+                self.models[person_name] = {'model_data': model_data, 'model_path': model_path}
+                print(f"  - {person_name}: {len(model_data['face_features'])} faces")
+            except Exception as e:
+                print(f"  - Failed to load {person_name}: {e}")
+        print(f"Successfully loaded {len(self.models)} model(s)")
+        return len(self.models) > 0
+
+    # ---- single-crop interface (reference signatures)
+    def extract_face_features(self, face_img, model_data):
+        rec = recognizer_for(model_data)
+        face_img = np.asarray(face_img)
+        h, w = face_img.shape[:2]
+        res = rec.recognize_boxes(face_img, [[0, 0, w, h]], 64, 0.0, want_residual=False)
+        return res.features[0]
+
+    def recognize_face_with_model(self, face_features, model_data, threshold=0.7):
+        """Cosine argmax of already extracted features against the model's gallery (device match kernel)."""
+        score, idx = match_features(np.asarray(face_features, dtype=np.float64)[None, :], model_data)
+        return _label_tuple(score[0], idx[0], model_data, threshold)
+
+    def recognize_face_all_models(self, face_img, threshold=0.8):
+        ids, names, confs = self.recognize_faces_all_models(np.asarray(face_img), None, threshold)
+        return ids[0], names[0], confs[0]
+
+    # ---- batched interface
+    def recognize_faces_all_models(self, frames, boxes, threshold=0.8):
+        """All detections of a frame (or clip) against every loaded model; keeps the best confidence per detection
+        with the reference's rules (strict >, first model wins ties, below-threshold name falls back to the model's
+        person; scan-template-v4.py:297-319).  boxes None = the whole image is one crop."""
+        frames = np.asarray(frames)
+        if boxes is None:
+            h, w = frames.shape[:2]
+            boxes = [[0, 0, w, h]]
+        B = len(boxes)
+        best_conf = np.zeros(B)
+        best_id = np.full(B, -1, dtype=np.int64)
+        best_name = np.array(["unknown"] * B, dtype=object)
+        for person_name, info in self.models.items():
+            model_data = info['model_data']
+            if model_data is None:
+                continue
+            try:
+                rec = recognizer_for(model_data)
+                res = rec.recognize_boxes(frames, boxes, 64, threshold, want_features=False, want_residual=False)
+            except Exception as e:
+                print(f"Error recognizing with model {person_name}: {e}")
+                continue
+            names = _names_for(res.label, model_data)
+            better = res.score > best_conf
+            best_conf = np.where(better, res.score, best_conf)
+            best_id = np.where(better, res.label, best_id)
+            best_name = np.where(better, np.where(names == "unknown", person_name, names), best_name)
+        return best_id.tolist(), best_name.tolist(), best_conf.tolist()
+
+
+def match_features(features, model_data):
+    """features [B,k] float64 -> (score [B], index [B]) with sklearn-cosine argmax on the device."""
+    import ctypes as C
+    import torch
+    from . import _lib
+    L = _lib.lib()
+    dev = torch.device("cuda", torch.cuda.current_device())
+    key = ("gal", id(model_data))
+    hit = _CACHE.get(key)
+    gal = np.asarray(model_data['face_features'], dtype=np.float64)
+    n, k = gal.shape
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    if hit is None or hit[0] is not model_data:
+        g = torch.from_numpy(np.ascontiguousarray(gal)).to(dev)
+        gp = torch.empty_like(g)
+        _lib.check(L.ef_gallery_prepare_device(g.data_ptr(), k, n, k, METRIC_COSINE_SK, gp.data_ptr(), k, None, stream),
+                   "ef_gallery_prepare_device")
+        _CACHE[key] = hit = (model_data, gp)
+    gp = hit[1]
+    p = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float64)).to(dev)
+    B = p.shape[0]
+    score = torch.empty(B, dtype=torch.float64, device=dev)
+    index = torch.empty(B, dtype=torch.int64, device=dev)
+    _lib.check(L.ef_match_device(p.data_ptr(), k, B, k, gp.data_ptr(), k, None, n, 0, METRIC_COSINE_SK,
+                                 score.data_ptr(), index.data_ptr(), None, stream), "ef_match_device")
+    return score.cpu().numpy(), index.cpu().numpy()
+
+
+def _names_for(labels, model_data):
+    inv = {pid: name for name, pid in reversed(list(model_data['person_id_map'].items()))}
+    return np.array([inv.get(int(l), "unknown") if l >= 0 else "unknown" for l in labels], dtype=object)
+
+
+def _label_tuple(score, idx, model_data, threshold):
+    if score >= threshold:
+        person_id = model_data['face_labels'][idx]
+        person_name = "unknown"
+        for name, pid in model_data['person_id_map'].items():
+            if pid == person_id:
+                person_name = name
+                break
+        return person_id, person_name, score
+    return -1, "unknown", score

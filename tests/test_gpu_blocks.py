@@ -1,0 +1,126 @@
+"""Device building blocks of the fit and of the sharded gallery, each against numpy."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import eigenfaces_b200 as ef
+from gpu_util import require_gpu
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream(torch):
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def test_dgemm_strided_layouts():
+    torch = require_gpu()
+    L = ef._lib.lib()
+    rng = np.random.default_rng(0)
+    for (M, N, K) in ((70, 33, 129), (256, 256, 64), (5, 300, 1000), (1, 1, 1)):
+        A = rng.normal(size=(M, K)); B = rng.normal(size=(K, N)); C0 = rng.normal(size=(M, N))
+        for ta in (False, True):
+            for tb in (False, True):
+                a = torch.from_numpy(np.ascontiguousarray(A.T if ta else A)).cuda()
+                b = torch.from_numpy(np.ascontiguousarray(B.T if tb else B)).cuda()
+                c = torch.from_numpy(C0.copy()).cuda()
+                sam, sak = (1, M) if ta else (K, 1)
+                sbk, sbn = (1, K) if tb else (N, 1)
+                ef._lib.check(L.ef_dgemm_device(M, N, K, 0.5, a.data_ptr(), sam, sak, b.data_ptr(), sbk, sbn, 2.0,
+                                                c.data_ptr(), N, _stream(torch)), "dgemm")
+                np.testing.assert_allclose(c.cpu().numpy(), 0.5 * A @ B + 2.0 * C0, rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 64, 229, 300])
+def test_jacobi_eigensolver(n):
+    torch = require_gpu()
+    L = ef._lib.lib()
+    rng = np.random.default_rng(n)
+    Z = rng.normal(size=(n, max(n // 2, 1) if n > 8 else n + 3))        # rank deficient for n > 8 (like a centred Gram)
+    A = Z @ Z.T
+    a = torch.from_numpy(A.copy()).cuda()
+    evals = torch.empty(n, dtype=torch.float64, device="cuda")
+    evecs = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    work = torch.empty(L.ef_eigh_work_bytes(n), dtype=torch.uint8, device="cuda")
+    sweeps, off = C.c_int32(), C.c_double()
+    ef._lib.check(L.ef_eigh_jacobi_device(a.data_ptr(), n, evals.data_ptr(), evecs.data_ptr(), work.data_ptr(), 0, 0.0,
+                                          C.byref(sweeps), C.byref(off), _stream(torch)), "jacobi")
+    w = evals.cpu().numpy(); V = evecs.cpu().numpy()
+    w_ref = np.linalg.eigvalsh(A)[::-1]
+    np.testing.assert_allclose(w, w_ref, rtol=1e-10, atol=1e-10 * max(1.0, abs(w_ref[0])))
+    assert np.all(np.diff(w) <= 1e-9 * max(1.0, abs(w[0])))                    # descending
+    np.testing.assert_allclose(V @ V.T, np.eye(n), atol=1e-11)
+    np.testing.assert_allclose(V @ A @ V.T, np.diag(w), atol=1e-9 * max(1.0, abs(w_ref[0])))
+    assert sweeps.value <= 20
+
+
+def test_integer_gram_colsum_and_centring():
+    torch = require_gpu()
+    L = ef._lib.lib()
+    rng = np.random.default_rng(1)
+    N, D = 150, 1000
+    X = rng.integers(0, 256, (N, D), dtype=np.uint8)
+    x = torch.from_numpy(X).cuda()
+    cs = torch.empty(D, dtype=torch.int64, device="cuda")
+    ef._lib.check(L.ef_colsum_u8_device(x.data_ptr(), D, N, D, cs.data_ptr(), _stream(torch)), "colsum")
+    assert np.array_equal(cs.cpu().numpy(), X.astype(np.int64).sum(0))
+    Xi = X.astype(np.int64)
+    for side, n in ((0, N), (1, D)):
+        G = torch.zeros((n, n), dtype=torch.int64, device="cuda")
+        # accumulate in two column (side 0) / row (side 1) chunks: the += contract of the sharded fit
+        if side == 0:
+            for d0, d1 in ((0, 333), (333, D)):
+                ef._lib.check(L.ef_gram_u8_device(x.data_ptr(), D, N, D, d0, d1, 0, G.data_ptr(), _stream(torch)), "gram")
+            want = Xi @ Xi.T
+        else:
+            for r0, r1 in ((0, 70), (70, N)):
+                ef._lib.check(L.ef_gram_u8_device(x[r0:r1].data_ptr(), D, r1 - r0, D, 0, D, 1, G.data_ptr(), _stream(torch)), "gram")
+            want = Xi.T @ Xi
+        assert np.array_equal(G.cpu().numpy(), want)
+        Cc = torch.empty((n, n), dtype=torch.float64, device="cuda")
+        work = torch.empty(max(L.ef_gram_center_work_bytes(n), 16), dtype=torch.uint8, device="cuda")
+        ef._lib.check(L.ef_gram_center_device(G.data_ptr(), n, side, cs.data_ptr(), N, 1.0 / (N - 1), Cc.data_ptr(),
+                                              work.data_ptr(), _stream(torch)), "center")
+        Xc = X.astype(np.float64) - X.astype(np.float64).mean(0)
+        ref = (Xc @ Xc.T if side == 0 else Xc.T @ Xc) / (N - 1)
+        np.testing.assert_allclose(Cc.cpu().numpy(), ref, rtol=1e-10, atol=1e-8)
+
+
+def test_match_kernels_sharded_equals_whole():
+    """Sharded gallery: per-shard top-1 + reduce == whole-gallery argmax (ties -> lowest global index)."""
+    torch = require_gpu()
+    L = ef._lib.lib()
+    rng = np.random.default_rng(7)
+    n, k, B = 5000, 24, 77
+    G = rng.normal(size=(n, k)); G[4000] = G[100]; G[4999] = G[100]       # duplicates across shards
+    P = np.concatenate([G[rng.integers(0, n, B - 1)] + 0.01 * rng.normal(size=(B - 1, k)), G[100:101]])
+    g = torch.from_numpy(G).cuda(); p = torch.from_numpy(P).cuda()
+    for metric in (ef.METRIC_COSINE_SK, ef.METRIC_COSINE_G1, ef.METRIC_L2):
+        results = []
+        for R in (1, 3):
+            scores = torch.empty((R, B), dtype=torch.float64, device="cuda")
+            idxs = torch.empty((R, B), dtype=torch.int64, device="cuda")
+            bounds = np.linspace(0, n, R + 1).astype(int)
+            for r in range(R):
+                lo, hi = int(bounds[r]), int(bounds[r + 1])
+                gp = torch.empty((hi - lo, k), dtype=torch.float64, device="cuda")
+                gn = torch.empty(hi - lo, dtype=torch.float64, device="cuda")
+                ef._lib.check(L.ef_gallery_prepare_device(g[lo:hi].data_ptr(), k, hi - lo, k, metric, gp.data_ptr(), k,
+                                                          gn.data_ptr(), _stream(torch)), "prepare")
+                work = torch.empty(L.ef_match_work_bytes(B, hi - lo) + 16, dtype=torch.uint8, device="cuda")
+                ef._lib.check(L.ef_match_device(p.data_ptr(), k, B, k, gp.data_ptr(), k, gn.data_ptr(), hi - lo, lo, metric,
+                                                scores[r].data_ptr(), idxs[r].data_ptr(), work.data_ptr(), _stream(torch)), "match")
+            bs = torch.empty(B, dtype=torch.float64, device="cuda"); bi = torch.empty(B, dtype=torch.int64, device="cuda")
+            ef._lib.check(L.ef_match_reduce_device(scores.data_ptr(), idxs.data_ptr(), R, B, metric, bs.data_ptr(),
+                                                   bi.data_ptr(), _stream(torch)), "reduce")
+            results.append((bs.cpu().numpy(), bi.cpu().numpy()))
+        assert np.array_equal(results[0][1], results[1][1])
+        np.testing.assert_allclose(results[0][0], results[1][0], rtol=1e-13)
+        if metric == ef.METRIC_L2:
+            d2 = ((P[:, None, :] - G[None]) ** 2).sum(-1)
+            assert np.array_equal(results[0][1], d2.argmin(1))
+        else:
+            Pn = P / np.linalg.norm(P, axis=1, keepdims=True); Gn = G / np.linalg.norm(G, axis=1, keepdims=True)
+            assert np.array_equal(results[0][1], (Pn @ Gn.T).argmax(1))
+        assert results[0][1][-1] == 100                                   # three identical rows: lowest index wins

@@ -1,0 +1,254 @@
+"""K2 parity: projection + nearest-gallery match through the C ABI against the oracle and the reference goldens.
+
+Bars (BASELINE.json north_star): identity labels / arg-best indices bit exact; projections and scores within a
+stated float tolerance (float64-equivalent path, S = 8 digit planes): |dp| <= 1e-9 * max(1, |p|), |dscore| <= 1e-12.
+"""
+import numpy as np
+import pytest
+
+import eigenfaces_b200 as ef
+from gpu_util import face_like, require_gpu
+from oracle import extras, gen1, gen2, preprocess
+
+pytestmark = pytest.mark.gpu
+
+PROJ_RTOL = 1e-9
+SCORE_ATOL = 1e-12
+
+
+def _close_proj(got, want):
+    np.testing.assert_allclose(got, want, rtol=PROJ_RTOL, atol=PROJ_RTOL)
+
+
+# ------------------------------------------------------------------------------------------------ Gen-1
+def test_gen1_reference_golden(golden, light_model, dark_model):
+    require_gpu()
+    g = golden("gen1_recog.npz")
+    Q, thr = g["queries_u8"], float(g["threshold"])
+    sign = np.sign(np.sum(light_model["projected_data"] * golden("gen1_light.npz")["pkl_projected"], axis=0))
+    _, sl, rl, res = ef.gen1.recognize_faces(Q, light_model, thr)
+    _, sd, rd, _ = ef.gen1.recognize_faces(Q, dark_model, thr)
+    np.testing.assert_allclose(res.features * sign, g["ref_proj_light"], rtol=1e-8, atol=1e-8)
+    np.testing.assert_allclose(sl, g["ref_sim_light"], atol=SCORE_ATOL)
+    np.testing.assert_allclose(sd, g["ref_sim_dark"], atol=SCORE_ATOL)
+    names, best, rec, _, _ = ef.gen1.recognize_faces_dual_model(Q, dark_model, light_model, thr)
+    np.testing.assert_allclose(best, g["ref_dual_best"], atol=SCORE_ATOL)
+    assert np.array_equal(rec, g["ref_dual_recognized"])
+    decided = np.abs(g["ref_sim_light"] - g["ref_sim_dark"]) > 1e-12
+    assert np.array_equal((names == "Joseph_Lai_dark")[decided], g["ref_dual_name_is_dark"][decided])
+    # single-crop signatures of the reference
+    name, s, ok = ef.gen1.recognize_face(Q[17].astype(np.float64), light_model, thr)
+    assert name == "Joseph_Lai" and abs(s - g["ref_sim_light"][17]) < SCORE_ATOL and ok == bool(s >= thr)
+    p = ef.gen1.project_face_to_eigenspace(Q[3].astype(np.float64), light_model["eigenfaces"], light_model["mean_face"])
+    _close_proj(p, gen1.project_face_to_eigenspace(Q[3].astype(np.float64), light_model["eigenfaces"], light_model["mean_face"]))
+
+
+@pytest.mark.parametrize("use_tc", [False, True])
+def test_gen1_batch_vs_oracle(golden, light_model, use_tc):
+    require_gpu()
+    X = golden("gen1_light.npz")["X_u8"]
+    rng = np.random.default_rng(1)
+    Q = np.concatenate([X, face_like(rng, X, 300), rng.integers(0, 256, (55, 10000), dtype=np.uint8)])
+    rec = ef.gen1.recognizer_for(light_model)
+    rec.use_tensor_cores(use_tc)
+    res = rec.recognize(Q, 0.8)
+    rec.use_tensor_cores(True)
+    want_p = gen1.project_batch(Q, light_model["eigenfaces"], light_model["mean_face"])
+    _close_proj(res.features, want_p)
+    best, idx, ok = gen1.recognize_batch(Q, light_model, 0.8)
+    np.testing.assert_allclose(res.score, best, atol=SCORE_ATOL)
+    sims = gen1.cosine_matrix(want_p, light_model["projected_data"])
+    # arg-best: identical wherever the reference's own top-2 margin is above its rounding noise
+    srt = np.sort(sims, axis=1)
+    decided = (srt[:, -1] - srt[:, -2]) > 1e-13
+    assert decided.mean() > 0.5
+    assert np.array_equal(res.index[decided], idx[decided])
+    assert np.array_equal(res.label >= 0, ok)
+    # residual: distance from face space, textbook form
+    want_r = extras.reconstruction_error2(Q.astype(np.float64) - light_model["mean_face"], light_model["eigenfaces"])
+    np.testing.assert_allclose(res.resid2, want_r, rtol=1e-9, atol=1e-6)
+
+
+def test_gen1_self_match_duplicates_lowest_index(light_model, golden):
+    """Every training crop returns its own gallery row, except exact duplicates where the LOWEST row wins
+    (np.argmax rule; SURVEY.md section 8c golden 6)."""
+    require_gpu()
+    Q = golden("gen1_light.npz")["X_u8"]
+    rng = np.random.default_rng(2)
+    G = light_model["projected_data"].copy()
+    dup_src = rng.choice(len(G), 20, replace=False)
+    dup_dst = rng.choice(np.setdiff1d(np.arange(len(G)), dup_src), 20, replace=False)
+    G[dup_dst] = G[dup_src]
+    rec = ef.Recognizer(light_model["eigenfaces"], light_model["mean_face"], G, metric=ef.METRIC_COSINE_G1)
+    res = rec.recognize(Q, 0.0)
+    sims = gen1.cosine_matrix(gen1.project_batch(Q, light_model["eigenfaces"], light_model["mean_face"]), G)
+    want = np.argmax(sims, axis=1)
+    srt = np.sort(sims, axis=1)
+    clear = (srt[:, -1] - srt[:, -2]) > 1e-13
+    assert np.array_equal(res.index[clear], want[clear])
+    for s, d in zip(dup_src, dup_dst):
+        assert res.index[s] == min(s, d)
+        assert not (res.index == max(s, d)).any(), "a duplicated gallery row must never beat its lower-index twin"
+    untouched = np.setdiff1d(np.arange(len(G)), np.concatenate([dup_src, dup_dst]))
+    assert np.array_equal(res.index[untouched][clear[untouched]], untouched[clear[untouched]])
+
+
+def test_gen1_slices_tolerance(light_model, golden):
+    """Fewer digit planes trade accuracy for tensor work: S=4 is float32-class, S=8 float64-class."""
+    require_gpu()
+    X = golden("gen1_light.npz")["X_u8"][:64]
+    want = gen1.project_batch(X, light_model["eigenfaces"], light_model["mean_face"])
+    for S, tol in ((3, 2e-2), (4, 2e-4), (6, 1e-8), (8, 1e-9)):
+        rec = ef.Recognizer(light_model["eigenfaces"], light_model["mean_face"], light_model["projected_data"],
+                            metric=ef.METRIC_COSINE_G1, n_slices=S)
+        got = rec.recognize(X, 0.8).features
+        assert np.abs(got - want).max() <= tol * max(1.0, np.abs(want).max() / 1e3), f"S={S}"
+
+
+def test_l2_metric_and_edge_batches(light_model, golden):
+    require_gpu()
+    X = golden("gen1_light.npz")["X_u8"]
+    rec = ef.Recognizer(light_model["eigenfaces"], light_model["mean_face"], light_model["projected_data"],
+                        metric=ef.METRIC_L2)
+    rng = np.random.default_rng(3)
+    Q = face_like(rng, X, 130, noise=12.0)
+    res = rec.recognize(Q, 1e12)
+    p = gen1.project_batch(Q, light_model["eigenfaces"], light_model["mean_face"])
+    d2, idx = extras.l2_nearest(p, light_model["projected_data"])
+    assert np.array_equal(res.index, idx)
+    np.testing.assert_allclose(res.score, d2, rtol=1e-9, atol=1e-6)
+    # ragged / tiny batches
+    for B in (0, 1, 31, 33, 129):
+        r = rec.recognize(Q[:B], 1e12)
+        assert r.index.shape == (B,) and np.array_equal(r.index, idx[:B])
+    # zero query under the Gen-1 cosine rule: similarity 0.0 (useless/scan.py:73-74)
+    rec_c = ef.gen1.recognizer_for(light_model)
+    mean_img = np.clip(np.rint(light_model["mean_face"]), 0, 255).astype(np.uint8)[None]
+    r = rec_c.recognize(mean_img, 0.8)
+    assert r.score[0] <= 1.0 and r.label[0] == -1 or r.score[0] >= 0.8
+
+
+# ------------------------------------------------------------------------------------------------ Gen-2
+def _gen2_model_dict(g, person):
+    from sklearn.decomposition import PCA
+    from sklearn.preprocessing import StandardScaler
+    pca = PCA(n_components=len(g[f"{person}_components"]))
+    pca.components_, pca.mean_ = g[f"{person}_components"], g[f"{person}_pca_mean"]
+    pca.explained_variance_ = g[f"{person}_explained_variance"]
+    pca.whiten = False
+    sc = StandardScaler()
+    sc.mean_, sc.scale_, sc.var_ = g[f"{person}_scaler_mean"], g[f"{person}_scaler_scale"], g[f"{person}_scaler_var"]
+    return dict(pca=pca, scaler=sc, face_features=g[f"{person}_face_features"],
+                face_labels=g[f"{person}_face_labels"], person_id_map={person: 0}, n_components=20,
+                mean_face=g[f"{person}_mean_face"], eigenfaces=pca.components_, face_shape=(64, 64))
+
+
+def test_gen2_reference_golden(golden):
+    require_gpu()
+    g = golden("gen2_recog.npz")
+    persons = [str(p) for p in g["persons"]]
+    scanner = ef.gen2.MultiModelFaceScanner()
+    for p in persons:
+        scanner.models[p] = {"model_data": _gen2_model_dict(g, p)}
+    for i in range(int(g["n_crops"])):
+        crop = g[f"crop_{i:02d}"]
+        for j, p in enumerate(persons):
+            md = scanner.models[p]["model_data"]
+            f = scanner.extract_face_features(crop, md)
+            np.testing.assert_allclose(f, g["ref_features"][i, j], rtol=1e-9, atol=1e-8)
+            pid, name, sim = scanner.recognize_face_with_model(f, md, 0.7)
+            assert int(pid) == int(g["ref_single_pid"][i, j]) and name == str(g["ref_single_name"][i, j])
+            assert abs(sim - g["ref_single_sim"][i, j]) < SCORE_ATOL
+        pid, name, conf = scanner.recognize_face_all_models(crop, 0.8)
+        assert int(pid) == int(g["ref_multi_pid"][i]) and name == str(g["ref_multi_name"][i])
+        assert abs(conf - g["ref_multi_conf"][i]) < SCORE_ATOL
+
+
+def test_gen2_shipped_pickle_labels_bit_exact(golden):
+    """The reference's one shipped Gen-2 pickle (float32 arrays, k=76, 77 faces): labels and arg-max rows equal the
+    reference's arithmetic exactly; features within tolerance."""
+    require_gpu()
+    g = golden("gen2_shipped.npz")
+    rec = ef.Recognizer(g["components"], g["scaler_mean"], g["face_features"], scale=g["scaler_scale"],
+                        pca_mean=g["pca_mean"], labels=g["face_labels"], metric=ef.METRIC_COSINE_SK,
+                        basis_is_components=True)
+    res = rec.recognize(g["X_u8"], 0.7)
+    assert np.array_equal(res.index, g["ref_argmax"])
+    assert np.array_equal(res.label, g["ref_pid"])
+    np.testing.assert_allclose(res.score, g["ref_sim"], atol=SCORE_ATOL)
+    np.testing.assert_allclose(res.features, g["ref_features"], rtol=1e-9, atol=1e-7)
+    m = dict(scaler_mean=g["scaler_mean"], scaler_scale=g["scaler_scale"], components=g["components"].astype(np.float64),
+             pca_mean=g["pca_mean"].astype(np.float64))
+    z = gen2.scaler_transform(g["X_u8"], m["scaler_mean"], m["scaler_scale"]) - m["pca_mean"]
+    want_r = extras.reconstruction_error2(z, m["components"].T)
+    np.testing.assert_allclose(res.resid2, want_r, rtol=1e-8, atol=1e-6)
+
+
+def test_gen2_full_k_model_vs_oracle(golden):
+    """train-v5 sets k = N (178): wide basis (NC = 8 * 179 digit-plane columns) through several N tiles."""
+    require_gpu()
+    X = golden("gen2_joseph.npz")["X_u8"]
+    fit = gen2.train_pca_model(X, 178)
+    rec = ef.Recognizer(fit["eigenfaces"], fit["scaler_mean"], fit["face_features"], scale=fit["scaler_scale"],
+                        pca_mean=fit["pca_mean"], labels=np.zeros(178, np.int32), metric=ef.METRIC_COSINE_SK,
+                        basis_is_components=True)
+    rng = np.random.default_rng(8)
+    Q = np.concatenate([X, face_like(rng, X, 100)])
+    res = rec.recognize(Q, 0.7)
+    m = dict(scaler_mean=fit["scaler_mean"], scaler_scale=fit["scaler_scale"], components=fit["eigenfaces"],
+             pca_mean=fit["pca_mean"], face_features=fit["face_features"], face_labels=np.zeros(178, int))
+    want = gen2.extract_features(Q, m["scaler_mean"], m["scaler_scale"], m["components"], m["pca_mean"])
+    np.testing.assert_allclose(res.features, want, rtol=1e-9, atol=1e-8)
+    best, idx, labels = gen2.recognize_batch(Q, m, 0.7)
+    np.testing.assert_allclose(res.score, best, atol=SCORE_ATOL)
+    sims = gen2.sk_cosine_similarity(want, m["face_features"])
+    srt = np.sort(sims, axis=1)
+    decided = (srt[:, -1] - srt[:, -2]) > 1e-13
+    assert np.array_equal(res.index[decided], idx[decided])
+    assert np.array_equal(res.label, labels)
+    assert np.array_equal(res.index[:178][decided[:178]], np.arange(178)[decided[:178]])   # self match
+
+
+def test_device_buffers_match_host_buffers(light_model, golden):
+    torch = require_gpu()
+    X = golden("gen1_light.npz")["X_u8"][:100]
+    rec = ef.gen1.recognizer_for(light_model)
+    host = rec.recognize(X, 0.8)
+    xd = torch.zeros((100, 10112), dtype=torch.uint8, device="cuda")
+    xd[:, :10000] = torch.from_numpy(X).cuda()
+    out = rec.recognize_device(xd, 0.8)
+    torch.cuda.synchronize()
+    assert np.array_equal(out["features"].cpu().numpy(), host.features)
+    assert np.array_equal(out["score"].cpu().numpy(), host.score)
+    assert np.array_equal(out["index"].cpu().numpy(), host.index)
+    assert np.array_equal(out["label"].cpu().numpy(), host.label)
+    assert np.array_equal(out["resid2"].cpu().numpy(), host.resid2)
+
+
+def test_baseline_config2_full_size_properties(light_model):
+    """BASELINE config 2 at full size (B=4096, D=10000, k=10, Ng=1024): size-independent properties --
+    linearity of the integer projection in the basis planes, permutation equivariance, determinism."""
+    require_gpu()
+    rng = np.random.default_rng(20250820)
+    E = np.asfortranarray(light_model["eigenfaces"][:, :10])
+    mu = light_model["mean_face"]
+    lam = light_model["eigenvalues"][:10]
+    G = rng.normal(0, 1, (1024, 10)) * np.sqrt(lam)
+    labels = (np.arange(1024) % 4).astype(np.int32)
+    rec = ef.Recognizer(E, mu, G, labels=labels, metric=ef.METRIC_COSINE_G1)
+    c = rng.normal(0, 1, (4096, 10)) * np.sqrt(lam)
+    Q = np.clip(np.rint(mu + c @ E.T + rng.normal(0, 8, (4096, 10000))), 0, 255).astype(np.uint8)
+    r1 = rec.recognize(Q, 0.5)
+    r2 = rec.recognize(Q, 0.5)
+    assert np.array_equal(r1.features, r2.features) and np.array_equal(r1.index, r2.index)      # deterministic
+    perm = rng.permutation(4096)
+    r3 = rec.recognize(Q[perm], 0.5)
+    assert np.array_equal(r3.features, r1.features[perm]) and np.array_equal(r3.index, r1.index[perm])
+    sub = rng.choice(4096, 256, replace=False)
+    want_p = gen1.project_batch(Q[sub], E, mu)
+    _close_proj(r1.features[sub], want_p)
+    sims = gen1.cosine_matrix(want_p, G)
+    assert np.array_equal(r1.index[sub], np.argmax(sims, axis=1))
+    assert np.array_equal(r1.label[sub], np.where(sims.max(1) >= 0.5, labels[np.argmax(sims, 1)], -1))
+    # the planted coefficients are recovered: projections correlate with c
+    assert np.corrcoef(r1.features[:, 0], c[:, 0])[0, 1] > 0.99
