@@ -264,7 +264,7 @@ def run_ours(args, rank, world):
     for i in range(max(args.warmup, 3)):
         rec.recognize(host_batches[i % 2], THRESHOLD, want_features=False)
     barrier()
-    e2e_steps = max(1, min(args.steps, 200))
+    e2e_steps = max(1, min(args.steps, 200)) if not args.profile else 1
     t0 = time.perf_counter()
     for i in range(e2e_steps):
         r = rec.recognize(host_batches[i % 2], THRESHOLD, want_features=False)
@@ -276,7 +276,7 @@ def run_ours(args, rank, world):
     # ---- post-roll under the same load so that nvidia-smi gets samples even when the timed region is short
     t_roll = time.perf_counter()
     i = 0
-    while time.perf_counter() - t_roll < 1.5:
+    while time.perf_counter() - t_roll < (0.0 if args.profile else 1.5):
         step(i); i += 1
         if i % 64 == 0:
             torch.cuda.synchronize()
@@ -295,7 +295,7 @@ def run_ours(args, rank, world):
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
         achieved = ALGO_BYTES_PER_CROP * B / (proj_ms * 1e-3) / 1e9 if proj_ms > 0 else 0.0
         cpu = None
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not args.profile:
             model, lam_c, _ = cpu_port_setup()
             Q = host_batches[0]
             times = cpu_port_time(model, Q, 12.0)
@@ -338,6 +338,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile", action="store_true",
+                    help="short run for ncu: no CPU baseline, no clock post-roll, one e2e step (numbers are not bench values)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", 0))

@@ -110,6 +110,7 @@ struct JacobiCtl {
   int sweeps;
   int converged;
   double off_final;
+  double fro;                  // Frobenius norm of A (invariant under the rotations): the scale of the stopping test
 };
 
 __device__ __forceinline__ bool grid_barrier(JacobiCtl* ctl, unsigned int target) {
@@ -159,7 +160,8 @@ jacobi_kernel(double* __restrict__ Bt, double* __restrict__ Vt, int n, int ld, J
   const int players = 2 * np;
   const int tid = threadIdx.x;
   unsigned int target = 0;
-  const double rot_tol = tol * 0.125;
+  const double rot_tol = tol * 0.25;
+  const double fro = ctl->fro;
 
   for (int sweep = 0; sweep < max_sweeps; ++sweep) {
     double local_off = 0.0;
@@ -180,8 +182,12 @@ jacobi_kernel(double* __restrict__ Bt, double* __restrict__ Vt, int n, int ld, J
           gamma = fma(x, y, gamma);
         }
         alpha = block_sum3(alpha, beta, gamma, red, beta, gamma);
-        const double denom = sqrt(alpha) * sqrt(beta);
-        if (!(denom > 0.0)) continue;
+        // gamma = (V^T A^2 V)_pq ~ (lambda_p + lambda_q) E_pq with E = offdiag(V^T A V): the pair is converged when
+        // |E_pq| <= tol * |A|_F, the absolute (norm-wise backward stable) criterion LAPACK's eigh meets too.
+        // A relative test |gamma| <= tol sqrt(alpha beta) cannot be met for the numerically null directions of a
+        // centred Gram matrix, whose columns of B = A V are rounding noise.
+        const double denom = (sqrt(alpha) + sqrt(beta)) * fro;
+        if (!(denom > 0.0) || gamma == 0.0) continue;
         const double off = fabs(gamma) / denom;
         local_off = fmax(local_off, off);
         if (off <= rot_tol) continue;
@@ -221,6 +227,21 @@ jacobi_kernel(double* __restrict__ Bt, double* __restrict__ Vt, int n, int ld, J
     if (off <= tol) return;
     target += gridDim.x;
     if (!grid_barrier(ctl, target)) return;   // reset visible before the next sweep's atomicMax
+  }
+}
+
+// |A|_F with a fixed summation order (one CTA), so that the stopping threshold is bit-reproducible
+__global__ void jacobi_fro_kernel(const double* __restrict__ A, int64_t count, JacobiCtl* ctl) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = threadIdx.x; i < count; i += blockDim.x) s = fma(A[i], A[i], s);
+  s = ef::warp_sum(s);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += red[w];
+    ctl->fro = sqrt(t);
   }
 }
 
@@ -438,12 +459,13 @@ int ef_eigh_jacobi_device(double* A, int32_t n, double* evals, double* evecs, vo
   if (n > 4096) return EF_ERR_UNSUPPORTED;
   cudaStream_t st = ef::as_stream(stream);
   if (max_sweeps <= 0) max_sweeps = 40;
-  if (!(tol > 0.0)) tol = 1e-14;
+  if (!(tol > 0.0)) tol = 1e-15;
   double* Vt = reinterpret_cast<double*>(work);
   double* lam = Vt + (size_t)n * n;
   JacobiCtl* ctl = reinterpret_cast<JacobiCtl*>(reinterpret_cast<char*>(work) +
                                                 ef::round_up(sizeof(double) * ((size_t)n * n + n), 128));
   EF_LAUNCH(jacobi_init_kernel, (unsigned)ef::ceil_div((int64_t)n * n, 256), 256, 0, st, Vt, n, n, ctl);
+  EF_LAUNCH(jacobi_fro_kernel, 1, 1024, 0, st, A, (int64_t)n * n, ctl);
   if (n > 1) {
     int per_sm = 0;
     EF_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jacobi_kernel, 128, 0));

@@ -256,6 +256,7 @@ int ef_model_reserve(ef_model_t* m, int32_t max_batch) {
 
 int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
                               const ef_result_t* out, ef_stream_t stream) {
+  if (m && B == 0) return EF_OK;
   if (!m || !x || !out || B < 0 || ldx < m->D) return EF_ERR_INVALID;
   if ((ldx & 15) || (reinterpret_cast<uintptr_t>(x) & 15)) return EF_ERR_INVALID;
   if (out->resid2 && !m->with_residual) return EF_ERR_INVALID;
@@ -323,6 +324,7 @@ static int copy_results_back(ef_model_t* m, int32_t B, const ef_result_t* out, c
 
 int ef_model_recognize_host(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
                             const ef_result_t* out) {
+  if (m && B == 0) return EF_OK;
   if (!m || !x || !out || B < 0 || ldx < m->D) return EF_ERR_INVALID;
   if (out->resid2 && !m->with_residual) return EF_ERR_INVALID;
   if (B == 0) return EF_OK;

@@ -133,6 +133,7 @@ extern "C" int ef_preprocess(const uint8_t* frames, int64_t frame_stride, int32_
                              int32_t height, int32_t channels, int32_t n_frames, const ef_box_t* boxes,
                              int32_t n_boxes, int32_t dw, int32_t dh, uint8_t* out, int64_t out_stride,
                              int32_t* bad_boxes, ef_stream_t stream) {
+  if (n_boxes == 0) return EF_OK;
   if (!frames || !boxes || !out) return EF_ERR_INVALID;
   if (n_boxes < 0 || width <= 0 || height <= 0 || n_frames <= 0 || dw <= 0 || dh <= 0) return EF_ERR_INVALID;
   if (channels != 1 && channels != 3) return EF_ERR_INVALID;

@@ -106,7 +106,8 @@ class Recognizer:
         label = np.empty(B, dtype=np.int32)
         resid = np.empty(B, dtype=np.float64) if want_residual else None
         res = Result(_ptr(feats), _ptr(score), _ptr(index), _ptr(label), _ptr(resid))
-        check(self._L.ef_model_recognize_host(self._h, _ptr(x), x.strides[0], B, float(threshold), C.byref(res)),
+        ldx = x.strides[0] if B > 1 else self.D          # numpy gives length-1 axes arbitrary strides
+        check(self._L.ef_model_recognize_host(self._h, _ptr(x), ldx, B, float(threshold), C.byref(res)),
               "ef_model_recognize_host")
         return RecognitionResult(feats, score, index, label, resid)
 

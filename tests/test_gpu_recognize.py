@@ -86,11 +86,14 @@ def test_gen1_self_match_duplicates_lowest_index(light_model, golden):
     srt = np.sort(sims, axis=1)
     clear = (srt[:, -1] - srt[:, -2]) > 1e-13
     assert np.array_equal(res.index[clear], want[clear])
+    # expected row for a training crop = lowest index among the gallery rows identical to its own row
+    # (the shipped set itself contains exact duplicate crops, e.g. rows 74 and 131)
+    first_of = np.array([np.flatnonzero((G == G[i]).all(axis=1))[0] for i in range(len(G))])
     for s, d in zip(dup_src, dup_dst):
-        assert res.index[s] == min(s, d)
+        assert res.index[s] == first_of[s] <= min(s, d)
         assert not (res.index == max(s, d)).any(), "a duplicated gallery row must never beat its lower-index twin"
-    untouched = np.setdiff1d(np.arange(len(G)), np.concatenate([dup_src, dup_dst]))
-    assert np.array_equal(res.index[untouched][clear[untouched]], untouched[clear[untouched]])
+    untouched = np.setdiff1d(np.arange(len(G)), dup_dst)
+    assert np.array_equal(res.index[untouched], first_of[untouched])
 
 
 def test_gen1_slices_tolerance(light_model, golden):
@@ -181,7 +184,13 @@ def test_gen2_shipped_pickle_labels_bit_exact(golden):
              pca_mean=g["pca_mean"].astype(np.float64))
     z = gen2.scaler_transform(g["X_u8"], m["scaler_mean"], m["scaler_scale"]) - m["pca_mean"]
     want_r = extras.reconstruction_error2(z, m["components"].T)
-    np.testing.assert_allclose(res.resid2, want_r, rtol=1e-8, atol=1e-6)
+    # |z|^2 - |p|^2 equals the direct form only up to the orthonormality defect of the basis; this pickle stores
+    # float32 components (defect ~1e-7), so the two textbook forms differ by ~1e-7 |z|^2 (unpinned extra, X1).
+    E = m["components"]
+    defect = np.abs(E @ E.T - np.eye(len(E))).max()
+    znorm2 = np.einsum('ij,ij->i', z, z)
+    assert 1e-9 < defect < 1e-5
+    assert np.all(np.abs(res.resid2 - want_r) <= 4 * len(E) * defect * znorm2)
 
 
 def test_gen2_full_k_model_vs_oracle(golden):
