@@ -57,6 +57,7 @@ SIGNATURES = {
     "ef_model_reserve": (C.c_int, [c_void, c_i32]),
     "ef_model_dims": (C.c_int, [c_void, p_i32, p_i32, p_i32, p_i32]),
     "ef_model_set_tensor_cores": (C.c_int, [c_void, c_i32]),
+    "ef_model_status": (C.c_int, [c_void, p_i32]),
     "ef_model_kernel_timing": (C.c_int, [c_void, c_i32]),
     "ef_model_kernel_timing_read": (C.c_int, [c_void, p_i32, p_dbl, p_i32]),
     "ef_model_recognize_device": (C.c_int, [c_void, c_void, c_i64, c_i32, c_dbl, C.POINTER(Result), c_void]),

@@ -6,18 +6,28 @@
 
 namespace ef {
 
-// ef_project.cu -- CUDA-core exact-integer projection
-int project_dp4a(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int32_t* acc,
+// Accumulator convention shared by all projection / epilogue kernels: int32 acc_t[NC][ld_acc] (plane-major, crop b in
+// column b), all zero on entry to a projection kernel, consumed AND cleared by the epilogue kernels.
+
+// ef_project.cu -- CUDA-core exact-integer projection (reference implementation of the integer semantics)
+int project_dp4a(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int32_t* acc_t,
                  int ld_acc, cudaStream_t stream);
-int project_finalize(const int32_t* acc, int ld_acc, int B, int k, int kq, int S, const int32_t* col_exp,
-                     const double* bias, double* proj, int64_t ldp, const double* sumsq, double c0, double* resid2,
-                     cudaStream_t stream);
 int row_sumsq(const uint8_t* X, int64_t ldx, int B, int D, const double* qq, double* out, cudaStream_t stream);
 
-// ef_project_tc.cu -- tcgen05 kind::i8 projection (same integers as project_dp4a)
-bool project_tc_supported(int B, int D, int NC);
-int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int32_t* acc,
-               int ld_acc, cudaStream_t stream);
+// ef_project_tc.cu -- tcgen05 kind::i8 projection (same integers as project_dp4a); sumsq (may be null) receives
+// += sum_d x^2 per crop.  Returns EF_ERR_UNSUPPORTED when the buffers do not meet the TMA alignment rules.
+int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int wq_rows,
+               int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream);
+
+// ef_epilogue.cu
+bool fused_epilogue_supported(int k, int64_t n);
+int fused_epilogue(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, const int32_t* col_exp, const double* bias,
+                   double* sumsq, double c0, const double* gp, const double* gnorm, int64_t n, const int32_t* labels,
+                   int metric, double threshold, double* out_proj, double* out_score, int32_t* out_index,
+                   int32_t* out_label, double* out_resid, cudaStream_t stream);
+int project_finalize(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, const int32_t* col_exp,
+                     const double* bias, double* proj, int64_t ldp, double* sumsq, double c0, double* resid2,
+                     cudaStream_t stream);
 
 // ef_match.cu
 // Gallery preparation: gn[j][:] = g[j][:] / |g_j| (COSINE_SK), copy + norms (COSINE_G1), copy (L2).

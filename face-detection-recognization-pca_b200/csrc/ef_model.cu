@@ -23,7 +23,9 @@ struct ef_model {
   ef::DevBuf wq, col_exp, bias, qq, gp, gnorm, labels;
   // workspaces (sized by reserve)
   int reserved = 0;
-  ef::DevBuf acc, proj, sumsq, score, index64, match_work;
+  ef::DevBuf acc, proj, sumsq, score, index64, match_work, status;
+  int nc_pad = 0;
+  bool dirty = false;
   // host-path staging
   int host_reserved = 0;
   ef::DevBuf x_dev, resid_dev, index32_dev, label_dev, frames_dev, boxes_dev, bad_dev;
@@ -103,7 +105,7 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
   m->n_gallery = desc->n_gallery;
   m->ldw = ef::round_up(D, 128);
   const int nc_pad = (int)ef::round_up(m->NC, 16);
-  m->ld_acc = nc_pad;
+  m->nc_pad = nc_pad;
 
   // ---- host-side preparation (float64, exact digit extraction)
   std::vector<double> t(D), inv_s(D, 1.0);
@@ -243,10 +245,17 @@ int ef_model_kernel_timing_read(ef_model_t* m, int32_t* n_calls, double* project
 int ef_model_reserve(ef_model_t* m, int32_t max_batch) {
   if (!m || max_batch <= 0) return EF_ERR_INVALID;
   if (max_batch <= m->reserved) return EF_OK;
-  const size_t B = (size_t)max_batch;
-  EF_TRY(m->acc.ensure(sizeof(int32_t) * B * m->ld_acc));
+  const size_t B = (size_t)ef::round_up(max_batch, 128);
+  m->ld_acc = (int)B;
+  // plane-major accumulators and the sum-of-squares buffer start out zero; the epilogue kernels keep them zero
+  EF_TRY(m->acc.ensure(sizeof(int32_t) * B * m->nc_pad));
+  EF_CUDA(cudaMemset(m->acc.p, 0, sizeof(int32_t) * B * m->nc_pad));
   EF_TRY(m->proj.ensure(sizeof(double) * B * m->k));
   EF_TRY(m->sumsq.ensure(sizeof(double) * B));
+  EF_CUDA(cudaMemset(m->sumsq.p, 0, sizeof(double) * B));
+  EF_TRY(m->status.ensure(16));
+  EF_CUDA(cudaMemset(m->status.p, 0, 16));
+  m->dirty = false;
   EF_TRY(m->score.ensure(sizeof(double) * B));
   EF_TRY(m->index64.ensure(sizeof(int64_t) * B));
   EF_TRY(m->match_work.ensure(ef::match_work_bytes(max_batch, m->n_gallery) + 16));
@@ -273,28 +282,55 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
     m->ev_b.push_back(eb);
     EF_CUDA(cudaEventRecord(ea, st));
   }
-  m->last_used_tc = m->use_tc && ef::project_tc_supported(B, m->D, m->NC);
-  if (m->last_used_tc) {
-    EF_TRY(ef::project_tc(x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, acc, m->ld_acc, st));
-  } else {
+  if (!out->score || !out->index) return EF_ERR_INVALID;
+  if (m->dirty) {   // a previous call failed between projection and epilogue: restore the all-zero invariant
+    EF_CUDA(cudaMemsetAsync(acc, 0, sizeof(int32_t) * (size_t)m->ld_acc * m->nc_pad, st));
+    EF_CUDA(cudaMemsetAsync(m->sumsq.p, 0, sizeof(double) * (size_t)m->ld_acc, st));
+  }
+  m->dirty = true;
+  const bool want_resid = out->resid2 != nullptr;
+  double* sumsq = m->sumsq.as<double>();
+  // the tensor-core kernel also produces the integer sum of squares (Gen-1 residual) from the staged crop tiles
+  const bool tc_sumsq = want_resid && !m->has_scale;
+  int st_tc = EF_ERR_UNSUPPORTED;
+  if (m->use_tc)
+    st_tc = ef::project_tc(x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, m->nc_pad, acc, m->ld_acc,
+                           tc_sumsq ? sumsq : nullptr, m->status.as<int>(), st);
+  m->last_used_tc = st_tc == EF_OK;
+  if (st_tc != EF_OK) {
+    if (st_tc != EF_ERR_UNSUPPORTED) return st_tc;
     EF_TRY(ef::project_dp4a(x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, acc, m->ld_acc, st));
   }
   if (eb) EF_CUDA(cudaEventRecord(eb, st));
-  // 2. residual ingredients
-  const bool want_resid = out->resid2 != nullptr;
-  if (want_resid) EF_TRY(ef::row_sumsq(x, ldx, B, m->D, m->has_scale ? m->qq.as<double>() : nullptr,
-                                       m->sumsq.as<double>(), st));
-  // 3. planes -> float64 features (+ residual)
-  double* proj = out->proj ? out->proj : m->proj.as<double>();
-  EF_TRY(ef::project_finalize(acc, m->ld_acc, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(), m->bias.as<double>(),
-                              proj, m->k, m->sumsq.as<double>(), m->c0, want_resid ? out->resid2 : nullptr, st));
-  // 4. nearest gallery row
-  if (!out->score || !out->index) return EF_ERR_INVALID;
-  EF_TRY(ef::match(proj, m->k, B, m->k, m->gp.as<double>(), m->k, m->gnorm.as<double>(), m->n_gallery, 0, m->metric,
-                   out->score, m->index64.as<int64_t>(), m->match_work.p, st));
-  // 5. threshold + label
-  EF_TRY(ef::label_lookup(out->score, m->index64.as<int64_t>(), B, m->labels.p ? m->labels.as<int32_t>() : nullptr,
-                          m->metric, threshold, out->index, out->label, st));
+  // 2. residual ingredient not produced by the projection kernel (weighted for the standardised models)
+  if (want_resid && !(m->last_used_tc && tc_sumsq))
+    EF_TRY(ef::row_sumsq(x, ldx, B, m->D, m->has_scale ? m->qq.as<double>() : nullptr, sumsq, st));
+  const int32_t* labels = m->labels.p ? m->labels.as<int32_t>() : nullptr;
+  if (ef::fused_epilogue_supported(m->k, m->n_gallery)) {
+    // 3. one launch: planes -> features (+ residual) -> nearest gallery row -> threshold / label
+    EF_TRY(ef::fused_epilogue(acc, m->ld_acc, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(), m->bias.as<double>(),
+                              sumsq, m->c0, m->gp.as<double>(), m->gnorm.as<double>(), m->n_gallery, labels, m->metric,
+                              threshold, out->proj, out->score, out->index, out->label,
+                              want_resid ? out->resid2 : nullptr, st));
+  } else {
+    // 3. planes -> float64 features (+ residual); 4. nearest gallery row; 5. threshold + label
+    double* proj = out->proj ? out->proj : m->proj.as<double>();
+    EF_TRY(ef::project_finalize(acc, m->ld_acc, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(), m->bias.as<double>(),
+                                proj, m->k, sumsq, m->c0, want_resid ? out->resid2 : nullptr, st));
+    EF_TRY(ef::match(proj, m->k, B, m->k, m->gp.as<double>(), m->k, m->gnorm.as<double>(), m->n_gallery, 0, m->metric,
+                     out->score, m->index64.as<int64_t>(), m->match_work.p, st));
+    EF_TRY(ef::label_lookup(out->score, m->index64.as<int64_t>(), B, labels, m->metric, threshold, out->index,
+                            out->label, st));
+  }
+  m->dirty = false;
+  return EF_OK;
+}
+
+int ef_model_status(ef_model_t* m, int32_t* tc_pipeline_timeouts) {
+  if (!m || !tc_pipeline_timeouts) return EF_ERR_INVALID;
+  *tc_pipeline_timeouts = 0;
+  if (!m->status.p) return EF_OK;
+  EF_CUDA(cudaMemcpy(tc_pipeline_timeouts, m->status.p, sizeof(int32_t), cudaMemcpyDeviceToHost));
   return EF_OK;
 }
 
@@ -318,7 +354,13 @@ static int copy_results_back(ef_model_t* m, int32_t B, const ef_result_t* out, c
   if (out->index) EF_CUDA(cudaMemcpyAsync(out->index, dev.index, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
   if (out->label) EF_CUDA(cudaMemcpyAsync(out->label, dev.label, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
   if (out->resid2) EF_CUDA(cudaMemcpyAsync(out->resid2, dev.resid2, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
+  int32_t timeouts = 0;
+  EF_CUDA(cudaMemcpyAsync(&timeouts, m->status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   EF_CUDA(cudaStreamSynchronize(st));
+  if (timeouts) {
+    ef::set_error_detail("tcgen05 projection pipeline timed out (mbarrier wait > 2 s)", cudaErrorLaunchTimeout);
+    return EF_ERR_CUDA;
+  }
   return EF_OK;
 }
 

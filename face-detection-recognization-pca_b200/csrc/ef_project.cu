@@ -128,7 +128,7 @@ project_dp4a_kernel(const uint8_t* __restrict__ X, int64_t ldx, int B, int D, co
 #pragma unroll
     for (int j = 0; j < CN; ++j) {
       const int col = n0 + j * 16 + tx;
-      if (col < NC) atomicAdd(acc + (int64_t)row * ld_acc + col, accr[i][j]);
+      if (col < NC && accr[i][j] != 0) atomicAdd(acc + (int64_t)col * ld_acc + row, accr[i][j]);   // plane-major
     }
   }
 }
@@ -136,36 +136,7 @@ project_dp4a_kernel(const uint8_t* __restrict__ X, int64_t ldx, int B, int D, co
 // Combine the digit planes: P[b][c] = 2^e_c * sum_s acc[b][s*kq + c] * 2^-(7s+6) - bias[c]   (float64)
 // and, when the residual column is present (column k of every plane),
 //   resid2[b] = sumsq[b] - 2 * (x . u~) + c0 - |P_b|^2
-__global__ void finalize_kernel(const int32_t* __restrict__ acc, int ld_acc, int B, int k, int kq, int S,
-                                const int32_t* __restrict__ col_exp, const double* __restrict__ bias,
-                                double* __restrict__ proj, int64_t ldp, const double* __restrict__ sumsq, double c0,
-                                double* __restrict__ resid2) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= B) return;
-  const int32_t* a = acc + (int64_t)warp * ld_acc;
-  double norm2 = 0.0, xu = 0.0;
-  for (int c = lane; c < kq; c += 32) {
-    double v = 0.0;
-    for (int s = S - 1; s >= 0; --s) v += ldexp((double)a[s * kq + c], -(7 * s + 6));
-    v = ldexp(v, col_exp[c]);
-    if (c < k) {
-      v -= bias[c];
-      proj[(int64_t)warp * ldp + c] = v;
-      norm2 += v * v;
-    } else {
-      xu = v;  // the single residual column: x . u~
-    }
-  }
-  if (resid2) {
-    norm2 = ef::warp_sum(norm2);
-    xu = ef::warp_sum(xu);
-    if (lane == 0) {
-      const double r = sumsq[warp] - 2.0 * xu + c0 - norm2;
-      resid2[warp] = r > 0.0 ? r : 0.0;
-    }
-  }
-}
+// (the combination kernels live in ef_epilogue.cu)
 
 // sumsq[b] = sum_d x^2 * qq[d]  (qq == NULL: exact integer sum of squares)
 __global__ void rowsumsq_kernel(const uint8_t* __restrict__ X, int64_t ldx, int B, int D,
@@ -228,8 +199,7 @@ namespace ef {
 
 int project_dp4a(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int32_t* acc,
                  int ld_acc, cudaStream_t stream) {
-  if (B <= 0) return EF_OK;
-  EF_CUDA(cudaMemsetAsync(acc, 0, sizeof(int32_t) * (size_t)B * ld_acc, stream));
+  if (B <= 0) return EF_OK;   // acc (plane-major [NC][ld_acc]) must be zero on entry: the epilogue kernels clear it
   const int cn = (int)std::min<int64_t>(8, ceil_div(NC, 16));
   switch (cn) {
     case 1: return launch_dp4a<1>(X, ldx, B, D, Wq, ldw, NC, acc, ld_acc, stream);
@@ -241,17 +211,6 @@ int project_dp4a(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, 
     case 7: return launch_dp4a<7>(X, ldx, B, D, Wq, ldw, NC, acc, ld_acc, stream);
     default: return launch_dp4a<8>(X, ldx, B, D, Wq, ldw, NC, acc, ld_acc, stream);
   }
-}
-
-int project_finalize(const int32_t* acc, int ld_acc, int B, int k, int kq, int S, const int32_t* col_exp,
-                     const double* bias, double* proj, int64_t ldp, const double* sumsq, double c0, double* resid2,
-                     cudaStream_t stream) {
-  if (B <= 0) return EF_OK;
-  const int threads = 128;
-  const int grid = (int)ceil_div((int64_t)B * 32, threads);
-  EF_LAUNCH(finalize_kernel, grid, threads, 0, stream, acc, ld_acc, B, k, kq, S, col_exp, bias, proj, ldp, sumsq, c0,
-            resid2);
-  return EF_OK;
 }
 
 int row_sumsq(const uint8_t* X, int64_t ldx, int B, int D, const double* qq, double* out, cudaStream_t stream) {

@@ -1,14 +1,413 @@
-// K2a on tensor cores: tcgen05 kind::i8 (uint8 crops x int8 digit planes -> int32 in TMEM).
-// Placeholder until the tcgen05 kernel lands: reports "unsupported" so the dp4a path (same integers) is used.
+// K2a on tensor cores: the exact-integer digit-plane projection as a tcgen05 kind::i8 GEMM.
+//
+//   acc[n][b] += sum_d X[b][d] * Wq[n][d]      X: uint8 crops (A, K-major), Wq: int8 digit planes (B, K-major)
+//
+// Blackwell mapping (sm_100a):
+//   * operands are staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) straight from HBM/L2 into shared memory --
+//     the uint8 crops need no conversion pass, kind::i8 multiplies u8 x s8 into s32 exactly;
+//   * one elected thread issues tcgen05.mma (M = 128 crops, N = all digit-plane columns of the tile, K = 32 bytes per
+//     instruction), accumulators live in TMEM (up to 512 columns = 512 plane columns per pass over the crops);
+//   * stream-K: the (crop tile, k block) space is cut into one contiguous range per SM, so all 148 SMs stream HBM
+//     even though a 4096-crop batch has only 32 crop tiles; partial tiles are merged with int32 RED atomics, which
+//     is bit-reproducible because integer addition is associative;
+//   * the four epilogue warps are idle during the main loop, so they walk the same pipeline stages and compute the
+//     per-crop sum of squares (needed for the reconstruction error) from the crop tile already in shared memory --
+//     the crops are read from HBM exactly once;
+//   * accumulators are stored plane-major (acc[n][b]) so that the 32 lanes of an epilogue warp (32 consecutive crops)
+//     hit one 128-byte line per RED.
+// Every mbarrier wait is bounded (2 s): on a timeout the kernel raises a status flag and drains instead of hanging.
+#include <cuda.h>
+
 #include "ef_common.cuh"
 #include "ef_internal.cuh"
 
+namespace {
+
+constexpr int BLOCK_M = 128;                        // crops per tile (UMMA M, cta_group::1)
+constexpr int BLOCK_K = 128;                        // bytes of K per stage = one 128-byte swizzle row
+constexpr int UMMA_K = 32;                          // K per tcgen05.mma for 8-bit operands
+constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K;    // 16 KB
+constexpr int kThreads = 192;                       // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue
+constexpr int kMaxStages = 8;
+constexpr int kSmemLimit = 227 * 1024;
+constexpr unsigned long long kTimeoutNs = 2000000000ull;
+
+struct Shared {
+  unsigned long long full_bar[kMaxStages];
+  unsigned long long empty_bar[kMaxStages];
+  unsigned long long tmem_full_bar;
+  unsigned long long tmem_empty_bar;
+  uint32_t tmem_base;
+  int failed;
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ unsigned long long globaltimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: false on timeout or when another role already failed.
+__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t parity, volatile int* failed) {
+  if (mbar_try_wait(bar, parity)) return true;
+  const unsigned long long t0 = globaltimer();
+  while (!mbar_try_wait(bar, parity)) {
+    if (*failed) return false;
+    if (globaltimer() - t0 > kTimeoutNs) {
+      *failed = 1;
+      return false;
+    }
+  }
+  return true;
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c_inner,
+                                            int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], u8 x s8 -> s32
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                        uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 bytes, 8-row atoms 1024 bytes apart.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address,  bits [0,14)
+  d |= (uint64_t)1 << 16;                        // leading byte offset (unused with swizzle), bits [16,30)
+  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset = 8 rows * 128 B, bits [32,46)
+  d |= (uint64_t)1 << 46;                        // descriptor version for sm_100
+  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
+  return d;
+}
+
+// Instruction descriptor for kind::i8: D = s32, A = u8 (K-major), B = s8 (K-major), M = 128, N = n.
+__host__ __device__ constexpr uint32_t umma_idesc_i8(int n) {
+  return (2u << 4)                 // c_format = S32
+         | (0u << 7)               // a_format = unsigned 8-bit
+         | (1u << 10)              // b_format = signed 8-bit
+         | (0u << 15) | (0u << 16) // both K-major
+         | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+struct Args {
+  int B, NC, block_n, n_tiles, m_tiles, kb_total, stages, tmem_cols;
+  int box_rows, n_loads;     // TMA boxes per B stage
+  int umma_n, n_umma;        // tcgen05.mma instructions per K step
+  int ld_acc;
+  int32_t* acc_t;
+  double* sumsq;             // may be null
+  int* status;
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
+                  const Args a) {
+  extern __shared__ uint8_t smem_raw[];
+  // 1024-byte alignment is required by the 128-byte swizzle atoms
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_stage_bytes = a.block_n * BLOCK_K;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)a.stages * A_STAGE_BYTES;
+  Shared* sh = reinterpret_cast<Shared*>(sB + (size_t)a.stages * b_stage_bytes);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const bool do_sumsq = a.sumsq != nullptr;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&sh->full_bar[s], 1);
+      mbar_init(&sh->empty_bar[s], do_sumsq ? 5 : 1);     // MMA commit (+ one arrive per epilogue warp)
+    }
+    mbar_init(&sh->tmem_full_bar, 1);
+    mbar_init(&sh->tmem_empty_bar, 4);
+    sh->failed = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                 "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = sh->tmem_base;
+  volatile int* failed = &sh->failed;
+
+  // this CTA's contiguous range of (n tile, m tile, k block) units
+  const long long total_units = (long long)a.n_tiles * a.m_tiles * a.kb_total;
+  const long long u_begin = total_units * blockIdx.x / gridDim.x;
+  const long long u_end = total_units * (blockIdx.x + 1) / gridDim.x;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_x) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_w) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t stage_bytes = (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
+      bool ok = true;
+      for (long long u = u_begin; u < u_end && ok;) {
+        const long long tile = u / a.kb_total;
+        const int kb0 = (int)(u % a.kb_total);
+        const int kb1 = (int)min((long long)a.kb_total, kb0 + (u_end - u));
+        const int n_tile = (int)(tile / a.m_tiles), m_tile = (int)(tile % a.m_tiles);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (!mbar_wait(&sh->empty_bar[stage], phase ^ 1, failed)) { ok = false; break; }
+          mbar_arrive_expect_tx(&sh->full_bar[stage], stage_bytes);
+          tma_load_2d(sA + (size_t)stage * A_STAGE_BYTES, &tmap_x, &sh->full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
+          for (int l = 0; l < a.n_loads; ++l)
+            tma_load_2d(sB + (size_t)stage * b_stage_bytes + (size_t)l * a.box_rows * BLOCK_K, &tmap_w,
+                        &sh->full_bar[stage], kb * BLOCK_K, n_tile * a.block_n + l * a.box_rows);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        u += kb1 - kb0;
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      uint32_t seg = 0;
+      const uint32_t idesc = umma_idesc_i8(a.umma_n);
+      bool ok = true;
+      for (long long u = u_begin; u < u_end && ok; ++seg) {
+        const int kb0 = (int)(u % a.kb_total);
+        const int kb1 = (int)min((long long)a.kb_total, kb0 + (u_end - u));
+        if (!mbar_wait(&sh->tmem_empty_bar, (seg & 1) ^ 1, failed)) { ok = false; break; }
+        tc_fence_after();
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (!mbar_wait(&sh->full_bar[stage], phase, failed)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + (size_t)stage * b_stage_bytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            const uint64_t da = umma_desc_sw128(a_addr + k * UMMA_K);
+            for (int h = 0; h < a.n_umma; ++h) {
+              const uint64_t db = umma_desc_sw128(b_addr + h * a.umma_n * BLOCK_K + k * UMMA_K);
+              umma_i8(tmem_base + h * a.umma_n, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&sh->empty_bar[stage]);      // frees the stage once these MMAs have read it
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        if (!ok) break;
+        umma_commit(&sh->tmem_full_bar);           // accumulator of this segment is complete
+        u += kb1 - kb0;
+      }
+    }
+  } else {
+    // ===================================================================== epilogue warps (+ sum of squares)
+    const int lane_group = warp & 3;                       // TMEM lanes [32 g, 32 g + 32) are visible to this warp
+    const int row_in_tile = lane_group * 32 + lane;
+    int stage = 0;
+    uint32_t phase = 0;
+    uint32_t seg = 0;
+    bool ok = true;
+    for (long long u = u_begin; u < u_end && ok; ++seg) {
+      const long long tile = u / a.kb_total;
+      const int kb0 = (int)(u % a.kb_total);
+      const int kb1 = (int)min((long long)a.kb_total, kb0 + (u_end - u));
+      const int n_tile = (int)(tile / a.m_tiles), m_tile = (int)(tile % a.m_tiles);
+      const int row = m_tile * BLOCK_M + row_in_tile;
+      unsigned long long ssq = 0;
+      if (do_sumsq) {
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (!mbar_wait(&sh->full_bar[stage], phase, failed)) { ok = false; break; }
+          if (n_tile == 0) {
+            // the crop's 128 bytes of this K block sit in one swizzled 128-byte line; summing is order free.
+            const uint4* line = reinterpret_cast<const uint4*>(sA + (size_t)stage * A_STAGE_BYTES + row_in_tile * BLOCK_K);
+            unsigned int part = 0;                              // <= 128 * 255^2 per K block
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const uint4 v = line[(j + row_in_tile) & 7];      // rotate the chunk order: conflict-free banks
+              part = __dp4a(v.x, v.x, part);
+              part = __dp4a(v.y, v.y, part);
+              part = __dp4a(v.z, v.z, part);
+              part = __dp4a(v.w, v.w, part);
+            }
+            ssq += part;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sh->empty_bar[stage]);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        if (!ok) break;
+      }
+      if (!mbar_wait(&sh->tmem_full_bar, seg & 1, failed)) { ok = false; break; }
+      tc_fence_after();
+      for (int c0 = 0; c0 < a.block_n; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)c0, v);
+        if (row < a.B) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int col = n_tile * a.block_n + c0 + j;
+            if (col < a.NC && v[j] != 0u) atomicAdd(a.acc_t + (size_t)col * a.ld_acc + row, (int)v[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->tmem_empty_bar);
+      if (do_sumsq && n_tile == 0 && row < a.B && ssq != 0ull) atomicAdd(a.sumsq + row, (double)ssq);
+      u += kb1 - kb0;
+    }
+  }
+
+  // ----------------------------------------------------------------------------------------- teardown
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
+                 : "memory");
+  }
+  if (threadIdx.x == 0 && sh->failed) atomicExch(a.status, 1);
+}
+
+// --------------------------------------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+// 2-D byte tensor [rows][pitch] with box [box_rows][128 bytes], 128-byte swizzle, zero fill out of bounds.
+bool make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows, uint64_t pitch, uint32_t box_rows) {
+  EncodeTiledFn fn = encode_fn();
+  if (!fn) return false;
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {pitch};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return fn(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(base), dims, strides, box, estr,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace
+
 namespace ef {
 
-bool project_tc_supported(int, int, int) { return false; }
+int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int wq_rows,
+               int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream) {
+  if (B <= 0) return EF_OK;
+  if ((ldx & 15) || (reinterpret_cast<uintptr_t>(X) & 15) || (ldw & 15) || (reinterpret_cast<uintptr_t>(Wq) & 15))
+    return EF_ERR_UNSUPPORTED;
+  if (!encode_fn()) return EF_ERR_UNSUPPORTED;
 
-int project_tc(const uint8_t*, int64_t, int, int, const int8_t*, int64_t, int, int32_t*, int, cudaStream_t) {
-  return EF_ERR_UNSUPPORTED;
+  Args a{};
+  a.B = B;
+  a.NC = NC;
+  const int nc16 = (int)round_up(NC, 16);
+  if (nc16 <= 256) {
+    a.block_n = nc16;
+    a.n_tiles = 1;
+  } else {
+    a.n_tiles = (int)ceil_div(NC, 512);
+    a.block_n = (int)round_up(ceil_div(NC, a.n_tiles), 32);
+  }
+  if (a.block_n <= 256) {
+    a.box_rows = a.block_n; a.n_loads = 1; a.umma_n = a.block_n; a.n_umma = 1;
+  } else {
+    a.box_rows = a.block_n / 2; a.n_loads = 2; a.umma_n = a.block_n / 2; a.n_umma = 2;
+  }
+  a.tmem_cols = 32;
+  while (a.tmem_cols < a.block_n) a.tmem_cols *= 2;
+  a.m_tiles = (int)ceil_div(B, BLOCK_M);
+  a.kb_total = (int)ceil_div(D, BLOCK_K);
+  const int stage_bytes = A_STAGE_BYTES + a.block_n * BLOCK_K;
+  a.stages = (kSmemLimit - 1024 - (int)sizeof(Shared)) / stage_bytes;
+  if (a.stages > kMaxStages) a.stages = kMaxStages;
+  if (a.stages < 2) return EF_ERR_UNSUPPORTED;
+  a.ld_acc = ld_acc;
+  a.acc_t = acc_t;
+  a.sumsq = sumsq;
+  a.status = status;
+
+  CUtensorMap mx, mw;
+  if (!make_map(&mx, X, (uint64_t)D, (uint64_t)B, (uint64_t)ldx, BLOCK_M)) return EF_ERR_UNSUPPORTED;
+  if (!make_map(&mw, Wq, (uint64_t)ldw, (uint64_t)wq_rows, (uint64_t)ldw, (uint32_t)a.box_rows)) return EF_ERR_UNSUPPORTED;
+
+  const size_t smem = (size_t)a.stages * stage_bytes + sizeof(Shared) + 1024;
+  static size_t attr_smem = 0;
+  if (smem > attr_smem) {
+    EF_CUDA(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_smem = smem;
+  }
+  const long long total_units = (long long)a.n_tiles * a.m_tiles * a.kb_total;
+  int grid = sm_count();
+  if (grid > total_units) grid = (int)total_units;
+  EF_LAUNCH(project_tc_kernel, grid, kThreads, smem, stream, mx, mw, a);
+  return EF_OK;
 }
 
 }  // namespace ef

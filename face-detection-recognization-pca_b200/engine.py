@@ -80,6 +80,12 @@ class Recognizer:
     def use_tensor_cores(self, enable=True):
         check(self._L.ef_model_set_tensor_cores(self._h, 1 if enable else 0), "ef_model_set_tensor_cores")
 
+    def pipeline_timeouts(self):
+        """Non-zero when the tcgen05 projection kernel hit a bounded-wait timeout (synchronous read)."""
+        n = C.c_int32()
+        check(self._L.ef_model_status(self._h, C.byref(n)), "ef_model_status")
+        return n.value
+
     def kernel_timing(self, enable=True):
         check(self._L.ef_model_kernel_timing(self._h, 1 if enable else 0), "ef_model_kernel_timing")
 

@@ -125,6 +125,9 @@ int ef_model_set_tensor_cores(ef_model_t* model, int32_t enable);
 /* Measurement hook (bench.py roofline): when enabled, every recognise call brackets its projection kernel (the
  * dominant kernel) with CUDA events on the launching stream; _read returns the mean duration over the calls since
  * the hook was (re)enabled.  Off by default. */
+/* Health flag of the tensor-core pipeline: non-zero when an mbarrier wait inside the tcgen05 kernel timed out (the
+ * kernel drains instead of hanging).  Synchronous 4-byte read; the host entry points check it on every call. */
+int ef_model_status(ef_model_t* model, int32_t* tc_pipeline_timeouts);
 int ef_model_kernel_timing(ef_model_t* model, int32_t enable);
 int ef_model_kernel_timing_read(ef_model_t* model, int32_t* n_calls, double* project_ms_mean,
                                 int32_t* used_tensor_cores);

@@ -45,7 +45,7 @@ def test_struct_layouts_match_the_header():
 def test_argument_validation_needs_no_gpu():
     L = ef._lib.lib()
     assert L.ef_model_create(None, None) == ef._lib.EF_ERR_INVALID
-    assert L.ef_preprocess(None, 0, 0, 0, 0, 1, 1, None, 0, 64, 64, None, 0, None, None) == ef._lib.EF_ERR_INVALID
+    assert L.ef_preprocess(None, 0, 0, 0, 0, 1, 1, None, 1, 64, 64, None, 0, None, None) == ef._lib.EF_ERR_INVALID
     assert L.ef_eigh_work_bytes(100) >= 8 * (100 * 100 + 100)
     assert L.ef_eigh_work_bytes(0) == 0
 
