@@ -1,9 +1,10 @@
 // K2 epilogue: digit planes -> float64 features (+ reconstruction error) -> nearest gallery row -> threshold/label.
 //
 // Two kernels share the first phase:
-//   fused_epilogue_kernel   k <= 32: features stay in registers / shared memory, the gallery streams through shared
-//                           memory once per 32 crops, arg-best reduction and labelling in the same kernel (one launch
-//                           after the projection instead of five);
+//   fused_epilogue_kernel   k <= 32: features stay in registers / shared memory, the (pre-padded) gallery is pulled
+//                           into shared memory with cp.async while the planes are being combined, every warp sweeps a
+//                           contiguous slice of gallery rows four at a time (independent DFMA chains), arg-best
+//                           reduction and labelling in the same kernel: ONE launch after the projection;
 //   finalize_kernel         any k: writes the features (and the residual) to global memory; the generic match
 //                           kernel (ef_match.cu) follows.
 // Both CONSUME AND CLEAR the int32 accumulators and the sum-of-squares buffer, so the next batch needs no memset.
@@ -19,8 +20,9 @@
 namespace {
 
 constexpr int QB = 32;          // crops per CTA (one per lane)
-constexpr int kWarps = 8;
+constexpr int kWarps = 16;
 constexpr int kThreads = QB * kWarps;
+constexpr int kSmemBudget = 200 * 1024;
 
 // P[b][c] = 2^e_c * sum_s acc[s*kq + c][b] * 2^-(7s+6) - bias[c]; small planes first, then clear the planes.
 __device__ __forceinline__ double combine_planes(int32_t* __restrict__ acc_t, int ld_acc, int b, int c, int kq, int S,
@@ -28,7 +30,8 @@ __device__ __forceinline__ double combine_planes(int32_t* __restrict__ acc_t, in
   double v = 0.0;
   for (int s = S - 1; s >= 0; --s) {
     int32_t* p = acc_t + (size_t)(s * kq + c) * ld_acc + b;
-    v += ldexp((double)*p, -(7 * s + 6));
+    // exact: |acc| < 2^31 and the scale is a power of two
+    v += (double)*p * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
     *p = 0;
   }
   return ldexp(v, exp_c);
@@ -40,6 +43,11 @@ __device__ __forceinline__ bool better(double s, int i, double bs, int bi) {
   return s > bs || (s == bs && i < bi);
 }
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem));
+}
+
 struct EpiArgs {
   int32_t* acc_t;
   int ld_acc, B, k, kq, S;
@@ -47,10 +55,11 @@ struct EpiArgs {
   const double* bias;
   double* sumsq;          // consumed and cleared when resid is requested
   double c0;
-  const double* gp;       // prepared gallery [n][k]
+  const double* gp;       // prepared gallery [n][KR] (zero padded to KR columns)
   const double* gnorm;    // [n] (COSINE_G1)
+  const double* ginv;     // [n] 1/|g| or 0 (COSINE_G1)
   int n;
-  int tile_rows;          // gallery rows per shared-memory tile
+  int tile_rows;          // gallery rows per shared-memory tile (multiple of 4)
   const int32_t* labels;
   double threshold;
   double* out_proj;       // nullable
@@ -63,16 +72,30 @@ struct EpiArgs {
 template <int METRIC, int KR>
 __global__ void __launch_bounds__(kThreads)
 fused_epilogue_kernel(const EpiArgs a) {
-  extern __shared__ double sm[];
-  double* ps = sm;                         // [KR][QB] features (normalised for COSINE_SK)
-  double* gs = ps + KR * QB;               // [tile_rows][KR] gallery tile, zero padded to KR
-  double* gw = gs + (size_t)a.tile_rows * KR;   // [tile_rows] 1/|g| (COSINE_G1)
+  extern __shared__ __align__(16) double sm[];
+  double* ps = sm;                                // [KR][QB] features
+  double* gs = ps + KR * QB;                      // [tile_rows][KR] gallery tile
+  double* gw = gs + (size_t)a.tile_rows * KR;     // [tile_rows] 1/|g| (COSINE_G1)
   __shared__ double pn_s[QB], xu_s[QB];
   __shared__ double red_s[kWarps][QB], red_d[kWarps][QB];
   __shared__ int red_i[kWarps][QB];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int b = blockIdx.x * QB + lane;
   const bool live = b < a.B;
+
+  auto load_tile = [&](int g0) {
+    const int rows = min(a.tile_rows, a.n - g0);
+    const char* src = reinterpret_cast<const char*>(a.gp + (size_t)g0 * KR);
+    const int chunks = rows * KR / 2;               // 16-byte chunks; KR is even
+    for (int e = tid; e < chunks; e += kThreads) cp_async16(reinterpret_cast<char*>(gs) + e * 16, src + e * 16);
+    if (METRIC == EF_METRIC_COSINE_G1)
+      for (int e = tid; e < (rows + 1) / 2; e += kThreads) {
+        // ginv is padded to an even count on the host side of the model
+        cp_async16(reinterpret_cast<char*>(gw) + e * 16, reinterpret_cast<const char*>(a.ginv + g0) + e * 16);
+      }
+    asm volatile("cp.async.commit_group;\n" ::);
+  };
+  load_tile(0);                                     // overlaps with the plane combination below
 
   // ---- phase 1: features
   for (int c = warp; c < KR; c += kWarps) ps[c * QB + lane] = 0.0;
@@ -111,39 +134,46 @@ fused_epilogue_kernel(const EpiArgs a) {
     p[c] = v;
   }
 
-  // ---- phase 2: gallery sweep, warp w takes rows w, w+8, ... of every tile
+  // ---- phase 2: gallery sweep; warp w owns a contiguous slice of every tile, four rows per iteration
   double best = (METRIC == EF_METRIC_L2) ? CUDART_INF : -CUDART_INF, best_dot = 0.0;
   int best_i = INT_MAX;
   for (int g0 = 0; g0 < a.n; g0 += a.tile_rows) {
     const int rows = min(a.tile_rows, a.n - g0);
-    __syncthreads();
-    for (int e = tid; e < rows * KR; e += kThreads) {
-      const int r = e / KR, c = e - r * KR;
-      gs[e] = (c < a.k) ? a.gp[(size_t)(g0 + r) * a.k + c] : 0.0;
+    if (g0 > 0) {
+      __syncthreads();                              // everyone is done with the previous tile
+      load_tile(g0);
     }
-    if (METRIC == EF_METRIC_COSINE_G1)
-      for (int r = tid; r < rows; r += kThreads) {
-        const double gn = a.gnorm[g0 + r];
-        gw[r] = gn == 0.0 ? 0.0 : 1.0 / gn;
-      }
+    asm volatile("cp.async.wait_group 0;\n" ::);
     __syncthreads();
-    for (int r = warp; r < rows; r += kWarps) {
-      const double* g = gs + (size_t)r * KR;
-      double d = 0.0;
+    const int per = ((rows + kWarps - 1) / kWarps + 3) & ~3;      // rows per warp, multiple of 4
+    const int r_begin = warp * per, r_end = min(rows, r_begin + per);
+    for (int r = r_begin; r < r_end; r += 4) {
+      double d[4] = {0.0, 0.0, 0.0, 0.0};
 #pragma unroll
-      for (int c = 0; c < KR; ++c) {
-        if (METRIC == EF_METRIC_L2) {
-          const double t = p[c] - g[c];
-          d = fma(t, t, d);
-        } else {
-          d = fma(p[c], g[c], d);
+      for (int c = 0; c < KR; c += 2) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // rows past the tile end read stale shared memory; their result is discarded below
+          const double2 g = *reinterpret_cast<const double2*>(gs + (size_t)(r + j) * KR + c);
+          if (METRIC == EF_METRIC_L2) {
+            const double t0 = p[c] - g.x, t1 = p[c + 1] - g.y;
+            d[j] = fma(t0, t0, d[j]);
+            d[j] = fma(t1, t1, d[j]);
+          } else {
+            d[j] = fma(p[c], g.x, d[j]);
+            d[j] = fma(p[c + 1], g.y, d[j]);
+          }
         }
       }
-      const double s = (METRIC == EF_METRIC_COSINE_G1) ? d * gw[r] : d;
-      if (better<METRIC>(s, g0 + r, best, best_i)) {
-        best = s;
-        best_dot = d;
-        best_i = g0 + r;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        if (r + j >= r_end) break;
+        const double s = (METRIC == EF_METRIC_COSINE_G1) ? d[j] * gw[r + j] : d[j];
+        if (better<METRIC>(s, g0 + r + j, best, best_i)) {
+          best = s;
+          best_dot = d[j];
+          best_i = g0 + r + j;
+        }
       }
     }
   }
@@ -178,18 +208,19 @@ fused_epilogue_kernel(const EpiArgs a) {
 }
 
 // Any k: features (+ residual) to global memory.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(256)
 finalize_kernel(int32_t* __restrict__ acc_t, int ld_acc, int B, int k, int kq, int S,
                 const int32_t* __restrict__ col_exp, const double* __restrict__ bias, double* __restrict__ proj,
                 int64_t ldp, double* __restrict__ sumsq, double c0, double* __restrict__ resid2) {
-  __shared__ double n2_s[kWarps][QB], xu_s[QB];
+  constexpr int W = 8;
+  __shared__ double n2_s[W][QB], xu_s[QB];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int b = blockIdx.x * QB + lane;
   const bool live = b < B;
   if (warp == 0) xu_s[lane] = 0.0;
   __syncthreads();
   double n2 = 0.0;
-  for (int c = warp; c < kq; c += kWarps) {
+  for (int c = warp; c < kq; c += W) {
     if (!live) continue;
     double v = combine_planes(acc_t, ld_acc, b, c, kq, S, col_exp[c]);
     if (c < k) {
@@ -204,7 +235,7 @@ finalize_kernel(int32_t* __restrict__ acc_t, int ld_acc, int B, int k, int kq, i
   __syncthreads();
   if (warp == 0 && live && resid2) {
     double t = 0.0;
-    for (int w = 0; w < kWarps; ++w) t += n2_s[w][lane];
+    for (int w = 0; w < W; ++w) t += n2_s[w][lane];
     const double r = sumsq[b] - 2.0 * xu_s[lane] + c0 - t;
     resid2[b] = r > 0.0 ? r : 0.0;
     sumsq[b] = 0.0;
@@ -212,8 +243,14 @@ finalize_kernel(int32_t* __restrict__ acc_t, int ld_acc, int B, int k, int kq, i
 }
 
 template <int METRIC, int KR>
-int launch_fused(const EpiArgs& a, cudaStream_t stream) {
-  const size_t smem = sizeof(double) * ((size_t)KR * QB + (size_t)a.tile_rows * (KR + 1));
+int launch_fused(EpiArgs& a, cudaStream_t stream) {
+  // gallery tile: as many rows as fit (the whole gallery for the shipped sizes), multiple of 4
+  int rows = (int)((kSmemBudget - sizeof(double) * KR * QB) / (sizeof(double) * (KR + 1)));
+  rows &= ~3;
+  const int n4 = (a.n + 3) & ~3;
+  if (rows > n4) rows = n4;
+  a.tile_rows = rows;
+  const size_t smem = sizeof(double) * ((size_t)KR * QB + (size_t)rows * (KR + 1)) + 64;
   static size_t attr = 0;
   if (smem > 48 * 1024 && smem > attr) {
     EF_CUDA(cudaFuncSetAttribute(fused_epilogue_kernel<METRIC, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -224,16 +261,13 @@ int launch_fused(const EpiArgs& a, cudaStream_t stream) {
 }
 
 template <int METRIC>
-int dispatch_kr(EpiArgs& a, cudaStream_t stream) {
-  const int kr = a.k <= 8 ? 8 : (a.k <= 16 ? 16 : 32);
-  // gallery tile: as much as fits in ~64 KB, at least 8 rows per warp round
-  int rows = (int)((64 * 1024) / (sizeof(double) * (kr + 1)));
-  rows = rows / kWarps * kWarps;
-  if (rows > a.n) rows = a.n;
-  a.tile_rows = rows;
+int dispatch_kr(EpiArgs& a, int kr, cudaStream_t stream) {
   switch (kr) {
+    case 4: return launch_fused<METRIC, 4>(a, stream);
     case 8: return launch_fused<METRIC, 8>(a, stream);
+    case 12: return launch_fused<METRIC, 12>(a, stream);
     case 16: return launch_fused<METRIC, 16>(a, stream);
+    case 24: return launch_fused<METRIC, 24>(a, stream);
     default: return launch_fused<METRIC, 32>(a, stream);
   }
 }
@@ -242,19 +276,28 @@ int dispatch_kr(EpiArgs& a, cudaStream_t stream) {
 
 namespace ef {
 
-bool fused_epilogue_supported(int k, int64_t n) { return k <= 32 && n > 0 && n < (1ll << 31); }
+bool fused_epilogue_supported(int k, int64_t n) { return k <= 32 && n > 0 && n < (1ll << 31) - 8; }
+
+// Column padding of the prepared gallery used by the fused kernel (the kernel is specialised on it).
+int fused_epilogue_kpad(int k) {
+  const int steps[] = {4, 8, 12, 16, 24, 32};
+  for (int s : steps)
+    if (k <= s) return s;
+  return k;
+}
 
 int fused_epilogue(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, const int32_t* col_exp, const double* bias,
-                   double* sumsq, double c0, const double* gp, const double* gnorm, int64_t n, const int32_t* labels,
-                   int metric, double threshold, double* out_proj, double* out_score, int32_t* out_index,
-                   int32_t* out_label, double* out_resid, cudaStream_t stream) {
+                   double* sumsq, double c0, const double* gp_padded, const double* gnorm, const double* ginv, int64_t n,
+                   const int32_t* labels, int metric, double threshold, double* out_proj, double* out_score,
+                   int32_t* out_index, int32_t* out_label, double* out_resid, cudaStream_t stream) {
   if (B <= 0) return EF_OK;
-  EpiArgs a{acc_t, ld_acc, B, k, kq, S, col_exp, bias, sumsq, c0, gp, gnorm, (int)n, 0, labels, threshold,
+  EpiArgs a{acc_t, ld_acc, B, k, kq, S, col_exp, bias, sumsq, c0, gp_padded, gnorm, ginv, (int)n, 0, labels, threshold,
             out_proj, out_score, out_index, out_label, out_resid};
+  const int kr = fused_epilogue_kpad(k);
   switch (metric) {
-    case EF_METRIC_COSINE_SK: return dispatch_kr<EF_METRIC_COSINE_SK>(a, stream);
-    case EF_METRIC_COSINE_G1: return dispatch_kr<EF_METRIC_COSINE_G1>(a, stream);
-    case EF_METRIC_L2: return dispatch_kr<EF_METRIC_L2>(a, stream);
+    case EF_METRIC_COSINE_SK: return dispatch_kr<EF_METRIC_COSINE_SK>(a, kr, stream);
+    case EF_METRIC_COSINE_G1: return dispatch_kr<EF_METRIC_COSINE_G1>(a, kr, stream);
+    case EF_METRIC_L2: return dispatch_kr<EF_METRIC_L2>(a, kr, stream);
     default: return EF_ERR_INVALID;
   }
 }
@@ -263,7 +306,7 @@ int project_finalize(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, co
                      const double* bias, double* proj, int64_t ldp, double* sumsq, double c0, double* resid2,
                      cudaStream_t stream) {
   if (B <= 0) return EF_OK;
-  EF_LAUNCH(finalize_kernel, (unsigned)ceil_div(B, QB), kThreads, 0, stream, acc_t, ld_acc, B, k, kq, S, col_exp, bias,
+  EF_LAUNCH(finalize_kernel, (unsigned)ceil_div(B, QB), 256, 0, stream, acc_t, ld_acc, B, k, kq, S, col_exp, bias,
             proj, ldp, sumsq, c0, resid2);
   return EF_OK;
 }

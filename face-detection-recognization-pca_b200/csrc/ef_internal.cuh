@@ -21,18 +21,21 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
 
 // ef_epilogue.cu
 bool fused_epilogue_supported(int k, int64_t n);
+int fused_epilogue_kpad(int k);   // column count the prepared gallery must be zero-padded to for the fused kernel
 int fused_epilogue(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, const int32_t* col_exp, const double* bias,
-                   double* sumsq, double c0, const double* gp, const double* gnorm, int64_t n, const int32_t* labels,
-                   int metric, double threshold, double* out_proj, double* out_score, int32_t* out_index,
-                   int32_t* out_label, double* out_resid, cudaStream_t stream);
+                   double* sumsq, double c0, const double* gp_padded, const double* gnorm, const double* ginv, int64_t n,
+                   const int32_t* labels, int metric, double threshold, double* out_proj, double* out_score,
+                   int32_t* out_index, int32_t* out_label, double* out_resid, cudaStream_t stream);
 int project_finalize(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, const int32_t* col_exp,
                      const double* bias, double* proj, int64_t ldp, double* sumsq, double c0, double* resid2,
                      cudaStream_t stream);
 
 // ef_match.cu
 // Gallery preparation: gn[j][:] = g[j][:] / |g_j| (COSINE_SK), copy + norms (COSINE_G1), copy (L2).
+// Columns [k, ldgp) of gp are left untouched (callers that need zero padding clear gp first); ginv (nullable)
+// receives 1/|g| (0 for a zero row).
 int gallery_prepare(const double* g, int64_t ldg, int64_t n, int k, int metric, double* gp, int64_t ldgp, double* gnorm,
-                    cudaStream_t stream);
+                    double* ginv, cudaStream_t stream);
 size_t match_work_bytes(int B, int64_t n);
 int match(const double* p, int64_t ldp, int B, int k, const double* gp, int64_t ldgp, const double* gnorm, int64_t n,
           int64_t index_base, int metric, double* out_score, int64_t* out_index, void* work, cudaStream_t stream);

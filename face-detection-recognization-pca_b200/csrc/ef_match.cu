@@ -185,7 +185,8 @@ __global__ void match_reduce_kernel(const double* __restrict__ scores, const int
 }
 
 __global__ void gallery_prepare_kernel(const double* __restrict__ g, int64_t ldg, int64_t n, int k, int metric,
-                                       double* __restrict__ gp, int64_t ldgp, double* __restrict__ gnorm) {
+                                       double* __restrict__ gp, int64_t ldgp, double* __restrict__ gnorm,
+                                       double* __restrict__ ginv) {
   const int64_t row = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (row >= n) return;
@@ -197,6 +198,7 @@ __global__ void gallery_prepare_kernel(const double* __restrict__ g, int64_t ldg
   const double div = (metric == EF_METRIC_COSINE_SK) ? (nrm == 0.0 ? 1.0 : nrm) : 1.0;
   for (int c = lane; c < k; c += 32) gp[row * ldgp + c] = (metric == EF_METRIC_COSINE_SK) ? src[c] / div : src[c];
   if (lane == 0 && gnorm) gnorm[row] = nrm;
+  if (lane == 0 && ginv) ginv[row] = nrm == 0.0 ? 0.0 : 1.0 / nrm;
 }
 
 __global__ void label_kernel(const double* __restrict__ score, const int64_t* __restrict__ index, int B,
@@ -227,11 +229,11 @@ int gallery_splits(int B, int64_t n) {
 namespace ef {
 
 int gallery_prepare(const double* g, int64_t ldg, int64_t n, int k, int metric, double* gp, int64_t ldgp, double* gnorm,
-                    cudaStream_t stream) {
+                    double* ginv, cudaStream_t stream) {
   if (n <= 0) return EF_OK;
   const int threads = 256;
   const int64_t grid = ceil_div(n * 32, threads);
-  EF_LAUNCH(gallery_prepare_kernel, (unsigned)grid, threads, 0, stream, g, ldg, n, k, metric, gp, ldgp, gnorm);
+  EF_LAUNCH(gallery_prepare_kernel, (unsigned)grid, threads, 0, stream, g, ldg, n, k, metric, gp, ldgp, gnorm, ginv);
   return EF_OK;
 }
 
@@ -296,7 +298,7 @@ int ef_gallery_prepare_device(const double* gallery, int64_t ldg, int64_t n, int
                               int64_t ldp, double* norms, ef_stream_t stream) {
   if (!gallery || !prepared || n < 0 || k <= 0 || ldg < k || ldp < k) return EF_ERR_INVALID;
   if (metric == EF_METRIC_COSINE_G1 && !norms) return EF_ERR_INVALID;
-  return ef::gallery_prepare(gallery, ldg, n, k, metric, prepared, ldp, norms, ef::as_stream(stream));
+  return ef::gallery_prepare(gallery, ldg, n, k, metric, prepared, ldp, norms, nullptr, ef::as_stream(stream));
 }
 
 int ef_match_device(const double* p, int64_t ldp, int32_t B, int32_t k, const double* prepared, int64_t ldg,

@@ -20,7 +20,8 @@ struct ef_model {
   int64_t ldw = 0;
   bool with_residual = false, has_scale = false;
   double c0 = 0.0;
-  ef::DevBuf wq, col_exp, bias, qq, gp, gnorm, labels;
+  ef::DevBuf wq, col_exp, bias, qq, gp, gnorm, ginv, labels;
+  int kpad = 0;                    // column pitch of the prepared gallery (zero padded for the fused epilogue)
   // workspaces (sized by reserve)
   int reserved = 0;
   ef::DevBuf acc, proj, sumsq, score, index64, match_work, status;
@@ -174,15 +175,25 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
       memcpy(&g[(size_t)j * k], desc->gallery + j * desc->gallery_ld, sizeof(double) * k);
     st = upload(raw, g.data(), sizeof(double) * g.size());
   }
-  if (st == EF_OK) st = m->gp.ensure(sizeof(double) * (size_t)desc->n_gallery * k);
-  if (st == EF_OK) st = m->gnorm.ensure(sizeof(double) * (size_t)desc->n_gallery);
+  m->kpad = ef::fused_epilogue_supported(k, desc->n_gallery) ? ef::fused_epilogue_kpad(k) : k;
+  const size_t gp_bytes = sizeof(double) * (size_t)desc->n_gallery * m->kpad;
+  const size_t gn_bytes = sizeof(double) * ((size_t)desc->n_gallery + 8);
+  if (st == EF_OK) st = m->gp.ensure(gp_bytes);
+  if (st == EF_OK) st = m->gnorm.ensure(gn_bytes);
+  if (st == EF_OK) st = m->ginv.ensure(gn_bytes);
+  if (st == EF_OK) {
+    cudaError_t e = cudaMemset(m->gp.p, 0, gp_bytes);
+    if (e == cudaSuccess) e = cudaMemset(m->gnorm.p, 0, gn_bytes);
+    if (e == cudaSuccess) e = cudaMemset(m->ginv.p, 0, gn_bytes);
+    if (e != cudaSuccess) { ef::set_error_detail("cudaMemset", e); st = EF_ERR_CUDA; }
+  }
   if (st == EF_OK) {
     cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) { ef::set_error_detail("cudaStreamCreate", e); st = EF_ERR_CUDA; }
   }
   if (st == EF_OK)
-    st = ef::gallery_prepare(raw.as<double>(), k, desc->n_gallery, k, m->metric, m->gp.as<double>(), k,
-                             m->gnorm.as<double>(), m->stream);
+    st = ef::gallery_prepare(raw.as<double>(), k, desc->n_gallery, k, m->metric, m->gp.as<double>(), m->kpad,
+                             m->gnorm.as<double>(), m->ginv.as<double>(), m->stream);
   if (st == EF_OK) {
     cudaError_t e = cudaStreamSynchronize(m->stream);
     if (e != cudaSuccess) { ef::set_error_detail("gallery_prepare", e); st = EF_ERR_CUDA; }
@@ -309,15 +320,15 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
   if (ef::fused_epilogue_supported(m->k, m->n_gallery)) {
     // 3. one launch: planes -> features (+ residual) -> nearest gallery row -> threshold / label
     EF_TRY(ef::fused_epilogue(acc, m->ld_acc, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(), m->bias.as<double>(),
-                              sumsq, m->c0, m->gp.as<double>(), m->gnorm.as<double>(), m->n_gallery, labels, m->metric,
-                              threshold, out->proj, out->score, out->index, out->label,
+                              sumsq, m->c0, m->gp.as<double>(), m->gnorm.as<double>(), m->ginv.as<double>(),
+                              m->n_gallery, labels, m->metric, threshold, out->proj, out->score, out->index, out->label,
                               want_resid ? out->resid2 : nullptr, st));
   } else {
     // 3. planes -> float64 features (+ residual); 4. nearest gallery row; 5. threshold + label
     double* proj = out->proj ? out->proj : m->proj.as<double>();
     EF_TRY(ef::project_finalize(acc, m->ld_acc, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(), m->bias.as<double>(),
                                 proj, m->k, sumsq, m->c0, want_resid ? out->resid2 : nullptr, st));
-    EF_TRY(ef::match(proj, m->k, B, m->k, m->gp.as<double>(), m->k, m->gnorm.as<double>(), m->n_gallery, 0, m->metric,
+    EF_TRY(ef::match(proj, m->k, B, m->k, m->gp.as<double>(), m->kpad, m->gnorm.as<double>(), m->n_gallery, 0, m->metric,
                      out->score, m->index64.as<int64_t>(), m->match_work.p, st));
     EF_TRY(ef::label_lookup(out->score, m->index64.as<int64_t>(), B, labels, m->metric, threshold, out->index,
                             out->label, st));

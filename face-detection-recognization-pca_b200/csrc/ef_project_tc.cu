@@ -18,6 +18,9 @@
 // Every mbarrier wait is bounded (2 s): on a timeout the kernel raises a status flag and drains instead of hanging.
 #include <cuda.h>
 
+#include <cstdlib>
+#include <vector>
+
 #include "ef_common.cuh"
 #include "ef_internal.cuh"
 
@@ -71,16 +74,21 @@ __device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t 
 }
 // Bounded wait: false on timeout or when another role already failed.
 __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t parity, volatile int* failed) {
-  if (mbar_try_wait(bar, parity)) return true;
-  const unsigned long long t0 = globaltimer();
-  while (!mbar_try_wait(bar, parity)) {
-    if (*failed) return false;
-    if (globaltimer() - t0 > kTimeoutNs) {
-      *failed = 1;
-      return false;
+  // fast path: plain try_wait spins (each try_wait already suspends the thread for a hardware-defined interval);
+  // the (slow) global timer and the shared failure flag are only consulted every 1024 unsuccessful polls.
+  unsigned long long t0 = 0;
+  for (unsigned int polls = 1;; ++polls) {
+    if (mbar_try_wait(bar, parity)) return true;
+    if ((polls & 1023u) == 0) {
+      if (*failed) return false;
+      const unsigned long long now = globaltimer();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > kTimeoutNs) {
+        *failed = 1;
+        return false;
+      }
     }
   }
-  return true;
 }
 
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c_inner,
@@ -148,12 +156,14 @@ struct Args {
   int32_t* acc_t;
   double* sumsq;             // may be null
   int* status;
+  unsigned long long* probe;   // optional [grid][8] timestamps (ns), debugging aid enabled by EF_TC_PROBE=1
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const Args a) {
   extern __shared__ uint8_t smem_raw[];
+  if (a.probe && threadIdx.x == 0) a.probe[(size_t)gridDim.x * 8] = a.probe[(size_t)gridDim.x * 8] ? a.probe[(size_t)gridDim.x * 8] : globaltimer();
   // 1024-byte alignment is required by the 128-byte swizzle atoms
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_stage_bytes = a.block_n * BLOCK_K;
@@ -184,6 +194,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
+  unsigned long long* probe = a.probe ? a.probe + (size_t)blockIdx.x * 8 : nullptr;
+  if (probe && threadIdx.x == 0) { probe[0] = a.probe[(size_t)gridDim.x * 8]; probe[1] = globaltimer(); }
   volatile int* failed = &sh->failed;
 
   // this CTA's contiguous range of (n tile, m tile, k block) units
@@ -233,6 +245,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         for (int kb = kb0; kb < kb1; ++kb) {
           if (!mbar_wait(&sh->full_bar[stage], phase, failed)) { ok = false; break; }
           tc_fence_after();
+          if (probe && probe[2] == 0) probe[2] = globaltimer();
           const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + (size_t)stage * b_stage_bytes);
 #pragma unroll
@@ -248,6 +261,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
         }
         if (!ok) break;
         umma_commit(&sh->tmem_full_bar);           // accumulator of this segment is complete
+        if (probe) probe[3] = globaltimer();
         u += kb1 - kb0;
       }
     }
@@ -305,6 +319,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->tmem_empty_bar);
+      if (probe && threadIdx.x == 64) probe[4] = globaltimer();
       if (do_sumsq && n_tile == 0 && row < a.B && ssq != 0ull) atomicAdd(a.sumsq + row, (double)ssq);
       u += kb1 - kb0;
     }
@@ -319,6 +334,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
                  : "memory");
   }
   if (threadIdx.x == 0 && sh->failed) atomicExch(a.status, 1);
+  if (probe && threadIdx.x == 0) probe[5] = globaltimer();
 }
 
 // --------------------------------------------------------------------------------------------- host side
@@ -387,11 +403,13 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
   const int stage_bytes = A_STAGE_BYTES + a.block_n * BLOCK_K;
   a.stages = (kSmemLimit - 1024 - (int)sizeof(Shared)) / stage_bytes;
   if (a.stages > kMaxStages) a.stages = kMaxStages;
+  if (const char* e = getenv("EF_TC_STAGES")) { const int v = atoi(e); if (v >= 2 && v < a.stages) a.stages = v; }
   if (a.stages < 2) return EF_ERR_UNSUPPORTED;
   a.ld_acc = ld_acc;
   a.acc_t = acc_t;
   a.sumsq = sumsq;
   a.status = status;
+  a.probe = nullptr;
 
   CUtensorMap mx, mw;
   if (!make_map(&mx, X, (uint64_t)D, (uint64_t)B, (uint64_t)ldx, BLOCK_M)) return EF_ERR_UNSUPPORTED;
@@ -405,8 +423,35 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
   }
   const long long total_units = (long long)a.n_tiles * a.m_tiles * a.kb_total;
   int grid = sm_count();
+  if (const char* e = getenv("EF_TC_GRID")) { const int v = atoi(e); if (v >= 1) grid = v; }
   if (grid > total_units) grid = (int)total_units;
+  static unsigned long long* probe_buf = nullptr;
+  static int probe_grid = 0;
+  const bool probing = getenv("EF_TC_PROBE") != nullptr;
+  if (probing) {
+    if (!probe_buf) EF_CUDA(cudaMalloc(&probe_buf, sizeof(unsigned long long) * 8 * 1025));
+    EF_CUDA(cudaMemsetAsync(probe_buf, 0, sizeof(unsigned long long) * 8 * 1025, stream));
+    a.probe = probe_buf;
+    probe_grid = grid;
+  }
   EF_LAUNCH(project_tc_kernel, grid, kThreads, smem, stream, mx, mw, a);
+  if (probing) {
+    // debugging aid: per-CTA phase timestamps relative to the first CTA entering the kernel
+    std::vector<unsigned long long> h(8 * (size_t)(probe_grid + 1));
+    EF_CUDA(cudaStreamSynchronize(stream));
+    EF_CUDA(cudaMemcpy(h.data(), probe_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    const unsigned long long t0 = h[(size_t)probe_grid * 8];
+    double mx_[6] = {0}, sum_[6] = {0};
+    for (int c = 0; c < probe_grid; ++c)
+      for (int i = 1; i < 6; ++i) {
+        const double v = h[(size_t)c * 8 + i] ? (double)(h[(size_t)c * 8 + i] - t0) * 1e-3 : 0.0;
+        sum_[i] += v;
+        if (v > mx_[i]) mx_[i] = v;
+      }
+    fprintf(stderr, "[ef_tc_probe] grid %d stages %d us since first CTA (mean/max): setup %.2f/%.2f first_full %.2f/%.2f last_mma %.2f/%.2f flush %.2f/%.2f end %.2f/%.2f\n",
+            probe_grid, a.stages, sum_[1] / probe_grid, mx_[1], sum_[2] / probe_grid, mx_[2], sum_[3] / probe_grid, mx_[3],
+            sum_[4] / probe_grid, mx_[4], sum_[5] / probe_grid, mx_[5]);
+  }
   return EF_OK;
 }
 

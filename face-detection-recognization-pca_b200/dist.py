@@ -1,0 +1,174 @@
+"""Multi-GPU partitioning of the hot path (one process per GPU, torch.distributed for the plumbing).
+
+Three natural shardings, each with at most one exchange step:
+  * queries / frames      independent -> no collective (see bench.py --gpus N)
+  * large gallery         contiguous row shards; per-shard top-1, one all-gather of (score, index), local reduce
+  * training rows         per-rank exact integer column sums + integer Gram, one all-reduce(SUM) of int64
+
+The collectives move exact integers or (score, index) pairs, so the result is bit identical to the single-GPU run for
+any world size: integer sums are order independent and candidate reduction breaks ties towards the smallest GLOBAL
+gallery row, exactly like np.argmax on the unsharded gallery.
+
+Functions that only route tensors (shard_bounds, allgather_candidates, reduce_candidates, allreduce_exact) work on
+CPU tensors with the gloo backend too; that is how the host logic is tested without GPUs.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import METRIC_COSINE_G1, METRIC_COSINE_SK, METRIC_L2, check
+
+
+def shard_bounds(n, world, rank):
+    """Contiguous partition of n rows: rank r owns [lo, hi); sizes differ by at most one, earlier ranks get the extra."""
+    base, extra = divmod(int(n), int(world))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _world(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def allgather_candidates(score, index, group=None):
+    """[B] score (float64) and [B] global index (int64) of this rank -> ([R, B], [R, B]) on every rank."""
+    import torch
+    import torch.distributed as dist
+    world, _ = _world(group)
+    if world == 1:
+        return score[None].clone(), index[None].clone()
+    n = score.numel()
+    scores = torch.empty(world * n, dtype=score.dtype, device=score.device)       # flat: gloo and nccl both accept it
+    idxs = torch.empty(world * n, dtype=index.dtype, device=index.device)
+    dist.all_gather_into_tensor(scores, score.contiguous().view(-1), group=group)
+    dist.all_gather_into_tensor(idxs, index.contiguous().view(-1), group=group)
+    return scores.view(world, n), idxs.view(world, n)
+
+
+def reduce_candidates(scores, indices, metric):
+    """Best candidate per query over R shards: higher cosine / lower L2 wins, ties -> smallest global index,
+    shards that returned index -1 (empty) are ignored.  CUDA tensors use ef_match_reduce_device; CPU tensors the same
+    rule in torch ops (host-logic tests)."""
+    import torch
+    R, B = scores.shape
+    if scores.is_cuda:
+        out_s = torch.empty(B, dtype=torch.float64, device=scores.device)
+        out_i = torch.empty(B, dtype=torch.int64, device=scores.device)
+        stream = C.c_void_p(torch.cuda.current_stream(scores.device).cuda_stream)
+        check(_lib.lib().ef_match_reduce_device(scores.contiguous().data_ptr(), indices.contiguous().data_ptr(), R, B,
+                                                metric, out_s.data_ptr(), out_i.data_ptr(), stream),
+              "ef_match_reduce_device")
+        return out_s, out_i
+    worst = float("inf") if metric == METRIC_L2 else -float("inf")
+    s = torch.where(indices < 0, torch.full_like(scores, worst), scores)
+    best = s.min(dim=0).values if metric == METRIC_L2 else s.max(dim=0).values
+    big = torch.iinfo(torch.int64).max
+    cand = torch.where((s == best[None]) & (indices >= 0), indices, torch.full_like(indices, big))
+    idx = cand.min(dim=0).values
+    idx = torch.where(idx == big, torch.full_like(idx, -1), idx)
+    return best, idx
+
+
+def allreduce_exact(t, group=None):
+    """SUM all-reduce of an integer tensor in place (exact, order independent)."""
+    import torch.distributed as dist
+    world, _ = _world(group)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+class ShardedGallery:
+    """This rank's contiguous slice of a large gallery, resident on the device.
+
+    gallery_shard: [n_local, k] float64 (numpy or CUDA tensor); index_base: global row of its first row.
+    match(features) returns the GLOBAL (score, index) per query, identical on every rank.
+    """
+
+    def __init__(self, gallery_shard, index_base, metric=METRIC_COSINE_SK, group=None):
+        import torch
+        L = _lib.lib()
+        dev = torch.device("cuda", torch.cuda.current_device())
+        g = gallery_shard if torch.is_tensor(gallery_shard) else torch.from_numpy(
+            np.ascontiguousarray(gallery_shard, dtype=np.float64))
+        g = g.to(dev, dtype=torch.float64).contiguous()
+        self.n, self.k = int(g.shape[0]), int(g.shape[1])
+        self.index_base, self.metric, self.group = int(index_base), metric, group
+        self.prepared = torch.empty_like(g)
+        self.norms = torch.zeros(max(self.n, 1), dtype=torch.float64, device=dev)
+        if self.n:
+            stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+            check(L.ef_gallery_prepare_device(g.data_ptr(), self.k, self.n, self.k, metric, self.prepared.data_ptr(),
+                                              self.k, self.norms.data_ptr(), stream), "ef_gallery_prepare_device")
+        self._L, self._work = L, None
+
+    def match_local(self, features):
+        """Top-1 of the queries against this shard only: (score [B], global index [B]; -1 when the shard is empty)."""
+        import torch
+        p = features.contiguous()
+        B = int(p.shape[0])
+        score = torch.empty(B, dtype=torch.float64, device=p.device)
+        index = torch.full((B,), -1, dtype=torch.int64, device=p.device)
+        if self.n == 0 or B == 0:
+            score.fill_(float("inf") if self.metric == METRIC_L2 else -float("inf"))
+            return score, index
+        need = int(self._L.ef_match_work_bytes(B, self.n)) + 16
+        if self._work is None or self._work.numel() < need:
+            self._work = torch.empty(need, dtype=torch.uint8, device=p.device)
+        stream = C.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)
+        check(self._L.ef_match_device(p.data_ptr(), p.stride(0), B, self.k, self.prepared.data_ptr(), self.k,
+                                      self.norms.data_ptr(), self.n, self.index_base, self.metric, score.data_ptr(),
+                                      index.data_ptr(), self._work.data_ptr(), stream), "ef_match_device")
+        return score, index
+
+    def match(self, features):
+        score, index = self.match_local(features)
+        scores, idxs = allgather_candidates(score, index, self.group)        # B x 16 bytes per rank over NVLink
+        return reduce_candidates(scores, idxs, self.metric)
+
+
+def fit_gen1_sharded(X_local, n_total, n_components, group=None):
+    """Row-sharded manual_pca (useless/train.py:56-128) for N >= D (the covariance branch, e.g. 100 000 x 4096):
+    every rank holds X_local uint8 [N_r, D] on its GPU.  Returns (eigenfaces [D,k], mean [D], projected_local [N_r,k],
+    eigenvalues [k]) as CUDA float64 tensors; eigenfaces / mean / eigenvalues are identical on every rank.
+
+    Per rank: exact integer column sums and Gram X_r^T X_r; ONE all-reduce(SUM) of int64 [D*D + D]; exact integer
+    centring; replicated Jacobi eigensolver; local projection of the local rows."""
+    import torch
+    L = _lib.lib()
+    dev = X_local.device
+    Nr, D = int(X_local.shape[0]), int(X_local.shape[1])
+    if n_total < D:
+        raise ValueError("fit_gen1_sharded covers the N >= D branch; small training sets fit on one GPU (fit_gen1)")
+    if D > 4096:
+        raise _lib.EigenfacesError(_lib.EF_ERR_UNSUPPORTED, "fit_gen1_sharded (D > 4096 needs the subspace solver)")
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    buf = torch.zeros(D * D + D, dtype=torch.int64, device=dev)
+    G, colsum = buf[:D * D], buf[D * D:]
+    if Nr:
+        check(L.ef_colsum_u8_device(X_local.data_ptr(), X_local.stride(0), Nr, D, colsum.data_ptr(), stream), "colsum")
+        check(L.ef_gram_u8_device(X_local.data_ptr(), X_local.stride(0), Nr, D, 0, D, 1, G.data_ptr(), stream), "gram")
+    allreduce_exact(buf, group)
+    cov = torch.empty((D, D), dtype=torch.float64, device=dev)
+    check(L.ef_gram_center_device(G.data_ptr(), D, 1, colsum.data_ptr(), int(n_total), 1.0 / (n_total - 1),
+                                  cov.data_ptr(), None, stream), "center")
+    evals = torch.empty(D, dtype=torch.float64, device=dev)
+    evecs = torch.empty((D, D), dtype=torch.float64, device=dev)
+    work = torch.empty(int(L.ef_eigh_work_bytes(D)), dtype=torch.uint8, device=dev)
+    check(L.ef_eigh_jacobi_device(cov.data_ptr(), D, evals.data_ptr(), evecs.data_ptr(), work.data_ptr(), 0, 0.0, None,
+                                  None, stream), "jacobi")
+    k = min(int(n_components), D)
+    mean = colsum.to(torch.float64) / float(n_total)
+    E = evecs[:k].T.contiguous()                                   # [D, k]
+    Z = torch.empty((max(Nr, 1), D), dtype=torch.float64, device=dev)
+    proj = torch.empty((Nr, k), dtype=torch.float64, device=dev)
+    if Nr:
+        check(L.ef_standardize_u8_device(X_local.data_ptr(), X_local.stride(0), Nr, D, mean.data_ptr(), None, None,
+                                         Z.data_ptr(), D, stream), "center rows")
+        check(L.ef_dgemm_device(Nr, k, D, 1.0, Z.data_ptr(), D, 1, E.data_ptr(), k, 1, 0.0, proj.data_ptr(), k, stream),
+              "project")
+    return E, mean, proj, evals[:k].clone()
