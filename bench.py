@@ -310,10 +310,13 @@ def run_ours(args, rank, world):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "basis": note, "n_slices": 8, "threshold": THRESHOLD,
                        "l2": f"{N_BATCHES} distinct resident batches rotated ({N_BATCHES * B * ld / 1e6:.0f} MB > 126 MB L2)",
-                       "projection_kernel": "tcgen05 kind::i8" if used_tc else "dp4a (CUDA cores)"},
+                       "projection_kernel": {2: "recognize_cluster_kernel: TMA + tcgen05 kind::i8 + DSMEM reduce + fused match (1 launch/step)",
+                                             1: "project_tc_kernel (tcgen05 kind::i8, stream-K) + fused_epilogue_kernel",
+                                             0: "project_dp4a_kernel (CUDA cores) + fused_epilogue_kernel"}[int(used_tc)]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": None,
-                         "kernel": "projection (digit-plane integer GEMM)", "kernel_ms": proj_ms,
+                         "kernel": ("recognize_cluster_kernel (whole step: projection + match)" if int(used_tc) == 2
+                                    else "projection (digit-plane integer GEMM)"), "kernel_ms": proj_ms,
                          "kernel_calls_timed": n_calls, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CROP * B,
                          "peak_source": peak_src},
             "cpu_baseline": cpu,

@@ -19,6 +19,15 @@ int row_sumsq(const uint8_t* X, int64_t ldx, int B, int D, const double* qq, dou
 int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int wq_rows,
                int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream);
 
+// ef_recognize_cluster.cu -- single-kernel form (cluster of 4, DSMEM reduction, fused match); EF_ERR_UNSUPPORTED when
+// the shape is outside its coverage (k <= 32, S*(k+1) <= 256, aligned buffers)
+int recognize_cluster(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int wq_rows,
+                      int k, int kq, int S, const int32_t* col_exp, const double* bias, const double* sumsq_ext,
+                      bool want_resid, double c0, const double* gp_padded, int kpad, const double* gnorm,
+                      const double* ginv, int64_t n, const int32_t* labels, int metric, double threshold,
+                      double* out_proj, double* out_score, int32_t* out_index, int32_t* out_label, double* out_resid,
+                      int* status, cudaStream_t stream);
+
 // ef_epilogue.cu
 bool fused_epilogue_supported(int k, int64_t n);
 int fused_epilogue_kpad(int k);   // column count the prepared gallery must be zero-padded to for the fused kernel

@@ -33,7 +33,9 @@ struct ef_model {
   int64_t x_ld = 0;
   cudaStream_t stream = nullptr;   // owned, used by the host entry points
   int ld_acc = 0;
-  bool use_tc = true;
+  int tc_mode = 2;                 // 0 dp4a, 1 tcgen05 stream-K + epilogue kernels, 2 single cluster kernel
+  int last_path = 0;
+  ef::DevBuf sumsq_w;              // weighted sum of squares for the cluster kernel (standardised models)
   // optional per-kernel timing (bench roofline): event pairs around the projection kernel of every call
   bool timing = false;
   std::vector<cudaEvent_t> ev_a, ev_b;
@@ -222,7 +224,7 @@ int ef_model_dims(const ef_model_t* m, int32_t* D, int32_t* k, int32_t* n_galler
 
 int ef_model_set_tensor_cores(ef_model_t* m, int32_t enable) {
   if (!m) return EF_ERR_INVALID;
-  m->use_tc = enable != 0;
+  m->tc_mode = enable < 0 ? 0 : (enable > 2 ? 2 : enable);
   return EF_OK;
 }
 
@@ -249,7 +251,7 @@ int ef_model_kernel_timing_read(ef_model_t* m, int32_t* n_calls, double* project
   }
   *n_calls = n;
   *project_ms_mean = n ? tot / n : 0.0;
-  if (used_tensor_cores) *used_tensor_cores = m->last_used_tc ? 1 : 0;
+  if (used_tensor_cores) *used_tensor_cores = m->last_path;
   return EF_OK;
 }
 
@@ -263,6 +265,7 @@ int ef_model_reserve(ef_model_t* m, int32_t max_batch) {
   EF_CUDA(cudaMemset(m->acc.p, 0, sizeof(int32_t) * B * m->nc_pad));
   EF_TRY(m->proj.ensure(sizeof(double) * B * m->k));
   EF_TRY(m->sumsq.ensure(sizeof(double) * B));
+  EF_TRY(m->sumsq_w.ensure(sizeof(double) * B));
   EF_CUDA(cudaMemset(m->sumsq.p, 0, sizeof(double) * B));
   EF_TRY(m->status.ensure(16));
   EF_CUDA(cudaMemset(m->status.p, 0, 16));
@@ -298,16 +301,39 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
     EF_CUDA(cudaMemsetAsync(acc, 0, sizeof(int32_t) * (size_t)m->ld_acc * m->nc_pad, st));
     EF_CUDA(cudaMemsetAsync(m->sumsq.p, 0, sizeof(double) * (size_t)m->ld_acc, st));
   }
-  m->dirty = true;
   const bool want_resid = out->resid2 != nullptr;
   double* sumsq = m->sumsq.as<double>();
+  const int32_t* labels = m->labels.p ? m->labels.as<int32_t>() : nullptr;
+  if (m->tc_mode >= 2) {
+    // single-kernel cluster form (TMA + tcgen05 + DSMEM reduction + fused match); falls through when unsupported
+    const double* sumsq_ext = nullptr;
+    if (want_resid && m->has_scale) {
+      EF_TRY(ef::row_sumsq(x, ldx, B, m->D, m->qq.as<double>(), m->sumsq_w.as<double>(), st));
+      sumsq_ext = m->sumsq_w.as<double>();
+    }
+    const int stc = ef::recognize_cluster(
+        x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, m->nc_pad, m->k, m->kq, m->S, m->col_exp.as<int32_t>(),
+        m->bias.as<double>(), sumsq_ext, want_resid, m->c0, m->gp.as<double>(), m->kpad, m->gnorm.as<double>(),
+        m->ginv.as<double>(), m->n_gallery, labels, m->metric, threshold, out->proj, out->score, out->index,
+        out->label, want_resid ? out->resid2 : nullptr, m->status.as<int>(), st);
+    if (stc == EF_OK) {
+      m->last_used_tc = true;
+      m->last_path = 2;
+      if (eb) EF_CUDA(cudaEventRecord(eb, st));
+      return EF_OK;
+    }
+    if (stc != EF_ERR_UNSUPPORTED) return stc;
+  }
+  m->dirty = true;
+  m->last_path = 0;
   // the tensor-core kernel also produces the integer sum of squares (Gen-1 residual) from the staged crop tiles
   const bool tc_sumsq = want_resid && !m->has_scale;
   int st_tc = EF_ERR_UNSUPPORTED;
-  if (m->use_tc)
+  if (m->tc_mode >= 1)
     st_tc = ef::project_tc(x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, m->nc_pad, acc, m->ld_acc,
                            tc_sumsq ? sumsq : nullptr, m->status.as<int>(), st);
   m->last_used_tc = st_tc == EF_OK;
+  m->last_path = m->last_used_tc ? 1 : 0;
   if (st_tc != EF_OK) {
     if (st_tc != EF_ERR_UNSUPPORTED) return st_tc;
     EF_TRY(ef::project_dp4a(x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, acc, m->ld_acc, st));
@@ -316,7 +342,6 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
   // 2. residual ingredient not produced by the projection kernel (weighted for the standardised models)
   if (want_resid && !(m->last_used_tc && tc_sumsq))
     EF_TRY(ef::row_sumsq(x, ldx, B, m->D, m->has_scale ? m->qq.as<double>() : nullptr, sumsq, st));
-  const int32_t* labels = m->labels.p ? m->labels.as<int32_t>() : nullptr;
   if (ef::fused_epilogue_supported(m->k, m->n_gallery)) {
     // 3. one launch: planes -> features (+ residual) -> nearest gallery row -> threshold / label
     EF_TRY(ef::fused_epilogue(acc, m->ld_acc, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(), m->bias.as<double>(),

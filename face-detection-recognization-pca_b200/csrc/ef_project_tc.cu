@@ -23,130 +23,12 @@
 
 #include "ef_common.cuh"
 #include "ef_internal.cuh"
+#include "ef_tc_common.cuh"
 
 namespace {
 
-constexpr int BLOCK_M = 128;                        // crops per tile (UMMA M, cta_group::1)
-constexpr int BLOCK_K = 128;                        // bytes of K per stage = one 128-byte swizzle row
-constexpr int UMMA_K = 32;                          // K per tcgen05.mma for 8-bit operands
-constexpr int A_STAGE_BYTES = BLOCK_M * BLOCK_K;    // 16 KB
+using namespace ef_tc;
 constexpr int kThreads = 192;                       // warp 0 TMA, warp 1 MMA + TMEM, warps 2..5 epilogue
-constexpr int kMaxStages = 8;
-constexpr int kSmemLimit = 227 * 1024;
-constexpr unsigned long long kTimeoutNs = 2000000000ull;
-
-struct Shared {
-  unsigned long long full_bar[kMaxStages];
-  unsigned long long empty_bar[kMaxStages];
-  unsigned long long tmem_full_bar;
-  unsigned long long tmem_empty_bar;
-  uint32_t tmem_base;
-  int failed;
-};
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ unsigned long long globaltimer() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  return t;
-}
-
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: false on timeout or when another role already failed.
-__device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t parity, volatile int* failed) {
-  // fast path: plain try_wait spins (each try_wait already suspends the thread for a hardware-defined interval);
-  // the (slow) global timer and the shared failure flag are only consulted every 1024 unsuccessful polls.
-  unsigned long long t0 = 0;
-  for (unsigned int polls = 1;; ++polls) {
-    if (mbar_try_wait(bar, parity)) return true;
-    if ((polls & 1023u) == 0) {
-      if (*failed) return false;
-      const unsigned long long now = globaltimer();
-      if (t0 == 0) t0 = now;
-      if (now - t0 > kTimeoutNs) {
-        *failed = 1;
-        return false;
-      }
-    }
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c_inner,
-                                            int c_outer) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
-      : "memory");
-}
-
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void umma_commit(unsigned long long* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-// D[tmem] (+)= A[smem] * B[smem], u8 x s8 -> s32
-__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                        uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-
-// Shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 bytes, 8-row atoms 1024 bytes apart.
-__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);   // start address,  bits [0,14)
-  d |= (uint64_t)1 << 16;                        // leading byte offset (unused with swizzle), bits [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset = 8 rows * 128 B, bits [32,46)
-  d |= (uint64_t)1 << 46;                        // descriptor version for sm_100
-  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-  return d;
-}
-
-// Instruction descriptor for kind::i8: D = s32, A = u8 (K-major), B = s8 (K-major), M = 128, N = n.
-__host__ __device__ constexpr uint32_t umma_idesc_i8(int n) {
-  return (2u << 4)                 // c_format = S32
-         | (0u << 7)               // a_format = unsigned 8-bit
-         | (1u << 10)              // b_format = signed 8-bit
-         | (0u << 15) | (0u << 16) // both K-major
-         | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-}
-
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 struct Args {
   int B, NC, block_n, n_tiles, m_tiles, kb_total, stages, tmem_cols;
@@ -337,11 +219,11 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (probe && threadIdx.x == 0) probe[5] = globaltimer();
 }
 
-// --------------------------------------------------------------------------------------------- host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+}  // namespace
 
+namespace ef_tc {
+
+// --------------------------------------------------------------------------------------------- host side
 EncodeTiledFn encode_fn() {
   static EncodeTiledFn fn = nullptr;
   static bool tried = false;
@@ -369,9 +251,11 @@ bool make_map(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-}  // namespace
+}  // namespace ef_tc
 
 namespace ef {
+
+using namespace ef_tc;
 
 int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int wq_rows,
                int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream) {

@@ -77,8 +77,9 @@ class Recognizer:
     def reserve(self, max_batch):
         check(self._L.ef_model_reserve(self._h, int(max_batch)), "ef_model_reserve")
 
-    def use_tensor_cores(self, enable=True):
-        check(self._L.ef_model_set_tensor_cores(self._h, 1 if enable else 0), "ef_model_set_tensor_cores")
+    def use_tensor_cores(self, mode=2):
+        """2 (default): single cluster kernel; 1 / True: tcgen05 stream-K projection + epilogue kernels; 0 / False: dp4a."""
+        check(self._L.ef_model_set_tensor_cores(self._h, int(mode)), "ef_model_set_tensor_cores")
 
     def pipeline_timeouts(self):
         """Non-zero when the tcgen05 projection kernel hit a bounded-wait timeout (synchronous read)."""
@@ -94,7 +95,7 @@ class Recognizer:
         n, ms, tc = C.c_int32(), C.c_double(), C.c_int32()
         check(self._L.ef_model_kernel_timing_read(self._h, C.byref(n), C.byref(ms), C.byref(tc)),
               "ef_model_kernel_timing_read")
-        return n.value, ms.value, bool(tc.value)
+        return n.value, ms.value, tc.value
 
     # ------------------------------------------------------------------ host buffers (numpy in, numpy out)
     def recognize(self, crops, threshold=0.7, want_features=True, want_residual=None):

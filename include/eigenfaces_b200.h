@@ -119,8 +119,9 @@ void ef_model_destroy(ef_model_t* model);
  * that later calls do not allocate. */
 int ef_model_reserve(ef_model_t* model, int32_t max_batch);
 int ef_model_dims(const ef_model_t* model, int32_t* D, int32_t* k, int32_t* n_gallery, int32_t* n_slices);
-/* Select the projection kernel: 1 (default) = tcgen05 kind::i8 tensor-core kernel when the shape is covered,
- * 0 = CUDA-core dp4a kernel.  Both produce the same integers. */
+/* Select the recognition kernels: 2 (default) = single cluster kernel (TMA + tcgen05 kind::i8 + DSMEM reduction +
+ * fused match) when the shape is covered, 1 = tcgen05 stream-K projection kernel + separate epilogue kernel(s),
+ * 0 = CUDA-core dp4a projection.  All three produce the same integers and the same labels. */
 int ef_model_set_tensor_cores(ef_model_t* model, int32_t enable);
 /* Measurement hook (bench.py roofline): when enabled, every recognise call brackets its projection kernel (the
  * dominant kernel) with CUDA events on the launching stream; _read returns the mean duration over the calls since

@@ -43,7 +43,7 @@ def test_gen1_reference_golden(golden, light_model, dark_model):
     _close_proj(p, gen1.project_face_to_eigenspace(Q[3].astype(np.float64), light_model["eigenfaces"], light_model["mean_face"]))
 
 
-@pytest.mark.parametrize("use_tc", [False, True])
+@pytest.mark.parametrize("use_tc", [0, 1, 2])
 def test_gen1_batch_vs_oracle(golden, light_model, use_tc):
     require_gpu()
     X = golden("gen1_light.npz")["X_u8"]
@@ -52,7 +52,7 @@ def test_gen1_batch_vs_oracle(golden, light_model, use_tc):
     rec = ef.gen1.recognizer_for(light_model)
     rec.use_tensor_cores(use_tc)
     res = rec.recognize(Q, 0.8)
-    rec.use_tensor_cores(True)
+    rec.use_tensor_cores(2)
     want_p = gen1.project_batch(Q, light_model["eigenfaces"], light_model["mean_face"])
     _close_proj(res.features, want_p)
     best, idx, ok = gen1.recognize_batch(Q, light_model, 0.8)
@@ -216,6 +216,26 @@ def test_gen2_full_k_model_vs_oracle(golden):
     assert np.array_equal(res.index[decided], idx[decided])
     assert np.array_equal(res.label, labels)
     assert np.array_equal(res.index[:178][decided[:178]], np.arange(178)[decided[:178]])   # self match
+
+
+def test_all_three_kernel_paths_agree_bit_for_bit(light_model, golden):
+    """dp4a (CUDA cores), tcgen05 stream-K + epilogue kernels, and the single cluster kernel compute the same integers,
+    hence the same float64 features, scores, indices, labels and residuals."""
+    require_gpu()
+    X = golden("gen1_light.npz")["X_u8"]
+    rng = np.random.default_rng(12)
+    Q = np.concatenate([X, face_like(rng, X, 411)])            # 640 crops: 5 full tiles
+    Q = np.concatenate([Q, Q[:37]])                            # + a ragged tail
+    rec = ef.Recognizer(light_model["eigenfaces"][:, :10].copy(order="F"), light_model["mean_face"],
+                        light_model["projected_data"][:, :10].copy(), metric=ef.METRIC_COSINE_G1)
+    outs = []
+    for mode in (0, 1, 2):
+        rec.use_tensor_cores(mode)
+        outs.append(rec.recognize(Q, 0.8))
+        assert rec.pipeline_timeouts() == 0
+    for o in outs[1:]:
+        for f in ("features", "score", "index", "label", "resid2"):
+            assert np.array_equal(getattr(o, f), getattr(outs[0], f)), f
 
 
 def test_device_buffers_match_host_buffers(light_model, golden):

@@ -37,6 +37,10 @@ def timed(tag, n=40):
     print(f"{tag}: step {1e3 * e0.elapsed_time(e1) / n:.1f} us, projection kernel {1e3 * ms:.1f} us (tc={tc})", flush=True)
 
 
+for mode in (2, 1):
+    rec.use_tensor_cores(mode)
+    timed(f"mode {mode}")
+rec.use_tensor_cores(1)
 for env in ({}, {"EF_TC_STAGES": "4"}, {"EF_TC_STAGES": "2"}, {"EF_TC_GRID": "128"}, {"EF_TC_GRID": "74"},
             {"EF_TC_GRID": "296"}):
     for k in ("EF_TC_STAGES", "EF_TC_GRID", "EF_TC_PROBE"):
