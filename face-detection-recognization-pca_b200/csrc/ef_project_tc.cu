@@ -44,10 +44,13 @@ struct Args {
 __global__ void __launch_bounds__(kThreads, 1)
 project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                   const Args a) {
-  extern __shared__ uint8_t smem_raw[];
-  if (a.probe && threadIdx.x == 0) a.probe[(size_t)gridDim.x * 8] = a.probe[(size_t)gridDim.x * 8] ? a.probe[(size_t)gridDim.x * 8] : globaltimer();
-  // 1024-byte alignment is required by the 128-byte swizzle atoms
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment is required by the 128-byte swizzle atoms.  The array is used directly (no pointer rounding
+  // through integers) so that the compiler keeps the shared address space and emits LDS/STS instead of generic loads.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) atomicExch(a.status, 2);
+    return;
+  }
   const int b_stage_bytes = a.block_n * BLOCK_K;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)a.stages * A_STAGE_BYTES;

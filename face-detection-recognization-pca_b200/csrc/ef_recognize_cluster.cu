@@ -15,6 +15,7 @@
 // recognize_face_with_model (scan-template-v4.py:265-287) for a whole batch.
 #include <climits>
 #include <cstdlib>
+#include <vector>
 #include <math_constants.h>
 
 #include "ef_common.cuh"
@@ -52,6 +53,7 @@ struct ClusterArgs {
   int32_t* out_label;
   double* out_resid;
   int* status;
+  unsigned long long* probe;   // debugging aid (EF_TC_PROBE): [grid][8] globaltimer stamps
 };
 
 struct ClusterShared {
@@ -81,8 +83,13 @@ template <int METRIC, int KR>
 __global__ void __launch_bounds__(kThreads, 1)
 recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w,
                          const ClusterArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // 1024-byte alignment is required by the 128-byte swizzle atoms.  The array is used directly (no pointer rounding
+  // through integers) so that the compiler keeps the shared address space and emits LDS/STS instead of generic loads.
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) atomicExch(a.status, 2);
+    return;
+  }
   const int b_stage_bytes = a.nc_pad * BLOCK_K;
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   uint8_t* sA = smem;                                            // [stages][128][128]
@@ -124,6 +131,8 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   tc_fence_after();
   const uint32_t tmem_base = sh->tmem_base;
   volatile int* failed = &sh->failed;
+  unsigned long long* probe = a.probe ? a.probe + (size_t)blockIdx.x * 8 : nullptr;
+  if (probe && tid == 0) probe[0] = globaltimer();
 
   auto load_gallery_tile = [&](int g0, int t0, int nthreads) {
     const int rows = min(a.tile_rows, a.n - g0);
@@ -160,6 +169,7 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       for (int kb = kb0; kb < kb1; ++kb) {
         if (!mbar_wait(&sh->full_bar[stage], phase, failed)) { ok = false; break; }
         tc_fence_after();
+        if (probe && kb == kb0) probe[1] = globaltimer();
         const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
         const uint32_t b_addr = smem_u32(sB + (size_t)stage * b_stage_bytes);
 #pragma unroll
@@ -170,6 +180,7 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
       if (ok) umma_commit(&sh->tmem_full_bar);
+      if (probe) probe[2] = globaltimer();
     }
   } else if (warp < 6) {
     // TMEM lane group = warp % 4; the same warps compute the exact sum of squares from the staged crop tiles
@@ -223,7 +234,9 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
 
   // ======================================================================= exchange partial tiles through DSMEM
   __syncthreads();
+  if (probe && tid == 0) probe[3] = globaltimer();
   cluster_sync_all();                               // every CTA's partial tile is in its shared memory
+  if (probe && tid == 0) probe[4] = globaltimer();
   const int b = m_tile * BLOCK_M + (int)rank * QB + lane;       // the crop this lane finishes
   const bool live = b < a.B;
   for (int c = warp; c < KR; c += kWarps) ps[c * QB + lane] = 0.0;
@@ -262,6 +275,7 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   }
   __syncthreads();
   cluster_sync_all();                               // nobody reads remote shared memory after this point
+  if (probe && tid == 0) probe[5] = globaltimer();
 
   if (warp == 0) {
     double n2 = 0.0;
@@ -361,6 +375,7 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                  : "memory");
   }
   if (tid == 0 && sh->failed) atomicExch(a.status, 1);
+  if (probe && tid == 0) probe[6] = globaltimer();
 }
 
 template <int METRIC, int KR>
@@ -387,6 +402,15 @@ int launch_cluster(const CUtensorMap& mx, const CUtensorMap& mw, ClusterArgs& a,
                                  (int)smem));
     attr = smem;
   }
+  static unsigned long long* probe_buf = nullptr;
+  const bool probing = getenv("EF_TC_PROBE") != nullptr;
+  const int grid_n = m_tiles * kCluster;
+  a.probe = nullptr;
+  if (probing && grid_n <= 4096) {
+    if (!probe_buf) EF_CUDA(cudaMalloc(&probe_buf, sizeof(unsigned long long) * 8 * 4096));
+    EF_CUDA(cudaMemsetAsync(probe_buf, 0, sizeof(unsigned long long) * 8 * 4096, stream));
+    a.probe = probe_buf;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(m_tiles * kCluster));
   cfg.blockDim = dim3(kThreads);
@@ -401,6 +425,25 @@ int launch_cluster(const CUtensorMap& mx, const CUtensorMap& mw, ClusterArgs& a,
   cfg.numAttrs = 1;
   EF_CUDA(cudaLaunchKernelEx(&cfg, recognize_cluster_kernel<METRIC, KR>, mx, mw, a));
   ef::g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (a.probe) {
+    std::vector<unsigned long long> h((size_t)grid_n * 8);
+    EF_CUDA(cudaStreamSynchronize(stream));
+    EF_CUDA(cudaMemcpy(h.data(), probe_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (int c = 0; c < grid_n; ++c) if (h[(size_t)c * 8] && h[(size_t)c * 8] < t0) t0 = h[(size_t)c * 8];
+    const char* names[7] = {"start", "first_full", "mma_issued", "block_done", "sync1", "sync2", "end"};
+    fprintf(stderr, "[ef_cluster_probe] grid %d stages %d tile_rows %d; us since first CTA start (mean/max):", grid_n, a.stages, a.tile_rows);
+    for (int i = 0; i < 7; ++i) {
+      double sum = 0, mx = 0;
+      for (int c = 0; c < grid_n; ++c) {
+        const double v = h[(size_t)c * 8 + i] ? (double)(h[(size_t)c * 8 + i] - t0) * 1e-3 : 0.0;
+        sum += v;
+        if (v > mx) mx = v;
+      }
+      fprintf(stderr, " %s %.2f/%.2f", names[i], sum / grid_n, mx);
+    }
+    fprintf(stderr, "\n");
+  }
   return EF_OK;
 }
 
