@@ -76,6 +76,9 @@ SIGNATURES = {
     "ef_fit_gen2_host": (C.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, C.POINTER(Gen2Fit), C.POINTER(FitInfo)]),
     "ef_colsum_u8_device": (C.c_int, [c_void, c_i64, c_i64, c_i32, c_void, c_void]),
     "ef_gram_u8_device": (C.c_int, [c_void, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_void, c_void]),
+    "ef_gram_u8_tc_work_bytes": (C.c_size_t, [c_i64, c_i32, c_i32]),
+    "ef_gram_u8_tc_device": (C.c_int, [c_void, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_void, c_void, C.c_size_t,
+                                       c_void]),
     "ef_gram_center_work_bytes": (C.c_size_t, [c_i32]),
     "ef_gram_center_device": (C.c_int, [c_void, c_i32, c_i32, c_void, c_i64, c_dbl, c_void, c_void, c_void]),
     "ef_eigh_work_bytes": (C.c_size_t, [c_i32]),

@@ -252,7 +252,7 @@ int launch_fused(EpiArgs& a, cudaStream_t stream) {
   a.tile_rows = rows;
   const size_t smem = sizeof(double) * ((size_t)KR * QB + (size_t)rows * (KR + 1)) + 64;
   static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
+  if (smem > attr) {   // always: dynamic + ~11 KB of static shared memory crosses the 48 KB default well below 48 KB dynamic
     EF_CUDA(cudaFuncSetAttribute(fused_epilogue_kernel<METRIC, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;
   }

@@ -173,6 +173,10 @@ int ef_fit_gen1_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
   EF_TRY(devecs.ensure(sizeof(double) * (size_t)n * n));
   EF_TRY(dE.ensure(sizeof(double) * (size_t)D * k));
   EF_TRY(dP.ensure(sizeof(double) * (size_t)N * k));
+  ef::DevBuf dG, dgw, dcw;
+  EF_TRY(dG.ensure(sizeof(int64_t) * (size_t)n * n));
+  EF_TRY(dgw.ensure(ef_gram_u8_tc_work_bytes(N, D, snapshot ? 0 : 1)));
+  EF_TRY(dcw.ensure(ef_gram_center_work_bytes(n) + 16));
   EF_CUDA(cudaMemcpy2DAsync(dX.p, ldxd, X, ldx, D, N, cudaMemcpyHostToDevice, st));
   EF_CUDA(cudaEventRecord(tm.a, st));
 
@@ -183,13 +187,15 @@ int ef_fit_gen1_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
   EF_TRY(ef_standardize_u8_device(dX.as<uint8_t>(), ldxd, N, D, dmean.as<double>(), nullptr, nullptr, dZ.as<double>(), D, st));
   const double alpha = 1.0 / (double)(N - 1);
   double* Z = dZ.as<double>();
-  if (snapshot) {
-    // cov = Xc Xc^T / (N-1)                                                                   :84
-    EF_TRY(ef_dgemm_device(N, N, D, alpha, Z, D, 1, Z, 1, D, 0.0, dA.as<double>(), N, st));
-  } else {
-    // cov = Xc^T Xc / (N-1)                                                                   :99
-    EF_TRY(ef_dgemm_device(D, D, N, alpha, Z, 1, D, Z, D, 1, 0.0, dA.as<double>(), D, st));
-  }
+  // cov = Xc Xc^T / (N-1)  (:84)  or  Xc^T Xc / (N-1)  (:99): exact integer Gram of the raw pixels on tensor cores,
+  // centred on the small matrix with an exact integer numerator (one rounding per entry)
+  const int side = snapshot ? 0 : 1;
+  EF_CUDA(cudaMemsetAsync(dG.p, 0, sizeof(int64_t) * (size_t)n * n, st));
+  int gst = ef_gram_u8_tc_device(dX.as<uint8_t>(), ldxd, N, D, 0, D, side, dG.as<int64_t>(), dgw.p, dgw.bytes, st);
+  if (gst == EF_ERR_UNSUPPORTED)
+    gst = ef_gram_u8_device(dX.as<uint8_t>(), ldxd, N, D, 0, D, side, dG.as<int64_t>(), st);
+  EF_TRY(gst);
+  EF_TRY(ef_gram_center_device(dG.as<int64_t>(), n, side, dsum.as<int64_t>(), N, alpha, dA.as<double>(), dcw.p, st));
   int sweeps = 0;
   double off = 0.0;
   const int est = ef_eigh_jacobi_device(dA.as<double>(), n, devals.as<double>(), devecs.as<double>(), dwork.p, 0, 0.0,
@@ -213,7 +219,13 @@ int ef_fit_gen1_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
   EF_CUDA(cudaMemcpyAsync(mean, dmean.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
   EF_CUDA(cudaMemcpyAsync(projected, dP.p, sizeof(double) * (size_t)N * k, cudaMemcpyDeviceToHost, st));
   EF_CUDA(cudaMemcpyAsync(eigenvalues, devals.p, sizeof(double) * k, cudaMemcpyDeviceToHost, st));
+  int32_t gram_flag = 0;
+  EF_CUDA(cudaMemcpyAsync(&gram_flag, dgw.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   EF_CUDA(cudaStreamSynchronize(st));
+  if (gram_flag) {
+    ef::set_error_detail("tcgen05 Gram pipeline timed out (mbarrier wait > 2 s)", cudaErrorLaunchTimeout);
+    return EF_ERR_CUDA;
+  }
   for (int c = 0; c < k; ++c)
     for (int d = 0; d < D; ++d) eigenfaces[(size_t)c * D + d] = Eh[(size_t)d * k + c];   // Fortran order [D][k]
   if (info) {

@@ -24,9 +24,13 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
 int recognize_cluster(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int wq_rows,
                       int k, int kq, int S, const int32_t* col_exp, const double* bias, const double* sumsq_ext,
                       bool want_resid, double c0, const double* gp_padded, int kpad, const double* gnorm,
-                      const double* ginv, int64_t n, const int32_t* labels, int metric, double threshold,
-                      double* out_proj, double* out_score, int32_t* out_index, int32_t* out_label, double* out_resid,
-                      int* status, cudaStream_t stream);
+                      const double* ginv, const void* gimg, int64_t n, const int32_t* labels, int metric,
+                      double threshold, double* out_proj, double* out_score, int32_t* out_index, int32_t* out_label,
+                      double* out_resid, int* status, cudaStream_t stream);
+// float16 [g_hi | g_lo | g_hi] image of a prepared gallery for the tensor-core filter of the cluster kernel
+size_t gallery_image_bytes(int k, int64_t n);
+int gallery_image(const double* gp, int kr, const double* ginv, int64_t n, int k, int metric, void* img,
+                  cudaStream_t stream);
 
 // ef_epilogue.cu
 bool fused_epilogue_supported(int k, int64_t n);
@@ -50,5 +54,10 @@ int match(const double* p, int64_t ldp, int B, int k, const double* gp, int64_t 
           int64_t index_base, int metric, double* out_score, int64_t* out_index, void* work, cudaStream_t stream);
 int label_lookup(const double* score, const int64_t* index, int B, const int32_t* labels, int metric, double threshold,
                  int32_t* out_index32, int32_t* out_label, cudaStream_t stream);
+
+// ef_gram_tc.cu -- exact integer Gram A A^T of uint8 rows on tensor cores (upper triangle + mirror), G int64 += .
+int gram_tc(const uint8_t* A, int64_t lda, int64_t n, int64_t K, int64_t* G, int64_t ldg, int* status,
+            cudaStream_t stream);
+int transpose_u8(const uint8_t* in, int64_t ldi, int64_t rows, int cols, uint8_t* out, int64_t ldo, cudaStream_t stream);
 
 }  // namespace ef

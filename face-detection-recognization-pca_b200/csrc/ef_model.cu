@@ -20,7 +20,7 @@ struct ef_model {
   int64_t ldw = 0;
   bool with_residual = false, has_scale = false;
   double c0 = 0.0;
-  ef::DevBuf wq, col_exp, bias, qq, gp, gnorm, ginv, labels;
+  ef::DevBuf wq, col_exp, bias, qq, gp, gnorm, ginv, gimg, labels;
   int kpad = 0;                    // column pitch of the prepared gallery (zero padded for the fused epilogue)
   // workspaces (sized by reserve)
   int reserved = 0;
@@ -196,6 +196,13 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
   if (st == EF_OK)
     st = ef::gallery_prepare(raw.as<double>(), k, desc->n_gallery, k, m->metric, m->gp.as<double>(), m->kpad,
                              m->gnorm.as<double>(), m->ginv.as<double>(), m->stream);
+  // float16 image of the gallery for the tensor-core filter of the cluster kernel (cosine metrics, k <= 32)
+  if (st == EF_OK && m->metric != EF_METRIC_L2 && ef::fused_epilogue_supported(k, desc->n_gallery)) {
+    st = m->gimg.ensure(ef::gallery_image_bytes(k, desc->n_gallery));
+    if (st == EF_OK)
+      st = ef::gallery_image(m->gp.as<double>(), m->kpad, m->ginv.as<double>(), desc->n_gallery, k, m->metric,
+                             m->gimg.p, m->stream);
+  }
   if (st == EF_OK) {
     cudaError_t e = cudaStreamSynchronize(m->stream);
     if (e != cudaSuccess) { ef::set_error_detail("gallery_prepare", e); st = EF_ERR_CUDA; }
@@ -314,7 +321,7 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
     const int stc = ef::recognize_cluster(
         x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, m->nc_pad, m->k, m->kq, m->S, m->col_exp.as<int32_t>(),
         m->bias.as<double>(), sumsq_ext, want_resid, m->c0, m->gp.as<double>(), m->kpad, m->gnorm.as<double>(),
-        m->ginv.as<double>(), m->n_gallery, labels, m->metric, threshold, out->proj, out->score, out->index,
+        m->ginv.as<double>(), m->gimg.p, m->n_gallery, labels, m->metric, threshold, out->proj, out->score, out->index,
         out->label, want_resid ? out->resid2 : nullptr, m->status.as<int>(), st);
     if (stc == EF_OK) {
       m->last_used_tc = true;

@@ -151,7 +151,14 @@ def fit_gen1_sharded(X_local, n_total, n_components, group=None):
     G, colsum = buf[:D * D], buf[D * D:]
     if Nr:
         check(L.ef_colsum_u8_device(X_local.data_ptr(), X_local.stride(0), Nr, D, colsum.data_ptr(), stream), "colsum")
-        check(L.ef_gram_u8_device(X_local.data_ptr(), X_local.stride(0), Nr, D, 0, D, 1, G.data_ptr(), stream), "gram")
+        # exact integer X_r^T X_r on tensor cores (tcgen05 kind::i8); the dp4a kernel covers unaligned buffers
+        wb = int(L.ef_gram_u8_tc_work_bytes(Nr, D, 1))
+        gwork = torch.empty(wb, dtype=torch.uint8, device=dev)
+        st_g = L.ef_gram_u8_tc_device(X_local.data_ptr(), X_local.stride(0), Nr, D, 0, D, 1, G.data_ptr(),
+                                      gwork.data_ptr(), wb, stream)
+        if st_g == _lib.EF_ERR_UNSUPPORTED:
+            st_g = L.ef_gram_u8_device(X_local.data_ptr(), X_local.stride(0), Nr, D, 0, D, 1, G.data_ptr(), stream)
+        check(st_g, "gram")
     allreduce_exact(buf, group)
     cov = torch.empty((D, D), dtype=torch.float64, device=dev)
     check(L.ef_gram_center_device(G.data_ptr(), D, 1, colsum.data_ptr(), int(n_total), 1.0 / (n_total - 1),

@@ -221,6 +221,18 @@ int ef_colsum_u8_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int
  * side = 1: G = X^T X (D x D, over the rows given).  G int64 [n][n] row-major, ACCUMULATED into (+=). */
 int ef_gram_u8_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int32_t d0, int32_t d1, int32_t side,
                       int64_t* G, ef_stream_t stream);
+/* The same exact integer Gram on TENSOR CORES: tcgen05 kind::i8 (u8 x u8 -> s32 in TMEM), TMA-staged 128 x 256
+ * tiles, s32 segments of <= 32768 bytes of K flushed into the int64 result, only upper-triangle tiles computed and the
+ * lower triangle mirrored.  Same contract as ef_gram_u8_device (G += ...; G must be symmetric on entry, e.g. zero);
+ * side 1 transposes X into `work` first so that both operands are K-major.
+ *   work: device scratch of ef_gram_u8_tc_work_bytes(N, D, side) bytes, 256-byte aligned.  Its first int32 is a
+ *   health flag: non-zero after the call completes means an mbarrier wait inside the kernel timed out.
+ * EF_ERR_UNSUPPORTED (use ef_gram_u8_device) when X or ldx is not 16-byte aligned, d0 % 16 != 0, or side 1 with a
+ * pixel sub-range.  Replaces np.dot(Xc, Xc.T) / np.cov(Xc.T) at useless/train.py:84,99 together with
+ * ef_gram_center_device. */
+size_t ef_gram_u8_tc_work_bytes(int64_t N, int32_t D, int32_t side);
+int ef_gram_u8_tc_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int32_t d0, int32_t d1, int32_t side,
+                         int64_t* G, void* work, size_t work_bytes, ef_stream_t stream);
 /* Centre an integer Gram into the float64 covariance-like matrix with an exact integer numerator:
  * side 0: C[i][j] = alpha * (n^2 G[i][j] - n (r_i + r_j) + g) / n^2, r = row sums of G, g = grand sum (double centring)
  * side 1: C[a][b] = alpha * (N G[a][b] - s_a s_b) / N, s = column sums of X, N = total rows.

@@ -124,3 +124,61 @@ def test_match_kernels_sharded_equals_whole():
             Pn = P / np.linalg.norm(P, axis=1, keepdims=True); Gn = G / np.linalg.norm(G, axis=1, keepdims=True)
             assert np.array_equal(results[0][1], (Pn @ Gn.T).argmax(1))
         assert results[0][1][-1] == 100                                   # three identical rows: lowest index wins
+
+
+def _gram_tc(torch, L, x, N, D, side, G, d0=0, d1=None):
+    d1 = D if d1 is None else d1
+    wb = int(L.ef_gram_u8_tc_work_bytes(N, D, side))
+    work = torch.empty(wb, dtype=torch.uint8, device="cuda")
+    st = L.ef_gram_u8_tc_device(x.data_ptr(), x.stride(0), N, D, d0, d1, side, G.data_ptr(), work.data_ptr(), wb,
+                                _stream(torch))
+    ef._lib.check(st, "ef_gram_u8_tc_device")
+    torch.cuda.synchronize()
+    assert int(work[:4].view(torch.int32).item()) == 0, "tcgen05 Gram pipeline timed out"
+
+
+@pytest.mark.parametrize("N,D,side", [
+    (229, 10000, 0),      # the shipped snapshot Gram (stream-K + RED)
+    (150, 1000, 1),       # covariance side through the transposed copy
+    (1, 16, 0), (5, 33, 1), (130, 257, 0), (300, 4096, 1),      # ragged tiles, K tails, n = 1
+    (64, 70000, 0),       # K > 32768: s32 segments flushed into int64
+    (40, 5000, 1),        # D x D = 5000 x 5000: whole-tile schedule (>= 2 tiles per SM), exclusive read-add-write
+])
+def test_tensor_core_gram_is_exact(N, D, side):
+    """tcgen05 kind::i8 SYRK == numpy int64 X X^T / X^T X, bit for bit, including the += contract."""
+    torch = require_gpu()
+    L = ef._lib.lib()
+    rng = np.random.default_rng(N * 7 + D)
+    ld = (D + 15) // 16 * 16
+    Xp = np.zeros((N, ld), dtype=np.uint8)
+    Xp[:, :D] = rng.integers(0, 256, (N, D), dtype=np.uint8)
+    if N >= 64 and side == 0:
+        Xp[3, :D] = 255                                  # worst case magnitude on a full row
+    x = torch.from_numpy(Xp).cuda()[:, :D]
+    Xi = Xp[:, :D].astype(np.int64)
+    n = N if side == 0 else D
+    want = Xi @ Xi.T if side == 0 else Xi.T @ Xi
+    G = torch.zeros((n, n), dtype=torch.int64, device="cuda")
+    _gram_tc(torch, L, x, N, D, side, G)
+    assert np.array_equal(G.cpu().numpy(), want)
+    _gram_tc(torch, L, x, N, D, side, G)                 # accumulates
+    assert np.array_equal(G.cpu().numpy(), 2 * want)
+    if side == 0 and D >= 64:                             # pixel sub-ranges (column-sharded snapshot Gram)
+        G.zero_()
+        cut = (D // 2) // 16 * 16
+        _gram_tc(torch, L, x, N, D, 0, G, 0, cut)
+        _gram_tc(torch, L, x, N, D, 0, G, cut, D)
+        assert np.array_equal(G.cpu().numpy(), want)
+
+
+def test_tensor_core_gram_matches_cuda_core_gram_all_255():
+    """Largest possible s32 segment sums (all pixels 255) agree between the tcgen05 and the dp4a kernels."""
+    torch = require_gpu()
+    L = ef._lib.lib()
+    N, D = 140, 40000
+    x = torch.full((N, D), 255, dtype=torch.uint8, device="cuda")
+    G1 = torch.zeros((N, N), dtype=torch.int64, device="cuda")
+    G2 = torch.zeros((N, N), dtype=torch.int64, device="cuda")
+    _gram_tc(torch, L, x, N, D, 0, G1)
+    ef._lib.check(L.ef_gram_u8_device(x.data_ptr(), D, N, D, 0, D, 0, G2.data_ptr(), _stream(torch)), "gram")
+    assert torch.equal(G1, G2) and int(G1[0, 0].item()) == D * 255 * 255

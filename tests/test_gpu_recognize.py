@@ -281,3 +281,49 @@ def test_baseline_config2_full_size_properties(light_model):
     assert np.array_equal(r1.label[sub], np.where(sims.max(1) >= 0.5, labels[np.argmax(sims, 1)], -1))
     # the planted coefficients are recovered: projections correlate with c
     assert np.corrcoef(r1.features[:, 0], c[:, 0])[0, 1] > 0.99
+
+
+@pytest.mark.parametrize("metric", [ef.METRIC_COSINE_SK, ef.METRIC_COSINE_G1])
+@pytest.mark.parametrize("k,n_gallery", [(10, 1024), (3, 1), (16, 255), (32, 700), (7, 2049)])
+def test_tensor_core_filter_is_exact_on_adversarial_galleries(metric, k, n_gallery):
+    """The tcgen05 float16 filter + float64 re-score of the cluster kernel returns the SAME arg-best as the full float64
+    scan (paths 0 and 1) on galleries built to defeat an approximate matcher: exact duplicates (lowest index must win),
+    near-duplicates 1e-9 .. 1e-5 apart, zero rows, rows of wildly different norms, and queries that are gallery rows."""
+    require_gpu()
+    rng = np.random.default_rng(1000 * k + n_gallery + metric)
+    D = 32 * 32
+    E = np.linalg.qr(rng.normal(size=(D, k)))[0]
+    mu = rng.uniform(60, 200, D)
+    G = rng.normal(size=(n_gallery, k)) * rng.uniform(1, 300, (1, k))
+    if n_gallery >= 64:
+        G[40] = G[7]                                            # exact duplicates, far apart in index
+        G[n_gallery - 1] = G[7]
+        for i, eps in enumerate((1e-9, 1e-7, 1e-6, 1e-5)):       # near duplicates below / at the filter resolution
+            G[50 + i] = G[11] * (1.0 + 0.0) + eps * rng.normal(size=k) * np.abs(G[11]).max()
+        G[60] = 0.0                                             # zero row
+        G[61] = G[12] * 1e-6                                    # same direction, tiny norm
+        G[62] = G[12] * 1e6
+    B = 300
+    coef = np.concatenate([G[rng.integers(0, n_gallery, B - 44)] + rng.normal(size=(B - 44, k)) * 0.5,
+                           G[rng.integers(0, n_gallery, 44)]])
+    coef = coef / np.abs(coef).max() * 40.0                      # keep the crops inside [0, 255]
+    Q = np.clip(np.rint(mu + coef @ E.T), 0, 255).astype(np.uint8)
+    Q[5] = np.clip(np.rint(mu), 0, 255).astype(np.uint8)         # (almost) zero projection
+    rec = ef.Recognizer(E, mu, G, metric=metric)
+    outs = []
+    for mode in (1, 2):
+        rec.use_tensor_cores(mode)
+        outs.append(rec.recognize(Q, 0.3))
+        assert rec.pipeline_timeouts() == 0
+    for f in ("features", "score", "index", "label", "resid2"):
+        assert np.array_equal(getattr(outs[0], f), getattr(outs[1], f)), f
+    # and against numpy on the device features (float64): arg-max with first-maximum tie rule
+    P = outs[1].features
+    if metric == ef.METRIC_COSINE_SK:
+        sims = gen2.sk_cosine_similarity(P, G)
+    else:
+        sims = gen1.cosine_matrix(P, G)
+    srt = np.sort(sims, axis=1)
+    decided = (srt[:, -1] - srt[:, -2]) > 1e-12 if n_gallery > 1 else np.ones(B, bool)
+    assert np.array_equal(outs[1].index[decided], np.argmax(sims, axis=1)[decided])
+    np.testing.assert_allclose(outs[1].score, sims.max(1), atol=SCORE_ATOL)
