@@ -49,7 +49,7 @@ static_assert(QB == 32, "one crop per lane");
 constexpr int kScanWarps = 8;
 constexpr int kGalTile = 256;               // gallery rows per filter MMA (UMMA N)
 constexpr int kMaxRing = 8;
-constexpr int kListCap = 512;               // re-score list entries per CTA (2 per scanning thread in the common case)
+constexpr int kListCap = 256;               // re-score list entries per CTA (2 per scanning thread in the common case)
 // Filter error bound.  Per component |a b - (a_hi b_hi + a_hi b_lo + a_lo b_hi)| <= 3 * 2^-22 |a b| + 2^-24 (float16
 // hi/lo split, subnormal floor), summed with |a|,|b| <= 1 and Cauchy-Schwarz: < 2e-6 for k <= 32; the 3k <= 96 exact
 // float16 products are accumulated in float32 with at most 2^-22 relative error per addition: < 2.3e-5.  5e-5 covers
@@ -76,12 +76,12 @@ struct ClusterArgs {
   int32_t* out_label;
   double* out_resid;
   int* status;
-  unsigned long long* probe;   // debugging aid (EF_TC_PROBE): [grid][8] globaltimer stamps
+  unsigned long long* probe;   // debugging aid (EF_TC_PROBE): [grid][32] globaltimer stamps
   // tensor-core filter
   int filter, kf, ring, g_tiles;
-  const __half* gimg;          // [g_tiles][256 rows x kf] float16 image, canonical no-swizzle K-major core matrices
+  const __half* gimg;          // [g_tiles][256 rows x kf] float16 image, swizzled K-major (swz_chunk_offset)
   // shared-memory offsets (bytes from the dynamic base), computed on the host
-  int off_sum, off_ps, off_pe, off_gal, off_aimg, off_sh;
+  int off_recv, off_ps, off_pe, off_gal, off_aimg, off_sh;
 };
 
 struct ClusterShared {
@@ -94,9 +94,10 @@ struct ClusterShared {
   unsigned long long score_empty[2];
   uint32_t tmem_base;
   int failed;
+  int list_cnt, overflow;
   double pn[QB];
   double xu[QB];
-  int list_cnt;
+  unsigned long long ssq_recv[kCluster][QB];       // written by the four CTAs of the cluster (DSMEM stores)
   float fmax_s[kScanWarps][QB];
   int list_L[kListCap], list_j[kListCap], list_label[kListCap];
   double list_key[kListCap], list_score[kListCap];
@@ -117,9 +118,9 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
 }
 
 // float16 hi / lo split of a value in [-1, 1]
-__device__ __forceinline__ void split_half(double v, __half& hi, __half& lo) {
-  hi = __double2half(v);
-  lo = __double2half(v - (double)__half2float(hi));
+__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
 }
 
 // Exact float64 score of gallery row j for the crop in column L of pe; same fma order as the full float64 scan.
@@ -163,11 +164,8 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   uint8_t* sA = smem;                                            // [stages][128][128]
   uint8_t* sB = smem + (size_t)a.stages * A_STAGE_BYTES;         // [stages][nc_pad][128]
-  // after the main loop the stage area is reused for the partial tile, grouped by destination CTA:
-  int32_t* part = reinterpret_cast<int32_t*>(smem);             // [4 dest][nc_pad][32] int32
-  unsigned long long* ssq_s = reinterpret_cast<unsigned long long*>(smem + (size_t)a.nc_pad * BLOCK_M * 4);   // [128]
-  int32_t* sum_s = reinterpret_cast<int32_t*>(smem + a.off_sum);  // [nc_pad][32] cluster-wide sums of my 32 crops
-  double* ps = reinterpret_cast<double*>(smem + a.off_ps);       // [KR][QB]
+  int32_t* recv = reinterpret_cast<int32_t*>(smem + a.off_recv); // [4 source CTAs][nc_pad][32] partial sums of MY crops
+  double* ps = reinterpret_cast<double*>(smem + a.off_ps);       // [KR][QB] features
   double* pe = reinterpret_cast<double*>(smem + a.off_pe);       // [KR][QB] features as the exact scorer uses them
   uint8_t* gal = smem + a.off_gal;                               // filter: ring of float16 gallery tiles
   double* gs = reinterpret_cast<double*>(gal);                   // float64 scan: [tile_rows][KR] + [tile_rows]
@@ -182,8 +180,9 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   const int kb1 = (int)((long long)a.kb_total * (rank + 1) / kCluster);
   const bool fused_ssq = a.want_resid && a.sumsq_ext == nullptr;
   const bool filter = METRIC != EF_METRIC_L2 && a.filter != 0;
-  const uint32_t gal_tile_bytes = (uint32_t)kGalTile * (uint32_t)a.kf * 2u;
-  const int n_seq = 2 * a.g_tiles;                               // filter: pass 0 (+ a rare pass 1) over all gallery tiles
+  const int row_bytes = a.kf * 2;
+  const uint32_t gal_tile_bytes = (uint32_t)kGalTile * (uint32_t)row_bytes;
+  const int n_seq = 2 * a.g_tiles;                               // filter: pass 0 + pass 1 over all gallery tiles
   // per-column constants of the feature combination, fetched before the main loop (off the critical path)
   int my_exp[3] = {0, 0, 0};
   double my_bias[3] = {0.0, 0.0, 0.0};
@@ -212,6 +211,7 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     }
     sh->failed = 0;
     sh->list_cnt = 0;
+    sh->overflow = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -224,6 +224,7 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  cluster_arrive();                                 // "this CTA runs": awaited before the first DSMEM store below
   const uint32_t tmem_base = sh->tmem_base;
   volatile int* failed = &sh->failed;
   unsigned long long* probe = a.probe ? a.probe + (size_t)blockIdx.x * 32 : nullptr;
@@ -255,6 +256,8 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
     }
+    __syncwarp();
+    cluster_wait();
   } else if (warp == 1) {
     if (lane == 0) {
       int stage = 0;
@@ -277,6 +280,8 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       if (ok) umma_commit(&sh->tmem_full_bar);
       if (probe) probe[2] = globaltimer();
     }
+    __syncwarp();
+    cluster_wait();
   } else if (warp < 6) {
     // TMEM lane group = warp % 4; the same warps compute the exact sum of squares from the staged crop tiles
     const int lane_group = warp & 3;
@@ -304,12 +309,15 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
     }
-    // drain the accumulator into shared memory (the pipeline stages are free once the last MMA has completed and
-    // all four warps have finished reading the last crop tile).  Rows of lane group q belong to destination CTA q.
+    // drain the accumulator: rows of lane group q belong to CTA q of the cluster, which finishes those 32 crops --
+    // PUSH the partial sums straight into its receive buffer (st.shared::cluster: no round-trip latency)
     if (ok && kb1 > kb0) ok = mbar_wait(&sh->tmem_full_bar, 0, failed);
+    ok = __all_sync(0xffffffffu, ok);
     tc_fence_after();
-    asm volatile("bar.sync 1, 128;" ::: "memory");
-    int32_t* my_part = part + (size_t)lane_group * a.nc_pad * 32 + lane;
+    __syncwarp();
+    cluster_wait();                                 // every CTA of the cluster has started: its shared memory exists
+    const uint32_t dst = map_to_cta(smem_u32(recv) + (uint32_t)(((int)rank * a.nc_pad * 32 + lane) * 4),
+                                    (uint32_t)lane_group);
     for (int c0 = 0; c0 < a.nc_pad; c0 += 16) {
       uint32_t v[16];
       if (ok && kb1 > kb0) {
@@ -319,119 +327,103 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         for (int j = 0; j < 16; ++j) v[j] = 0u;
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) my_part[(size_t)(c0 + j) * 32] = (int32_t)v[j];
+      for (int j = 0; j < 16; ++j) st_cluster_u32(dst + (uint32_t)(c0 + j) * 128u, v[j]);
     }
-    ssq_s[row_in_tile] = ssq;
+    st_cluster_u64(map_to_cta(smem_u32(&sh->ssq_recv[rank][lane]), (uint32_t)lane_group), ssq);
     tc_fence_before();
-  } else if (filter) {
-    // warp 6: first fill of the float16 gallery ring while the crops stream
-    if (warp == 6 && lane == 0) {
-      const int first = min(a.ring, n_seq);
-      for (int s = 0; s < first; ++s) {
-        mbar_arrive_expect_tx(&sh->gal_full[s], gal_tile_bytes);
-        bulk_load(gal + (size_t)s * gal_tile_bytes,
-                  reinterpret_cast<const uint8_t*>(a.gimg) + (size_t)(s % a.g_tiles) * gal_tile_bytes, gal_tile_bytes,
-                  &sh->gal_full[s]);
-      }
-    }
   } else {
-    // warps 6..15: pull the first float64 gallery tile into shared memory while the crops stream
-    load_gallery_tile(0, tid - 6 * 32, kThreads - 6 * 32);
+    if (filter) {
+      // warp 6: first fill of the float16 gallery ring while the crops stream
+      if (warp == 6 && lane == 0) {
+        const int first = min(a.ring, n_seq);
+        for (int s = 0; s < first; ++s) {
+          mbar_arrive_expect_tx(&sh->gal_full[s], gal_tile_bytes);
+          bulk_load(gal + (size_t)s * gal_tile_bytes,
+                    reinterpret_cast<const uint8_t*>(a.gimg) + (size_t)(s % a.g_tiles) * gal_tile_bytes, gal_tile_bytes,
+                    &sh->gal_full[s]);
+        }
+      }
+    } else {
+      // warps 6..15: pull the first float64 gallery tile into shared memory while the crops stream
+      load_gallery_tile(0, tid - 6 * 32, kThreads - 6 * 32);
+    }
+    __syncwarp();
+    cluster_wait();
   }
 
-  // ======================================================================= exchange partial tiles through DSMEM
+  // ======================================================================= partial tiles have been exchanged (DSMEM)
   __syncthreads();
   if (probe && tid == 0) probe[3] = globaltimer();
-  cluster_sync_all();                               // every CTA's partial tile is in its shared memory
+  cluster_sync_all();                               // all four partial slabs of my 32 crops are in my receive buffer
   if (probe && tid == 0) probe[4] = globaltimer();
   const int b = m_tile * BLOCK_M + (int)rank * QB + lane;       // the crop this lane finishes
   const bool live = b < a.B;
-  {
-    // pass 1: my slab (destination = rank) of all four CTAs, summed 16 bytes at a time (exact: |full-K sum| < 2^31)
-    const uint32_t slab_local = smem_u32(part) + rank * (uint32_t)a.nc_pad * 128u;
-    uint32_t slab[kCluster];
-#pragma unroll
-    for (int q = 0; q < kCluster; ++q) slab[q] = map_to_cta(slab_local, (uint32_t)q);
-    const int n_vec = a.nc_pad * 8;
-    for (int e = tid; e < n_vec; e += kThreads) {
-      int4 acc = ld_cluster_v4(slab[0] + (uint32_t)e * 16u);
-#pragma unroll
-      for (int q = 1; q < kCluster; ++q) {
-        const int4 v = ld_cluster_v4(slab[q] + (uint32_t)e * 16u);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
-      }
-      reinterpret_cast<int4*>(sum_s)[e] = acc;
-    }
-  }
   unsigned long long ssq_total = 0;
   if (warp == 0 && fused_ssq) {
-    const uint32_t ssq_local = smem_u32(ssq_s + (int)rank * QB + lane);
 #pragma unroll
-    for (int q = 0; q < kCluster; ++q) ssq_total += ld_cluster_u64(map_to_cta(ssq_local, (uint32_t)q));
+    for (int q = 0; q < kCluster; ++q) ssq_total += sh->ssq_recv[q][lane];
   }
-  for (int c = warp; c < KR; c += kWarps) ps[c * QB + lane] = 0.0;
-  if (warp == 0) sh->xu[lane] = 0.0;
-  if (probe && tid == 0) probe[13] = globaltimer();
-  __syncthreads();
-  if (probe && tid == 0) probe[14] = globaltimer();
-  cluster_arrive();                                 // my remote reads are done; the matching wait is at the very end
-  // pass 2: digit planes -> float64 features (small planes first)
-  for (int c = warp, it = 0; c < a.kq; c += kWarps, ++it) {
+  // digit planes -> float64 features: exact integer sum over the four K quarters, small planes first
+  for (int c = warp, it = 0; c < KR; c += kWarps, ++it) {
     double v = 0.0;
-    for (int s = a.S - 1; s >= 0; --s)
-      v += (double)sum_s[(s * a.kq + c) * 32 + lane] * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
-    v = ldexp(v, my_exp[it]);
+    if (c < a.kq) {
+      for (int s = a.S - 1; s >= 0; --s) {
+        const int32_t* src = recv + (s * a.kq + c) * 32 + lane;
+        int sum = 0;
+#pragma unroll
+        for (int q = 0; q < kCluster; ++q) sum += src[q * a.nc_pad * 32];     // exact: |full-K sum| < 2^31
+        v += (double)sum * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
+      }
+      v = ldexp(v, my_exp[it]);
+    }
     if (c < a.k) {
       v -= my_bias[it];
-      ps[c * QB + lane] = v;
       if (a.out_proj && live) a.out_proj[(size_t)b * a.k + c] = v;
-    } else {
-      sh->xu[lane] = v;
+    }
+    ps[c * QB + lane] = c < a.k ? v : 0.0;        // padding columns (k .. KR) must be exact zeros
+    if (c >= a.k && c < a.kq) sh->xu[lane] = v;    // residual column x . u
+  }
+  if (KR < a.kq && warp == 0) {                     // residual column beyond the padded feature count
+    for (int c = KR; c < a.kq; ++c) {
+      double v = 0.0;
+      for (int s = a.S - 1; s >= 0; --s) {
+        const int32_t* src = recv + (s * a.kq + c) * 32 + lane;
+        int sum = 0;
+#pragma unroll
+        for (int q = 0; q < kCluster; ++q) sum += src[q * a.nc_pad * 32];
+        v += (double)sum * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
+      }
+      sh->xu[lane] = ldexp(v, a.col_exp[c]);
     }
   }
   __syncthreads();
   if (probe && tid == 0) probe[5] = globaltimer();
 
-  // every thread derives the norm of ITS lane's crop (same fma order in all warps: bit-identical values)
+  // every thread derives the squared norm of ITS lane's crop (same fma order in all warps: bit-identical values)
   double n2 = 0.0;
   for (int c = 0; c < a.k; ++c) n2 = fma(ps[c * QB + lane], ps[c * QB + lane], n2);
-  double pn = sqrt(n2);
-  if (METRIC == EF_METRIC_COSINE_SK && pn == 0.0) pn = 1.0;
-  if (warp == 0) {
-    sh->pn[lane] = pn;
-    if (a.want_resid && live) {
-      const double sq = fused_ssq ? (double)ssq_total : a.sumsq_ext[b];
-      const double r = sq - 2.0 * sh->xu[lane] + a.c0 - n2;
-      a.out_resid[b] = r > 0.0 ? r : 0.0;
-    }
-  }
 
   if (filter) {
     // ===================================================================== tensor-core filter + exact re-score
     const int KC = a.kf >> 3;                       // 16-byte chunks (8 halfs) per row
-    // pe: the feature vector exactly as the float64 scan uses it (divided by its norm for the sklearn rule)
-    for (int c = warp; c < KR; c += kWarps) {
-      double v = ps[c * QB + lane];
-      if (METRIC == EF_METRIC_COSINE_SK) v = v / pn;
-      pe[c * QB + lane] = v;
-    }
     {
-      // A operand: rows r = lane + 32 q hold crop `lane` (the four TMEM lane groups see the same 32 crops),
-      // K = [hi | hi | lo]; this thread writes the 16-byte chunks (q, kc) = warp, warp + 16, ...
-      const double rinv = pn > 0.0 ? 1.0 / pn : 0.0;
+      // A operand (float32 arithmetic is plenty: the filter is approximate by construction): rows r = lane + 32 q hold
+      // crop `lane` (the four TMEM lane groups see the same 32 crops), K = [hi | hi | lo]; this thread writes the
+      // 16-byte chunks (q, kc) = warp, warp + 16, ...
+      const float rinv = n2 > 0.0 ? rsqrtf((float)n2) : 0.f;
+      const int kc_log2 = 31 - __clz(KC);
       for (int e = warp; e < 4 * KC; e += kWarps) {
-        const int qq = e / KC, kc = e - qq * KC, r = lane + 32 * qq;
+        const int qq = e >> kc_log2, kc = e & (KC - 1), r = lane + 32 * qq;
         __align__(16) __half h[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int kk = kc * 8 + i;
           const int seg = kk >= 3 * a.k ? 3 : (kk >= 2 * a.k ? 2 : (kk >= a.k ? 1 : 0));
-          __half hi = __float2half(0.f), lo = hi;
-          if (seg < 3) split_half(ps[(kk - seg * a.k) * QB + lane] * rinv, hi, lo);
+          __half hi = __float2half_rn(0.f), lo = hi;
+          if (seg < 3) split_half((float)ps[(kk - seg * a.k) * QB + lane] * rinv, hi, lo);
           h[i] = seg < 2 ? hi : lo;
         }
-        *reinterpret_cast<uint4*>(aimg + ((size_t)((r >> 3) * KC + kc) * 128 + (r & 7) * 16)) =
-            *reinterpret_cast<const uint4*>(h);
+        *reinterpret_cast<uint4*>(aimg + swz_chunk_offset(r, kc, row_bytes, BLOCK_M)) = *reinterpret_cast<const uint4*>(h);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
@@ -440,35 +432,70 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     if (warp == 0) {
       // gallery ring refills (the first `ring` tiles were requested while the crops streamed)
       if (lane == 0) {
+        int slot = 0, t = a.ring % a.g_tiles;
+        uint32_t ephase = 0;                       // parity of the (use - 1)-th completion of gal_empty[slot]
         for (int s = a.ring; s < n_seq; ++s) {
-          const int slot = s % a.ring, use = s / a.ring;
-          if (!mbar_wait(&sh->gal_empty[slot], (uint32_t)((use - 1) & 1), failed)) break;
+          if (!mbar_wait(&sh->gal_empty[slot], ephase, failed)) break;
           mbar_arrive_expect_tx(&sh->gal_full[slot], gal_tile_bytes);
           bulk_load(gal + (size_t)slot * gal_tile_bytes,
-                    reinterpret_cast<const uint8_t*>(a.gimg) + (size_t)(s % a.g_tiles) * gal_tile_bytes, gal_tile_bytes,
+                    reinterpret_cast<const uint8_t*>(a.gimg) + (size_t)t * gal_tile_bytes, gal_tile_bytes,
                     &sh->gal_full[slot]);
+          if (++slot == a.ring) { slot = 0; ephase ^= 1; }
+          if (++t == a.g_tiles) t = 0;
         }
+      }
+      __syncwarp();
+      // squared distance from face space (needs no square root)
+      if (a.want_resid && live) {
+        const double sq = fused_ssq ? (double)ssq_total : a.sumsq_ext[b];
+        const double r = sq - 2.0 * sh->xu[lane] + a.c0 - n2;
+        a.out_resid[b] = r > 0.0 ? r : 0.0;
       }
     } else if (warp == 1) {
       if (lane == 0) {
+        // single-thread issue loop: everything that can be precomputed is (descriptors advance linearly with the
+        // shared-memory address, so the B descriptor of a ring slot is a base value plus a constant per slot)
         const uint32_t idesc = umma_idesc_f16(kGalTile);
-        const uint32_t a_addr = smem_u32(aimg);
-        const uint32_t sbo = (uint32_t)KC * 128u;
+        const int n_ks = a.kf >> 4;
+        uint64_t adesc[8], bdesc0[8];
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          adesc[ks] = ks < n_ks ? umma_desc_swz(smem_u32(aimg), ks, row_bytes, BLOCK_M) : 0ull;
+          bdesc0[ks] = ks < n_ks ? umma_desc_swz(smem_u32(gal), ks, row_bytes, kGalTile) : 0ull;
+        }
+        const uint64_t slot_step = (uint64_t)(gal_tile_bytes >> 4);
+        int slot = 0;
+        uint32_t gphase = 0;
         for (int s = 0; s < n_seq; ++s) {
-          const int slot = s % a.ring, guse = s / a.ring, buf = s & 1, suse = s >> 1;
-          if (!mbar_wait(&sh->gal_full[slot], (uint32_t)(guse & 1), failed)) break;
-          if (!mbar_wait(&sh->score_empty[buf], (uint32_t)((suse & 1) ^ 1), failed)) break;
+          const int buf = s & 1;
+          if (!mbar_wait(&sh->gal_full[slot], gphase, failed)) break;
+          if (!mbar_wait(&sh->score_empty[buf], (uint32_t)(((s >> 1) & 1) ^ 1), failed)) break;
           tc_fence_after();
           if (probe && s < 4) probe[20 + s] = globaltimer();
-          const uint32_t b_addr = smem_u32(gal + (size_t)slot * gal_tile_bytes);
-          for (int ks = 0; ks < a.kf / 16; ++ks)
-            umma_f16(tmem_base + (uint32_t)buf * kGalTile, umma_desc_nosw(a_addr + ks * 256, 128u, sbo),
-                     umma_desc_nosw(b_addr + ks * 256, 128u, sbo), idesc, ks > 0 ? 1u : 0u);
+          const uint32_t d_addr = tmem_base + (uint32_t)buf * kGalTile;
+          const uint64_t boff = slot_step * (uint64_t)slot;
+#pragma unroll
+          for (int ks = 0; ks < 8; ++ks)
+            if (ks < n_ks) umma_f16(d_addr, adesc[ks], bdesc0[ks] + boff, idesc, ks > 0 ? 1u : 0u);
           umma_commit(&sh->gal_empty[slot]);
           umma_commit(&sh->score_full[buf]);
+          if (++slot == a.ring) { slot = 0; gphase ^= 1; }
         }
       }
-    } else if (warp >= kWarps - kScanWarps) {
+    } else if (warp < kWarps - kScanWarps) {
+      // helper warps 2..7, off the critical path: the exact norm and the feature vectors as the exact scorer uses
+      // them (divided by the norm for the sklearn rule) -- needed only when the re-score list is processed
+      double pn = sqrt(n2);
+      if (METRIC == EF_METRIC_COSINE_SK && pn == 0.0) pn = 1.0;
+      if (warp == 2) sh->pn[lane] = pn;
+      for (int c = warp - 2; c < KR; c += kWarps - kScanWarps - 2) {
+        double v = ps[c * QB + lane];
+        if (METRIC == EF_METRIC_COSINE_SK) v = v / pn;
+        pe[c * QB + lane] = v;
+      }
+      __threadfence_block();
+      asm volatile("bar.arrive 3, 448;" ::: "memory");
+    } else {
       // scanning warps: lane group q = warp % 4 (all groups hold the same 32 crops), 32 of the 256 columns each.
       // Pass 0: approximate maximum per crop.  Pass 1: rows within the filter band go to the re-score list.
       const int sw = warp - (kWarps - kScanWarps), stid = tid - (kWarps - kScanWarps) * 32;
@@ -480,9 +507,14 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         if (better<METRIC>(key, j, best, best_i)) { best = key; best_score = score; best_label = label; best_i = j; }
       };
       float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F, thr = 0.f;
+#ifdef EF_DEBUG_FILTER
+      float dbg_m1 = -CUDART_INF_F;
+#endif
       bool ok = true;
+      int t = -1, pass = 0;
       for (int s = 0; s < n_seq; ++s) {
-        const int t = s % a.g_tiles, pass = s / a.g_tiles, buf = s & 1, suse = s >> 1;
+        const int buf = s & 1, suse = s >> 1;
+        if (++t == a.g_tiles) { t = 0; pass = 1; }
         if (pass == 1 && t == 0) {
           sh->fmax_s[sw][lane] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
           asm volatile("bar.sync 2, 256;" ::: "memory");
@@ -524,28 +556,31 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
           unsigned mask = 0u;
 #pragma unroll
           for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(v[i]) >= thr ? 1u : 0u) << i;
+#ifdef EF_DEBUG_FILTER
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dbg_m1 = fmaxf(dbg_m1, __uint_as_float(v[i]));
+#endif
           if (valid < 32) mask &= (1u << valid) - 1u;
           while (mask) {
             const int i = __ffs(mask) - 1;
             mask &= mask - 1u;
-            const int j = j0 + i;
             const int slot = atomicAdd(&sh->list_cnt, 1);
             if (slot < kListCap) {
               sh->list_L[slot] = lane;
-              sh->list_j[slot] = j;
-            } else {                                // list full: score it here (slow, correct)
-              double key, score; int label;
-              exact_entry<METRIC, KR>(a.gp, a.ginv, a.gnorm, a.labels, pe, lane, j, pn, key, score, label);
-              consider(key, score, label, j);
+              sh->list_j[slot] = j0 + i;
+            } else {
+              sh->overflow = 1;                     // more survivors than list entries: full float64 scan below
             }
           }
         }
         if (probe && stid == 0 && s < 4) probe[16 + s] = globaltimer();
       }
-      asm volatile("bar.sync 2, 256;" ::: "memory");
+      __threadfence_block();
+      asm volatile("bar.sync 3, 448;" ::: "memory");      // list complete; pn / pe ready (helper warps)
       if (probe && stid == 0) probe[10] = globaltimer();
+      const bool overflow = *reinterpret_cast<volatile int*>(&sh->overflow) != 0;
+      const int total = overflow ? 0 : *reinterpret_cast<volatile int*>(&sh->list_cnt);
       // ---- exact float64 scores of the surviving rows, one per thread (all L2 reads in flight together)
-      const int total = min(*reinterpret_cast<volatile int*>(&sh->list_cnt), kListCap);
       for (int e = stid; e < total; e += kScanWarps * 32) {
         const int L = sh->list_L[e];
         double key, score; int label;
@@ -558,10 +593,27 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       if (probe && stid == 0) probe[11] = globaltimer();
       for (int e = sw; e < total; e += kScanWarps)
         if (sh->list_L[e] == lane) consider(sh->list_key[e], sh->list_score[e], sh->list_label[e], sh->list_j[e]);
+      if (overflow) {
+        // degenerate gallery (hundreds of rows within the filter band of one crop tile): exact scan of every row
+        const double pn = sh->pn[lane];
+        for (int j = sw; j < a.n; j += kScanWarps) {
+          double key, score; int label;
+          exact_entry<METRIC, KR>(a.gp, a.ginv, a.gnorm, a.labels, pe, lane, j, pn, key, score, label);
+          consider(key, score, label, j);
+        }
+      }
       sh->red_s[sw][lane] = best;
       sh->red_d[sw][lane] = best_score;
       sh->red_i[sw][lane] = best_i;
       sh->red_l[sw][lane] = best_label;
+#ifdef EF_DEBUG_FILTER
+      {
+        const float mypass0 = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+        if (dbg_m1 != mypass0)
+          printf("DBG blk %d sw %d lane %d pass0 max %.9g pass1 max %.9g thr %.9g total %d ovf %d\n", blockIdx.x, sw, lane,
+                 mypass0, dbg_m1, thr, total, (int)overflow);
+      }
+#endif
       if (probe && stid == 0) probe[12] = globaltimer();
     }
     __syncthreads();
@@ -575,6 +627,9 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
           bi = sh->red_i[w][lane];
           bl = sh->red_l[w][lane];
         }
+#ifdef EF_DEBUG_FILTER
+      if (bi == INT_MAX) printf("DBG nocand blk %d lane %d list_cnt %d pn %g pe0 %g\n", blockIdx.x, lane, sh->list_cnt, sh->pn[lane], pe[lane]);
+#endif
       if (bi == INT_MAX) { bi = 0; bl = -1; }       // only after a pipeline failure (the status flag is raised below)
       a.out_score[b] = score;
       a.out_index[b] = bi;
@@ -582,6 +637,13 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     }
   } else {
     // ===================================================================== float64 scan of a shared-memory gallery tile
+    double pn = sqrt(n2);
+    if (METRIC == EF_METRIC_COSINE_SK && pn == 0.0) pn = 1.0;
+    if (warp == 0 && a.want_resid && live) {
+      const double sq = fused_ssq ? (double)ssq_total : a.sumsq_ext[b];
+      const double r = sq - 2.0 * sh->xu[lane] + a.c0 - n2;
+      a.out_resid[b] = r > 0.0 ? r : 0.0;
+    }
     double best = (METRIC == EF_METRIC_L2) ? CUDART_INF : -CUDART_INF, best_dot = 0.0;
     int best_i = INT_MAX;
     double p[KR];
@@ -657,7 +719,6 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
     }
   }
 
-
   // ======================================================================= teardown
   tc_fence_before();
   __syncthreads();
@@ -667,11 +728,10 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
                  : "memory");
   }
   if (tid == 0 && sh->failed) atomicExch(a.status, 1);
-  cluster_wait();                                   // nobody reads this CTA's shared memory any more
   if (probe && tid == 0) probe[6] = globaltimer();
 }
 
-// gallery rows -> float16 [g_hi | g_lo | g_hi] image in the canonical no-swizzle K-major layout, 256-row tiles
+// gallery rows -> float16 [g_hi | g_lo | g_hi] image, 256-row tiles in the swizzled K-major layout of swz_chunk_offset
 __global__ void gallery_image_kernel(const double* __restrict__ gp, int kr, const double* __restrict__ ginv, int n, int k,
                                      int kf, int metric, __half* __restrict__ img) {
   const int KC = kf >> 3;
@@ -683,36 +743,36 @@ __global__ void gallery_image_kernel(const double* __restrict__ gp, int kr, cons
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int kk = kc * 8 + i;
-    const int seg = kk / k, c = kk - seg * k;
-    __half hi = __float2half(0.f), lo = hi;
-    if (seg < 3) split_half(gp[(size_t)j * kr + c] * scale, hi, lo);
+    const int seg = kk >= 3 * k ? 3 : (kk >= 2 * k ? 2 : (kk >= k ? 1 : 0));
+    __half hi = __float2half_rn(0.f), lo = hi;
+    if (seg < 3) {
+      const double v = gp[(size_t)j * kr + (kk - seg * k)] * scale;
+      hi = __double2half(v);
+      lo = __double2half(v - (double)__half2float(hi));
+    }
     h[i] = seg == 1 ? lo : hi;
-    if (seg >= 3) h[i] = __float2half(0.f);
   }
   const int tile = j / kGalTile, rr = j - tile * kGalTile;
   uint8_t* dst = reinterpret_cast<uint8_t*>(img) + (size_t)tile * kGalTile * kf * 2 +
-                 ((size_t)((rr >> 3) * KC + kc) * 128 + (rr & 7) * 16);
+                 swz_chunk_offset(rr, kc, kf * 2, kGalTile);
   *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(h);
 }
 
 template <int METRIC, int KR>
 int launch_cluster(const CUtensorMap& mx, const CUtensorMap& mw, ClusterArgs& a, int m_tiles, cudaStream_t stream) {
   const int stage_bytes = A_STAGE_BYTES + a.nc_pad * BLOCK_K;
-  // pipeline depth: 3 stages are enough (the main loop is throughput bound, see tools/tc_probe.py); the partial tile
-  // (nc_pad x 128 int32 + 128 x u64) must fit in the stage area
+  // pipeline depth: 3 stages are enough (the main loop is throughput bound, see tools/tc_probe.py)
   int stages = 3;
-  while ((size_t)stages * stage_bytes < (size_t)a.nc_pad * BLOCK_M * 4 + BLOCK_M * 8) ++stages;
-  if (stages > kMaxStages) return EF_ERR_UNSUPPORTED;
   a.stages = stages;
   size_t off = (size_t)stages * stage_bytes;
-  a.off_sum = (int)off;  off += (size_t)a.nc_pad * 128;
+  a.off_recv = (int)off; off += (size_t)a.nc_pad * 512;           // [4][nc_pad][32] int32
   a.off_ps = (int)off;   off += sizeof(double) * KR * QB;
   a.off_pe = (int)off;   off += sizeof(double) * KR * QB;
-  off = (size_t)ef::round_up((int64_t)off, 128);
+  off = (size_t)ef::round_up((int64_t)off, 1024);
   const size_t tail = (size_t)ef::round_up((int64_t)sizeof(ClusterShared), 128) + 128;
   bool filter = METRIC != EF_METRIC_L2 && a.gimg != nullptr && getenv("EF_NO_FILTER") == nullptr;
   if (filter) {
-    const size_t aimg_bytes = (size_t)BLOCK_M * a.kf * 2;
+    const size_t aimg_bytes = (size_t)ef::round_up((int64_t)BLOCK_M * a.kf * 2, 1024);
     const size_t tile_bytes = (size_t)kGalTile * a.kf * 2;
     const size_t left = (size_t)kSmemLimit > off + aimg_bytes + tail ? (size_t)kSmemLimit - off - aimg_bytes - tail : 0;
     int ring = (int)std::min<size_t>(kMaxRing, left / tile_bytes);
@@ -816,7 +876,12 @@ int dispatch_kr(const CUtensorMap& mx, const CUtensorMap& mw, ClusterArgs& a, in
 
 namespace ef {
 
-int filter_kf(int k) { return (int)round_up(3 * (int64_t)k, 16); }
+// float16 K extent of the filter operands: [hi | lo | hi] = 3k, padded to a power of two (one swizzle row)
+int filter_kf(int k) {
+  int kf = 16;
+  while (kf < 3 * k) kf *= 2;
+  return kf;
+}
 
 size_t gallery_image_bytes(int k, int64_t n) {
   return (size_t)ceil_div(n, kGalTile) * kGalTile * (size_t)filter_kf(k) * 2;

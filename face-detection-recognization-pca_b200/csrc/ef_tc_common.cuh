@@ -208,6 +208,40 @@ __device__ __forceinline__ unsigned long long ld_cluster_u64(uint32_t addr) {
   asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
   return v;
 }
+__device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
+  asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_cluster_u64(uint32_t addr, unsigned long long v) {
+  asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+
+// K-major operand image with the widest swizzle that fits the row: rows of row_bytes in {32, 64, 128, 256} bytes
+// (256 = two 128-byte swizzle atoms side by side in K).  Byte offset of 16-byte chunk `chunk` of row `row` in an image
+// of `rows` rows whose base is 1024-byte aligned (Swizzle<1|2|3,4,3>: chunk index XOR row bits).
+__host__ __device__ __forceinline__ uint32_t swz_chunk_offset(int row, int chunk, int row_bytes, int rows) {
+  const int swb = row_bytes < 128 ? row_bytes : 128;
+  const int cps = swb >> 4;                                   // chunks per swizzle row: 2, 4, 8
+  const int shift = cps == 8 ? 0 : (cps == 4 ? 1 : 2);
+  const int cps_log2 = cps == 8 ? 3 : (cps == 4 ? 2 : 1);
+  const int katom = chunk >> cps_log2, cin = chunk & (cps - 1);
+  return (uint32_t)(katom * rows * swb + row * swb + ((cin ^ ((row >> shift) & (cps - 1))) << 4));
+}
+// Matching shared-memory descriptor for k-step `ks` (32 bytes of K) of such an image.
+__device__ __forceinline__ uint64_t umma_desc_swz(uint32_t base_addr, int ks, int row_bytes, int rows) {
+  const int swb = row_bytes < 128 ? row_bytes : 128;
+  const int per_atom = swb >> 5;                              // k-steps per swizzle atom: 1, 2, 4
+  const int pa_log2 = per_atom == 4 ? 2 : (per_atom == 2 ? 1 : 0);
+  const int katom = ks >> pa_log2, kin = ks & (per_atom - 1);
+  const uint32_t addr = base_addr + (uint32_t)(katom * rows * swb + kin * 32);
+  const uint64_t layout = swb == 128 ? 2ull : (swb == 64 ? 4ull : 6ull);
+  uint64_t d = 0;
+  d |= (uint64_t)((addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;                                     // leading byte offset: unused inside one swizzle atom
+  d |= (uint64_t)((8 * swb) >> 4) << 32;                      // stride byte offset: 8 rows
+  d |= (uint64_t)1 << 46;
+  d |= layout << 61;
+  return d;
+}
 
 // --------------------------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
