@@ -225,6 +225,11 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
   __syncthreads();
   tc_fence_after();
   cluster_arrive();                                 // "this CTA runs": awaited before the first DSMEM store below
+  // Programmatic dependent launch: the next kernel of the stream may be scheduled as soon as every CTA got here (its
+  // CTAs start as ours retire); everything above touched only this CTA's own resources, everything below may read
+  // buffers written by the previous kernel (the crops) or write buffers it reads or writes (the results).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const uint32_t tmem_base = sh->tmem_base;
   volatile int* failed = &sh->failed;
   unsigned long long* probe = a.probe ? a.probe + (size_t)blockIdx.x * 32 : nullptr;
@@ -453,19 +458,19 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       }
     } else if (warp == 1) {
       if (lane == 0) {
-        // single-thread issue loop: everything that can be precomputed is (descriptors advance linearly with the
-        // shared-memory address, so the B descriptor of a ring slot is a base value plus a constant per slot)
+        // single-thread issue loop, kept small: descriptors advance linearly with the shared-memory address, so the
+        // descriptor of k-step ks in ring slot `slot` is a base value plus multiples of three constants
         const uint32_t idesc = umma_idesc_f16(kGalTile);
         const int n_ks = a.kf >> 4;
-        uint64_t adesc[8], bdesc0[8];
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          adesc[ks] = ks < n_ks ? umma_desc_swz(smem_u32(aimg), ks, row_bytes, BLOCK_M) : 0ull;
-          bdesc0[ks] = ks < n_ks ? umma_desc_swz(smem_u32(gal), ks, row_bytes, kGalTile) : 0ull;
-        }
+        const int swb = row_bytes < 128 ? row_bytes : 128;
+        const int pa_log2 = swb == 128 ? 2 : (swb == 64 ? 1 : 0);           // k-steps per swizzle atom: 4, 2, 1
+        const uint64_t adesc0 = umma_desc_swz(smem_u32(aimg), 0, row_bytes, BLOCK_M);
+        const uint64_t bdesc0 = umma_desc_swz(smem_u32(gal), 0, row_bytes, kGalTile);
+        const uint64_t a_atom = (uint64_t)((BLOCK_M * swb) >> 4), b_atom = (uint64_t)((kGalTile * swb) >> 4);
         const uint64_t slot_step = (uint64_t)(gal_tile_bytes >> 4);
         int slot = 0;
         uint32_t gphase = 0;
+        uint64_t bslot = bdesc0;
         for (int s = 0; s < n_seq; ++s) {
           const int buf = s & 1;
           if (!mbar_wait(&sh->gal_full[slot], gphase, failed)) break;
@@ -473,13 +478,16 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
           tc_fence_after();
           if (probe && s < 4) probe[20 + s] = globaltimer();
           const uint32_t d_addr = tmem_base + (uint32_t)buf * kGalTile;
-          const uint64_t boff = slot_step * (uint64_t)slot;
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)
-            if (ks < n_ks) umma_f16(d_addr, adesc[ks], bdesc0[ks] + boff, idesc, ks > 0 ? 1u : 0u);
+#pragma unroll 1
+          for (int ks = 0; ks < n_ks; ++ks) {
+            const uint64_t koff = (uint64_t)((ks & ((1 << pa_log2) - 1)) << 1);   // 32 bytes per k-step inside an atom
+            const uint64_t katom = (uint64_t)(ks >> pa_log2);
+            umma_f16(d_addr, adesc0 + koff + katom * a_atom, bslot + koff + katom * b_atom, idesc, ks > 0 ? 1u : 0u);
+          }
           umma_commit(&sh->gal_empty[slot]);
           umma_commit(&sh->score_full[buf]);
-          if (++slot == a.ring) { slot = 0; gphase ^= 1; }
+          bslot += slot_step;
+          if (++slot == a.ring) { slot = 0; gphase ^= 1; bslot = bdesc0; }
         }
       }
     } else if (warp < kWarps - kScanWarps) {
@@ -824,13 +832,15 @@ int launch_cluster(const CUtensorMap& mx, const CUtensorMap& mw, ClusterArgs& a,
   cfg.blockDim = dim3(kThreads);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attrs[1];
+  cudaLaunchAttribute attrs[2];
   attrs[0].id = cudaLaunchAttributeClusterDimension;
   attrs[0].val.clusterDim.x = kCluster;
   attrs[0].val.clusterDim.y = 1;
   attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attrs;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = getenv("EF_NO_PDL") ? 1 : 2;
   EF_CUDA(cudaLaunchKernelEx(&cfg, recognize_cluster_kernel<METRIC, KR>, mx, mw, a));
   ef::g_launches.fetch_add(1, std::memory_order_relaxed);
   if (a.probe) {
@@ -840,9 +850,9 @@ int launch_cluster(const CUtensorMap& mx, const CUtensorMap& mw, ClusterArgs& a,
     unsigned long long t0 = ~0ull;
     for (int c = 0; c < grid_n; ++c) if (h[(size_t)c * 32] && h[(size_t)c * 32] < t0) t0 = h[(size_t)c * 32];
     const char* names[32] = {"start", "first_full", "mma_issued", "block_done", "sync1", "features", "end",
-                             "aimg", "max_known", "-", "listed", "exact", "gathered", "rd_issued", "rd_done", "-",
+                             "aimg", "max_known", "-", "listed", "exact", "gathered", "-", "-", "-",
                              "scan_t0", "scan_t1", "scan_t2", "scan_t3", "mma_t0", "mma_t1", "mma_t2", "mma_t3",
-                             "gal_t0", "gal_t1", "gal_t2", "gal_t3", "ld_t0", "ld_t1", "ld_t2", "ld_t3"};
+                             "-", "-", "-", "-", "ld_t0", "ld_t1", "ld_t2", "ld_t3"};
     fprintf(stderr, "[ef_cluster_probe] grid %d stages %d filter %d ring %d tile_rows %d; us since first CTA start (mean/max):",
             grid_n, a.stages, a.filter, a.ring, a.tile_rows);
     for (int i = 0; i < 32; ++i) {

@@ -27,8 +27,10 @@ for resid in (True, False):
     e1.record()
     torch.cuda.synchronize()
     print(f"with_residual={resid}: step {1e3 * e0.elapsed_time(e1) / 50:.1f} us", flush=True)
-    os.environ["EF_TC_PROBE"] = "1"
-    for i in range(2):
-        rec.recognize_device(xs[i + 1], 0.8, out=out)
-    torch.cuda.synchronize()
-    os.environ.pop("EF_TC_PROBE")
+    for mode in os.environ.get("PROBE_MODES", "1").split(","):
+        os.environ["EF_TC_PROBE"] = mode
+        print("probe mode", mode, flush=True)
+        for i in range(2):
+            rec.recognize_device(xs[i + 1], 0.8, out=out)
+        torch.cuda.synchronize()
+        os.environ.pop("EF_TC_PROBE")
