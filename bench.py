@@ -166,6 +166,89 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+
+# ------------------------------------------------------------------------------------ secondary measurements
+def fit_and_gram_section(ef, torch, dev, peaks):
+    """PCA fit seconds (the second half of BASELINE.json's metric) and the tensor-core Gram behind it.  Bounded: a few
+    seconds.  fit: the shipped Gen-1 configuration (229 light crops x 10 000 pixels, k = 50) through ef_fit_gen1_host
+    (H2D + Gram + Jacobi + back-projection + D2H), the oracle's manual_pca on the host cores beside it.  gram: the
+    exact u8 x u8 tcgen05 SYRK at the config-4 per-GPU shape (12 500 rows x 10 000 pixels -> 10 000 x 10 000)."""
+    import ctypes as C
+    from oracle import gen1
+    out = {}
+    X, note = training_matrix()
+    t0 = time.perf_counter(); ef.fit_gen1(X, 50); torch.cuda.synchronize()
+    walls, gpu = [], []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        info = ef.fit_gen1(X, 50)[4]
+        walls.append(time.perf_counter() - t0); gpu.append(info["gpu_ms"])
+    cpu = []
+    Xf = X.astype(np.float64)
+    for _ in range(3):
+        t0 = time.perf_counter(); gen1.manual_pca(Xf, 50); cpu.append(time.perf_counter() - t0)
+    out["fit"] = {"what": f"manual_pca {X.shape[0]}x{X.shape[1]} k=50 ({note})", "unit": "s",
+                  "gpu_wall_s": min(walls), "gpu_device_s": min(gpu) * 1e-3, "jacobi_sweeps": info["sweeps"],
+                  "cpu_port_s": min(cpu), "cpu_cores": os.cpu_count(),
+                  "note": "gpu_wall_s = ef_fit_gen1_host call incl. H2D/D2H and allocations; cpu_port_s = oracle/gen1.py:manual_pca (numpy, all cores)"}
+    L = ef._lib.lib()
+    N, Dg = 12500, 10000
+    x = torch.randint(0, 256, (N, Dg), dtype=torch.uint8, device=dev)
+    G = torch.zeros((Dg, Dg), dtype=torch.int64, device=dev)
+    wb = int(L.ef_gram_u8_tc_work_bytes(N, Dg, 1))
+    work = torch.empty(wb, dtype=torch.uint8, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+    def run():
+        ef._lib.check(L.ef_gram_u8_tc_device(x.data_ptr(), x.stride(0), N, Dg, 0, Dg, 1, G.data_ptr(), work.data_ptr(),
+                                             wb, st), "ef_gram_u8_tc_device")
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 5
+    e0.record()
+    for _ in range(reps):
+        run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    tiles = sum(min((256 * tj + 255) // 128 + 1, (Dg + 127) // 128) for tj in range((Dg + 255) // 256))
+    executed = 2.0 * tiles * 128 * 256 * ((N + 127) // 128 * 128)
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)
+    out["gram"] = {"what": f"ef_gram_u8_tc_device side 1: X^T X of u8[{N},{Dg}] -> int64[{Dg},{Dg}] (transpose + tcgen05 "
+                           "kind::i8 SYRK upper triangle + mirror), exact",
+                   "ms": ms, "algorithmic_tops": 2.0 * Dg * Dg * N / ms / 1e9 / 2.0,
+                   "executed_tops": executed / ms / 1e9,
+                   "roofline": {"bound": "tensor", "achieved": executed / ms / 1e9, "peak": bf16_peak, "unit": "TOP/s (int8 ops) vs measured bf16 TFLOP/s",
+                                "frac": executed / ms / 1e9 / bf16_peak,
+                                "note": "algorithmic = N*D^2 (symmetric half); executed = upper-triangle tiles incl. the diagonal overlap; int8 nominal peak is 2x bf16"},
+                   "flag": int(work[:4].view(torch.int32).item())}
+    del x, G, work
+    # K1: resize-active preprocess, ROI 100..300 px squares inside 1080p gray frames -> 100x100
+    rng = np.random.default_rng(5150)
+    F, H, W, nb = 8, 1080, 1920, 4096
+    frames = torch.randint(0, 256, (F, H, W), dtype=torch.uint8, device=dev)
+    side = rng.integers(100, 301, nb)
+    bx = np.stack([rng.integers(0, F, nb), (rng.random(nb) * (W - side)).astype(np.int64),
+                   (rng.random(nb) * (H - side)).astype(np.int64), side, side], axis=1).astype(np.int32)
+    boxes = torch.from_numpy(bx).to(dev)
+    outp = ef.engine.preprocess_device(frames, boxes, 100)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(20):
+        ef.engine.preprocess_device(frames, boxes, 100, out=outp)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 20
+    bytes_alg = float((side.astype(np.int64) ** 2).sum() + nb * 10000)
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    out["preprocess"] = {"what": "ef_preprocess: 4096 square ROIs (100..300 px) of 1080p gray frames -> 100x100 (bit exact cv2.resize INTER_LINEAR)",
+                         "ms": ms, "crops_per_s": nb / ms * 1e3,
+                         "roofline": {"bound": "hbm", "achieved": bytes_alg / ms / 1e6, "peak": hbm, "unit": "GB/s",
+                                      "frac": bytes_alg / ms / 1e6 / hbm,
+                                      "note": "algorithmic bytes = ROI pixels read once + 10 000 B written per crop"}}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------- ours
 def run_ours(args, rank, world):
     import torch
@@ -293,7 +376,16 @@ def run_ours(args, rank, world):
             peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs"
         else:
             peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-        achieved = ALGO_BYTES_PER_CROP * B / (proj_ms * 1e-3) / 1e9 if proj_ms > 0 else 0.0
+        # one launch per step (single cluster kernel): the average launch duration over the timed region IS the step
+        # time, launch gaps included (consecutive launches overlap through programmatic dependent launch, so bracketing
+        # each launch with its own events would serialise them: that figure is kept as kernel_ms_isolated)
+        one_launch = int(used_tc) == 2 and launches == args.steps
+        kernel_ms = ms / args.steps if one_launch else proj_ms
+        achieved = ALGO_BYTES_PER_CROP * B / (kernel_ms * 1e-3) / 1e9 if kernel_ms > 0 else 0.0
+        peaks = json.load(open(peaks_path)) if os.path.exists(peaks_path) else {}
+        extra = {}
+        if world == 1 and not args.profile and not args.no_extras:
+            extra = fit_and_gram_section(ef, torch, dev, peaks)
         cpu = None
         if world == 1 and not args.no_cpu_baseline and not args.profile:
             model, lam_c, _ = cpu_port_setup()
@@ -310,15 +402,17 @@ def run_ours(args, rank, world):
             "data": "synthetic",
             "config": {"workload": WORKLOAD, "basis": note, "n_slices": 8, "threshold": THRESHOLD,
                        "l2": f"{N_BATCHES} distinct resident batches rotated ({N_BATCHES * B * ld / 1e6:.0f} MB > 126 MB L2)",
-                       "projection_kernel": {2: "recognize_cluster_kernel: TMA + tcgen05 kind::i8 + DSMEM reduce + fused match (1 launch/step)",
+                       "projection_kernel": {2: "recognize_cluster_kernel: TMA + tcgen05 kind::i8 + DSMEM push + tcgen05 f16 filter + exact f64 re-score (1 launch/step, PDL)",
                                              1: "project_tc_kernel (tcgen05 kind::i8, stream-K) + fused_epilogue_kernel",
                                              0: "project_dp4a_kernel (CUDA cores) + fused_epilogue_kernel"}[int(used_tc)]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak if peak else None, "traffic": None,
                          "kernel": ("recognize_cluster_kernel (whole step: projection + match)" if int(used_tc) == 2
-                                    else "projection (digit-plane integer GEMM)"), "kernel_ms": proj_ms,
-                         "kernel_calls_timed": n_calls, "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CROP * B,
-                         "peak_source": peak_src},
+                                    else "projection (digit-plane integer GEMM)"), "kernel_ms": kernel_ms,
+                         "kernel_ms_isolated": proj_ms, "kernel_calls_timed": args.steps if one_launch else n_calls,
+                         "how": ("device-timed region / launches (1 launch per step, CUDA events on the launching stream)"
+                                 if one_launch else "CUDA event pair around every projection launch"),
+                         "algorithmic_bytes_per_launch": ALGO_BYTES_PER_CROP * B, "peak_source": peak_src},
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": "crops/s", "h2d_bytes_per_step": B * D, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": 1e3 * e2e_s / e2e_steps,
@@ -328,6 +422,7 @@ def run_ours(args, rank, world):
             "fit_setup": {"what": "ef_fit_gen1_host 229x10000 k=10 (model setup, untimed)", "gpu_ms": fit_info["gpu_ms"],
                           "jacobi_sweeps": fit_info["sweeps"]},
         }
+        line.update(extra)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -341,6 +436,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the fit / Gram / preprocess side measurements")
     ap.add_argument("--profile", action="store_true",
                     help="short run for ncu: no CPU baseline, no clock post-roll, one e2e step (numbers are not bench values)")
     args = ap.parse_args()
