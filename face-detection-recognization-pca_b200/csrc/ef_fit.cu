@@ -320,6 +320,29 @@ int ef_fit_gen2_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
   }
   EF_LAUNCH(rownorm_flip_kernel, k, 256, 0, st, Vt, k, D, dsign.as<double>());
   if (snapshot) {
+    // Numerically null singular values (the centred matrix has rank <= N - 1, so with k = N the last one always is):
+    // u^T Zc is rounding noise there, and its normalisation would be a direction INSIDE the row space.  LAPACK (and so
+    // the reference's pickles) returns a unit vector orthogonal to all other components, for which Zc v = sigma u ~ 0:
+    // the training crops then project to ~0 on it, matching the stored face_features.  Build exactly that: take the
+    // noise row, project out every other component twice (classical Gram-Schmidt with re-orthogonalisation), renormalise.
+    // (the spectrum comes from the Gram matrix, whose eigenvalues carry an absolute error ~ n eps lambda_1: singular
+    // values below sqrt(n eps) sigma_1 are unresolved and count as null)
+    const double null_tol = S[0] * std::sqrt((double)std::max(N, D) * 2.220446049250313e-16);
+    ef::DevBuf dcoef;
+    for (int c = 0; c < k; ++c) {
+      if (S[c] > null_tol) continue;
+      EF_TRY(dcoef.ensure(sizeof(double) * k));
+      double* w = Vt + (size_t)c * D;
+      for (int pass = 0; pass < 2; ++pass) {
+        // coef = Vt w (k values); the component's own coefficient is zeroed; w -= Vt^T coef
+        EF_TRY(ef_dgemm_device(k, 1, D, 1.0, Vt, D, 1, w, 1, 1, 0.0, dcoef.as<double>(), 1, st));
+        EF_CUDA(cudaMemsetAsync(dcoef.as<double>() + c, 0, sizeof(double), st));
+        EF_TRY(ef_dgemm_device(D, 1, k, -1.0, Vt, 1, D, dcoef.as<double>(), 1, 1, 1.0, w, 1, st));
+      }
+      EF_LAUNCH(rownorm_flip_kernel, 1, 256, 0, st, w, 1, D, dsign.as<double>() + c);
+    }
+  }
+  if (snapshot) {
     EF_LAUNCH(features_kernel, (unsigned)ef::ceil_div((int64_t)N * k, 256), 256, 0, st, devecs.as<double>(), N, k,
               dS.as<double>(), dsign.as<double>(), dF.as<double>());
   } else {
