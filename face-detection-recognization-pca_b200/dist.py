@@ -169,7 +169,9 @@ def fit_gen1_sharded(X_local, n_total, n_components, group=None):
     check(L.ef_eigh_jacobi_device(cov.data_ptr(), D, evals.data_ptr(), evecs.data_ptr(), work.data_ptr(), 0, 0.0, None,
                                   None, stream), "jacobi")
     k = min(int(n_components), D)
-    mean = colsum.to(torch.float64) / float(n_total)
+    # tensor divisor: torch turns division by a Python scalar into a multiplication by the reciprocal on CUDA, which is
+    # not the correctly rounded quotient np.mean (and the single-GPU fit) returns
+    mean = colsum.to(torch.float64) / torch.full((1,), float(n_total), dtype=torch.float64, device=dev)
     E = evecs[:k].T.contiguous()                                   # [D, k]
     Z = torch.empty((max(Nr, 1), D), dtype=torch.float64, device=dev)
     proj = torch.empty((Nr, k), dtype=torch.float64, device=dev)
