@@ -32,6 +32,8 @@ struct ef_model {
   ef::DevBuf x_dev, resid_dev, index32_dev, label_dev, frames_dev, boxes_dev, bad_dev;
   int64_t x_ld = 0;
   cudaStream_t stream = nullptr;   // owned, used by the host entry points
+  cudaStream_t copy_stream = nullptr;                 // owned: chunked H2D of the host path runs ahead of the kernels
+  std::vector<cudaEvent_t> chunk_ev;                  // one per in-flight H2D chunk
   int ld_acc = 0;
   int tc_mode = 2;                 // 0 dp4a, 1 tcgen05 stream-K + epilogue kernels, 2 single cluster kernel
   int last_path = 0;
@@ -215,6 +217,8 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
 void ef_model_destroy(ef_model_t* m) {
   if (!m) return;
   if (m->stream) cudaStreamDestroy(m->stream);
+  if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  for (cudaEvent_t e : m->chunk_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_a) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_b) cudaEventDestroy(e);
   delete m;
@@ -415,18 +419,44 @@ int ef_model_recognize_host(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_
   if (B == 0) return EF_OK;
   EF_TRY(host_reserve(m, B));
   cudaStream_t st = m->stream;
-  if (ldx == m->x_ld) {
-    EF_CUDA(cudaMemcpyAsync(m->x_dev.p, x, (size_t)B * ldx, cudaMemcpyHostToDevice, st));
-  } else {
-    EF_CUDA(cudaMemcpy2DAsync(m->x_dev.p, m->x_ld, x, ldx, m->D, B, cudaMemcpyHostToDevice, st));
-  }
   ef_result_t dev;
   dev.proj = out->proj ? m->proj.as<double>() : nullptr;
   dev.score = m->score.as<double>();
   dev.index = m->index32_dev.as<int32_t>();
   dev.label = m->label_dev.as<int32_t>();
   dev.resid2 = out->resid2 ? m->resid_dev.as<double>() : nullptr;
-  EF_TRY(ef_model_recognize_device(m, m->x_dev.as<uint8_t>(), m->x_ld, B, threshold, &dev, st));
+  // Large batches: the crops go up in chunks on a copy stream and every chunk is recognised as soon as it has landed,
+  // so only the last chunk's kernel is exposed behind the PCIe transfer (the host->device copy dominates this path).
+  constexpr int kChunk = 1024;
+  const int n_chunks = B >= 2 * kChunk ? (B + kChunk - 1) / kChunk : 1;
+  if (n_chunks > 1 && !m->copy_stream) EF_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  while ((int)m->chunk_ev.size() < n_chunks) {
+    cudaEvent_t e;
+    EF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    m->chunk_ev.push_back(e);
+  }
+  for (int c = 0; c < n_chunks; ++c) {
+    const int b0 = c * kChunk, rows = n_chunks == 1 ? B : std::min(kChunk, B - b0);
+    cudaStream_t cs = n_chunks == 1 ? st : m->copy_stream;
+    uint8_t* xd = m->x_dev.as<uint8_t>() + (size_t)b0 * m->x_ld;
+    const uint8_t* xh = x + (size_t)b0 * ldx;
+    if (ldx == m->x_ld) {
+      EF_CUDA(cudaMemcpyAsync(xd, xh, (size_t)rows * ldx, cudaMemcpyHostToDevice, cs));
+    } else {
+      EF_CUDA(cudaMemcpy2DAsync(xd, m->x_ld, xh, ldx, m->D, rows, cudaMemcpyHostToDevice, cs));
+    }
+    if (n_chunks > 1) {
+      EF_CUDA(cudaEventRecord(m->chunk_ev[c], cs));
+      EF_CUDA(cudaStreamWaitEvent(st, m->chunk_ev[c], 0));
+    }
+    ef_result_t part;
+    part.proj = dev.proj ? dev.proj + (size_t)b0 * m->k : nullptr;
+    part.score = dev.score + b0;
+    part.index = dev.index + b0;
+    part.label = dev.label + b0;
+    part.resid2 = dev.resid2 ? dev.resid2 + b0 : nullptr;
+    EF_TRY(ef_model_recognize_device(m, xd, m->x_ld, rows, threshold, &part, st));
+  }
   return copy_results_back(m, B, out, dev);
 }
 
