@@ -32,6 +32,8 @@ struct ef_model {
   ef::DevBuf x_dev, resid_dev, index32_dev, label_dev, frames_dev, boxes_dev, bad_dev;
   int64_t x_ld = 0;
   cudaStream_t stream = nullptr;   // owned, used by the host entry points
+  void* pinned = nullptr;                             // owned page-locked staging for the results of the host path
+  size_t pinned_bytes = 0;
   cudaStream_t copy_stream = nullptr;                 // owned: chunked H2D of the host path runs ahead of the kernels
   std::vector<cudaEvent_t> chunk_ev;                  // one per in-flight H2D chunk
   int ld_acc = 0;
@@ -218,6 +220,7 @@ void ef_model_destroy(ef_model_t* m) {
   if (!m) return;
   if (m->stream) cudaStreamDestroy(m->stream);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+  if (m->pinned) cudaFreeHost(m->pinned);
   for (cudaEvent_t e : m->chunk_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_a) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_b) cudaEventDestroy(e);
@@ -384,7 +387,7 @@ int ef_model_status(ef_model_t* m, int32_t* tc_pipeline_timeouts) {
 static int host_reserve(ef_model_t* m, int32_t B) {
   EF_TRY(ef_model_reserve(m, B));
   if (B <= m->host_reserved) return EF_OK;
-  m->x_ld = ef::round_up(m->D, 128);
+  m->x_ld = ef::round_up(m->D, 16);     // dense when D % 16 == 0: contiguous host batches go up as ONE 1-D copy per chunk
   EF_TRY(m->x_dev.ensure((size_t)B * m->x_ld));
   EF_TRY(m->resid_dev.ensure(sizeof(double) * (size_t)B));
   EF_TRY(m->index32_dev.ensure(sizeof(int32_t) * (size_t)B));
@@ -395,16 +398,39 @@ static int host_reserve(ef_model_t* m, int32_t B) {
 }
 
 static int copy_results_back(ef_model_t* m, int32_t B, const ef_result_t* out, const ef_result_t& dev) {
+  // The caller's arrays are ordinary (pageable) host memory: a device->host copy straight into them is staged and
+  // synchronised by the driver one array at a time.  Copy everything into one page-locked block instead (asynchronous,
+  // back to back), synchronise once, then scatter with memcpy.
   cudaStream_t st = m->stream;
-  if (out->proj) EF_CUDA(cudaMemcpyAsync(out->proj, dev.proj, sizeof(double) * (size_t)B * m->k, cudaMemcpyDeviceToHost, st));
-  if (out->score) EF_CUDA(cudaMemcpyAsync(out->score, dev.score, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
-  if (out->index) EF_CUDA(cudaMemcpyAsync(out->index, dev.index, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
-  if (out->label) EF_CUDA(cudaMemcpyAsync(out->label, dev.label, sizeof(int32_t) * (size_t)B, cudaMemcpyDeviceToHost, st));
-  if (out->resid2) EF_CUDA(cudaMemcpyAsync(out->resid2, dev.resid2, sizeof(double) * (size_t)B, cudaMemcpyDeviceToHost, st));
-  int32_t timeouts = 0;
-  EF_CUDA(cudaMemcpyAsync(&timeouts, m->status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  const size_t nB = (size_t)B;
+  const size_t need = sizeof(double) * nB * (size_t)m->k + sizeof(double) * nB * 2 + sizeof(int32_t) * nB * 2 + 64;
+  if (need > m->pinned_bytes) {
+    if (m->pinned) cudaFreeHost(m->pinned);
+    m->pinned = nullptr;
+    m->pinned_bytes = 0;
+    EF_CUDA(cudaMallocHost(&m->pinned, need));
+    m->pinned_bytes = need;
+  }
+  char* p = reinterpret_cast<char*>(m->pinned);
+  double* h_proj = reinterpret_cast<double*>(p);   p += sizeof(double) * nB * (size_t)m->k;
+  double* h_score = reinterpret_cast<double*>(p);  p += sizeof(double) * nB;
+  double* h_resid = reinterpret_cast<double*>(p);  p += sizeof(double) * nB;
+  int32_t* h_index = reinterpret_cast<int32_t*>(p); p += sizeof(int32_t) * nB;
+  int32_t* h_label = reinterpret_cast<int32_t*>(p); p += sizeof(int32_t) * nB;
+  int32_t* h_flag = reinterpret_cast<int32_t*>(p);
+  if (out->proj) EF_CUDA(cudaMemcpyAsync(h_proj, dev.proj, sizeof(double) * nB * m->k, cudaMemcpyDeviceToHost, st));
+  if (out->score) EF_CUDA(cudaMemcpyAsync(h_score, dev.score, sizeof(double) * nB, cudaMemcpyDeviceToHost, st));
+  if (out->index) EF_CUDA(cudaMemcpyAsync(h_index, dev.index, sizeof(int32_t) * nB, cudaMemcpyDeviceToHost, st));
+  if (out->label) EF_CUDA(cudaMemcpyAsync(h_label, dev.label, sizeof(int32_t) * nB, cudaMemcpyDeviceToHost, st));
+  if (out->resid2) EF_CUDA(cudaMemcpyAsync(h_resid, dev.resid2, sizeof(double) * nB, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(h_flag, m->status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
   EF_CUDA(cudaStreamSynchronize(st));
-  if (timeouts) {
+  if (out->proj) memcpy(out->proj, h_proj, sizeof(double) * nB * m->k);
+  if (out->score) memcpy(out->score, h_score, sizeof(double) * nB);
+  if (out->index) memcpy(out->index, h_index, sizeof(int32_t) * nB);
+  if (out->label) memcpy(out->label, h_label, sizeof(int32_t) * nB);
+  if (out->resid2) memcpy(out->resid2, h_resid, sizeof(double) * nB);
+  if (*h_flag) {
     ef::set_error_detail("tcgen05 projection pipeline timed out (mbarrier wait > 2 s)", cudaErrorLaunchTimeout);
     return EF_ERR_CUDA;
   }

@@ -131,21 +131,114 @@ class ShardedGallery:
         return reduce_candidates(scores, idxs, self.metric)
 
 
-def fit_gen1_sharded(X_local, n_total, n_components, group=None):
+
+# ------------------------------------------------------------------------------ top-k eigenpairs of a large matrix
+def _dgemm(L, stream, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, Cm, ldc):
+    check(L.ef_dgemm_device(M, N, K, float(alpha), A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, float(beta),
+                            Cm.data_ptr(), ldc, stream), "ef_dgemm_device")
+
+
+def _jacobi(L, stream, H, work):
+    """Symmetric m x m eigendecomposition on the device (destroys H): (evals descending [m], evecs [m, m] rows)."""
+    import torch
+    m = H.shape[0]
+    evals = torch.empty(m, dtype=torch.float64, device=H.device)
+    evecs = torch.empty((m, m), dtype=torch.float64, device=H.device)
+    check(L.ef_eigh_jacobi_device(H.data_ptr(), m, evals.data_ptr(), evecs.data_ptr(), work.data_ptr(), 0, 0.0, None, None,
+                                  stream), "ef_eigh_jacobi_device")
+    return evals, evecs
+
+
+def eigh_topk_device(Cm, k, tol=1e-11, max_outer=60, degree=8, block=None, seed=1234):
+    """Largest k eigenpairs of a symmetric positive semi-definite CUDA float64 matrix Cm [n, n] that is too large for the
+    Jacobi solver (config 4: the 10 000 x 10 000 covariance, k = 256): Chebyshev-filtered subspace iteration with
+    Rayleigh-Ritz (Zhou & Saad's scaled filter).  Every dense product is ef_dgemm_device, every small eigenproblem
+    (block x block, block <= 320) the cluster-resident Jacobi kernel; torch only allocates and does O(n block) vector work.
+    Replaces np.linalg.eigh(cov) + descending sort + top-k of useless/train.py:103-116 for large D.
+    Returns (evals [k] descending, evecs [n, k] orthonormal columns, info dict)."""
+    import torch
+    L = _lib.lib()
+    dev = Cm.device
+    n = int(Cm.shape[0])
+    k = int(k)
+    m = int(block) if block else min(n, max(k + 32, k + k // 8))
+    m = min(m, n)
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    work = torch.empty(int(L.ef_eigh_work_bytes(m)), dtype=torch.uint8, device=dev)
+    f64 = dict(dtype=torch.float64, device=dev)
+
+    def orth(Y):
+        """Orthonormal basis of span(Y): G = Y^T Y = W^T diag(g) W, Q = Y W^T diag(g^-1/2).  The columns are brought
+        to unit norm first: after the filter they are nearly orthogonal Ritz directions whose NORMS span many orders of
+        magnitude, and the Gram matrix of the unscaled block would lose the small ones."""
+        norms = Y.norm(dim=0)
+        Y = (Y / torch.where(norms > 0, norms, torch.ones_like(norms))[None, :]).contiguous()
+        G = torch.empty((m, m), **f64)
+        _dgemm(L, stream, m, m, n, 1.0, Y, 1, m, Y, m, 1, 0.0, G, m)                # Y^T Y
+        g, W = _jacobi(L, stream, G, work)
+        scale = torch.where(g > g[0] * 1e-28, g.clamp_min(1e-300).rsqrt(), torch.zeros_like(g))
+        Ws = (W * scale[:, None]).contiguous()                                      # row i scaled by g_i^-1/2
+        Q = torch.empty((n, m), **f64)
+        _dgemm(L, stream, n, m, m, 1.0, Y, m, 1, Ws, 1, m, 0.0, Q, m)               # Y Ws^T
+        return Q
+
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(seed)
+    Q = orth(torch.randn((n, m), generator=gen, **f64))
+    Q = orth(Q)                                                                     # second pass: orthonormal to rounding
+    Y = torch.empty((n, m), **f64)
+    lam = None
+    info = {"outer": 0, "products": 0, "block": m, "residual": None}
+    for outer in range(max_outer):
+        _dgemm(L, stream, n, m, n, 1.0, Cm, n, 1, Q, m, 1, 0.0, Y, m)               # Y = C Q
+        H = torch.empty((m, m), **f64)
+        _dgemm(L, stream, m, m, n, 1.0, Q, 1, m, Y, m, 1, 0.0, H, m)                # H = Q^T C Q
+        H = ((H + H.T) * 0.5).contiguous()
+        lam, W = _jacobi(L, stream, H, work)
+        Qr = torch.empty((n, m), **f64)
+        Yr = torch.empty((n, m), **f64)
+        _dgemm(L, stream, n, m, m, 1.0, Q, m, 1, W, 1, m, 0.0, Qr, m)               # Ritz vectors Q W^T
+        _dgemm(L, stream, n, m, m, 1.0, Y, m, 1, W, 1, m, 0.0, Yr, m)               # C (Q W^T)
+        res = (Yr[:, :k] - Qr[:, :k] * lam[None, :k]).norm(dim=0).max() / lam[0].clamp_min(1e-300)
+        info.update(outer=outer + 1, products=info["products"] + 1, residual=float(res))
+        Q = Qr
+        if float(res) <= tol or m == n:
+            break
+        # scaled Chebyshev filter of degree `degree`: damps the unwanted interval [0, beta], beta = smallest Ritz value
+        beta, top = float(lam[m - 1]), float(lam[0])
+        if not (top > beta > 0.0):
+            beta = max(beta, 0.0) + 1e-3 * top
+        e = c = 0.5 * beta
+        sigma = e / (top - c)
+        sigma1 = sigma
+        Y1 = Yr.clone()
+        Y1.sub_(Q * c).mul_(sigma1 / e)                                             # (C Q - c Q) sigma1 / e
+        Qp = Q
+        for _ in range(2, degree + 1):
+            sigma_new = 1.0 / (2.0 / sigma1 - sigma)
+            Y2 = (Qp * (-sigma * sigma_new)).contiguous()
+            Y2.sub_(Y1 * (2.0 * sigma_new * c / e))
+            _dgemm(L, stream, n, m, n, 2.0 * sigma_new / e, Cm, n, 1, Y1, m, 1, 1.0, Y2, m)
+            info["products"] += 1
+            Qp, Y1, sigma = Y1, Y2, sigma_new
+        Q = orth(Y1)
+    return lam[:k].clone(), Q[:, :k].contiguous(), info
+
+
+def fit_gen1_sharded(X_local, n_total, n_components, group=None, solver="auto"):
     """Row-sharded manual_pca (useless/train.py:56-128) for N >= D (the covariance branch, e.g. 100 000 x 4096):
     every rank holds X_local uint8 [N_r, D] on its GPU.  Returns (eigenfaces [D,k], mean [D], projected_local [N_r,k],
     eigenvalues [k]) as CUDA float64 tensors; eigenfaces / mean / eigenvalues are identical on every rank.
 
     Per rank: exact integer column sums and Gram X_r^T X_r; ONE all-reduce(SUM) of int64 [D*D + D]; exact integer
-    centring; replicated Jacobi eigensolver; local projection of the local rows."""
+    centring; replicated eigensolver (Jacobi for D <= 2048, Chebyshev-filtered subspace iteration for the top k above:
+    `solver` = "auto" | "jacobi" | "subspace"); local projection of the local rows."""
     import torch
     L = _lib.lib()
     dev = X_local.device
     Nr, D = int(X_local.shape[0]), int(X_local.shape[1])
     if n_total < D:
         raise ValueError("fit_gen1_sharded covers the N >= D branch; small training sets fit on one GPU (fit_gen1)")
-    if D > 4096:
-        raise _lib.EigenfacesError(_lib.EF_ERR_UNSUPPORTED, "fit_gen1_sharded (D > 4096 needs the subspace solver)")
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     buf = torch.zeros(D * D + D, dtype=torch.int64, device=dev)
     G, colsum = buf[:D * D], buf[D * D:]
@@ -163,16 +256,21 @@ def fit_gen1_sharded(X_local, n_total, n_components, group=None):
     cov = torch.empty((D, D), dtype=torch.float64, device=dev)
     check(L.ef_gram_center_device(G.data_ptr(), D, 1, colsum.data_ptr(), int(n_total), 1.0 / (n_total - 1),
                                   cov.data_ptr(), None, stream), "center")
-    evals = torch.empty(D, dtype=torch.float64, device=dev)
-    evecs = torch.empty((D, D), dtype=torch.float64, device=dev)
-    work = torch.empty(int(L.ef_eigh_work_bytes(D)), dtype=torch.uint8, device=dev)
-    check(L.ef_eigh_jacobi_device(cov.data_ptr(), D, evals.data_ptr(), evecs.data_ptr(), work.data_ptr(), 0, 0.0, None,
-                                  None, stream), "jacobi")
     k = min(int(n_components), D)
+    if solver == "subspace" or (solver == "auto" and D > 2048):
+        # large D (config 4: 10 000 pixels): only the top k eigenpairs, by filtered subspace iteration
+        evals, E_top, _ = eigh_topk_device(cov, k)
+        evecs = None
+    else:
+        evals = torch.empty(D, dtype=torch.float64, device=dev)
+        evecs = torch.empty((D, D), dtype=torch.float64, device=dev)
+        work = torch.empty(int(L.ef_eigh_work_bytes(D)), dtype=torch.uint8, device=dev)
+        check(L.ef_eigh_jacobi_device(cov.data_ptr(), D, evals.data_ptr(), evecs.data_ptr(), work.data_ptr(), 0, 0.0, None,
+                                      None, stream), "jacobi")
     # tensor divisor: torch turns division by a Python scalar into a multiplication by the reciprocal on CUDA, which is
     # not the correctly rounded quotient np.mean (and the single-GPU fit) returns
     mean = colsum.to(torch.float64) / torch.full((1,), float(n_total), dtype=torch.float64, device=dev)
-    E = evecs[:k].T.contiguous()                                   # [D, k]
+    E = evecs[:k].T.contiguous() if evecs is not None else E_top   # [D, k]
     Z = torch.empty((max(Nr, 1), D), dtype=torch.float64, device=dev)
     proj = torch.empty((Nr, k), dtype=torch.float64, device=dev)
     if Nr:

@@ -142,3 +142,43 @@ def test_trained_model_recognises_its_own_faces(golden):
     _, idx, _ = gen2.recognize_batch(X, m, 0.7)
     uniq = np.unique(X, axis=0, return_index=True)[1]
     assert np.array_equal(res.index[uniq], idx[uniq])
+
+
+def test_subspace_eigensolver_matches_numpy_eigh():
+    """Chebyshev-filtered subspace iteration (the config-4 solver: top-k of a covariance too large for Jacobi) against
+    numpy eigh on a planted spectrum; eigenvalues 1e-9 rel, subspace by principal angles, orthonormal columns."""
+    torch = require_gpu()
+    rng = np.random.default_rng(4242)
+    n, k = 1500, 40
+    F = np.linalg.qr(rng.normal(size=(n, 300)))[0]
+    sig = 40.0 * np.arange(1, 301) ** -0.7
+    Cm = (F * sig ** 2) @ F.T + 16.0 * np.eye(n) + 1e-3 * np.diag(rng.random(n))
+    Cm = (Cm + Cm.T) / 2
+    w, V = np.linalg.eigh(Cm)
+    w, V = w[::-1], V[:, ::-1]
+    lam, Q, info = ef.dist.eigh_topk_device(torch.from_numpy(Cm).cuda(), k)
+    lam, Q = lam.cpu().numpy(), Q.cpu().numpy()
+    np.testing.assert_allclose(lam, w[:k], rtol=1e-9)
+    np.testing.assert_allclose(Q.T @ Q, np.eye(k), atol=1e-10)
+    # principal angles between span(Q) and span(V[:, :k]): cosines = singular values of V_k^T Q
+    cosines = np.linalg.svd(V[:, :k].T @ Q, compute_uv=False)
+    assert np.sqrt(np.maximum(0.0, 1.0 - cosines.min() ** 2)) < 1e-6, (cosines.min(), info)
+    assert info["residual"] <= 1e-11 and info["outer"] < 60, info
+
+
+def test_row_sharded_fit_subspace_branch_matches_oracle():
+    """fit_gen1_sharded with the subspace solver (what D = 10 000 uses) on a size the oracle finishes quickly."""
+    torch = require_gpu()
+    rng = np.random.default_rng(7)
+    N, D, k = 2500, 640, 16
+    X = np.clip(np.rint(128 + 25 * rng.normal(size=(N, 24)) @ rng.normal(size=(24, D)) / np.sqrt(24) * np.linspace(2, 0.3, D)
+                        + rng.normal(0, 3, (N, D))), 0, 255).astype(np.uint8)
+    E, mean, proj, ev = ef.dist.fit_gen1_sharded(torch.from_numpy(X).cuda(), N, k, solver="subspace")
+    E_ref, mean_ref, proj_ref, ev_ref = gen1.manual_pca(X.astype(np.float64), k)
+    np.testing.assert_allclose(ev.cpu().numpy(), ev_ref, rtol=1e-9)
+    assert np.array_equal(mean.cpu().numpy(), mean_ref)
+    sign = np.sign(np.sum(E.cpu().numpy() * E_ref, axis=0))
+    gaps = np.abs(np.diff(ev_ref)) / ev_ref[:-1]
+    well = np.concatenate([[True], gaps > 1e-3]) & np.concatenate([gaps > 1e-3, [True]])   # well-separated components
+    np.testing.assert_allclose((E.cpu().numpy() * sign)[:, well], E_ref[:, well], atol=1e-6)
+    np.testing.assert_allclose((proj.cpu().numpy() * sign)[:, well], proj_ref[:, well], atol=1e-4)
