@@ -1,9 +1,11 @@
 // K1: crop preprocess, bit-exact with OpenCV's BGR2GRAY + INTER_LINEAR resize on uint8.
 //
 // Replaces cv2.cvtColor + cv2.resize + .flatten() at scan-template-v4.py:257-263, train-v5.py:329-332 and
-// useless/scan.py:248-252 for a whole batch of detection boxes.  HBM-bound byte work: one CTA walks crops,
-// coefficient tables live in shared memory, the source ROI is read through L1 (each source pixel is needed by
-// at most two destination rows / columns), the destination row is written coalesced.
+// useless/scan.py:248-252 for a whole batch of detection boxes.  HBM-bound byte work: one CTA walks crops;
+// per crop the coefficient tables live in shared memory, the source rows a band of output rows needs are STAGED in
+// shared memory as gray bytes (16-byte coalesced loads for gray frames, fused BGR->gray for colour frames) so that
+// every source byte is read from HBM/L2 once, the four taps of an output pixel come from shared memory, the x-axis
+// taps / weights of a thread's column stay in registers, and the destination row is written coalesced.
 //
 // Fixed-point spec (the same one oracle/preprocess.py states and tests pin against cv2):
 //   gray = (3735 B + 19235 G + 9798 R + 2^14) >> 15
@@ -26,10 +28,12 @@ __device__ __forceinline__ int gray_at(const uint8_t* __restrict__ row, int x, i
 }
 
 // One axis of OpenCV's coefficient table, computed with explicitly rounded (never fused) operations.
-__device__ __forceinline__ void axis_coeff(int d, int src, int dst, bool clamp_frac, int& s0, int& s1, int& w0,
-                                           int& w1) {
+__device__ __forceinline__ double axis_scale(int src, int dst) {
   const double inv_scale = __ddiv_rn((double)dst, (double)src);
-  const double scale = __ddiv_rn(1.0, inv_scale);
+  return __ddiv_rn(1.0, inv_scale);
+}
+__device__ __forceinline__ void axis_coeff(int d, int src, double scale, bool clamp_frac, int& s0, int& s1, int& w0,
+                                           int& w1) {
   const double fd = __dadd_rn(__dmul_rn((double)d + 0.5, scale), -0.5);
   float f = __double2float_rn(fd);
   const float fl = floorf(f);
@@ -48,8 +52,9 @@ __device__ __forceinline__ void axis_coeff(int d, int src, int dst, bool clamp_f
 __global__ void __launch_bounds__(kThreads)
 preprocess_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int pitch, int width, int height,
                   int channels, int n_frames, const ef_box_t* __restrict__ boxes, int n_boxes, int dw, int dh,
-                  uint8_t* __restrict__ out, int64_t out_stride, int* __restrict__ bad_boxes) {
-  extern __shared__ int tab[];
+                  uint8_t* __restrict__ out, int64_t out_stride, int* __restrict__ bad_boxes, int stage_bytes) {
+  extern __shared__ __align__(16) int tab[];
+  __shared__ double scales[2];
   int* xs0 = tab;
   int* xs1 = xs0 + dw;
   int* xa0 = xs1 + dw;
@@ -58,6 +63,7 @@ preprocess_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int 
   int* ys1 = ys0 + dh;
   int* yb0 = ys1 + dh;
   int* yb1 = yb0 + dh;
+  uint8_t* stage = reinterpret_cast<uint8_t*>(yb1 + dh);   // byte offset 16 (dw + dh): 16-byte aligned
   const int tid = threadIdx.x;
   const int npix = dw * dh;
 
@@ -103,24 +109,123 @@ preprocess_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int 
         o[i] = (uint8_t)((s + 2) >> 2);
       }
     } else {
-      for (int d = tid; d < dw + dh; d += kThreads) {
-        if (d < dw) {
-          axis_coeff(d, w, dw, true, xs0[d], xs1[d], xa0[d], xa1[d]);
-        } else {
-          const int e = d - dw;
-          axis_coeff(e, h, dh, false, ys0[e], ys1[e], yb0[e], yb1[e]);
+      // the two double-precision divisions of an axis scale are done once per crop (threads 0 and 32), not per entry
+      if (tid == 0) scales[0] = axis_scale(w, dw);
+      if (tid == 32) scales[1] = axis_scale(h, dh);
+      __syncthreads();
+      {
+        const double sx = scales[0], sy = scales[1];
+        for (int d = tid; d < dw + dh; d += kThreads) {
+          if (d < dw) {
+            axis_coeff(d, w, sx, true, xs0[d], xs1[d], xa0[d], xa1[d]);
+          } else {
+            const int e = d - dw;
+            axis_coeff(e, h, sy, false, ys0[e], ys1[e], yb0[e], yb1[e]);
+          }
         }
       }
       __syncthreads();
-      for (int i = tid; i < npix; i += kThreads) {
-        const int y = i / dw, x = i - y * dw;
-        const uint8_t* r0 = src + (int64_t)ys0[y] * pitch;
-        const uint8_t* r1 = src + (int64_t)ys1[y] * pitch;
-        const int x0 = xs0[x], x1 = xs1[x], a0 = xa0[x], a1 = xa1[x];
-        const int h0 = gray_at(r0, x0, channels) * a0 + gray_at(r0, x1, channels) * a1;
-        const int h1 = gray_at(r1, x0, channels) * a0 + gray_at(r1, x1, channels) * a1;
-        const int v = (((yb0[y] * (h0 >> 4)) >> 16) + ((yb1[y] * (h1 >> 4)) >> 16) + 2) >> 2;
-        o[i] = (uint8_t)min(max(v, 0), 255);
+      // shared-memory row pitch of the staged gray rows; gray frames keep the 16-byte phase of the source address so
+      // that the staging loads are aligned uint4 (pixel x of a row sits at column `phase + x`)
+      const bool vec = channels == 1 && (pitch % 16 == 0) && ((reinterpret_cast<uintptr_t>(frames) & 15) == 0) &&
+                       (frame_stride % 16 == 0);
+      const int phase = vec ? (int)((reinterpret_cast<uintptr_t>(src)) & 15) : 0;
+      const int wp = ((phase + w + 15) & ~15);
+      const int rows_fit = stage_bytes / wp;
+      if (rows_fit < 2 || dw > kThreads) {
+        // ROI row too wide for the staging buffer (or very wide output): taps straight from global memory
+        for (int i = tid; i < npix; i += kThreads) {
+          const int y = i / dw, x = i - y * dw;
+          const uint8_t* r0 = src + (int64_t)ys0[y] * pitch;
+          const uint8_t* r1 = src + (int64_t)ys1[y] * pitch;
+          const int x0 = xs0[x], x1 = xs1[x], a0 = xa0[x], a1 = xa1[x];
+          const int h0 = gray_at(r0, x0, channels) * a0 + gray_at(r0, x1, channels) * a1;
+          const int h1 = gray_at(r1, x0, channels) * a0 + gray_at(r1, x1, channels) * a1;
+          const int v = (((yb0[y] * (h0 >> 4)) >> 16) + ((yb1[y] * (h1 >> 4)) >> 16) + 2) >> 2;
+          o[i] = (uint8_t)min(max(v, 0), 255);
+        }
+      } else {
+        // this thread's FOUR adjacent output columns and its row phase; the x-axis taps and weights stay in registers
+        // (dw % 4 == 0 and 4-byte aligned output rows: one 32-bit store per thread and row; otherwise one column each)
+        const bool quad = (dw % 4 == 0) && (out_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 3) == 0);
+        const int cols = quad ? dw / 4 : dw;               // work items per output row
+        const int R = kThreads / cols;                     // output rows in flight per pass
+        const int ph = tid / cols, cx = tid - ph * cols;
+        const bool worker = ph < R;
+        int tx0[4], tx1[4], ta0[4], ta1[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int dx = quad ? 4 * cx + j : cx;
+          tx0[j] = worker ? phase + xs0[dx] : 0;
+          tx1[j] = worker ? phase + xs1[dx] : 0;
+          ta0[j] = worker ? xa0[dx] : 0;
+          ta1[j] = worker ? xa1[dx] : 0;
+        }
+        int dy0 = 0;
+        while (dy0 < dh) {
+          // band of output rows [dy0, dy1) whose source rows [r_lo, r_hi] fit the staging buffer
+          const int r_lo = ys0[dy0];
+          int dy1 = dh;                                     // common case: everything that is left fits
+          if (ys1[dh - 1] - r_lo + 1 > rows_fit) {
+            int lo = dy0 + 1, hi = dh;                      // largest dy1 with ys1[dy1 - 1] - r_lo + 1 <= rows_fit
+            while (lo < hi) {
+              const int mid = (lo + hi + 1) >> 1;
+              if (ys1[mid - 1] - r_lo + 1 <= rows_fit) lo = mid; else hi = mid - 1;
+            }
+            dy1 = lo;
+          }
+          const int r_hi = ys1[dy1 - 1];
+          const int n_rows = r_hi - r_lo + 1;
+          if (vec) {
+            const int vec_per_row = wp >> 4;
+            const uint8_t* base = src - phase + (int64_t)r_lo * pitch;          // 16-byte aligned
+            // 8 / 16 / 32 lanes per source row (power of two: shifts, no divisions)
+            const int lpr_log2 = vec_per_row <= 8 ? 3 : (vec_per_row <= 16 ? 4 : 5);
+            const int lane_v = tid & ((1 << lpr_log2) - 1), row_slot = tid >> lpr_log2, slots = kThreads >> lpr_log2;
+            // cp.async: every thread's copies are in flight together (one memory latency per band, not one per row)
+            for (int r = row_slot; r < n_rows; r += slots) {
+              const uint8_t* g = base + (int64_t)r * pitch;
+              const unsigned sm = (unsigned)__cvta_generic_to_shared(stage + r * wp);
+              for (int v = lane_v; v < vec_per_row; v += 1 << lpr_log2)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sm + 16u * v), "l"(g + 16 * v));
+            }
+            asm volatile("cp.async.commit_group;\n" ::);
+            asm volatile("cp.async.wait_group 0;\n" ::);
+          } else {
+            // one warp per source row: coalesced byte reads, BGR -> gray fused into the staging
+            for (int r = tid >> 5; r < n_rows; r += kThreads >> 5) {
+              const uint8_t* g = src + (int64_t)(r_lo + r) * pitch;
+#pragma unroll 4
+              for (int x = tid & 31; x < w; x += 32) stage[r * wp + x] = (uint8_t)gray_at(g, x, channels);
+            }
+          }
+          __syncthreads();
+          if (worker) {
+            for (int y = dy0 + ph; y < dy1; y += R) {
+              const uint8_t* r0 = stage + (ys0[y] - r_lo) * wp;
+              const uint8_t* r1 = stage + (ys1[y] - r_lo) * wp;
+              const int b0 = yb0[y], b1 = yb1[y];
+              if (quad) {
+                unsigned packed = 0;
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const int h0 = r0[tx0[j]] * ta0[j] + r0[tx1[j]] * ta1[j];
+                  const int h1 = r1[tx0[j]] * ta0[j] + r1[tx1[j]] * ta1[j];
+                  const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                  packed |= (unsigned)min(max(v, 0), 255) << (8 * j);
+                }
+                *reinterpret_cast<unsigned*>(o + y * dw + 4 * cx) = packed;
+              } else {
+                const int h0 = r0[tx0[0]] * ta0[0] + r0[tx1[0]] * ta1[0];
+                const int h1 = r1[tx0[0]] * ta0[0] + r1[tx1[0]] * ta1[0];
+                const int v = (((b0 * (h0 >> 4)) >> 16) + ((b1 * (h1 >> 4)) >> 16) + 2) >> 2;
+                o[y * dw + cx] = (uint8_t)min(max(v, 0), 255);
+              }
+            }
+          }
+          __syncthreads();                                  // the staging buffer is refilled by the next band
+          dy0 = dy1;
+        }
       }
       __syncthreads();  // tables are rewritten by the next crop
     }
@@ -140,9 +245,18 @@ extern "C" int ef_preprocess(const uint8_t* frames, int64_t frame_stride, int32_
   if (pitch < width * channels || out_stride < (int64_t)dw * dh) return EF_ERR_INVALID;
   if (dw > kMaxSide || dh > kMaxSide) return EF_ERR_UNSUPPORTED;
   if (n_boxes == 0) return EF_OK;
-  const int grid = (int)(n_boxes < (int64_t)ef::sm_count() * 8 ? n_boxes : ef::sm_count() * 8);
-  const size_t smem = sizeof(int) * 4 * (size_t)(dw + dh);
+  // coefficient tables + a 64 KB staging buffer for the source rows of a band: three CTAs per SM
+  constexpr int kStageBytes = 64 * 1024;
+  const size_t tables = sizeof(int) * (4 * (size_t)(dw + dh) + 4);
+  const size_t smem = tables + kStageBytes;
+  static bool configured = false;
+  if (!configured) {
+    EF_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    configured = true;
+  }
+  const int64_t resident = (int64_t)ef::sm_count() * 3;
+  const int grid = (int)(n_boxes < resident ? n_boxes : resident);
   EF_LAUNCH(preprocess_kernel, grid, kThreads, smem, ef::as_stream(stream), frames, frame_stride, pitch, width,
-            height, channels, n_frames, boxes, n_boxes, dw, dh, out, out_stride, bad_boxes);
+            height, channels, n_frames, boxes, n_boxes, dw, dh, out, out_stride, bad_boxes, kStageBytes);
   return EF_OK;
 }
