@@ -27,6 +27,17 @@ int recognize_cluster(const uint8_t* X, int64_t ldx, int B, int D, const int8_t*
                       const double* ginv, const void* gimg, int64_t n, const int32_t* labels, int metric,
                       double threshold, double* out_proj, double* out_score, int32_t* out_index, int32_t* out_label,
                       double* out_resid, int* status, cudaStream_t stream);
+// ef_recognize_pipe.cu -- software-pipelined form: streams batch i while matching batch i-1 (rows carried in global
+// memory between launches); B = 0 flushes, Bp = 0 is the first submit
+bool pipe_supported(int k, int NC, int metric, int64_t n);
+int filter_kf(int k);
+int recognize_pipe(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int wq_rows, int k,
+                   int kq, int S, const int32_t* col_exp, const double* bias, const double* sumsq_ext, bool want_resid,
+                   double c0, double* out_proj, double* out_resid, double* carry_pe, double* carry_pn, void* carry_img,
+                   int Bp, const double* prev_pe, const double* prev_pn, const void* prev_img, double* out_score,
+                   int32_t* out_index, int32_t* out_label, double threshold, const double* gp_padded, int kpad,
+                   const double* gnorm, const double* ginv, const void* gimg, int64_t n, const int32_t* labels,
+                   int metric, int* status, cudaStream_t stream);
 // float16 [g_hi | g_lo | g_hi] image of a prepared gallery for the tensor-core filter of the cluster kernel
 size_t gallery_image_bytes(int k, int64_t n);
 int gallery_image(const double* gp, int kr, const double* ginv, int64_t n, int k, int metric, void* img,

@@ -32,6 +32,17 @@ struct ef_model {
   ef::DevBuf x_dev, resid_dev, index32_dev, label_dev, frames_dev, boxes_dev, bad_dev;
   int64_t x_ld = 0;
   cudaStream_t stream = nullptr;   // owned, used by the host entry points
+  // pipelined submission (ef_model_submit_device): rows carried from one launch to the next, double buffered
+  ef::DevBuf carry_pe[2], carry_pn[2], carry_img[2];
+  int carry_reserved = 0;
+  struct Pending {
+    int B = 0;
+    double* score = nullptr;
+    int32_t* index = nullptr;
+    int32_t* label = nullptr;
+    double threshold = 0.0;
+    int slot = 0;
+  } pending;
   void* pinned = nullptr;                             // owned page-locked staging for the results of the host path
   size_t pinned_bytes = 0;
   cudaStream_t copy_stream = nullptr;                 // owned: chunked H2D of the host path runs ahead of the kernels
@@ -299,6 +310,7 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
   if (out->resid2 && !m->with_residual) return EF_ERR_INVALID;
   if (B == 0) return EF_OK;
   EF_TRY(ef_model_reserve(m, B));
+  if (m->pending.B > 0) EF_TRY(ef_model_flush_device(m, stream));   // results of a pipelined batch come out first
   cudaStream_t st = ef::as_stream(stream);
   int32_t* acc = m->acc.as<int32_t>();
   // 1. exact integer digit-plane dot products
@@ -374,6 +386,69 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
   }
   m->dirty = false;
   return EF_OK;
+}
+
+static int pipe_launch(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
+                       const ef_result_t* out, cudaStream_t st) {
+  const int kr = m->kpad;
+  const int slot = m->pending.slot ^ 1;              // rows of the batch submitted now go to the other buffer
+  const int cap = std::max(B, m->pending.B);
+  if (cap > m->carry_reserved) {
+    // growing the carry buffers would lose the pending rows: finish the pending batch with an empty launch first
+    if (m->pending.B > 0) EF_TRY(pipe_launch(m, nullptr, 0, 0, 0.0, nullptr, st));
+    EF_CUDA(cudaStreamSynchronize(st));
+    const size_t rows = (size_t)ef::round_up(cap, 128);
+    for (int i = 0; i < 2; ++i) {
+      EF_TRY(m->carry_pe[i].ensure(sizeof(double) * rows * kr));
+      EF_TRY(m->carry_pn[i].ensure(sizeof(double) * rows));
+      EF_TRY(m->carry_img[i].ensure(2 * rows * (size_t)ef::filter_kf(m->k)));
+    }
+    m->carry_reserved = (int)rows;
+  }
+  const bool want_resid = B > 0 && out->resid2 != nullptr;
+  const double* sumsq_ext = nullptr;
+  if (want_resid && m->has_scale) {
+    EF_TRY(ef::row_sumsq(x, ldx, B, m->D, m->qq.as<double>(), m->sumsq_w.as<double>(), st));
+    sumsq_ext = m->sumsq_w.as<double>();
+  }
+  const int32_t* labels = m->labels.p ? m->labels.as<int32_t>() : nullptr;
+  const ef_model::Pending& pv = m->pending;
+  EF_TRY(ef::recognize_pipe(
+      x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, m->nc_pad, m->k, m->kq, m->S, m->col_exp.as<int32_t>(),
+      m->bias.as<double>(), sumsq_ext, want_resid, m->c0, B > 0 ? out->proj : nullptr, want_resid ? out->resid2 : nullptr,
+      m->carry_pe[slot].as<double>(), m->carry_pn[slot].as<double>(), m->carry_img[slot].p, pv.B,
+      m->carry_pe[pv.slot].as<double>(), m->carry_pn[pv.slot].as<double>(), m->carry_img[pv.slot].p, pv.score, pv.index,
+      pv.label, pv.threshold, m->gp.as<double>(), m->kpad, m->gnorm.as<double>(), m->ginv.as<double>(), m->gimg.p,
+      m->n_gallery, labels, m->metric, m->status.as<int>(), st));
+  m->pending.B = B;
+  m->pending.slot = slot;
+  if (B > 0) {
+    m->pending.score = out->score;
+    m->pending.index = out->index;
+    m->pending.label = out->label;
+    m->pending.threshold = threshold;
+  }
+  m->last_used_tc = true;
+  m->last_path = 3;
+  return EF_OK;
+}
+
+int ef_model_submit_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
+                           const ef_result_t* out, ef_stream_t stream) {
+  if (m && B == 0) return EF_OK;
+  if (!m || !x || !out || B < 0 || ldx < m->D || !out->score || !out->index) return EF_ERR_INVALID;
+  if (out->resid2 && !m->with_residual) return EF_ERR_INVALID;
+  const bool aligned = !(ldx & 15) && !(reinterpret_cast<uintptr_t>(x) & 15);
+  if (m->tc_mode < 2 || !aligned || !m->gimg.p || !ef::pipe_supported(m->k, m->NC, m->metric, m->n_gallery))
+    return ef_model_recognize_device(m, x, ldx, B, threshold, out, stream);    // not pipelined: results right away
+  EF_TRY(ef_model_reserve(m, B));
+  return pipe_launch(m, x, ldx, B, threshold, out, ef::as_stream(stream));
+}
+
+int ef_model_flush_device(ef_model_t* m, ef_stream_t stream) {
+  if (!m) return EF_ERR_INVALID;
+  if (m->pending.B <= 0) return EF_OK;
+  return pipe_launch(m, nullptr, 0, 0, 0.0, nullptr, ef::as_stream(stream));
 }
 
 int ef_model_status(ef_model_t* m, int32_t* tc_pipeline_timeouts) {

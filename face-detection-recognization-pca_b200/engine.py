@@ -171,6 +171,36 @@ class Recognizer:
                                                 C.c_void_p(stream)), "ef_model_recognize_device")
         return out
 
+    def submit_device(self, x, threshold=0.7, out=None, want_residual=None):
+        """Pipelined form of recognize_device for a stream of batches (ef_model_submit_device): features / resid2 of
+        this batch are produced by this call's launch, score / index / label by the NEXT submit_device or by
+        flush_device().  Returns the dict of output tensors (keep it alive until then)."""
+        import torch
+        if not (x.is_cuda and x.dtype == torch.uint8 and x.dim() == 2 and x.stride(1) == 1):
+            raise ValueError("x must be a 2-D uint8 CUDA tensor with unit inner stride")
+        B = x.shape[0]
+        want_residual = self.with_residual if want_residual is None else want_residual
+        if out is None:
+            out = {
+                "features": torch.empty((B, self.k), dtype=torch.float64, device=x.device),
+                "score": torch.empty(B, dtype=torch.float64, device=x.device),
+                "index": torch.empty(B, dtype=torch.int32, device=x.device),
+                "label": torch.empty(B, dtype=torch.int32, device=x.device),
+                "resid2": torch.empty(B, dtype=torch.float64, device=x.device) if want_residual else None,
+            }
+        res = Result(out["features"].data_ptr(), out["score"].data_ptr(), out["index"].data_ptr(),
+                     out["label"].data_ptr(), out["resid2"].data_ptr() if out.get("resid2") is not None else None)
+        stream = torch.cuda.current_stream(x.device).cuda_stream
+        check(self._L.ef_model_submit_device(self._h, x.data_ptr(), x.stride(0), B, float(threshold), C.byref(res),
+                                             C.c_void_p(stream)), "ef_model_submit_device")
+        return out
+
+    def flush_device(self, device=None):
+        """Completes the batch left pending by submit_device (enqueues on torch's current stream)."""
+        import torch
+        stream = torch.cuda.current_stream(device).cuda_stream
+        check(self._L.ef_model_flush_device(self._h, C.c_void_p(stream)), "ef_model_flush_device")
+
     def recognize_boxes_device(self, frames, boxes, side, threshold=0.7, out=None, want_residual=None):
         """frames: torch uint8 CUDA [F, H, W] / [F, H, W, 3]; boxes: torch int32 CUDA [B, 5] (frame, x, y, w, h)."""
         import torch

@@ -142,6 +142,19 @@ int ef_model_recognize_device(ef_model_t* model, const uint8_t* x, int64_t ldx, 
                               const ef_result_t* out, ef_stream_t stream);
 int ef_model_recognize_host(ef_model_t* model, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
                             const ef_result_t* out);
+/* Pipelined submission for a STREAM of batches on one CUDA stream (serving loop; replaces the same reference lines as
+ * ef_model_recognize_device).  Each launch streams the batch submitted now AND matches the batch submitted before, on
+ * different warps of the same kernel, so HBM streaming of batch i overlaps the nearest-gallery search of batch i-1.
+ *   - out->proj and out->resid2 of a batch are written by the launch of its own submit call;
+ *   - out->score / out->index / out->label of a batch are written by the NEXT ef_model_submit_device on the model, or by
+ *     ef_model_flush_device: the arrays must stay valid (and are complete in stream order) until then;
+ *   - every value is bit identical to ef_model_recognize_device.
+ * Shapes outside the pipelined kernel (L2 metric, k > 21, more than 128 digit-plane columns, unaligned crops) are
+ * recognised immediately, exactly like ef_model_recognize_device.  Any other recognise call on the model flushes a
+ * pending batch first.  All calls of one pipeline must use the same stream. */
+int ef_model_submit_device(ef_model_t* model, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
+                           const ef_result_t* out, ef_stream_t stream);
+int ef_model_flush_device(ef_model_t* model, ef_stream_t stream);
 /* Same, starting from frames + boxes (K1 then K2).  Host variant copies the frames and boxes in. */
 int ef_model_recognize_boxes_device(ef_model_t* model, const uint8_t* frames, int64_t frame_stride, int32_t pitch,
                                     int32_t width, int32_t height, int32_t channels, int32_t n_frames,

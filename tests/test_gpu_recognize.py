@@ -327,3 +327,49 @@ def test_tensor_core_filter_is_exact_on_adversarial_galleries(metric, k, n_galle
     decided = (srt[:, -1] - srt[:, -2]) > 1e-12 if n_gallery > 1 else np.ones(B, bool)
     assert np.array_equal(outs[1].index[decided], np.argmax(sims, axis=1)[decided])
     np.testing.assert_allclose(outs[1].score, sims.max(1), atol=SCORE_ATOL)
+
+
+@pytest.mark.parametrize("metric", [ef.METRIC_COSINE_G1, ef.METRIC_COSINE_SK])
+def test_pipelined_submission_is_bit_identical(metric, light_model, golden):
+    """ef_model_submit_device / ef_model_flush_device (streaming half of batch i and matching half of batch i-1 in one
+    launch) return exactly what ef_model_recognize_device returns, for batches of changing sizes, including ragged
+    tiles, a batch larger and one smaller than its predecessor, a single crop, and an interleaved ordinary call."""
+    torch = require_gpu()
+    X = golden("gen1_light.npz")["X_u8"]
+    rng = np.random.default_rng(77 + metric)
+    k = 10
+    E = light_model["eigenfaces"][:, :k].copy(order="F")
+    G = light_model["projected_data"][:, :k].copy()
+    kw = {}
+    if metric == ef.METRIC_COSINE_SK:
+        kw = dict(scale=rng.uniform(20.0, 60.0, 10000), pca_mean=rng.normal(0, 1e-3, 10000))
+    rec = ef.Recognizer(E, light_model["mean_face"], G, metric=metric, labels=np.arange(len(G)) % 3, **kw)
+    sizes = [300, 1000, 129, 1, 640, 128, 4096]
+    batches = []
+    for n in sizes:
+        xb = torch.zeros((n, 10112), dtype=torch.uint8, device="cuda")
+        xb[:, :10000] = torch.from_numpy(face_like(rng, X, n)).cuda()
+        batches.append(xb)
+    want = [{f: v.clone() for f, v in rec.recognize_device(xb, 0.8).items()} for xb in batches]
+    torch.cuda.synchronize()
+    outs = [rec.submit_device(xb, 0.8) for xb in batches]
+    rec.flush_device()
+    torch.cuda.synchronize()
+    assert rec.pipeline_timeouts() == 0
+    for i, (o, w) in enumerate(zip(outs, want)):
+        for f in ("features", "score", "index", "label", "resid2"):
+            assert torch.equal(o[f], w[f]), (i, sizes[i], f)
+    # an ordinary call in the middle of a pipeline flushes the pending batch first
+    o1 = rec.submit_device(batches[0], 0.8)
+    mid = rec.recognize_device(batches[1], 0.8)
+    torch.cuda.synchronize()
+    for f in ("score", "index", "label"):
+        assert torch.equal(o1[f], want[0][f]) and torch.equal(mid[f], want[1][f]), f
+    rec.flush_device()                                            # nothing pending: no-op
+    # shapes outside the pipelined kernel fall back to the immediate path
+    rec50 = ef.gen1.recognizer_for(light_model)                    # k = 50
+    o50 = rec50.submit_device(batches[0], 0.8)
+    w50 = rec50.recognize_device(batches[0], 0.8)
+    torch.cuda.synchronize()
+    for f in ("features", "score", "index", "label"):
+        assert torch.equal(o50[f], w50[f]), f
