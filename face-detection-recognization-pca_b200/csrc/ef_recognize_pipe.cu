@@ -20,6 +20,7 @@
 // scaler.transform + pca.transform + recognize_face_with_model (scan-template-v4.py:265-287) for a stream of batches.
 #include <climits>
 #include <cstdlib>
+#include <vector>
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
@@ -37,7 +38,8 @@ constexpr int kThreads = kWarps * 32;
 constexpr int QB = BLOCK_M / kCluster;      // crops finished by each CTA (one per lane)
 constexpr int kStreamWarps = 6;             // warp 0 TMA, warp 1 MMA, warps 2..5 drain; all six combine the features
 constexpr int kScanWarps = 8;               // warps 8..15
-constexpr int kGalTile = 128;               // gallery rows per filter MMA (two 128-column TMEM score buffers)
+constexpr int kGalTile = 128;               // gallery rows per filter MMA
+constexpr int kScoreBufs = 3;               // 128-column TMEM score buffers (columns 128..511; the accumulator has 0..127)
 constexpr int kMaxRing = 8;
 constexpr int kListCap = 256;
 constexpr float kFilterEps = 5e-5f;         // same bound as recognize_cluster_kernel
@@ -73,6 +75,7 @@ struct PipeArgs {
   const __half* gimg;
   int* status;
   int off_recv, off_ps, off_pe, off_aimg, off_gal, off_sh;
+  unsigned long long* probe;   // debugging aid (EF_TC_PROBE): [grid][16] globaltimer stamps
 };
 
 struct PipeShared {
@@ -81,8 +84,8 @@ struct PipeShared {
   unsigned long long tmem_full_bar;
   unsigned long long gal_full[kMaxRing];
   unsigned long long gal_empty[kMaxRing];
-  unsigned long long score_full[2];
-  unsigned long long score_empty[2];
+  unsigned long long score_full[kScoreBufs];
+  unsigned long long score_empty[kScoreBufs];
   unsigned long long aimg_ready;
   uint32_t tmem_base;
   int failed;
@@ -168,6 +171,19 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   const uint32_t gal_tile_bytes = (uint32_t)kGalTile * (uint32_t)row_bytes;
   const int n_seq = 2 * a.g_tiles;
   const int b = m_tile * BLOCK_M + (int)rank * QB + lane;       // the crop this lane finishes (either batch)
+  // per-column constants of the feature combination, fetched before the main loop (off the critical path)
+  int my_exp[6] = {0, 0, 0, 0, 0, 0};
+  double my_bias[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (warp < kStreamWarps) {
+#pragma unroll
+    for (int it = 0; it < 6; ++it) {
+      const int c = warp + it * kStreamWarps;
+      if (c < a.kq) {
+        my_exp[it] = a.col_exp[c];
+        if (c < a.k) my_bias[it] = a.bias[c];
+      }
+    }
+  }
 
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
@@ -179,7 +195,7 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       mbar_init(&sh->gal_full[s], 1);
       mbar_init(&sh->gal_empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kScoreBufs; ++s) {
       mbar_init(&sh->score_full[s], 1);
       mbar_init(&sh->score_empty[s], kScanWarps);
     }
@@ -204,6 +220,8 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
   asm volatile("griddepcontrol.wait;" ::: "memory"); // the previous launch wrote the carried rows read below
   const uint32_t tmem_base = sh->tmem_base;
   volatile int* failed = &sh->failed;
+  unsigned long long* probe = a.probe ? a.probe + (size_t)blockIdx.x * 16 : nullptr;
+  if (probe && tid == 0) probe[0] = globaltimer();
 
   if (warp < kStreamWarps) {
     // =================================================================== stream half (current batch)
@@ -242,6 +260,7 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         if (ok) umma_commit(&sh->tmem_full_bar);
+        if (probe) probe[1] = globaltimer();
       }
       __syncwarp();
       cluster_wait();                               // #1
@@ -295,8 +314,10 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       tc_fence_before();
     }
     bar_stream();
+    if (probe && tid == 0) probe[2] = globaltimer();
     cluster_arrive();                               // #2: my pushes are out
     cluster_wait();                                 //     all four partial slabs of my 32 crops have landed
+    if (probe && tid == 0) probe[3] = globaltimer();
     if (have_cur) {
       const bool live = b < a.B;
       unsigned long long ssq_total = 0;
@@ -304,7 +325,10 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
         for (int q = 0; q < kCluster; ++q) ssq_total += sh->ssq_recv[q][lane];
       }
-      for (int c = warp; c < KR; c += kStreamWarps) {
+#pragma unroll
+      for (int it = 0; it < 6; ++it) {
+        const int c = warp + it * kStreamWarps;
+        if (c >= KR) break;
         double v = 0.0;
         if (c < a.kq) {
           for (int s = a.S - 1; s >= 0; --s) {
@@ -314,10 +338,10 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             for (int q = 0; q < kCluster; ++q) sum += src[q * a.nc_pad * 32];
             v += (double)sum * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
           }
-          v = ldexp(v, a.col_exp[c]);
+          v = ldexp(v, my_exp[it]);
         }
         if (c < a.k) {
-          v -= a.bias[c];
+          v -= my_bias[it];
           if (a.out_proj && live) a.out_proj[(size_t)b * a.k + c] = v;
         }
         ps[c * QB + lane] = c < a.k ? v : 0.0;
@@ -372,6 +396,7 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
       }
     }
+    if (probe && tid == 0) probe[4] = globaltimer();
   } else {
     // =================================================================== match half (previous batch)
     cluster_wait();                                 // #1
@@ -414,10 +439,11 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           int slot = 0;
           uint32_t gphase = 0;
           uint64_t bslot = bdesc0;
+          int buf = 0;
+          uint32_t bphase = 1;                       // parity trick: a fresh barrier passes a wait on parity 1
           for (int s = 0; s < n_seq && ok; ++s) {
-            const int buf = s & 1;
             if (!mbar_wait(&sh->gal_full[slot], gphase, failed)) break;
-            if (!mbar_wait(&sh->score_empty[buf], (uint32_t)(((s >> 1) & 1) ^ 1), failed)) break;
+            if (!mbar_wait(&sh->score_empty[buf], bphase, failed)) break;
             tc_fence_after();
             const uint32_t d_addr = tmem_base + 128u + (uint32_t)buf * kGalTile;
 #pragma unroll 1
@@ -429,6 +455,7 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
             umma_commit(&sh->score_full[buf]);
             bslot += slot_step;
             if (++slot == a.ring) { slot = 0; gphase ^= 1; bslot = bdesc0; }
+            if (++buf == kScoreBufs) { buf = 0; bphase ^= 1; }
           }
         }
       } else {
@@ -450,6 +477,7 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh->aimg_ready);
+        if (probe && stid == 0) probe[8] = globaltimer();
         double best = -CUDART_INF, best_score = 0.0;
         int best_i = INT_MAX, best_label = -1;
         auto consider = [&](double key, double score, int label, int j) {
@@ -457,9 +485,10 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         };
         float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F, thr = 0.f;
         bool ok = true;
-        int t = -1, pass = 0;
+        int t = -1, pass = 0, buf = -1;
+        uint32_t fphase = 0;
         for (int s = 0; s < n_seq; ++s) {
-          const int buf = s & 1, suse = s >> 1;
+          if (++buf == kScoreBufs) { buf = 0; fphase ^= 1; }
           if (++t == a.g_tiles) { t = 0; pass = 1; }
           if (pass == 1 && t == 0) {
             sh->fmax_s[sw][lane] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
@@ -468,8 +497,9 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
 #pragma unroll
             for (int w = 1; w < kScanWarps; ++w) M = fmaxf(M, sh->fmax_s[w][lane]);
             thr = M - 2.f * kFilterEps;
+            if (probe && stid == 0) probe[9] = globaltimer();
           }
-          ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->score_full[buf], (uint32_t)(suse & 1), failed));
+          ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->score_full[buf], fphase, failed));
           if (!ok) continue;
           tc_fence_after();
           uint32_t v[16];
@@ -514,6 +544,7 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         }
         __threadfence_block();
         bar_scan();
+        if (probe && stid == 0) probe[10] = globaltimer();
         const bool overflow = *reinterpret_cast<volatile int*>(&sh->overflow) != 0;
         const int total = overflow ? 0 : *reinterpret_cast<volatile int*>(&sh->list_cnt);
         for (int e = stid; e < total; e += kScanWarps * 32) {
@@ -555,6 +586,7 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
           a.out_index[b] = bi;
           if (a.out_label) a.out_label[b] = score >= a.threshold ? bl : -1;
         }
+        if (probe && stid == 0) probe[11] = globaltimer();
       }
     }
     __syncwarp();
@@ -569,6 +601,7 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
   if (tid == 0 && sh->failed) atomicExch(a.status, 1);
+  if (probe && tid == 0) probe[6] = globaltimer();
 }
 
 template <int METRIC, int KR>
@@ -600,6 +633,15 @@ int launch_pipe(const CUtensorMap& mx, const CUtensorMap& mw, PipeArgs& a, int m
                                  (int)smem));
     attr = smem;
   }
+  static unsigned long long* probe_buf = nullptr;
+  const bool probing = getenv("EF_TC_PROBE") != nullptr;
+  const int grid_n = m_tiles * kCluster;
+  a.probe = nullptr;
+  if (probing && grid_n <= 4096) {
+    if (!probe_buf) EF_CUDA(cudaMalloc(&probe_buf, sizeof(unsigned long long) * 16 * 4096));
+    EF_CUDA(cudaMemsetAsync(probe_buf, 0, sizeof(unsigned long long) * 16 * 4096, stream));
+    a.probe = probe_buf;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(m_tiles * kCluster));
   cfg.blockDim = dim3(kThreads);
@@ -616,6 +658,27 @@ int launch_pipe(const CUtensorMap& mx, const CUtensorMap& mw, PipeArgs& a, int m
   cfg.numAttrs = getenv("EF_NO_PDL") ? 1 : 2;
   EF_CUDA(cudaLaunchKernelEx(&cfg, recognize_pipe_kernel<METRIC, KR>, mx, mw, a));
   ef::g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (a.probe) {
+    std::vector<unsigned long long> h((size_t)grid_n * 16);
+    EF_CUDA(cudaStreamSynchronize(stream));
+    EF_CUDA(cudaMemcpy(h.data(), probe_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (int c = 0; c < grid_n; ++c) if (h[(size_t)c * 16] && h[(size_t)c * 16] < t0) t0 = h[(size_t)c * 16];
+    const char* names[16] = {"start", "mma_issued", "pushed", "exchanged", "carried", "-", "end", "-",
+                             "aimg", "max_known", "listed", "matched", "-", "-", "-", "-"};
+    fprintf(stderr, "[ef_pipe_probe] grid %d B %d Bp %d ring %d; us since first CTA start (mean/max):", grid_n, a.B, a.Bp, a.ring);
+    for (int i = 0; i < 16; ++i) {
+      if (names[i][0] == '-') continue;
+      double sum = 0, mx = 0;
+      for (int c = 0; c < grid_n; ++c) {
+        const double v = h[(size_t)c * 16 + i] ? (double)(h[(size_t)c * 16 + i] - t0) * 1e-3 : 0.0;
+        sum += v;
+        if (v > mx) mx = v;
+      }
+      fprintf(stderr, " %s %.2f/%.2f", names[i], sum / grid_n, mx);
+    }
+    fprintf(stderr, "\n");
+  }
   return EF_OK;
 }
 

@@ -33,4 +33,17 @@ for resid in (True, False):
         for i in range(2):
             rec.recognize_device(xs[i + 1], 0.8, out=out)
         torch.cuda.synchronize()
+        for i in range(3):
+            rec.submit_device(xs[i + 1], 0.8, out=out)
+        rec.flush_device()
+        torch.cuda.synchronize()
         os.environ.pop("EF_TC_PROBE")
+    for i in range(5):
+        rec.submit_device(xs[i % 6], 0.8, out=out)
+    e0.record()
+    for i in range(50):
+        rec.submit_device(xs[i % 6], 0.8, out=out)
+    rec.flush_device()
+    e1.record()
+    torch.cuda.synchronize()
+    print(f"with_residual={resid}: pipelined step {1e3 * e0.elapsed_time(e1) / 51:.1f} us", flush=True)
