@@ -161,7 +161,17 @@ int ef_fit_gen1_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
   EF_CUDA(cudaEventCreate(&tm.a));
   EF_CUDA(cudaEventCreate(&tm.b));
 
-  ef::DevBuf dX, dsum, dmean, dZ, dA, dwork, devals, devecs, dE, dP;
+  // workspaces are kept per host thread and only ever grow: repeated fits (one model per person) pay for cudaMalloc /
+  // cudaFree once, not ~15 times per call
+  static thread_local ef::DevBuf dX, dsum, dmean, dZ, dA, dwork, devals, devecs, dE, dP;
+  static thread_local ef::DevBuf dG, dgw, dcw;
+  static thread_local int ws_device = -1;
+  int cur_device = 0;
+  EF_CUDA(cudaGetDevice(&cur_device));
+  if (cur_device != ws_device) {     // the cached buffers belong to another device: drop them
+    for (ef::DevBuf* bptr : {&dX, &dsum, &dmean, &dZ, &dA, &dwork, &devals, &devecs, &dE, &dP, &dG, &dgw, &dcw}) bptr->release();
+    ws_device = cur_device;
+  }
   const int64_t ldxd = ef::round_up(D, 16);
   EF_TRY(dX.ensure((size_t)N * ldxd));
   EF_TRY(dsum.ensure(sizeof(int64_t) * D));
@@ -173,7 +183,6 @@ int ef_fit_gen1_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
   EF_TRY(devecs.ensure(sizeof(double) * (size_t)n * n));
   EF_TRY(dE.ensure(sizeof(double) * (size_t)D * k));
   EF_TRY(dP.ensure(sizeof(double) * (size_t)N * k));
-  ef::DevBuf dG, dgw, dcw;
   EF_TRY(dG.ensure(sizeof(int64_t) * (size_t)n * n));
   EF_TRY(dgw.ensure(ef_gram_u8_tc_work_bytes(N, D, snapshot ? 0 : 1)));
   EF_TRY(dcw.ensure(ef_gram_center_work_bytes(n) + 16));
@@ -257,7 +266,17 @@ int ef_fit_gen2_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
   EF_CUDA(cudaEventCreate(&tm.a));
   EF_CUDA(cudaEventCreate(&tm.b));
 
-  ef::DevBuf dX, dsum, dmean, dvar, dscale, dpm, dZ, dA, dwork, devals, devecs, dVt, dS, dsign, dF;
+  static thread_local ef::DevBuf dX, dsum, dmean, dvar, dscale, dpm, dZ, dA, dwork, devals, devecs, dVt, dS, dsign, dF,
+      dcoef;
+  static thread_local int ws_device = -1;
+  int cur_device = 0;
+  EF_CUDA(cudaGetDevice(&cur_device));
+  if (cur_device != ws_device) {
+    for (ef::DevBuf* bptr : {&dX, &dsum, &dmean, &dvar, &dscale, &dpm, &dZ, &dA, &dwork, &devals, &devecs, &dVt, &dS,
+                             &dsign, &dF, &dcoef})
+      bptr->release();
+    ws_device = cur_device;
+  }
   const int64_t ldxd = ef::round_up(D, 16);
   EF_TRY(dX.ensure((size_t)N * ldxd));
   EF_TRY(dsum.ensure(sizeof(int64_t) * D));
@@ -328,7 +347,6 @@ int ef_fit_gen2_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
     // (the spectrum comes from the Gram matrix, whose eigenvalues carry an absolute error ~ n eps lambda_1: singular
     // values below sqrt(n eps) sigma_1 are unresolved and count as null)
     const double null_tol = S[0] * std::sqrt((double)std::max(N, D) * 2.220446049250313e-16);
-    ef::DevBuf dcoef;
     for (int c = 0; c < k; ++c) {
       if (S[c] > null_tol) continue;
       EF_TRY(dcoef.ensure(sizeof(double) * k));
