@@ -32,8 +32,6 @@ def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
     cmd = [_nvcc()] + NVCC_FLAGS + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB + ".tmp"]
-    if os.environ.get("EF_DEBUG_FILTER"):
-        cmd.insert(1, "-DEF_DEBUG_FILTER")
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")

@@ -515,9 +515,6 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
         if (better<METRIC>(key, j, best, best_i)) { best = key; best_score = score; best_label = label; best_i = j; }
       };
       float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F, thr = 0.f;
-#ifdef EF_DEBUG_FILTER
-      float dbg_m1 = -CUDART_INF_F;
-#endif
       bool ok = true;
       int t = -1, pass = 0;
       for (int s = 0; s < n_seq; ++s) {
@@ -564,10 +561,6 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
           unsigned mask = 0u;
 #pragma unroll
           for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(v[i]) >= thr ? 1u : 0u) << i;
-#ifdef EF_DEBUG_FILTER
-#pragma unroll
-          for (int i = 0; i < 32; ++i) dbg_m1 = fmaxf(dbg_m1, __uint_as_float(v[i]));
-#endif
           if (valid < 32) mask &= (1u << valid) - 1u;
           while (mask) {
             const int i = __ffs(mask) - 1;
@@ -614,14 +607,6 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
       sh->red_d[sw][lane] = best_score;
       sh->red_i[sw][lane] = best_i;
       sh->red_l[sw][lane] = best_label;
-#ifdef EF_DEBUG_FILTER
-      {
-        const float mypass0 = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-        if (dbg_m1 != mypass0)
-          printf("DBG blk %d sw %d lane %d pass0 max %.9g pass1 max %.9g thr %.9g total %d ovf %d\n", blockIdx.x, sw, lane,
-                 mypass0, dbg_m1, thr, total, (int)overflow);
-      }
-#endif
       if (probe && stid == 0) probe[12] = globaltimer();
     }
     __syncthreads();
@@ -635,9 +620,6 @@ recognize_cluster_kernel(const __grid_constant__ CUtensorMap tmap_x, const __gri
           bi = sh->red_i[w][lane];
           bl = sh->red_l[w][lane];
         }
-#ifdef EF_DEBUG_FILTER
-      if (bi == INT_MAX) printf("DBG nocand blk %d lane %d list_cnt %d pn %g pe0 %g\n", blockIdx.x, lane, sh->list_cnt, sh->pn[lane], pe[lane]);
-#endif
       if (bi == INT_MAX) { bi = 0; bl = -1; }       // only after a pipeline failure (the status flag is raised below)
       a.out_score[b] = score;
       a.out_index[b] = bi;

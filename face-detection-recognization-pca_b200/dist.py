@@ -149,12 +149,14 @@ def _jacobi(L, stream, H, work):
     return evals, evecs
 
 
-def eigh_topk_device(Cm, k, tol=1e-11, max_outer=60, degree=8, block=None, seed=1234):
+def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=1234):
     """Largest k eigenpairs of a symmetric positive semi-definite CUDA float64 matrix Cm [n, n] that is too large for the
     Jacobi solver (config 4: the 10 000 x 10 000 covariance, k = 256): Chebyshev-filtered subspace iteration with
     Rayleigh-Ritz (Zhou & Saad's scaled filter).  Every dense product is ef_dgemm_device, every small eigenproblem
     (block x block, block <= 320) the cluster-resident Jacobi kernel; torch only allocates and does O(n block) vector work.
     Replaces np.linalg.eigh(cov) + descending sort + top-k of useless/train.py:103-116 for large D.
+    Stops when max_i |C q_i - theta_i q_i| <= tol * theta_1, after max_outer outer iterations, or when the residual
+    stagnates (info["stagnated"]: near-degenerate trailing eigenvalues, e.g. planted factors below the noise floor).
     Returns (evals [k] descending, evecs [n, k] orthonormal columns, info dict)."""
     import torch
     L = _lib.lib()
@@ -176,19 +178,30 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=60, degree=8, block=None, seed=
         G = torch.empty((m, m), **f64)
         _dgemm(L, stream, m, m, n, 1.0, Y, 1, m, Y, m, 1, 0.0, G, m)                # Y^T Y
         g, W = _jacobi(L, stream, G, work)
-        scale = torch.where(g > g[0] * 1e-28, g.clamp_min(1e-300).rsqrt(), torch.zeros_like(g))
+        dead = g <= g[0] * 1e-28                                                    # directions lost to rounding
+        scale = torch.where(dead, torch.zeros_like(g), g.clamp_min(1e-300).rsqrt())
         Ws = (W * scale[:, None]).contiguous()                                      # row i scaled by g_i^-1/2
         Q = torch.empty((n, m), **f64)
         _dgemm(L, stream, n, m, m, 1.0, Y, m, 1, Ws, 1, m, 0.0, Q, m)               # Y Ws^T
+        n_dead = int(dead.sum())
+        if n_dead:
+            # rank loss: fresh random directions keep the block at full rank (zero columns would stay zero for ever);
+            # the caller's second orthonormalisation pass makes them orthogonal to the rest
+            Q[:, dead] = torch.randn((n, n_dead), generator=gen, **f64)
         return Q
+
+    def orth2(Y):
+        """Two passes (the Gram-matrix route squares the condition number; the second pass restores orthonormality to
+        rounding, like CholQR2)."""
+        return orth(orth(Y))
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
-    Q = orth(torch.randn((n, m), generator=gen, **f64))
-    Q = orth(Q)                                                                     # second pass: orthonormal to rounding
+    Q = orth2(torch.randn((n, m), generator=gen, **f64))
     Y = torch.empty((n, m), **f64)
     lam = None
-    info = {"outer": 0, "products": 0, "block": m, "residual": None}
+    info = {"outer": 0, "products": 0, "block": m, "residual": None, "stagnated": False}
+    history = []
     for outer in range(max_outer):
         _dgemm(L, stream, n, m, n, 1.0, Cm, n, 1, Q, m, 1, 0.0, Y, m)               # Y = C Q
         H = torch.empty((m, m), **f64)
@@ -199,10 +212,16 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=60, degree=8, block=None, seed=
         Yr = torch.empty((n, m), **f64)
         _dgemm(L, stream, n, m, m, 1.0, Q, m, 1, W, 1, m, 0.0, Qr, m)               # Ritz vectors Q W^T
         _dgemm(L, stream, n, m, m, 1.0, Y, m, 1, W, 1, m, 0.0, Yr, m)               # C (Q W^T)
-        res = (Yr[:, :k] - Qr[:, :k] * lam[None, :k]).norm(dim=0).max() / lam[0].clamp_min(1e-300)
-        info.update(outer=outer + 1, products=info["products"] + 1, residual=float(res))
+        res = float((Yr[:, :k] - Qr[:, :k] * lam[None, :k]).norm(dim=0).max() / lam[0].clamp_min(1e-300))
+        info.update(outer=outer + 1, products=info["products"] + 1, residual=res)
+        history.append(res)
         Q = Qr
-        if float(res) <= tol or m == n:
+        if res <= tol or m == n:
+            break
+        # stagnation: eigenvalues buried in a flat noise floor (gap << rounding of the products) cannot be resolved any
+        # further; their invariant subspace is already captured to the reported residual
+        if len(history) >= 10 and res > 0.9 * history[-7]:
+            info["stagnated"] = True
             break
         # scaled Chebyshev filter of degree `degree`: damps the unwanted interval [0, beta], beta = smallest Ritz value
         beta, top = float(lam[m - 1]), float(lam[0])
@@ -221,7 +240,7 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=60, degree=8, block=None, seed=
             _dgemm(L, stream, n, m, n, 2.0 * sigma_new / e, Cm, n, 1, Y1, m, 1, 1.0, Y2, m)
             info["products"] += 1
             Qp, Y1, sigma = Y1, Y2, sigma_new
-        Q = orth(Y1)
+        Q = orth2(Y1)
     return lam[:k].clone(), Q[:, :k].contiguous(), info
 
 
@@ -259,7 +278,8 @@ def fit_gen1_sharded(X_local, n_total, n_components, group=None, solver="auto"):
     k = min(int(n_components), D)
     if solver == "subspace" or (solver == "auto" and D > 2048):
         # large D (config 4: 10 000 pixels): only the top k eigenpairs, by filtered subspace iteration
-        evals, E_top, _ = eigh_topk_device(cov, k)
+        evals, E_top, solver_info = eigh_topk_device(cov, k)
+        fit_gen1_sharded.last_solver_info = solver_info
         evecs = None
     else:
         evals = torch.empty(D, dtype=torch.float64, device=dev)
