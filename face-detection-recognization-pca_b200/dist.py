@@ -89,7 +89,7 @@ class ShardedGallery:
     match(features) returns the GLOBAL (score, index) per query, identical on every rank.
     """
 
-    def __init__(self, gallery_shard, index_base, metric=METRIC_COSINE_SK, group=None):
+    def __init__(self, gallery_shard, index_base, metric=METRIC_COSINE_SK, group=None, use_tensor_cores=True):
         import torch
         L = _lib.lib()
         dev = torch.device("cuda", torch.cuda.current_device())
@@ -105,6 +105,14 @@ class ShardedGallery:
             check(L.ef_gallery_prepare_device(g.data_ptr(), self.k, self.n, self.k, metric, self.prepared.data_ptr(),
                                               self.k, self.norms.data_ptr(), stream), "ef_gallery_prepare_device")
         self._L, self._work = L, None
+        # tensor-core filter (cosine metrics, k <= 128): float16 image of this shard, built once
+        self.image = None
+        self.last_flags = None
+        if use_tensor_cores and self.n and metric != METRIC_L2 and self.k <= 128:
+            self.image = torch.empty(int(L.ef_match_tc_image_bytes(self.n, self.k)), dtype=torch.uint8, device=dev)
+            check(L.ef_match_tc_prepare_device(self.prepared.data_ptr(), self.k, self.norms.data_ptr(), self.n, self.k,
+                                               metric, self.image.data_ptr(), stream), "ef_match_tc_prepare_device")
+            self._work_tc = None
 
     def match_local(self, features):
         """Top-1 of the queries against this shard only: (score [B], global index [B]; -1 when the shard is empty)."""
@@ -116,6 +124,24 @@ class ShardedGallery:
         if self.n == 0 or B == 0:
             score.fill_(float("inf") if self.metric == METRIC_L2 else -float("inf"))
             return score, index
+        stream = C.c_void_p(torch.cuda.current_stream(p.device).cuda_stream)
+        if self.image is not None:
+            # filter on tensor cores + exact float64 re-score of the survivors (bit identical to the float64 scan)
+            wb = int(self._L.ef_match_tc_work_bytes(B, self.n, self.k))
+            if self._work_tc is None or self._work_tc.numel() < wb:
+                self._work_tc = torch.empty(wb, dtype=torch.uint8, device=p.device)
+            check(self._L.ef_match_tc_device(p.data_ptr(), p.stride(0), B, self.k, self.prepared.data_ptr(), self.k,
+                                             self.norms.data_ptr(), self.image.data_ptr(), self.n, self.index_base,
+                                             self.metric, score.data_ptr(), index.data_ptr(), self._work_tc.data_ptr(), wb,
+                                             stream), "ef_match_tc_device")
+            flags = (C.c_int32 * 3)()
+            check(self._L.ef_match_tc_flags(self._work_tc.data_ptr(), flags), "ef_match_tc_flags")   # synchronises
+            self.last_flags = {"timeout": flags[0], "candidates": flags[1], "overflow": flags[2]}
+            if flags[0]:
+                raise _lib.EigenfacesError(_lib.EF_ERR_CUDA, "ef_match_tc_device", "tcgen05 pipeline timed out")
+            if not flags[2]:
+                return score, index
+            # degenerate gallery (candidate list overflow): the float64 scan below recomputes everything
         need = int(self._L.ef_match_work_bytes(B, self.n)) + 16
         if self._work is None or self._work.numel() < need:
             self._work = torch.empty(need, dtype=torch.uint8, device=p.device)

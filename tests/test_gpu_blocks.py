@@ -182,3 +182,63 @@ def test_tensor_core_gram_matches_cuda_core_gram_all_255():
     _gram_tc(torch, L, x, N, D, 0, G1)
     ef._lib.check(L.ef_gram_u8_device(x.data_ptr(), D, N, D, 0, D, 0, G2.data_ptr(), _stream(torch)), "gram")
     assert torch.equal(G1, G2) and int(G1[0, 0].item()) == D * 255 * 255
+
+
+@pytest.mark.parametrize("metric", [ef.METRIC_COSINE_SK, ef.METRIC_COSINE_G1])
+@pytest.mark.parametrize("n,k,B", [(30_000, 128, 300), (5000, 24, 77), (1, 7, 3), (257, 1, 129), (70_001, 50, 40)])
+def test_tensor_core_matcher_equals_float64_scan(metric, n, k, B):
+    """ef_match_tc_device (float16 tcgen05 filter + exact re-score) returns bit-identical (score, index) to the float64
+    scan ef_match_device, including duplicates (lowest index), near-duplicates, zero rows and a zero query."""
+    torch = require_gpu()
+    L = ef._lib.lib()
+    rng = np.random.default_rng(n + 31 * k + metric)
+    G = rng.normal(size=(n, k)) / np.arange(1, k + 1)
+    if n > 4200:
+        G[4000] = G[100]; G[n - 1] = G[100]                    # exact duplicates
+        G[200] = G[300] * (1 + 1e-9); G[201] = G[300] + 1e-7 * rng.normal(size=k)   # near duplicates
+        G[400] = 0.0                                            # zero row
+        G[401] = G[402] * 1e6
+    P = G[rng.integers(0, n, B)] + 0.02 * rng.normal(size=(B, k)) / np.arange(1, k + 1)
+    zero_query = B > 2 and n <= 60_000                          # (it ties with every row: n candidates of the 65 536 list)
+    if B > 2:
+        if zero_query:
+            P[1] = 0.0
+        P[2] = G[min(100, n - 1)]
+    g = torch.from_numpy(G).cuda(); p = torch.from_numpy(P).cuda()
+    gp = torch.empty_like(g); gn = torch.empty(n, dtype=torch.float64, device="cuda")
+    ef._lib.check(L.ef_gallery_prepare_device(g.data_ptr(), k, n, k, metric, gp.data_ptr(), k, gn.data_ptr(), _stream(torch)), "prep")
+    # float64 scan
+    s_ref = torch.empty(B, dtype=torch.float64, device="cuda"); i_ref = torch.empty(B, dtype=torch.int64, device="cuda")
+    work = torch.empty(L.ef_match_work_bytes(B, n) + 16, dtype=torch.uint8, device="cuda")
+    ef._lib.check(L.ef_match_device(p.data_ptr(), k, B, k, gp.data_ptr(), k, gn.data_ptr(), n, 1000, metric, s_ref.data_ptr(),
+                                    i_ref.data_ptr(), work.data_ptr(), _stream(torch)), "match")
+    # tensor-core filter + exact re-score
+    img = torch.empty(L.ef_match_tc_image_bytes(n, k), dtype=torch.uint8, device="cuda")
+    ef._lib.check(L.ef_match_tc_prepare_device(gp.data_ptr(), k, gn.data_ptr(), n, k, metric, img.data_ptr(), _stream(torch)), "tc prep")
+    wb = L.ef_match_tc_work_bytes(B, n, k)
+    wtc = torch.empty(wb, dtype=torch.uint8, device="cuda")
+    s_tc = torch.empty(B, dtype=torch.float64, device="cuda"); i_tc = torch.empty(B, dtype=torch.int64, device="cuda")
+    ef._lib.check(L.ef_match_tc_device(p.data_ptr(), k, B, k, gp.data_ptr(), k, gn.data_ptr(), img.data_ptr(), n, 1000, metric,
+                                       s_tc.data_ptr(), i_tc.data_ptr(), wtc.data_ptr(), wb, _stream(torch)), "tc match")
+    flags = (C.c_int32 * 3)()
+    ef._lib.check(L.ef_match_tc_flags(wtc.data_ptr(), flags), "flags")
+    assert flags[0] == 0 and flags[2] == 0, list(flags)
+    assert flags[1] >= B - 1                                    # at least one survivor per (non-degenerate) query
+    assert torch.equal(i_tc, i_ref)
+    assert torch.equal(s_tc, s_ref)
+    # the zero query ties with every row (all cosines are 0), everything else keeps a handful of survivors
+    if k > 1:                                                    # with k = 1 every cosine is +-1: half the gallery ties
+        assert flags[1] < 50 * B + 2000 + (n if zero_query else 0), f"filter too loose: {flags[1]} candidates for {B} queries"
+
+
+def test_tensor_core_matcher_overflow_falls_back():
+    """A gallery of identical rows puts every row inside the band: the candidate list overflows, the flag is raised and
+    ShardedGallery answers from the float64 scan (lowest index wins)."""
+    torch = require_gpu()
+    n, k, B = 300_000, 16, 300
+    G = np.tile(np.linspace(1.0, 2.0, k), (n, 1))
+    P = np.tile(np.linspace(1.0, 2.0, k), (B, 1)) * np.linspace(0.5, 3.0, B)[:, None]
+    sg = ef.dist.ShardedGallery(G, 7, ef.METRIC_COSINE_SK)
+    score, index = sg.match_local(torch.from_numpy(P).cuda())
+    assert sg.last_flags["overflow"] == 1
+    assert torch.all(index == 7) and torch.allclose(score, torch.ones_like(score), atol=1e-12)
