@@ -246,6 +246,58 @@ def fit_and_gram_section(ef, torch, dev, peaks):
                          "roofline": {"bound": "hbm", "achieved": bytes_alg / ms / 1e6, "peak": hbm, "unit": "GB/s",
                                       "frac": bytes_alg / ms / 1e6 / hbm,
                                       "note": "algorithmic bytes = ROI pixels read once + 10 000 B written per crop"}}
+    del frames, boxes, outp
+    # config 3 on one GPU: 1 M gallery identities x k = 128, 4096 queries, tensor-core filter + exact float64 re-score
+    gen = torch.Generator(device=dev); gen.manual_seed(1_000_003)
+    n3, k3 = 1_000_000, 128
+    lam3 = torch.arange(1, k3 + 1, device=dev, dtype=torch.float64) ** -2.0
+    G3 = torch.randn((n3, k3), generator=gen, device=dev, dtype=torch.float64) * lam3.sqrt()
+    truth = torch.randint(0, n3, (4096,), generator=gen, device=dev)
+    P3 = G3[truth] + 0.05 * torch.randn((4096, k3), generator=gen, device=dev, dtype=torch.float64) * lam3.sqrt()
+    sg = ef.dist.ShardedGallery(G3, 0, ef.METRIC_COSINE_SK)
+    for _ in range(2):
+        sg.match_local(P3)
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(5):
+        s3, i3 = sg.match_local(P3)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    sg64 = ef.dist.ShardedGallery(G3, 0, ef.METRIC_COSINE_SK, use_tensor_cores=False)
+    sg64.match_local(P3[:64]); torch.cuda.synchronize()
+    e0.record(); s64, i64 = sg64.match_local(P3[:64]); e1.record(); torch.cuda.synchronize()
+    ms64 = e0.elapsed_time(e1) * 4096 / 64
+    f16_flops = 2.0 * 2 * 4096 * n3 * 384
+    bf16_peak = peaks.get("bf16_tflops", 1590.0)
+    out["large_gallery"] = {
+        "what": "config 3 on one GPU: 4096 queries x 1 000 000 gallery rows x k = 128, cosine top-1 (ef_match_tc_device: "
+                "tcgen05 f16 hi/lo filter GEMM, two passes, + exact float64 re-score of the survivors)",
+        "ms_per_batch": ms, "queries_per_s": 4096 / ms * 1e3, "candidates_rescored": sg.last_flags["candidates"],
+        "top1_accuracy_vs_planted": float((i3 == truth).double().mean()),
+        "bit_identical_to_float64_scan_on_64_queries": bool(torch.equal(i64, i3[:64]) and torch.equal(s64, s3[:64])),
+        "float64_scan_ms_per_batch_extrapolated": ms64,
+        "roofline": {"bound": "tensor", "achieved": f16_flops / ms / 1e9, "peak": bf16_peak, "unit": "TFLOP/s (f16 filter GEMM, both passes)",
+                     "frac": f16_flops / ms / 1e9 / bf16_peak}}
+    del G3, P3, sg, sg64
+    # config 4 shape on one GPU (N reduced to 25 000 rows to bound the run): tensor-core Gram, exact centring,
+    # Chebyshev-filtered subspace iteration for the top 256 eigenpairs of the 10 000 x 10 000 covariance, projection
+    N4, D4, R4, K4 = 25_000, 10_000, 300, 256
+    gen.manual_seed(4242)
+    F4 = torch.linalg.qr(torch.randn((D4, R4), generator=gen, device=dev, dtype=torch.float32))[0]
+    sig4 = 40.0 * torch.arange(1, R4 + 1, device=dev, dtype=torch.float32) ** -0.7
+    X4 = torch.empty((N4, D4), dtype=torch.uint8, device=dev)
+    for i in range(0, N4, 5000):
+        L4 = torch.randn((5000, R4), generator=gen, device=dev) * sig4
+        X4[i:i + 5000] = (128 + L4 @ F4.T + 4.0 * torch.randn((5000, D4), generator=gen, device=dev)).round_().clamp_(0, 255).to(torch.uint8)
+    ef.dist.fit_gen1_sharded(X4, N4, K4); torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    E4, _, _, ev4 = ef.dist.fit_gen1_sharded(X4, N4, K4)
+    torch.cuda.synchronize()
+    info4 = dict(ef.dist.fit_gen1_sharded.last_solver_info)
+    out["fit_large"] = {"what": f"config 4 shape, one GPU: manual_pca covariance branch on u8[{N4},{D4}], k = {K4} "
+                                "(tensor-core Gram + integer centring + filtered subspace iteration + projection)",
+                        "seconds": time.perf_counter() - t0, "solver": info4,
+                        "orthonormality_error": float((E4.T @ E4 - torch.eye(K4, device=dev, dtype=torch.float64)).abs().max())}
     return out
 
 
