@@ -276,7 +276,8 @@ class MultiModelFaceScanner:
         """All detections of a frame (or clip) against every loaded model; keeps the best confidence per detection
         with the reference's rules (strict >, first model wins ties, below-threshold name falls back to the model's
         person; scan-template-v4.py:297-319).  boxes None = the whole image is one crop."""
-        frames = np.asarray(frames)
+        import torch
+        frames = np.ascontiguousarray(frames)
         if boxes is None:
             h, w = frames.shape[:2]
             boxes = [[0, 0, w, h]]
@@ -284,20 +285,32 @@ class MultiModelFaceScanner:
         best_conf = np.zeros(B)
         best_id = np.full(B, -1, dtype=np.int64)
         best_name = np.array(["unknown"] * B, dtype=object)
+        if B == 0:
+            return [], [], []
+        # K1 once for all models (every model of the reference uses the same 64 x 64 gray crop, scan-template-v4.py:262):
+        # frames and boxes go up once, the preprocessed crops stay on the device and feed every model's K2
+        if frames.ndim == 2 or (frames.ndim == 3 and frames.shape[2] == 3):
+            frames = frames[None]
+        bx = np.asarray(boxes, dtype=np.int32).reshape(B, -1)
+        if bx.shape[1] == 4:
+            bx = np.concatenate([np.zeros((B, 1), np.int32), bx], axis=1)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        crops = engine.preprocess_device(torch.from_numpy(frames).to(dev), torch.from_numpy(np.ascontiguousarray(bx)).to(dev), 64)
         for person_name, info in self.models.items():
             model_data = info['model_data']
             if model_data is None:
                 continue
             try:
                 rec = recognizer_for(model_data)
-                res = rec.recognize_boxes(frames, boxes, 64, threshold, want_features=False, want_residual=False)
+                out = rec.recognize_device(crops, threshold, want_residual=False)
+                score, label = out["score"].cpu().numpy(), out["label"].cpu().numpy()
             except Exception as e:
                 print(f"Error recognizing with model {person_name}: {e}")
                 continue
-            names = _names_for(res.label, model_data)
-            better = res.score > best_conf
-            best_conf = np.where(better, res.score, best_conf)
-            best_id = np.where(better, res.label, best_id)
+            names = _names_for(label, model_data)
+            better = score > best_conf
+            best_conf = np.where(better, score, best_conf)
+            best_id = np.where(better, label, best_id)
             best_name = np.where(better, np.where(names == "unknown", person_name, names), best_name)
         return best_id.tolist(), best_name.tolist(), best_conf.tolist()
 
