@@ -42,7 +42,9 @@ struct ef_model {
     int32_t* label = nullptr;
     double threshold = 0.0;
     int slot = 0;
+    cudaStream_t stream = nullptr;                    // the stream the pending batch was submitted on
   } pending;
+  cudaEvent_t flush_ev = nullptr;
   void* pinned = nullptr;                             // owned page-locked staging for the results of the host path
   size_t pinned_bytes = 0;
   cudaStream_t copy_stream = nullptr;                 // owned: chunked H2D of the host path runs ahead of the kernels
@@ -232,6 +234,7 @@ void ef_model_destroy(ef_model_t* m) {
   if (m->stream) cudaStreamDestroy(m->stream);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->pinned) cudaFreeHost(m->pinned);
+  if (m->flush_ev) cudaEventDestroy(m->flush_ev);
   for (cudaEvent_t e : m->chunk_ev) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_a) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_b) cudaEventDestroy(e);
@@ -422,6 +425,7 @@ static int pipe_launch(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, 
       m->n_gallery, labels, m->metric, m->status.as<int>(), st));
   m->pending.B = B;
   m->pending.slot = slot;
+  m->pending.stream = st;
   if (B > 0) {
     m->pending.score = out->score;
     m->pending.index = out->index;
@@ -442,13 +446,23 @@ int ef_model_submit_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t
   if (m->tc_mode < 2 || !aligned || !m->gimg.p || !ef::pipe_supported(m->k, m->NC, m->metric, m->n_gallery))
     return ef_model_recognize_device(m, x, ldx, B, threshold, out, stream);    // not pipelined: results right away
   EF_TRY(ef_model_reserve(m, B));
+  if (m->pending.B > 0 && m->pending.stream != ef::as_stream(stream)) EF_TRY(ef_model_flush_device(m, stream));
   return pipe_launch(m, x, ldx, B, threshold, out, ef::as_stream(stream));
 }
 
 int ef_model_flush_device(ef_model_t* m, ef_stream_t stream) {
   if (!m) return EF_ERR_INVALID;
   if (m->pending.B <= 0) return EF_OK;
-  return pipe_launch(m, nullptr, 0, 0, 0.0, nullptr, ef::as_stream(stream));
+  // The matching launch reads the rows carried by the submit launch, so it runs on the stream of that submit; when the
+  // caller flushes from another stream (e.g. a host-buffer call on the model's own stream), that stream is made to wait.
+  cudaStream_t want = ef::as_stream(stream), owner = m->pending.stream;
+  EF_TRY(pipe_launch(m, nullptr, 0, 0, 0.0, nullptr, owner));
+  if (want != owner) {
+    if (!m->flush_ev) EF_CUDA(cudaEventCreateWithFlags(&m->flush_ev, cudaEventDisableTiming));
+    EF_CUDA(cudaEventRecord(m->flush_ev, owner));
+    EF_CUDA(cudaStreamWaitEvent(want, m->flush_ev, 0));
+  }
+  return EF_OK;
 }
 
 int ef_model_status(ef_model_t* m, int32_t* tc_pipeline_timeouts) {

@@ -175,7 +175,7 @@ def _jacobi(L, stream, H, work):
     return evals, evecs
 
 
-def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=1234):
+def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=1234, group=None):
     """Largest k eigenpairs of a symmetric positive semi-definite CUDA float64 matrix Cm [n, n] that is too large for the
     Jacobi solver (config 4: the 10 000 x 10 000 covariance, k = 256): Chebyshev-filtered subspace iteration with
     Rayleigh-Ritz (Zhou & Saad's scaled filter).  Every dense product is ef_dgemm_device, every small eigenproblem
@@ -183,17 +183,41 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=
     Replaces np.linalg.eigh(cov) + descending sort + top-k of useless/train.py:103-116 for large D.
     Stops when max_i |C q_i - theta_i q_i| <= tol * theta_1, after max_outer outer iterations, or when the residual
     stagnates (info["stagnated"]: near-degenerate trailing eigenvalues, e.g. planted factors below the noise floor).
+    With a process group the dominant cost -- the n x n by n x block covariance products -- is SHARDED: rank r multiplies
+    its contiguous block of rows of C and one all-gather (n x block float64 over NVLink) reassembles the product; every
+    element is computed by the same kernel with the same summation order whoever owns its row, so all ranks hold
+    bit-identical iterates (and the same result as a single GPU).  The block x block work stays replicated.
     Returns (evals [k] descending, evecs [n, k] orthonormal columns, info dict)."""
     import torch
     L = _lib.lib()
     dev = Cm.device
     n = int(Cm.shape[0])
+    world, rank = _world(group)
+    rows_per = -(-n // world)
+    lo, hi = min(n, rank * rows_per), min(n, (rank + 1) * rows_per)
     k = int(k)
     m = int(block) if block else min(n, max(k + 32, k + k // 8))
     m = min(m, n)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     work = torch.empty(int(L.ef_eigh_work_bytes(m)), dtype=torch.uint8, device=dev)
     f64 = dict(dtype=torch.float64, device=dev)
+
+    gather_buf = torch.empty((world * rows_per, m), **f64) if world > 1 else None
+
+    def cprod(alpha, Yin, beta, Yout):
+        """Yout = alpha * C Yin + beta * Yout, rows of C sharded over the group."""
+        if world == 1:
+            _dgemm(L, stream, n, m, n, alpha, Cm, n, 1, Yin, m, 1, beta, Yout, m)
+            return
+        import torch.distributed as dist
+        if hi > lo:
+            _dgemm(L, stream, hi - lo, m, n, alpha, Cm[lo:hi], n, 1, Yin, m, 1, beta, Yout[lo:hi], m)
+        mine = gather_buf[rank * rows_per:(rank + 1) * rows_per]
+        mine.zero_()
+        mine[:hi - lo].copy_(Yout[lo:hi])
+        dist.all_gather_into_tensor(gather_buf.view(-1), mine.reshape(-1).clone(), group=group)
+        Yout.copy_(gather_buf[:n])
+        info["allgathers"] = info.get("allgathers", 0) + 1
 
     def orth(Y):
         """Orthonormal basis of span(Y): G = Y^T Y = W^T diag(g) W, Q = Y W^T diag(g^-1/2).  The columns are brought
@@ -229,7 +253,7 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=
     info = {"outer": 0, "products": 0, "block": m, "residual": None, "stagnated": False}
     history = []
     for outer in range(max_outer):
-        _dgemm(L, stream, n, m, n, 1.0, Cm, n, 1, Q, m, 1, 0.0, Y, m)               # Y = C Q
+        cprod(1.0, Q, 0.0, Y)                                                       # Y = C Q
         H = torch.empty((m, m), **f64)
         _dgemm(L, stream, m, m, n, 1.0, Q, 1, m, Y, m, 1, 0.0, H, m)                # H = Q^T C Q
         H = ((H + H.T) * 0.5).contiguous()
@@ -263,7 +287,7 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=
             sigma_new = 1.0 / (2.0 / sigma1 - sigma)
             Y2 = (Qp * (-sigma * sigma_new)).contiguous()
             Y2.sub_(Y1 * (2.0 * sigma_new * c / e))
-            _dgemm(L, stream, n, m, n, 2.0 * sigma_new / e, Cm, n, 1, Y1, m, 1, 1.0, Y2, m)
+            cprod(2.0 * sigma_new / e, Y1, 1.0, Y2)
             info["products"] += 1
             Qp, Y1, sigma = Y1, Y2, sigma_new
         Q = orth2(Y1)
@@ -304,7 +328,7 @@ def fit_gen1_sharded(X_local, n_total, n_components, group=None, solver="auto"):
     k = min(int(n_components), D)
     if solver == "subspace" or (solver == "auto" and D > 2048):
         # large D (config 4: 10 000 pixels): only the top k eigenpairs, by filtered subspace iteration
-        evals, E_top, solver_info = eigh_topk_device(cov, k)
+        evals, E_top, solver_info = eigh_topk_device(cov, k, group=group)
         fit_gen1_sharded.last_solver_info = solver_info
         evecs = None
     else:

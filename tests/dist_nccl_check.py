@@ -52,6 +52,17 @@ def main():
     sign = np.sign(np.sum(E.cpu().numpy() * E1, axis=0))
     np.testing.assert_allclose(E.cpu().numpy() * sign, E1, atol=1e-8)
     np.testing.assert_allclose(proj.cpu().numpy() * sign, proj1[lo:hi], atol=1e-6)
+    # ---- subspace solver with the covariance products sharded over the ranks: bit identical to the unsharded solve
+    solo = [dist.new_group([r]) for r in range(world)][rank]      # every rank creates every group, keeps its own
+    Mx = rng.normal(size=(900, 900)); Cm = torch.from_numpy(Mx @ Mx.T / 900 + np.diag(np.linspace(50, 0, 900))).to(dev)
+    lam_s, Q_s, info_s = ef.dist.eigh_topk_device(Cm, 20)                       # sharded over the default group
+    lam_1, Q_1, info_1 = ef.dist.eigh_topk_device(Cm, 20, group=solo)           # same solve on one rank
+    assert info_s.get("allgathers", 0) > 0 and "allgathers" not in info_1
+    assert torch.equal(lam_s, lam_1) and torch.equal(Q_s, Q_1), "sharded covariance products changed the iterates"
+    w_ref = np.linalg.eigvalsh(Cm.cpu().numpy())[::-1][:20]
+    np.testing.assert_allclose(lam_s.cpu().numpy(), w_ref, rtol=1e-9)
+    Es, means, projs, evs = ef.dist.fit_gen1_sharded(torch.from_numpy(X[lo:hi]).to(dev), N, kk, solver="subspace")
+    np.testing.assert_allclose(evs.cpu().numpy(), ev1, rtol=1e-9)
     gathered = [torch.empty_like(ev) for _ in range(world)]
     dist.all_gather(gathered, ev)
     assert all(torch.equal(g, ev) for g in gathered), "eigenvalues must be bit identical on every rank"

@@ -366,6 +366,12 @@ def test_pipelined_submission_is_bit_identical(metric, light_model, golden):
     for f in ("score", "index", "label"):
         assert torch.equal(o1[f], want[0][f]) and torch.equal(mid[f], want[1][f]), f
     rec.flush_device()                                            # nothing pending: no-op
+    # a host-buffer call (the model's own stream) while a batch is pending on torch's stream: ordered and correct
+    o2 = rec.submit_device(batches[2], 0.8)
+    host = rec.recognize(batches[3][:, :10000].cpu().numpy(), 0.8)
+    torch.cuda.synchronize()
+    assert torch.equal(o2["index"], want[2]["index"]) and torch.equal(o2["score"], want[2]["score"])
+    assert np.array_equal(host.index, want[3]["index"].cpu().numpy())
     # shapes outside the pipelined kernel fall back to the immediate path
     rec50 = ef.gen1.recognizer_for(light_model)                    # k = 50
     o50 = rec50.submit_device(batches[0], 0.8)
