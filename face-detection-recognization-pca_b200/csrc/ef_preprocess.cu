@@ -14,6 +14,9 @@
 //   a = rint(f * 2048) (float32, half-even); H = s0 * a0 + s1 * a1
 //   out = (((b0 * (H0 >> 4)) >> 16) + ((b1 * (H1 >> 4)) >> 16) + 2) >> 2
 //   src == 2 dst on both axes -> 2x2 box (a + b + c + d + 2) >> 2 ; src == dst -> copy
+#include <algorithm>
+#include <cstdlib>
+
 #include "ef_common.cuh"
 
 namespace {
@@ -52,7 +55,8 @@ __device__ __forceinline__ void axis_coeff(int d, int src, double scale, bool cl
 __global__ void __launch_bounds__(kThreads)
 preprocess_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int pitch, int width, int height,
                   int channels, int n_frames, const ef_box_t* __restrict__ boxes, int n_boxes, int dw, int dh,
-                  uint8_t* __restrict__ out, int64_t out_stride, int* __restrict__ bad_boxes, int stage_bytes) {
+                  uint8_t* __restrict__ out, int64_t out_stride, int* __restrict__ bad_boxes, int stage_bytes,
+                  unsigned int* __restrict__ next_box) {
   extern __shared__ __align__(16) int tab[];
   __shared__ double scales[2];
   int* xs0 = tab;
@@ -67,7 +71,14 @@ preprocess_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int 
   const int tid = threadIdx.x;
   const int npix = dw * dh;
 
-  for (int b = blockIdx.x; b < n_boxes; b += gridDim.x) {
+  // dynamic schedule: crops differ in size by up to 9x, so every CTA takes the next unprocessed box when it is free
+  __shared__ int next_s;
+  for (;;) {
+    __syncthreads();                                 // previous crop finished with the tables / staging / next_s
+    if (tid == 0) next_s = (int)atomicAdd(next_box, 1u);
+    __syncthreads();
+    const int b = next_s;
+    if (b >= n_boxes) break;
     const ef_box_t box = boxes[b];
     uint8_t* __restrict__ o = out + (int64_t)b * out_stride;
     const bool ok = box.frame >= 0 && box.frame < n_frames && box.w > 0 && box.h > 0 && box.x >= 0 && box.y >= 0 &&
@@ -246,7 +257,8 @@ extern "C" int ef_preprocess(const uint8_t* frames, int64_t frame_stride, int32_
   if (dw > kMaxSide || dh > kMaxSide) return EF_ERR_UNSUPPORTED;
   if (n_boxes == 0) return EF_OK;
   // coefficient tables + a 64 KB staging buffer for the source rows of a band: three CTAs per SM
-  constexpr int kStageBytes = 64 * 1024;
+  int kStageBytes = 64 * 1024;                      // three CTAs per SM; a 250 x 250 ROI fits one band
+  if (const char* e = getenv("EF_PRE_STAGE_KB")) { const int v = atoi(e); if (v >= 8 && v <= 96) kStageBytes = v * 1024; }
   const size_t tables = sizeof(int) * (4 * (size_t)(dw + dh) + 4);
   const size_t smem = tables + kStageBytes;
   static bool configured = false;
@@ -254,9 +266,20 @@ extern "C" int ef_preprocess(const uint8_t* frames, int64_t frame_stride, int32_
     EF_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     configured = true;
   }
-  const int64_t resident = (int64_t)ef::sm_count() * 3;
+  const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>(8, (220 * 1024) / (int64_t)(smem + 1024)));
+  const int64_t resident = (int64_t)ef::sm_count() * per_sm;
   const int grid = (int)(n_boxes < resident ? n_boxes : resident);
+  // work counter of this launch: one of 256 slots of a device array owned by the library (concurrent launches on other
+  // streams take other slots), zeroed on the launching stream
+  static unsigned int* counters_of[64] = {nullptr};
+  static std::atomic<unsigned int> next_slot{0};
+  int dev = 0;
+  EF_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return EF_ERR_UNSUPPORTED;
+  if (!counters_of[dev]) EF_CUDA(cudaMalloc(&counters_of[dev], 256 * sizeof(unsigned int)));
+  unsigned int* counter = counters_of[dev] + (next_slot.fetch_add(1) & 255u);
+  EF_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), ef::as_stream(stream)));
   EF_LAUNCH(preprocess_kernel, grid, kThreads, smem, ef::as_stream(stream), frames, frame_stride, pitch, width,
-            height, channels, n_frames, boxes, n_boxes, dw, dh, out, out_stride, bad_boxes, kStageBytes);
+            height, channels, n_frames, boxes, n_boxes, dw, dh, out, out_stride, bad_boxes, kStageBytes, counter);
   return EF_OK;
 }
