@@ -96,6 +96,100 @@ dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, in
   }
 }
 
+// Large products (the covariance x block products of the subspace solver, back-projection at scale): 128 x 128 tile,
+// 8 x 8 outputs per thread -- one shared-memory read per four DFMAs instead of one per two.  Every output still
+// accumulates its K terms in ascending order with one fma each, so the result is bit identical to dgemm_kernel.
+template <int RJ>
+__global__ void __launch_bounds__(256, 1)
+dgemm_big_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int64_t sam, int64_t sak,
+                 const double* __restrict__ Bm, int64_t sbk, int64_t sbn, double beta, double* __restrict__ C,
+                 int64_t ldc) {
+  constexpr int TM = 128, TN = 16 * RJ, KC = 8, R = 8;
+  constexpr int LA = TM * KC / 256, LB = (TN * KC + 255) / 256;     // elements per thread and chunk
+  __shared__ double As[KC][TM + 2];
+  __shared__ double Bs[KC][TN + 2];
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  double acc[R][RJ];
+#pragma unroll
+  for (int i = 0; i < R; ++i)
+#pragma unroll
+    for (int j = 0; j < RJ; ++j) acc[i][j] = 0.0;
+  const bool a_k_contig = (sak == 1);
+  const bool b_n_contig = (sbn == 1);
+  double ra[LA], rb[LB];
+  // the next K chunk is fetched into registers while the current one is multiplied (one memory latency per chunk
+  // would otherwise be exposed: there is a single CTA of 8 warps per SM)
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int l = 0; l < LA; ++l) {
+      const int e = l * 256 + tid;
+      int mm, kk;
+      if (a_k_contig) { mm = e / KC; kk = e % KC; } else { mm = e % TM; kk = e / TM; }
+      const int m = m0 + mm, k = k0 + kk;
+      ra[l] = (m < M && k < K) ? A[(int64_t)m * sam + (int64_t)k * sak] : 0.0;
+    }
+#pragma unroll
+    for (int l = 0; l < LB; ++l) {
+      const int e = l * 256 + tid;
+      int nn, kk;
+      if (b_n_contig) { nn = e % TN; kk = e / TN; } else { nn = e / KC; kk = e % KC; }
+      const int n = n0 + nn, k = k0 + kk;
+      rb[l] = (e < TN * KC && n < N && k < K) ? Bm[(int64_t)k * sbk + (int64_t)n * sbn] : 0.0;
+    }
+  };
+  auto stash = [&]() {
+#pragma unroll
+    for (int l = 0; l < LA; ++l) {
+      const int e = l * 256 + tid;
+      int mm, kk;
+      if (a_k_contig) { mm = e / KC; kk = e % KC; } else { mm = e % TM; kk = e / TM; }
+      As[kk][mm] = ra[l];
+    }
+#pragma unroll
+    for (int l = 0; l < LB; ++l) {
+      const int e = l * 256 + tid;
+      int nn, kk;
+      if (b_n_contig) { nn = e % TN; kk = e / TN; } else { nn = e / KC; kk = e % KC; }
+      if (e < TN * KC) Bs[kk][nn] = rb[l];
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < K; k0 += KC) {
+    stash();
+    __syncthreads();
+    if (k0 + KC < K) fetch(k0 + KC);
+#pragma unroll
+    for (int kk = 0; kk < KC; ++kk) {
+      double av[R], bv[RJ];
+      // rows ty + 16 i, columns tx + 16 j: consecutive lanes read consecutive shared-memory words (no bank conflicts)
+#pragma unroll
+      for (int i = 0; i < R; ++i) av[i] = As[kk][ty + 16 * i];
+#pragma unroll
+      for (int j = 0; j < RJ; ++j) bv[j] = Bs[kk][tx + 16 * j];
+#pragma unroll
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < RJ; ++j) acc[i][j] = fma(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < R; ++i) {
+    const int m = m0 + ty + 16 * i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < RJ; ++j) {
+      const int n = n0 + tx + 16 * j;
+      if (n >= N) continue;
+      double v = alpha * acc[i][j];
+      if (beta != 0.0) v += beta * C[(int64_t)m * ldc + n];
+      C[(int64_t)m * ldc + n] = v;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------- Jacobi
 // One-sided (Hestenes) Jacobi on the symmetric matrix A: the rows of Bt start as the columns of A, the rows of
 // Vt as the identity; plane rotations applied to row pairs of both drive the rows of Bt = (A V)^T to mutual
@@ -689,8 +783,19 @@ int ef_dgemm_device(int32_t M, int32_t N, int32_t K, double alpha, const double*
   if (!A || !B || !C || M < 0 || N < 0 || K < 0 || ldc < N) return EF_ERR_INVALID;
   if (M == 0 || N == 0) return EF_OK;
   cudaStream_t st = ef::as_stream(stream);
+  const int64_t tiles128 = ef::ceil_div(M, 128) * ef::ceil_div(N, 128);
   const int64_t tiles64 = ef::ceil_div(M, 64) * ef::ceil_div(N, 64);
-  if (tiles64 >= ef::sm_count()) {
+  if (tiles128 >= ef::sm_count() && K >= 64) {
+    // 128 x 128 or 128 x 96 tiles, whichever wastes fewer columns (N = 288 = 3 x 96)
+    const int64_t waste128 = ef::round_up(N, 128) - N, waste96 = ef::round_up(N, 96) - N;
+    if (waste96 < waste128) {
+      dim3 grid((unsigned)ef::ceil_div(N, 96), (unsigned)ef::ceil_div(M, 128));
+      EF_LAUNCH(dgemm_big_kernel<6>, grid, 256, 0, st, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc);
+    } else {
+      dim3 grid((unsigned)ef::ceil_div(N, 128), (unsigned)ef::ceil_div(M, 128));
+      EF_LAUNCH(dgemm_big_kernel<8>, grid, 256, 0, st, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc);
+    }
+  } else if (tiles64 >= ef::sm_count()) {
     dim3 grid((unsigned)ef::ceil_div(N, 64), (unsigned)ef::ceil_div(M, 64));
     EF_LAUNCH(dgemm_kernel<64>, grid, 256, 0, st, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, C, ldc);
   } else {
