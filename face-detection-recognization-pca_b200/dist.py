@@ -241,17 +241,17 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=
         return Q
 
     def orth2(Y):
-        """Two passes (the Gram-matrix route squares the condition number; the second pass restores orthonormality to
-        rounding, like CholQR2)."""
+        """Two passes: the Gram-matrix route squares the condition number, the second pass (like CholQR2) restores
+        orthonormality to rounding -- one pass leaves ~1e-9, which would floor the Ritz residual above the tolerance."""
         return orth(orth(Y))
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
+    info = {"outer": 0, "products": 0, "block": m, "residual": None, "stagnated": False}
+    history = []
     Q = orth2(torch.randn((n, m), generator=gen, **f64))
     Y = torch.empty((n, m), **f64)
     lam = None
-    info = {"outer": 0, "products": 0, "block": m, "residual": None, "stagnated": False}
-    history = []
     for outer in range(max_outer):
         cprod(1.0, Q, 0.0, Y)                                                       # Y = C Q
         H = torch.empty((m, m), **f64)
