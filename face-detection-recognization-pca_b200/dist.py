@@ -196,7 +196,7 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=
     rows_per = -(-n // world)
     lo, hi = min(n, rank * rows_per), min(n, (rank + 1) * rows_per)
     k = int(k)
-    m = int(block) if block else min(n, max(k + 32, k + k // 8))
+    m = int(block) if block else min(n, k + max(32, k // 4))      # k = 256 -> 320: the cluster Jacobi's largest size
     m = min(m, n)
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     work = torch.empty(int(L.ef_eigh_work_bytes(m)), dtype=torch.uint8, device=dev)
