@@ -27,13 +27,18 @@ constexpr int kSmemBudget = 200 * 1024;
 // P[b][c] = 2^e_c * sum_s acc[s*kq + c][b] * 2^-(7s+6) - bias[c]; small planes first, then clear the planes.
 __device__ __forceinline__ double combine_planes(int32_t* __restrict__ acc_t, int ld_acc, int b, int c, int kq, int S,
                                                  int exp_c) {
+  // loads first, clearing stores afterwards (a store behind an in-flight load of the same address stalls the pipeline)
+  int32_t plane[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) plane[s] = s < S ? __ldcg(acc_t + (size_t)(s * kq + c) * ld_acc + b) : 0;
+#pragma unroll
+  for (int s = 0; s < 8; ++s)
+    if (s < S) __stcg(acc_t + (size_t)(s * kq + c) * ld_acc + b, 0);
   double v = 0.0;
-  for (int s = S - 1; s >= 0; --s) {
-    int32_t* p = acc_t + (size_t)(s * kq + c) * ld_acc + b;
+#pragma unroll
+  for (int s = 7; s >= 0; --s)
     // exact: |acc| < 2^31 and the scale is a power of two
-    v += (double)*p * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
-    *p = 0;
-  }
+    if (s < S) v += (double)plane[s] * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
   return ldexp(v, exp_c);
 }
 
@@ -207,36 +212,73 @@ fused_epilogue_kernel(const EpiArgs a) {
   }
 }
 
-// Any k: features (+ residual) to global memory.
+// Any k: features (+ residual) to global memory, two kernels.
+//   finalize_combine_kernel  one thread per (crop, column): the S plane loads of a column are independent and in flight
+//                            together (crop index fastest: coalesced), the planes are cleared, the 32 x 32 tile of
+//                            features is transposed through shared memory so that the feature rows are written
+//                            coalesced; the residual column x.u goes to resid2 as a temporary
+//   finalize_resid_kernel    one warp per crop: |p|^2 with a fixed summation order, then the reconstruction error
 __global__ void __launch_bounds__(256)
-finalize_kernel(int32_t* __restrict__ acc_t, int ld_acc, int B, int k, int kq, int S,
-                const int32_t* __restrict__ col_exp, const double* __restrict__ bias, double* __restrict__ proj,
-                int64_t ldp, double* __restrict__ sumsq, double c0, double* __restrict__ resid2) {
-  constexpr int W = 8;
-  __shared__ double n2_s[W][QB], xu_s[QB];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x * QB + lane;
-  const bool live = b < B;
-  if (warp == 0) xu_s[lane] = 0.0;
-  __syncthreads();
-  double n2 = 0.0;
-  for (int c = warp; c < kq; c += W) {
-    if (!live) continue;
-    double v = combine_planes(acc_t, ld_acc, b, c, kq, S, col_exp[c]);
-    if (c < k) {
-      v -= bias[c];
-      proj[(size_t)b * ldp + c] = v;
-      n2 = fma(v, v, n2);
-    } else {
-      xu_s[lane] = v;
-    }
+finalize_combine_kernel(int32_t* __restrict__ acc_t, int ld_acc, int B, int k, int kq, int S,
+                        const int32_t* __restrict__ col_exp, const double* __restrict__ bias, double* __restrict__ proj,
+                        int64_t ldp, double* __restrict__ xu_out) {
+  __shared__ double tile[32][33];
+  const int lane = threadIdx.x & 31, wy = threadIdx.x >> 5;          // 32 crops x 8 column phases
+  const int b = blockIdx.x * 32 + lane;
+  const int c_base = blockIdx.y * 32;
+  // all plane loads of this thread first, the clearing stores afterwards: a store to an address whose load is still in
+  // flight stalls the memory pipeline behind it (load latency x planes instead of one latency)
+  int32_t plane[4][8];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int c = c_base + wy + 8 * it;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      plane[it][s] = (b < B && c < kq && s < S) ? __ldcg(acc_t + (size_t)(s * kq + c) * ld_acc + b) : 0;
   }
-  n2_s[warp][lane] = n2;
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int c = c_base + wy + 8 * it;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      if (b < B && c < kq && s < S) __stcg(acc_t + (size_t)(s * kq + c) * ld_acc + b, 0);
+  }
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int cy = wy + 8 * it;
+    const int c = c_base + cy;
+    double v = 0.0;
+    if (b < B && c < kq) {
+#pragma unroll
+      for (int s = 7; s >= 0; --s)                                     // small planes first, like combine_planes
+        if (s < S) v += (double)plane[it][s] * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
+      v = ldexp(v, col_exp[c]);
+      if (c < k) v -= bias[c];
+      else if (xu_out) xu_out[b] = v;                                  // the residual column x . u~
+    }
+    tile[cy][lane] = v;
+  }
   __syncthreads();
-  if (warp == 0 && live && resid2) {
-    double t = 0.0;
-    for (int w = 0; w < W; ++w) t += n2_s[w][lane];
-    const double r = sumsq[b] - 2.0 * xu_s[lane] + c0 - t;
+  for (int by = wy; by < 32; by += 8) {
+    const int bb = blockIdx.x * 32 + by, c = c_base + lane;
+    if (bb < B && c < k) proj[(size_t)bb * ldp + c] = tile[lane][by];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+finalize_resid_kernel(const double* __restrict__ proj, int64_t ldp, int B, int k, double* __restrict__ sumsq, double c0,
+                      double* __restrict__ resid2) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (b >= B) return;
+  double n2 = 0.0;
+  for (int c = lane; c < k; c += 32) {
+    const double v = proj[(size_t)b * ldp + c];
+    n2 = fma(v, v, n2);
+  }
+  n2 = ef::warp_sum(n2);
+  if (lane == 0) {
+    const double r = sumsq[b] - 2.0 * resid2[b] + c0 - n2;            // resid2[b] holds x . u~ from the combine kernel
     resid2[b] = r > 0.0 ? r : 0.0;
     sumsq[b] = 0.0;
   }
@@ -306,8 +348,13 @@ int project_finalize(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, co
                      const double* bias, double* proj, int64_t ldp, double* sumsq, double c0, double* resid2,
                      cudaStream_t stream) {
   if (B <= 0) return EF_OK;
-  EF_LAUNCH(finalize_kernel, (unsigned)ceil_div(B, QB), 256, 0, stream, acc_t, ld_acc, B, k, kq, S, col_exp, bias,
-            proj, ldp, sumsq, c0, resid2);
+  if (S > 8) return EF_ERR_INVALID;
+  dim3 grid((unsigned)ceil_div(B, 32), (unsigned)ceil_div(kq, 32));
+  EF_LAUNCH(finalize_combine_kernel, grid, 256, 0, stream, acc_t, ld_acc, B, k, kq, S, col_exp, bias, proj, ldp,
+            (kq > k) ? resid2 : nullptr);
+  if (resid2)
+    EF_LAUNCH(finalize_resid_kernel, (unsigned)ceil_div((int64_t)B * 32, 256), 256, 0, stream, proj, ldp, B, k, sumsq,
+              c0, resid2);
   return EF_OK;
 }
 

@@ -287,14 +287,14 @@ int ef_model_reserve(ef_model_t* m, int32_t max_batch) {
   if (!m || max_batch <= 0) return EF_ERR_INVALID;
   if (max_batch <= m->reserved) return EF_OK;
   const size_t B = (size_t)ef::round_up(max_batch, 128);
-  m->ld_acc = (int)B;
+  m->ld_acc = (int)B + 32;          // plane pitch off the power of two: consecutive planes land in different L2 slices
   // plane-major accumulators and the sum-of-squares buffer start out zero; the epilogue kernels keep them zero
-  EF_TRY(m->acc.ensure(sizeof(int32_t) * B * m->nc_pad));
-  EF_CUDA(cudaMemset(m->acc.p, 0, sizeof(int32_t) * B * m->nc_pad));
+  EF_TRY(m->acc.ensure(sizeof(int32_t) * (B + 32) * m->nc_pad));
+  EF_CUDA(cudaMemset(m->acc.p, 0, sizeof(int32_t) * (B + 32) * m->nc_pad));
   EF_TRY(m->proj.ensure(sizeof(double) * B * m->k));
-  EF_TRY(m->sumsq.ensure(sizeof(double) * B));
-  EF_TRY(m->sumsq_w.ensure(sizeof(double) * B));
-  EF_CUDA(cudaMemset(m->sumsq.p, 0, sizeof(double) * B));
+  EF_TRY(m->sumsq.ensure(sizeof(double) * (B + 32)));
+  EF_TRY(m->sumsq_w.ensure(sizeof(double) * (B + 32)));
+  EF_CUDA(cudaMemset(m->sumsq.p, 0, sizeof(double) * (B + 32)));
   EF_TRY(m->status.ensure(16));
   EF_CUDA(cudaMemset(m->status.p, 0, 16));
   m->dirty = false;
@@ -336,11 +336,12 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
   if (m->tc_mode >= 2) {
     // single-kernel cluster form (TMA + tcgen05 + DSMEM reduction + fused match); falls through when unsupported
     const double* sumsq_ext = nullptr;
-    if (want_resid && m->has_scale) {
+    const bool cluster_shape = m->k <= 32 && m->nc_pad <= 256;      // what recognize_cluster covers (else it declines)
+    if (want_resid && m->has_scale && cluster_shape) {
       EF_TRY(ef::row_sumsq(x, ldx, B, m->D, m->qq.as<double>(), m->sumsq_w.as<double>(), st));
       sumsq_ext = m->sumsq_w.as<double>();
     }
-    const int stc = ef::recognize_cluster(
+    const int stc = !cluster_shape ? EF_ERR_UNSUPPORTED : ef::recognize_cluster(
         x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, m->nc_pad, m->k, m->kq, m->S, m->col_exp.as<int32_t>(),
         m->bias.as<double>(), sumsq_ext, want_resid, m->c0, m->gp.as<double>(), m->kpad, m->gnorm.as<double>(),
         m->ginv.as<double>(), m->gimg.p, m->n_gallery, labels, m->metric, threshold, out->proj, out->score, out->index,
