@@ -481,7 +481,11 @@ def run_ours(args, rank, world):
             "unpipelined": {"value": world * B * args.steps / (ms_unpipelined * 1e-3), "ms_per_step": ms_unpipelined / args.steps,
                             "what": "same steps through ef_model_recognize_device (all results of a batch ready after its own call)"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak if peak else None, "traffic": None,
+                         "frac": achieved / peak if peak else None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel (ncu --set full,
+                         # profiles/r1_h_summary.md): the crops are read once, nothing is re-read
+                         "traffic": 43332864 if launches == args.steps + 1 else None,
+                         "traffic_source": "profiles/r1_h_summary.md (ncu --set full, recognize_pipe_kernel<1,12>, bytes per launch)",
                          "kernel": ("recognize_pipe_kernel (whole step: stream + project batch i, match batch i-1)" if one_launch
                                     else "projection (digit-plane integer GEMM)"), "kernel_ms": kernel_ms,
                          "kernel_ms_isolated": proj_ms, "kernel_calls_timed": args.steps if one_launch else n_calls,
