@@ -379,3 +379,46 @@ def test_pipelined_submission_is_bit_identical(metric, light_model, golden):
     torch.cuda.synchronize()
     for f in ("features", "score", "index", "label"):
         assert torch.equal(o50[f], w50[f]), f
+
+
+def test_random_shapes_all_paths_agree():
+    """Fuzz: random pixel counts (not multiples of 16 / 128), component counts, digit-plane counts, gallery and batch
+    sizes, metrics and scalers -- the CUDA-core path (0), the stream-K tensor-core path (1), the single cluster kernel
+    (2) and the pipelined submission must return identical features / scores / indices / labels / residuals."""
+    torch = require_gpu()
+    rng = np.random.default_rng(20261018)
+    for trial in range(24):
+        D = int(rng.choice([64, 100, 257, 1024, 1600, 4096, 5000]))
+        k = int(rng.integers(1, 41))
+        S = int(rng.choice([0, 0, 4, 6, 8]))
+        n = int(rng.integers(1, 1500))
+        B = int(rng.integers(1, 700))
+        metric = int(rng.choice([ef.METRIC_COSINE_SK, ef.METRIC_COSINE_G1, ef.METRIC_L2]))
+        scaled = bool(rng.integers(0, 2))
+        E = np.linalg.qr(rng.normal(size=(D, min(k, D))))[0]
+        k = E.shape[1]
+        G = rng.normal(size=(n, k)) * rng.uniform(0.5, 200, (1, k))
+        if n > 3:
+            G[n - 1] = G[0]                                        # a duplicate: lowest index must win everywhere
+        kw = dict(scale=rng.uniform(5.0, 80.0, D), pca_mean=rng.normal(0, 1e-2, D)) if scaled else {}
+        rec = ef.Recognizer(E, rng.uniform(40, 210, D), G, metric=metric, n_slices=S, labels=rng.integers(0, 5, n), **kw)
+        X = rng.integers(0, 256, (B, D), dtype=np.uint8)
+        thr = 0.3 if metric != ef.METRIC_L2 else 1e12
+        outs = []
+        for mode in (0, 1, 2):
+            rec.use_tensor_cores(mode)
+            outs.append(rec.recognize(X, thr))
+            assert rec.pipeline_timeouts() == 0
+        ld = (D + 15) // 16 * 16
+        xd = torch.zeros((B, ld), dtype=torch.uint8, device="cuda")
+        xd[:, :D] = torch.from_numpy(X).cuda()
+        po = rec.submit_device(xd, thr)
+        rec.flush_device()
+        torch.cuda.synchronize()
+        tag = f"trial {trial}: D={D} k={k} S={S} n={n} B={B} metric={metric} scaled={scaled}"
+        for f in ("features", "score", "index", "label", "resid2"):
+            a0 = getattr(outs[0], f)
+            for o in outs[1:]:
+                assert np.array_equal(a0, getattr(o, f)), (tag, f)
+            assert np.array_equal(a0, po[f].cpu().numpy()), (tag, f, "pipelined")
+        rec.close()
