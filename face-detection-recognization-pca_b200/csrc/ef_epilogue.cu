@@ -346,13 +346,13 @@ int fused_epilogue(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, cons
 
 int project_finalize(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, const int32_t* col_exp,
                      const double* bias, double* proj, int64_t ldp, double* sumsq, double c0, double* resid2,
-                     cudaStream_t stream) {
+                     bool resid_pass, cudaStream_t stream) {
   if (B <= 0) return EF_OK;
   if (S > 8) return EF_ERR_INVALID;
   dim3 grid((unsigned)ceil_div(B, 32), (unsigned)ceil_div(kq, 32));
   EF_LAUNCH(finalize_combine_kernel, grid, 256, 0, stream, acc_t, ld_acc, B, k, kq, S, col_exp, bias, proj, ldp,
             (kq > k) ? resid2 : nullptr);
-  if (resid2)
+  if (resid2 && resid_pass)
     EF_LAUNCH(finalize_resid_kernel, (unsigned)ceil_div((int64_t)B * 32, 256), 256, 0, stream, proj, ldp, B, k, sumsq,
               c0, resid2);
   return EF_OK;

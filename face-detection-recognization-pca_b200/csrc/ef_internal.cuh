@@ -50,9 +50,10 @@ int fused_epilogue(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, cons
                    double* sumsq, double c0, const double* gp_padded, const double* gnorm, const double* ginv, int64_t n,
                    const int32_t* labels, int metric, double threshold, double* out_proj, double* out_score,
                    int32_t* out_index, int32_t* out_label, double* out_resid, cudaStream_t stream);
+// resid_pass = false leaves x . u~ in resid2 and sumsq untouched: the caller's next kernel (match_small) finishes it
 int project_finalize(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, const int32_t* col_exp,
                      const double* bias, double* proj, int64_t ldp, double* sumsq, double c0, double* resid2,
-                     cudaStream_t stream);
+                     bool resid_pass, cudaStream_t stream);
 
 // ef_match.cu
 // Gallery preparation: gn[j][:] = g[j][:] / |g_j| (COSINE_SK), copy + norms (COSINE_G1), copy (L2).
@@ -65,6 +66,13 @@ int match(const double* p, int64_t ldp, int B, int k, const double* gp, int64_t 
           int64_t index_base, int metric, double* out_score, int64_t* out_index, void* work, cudaStream_t stream);
 int label_lookup(const double* score, const int64_t* index, int B, const int32_t* labels, int metric, double threshold,
                  int32_t* out_index32, int32_t* out_label, cudaStream_t stream);
+
+// ef_match_small.cu -- residual + match + threshold/label in one launch when every CTA can sweep the whole gallery
+// (same float64 arithmetic as finalize_resid_kernel + match + label_lookup); resid2 (nullable) holds x . u~ on entry
+bool match_small_supported(int B, int k, int64_t n);
+int match_small(const double* proj, int64_t ldp, int B, int k, const double* gp, int64_t ldgp, const double* gnorm,
+                int64_t n, const int32_t* labels, int metric, double threshold, double* sumsq, double c0, double* resid2,
+                double* out_score, int32_t* out_index, int32_t* out_label, cudaStream_t stream);
 
 // ef_gram_tc.cu -- exact integer Gram A A^T of uint8 rows on tensor cores (upper triangle + mirror), G int64 += .
 int gram_tc(const uint8_t* A, int64_t lda, int64_t n, int64_t K, int64_t* G, int64_t ldg, int* status,

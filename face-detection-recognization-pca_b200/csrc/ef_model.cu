@@ -381,12 +381,19 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
   } else {
     // 3. planes -> float64 features (+ residual); 4. nearest gallery row; 5. threshold + label
     double* proj = out->proj ? out->proj : m->proj.as<double>();
+    const bool small = ef::match_small_supported(B, m->k, m->n_gallery) && !getenv("EF_NO_MATCH_SMALL");
     EF_TRY(ef::project_finalize(acc, m->ld_acc, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(), m->bias.as<double>(),
-                                proj, m->k, sumsq, m->c0, want_resid ? out->resid2 : nullptr, st));
-    EF_TRY(ef::match(proj, m->k, B, m->k, m->gp.as<double>(), m->kpad, m->gnorm.as<double>(), m->n_gallery, 0, m->metric,
-                     out->score, m->index64.as<int64_t>(), m->match_work.p, st));
-    EF_TRY(ef::label_lookup(out->score, m->index64.as<int64_t>(), B, labels, m->metric, threshold, out->index,
-                            out->label, st));
+                                proj, m->k, sumsq, m->c0, want_resid ? out->resid2 : nullptr, !small, st));
+    if (small) {
+      EF_TRY(ef::match_small(proj, m->k, B, m->k, m->gp.as<double>(), m->kpad, m->gnorm.as<double>(), m->n_gallery,
+                             labels, m->metric, threshold, sumsq, m->c0, want_resid ? out->resid2 : nullptr, out->score,
+                             out->index, out->label, st));
+    } else {
+      EF_TRY(ef::match(proj, m->k, B, m->k, m->gp.as<double>(), m->kpad, m->gnorm.as<double>(), m->n_gallery, 0,
+                       m->metric, out->score, m->index64.as<int64_t>(), m->match_work.p, st));
+      EF_TRY(ef::label_lookup(out->score, m->index64.as<int64_t>(), B, labels, m->metric, threshold, out->index,
+                              out->label, st));
+    }
   }
   m->dirty = false;
   return EF_OK;

@@ -422,3 +422,40 @@ def test_random_shapes_all_paths_agree():
                 assert np.array_equal(a0, getattr(o, f)), (tag, f)
             assert np.array_equal(a0, po[f].cpu().numpy()), (tag, f, "pipelined")
         rec.close()
+
+
+def test_small_gallery_fused_match_equals_generic_chain():
+    """k > 32: the one-launch residual + match + label kernel (ef_match_small.cu) against the generic
+    finalize_resid -> match -> reduce -> label chain (EF_NO_MATCH_SMALL=1): every output bit for bit."""
+    import os
+    require_gpu()
+    rng = np.random.default_rng(77)
+    cases = [(1600, 50, 229, 700, ef.METRIC_COSINE_G1, False), (1024, 178, 178, 300, ef.METRIC_COSINE_SK, True),
+             (1024, 50, 590, 513, ef.METRIC_COSINE_SK, True), (900, 33, 1, 40, ef.METRIC_L2, False),
+             (700, 600, 129, 50, ef.METRIC_COSINE_G1, False), (640, 97, 1000, 33, ef.METRIC_L2, True),
+             (4096, 64, 257, 31, ef.METRIC_COSINE_G1, True)]
+    for D, k, n, B, metric, scaled in cases:
+        E = np.linalg.qr(rng.normal(size=(D, k)))[0]
+        G = rng.normal(size=(n, k)) * rng.uniform(0.5, 50, (1, k))
+        if n > 10:
+            G[n - 2] = G[3]
+            G[7] = 0.0                                             # a zero gallery row: score 0.0 by the reference's rule
+        kw = dict(scale=rng.uniform(5.0, 80.0, D), pca_mean=rng.normal(0, 1e-2, D)) if scaled else {}
+        rec = ef.Recognizer(E, rng.uniform(40, 210, D), G, metric=metric, labels=rng.integers(0, 9, n), **kw)
+        X = rng.integers(0, 256, (B, D), dtype=np.uint8)
+        thr = 0.1 if metric != ef.METRIC_L2 else 1e12
+        os.environ.pop("EF_NO_MATCH_SMALL", None)
+        l0 = ef.launch_count()
+        a = rec.recognize(X, thr)
+        fused_launches = ef.launch_count() - l0
+        os.environ["EF_NO_MATCH_SMALL"] = "1"
+        try:
+            l0 = ef.launch_count()
+            b = rec.recognize(X, thr)
+            chain_launches = ef.launch_count() - l0
+        finally:
+            os.environ.pop("EF_NO_MATCH_SMALL", None)
+        assert fused_launches < chain_launches
+        for f in ("features", "score", "index", "label", "resid2"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), (D, k, n, B, metric, f)
+        rec.close()
