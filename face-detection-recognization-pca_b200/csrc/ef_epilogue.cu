@@ -284,6 +284,34 @@ finalize_resid_kernel(const double* __restrict__ proj, int64_t ldp, int B, int k
   }
 }
 
+// Split-K slabs (ef_project_tc.cu, row-major part[split][crop][ld_part]) -> features: one thread per (crop, column),
+// lanes along the columns of a plane (coalesced reads and feature writes), integer sum over the splits first (exact),
+// then the same float64 combination as combine_planes.
+__global__ void __launch_bounds__(256)
+finalize_slabs_kernel(const int32_t* __restrict__ part, int splits, long long slab_stride, int ld_part, int B, int k,
+                      int kq, int S, const int32_t* __restrict__ col_exp, const double* __restrict__ bias,
+                      double* __restrict__ proj, int64_t ldp, double* __restrict__ xu_out) {
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  const int b = blockIdx.y * 8 + threadIdx.y;
+  if (c >= kq || b >= B) return;
+  int32_t plane[8];
+#pragma unroll
+  for (int s = 0; s < 8; ++s) plane[s] = 0;
+  for (int sp = 0; sp < splits; ++sp) {
+    const int32_t* src = part + (size_t)sp * slab_stride + (size_t)b * ld_part + c;
+#pragma unroll
+    for (int s = 0; s < 8; ++s)
+      if (s < S) plane[s] += __ldcg(src + s * kq);
+  }
+  double v = 0.0;
+#pragma unroll
+  for (int s = 7; s >= 0; --s)                                         // small planes first, like combine_planes
+    if (s < S) v += (double)plane[s] * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
+  v = ldexp(v, col_exp[c]);
+  if (c < k) proj[(size_t)b * ldp + c] = v - bias[c];
+  else if (xu_out) xu_out[b] = v;                                      // the residual column x . u~
+}
+
 template <int METRIC, int KR>
 int launch_fused(EpiArgs& a, cudaStream_t stream) {
   // gallery tile: as many rows as fit (the whole gallery for the shipped sizes), multiple of 4
@@ -342,6 +370,26 @@ int fused_epilogue(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, cons
     case EF_METRIC_L2: return dispatch_kr<EF_METRIC_L2>(a, kr, stream);
     default: return EF_ERR_INVALID;
   }
+}
+
+int project_finalize_slabs(const int32_t* part, int splits, int ld_part, int B, int k, int kq, int S,
+                           const int32_t* col_exp, const double* bias, double* proj, int64_t ldp, double* resid2,
+                           cudaStream_t stream) {
+  if (B <= 0) return EF_OK;
+  if (S > 8) return EF_ERR_INVALID;
+  dim3 grid((unsigned)ceil_div(kq, 32), (unsigned)ceil_div(B, 8)), block(32, 8);
+  EF_LAUNCH(finalize_slabs_kernel, grid, block, 0, stream, part, splits, (long long)B * ld_part, ld_part, B, k, kq, S,
+            col_exp, bias, proj, ldp, (kq > k) ? resid2 : nullptr);
+  return EF_OK;
+}
+
+// the residual pass alone: resid2 holds x . u~ on entry
+int project_resid(const double* proj, int64_t ldp, int B, int k, double* sumsq, double c0, double* resid2,
+                  cudaStream_t stream) {
+  if (B <= 0) return EF_OK;
+  EF_LAUNCH(finalize_resid_kernel, (unsigned)ceil_div((int64_t)B * 32, 256), 256, 0, stream, proj, ldp, B, k, sumsq, c0,
+            resid2);
+  return EF_OK;
 }
 
 int project_finalize(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, const int32_t* col_exp,

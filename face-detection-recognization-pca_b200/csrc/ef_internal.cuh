@@ -16,8 +16,13 @@ int row_sumsq(const uint8_t* X, int64_t ldx, int B, int D, const double* qq, dou
 
 // ef_project_tc.cu -- tcgen05 kind::i8 projection (same integers as project_dp4a); sumsq (may be null) receives
 // += sum_d x^2 per crop.  Returns EF_ERR_UNSUPPORTED when the buffers do not meet the TMA alignment rules.
+// part == null: stream-K schedule, partial tiles merged into acc_t with int32 RED atomics.
+// part != null: split-K schedule, partial tiles STORED row-major as part[split][crop][ld_part] (shape from
+// project_tc_split_shape, bytes from project_tc_part_bytes); acc_t is not touched; project_finalize_slabs consumes it.
 int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int wq_rows,
-               int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream);
+               int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream, int32_t* part = nullptr);
+void project_tc_split_shape(int B, int D, int NC, int* splits, int* ld_part);
+size_t project_tc_part_bytes(int B, int D, int NC);
 
 // ef_recognize_cluster.cu -- single-kernel form (cluster of 4, DSMEM reduction, fused match); EF_ERR_UNSUPPORTED when
 // the shape is outside its coverage (k <= 32, S*(k+1) <= 256, aligned buffers)
@@ -54,6 +59,14 @@ int fused_epilogue(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, cons
 int project_finalize(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, const int32_t* col_exp,
                      const double* bias, double* proj, int64_t ldp, double* sumsq, double c0, double* resid2,
                      bool resid_pass, cudaStream_t stream);
+
+// split-K slabs of project_tc -> float64 features (and x . u~ into resid2 when kq > k); nothing to clear
+int project_finalize_slabs(const int32_t* part, int splits, int ld_part, int B, int k, int kq, int S,
+                           const int32_t* col_exp, const double* bias, double* proj, int64_t ldp, double* resid2,
+                           cudaStream_t stream);
+
+int project_resid(const double* proj, int64_t ldp, int B, int k, double* sumsq, double c0, double* resid2,
+                  cudaStream_t stream);
 
 // ef_match.cu
 // Gallery preparation: gn[j][:] = g[j][:] / |g_j| (COSINE_SK), copy + norms (COSINE_G1), copy (L2).

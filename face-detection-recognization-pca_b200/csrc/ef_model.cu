@@ -25,6 +25,7 @@ struct ef_model {
   // workspaces (sized by reserve)
   int reserved = 0;
   ef::DevBuf acc, proj, sumsq, score, index64, match_work, status;
+  ef::DevBuf part;                 // split-K slabs of the tensor-core projection (k > 32)
   int nc_pad = 0;
   bool dirty = false;
   // host-path staging
@@ -292,6 +293,13 @@ int ef_model_reserve(ef_model_t* m, int32_t max_batch) {
   EF_TRY(m->acc.ensure(sizeof(int32_t) * (B + 32) * m->nc_pad));
   EF_CUDA(cudaMemset(m->acc.p, 0, sizeof(int32_t) * (B + 32) * m->nc_pad));
   EF_TRY(m->proj.ensure(sizeof(double) * B * m->k));
+  if (!ef::fused_epilogue_supported(m->k, m->n_gallery)) {
+    // splits x crops never exceeds max(batch, one wave of 128-crop tiles): see project_tc_split_shape
+    int splits = 1, ld_part = 0;
+    ef::project_tc_split_shape((int)B, m->D, m->NC, &splits, &ld_part);
+    const size_t rows = std::max(B, (size_t)ef::sm_count() * 128);
+    EF_TRY(m->part.ensure(sizeof(int32_t) * rows * ld_part));
+  }
   EF_TRY(m->sumsq.ensure(sizeof(double) * (B + 32)));
   EF_TRY(m->sumsq_w.ensure(sizeof(double) * (B + 32)));
   EF_CUDA(cudaMemset(m->sumsq.p, 0, sizeof(double) * (B + 32)));
@@ -359,9 +367,11 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
   // the tensor-core kernel also produces the integer sum of squares (Gen-1 residual) from the staged crop tiles
   const bool tc_sumsq = want_resid && !m->has_scale;
   int st_tc = EF_ERR_UNSUPPORTED;
+  // k > 32: split-K slabs (plain stores, no accumulator invariants) instead of stream-K + int32 RED atomics
+  int32_t* part = (m->part.p && !getenv("EF_NO_SLABS")) ? m->part.as<int32_t>() : nullptr;
   if (m->tc_mode >= 1)
     st_tc = ef::project_tc(x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, m->nc_pad, acc, m->ld_acc,
-                           tc_sumsq ? sumsq : nullptr, m->status.as<int>(), st);
+                           tc_sumsq ? sumsq : nullptr, m->status.as<int>(), st, part);
   m->last_used_tc = st_tc == EF_OK;
   m->last_path = m->last_used_tc ? 1 : 0;
   if (st_tc != EF_OK) {
@@ -382,8 +392,18 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
     // 3. planes -> float64 features (+ residual); 4. nearest gallery row; 5. threshold + label
     double* proj = out->proj ? out->proj : m->proj.as<double>();
     const bool small = ef::match_small_supported(B, m->k, m->n_gallery) && !getenv("EF_NO_MATCH_SMALL");
-    EF_TRY(ef::project_finalize(acc, m->ld_acc, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(), m->bias.as<double>(),
-                                proj, m->k, sumsq, m->c0, want_resid ? out->resid2 : nullptr, !small, st));
+    if (m->last_used_tc && part) {
+      int splits = 1, ld_part = 0;
+      ef::project_tc_split_shape(B, m->D, m->NC, &splits, &ld_part);
+      EF_TRY(ef::project_finalize_slabs(part, splits, ld_part, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(),
+                                        m->bias.as<double>(), proj, m->k, want_resid ? out->resid2 : nullptr, st));
+      if (!small && want_resid)
+        EF_TRY(ef::project_resid(proj, m->k, B, m->k, sumsq, m->c0, out->resid2, st));
+    } else {
+      EF_TRY(ef::project_finalize(acc, m->ld_acc, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(),
+                                  m->bias.as<double>(), proj, m->k, sumsq, m->c0, want_resid ? out->resid2 : nullptr,
+                                  !small, st));
+    }
     if (small) {
       EF_TRY(ef::match_small(proj, m->k, B, m->k, m->gp.as<double>(), m->kpad, m->gnorm.as<double>(), m->n_gallery,
                              labels, m->metric, threshold, sumsq, m->c0, want_resid ? out->resid2 : nullptr, out->score,

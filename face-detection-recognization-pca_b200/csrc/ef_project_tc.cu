@@ -36,6 +36,11 @@ struct Args {
   int umma_n, n_umma;        // tcgen05.mma instructions per K step
   int ld_acc;
   int32_t* acc_t;
+  // split-K mode (part != null): CTA = (tile, split) with one contiguous K range of ONE tile, its partial tile is
+  // STORED row-major into slab `split` (part[split][row][ld_part]) -- no atomics, no zero-initialised accumulators
+  int32_t* part;
+  int splits, ld_part;
+  long long slab_stride;
   double* sumsq;             // may be null
   int* status;
   unsigned long long* probe;   // optional [grid][8] timestamps (ns), debugging aid enabled by EF_TC_PROBE=1
@@ -85,8 +90,17 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 
   // this CTA's contiguous range of (n tile, m tile, k block) units
   const long long total_units = (long long)a.n_tiles * a.m_tiles * a.kb_total;
-  const long long u_begin = total_units * blockIdx.x / gridDim.x;
-  const long long u_end = total_units * (blockIdx.x + 1) / gridDim.x;
+  long long u_begin, u_end;
+  int split = 0;
+  if (a.part) {
+    const long long tile = blockIdx.x / a.splits;
+    split = blockIdx.x - (int)tile * a.splits;
+    u_begin = tile * a.kb_total + (long long)a.kb_total * split / a.splits;
+    u_end = tile * a.kb_total + (long long)a.kb_total * (split + 1) / a.splits;
+  } else {
+    u_begin = total_units * blockIdx.x / gridDim.x;
+    u_end = total_units * (blockIdx.x + 1) / gridDim.x;
+  }
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -193,7 +207,14 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       for (int c0 = 0; c0 < a.block_n; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)c0, v);
-        if (row < a.B) {
+        if (a.part) {
+          if (row < a.B) {
+            uint4* dst = reinterpret_cast<uint4*>(a.part + (size_t)split * a.slab_stride + (size_t)row * a.ld_part +
+                                                  n_tile * a.block_n + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) __stcg(dst + j, make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]));
+          }
+        } else if (row < a.B) {
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
             const int col = n_tile * a.block_n + c0 + j;
@@ -260,8 +281,40 @@ namespace ef {
 
 using namespace ef_tc;
 
+// Tile shape shared by the two schedules.
+static void tile_shape(int NC, int* block_n, int* n_tiles) {
+  const int nc16 = (int)round_up(NC, 16);
+  if (nc16 <= 256) {
+    *block_n = nc16;
+    *n_tiles = 1;
+  } else {
+    *n_tiles = (int)ceil_div(NC, 512);
+    *block_n = (int)round_up(ceil_div(NC, *n_tiles), 32);
+  }
+}
+
+// Split-K schedule: as many K ranges per tile as whole waves of one CTA per SM allow.
+void project_tc_split_shape(int B, int D, int NC, int* splits, int* ld_part) {
+  int block_n, n_tiles;
+  tile_shape(NC, &block_n, &n_tiles);
+  const long long tiles = (long long)n_tiles * ceil_div(B, BLOCK_M);
+  const int kb_total = (int)ceil_div(D, BLOCK_K);
+  long long s = sm_count() / tiles;
+  if (s < 1) s = 1;
+  if (s > kb_total) s = kb_total;
+  if (s > 8) s = 8;
+  *splits = (int)s;
+  *ld_part = n_tiles * block_n;
+}
+
+size_t project_tc_part_bytes(int B, int D, int NC) {
+  int splits, ld_part;
+  project_tc_split_shape(B, D, NC, &splits, &ld_part);
+  return sizeof(int32_t) * (size_t)splits * (size_t)B * ld_part;
+}
+
 int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int wq_rows,
-               int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream) {
+               int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream, int32_t* part) {
   if (B <= 0) return EF_OK;
   if ((ldx & 15) || (reinterpret_cast<uintptr_t>(X) & 15) || (ldw & 15) || (reinterpret_cast<uintptr_t>(Wq) & 15))
     return EF_ERR_UNSUPPORTED;
@@ -270,14 +323,7 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
   Args a{};
   a.B = B;
   a.NC = NC;
-  const int nc16 = (int)round_up(NC, 16);
-  if (nc16 <= 256) {
-    a.block_n = nc16;
-    a.n_tiles = 1;
-  } else {
-    a.n_tiles = (int)ceil_div(NC, 512);
-    a.block_n = (int)round_up(ceil_div(NC, a.n_tiles), 32);
-  }
+  tile_shape(NC, &a.block_n, &a.n_tiles);
   if (a.block_n <= 256) {
     a.box_rows = a.block_n; a.n_loads = 1; a.umma_n = a.block_n; a.n_umma = 1;
   } else {
@@ -294,6 +340,11 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
   if (a.stages < 2) return EF_ERR_UNSUPPORTED;
   a.ld_acc = ld_acc;
   a.acc_t = acc_t;
+  a.part = part;
+  if (part) {
+    project_tc_split_shape(B, D, NC, &a.splits, &a.ld_part);
+    a.slab_stride = (long long)B * a.ld_part;
+  }
   a.sumsq = sumsq;
   a.status = status;
   a.probe = nullptr;
@@ -312,6 +363,7 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
   int grid = sm_count();
   if (const char* e = getenv("EF_TC_GRID")) { const int v = atoi(e); if (v >= 1) grid = v; }
   if (grid > total_units) grid = (int)total_units;
+  if (part) grid = a.n_tiles * a.m_tiles * a.splits;
   static unsigned long long* probe_buf = nullptr;
   static int probe_grid = 0;
   const bool probing = getenv("EF_TC_PROBE") != nullptr;

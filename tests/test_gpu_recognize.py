@@ -459,3 +459,36 @@ def test_small_gallery_fused_match_equals_generic_chain():
         for f in ("features", "score", "index", "label", "resid2"):
             assert np.array_equal(getattr(a, f), getattr(b, f)), (D, k, n, B, metric, f)
         rec.close()
+
+
+def test_split_k_slabs_equal_stream_k_atomics():
+    """k > 32 on tensor cores: the split-K schedule that STORES partial tiles into slabs (default) against the stream-K
+    schedule that merges them with int32 RED atomics (EF_NO_SLABS=1) and against the CUDA-core path (mode 0)."""
+    import os
+    require_gpu()
+    rng = np.random.default_rng(99)
+    # (D, k, n, B): 1..3 column tiles, 1..8 K ranges per tile, more tiles than SMs, K blocks fewer than SMs / tiles
+    cases = [(1024, 50, 229, 4096), (1024, 50, 229, 20000), (640, 178, 178, 300), (4096, 64, 100, 129),
+             (256, 40, 64, 1), (10000, 50, 229, 1000), (130, 33, 10, 257)]
+    for D, k, n, B in cases:
+        E = np.linalg.qr(rng.normal(size=(D, min(k, D))))[0]
+        k = E.shape[1]
+        G = rng.normal(size=(n, k)) * 30
+        rec = ef.Recognizer(E, rng.uniform(40, 210, D), G, metric=ef.METRIC_COSINE_G1)
+        X = rng.integers(0, 256, (B, D), dtype=np.uint8)
+        os.environ.pop("EF_NO_SLABS", None)
+        rec.use_tensor_cores(1)
+        a = rec.recognize(X, 0.2)
+        a2 = rec.recognize(X, 0.2)                                 # nothing left behind by the first call
+        os.environ["EF_NO_SLABS"] = "1"
+        try:
+            b = rec.recognize(X, 0.2)
+        finally:
+            os.environ.pop("EF_NO_SLABS", None)
+        rec.use_tensor_cores(0)
+        c = rec.recognize(X, 0.2)
+        for f in ("features", "score", "index", "label", "resid2"):
+            for other in (a2, b, c):
+                assert np.array_equal(getattr(a, f), getattr(other, f)), (D, k, n, B, f)
+        assert rec.pipeline_timeouts() == 0
+        rec.close()
