@@ -291,9 +291,11 @@ __global__ void __launch_bounds__(256)
 finalize_slabs_kernel(const int32_t* __restrict__ part, int splits, long long slab_stride, int ld_part, int B, int k,
                       int kq, int S, const int32_t* __restrict__ col_exp, const double* __restrict__ bias,
                       double* __restrict__ proj, int64_t ldp, double* __restrict__ xu_out) {
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  const int b = blockIdx.y * 8 + threadIdx.y;
-  if (c >= kq || b >= B) return;
+  // flattened (crop, column) index: every lane is busy whatever kq is; runs of kq consecutive lanes read one crop
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(idx / kq);
+  const int c = (int)(idx - (long long)b * kq);
+  if (b >= B) return;
   int32_t plane[8];
 #pragma unroll
   for (int s = 0; s < 8; ++s) plane[s] = 0;
@@ -377,8 +379,8 @@ int project_finalize_slabs(const int32_t* part, int splits, int ld_part, int B, 
                            cudaStream_t stream) {
   if (B <= 0) return EF_OK;
   if (S > 8) return EF_ERR_INVALID;
-  dim3 grid((unsigned)ceil_div(kq, 32), (unsigned)ceil_div(B, 8)), block(32, 8);
-  EF_LAUNCH(finalize_slabs_kernel, grid, block, 0, stream, part, splits, (long long)B * ld_part, ld_part, B, k, kq, S,
+  const unsigned grid = (unsigned)ceil_div((int64_t)B * kq, 256);
+  EF_LAUNCH(finalize_slabs_kernel, grid, 256, 0, stream, part, splits, (long long)B * ld_part, ld_part, B, k, kq, S,
             col_exp, bias, proj, ldp, (kq > k) ? resid2 : nullptr);
   return EF_OK;
 }

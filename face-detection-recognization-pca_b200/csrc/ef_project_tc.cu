@@ -41,9 +41,31 @@ struct Args {
   int32_t* part;
   int splits, ld_part;
   long long slab_stride;
+  // split-K mode with mcast > 1: clusters of `mcast` consecutive crop tiles of the same (column tile, K range) share the
+  // basis tile -- every CTA fetches 1/mcast of it and TMA-multicasts that part into the shared memory of all of them
+  int mcast, m_tiles_pad;
   double* sumsq;             // may be null
   int* status;
   unsigned long long* probe;   // optional [grid][8] timestamps (ns), debugging aid enabled by EF_TC_PROBE=1
+};
+
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, unsigned long long* bar, int c_inner,
+                                               int c_outer, uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+      " [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "h"(cta_mask)
+      : "memory");
+}
+// arrives on the barrier at the same shared-memory offset in every CTA of the mask once the MMAs issued so far are done
+__device__ __forceinline__ void umma_commit_mc(unsigned long long* bar, uint16_t cta_mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(cta_mask)
+               : "memory");
+}
+
+struct Seg {
+  int n_tile, m_tile, kb0, kb1;
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -66,7 +88,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   if (threadIdx.x == 0) {
     for (int s = 0; s < a.stages; ++s) {
       mbar_init(&sh->full_bar[s], 1);
-      mbar_init(&sh->empty_bar[s], do_sumsq ? 5 : 1);     // MMA commit (+ one arrive per epilogue warp)
+      // MMA commit of every CTA that writes into this stage (+ one arrive per local epilogue warp)
+      mbar_init(&sh->empty_bar[s], (do_sumsq ? 4 : 0) + (a.part ? a.mcast : 1));
     }
     mbar_init(&sh->tmem_full_bar, 1);
     mbar_init(&sh->tmem_empty_bar, 4);
@@ -83,6 +106,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  const bool clustered = a.part && a.mcast > 1;
+  if (clustered) cluster_sync_all();                  // the peers' barriers exist before anything is multicast to them
   const uint32_t tmem_base = sh->tmem_base;
   unsigned long long* probe = a.probe ? a.probe + (size_t)blockIdx.x * 8 : nullptr;
   if (probe && threadIdx.x == 0) { probe[0] = a.probe[(size_t)gridDim.x * 8]; probe[1] = globaltimer(); }
@@ -92,15 +117,29 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   const long long total_units = (long long)a.n_tiles * a.m_tiles * a.kb_total;
   long long u_begin, u_end;
   int split = 0;
+  Seg fixed{0, 0, 0, 0};
   if (a.part) {
-    const long long tile = blockIdx.x / a.splits;
-    split = blockIdx.x - (int)tile * a.splits;
-    u_begin = tile * a.kb_total + (long long)a.kb_total * split / a.splits;
-    u_end = tile * a.kb_total + (long long)a.kb_total * (split + 1) / a.splits;
+    // blockIdx = (column tile, K range, crop tile): the `mcast` CTAs of a cluster are consecutive crop tiles
+    const int grp = blockIdx.x / a.m_tiles_pad;
+    fixed.m_tile = blockIdx.x - grp * a.m_tiles_pad;         // may lie past the batch (cluster padding): loads zero fill
+    fixed.n_tile = grp / a.splits;
+    split = grp - fixed.n_tile * a.splits;
+    fixed.kb0 = (int)((long long)a.kb_total * split / a.splits);
+    fixed.kb1 = (int)((long long)a.kb_total * (split + 1) / a.splits);
+    u_begin = 0;
+    u_end = fixed.kb1 - fixed.kb0;
   } else {
     u_begin = total_units * blockIdx.x / gridDim.x;
     u_end = total_units * (blockIdx.x + 1) / gridDim.x;
   }
+  auto seg_at = [&](long long u) -> Seg {
+    if (a.part) return fixed;
+    const long long tile = u / a.kb_total;
+    const int kb0 = (int)(u % a.kb_total);
+    return Seg{(int)(tile / a.m_tiles), (int)(tile % a.m_tiles), kb0, (int)min((long long)a.kb_total, kb0 + (u_end - u))};
+  };
+  const uint16_t cta_mask = (uint16_t)((1u << a.mcast) - 1u);
+  const int rank = clustered ? (int)cluster_ctarank() : 0;
 
   if (warp == 0) {
     // ===================================================================== TMA producer
@@ -112,20 +151,23 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const uint32_t stage_bytes = (uint32_t)(A_STAGE_BYTES + b_stage_bytes);
       bool ok = true;
       for (long long u = u_begin; u < u_end && ok;) {
-        const long long tile = u / a.kb_total;
-        const int kb0 = (int)(u % a.kb_total);
-        const int kb1 = (int)min((long long)a.kb_total, kb0 + (u_end - u));
-        const int n_tile = (int)(tile / a.m_tiles), m_tile = (int)(tile % a.m_tiles);
-        for (int kb = kb0; kb < kb1; ++kb) {
+        const Seg sg = seg_at(u);
+        for (int kb = sg.kb0; kb < sg.kb1; ++kb) {
           if (!mbar_wait(&sh->empty_bar[stage], phase ^ 1, failed)) { ok = false; break; }
           mbar_arrive_expect_tx(&sh->full_bar[stage], stage_bytes);
-          tma_load_2d(sA + (size_t)stage * A_STAGE_BYTES, &tmap_x, &sh->full_bar[stage], kb * BLOCK_K, m_tile * BLOCK_M);
-          for (int l = 0; l < a.n_loads; ++l)
-            tma_load_2d(sB + (size_t)stage * b_stage_bytes + (size_t)l * a.box_rows * BLOCK_K, &tmap_w,
-                        &sh->full_bar[stage], kb * BLOCK_K, n_tile * a.block_n + l * a.box_rows);
+          tma_load_2d(sA + (size_t)stage * A_STAGE_BYTES, &tmap_x, &sh->full_bar[stage], kb * BLOCK_K, sg.m_tile * BLOCK_M);
+          if (clustered) {
+            // this CTA's share of the basis tile, delivered to every CTA of the cluster (their full barriers count it)
+            tma_load_2d_mc(sB + (size_t)stage * b_stage_bytes + (size_t)rank * a.box_rows * BLOCK_K, &tmap_w,
+                           &sh->full_bar[stage], kb * BLOCK_K, sg.n_tile * a.block_n + rank * a.box_rows, cta_mask);
+          } else {
+            for (int l = 0; l < a.n_loads; ++l)
+              tma_load_2d(sB + (size_t)stage * b_stage_bytes + (size_t)l * a.box_rows * BLOCK_K, &tmap_w,
+                          &sh->full_bar[stage], kb * BLOCK_K, sg.n_tile * a.block_n + l * a.box_rows);
+          }
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
-        u += kb1 - kb0;
+        u += sg.kb1 - sg.kb0;
       }
     }
   } else if (warp == 1) {
@@ -137,8 +179,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       const uint32_t idesc = umma_idesc_i8(a.umma_n);
       bool ok = true;
       for (long long u = u_begin; u < u_end && ok; ++seg) {
-        const int kb0 = (int)(u % a.kb_total);
-        const int kb1 = (int)min((long long)a.kb_total, kb0 + (u_end - u));
+        const Seg sg = seg_at(u);
+        const int kb0 = sg.kb0, kb1 = sg.kb1;
         if (!mbar_wait(&sh->tmem_empty_bar, (seg & 1) ^ 1, failed)) { ok = false; break; }
         tc_fence_after();
         for (int kb = kb0; kb < kb1; ++kb) {
@@ -155,7 +197,9 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
               umma_i8(tmem_base + h * a.umma_n, da, db, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
-          umma_commit(&sh->empty_bar[stage]);      // frees the stage once these MMAs have read it
+          // frees the stage once these MMAs have read it -- in every CTA that multicasts into it
+          if (clustered) umma_commit_mc(&sh->empty_bar[stage], cta_mask);
+          else umma_commit(&sh->empty_bar[stage]);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
         if (!ok) break;
@@ -173,10 +217,8 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     uint32_t seg = 0;
     bool ok = true;
     for (long long u = u_begin; u < u_end && ok; ++seg) {
-      const long long tile = u / a.kb_total;
-      const int kb0 = (int)(u % a.kb_total);
-      const int kb1 = (int)min((long long)a.kb_total, kb0 + (u_end - u));
-      const int n_tile = (int)(tile / a.m_tiles), m_tile = (int)(tile % a.m_tiles);
+      const Seg sg = seg_at(u);
+      const int kb0 = sg.kb0, kb1 = sg.kb1, n_tile = sg.n_tile, m_tile = sg.m_tile;
       const int row = m_tile * BLOCK_M + row_in_tile;
       unsigned long long ssq = 0;
       if (do_sumsq) {
@@ -234,6 +276,7 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   // ----------------------------------------------------------------------------------------- teardown
   tc_fence_before();
   __syncthreads();
+  if (clustered) cluster_sync_all();                  // no peer still multicasts into, or arrives on, this CTA's memory
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.tmem_cols)
@@ -293,11 +336,22 @@ static void tile_shape(int NC, int* block_n, int* n_tiles) {
   }
 }
 
-// Split-K schedule: as many K ranges per tile as whole waves of one CTA per SM allow.
-void project_tc_split_shape(int B, int D, int NC, int* splits, int* ld_part) {
+// Split-K schedule: clusters of `mcast` crop tiles share the basis tile; as many K ranges per tile as whole waves of one
+// CTA per SM allow.
+static void split_shape(int B, int D, int NC, int* splits, int* ld_part, int* mcast, int* m_tiles_pad) {
   int block_n, n_tiles;
   tile_shape(NC, &block_n, &n_tiles);
-  const long long tiles = (long long)n_tiles * ceil_div(B, BLOCK_M);
+  const int m_tiles = (int)ceil_div(B, BLOCK_M);
+  int c = 1;
+  // measured on B200 (4096 x 10 000 x 416 columns): the main loop is bound by the kind::i8 tensor pipe, not by L2 -> SM
+  // traffic, and sharing the basis tile changes nothing (72.7 us against 71.2 us per batch): off unless asked for
+  if (getenv("EF_TC_MULTICAST")) {
+    if (m_tiles >= 3 && block_n % 32 == 0) c = 4;
+    else if (m_tiles >= 2 && block_n % 16 == 0) c = 2;
+  }
+  *mcast = c;
+  *m_tiles_pad = (int)round_up(m_tiles, c);
+  const long long tiles = (long long)n_tiles * *m_tiles_pad;
   const int kb_total = (int)ceil_div(D, BLOCK_K);
   long long s = sm_count() / tiles;
   if (s < 1) s = 1;
@@ -305,6 +359,11 @@ void project_tc_split_shape(int B, int D, int NC, int* splits, int* ld_part) {
   if (s > 8) s = 8;
   *splits = (int)s;
   *ld_part = n_tiles * block_n;
+}
+
+void project_tc_split_shape(int B, int D, int NC, int* splits, int* ld_part) {
+  int mcast, m_tiles_pad;
+  split_shape(B, D, NC, splits, ld_part, &mcast, &m_tiles_pad);
 }
 
 size_t project_tc_part_bytes(int B, int D, int NC) {
@@ -341,9 +400,14 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
   a.ld_acc = ld_acc;
   a.acc_t = acc_t;
   a.part = part;
+  a.mcast = 1;
   if (part) {
-    project_tc_split_shape(B, D, NC, &a.splits, &a.ld_part);
+    split_shape(B, D, NC, &a.splits, &a.ld_part, &a.mcast, &a.m_tiles_pad);
     a.slab_stride = (long long)B * a.ld_part;
+    if (a.mcast > 1) {                       // one box per CTA: its share of the basis tile
+      a.box_rows = a.block_n / a.mcast;
+      a.n_loads = 1;
+    }
   }
   a.sumsq = sumsq;
   a.status = status;
@@ -363,7 +427,7 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
   int grid = sm_count();
   if (const char* e = getenv("EF_TC_GRID")) { const int v = atoi(e); if (v >= 1) grid = v; }
   if (grid > total_units) grid = (int)total_units;
-  if (part) grid = a.n_tiles * a.m_tiles * a.splits;
+  if (part) grid = a.n_tiles * a.m_tiles_pad * a.splits;
   static unsigned long long* probe_buf = nullptr;
   static int probe_grid = 0;
   const bool probing = getenv("EF_TC_PROBE") != nullptr;
@@ -373,7 +437,24 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
     a.probe = probe_buf;
     probe_grid = grid;
   }
-  EF_LAUNCH(project_tc_kernel, grid, kThreads, smem, stream, mx, mw, a);
+  if (part && a.mcast > 1) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[1];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = (unsigned)a.mcast;
+    attrs[0].val.clusterDim.y = 1;
+    attrs[0].val.clusterDim.z = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = 1;
+    EF_CUDA(cudaLaunchKernelEx(&cfg, project_tc_kernel, mx, mw, a));
+    ef::g_launches.fetch_add(1, std::memory_order_relaxed);
+  } else {
+    EF_LAUNCH(project_tc_kernel, grid, kThreads, smem, stream, mx, mw, a);
+  }
   if (probing) {
     // debugging aid: per-CTA phase timestamps relative to the first CTA entering the kernel
     std::vector<unsigned long long> h(8 * (size_t)(probe_grid + 1));

@@ -485,10 +485,15 @@ def test_split_k_slabs_equal_stream_k_atomics():
             b = rec.recognize(X, 0.2)
         finally:
             os.environ.pop("EF_NO_SLABS", None)
+        os.environ["EF_TC_MULTICAST"] = "1"                        # basis tile TMA-multicast across crop-tile clusters
+        try:
+            e = rec.recognize(X, 0.2)
+        finally:
+            os.environ.pop("EF_TC_MULTICAST", None)
         rec.use_tensor_cores(0)
         c = rec.recognize(X, 0.2)
         for f in ("features", "score", "index", "label", "resid2"):
-            for other in (a2, b, c):
+            for other in (a2, b, c, e):
                 assert np.array_equal(getattr(a, f), getattr(other, f)), (D, k, n, B, f)
         assert rec.pipeline_timeouts() == 0
         rec.close()
