@@ -81,13 +81,15 @@ match_small_kernel(const MsArgs a) {
   auto issue = [&](int stage) {
     const int t = stage / n_chunks, c = stage - t * n_chunks;
     double* dst = gs + (size_t)(stage & 1) * GT * GS;
-    const int kk = lane, col = c * KC + kk;
-    const double* src = a.G + (int64_t)(t * GT) * a.ldg + col;
+    const double* src = a.G + (int64_t)(t * GT) * a.ldg + c * KC;
     const int rows = min(GT, a.n - t * GT);
-#pragma unroll 4
+#pragma unroll 2
     for (int r = warp; r < GT; r += kWarps) {
-      if (r < rows && col < a.k) cp_async8(dst + r * GS + kk, src + (int64_t)r * a.ldg);
-      else dst[r * GS + kk] = 0.0;
+#pragma unroll
+      for (int kk = lane; kk < KC; kk += 32) {
+        if (r < rows && c * KC + kk < a.k) cp_async8(dst + r * GS + kk, src + (int64_t)r * a.ldg + kk);
+        else dst[r * GS + kk] = 0.0;
+      }
     }
     asm volatile("cp.async.commit_group;\n" ::: "memory");
   };
