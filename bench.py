@@ -298,6 +298,46 @@ def fit_and_gram_section(ef, torch, dev, peaks):
                                 "(tensor-core Gram + integer centring + filtered subspace iteration + projection)",
                         "seconds": time.perf_counter() - t0, "solver": info4,
                         "orthonormality_error": float((E4.T @ E4 - torch.eye(K4, device=dev, dtype=torch.float64)).abs().max())}
+    # ---- template-matching detector: one 640x480 camera frame against 4 persons x 5 template crops
+    # x 3 scales = 60 TM_CCOEFF_NORMED maps + arg-max, the per-frame work of scan-template-v4.py:129-197
+    rng = np.random.default_rng(640480)
+    frame = rng.integers(0, 256, (480, 640), dtype=np.uint8)
+    tmpls = [rng.integers(0, 256, (int(rng.integers(80, 121)), int(rng.integers(80, 121))), dtype=np.uint8) for _ in range(20)]
+    tmpls[3] = frame[200:300, 250:340].copy()
+    matcher = ef.template.TemplateMatcher(tmpls)
+    frame_dev = torch.from_numpy(frame).to(dev)
+    res = matcher.match(frame_dev)
+    torch.cuda.synchronize()
+    l0 = ef.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    for _ in range(5):
+        res = matcher.match(frame_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / 5
+    macs = sum((640 - w + 1) * (480 - h + 1) * w * h for (_, _, w, h) in matcher.jobs)
+    tm = {"what": f"cv2.matchTemplate(TM_CCOEFF_NORMED) + minMaxLoc, 640x480 gray frame, {len(matcher.jobs)} (template, scale) jobs "
+                  "of 64..144 px (scan-template-v4.py:129-197 per frame)",
+          "ms_per_frame_device": e0.elapsed_time(e1) / 5, "ms_per_frame_wall": wall * 1e3, "launches_per_frame": (ef.launch_count() - l0) / 5,
+          "exact_integer_tmac_per_s": macs / (e0.elapsed_time(e1) / 5 * 1e-3) / 1e12,
+          "found_pasted_template_at": [res[10]["x"], res[10]["y"]] if res[10] else None}
+    try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count())
+        t0 = time.perf_counter()
+        n_cpu = 0
+        for ti, scale, w, h in matcher.jobs[:12]:                       # bounded sample: 12 of the 60 jobs
+            st = cv2.resize(tmpls[ti], (w, h))
+            r = cv2.matchTemplate(frame, st, cv2.TM_CCOEFF_NORMED)
+            cv2.minMaxLoc(r)
+            n_cpu += 1
+        tm["cpu_cv2_ms_per_frame"] = (time.perf_counter() - t0) / n_cpu * len(matcher.jobs) * 1e3
+        tm["cpu_note"] = f"cv2 {cv2.__version__} on {os.cpu_count()} host cores, {n_cpu} of the jobs timed and scaled to all"
+    except ImportError:
+        tm["cpu_cv2_ms_per_frame"] = None
+    out["template_match"] = tm
     return out
 
 

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libeigenfaces_b200.so")
 SOURCES = ["ef_abi.cu", "ef_preprocess.cu", "ef_project.cu", "ef_project_tc.cu", "ef_recognize_cluster.cu", "ef_recognize_pipe.cu", "ef_epilogue.cu", "ef_match.cu", "ef_match_small.cu", "ef_match_tc.cu", "ef_linalg.cu",
-           "ef_model.cu", "ef_fit.cu", "ef_gram_tc.cu"]
+           "ef_model.cu", "ef_fit.cu", "ef_gram_tc.cu", "ef_template.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared", "-cudart", "static"]
 

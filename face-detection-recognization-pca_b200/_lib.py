@@ -78,6 +78,9 @@ SIGNATURES = {
     "ef_match_tc_device": (C.c_int, [c_void, c_i64, c_i32, c_i32, c_void, c_i64, c_void, c_void, c_i64, c_i64, c_i32,
                                      c_void, c_void, c_void, C.c_size_t, c_void]),
     "ef_match_tc_flags": (C.c_int, [c_void, p_i32]),
+    "ef_template_match_work_bytes": (C.c_size_t, [c_i32, c_i32, c_i32, c_void, c_void]),
+    "ef_template_match_device": (C.c_int, [c_void, c_i64, c_i32, c_i32, c_void, c_void, c_void, c_void, c_i32, c_void,
+                                           c_void, c_void, c_void, c_void, C.c_size_t, c_void]),
     "ef_match_reduce_device": (C.c_int, [c_void, c_void, c_i32, c_i32, c_i32, c_void, c_void, c_void]),
     "ef_fit_gen1_host": (C.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_void, c_void, c_void,
                                    C.POINTER(FitInfo)]),

@@ -14,7 +14,7 @@ from datetime import datetime
 
 import numpy as np
 
-from . import engine
+from . import engine, template
 from ._lib import METRIC_COSINE_SK
 
 _CACHE = {}
@@ -236,7 +236,10 @@ class MultiModelFaceScanner:
         self.models = {}
 
     def load_all_models(self, model_pattern="faces/lock_version/*/face_model.pkl"):
-        """scan-template-v4.py:17-74 without the template images (detection stays on the host, out of scope)."""
+        """scan-template-v4.py:17-74: models, detection JSON and the first five face crops of every person as
+        template images.  The reference opens face_data['image_path'] as written by detection-v4.py (Windows
+        separators); here the same path is tried first, then with normalised separators, then the file name inside
+        the person's directory (train-v5.py:305-306's rule) so that the templates also load on POSIX hosts."""
         model_paths = glob.glob(model_pattern)
         if not model_paths:
             print(f"No models found matching pattern: {model_pattern}")
@@ -247,12 +250,70 @@ class MultiModelFaceScanner:
             try:
                 with open(model_path, 'rb') as f:
                     model_data = pickle.load(f)
-                self.models[person_name] = {'model_data': model_data, 'model_path': model_path}
+                person_dir = os.path.dirname(model_path)
+                detection_json_path = os.path.join(person_dir, f"{person_name}_faces_detection.json")
+                detection_data = None
+                if os.path.exists(detection_json_path):
+                    with open(detection_json_path, 'r', encoding='utf-8') as f:
+                        detection_data = json.load(f)
+                template_images = []
+                if detection_data and detection_data.get('faces'):
+                    import cv2
+                    for face_data in detection_data['faces'][:5]:
+                        cands = [face_data.get('image_path', ''), face_data.get('image_path', '').replace('\\', '/'),
+                                 os.path.join(person_dir, face_data.get('image_filename', ''))]
+                        path = next((c for c in cands if c and os.path.exists(c)), None)
+                        if path is None:
+                            continue
+                        template_img = cv2.imread(path, cv2.IMREAD_GRAYSCALE)
+                        if template_img is not None:
+                            template_images.append({'image': template_img, 'width': face_data['width'],
+                                                    'height': face_data['height']})
+                self.models[person_name] = {'model_data': model_data, 'detection_data': detection_data,
+                                            'template_images': template_images, 'model_path': model_path}
                 print(f"  - {person_name}: {len(model_data['face_features'])} faces")
             except Exception as e:
                 print(f"  - Failed to load {person_name}: {e}")
         print(f"Successfully loaded {len(self.models)} model(s)")
         return len(self.models) > 0
+
+    # ---- template-matching detector (scan-template-v4.py:75-251) on the device
+    def is_detection_in_corner(self, detection, frame_width, frame_height, corner_threshold=0.15,
+                               border_threshold=0.05):
+        return template.is_detection_in_corner(detection, frame_width, frame_height, corner_threshold, border_threshold)
+
+    def non_max_suppression(self, detections, overlap_threshold=0.3):
+        return template.non_max_suppression(detections, overlap_threshold)
+
+    def calculate_overlap(self, det1, det2):
+        return template.calculate_overlap(det1, det2)
+
+    def template_match_all_models(self, frame):
+        """scan-template-v4.py:129-197: every template image of every person at the scales 0.8 / 1.0 / 1.2 against the
+        gray frame -- ONE batch of device launches for all of them (K6) instead of a matchTemplate call each; the
+        per-person selection (strict >, corner / border filter, 0.6 threshold) follows the reference's loop order."""
+        frame = np.asarray(frame)
+        frame_height, frame_width = frame.shape[:2]
+        persons = [(name, info) for name, info in self.models.items()
+                   if info.get('template_images') and info.get('detection_data')]
+        if not persons:
+            return []
+        key = tuple((name, len(info['template_images'])) for name, info in persons)
+        if getattr(self, '_tm_key', None) != key:
+            images = [t['image'] for _, info in persons for t in info['template_images']]
+            self._tm = template.TemplateMatcher(images)
+            self._tm_key = key
+        results = self._tm.match(frame)
+        detected_faces = []
+        first = 0
+        for name, info in persons:
+            n_t = len(info['template_images'])
+            mine = [r for r, (ti, _, _, _) in zip(results, self._tm.jobs) if first <= ti < first + n_t]
+            first += n_t
+            best = template.select_best_match(name, mine, frame_width, frame_height)
+            if best:
+                detected_faces.append(best)
+        return detected_faces
 
     # ---- single-crop interface (reference signatures)
     def extract_face_features(self, face_img, model_data):

@@ -203,6 +203,25 @@ int ef_match_tc_flags(const void* work, int32_t* flags3);
 int ef_match_reduce_device(const double* scores, const int64_t* indices, int32_t R, int32_t B, int32_t metric,
                            double* out_score, int64_t* out_index, ef_stream_t stream);
 
+/* ------------------------------------------------------------------------------- template-matching detector */
+/* cv2.matchTemplate(frame, template, cv2.TM_CCOEFF_NORMED) + cv2.minMaxLoc for n_jobs <= 48 templates against one gray
+ * frame -- the inner loop of MultiModelFaceScanner.template_match_all_models, scan-template-v4.py:147-174 (every
+ * template image of every person at the scales 0.8 / 1.0 / 1.2 is one job).
+ *   frame      device uint8 [H][ldf]
+ *   templates  device uint8, job i = th[i] rows of tw[i] bytes, contiguous, starting at templates + t_off[i]
+ *   t_off, tw, th, r_off   HOST arrays [n_jobs]; every template must fit the frame and be at most 1024 wide
+ *   result     device float32 or NULL; job i's map [H - th + 1][W - tw + 1] is written at result + r_off[i]
+ *   best_val   device double [n_jobs]   the map's maximum (float32 value, like minMaxLoc on the cv2 result)
+ *   best_xy    device int32 [n_jobs][2] its first position in row-major order (x, y) = minMaxLoc's max_loc
+ *   work       device scratch of ef_template_match_work_bytes(...) bytes
+ * All sums are exact integers (dp4a cross term, integral images); the score is common_matchTemplate's formula in
+ * float64, rounded to float32.  Agrees with cv2 to the accuracy of cv2's float32 DFT (about 1e-5). */
+size_t ef_template_match_work_bytes(int32_t W, int32_t H, int32_t n_jobs, const int32_t* tw, const int32_t* th);
+int ef_template_match_device(const uint8_t* frame, int64_t ldf, int32_t W, int32_t H, const uint8_t* templates,
+                             const int64_t* t_off, const int32_t* tw, const int32_t* th, int32_t n_jobs, float* result,
+                             const int64_t* r_off, double* best_val, int32_t* best_xy, void* work, size_t work_bytes,
+                             ef_stream_t stream);
+
 /* --------------------------------------------------------------------------------------------- PCA fit */
 /* manual_pca(data_matrix, n_components) -- useless/train.py:56-128 -- for uint8 crops.
  *   X host uint8 [N][ldx]; k = n_components (clamped to the number of eigenvalues like :114)
