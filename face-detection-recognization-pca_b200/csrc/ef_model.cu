@@ -50,6 +50,18 @@ struct ef_model {
   size_t pinned_bytes = 0;
   cudaStream_t copy_stream = nullptr;                 // owned: chunked H2D of the host path runs ahead of the kernels
   std::vector<cudaEvent_t> chunk_ev;                  // one per in-flight H2D chunk
+  // asynchronous host path (ef_model_submit_host / ef_model_wait_host): two batches in flight, each with its own crop
+  // buffer, page-locked result block and completion event
+  struct HostSlot {
+    ef::DevBuf x;
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+    cudaEvent_t done = nullptr;
+    std::vector<cudaEvent_t> chunk_ev;
+    int B = 0;
+    bool busy = false, want_proj = false, want_resid = false, want_label = false;
+  } hslot[2];
+  int next_slot = 0;
   int ld_acc = 0;
   int tc_mode = 2;                 // 0 dp4a, 1 tcgen05 stream-K + epilogue kernels, 2 single cluster kernel
   int last_path = 0;
@@ -237,6 +249,11 @@ void ef_model_destroy(ef_model_t* m) {
   if (m->pinned) cudaFreeHost(m->pinned);
   if (m->flush_ev) cudaEventDestroy(m->flush_ev);
   for (cudaEvent_t e : m->chunk_ev) cudaEventDestroy(e);
+  for (auto& hs : m->hslot) {
+    if (hs.pinned) cudaFreeHost(hs.pinned);
+    if (hs.done) cudaEventDestroy(hs.done);
+    for (cudaEvent_t e : hs.chunk_ev) cudaEventDestroy(e);
+  }
   for (cudaEvent_t e : m->ev_a) cudaEventDestroy(e);
   for (cudaEvent_t e : m->ev_b) cudaEventDestroy(e);
   delete m;
@@ -514,84 +531,107 @@ static int host_reserve(ef_model_t* m, int32_t B) {
   return EF_OK;
 }
 
-static int copy_results_back(ef_model_t* m, int32_t B, const ef_result_t* out, const ef_result_t& dev) {
-  // The caller's arrays are ordinary (pageable) host memory: a device->host copy straight into them is staged and
-  // synchronised by the driver one array at a time.  Copy everything into one page-locked block instead (asynchronous,
-  // back to back), synchronise once, then scatter with memcpy.
+// The caller's arrays are ordinary (pageable) host memory: a device->host copy straight into them is staged and
+// synchronised by the driver one array at a time.  Everything goes into one page-locked block instead (asynchronous, back
+// to back); after ONE synchronisation the block is scattered with memcpy.
+struct ResultBlock {
+  double *proj, *score, *resid;
+  int32_t *index, *label, *flag;
+};
+
+static size_t result_block_bytes(const ef_model_t* m, size_t nB) {
+  return sizeof(double) * nB * (size_t)m->k + sizeof(double) * nB * 2 + sizeof(int32_t) * nB * 2 + 64;
+}
+
+static ResultBlock carve(const ef_model_t* m, void* pinned, size_t nB) {
+  char* p = reinterpret_cast<char*>(pinned);
+  ResultBlock r;
+  r.proj = reinterpret_cast<double*>(p);   p += sizeof(double) * nB * (size_t)m->k;
+  r.score = reinterpret_cast<double*>(p);  p += sizeof(double) * nB;
+  r.resid = reinterpret_cast<double*>(p);  p += sizeof(double) * nB;
+  r.index = reinterpret_cast<int32_t*>(p); p += sizeof(int32_t) * nB;
+  r.label = reinterpret_cast<int32_t*>(p); p += sizeof(int32_t) * nB;
+  r.flag = reinterpret_cast<int32_t*>(p);
+  return r;
+}
+
+static int ensure_pinned(void** pinned, size_t* have, size_t need) {
+  if (need <= *have) return EF_OK;
+  if (*pinned) cudaFreeHost(*pinned);
+  *pinned = nullptr;
+  *have = 0;
+  EF_CUDA(cudaMallocHost(pinned, need));
+  *have = need;
+  return EF_OK;
+}
+
+static int enqueue_results(ef_model_t* m, int32_t B, bool proj, bool resid, bool label, const ef_result_t& dev,
+                           void* pinned) {
   cudaStream_t st = m->stream;
   const size_t nB = (size_t)B;
-  const size_t need = sizeof(double) * nB * (size_t)m->k + sizeof(double) * nB * 2 + sizeof(int32_t) * nB * 2 + 64;
-  if (need > m->pinned_bytes) {
-    if (m->pinned) cudaFreeHost(m->pinned);
-    m->pinned = nullptr;
-    m->pinned_bytes = 0;
-    EF_CUDA(cudaMallocHost(&m->pinned, need));
-    m->pinned_bytes = need;
-  }
-  char* p = reinterpret_cast<char*>(m->pinned);
-  double* h_proj = reinterpret_cast<double*>(p);   p += sizeof(double) * nB * (size_t)m->k;
-  double* h_score = reinterpret_cast<double*>(p);  p += sizeof(double) * nB;
-  double* h_resid = reinterpret_cast<double*>(p);  p += sizeof(double) * nB;
-  int32_t* h_index = reinterpret_cast<int32_t*>(p); p += sizeof(int32_t) * nB;
-  int32_t* h_label = reinterpret_cast<int32_t*>(p); p += sizeof(int32_t) * nB;
-  int32_t* h_flag = reinterpret_cast<int32_t*>(p);
-  if (out->proj) EF_CUDA(cudaMemcpyAsync(h_proj, dev.proj, sizeof(double) * nB * m->k, cudaMemcpyDeviceToHost, st));
-  if (out->score) EF_CUDA(cudaMemcpyAsync(h_score, dev.score, sizeof(double) * nB, cudaMemcpyDeviceToHost, st));
-  if (out->index) EF_CUDA(cudaMemcpyAsync(h_index, dev.index, sizeof(int32_t) * nB, cudaMemcpyDeviceToHost, st));
-  if (out->label) EF_CUDA(cudaMemcpyAsync(h_label, dev.label, sizeof(int32_t) * nB, cudaMemcpyDeviceToHost, st));
-  if (out->resid2) EF_CUDA(cudaMemcpyAsync(h_resid, dev.resid2, sizeof(double) * nB, cudaMemcpyDeviceToHost, st));
-  EF_CUDA(cudaMemcpyAsync(h_flag, m->status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-  EF_CUDA(cudaStreamSynchronize(st));
-  if (out->proj) memcpy(out->proj, h_proj, sizeof(double) * nB * m->k);
-  if (out->score) memcpy(out->score, h_score, sizeof(double) * nB);
-  if (out->index) memcpy(out->index, h_index, sizeof(int32_t) * nB);
-  if (out->label) memcpy(out->label, h_label, sizeof(int32_t) * nB);
-  if (out->resid2) memcpy(out->resid2, h_resid, sizeof(double) * nB);
-  if (*h_flag) {
+  const ResultBlock h = carve(m, pinned, nB);
+  if (proj) EF_CUDA(cudaMemcpyAsync(h.proj, dev.proj, sizeof(double) * nB * m->k, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(h.score, dev.score, sizeof(double) * nB, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(h.index, dev.index, sizeof(int32_t) * nB, cudaMemcpyDeviceToHost, st));
+  if (label) EF_CUDA(cudaMemcpyAsync(h.label, dev.label, sizeof(int32_t) * nB, cudaMemcpyDeviceToHost, st));
+  if (resid) EF_CUDA(cudaMemcpyAsync(h.resid, dev.resid2, sizeof(double) * nB, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(h.flag, m->status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  return EF_OK;
+}
+
+static int scatter_results(const ef_model_t* m, int32_t B, const ef_result_t* out, const void* pinned) {
+  const size_t nB = (size_t)B;
+  const ResultBlock h = carve(m, const_cast<void*>(pinned), nB);
+  if (out->proj) memcpy(out->proj, h.proj, sizeof(double) * nB * m->k);
+  if (out->score) memcpy(out->score, h.score, sizeof(double) * nB);
+  if (out->index) memcpy(out->index, h.index, sizeof(int32_t) * nB);
+  if (out->label) memcpy(out->label, h.label, sizeof(int32_t) * nB);
+  if (out->resid2) memcpy(out->resid2, h.resid, sizeof(double) * nB);
+  if (*h.flag) {
     ef::set_error_detail("tcgen05 projection pipeline timed out (mbarrier wait > 2 s)", cudaErrorLaunchTimeout);
     return EF_ERR_CUDA;
   }
   return EF_OK;
 }
 
-int ef_model_recognize_host(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
-                            const ef_result_t* out) {
-  if (m && B == 0) return EF_OK;
-  if (!m || !x || !out || B < 0 || ldx < m->D) return EF_ERR_INVALID;
-  if (out->resid2 && !m->with_residual) return EF_ERR_INVALID;
-  if (B == 0) return EF_OK;
-  EF_TRY(host_reserve(m, B));
+static int copy_results_back(ef_model_t* m, int32_t B, const ef_result_t* out, const ef_result_t& dev) {
+  EF_TRY(ensure_pinned(&m->pinned, &m->pinned_bytes, result_block_bytes(m, (size_t)B)));
+  EF_TRY(enqueue_results(m, B, out->proj != nullptr, out->resid2 != nullptr, out->label != nullptr, dev, m->pinned));
+  EF_CUDA(cudaStreamSynchronize(m->stream));
+  return scatter_results(m, B, out, m->pinned);
+}
+
+// Crops of a host batch -> xbuf in chunks on the copy stream, every chunk recognised as soon as it has landed (only the
+// last chunk's kernel is exposed behind the PCIe transfer, which dominates this path).
+static int enqueue_host_batch(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, double threshold, bool proj,
+                              bool resid, uint8_t* xbuf, std::vector<cudaEvent_t>& evs, ef_result_t* dev_out) {
   cudaStream_t st = m->stream;
   ef_result_t dev;
-  dev.proj = out->proj ? m->proj.as<double>() : nullptr;
+  dev.proj = proj ? m->proj.as<double>() : nullptr;
   dev.score = m->score.as<double>();
   dev.index = m->index32_dev.as<int32_t>();
   dev.label = m->label_dev.as<int32_t>();
-  dev.resid2 = out->resid2 ? m->resid_dev.as<double>() : nullptr;
-  // Large batches: the crops go up in chunks on a copy stream and every chunk is recognised as soon as it has landed,
-  // so only the last chunk's kernel is exposed behind the PCIe transfer (the host->device copy dominates this path).
+  dev.resid2 = resid ? m->resid_dev.as<double>() : nullptr;
   constexpr int kChunk = 1024;
   const int n_chunks = B >= 2 * kChunk ? (B + kChunk - 1) / kChunk : 1;
-  if (n_chunks > 1 && !m->copy_stream) EF_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-  while ((int)m->chunk_ev.size() < n_chunks) {
+  if (!m->copy_stream) EF_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+  while ((int)evs.size() < n_chunks + 1) {
     cudaEvent_t e;
     EF_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    m->chunk_ev.push_back(e);
+    evs.push_back(e);
   }
   for (int c = 0; c < n_chunks; ++c) {
     const int b0 = c * kChunk, rows = n_chunks == 1 ? B : std::min(kChunk, B - b0);
-    cudaStream_t cs = n_chunks == 1 ? st : m->copy_stream;
-    uint8_t* xd = m->x_dev.as<uint8_t>() + (size_t)b0 * m->x_ld;
+    cudaStream_t cs = m->copy_stream;
+    uint8_t* xd = xbuf + (size_t)b0 * m->x_ld;
     const uint8_t* xh = x + (size_t)b0 * ldx;
     if (ldx == m->x_ld) {
       EF_CUDA(cudaMemcpyAsync(xd, xh, (size_t)rows * ldx, cudaMemcpyHostToDevice, cs));
     } else {
       EF_CUDA(cudaMemcpy2DAsync(xd, m->x_ld, xh, ldx, m->D, rows, cudaMemcpyHostToDevice, cs));
     }
-    if (n_chunks > 1) {
-      EF_CUDA(cudaEventRecord(m->chunk_ev[c], cs));
-      EF_CUDA(cudaStreamWaitEvent(st, m->chunk_ev[c], 0));
-    }
+    EF_CUDA(cudaEventRecord(evs[c], cs));
+    EF_CUDA(cudaStreamWaitEvent(st, evs[c], 0));
     ef_result_t part;
     part.proj = dev.proj ? dev.proj + (size_t)b0 * m->k : nullptr;
     part.score = dev.score + b0;
@@ -600,7 +640,57 @@ int ef_model_recognize_host(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_
     part.resid2 = dev.resid2 ? dev.resid2 + b0 : nullptr;
     EF_TRY(ef_model_recognize_device(m, xd, m->x_ld, rows, threshold, &part, st));
   }
+  *dev_out = dev;
+  return EF_OK;
+}
+
+int ef_model_recognize_host(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
+                            const ef_result_t* out) {
+  if (m && B == 0) return EF_OK;
+  if (!m || !x || !out || B < 0 || ldx < m->D) return EF_ERR_INVALID;
+  if (out->resid2 && !m->with_residual) return EF_ERR_INVALID;
+  if (m->hslot[0].busy || m->hslot[1].busy) return EF_ERR_INVALID;     // asynchronous batches in flight: wait first
+  EF_TRY(host_reserve(m, B));
+  ef_result_t dev;
+  EF_TRY(enqueue_host_batch(m, x, ldx, B, threshold, out->proj != nullptr, out->resid2 != nullptr,
+                            m->x_dev.as<uint8_t>(), m->chunk_ev, &dev));
   return copy_results_back(m, B, out, dev);
+}
+
+int ef_model_submit_host(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, double threshold, int32_t want,
+                         int32_t* ticket) {
+  if (!m || !x || !ticket || B <= 0 || ldx < m->D) return EF_ERR_INVALID;
+  const bool proj = want & 1, resid = want & 2, label = want & 4;
+  if (resid && !m->with_residual) return EF_ERR_INVALID;
+  auto& hs = m->hslot[m->next_slot];
+  if (hs.busy) return EF_ERR_INVALID;                                  // both slots in flight: ef_model_wait_host first
+  EF_TRY(host_reserve(m, B));
+  EF_TRY(hs.x.ensure((size_t)B * m->x_ld));
+  EF_TRY(ensure_pinned(&hs.pinned, &hs.pinned_bytes, result_block_bytes(m, (size_t)B)));
+  if (!hs.done) EF_CUDA(cudaEventCreateWithFlags(&hs.done, cudaEventDisableTiming));
+  ef_result_t dev;
+  EF_TRY(enqueue_host_batch(m, x, ldx, B, threshold, proj, resid, hs.x.as<uint8_t>(), hs.chunk_ev, &dev));
+  EF_TRY(enqueue_results(m, B, proj, resid, label, dev, hs.pinned));
+  EF_CUDA(cudaEventRecord(hs.done, m->stream));
+  hs.B = B;
+  hs.busy = true;
+  hs.want_proj = proj;
+  hs.want_resid = resid;
+  hs.want_label = label;
+  *ticket = m->next_slot;
+  m->next_slot ^= 1;
+  return EF_OK;
+}
+
+int ef_model_wait_host(ef_model_t* m, int32_t ticket, const ef_result_t* out) {
+  if (!m || !out || ticket < 0 || ticket > 1) return EF_ERR_INVALID;
+  auto& hs = m->hslot[ticket];
+  if (!hs.busy) return EF_ERR_INVALID;
+  if ((out->proj && !hs.want_proj) || (out->resid2 && !hs.want_resid) || (out->label && !hs.want_label))
+    return EF_ERR_INVALID;
+  EF_CUDA(cudaEventSynchronize(hs.done));
+  hs.busy = false;
+  return scatter_results(m, hs.B, out, hs.pinned);
 }
 
 int ef_model_recognize_boxes_device(ef_model_t* m, const uint8_t* frames, int64_t frame_stride, int32_t pitch,

@@ -118,6 +118,37 @@ class Recognizer:
               "ef_model_recognize_host")
         return RecognitionResult(feats, score, index, label, resid)
 
+    def submit(self, crops, threshold=0.7, want_features=True, want_residual=None):
+        """Asynchronous recognize(): enqueues copy-in, kernels and copy-out and returns a ticket for wait().  At most
+        two batches may be in flight; the crops array must stay alive (and should be page-locked, e.g. a pinned torch
+        tensor's .numpy()) until the matching wait().  The upload of batch i+1 overlaps the kernels and the result copy
+        of batch i."""
+        x = np.asarray(crops)
+        if x.dtype != np.uint8 or x.ndim != 2 or x.shape[1] != self.D:
+            raise ValueError(f"crops must be uint8 [B, {self.D}], got {x.dtype} {x.shape}")
+        if x.strides[1] != 1:
+            x = np.ascontiguousarray(x)
+        B = x.shape[0]
+        want_residual = self.with_residual if want_residual is None else want_residual
+        want = (1 if want_features else 0) | (2 if want_residual else 0) | 4
+        ticket = C.c_int32(-1)
+        ldx = x.strides[0] if B > 1 else self.D
+        check(self._L.ef_model_submit_host(self._h, _ptr(x), ldx, B, float(threshold), want, C.byref(ticket)),
+              "ef_model_submit_host")
+        return (ticket.value, B, bool(want_features), bool(want_residual), x)      # x kept alive by the ticket
+
+    def wait(self, ticket):
+        """Blocks until the batch behind `ticket` is done; returns its RecognitionResult (same values as recognize())."""
+        slot, B, want_features, want_residual, _x = ticket
+        feats = np.empty((B, self.k), dtype=np.float64) if want_features else None
+        score = np.empty(B, dtype=np.float64)
+        index = np.empty(B, dtype=np.int32)
+        label = np.empty(B, dtype=np.int32)
+        resid = np.empty(B, dtype=np.float64) if want_residual else None
+        res = Result(_ptr(feats), _ptr(score), _ptr(index), _ptr(label), _ptr(resid))
+        check(self._L.ef_model_wait_host(self._h, slot, C.byref(res)), "ef_model_wait_host")
+        return RecognitionResult(feats, score, index, label, resid)
+
     def recognize_boxes(self, frames, boxes, side, threshold=0.7, want_features=True, want_residual=None):
         """frames: uint8 [F, H, W] gray or [F, H, W, 3] BGR (or a single frame); boxes: int [B, 4] (x, y, w, h) or
         [B, 5] (frame, x, y, w, h).  K1 + K2 through host buffers."""

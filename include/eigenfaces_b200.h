@@ -155,6 +155,16 @@ int ef_model_recognize_host(ef_model_t* model, const uint8_t* x, int64_t ldx, in
 int ef_model_submit_device(ef_model_t* model, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
                            const ef_result_t* out, ef_stream_t stream);
 int ef_model_flush_device(ef_model_t* model, ef_stream_t stream);
+/* Asynchronous form of ef_model_recognize_host for a serving loop: at most two batches in flight.  submit enqueues the
+ * chunked host->device copy, the kernels and the device->host copy of the results and returns a ticket (0 or 1); wait
+ * blocks until that batch is done and fills the caller's arrays.  The copy of batch i+1 overlaps the kernels and the
+ * result copy of batch i, so a steady stream of batches runs at the PCIe rate.  x must stay valid (and should be
+ * page-locked) until the matching wait.  want: bit 0 = features, bit 1 = resid2, bit 2 = labels (score and index are
+ * always produced); wait may only ask for what submit requested.  Same results as ef_model_recognize_host. */
+int ef_model_submit_host(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, double threshold, int32_t want,
+                         int32_t* ticket);
+int ef_model_wait_host(ef_model_t* m, int32_t ticket, const ef_result_t* out);
+
 /* Same, starting from frames + boxes (K1 then K2).  Host variant copies the frames and boxes in. */
 int ef_model_recognize_boxes_device(ef_model_t* model, const uint8_t* frames, int64_t frame_stride, int32_t pitch,
                                     int32_t width, int32_t height, int32_t channels, int32_t n_frames,

@@ -497,3 +497,36 @@ def test_split_k_slabs_equal_stream_k_atomics():
                 assert np.array_equal(getattr(a, f), getattr(other, f)), (D, k, n, B, f)
         assert rec.pipeline_timeouts() == 0
         rec.close()
+
+
+def test_async_host_submit_wait_equals_recognize():
+    """ef_model_submit_host / ef_model_wait_host: two batches in flight, results identical to the synchronous call;
+    a third submit without a wait, a wait on an idle ticket and a synchronous call with batches in flight are refused."""
+    torch = require_gpu()
+    rng = np.random.default_rng(31)
+    D, k, n = 10000, 10, 300
+    E = np.linalg.qr(rng.normal(size=(D, k)))[0]
+    rec = ef.Recognizer(E, rng.uniform(40, 210, D), rng.normal(size=(n, k)) * 50, metric=ef.METRIC_COSINE_G1,
+                        labels=rng.integers(0, 4, n))
+    batches = [torch.from_numpy(rng.integers(0, 256, (B, D), dtype=np.uint8)).pin_memory().numpy()
+               for B in (4096, 700, 2500, 1, 4096)]
+    want = [rec.recognize(x, 0.3) for x in batches]
+    tickets = [rec.submit(batches[0], 0.3), rec.submit(batches[1], 0.3)]
+    with pytest.raises(ef.EigenfacesError):
+        rec.submit(batches[2], 0.3)                               # both slots busy
+    with pytest.raises(ef.EigenfacesError):
+        rec.recognize(batches[2], 0.3)                            # synchronous call while batches are in flight
+    got = []
+    for i in range(len(batches)):
+        got.append(rec.wait(tickets[i % 2]))
+        if i + 2 < len(batches):
+            tickets[i % 2] = rec.submit(batches[i + 2], 0.3)
+    for a, b in zip(want, got):
+        for f in ("features", "score", "index", "label", "resid2"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    with pytest.raises(ef.EigenfacesError):
+        rec.wait(tickets[0])                                      # nothing in flight behind this ticket any more
+    t = rec.submit(batches[1], 0.3, want_features=False, want_residual=False)
+    r = rec.wait(t)
+    assert r.features is None and r.resid2 is None and np.array_equal(r.label, want[1].label)
+    rec.close()
