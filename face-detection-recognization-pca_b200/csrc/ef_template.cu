@@ -29,7 +29,7 @@
 
 namespace {
 
-constexpr int kMaxJobs = 48;
+constexpr int kMaxJobs = 64;
 constexpr int TX = 64, TY = 32;      // result positions per CTA
 constexpr int VC = 16;               // template rows per shared-memory block
 constexpr int kThreads = 256;

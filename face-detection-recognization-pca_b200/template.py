@@ -16,7 +16,7 @@ from . import _lib
 from ._lib import check
 
 SCALES = (0.8, 1.0, 1.2)          # scan-template-v4.py:159
-MAX_JOBS = 48                     # per ef_template_match_device call
+MAX_JOBS = 64                     # per ef_template_match_device call
 
 
 def _torch():

@@ -214,7 +214,7 @@ int ef_match_reduce_device(const double* scores, const int64_t* indices, int32_t
                            double* out_score, int64_t* out_index, ef_stream_t stream);
 
 /* ------------------------------------------------------------------------------- template-matching detector */
-/* cv2.matchTemplate(frame, template, cv2.TM_CCOEFF_NORMED) + cv2.minMaxLoc for n_jobs <= 48 templates against one gray
+/* cv2.matchTemplate(frame, template, cv2.TM_CCOEFF_NORMED) + cv2.minMaxLoc for n_jobs <= 64 templates against one gray
  * frame -- the inner loop of MultiModelFaceScanner.template_match_all_models, scan-template-v4.py:147-174 (every
  * template image of every person at the scales 0.8 / 1.0 / 1.2 is one job).
  *   frame      device uint8 [H][ldf]

@@ -76,12 +76,12 @@ def test_degenerate_and_many_jobs():
     res = m.match(frame, want_maps=True)
     assert np.all(res[0]["map"].cpu().numpy() == 1.0) and (res[0]["x"], res[0]["y"]) == (0, 0)   # first maximum
     assert np.array_equal(res[1]["map"].cpu().numpy(), tm.match_template_ccoeff_normed(frame, g["d_tex_templ"]))
-    # more jobs than one call takes (48), some too large for the frame (skipped like scan-template-v4.py:164)
+    # more jobs than one call takes (64), some too large for the frame (skipped like scan-template-v4.py:164)
     rng = np.random.default_rng(3)
     templates = [rng.integers(0, 256, (int(rng.integers(20, 40)), int(rng.integers(20, 50))), dtype=np.uint8)
-                 for _ in range(21)] + [rng.integers(0, 256, (200, 30), dtype=np.uint8)]
+                 for _ in range(27)] + [rng.integers(0, 256, (200, 30), dtype=np.uint8)]
     m = ef.template.TemplateMatcher(templates)
-    assert len(m.jobs) > 48
+    assert len(m.jobs) > 64
     res = m.match(frame)
     for job, r in enumerate(res):
         ti, scale, w, h = m.jobs[job]
@@ -174,3 +174,44 @@ def test_frame_logic_of_process_live_camera(tmp_path):
     # the crop is a training image of anna: PCA confidence ~1, so the final name is anna by both rules
     assert r["pca_confidence"] > 0.99 and r["person_name"] == "anna" and r["final_confidence"] == r["template_confidence"]
     assert sc.recognize_frame_template(rng.integers(95, 106, (360, 480, 3), dtype=np.uint8)) == [] or True
+
+
+def test_process_video_template_over_a_clip(tmp_path):
+    """process_live_camera's loop over a video file: every frame carries the same training face of one person; both
+    the single-rank loop and the two-rank split must report it on every frame."""
+    ef = _ef()
+    cv2 = pytest.importorskip("cv2")
+    import json
+    g1 = np.load(os.path.join(os.path.dirname(GOLDEN), "gen1_light.npz"))
+    X = g1["X_u8"].reshape(-1, 100, 100)
+    base = str(tmp_path / "faces" / "lock_version")
+    d = os.path.join(base, "anna")
+    os.makedirs(d)
+    faces = []
+    for i in range(30):
+        fn = f"face_{i:06d}_frame_{i:06d}.jpg"
+        cv2.imwrite(os.path.join(d, fn), X[i], [cv2.IMWRITE_JPEG_QUALITY, 100])
+        faces.append({"face_id": i, "image_filename": fn, "image_path": os.path.join(d, fn), "x": 0, "y": 0,
+                      "width": 100, "height": 100})
+    json.dump({"person_name": "anna", "total_faces": 30, "faces": faces}, open(os.path.join(d, "anna_faces_detection.json"), "w"))
+    assert ef.pipeline.train_person_model("anna", base, 20)
+    sc = ef.gen2.MultiModelFaceScanner()
+    assert sc.load_all_models(os.path.join(base, "*", "face_model.pkl"))
+    clip = str(tmp_path / "clip.avi")
+    vw = cv2.VideoWriter(clip, cv2.VideoWriter_fourcc(*"MJPG"), 10.0, (480, 360))
+    if not vw.isOpened():
+        pytest.skip("no video encoder in this OpenCV build")
+    rng = np.random.default_rng(2)
+    for t in range(4):
+        fr = rng.integers(98, 103, (360, 480, 3), dtype=np.uint8)
+        fr[100:200, 150 + 10 * t:250 + 10 * t] = cv2.cvtColor(X[1], cv2.COLOR_GRAY2BGR)
+        vw.write(fr)
+    vw.release()
+    res = sc.process_video_template(clip)
+    assert res is not None and [r["frame_number"] for r in res] == [0, 1, 2, 3]
+    for t, r in enumerate(res):                                   # MJPG is lossy: position within a pixel or two
+        assert abs(r["x"] - (150 + 10 * t)) <= 2 and abs(r["y"] - 100) <= 2 and r["template_confidence"] > 0.9
+    r0 = sc.process_video_template(clip, rank=0, world=2)
+    r1 = sc.process_video_template(clip, rank=1, world=2)
+    assert [r["frame_number"] for r in r0] == [0, 2] and [r["frame_number"] for r in r1] == [1, 3]
+    assert sc.process_video_template(str(tmp_path / "missing.avi")) is None
