@@ -171,6 +171,75 @@ __global__ void rowsumsq_kernel(const uint8_t* __restrict__ X, int64_t ldx, int 
   }
 }
 
+// Weighted form for aligned rows with D % 16 == 0 (the standardised 64 x 64 models).  The warp-per-row kernel above is
+// latency bound there (one dependent chain of D / 32 steps per warp, 22 us for 4096 x 4096).  Here a thread owns 16
+// consecutive pixels of a 4096-pixel strip with their 16 weights in registers and the CTA walks over kRowsW rows, eight
+// at a time: the eight 16-byte crop loads of a thread are independent and in flight together, x^2 is formed in integers
+// (exact) and enters one fma per pixel (two interleaved chains), the eight warp reductions interleave.  Fixed order:
+// warp tree, strips in sequence, warps in sequence -- every path of the library gets its weighted sum of squares here.
+constexpr int kRowsW = 16;
+// exact uint32 -> double without the conversion pipe: 2^52 + v has v in its low mantissa word
+__device__ __forceinline__ double u32_to_double(unsigned v) {
+  return __hiloint2double(0x43300000, (int)v) - 4503599627370496.0;
+}
+__global__ void __launch_bounds__(256, 2)
+rowsumsq_weighted_kernel(const uint8_t* __restrict__ X, int64_t ldx, int B, int D, const double* __restrict__ qq,
+                         double* __restrict__ out) {
+  __shared__ double part[kRowsW][8];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int row0 = blockIdx.x * kRowsW;
+  for (int base = 0; base < D; base += 4096) {
+    const int d0 = base + 16 * tid;
+    const bool live = d0 < D;                                   // D % 16 == 0: a live thread has all 16 pixels
+    double w[16];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const double2 t = live ? __ldg(reinterpret_cast<const double2*>(qq + d0) + j) : make_double2(0.0, 0.0);
+      w[2 * j] = t.x;
+      w[2 * j + 1] = t.y;
+    }
+#pragma unroll
+    for (int r0 = 0; r0 < kRowsW; r0 += 8) {
+      uint4 v[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {                              // rows past the batch re-read the last row (discarded)
+        const int row = min(row0 + r0 + r, B - 1);
+        v[r] = live ? __ldg(reinterpret_cast<const uint4*>(X + (int64_t)row * ldx + d0)) : make_uint4(0u, 0u, 0u, 0u);
+      }
+      double s[8];
+#pragma unroll
+      for (int r = 0; r < 8; ++r) {
+        const unsigned word[4] = {v[r].x, v[r].y, v[r].z, v[r].w};
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const unsigned b0 = word[j] & 255u, b1 = (word[j] >> 8) & 255u, b2 = (word[j] >> 16) & 255u, b3 = word[j] >> 24;
+          s0 = fma(u32_to_double(b0 * b0), w[4 * j], s0);
+          s1 = fma(u32_to_double(b1 * b1), w[4 * j + 1], s1);
+          s0 = fma(u32_to_double(b2 * b2), w[4 * j + 2], s0);
+          s1 = fma(u32_to_double(b3 * b3), w[4 * j + 3], s1);
+        }
+        s[r] = s0 + s1;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) s[r] += __shfl_xor_sync(0xffffffffu, s[r], o);
+      if (lane == 0) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) part[r0 + r][warp] = base == 0 ? s[r] : part[r0 + r][warp] + s[r];
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < kRowsW && row0 + tid < B) {
+    double s = part[tid][0];
+#pragma unroll
+    for (int w8 = 1; w8 < 8; ++w8) s += part[tid][w8];
+    out[row0 + tid] = s;
+  }
+}
+
 template <int CN>
 int launch_dp4a(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int32_t* acc,
                 int ld_acc, cudaStream_t stream) {
@@ -217,6 +286,11 @@ int row_sumsq(const uint8_t* X, int64_t ldx, int B, int D, const double* qq, dou
   if (B <= 0) return EF_OK;
   const int threads = 256;
   const int grid = (int)ceil_div((int64_t)B * 32, threads);
+  if (qq && D % 16 == 0 && (ldx & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
+      (reinterpret_cast<uintptr_t>(qq) & 15) == 0) {
+    EF_LAUNCH(rowsumsq_weighted_kernel, (unsigned)ceil_div(B, kRowsW), 256, 0, stream, X, ldx, B, D, qq, out);
+    return EF_OK;
+  }
   EF_LAUNCH(rowsumsq_kernel, grid, threads, 0, stream, X, ldx, B, D, qq, out);
   return EF_OK;
 }
