@@ -308,8 +308,13 @@ int launch_q(const MsArgs& a, cudaStream_t stream) {
 
 template <int METRIC>
 int launch(const MsArgs& a, cudaStream_t stream) {
-  // 32 queries per CTA while the query rows fit next to the gallery blocks, 16 for the largest k
-  return smem_bytes(32, a.kc_total) <= 200 * 1024 ? launch_q<METRIC, 8>(a, stream) : launch_q<METRIC, 4>(a, stream);
+  // 32 queries per CTA while the query rows fit next to the gallery blocks and the sweep is long enough to amortise the
+  // block staging; 16 for the largest k and for short sweeps (<= 6 blocks: twice the CTAs, two per SM, so that one
+  // CTA's prologue and barriers overlap the other's arithmetic -- measured 5 us faster on the 229 x 50 gallery,
+  // 4 us slower on the 178 x 178 one; 8 queries per CTA is slower again)
+  const int n_stages = (int)ef::ceil_div(a.n, GT) * (a.kc_total / KC);
+  const bool wide = smem_bytes(32, a.kc_total) <= 200 * 1024 && n_stages > 6;
+  return wide ? launch_q<METRIC, 8>(a, stream) : launch_q<METRIC, 4>(a, stream);
 }
 
 }  // namespace
