@@ -52,7 +52,7 @@ __device__ __forceinline__ void axis_coeff(int d, int src, double scale, bool cl
   s1 = min(max(s + 1, 0), src - 1);
 }
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 3)
 preprocess_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int pitch, int width, int height,
                   int channels, int n_frames, const ef_box_t* __restrict__ boxes, int n_boxes, int dw, int dh,
                   uint8_t* __restrict__ out, int64_t out_stride, int* __restrict__ bad_boxes, int stage_bytes,
@@ -264,6 +264,9 @@ extern "C" int ef_preprocess(const uint8_t* frames, int64_t frame_stride, int32_
   static bool configured = false;
   if (!configured) {
     EF_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    // three CTAs of 69 KB per SM need the largest shared-memory carve-out (the default heuristic settles for two)
+    EF_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared));
     configured = true;
   }
   const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>(8, (220 * 1024) / (int64_t)(smem + 1024)));
