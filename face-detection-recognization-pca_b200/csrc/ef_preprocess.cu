@@ -52,7 +52,7 @@ __device__ __forceinline__ void axis_coeff(int d, int src, double scale, bool cl
   s1 = min(max(s + 1, 0), src - 1);
 }
 
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, 4)
 preprocess_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int pitch, int width, int height,
                   int channels, int n_frames, const ef_box_t* __restrict__ boxes, int n_boxes, int dw, int dh,
                   uint8_t* __restrict__ out, int64_t out_stride, int* __restrict__ bad_boxes, int stage_bytes,
@@ -256,15 +256,15 @@ extern "C" int ef_preprocess(const uint8_t* frames, int64_t frame_stride, int32_
   if (pitch < width * channels || out_stride < (int64_t)dw * dh) return EF_ERR_INVALID;
   if (dw > kMaxSide || dh > kMaxSide) return EF_ERR_UNSUPPORTED;
   if (n_boxes == 0) return EF_OK;
-  // coefficient tables + a 64 KB staging buffer for the source rows of a band: three CTAs per SM
-  int kStageBytes = 64 * 1024;                      // three CTAs per SM; a 250 x 250 ROI fits one band
+  // coefficient tables + a 48 KB staging buffer for the source rows of a band: four CTAs per SM (64 registers)
+  int kStageBytes = 48 * 1024;                      // four CTAs per SM; a 220 x 220 ROI fits one band
   if (const char* e = getenv("EF_PRE_STAGE_KB")) { const int v = atoi(e); if (v >= 8 && v <= 96) kStageBytes = v * 1024; }
   const size_t tables = sizeof(int) * (4 * (size_t)(dw + dh) + 4);
   const size_t smem = tables + kStageBytes;
   static bool configured = false;
   if (!configured) {
     EF_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-    // three CTAs of 69 KB per SM need the largest shared-memory carve-out (the default heuristic settles for two)
+    // four CTAs of 52 KB per SM need the largest shared-memory carve-out (the default heuristic settles for less)
     EF_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
     configured = true;
