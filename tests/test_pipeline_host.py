@@ -54,3 +54,34 @@ def test_script_shims_expose_the_reference_cli():
         for f in flags:
             assert f in res.stdout
     assert os.path.exists(os.path.join(ROOT, "scripts", "train-v5.py"))
+
+
+def test_scanner_loads_templates_like_the_reference(tmp_path):
+    """load_all_models (scan-template-v4.py:17-74) without a GPU: the model pickle, the detection JSON and the first
+    five face crops as gray templates -- found through image_path, through image_path with normalised separators
+    (detection-v4.py writes Windows paths) or through image_filename inside the person's directory."""
+    import pickle
+    rng = np.random.default_rng(1)
+    base = str(tmp_path / "faces" / "lock_version")
+    d = _write_person(base, "carol", 7, rng)
+    assert ef.pipeline.generate_detection_json_for_person("carol", d)
+    info_path = os.path.join(d, "carol_faces_detection.json")
+    info = json.load(open(info_path))
+    for face in info["faces"]:                                    # what the reference's Windows run would have written
+        face["image_path"] = "faces\\lock_version\\carol\\" + face["image_filename"]
+    json.dump(info, open(info_path, "w"))
+    pickle.dump({"face_features": np.zeros((7, 3)), "face_labels": np.zeros(7, int), "person_id_map": {"carol": 0}},
+                open(os.path.join(d, "face_model.pkl"), "wb"))
+    sc = ef.gen2.MultiModelFaceScanner()
+    assert sc.load_all_models(os.path.join(base, "*", "face_model.pkl"))
+    m = sc.models["carol"]
+    assert len(m["template_images"]) == 5 and len(m["detection_data"]["faces"]) == 7
+    t = m["template_images"][0]
+    assert t["image"].ndim == 2 and t["image"].dtype == np.uint8 and (t["width"], t["height"]) == (87, 80)
+    # no detection JSON -> no templates, like the reference; the detector then reports nothing for that person
+    os.remove(info_path)
+    sc2 = ef.gen2.MultiModelFaceScanner()
+    assert sc2.load_all_models(os.path.join(base, "*", "face_model.pkl"))
+    assert sc2.models["carol"]["template_images"] == [] and sc2.models["carol"]["detection_data"] is None
+    assert sc2.template_match_all_models(np.zeros((120, 160), np.uint8)) == []
+    assert not ef.gen2.MultiModelFaceScanner().load_all_models(str(tmp_path / "nothing" / "*.pkl"))
