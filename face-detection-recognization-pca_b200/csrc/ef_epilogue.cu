@@ -292,9 +292,9 @@ finalize_slabs_kernel(const int32_t* __restrict__ part, int splits, long long sl
                       int kq, int S, const int32_t* __restrict__ col_exp, const double* __restrict__ bias,
                       double* __restrict__ proj, int64_t ldp, double* __restrict__ xu_out) {
   // flattened (crop, column) index: every lane is busy whatever kq is; runs of kq consecutive lanes read one crop
-  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  const int b = (int)(idx / kq);
-  const int c = (int)(idx - (long long)b * kq);
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;          // B * kq < 2^31 (checked by the launcher)
+  const int b = (int)(idx / (unsigned)kq);                             // 32-bit division: the 64-bit one costs more
+  const int c = (int)(idx - (unsigned)b * (unsigned)kq);               // than the eight loads of the thread
   if (b >= B) return;
   int32_t plane[8];
 #pragma unroll
@@ -378,7 +378,7 @@ int project_finalize_slabs(const int32_t* part, int splits, int ld_part, int B, 
                            const int32_t* col_exp, const double* bias, double* proj, int64_t ldp, double* resid2,
                            cudaStream_t stream) {
   if (B <= 0) return EF_OK;
-  if (S > 8) return EF_ERR_INVALID;
+  if (S > 8 || (int64_t)B * kq >= (1ll << 31) - 256) return EF_ERR_INVALID;
   const unsigned grid = (unsigned)ceil_div((int64_t)B * kq, 256);
   EF_LAUNCH(finalize_slabs_kernel, grid, 256, 0, stream, part, splits, (long long)B * ld_part, ld_part, B, k, kq, S,
             col_exp, bias, proj, ldp, (kq > k) ? resid2 : nullptr);
