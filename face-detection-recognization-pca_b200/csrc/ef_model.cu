@@ -244,6 +244,10 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
 
 void ef_model_destroy(ef_model_t* m) {
   if (!m) return;
+  // batches submitted with ef_model_submit_host / _device may still be in flight: drain before the buffers go away
+  if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
+  if (m->stream) cudaStreamSynchronize(m->stream);
+  if (m->pending.B > 0) cudaStreamSynchronize(m->pending.stream);
   if (m->stream) cudaStreamDestroy(m->stream);
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->pinned) cudaFreeHost(m->pinned);

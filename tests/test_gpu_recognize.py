@@ -530,3 +530,23 @@ def test_async_host_submit_wait_equals_recognize():
     r = rec.wait(t)
     assert r.features is None and r.resid2 is None and np.array_equal(r.label, want[1].label)
     rec.close()
+
+
+def test_close_with_batches_in_flight():
+    """Destroying a model while submitted batches are still running must drain them first (no use-after-free)."""
+    torch = require_gpu()
+    rng = np.random.default_rng(5)
+    D, k, n = 4096, 12, 200
+    E = np.linalg.qr(rng.normal(size=(D, k)))[0]
+    for _ in range(3):
+        rec = ef.Recognizer(E, rng.uniform(40, 210, D), rng.normal(size=(n, k)) * 50, metric=ef.METRIC_COSINE_SK)
+        x = torch.from_numpy(rng.integers(0, 256, (4096, D), dtype=np.uint8)).pin_memory().numpy()
+        rec.submit(x, 0.3)
+        rec.submit(x, 0.3)
+        xd = torch.from_numpy(x).cuda()
+        rec.submit_device(xd, 0.3)
+        rec.close()                                               # never waited for
+    torch.cuda.synchronize()
+    rec = ef.Recognizer(E, rng.uniform(40, 210, D), rng.normal(size=(n, k)) * 50, metric=ef.METRIC_COSINE_SK)
+    assert rec.recognize(x[:8], 0.3).index.shape == (8,)
+    rec.close()
