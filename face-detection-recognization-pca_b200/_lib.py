@@ -70,6 +70,7 @@ SIGNATURES = {
                                                   c_i32, c_i32, c_i32, c_dbl, C.POINTER(Result), c_void]),
     "ef_model_recognize_boxes_host": (C.c_int, [c_void, c_void, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_void,
                                                 c_i32, c_i32, c_i32, c_dbl, C.POINTER(Result)]),
+    "ef_model_bad_boxes": (C.c_int, [c_void, c_void, p_i32]),
     "ef_match_work_bytes": (C.c_size_t, [c_i32, c_i64]),
     "ef_gallery_prepare_device": (C.c_int, [c_void, c_i64, c_i64, c_i32, c_i32, c_void, c_i64, c_void, c_void]),
     "ef_match_device": (C.c_int, [c_void, c_i64, c_i32, c_i32, c_void, c_i64, c_void, c_i64, c_i64, c_i32, c_void,
@@ -108,9 +109,9 @@ def lib():
     """The loaded library (built on first use when the .so is missing and nvcc is available)."""
     global _LIB
     if _LIB is None:
-        path = _build.LIB
-        if not os.path.exists(path):
-            path = _build.build()
+        # content-hash check against the build manifest: a library older than csrc/ or the header is rebuilt (the
+        # build is incremental and serialised across processes by a file lock), never loaded stale
+        path = _build.build()
         handle = C.CDLL(path)
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError here == header / library drift
@@ -124,7 +125,8 @@ def lib():
 
 def check(status, where):
     if status != EF_OK:
-        detail = lib().ef_last_error_detail().decode() if status == EF_ERR_CUDA else ""
+        with_detail = status == EF_ERR_CUDA or (status == EF_ERR_INVALID and "boxes" in where)
+        detail = lib().ef_last_error_detail().decode() if with_detail else ""
         raise EigenfacesError(status, where, detail)
 
 

@@ -106,9 +106,12 @@ void slice_column(const std::vector<double>& w, int D, int S, int e, int8_t* pla
   }
 }
 
-int upload(ef::DevBuf& buf, const void* src, size_t bytes) {
+// Uploads run on the stream that consumes the buffer (the model's own non-blocking stream does not order against the
+// legacy default stream).  The host source is pageable: cudaMemcpyAsync stages it before returning, and create()
+// synchronises the stream before any of the sources go out of scope.
+int upload(ef::DevBuf& buf, const void* src, size_t bytes, cudaStream_t st) {
   EF_TRY(buf.ensure(bytes ? bytes : 16));
-  if (bytes) EF_CUDA(cudaMemcpy(buf.p, src, bytes, cudaMemcpyHostToDevice));
+  if (bytes) EF_CUDA(cudaMemcpyAsync(buf.p, src, bytes, cudaMemcpyHostToDevice, st));
   return EF_OK;
 }
 
@@ -140,8 +143,13 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
   const int nc_pad = (int)ef::round_up(m->NC, 16);
   m->nc_pad = nc_pad;
 
+  {
+    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { ef::set_error_detail("cudaStreamCreate", e); delete m; return EF_ERR_CUDA; }
+  }
   // ---- host-side preparation (float64, exact digit extraction)
   std::vector<double> t(D), inv_s(D, 1.0);
+  std::vector<double> qq;
   for (int d = 0; d < D; ++d) {
     const double s = desc->scale ? desc->scale[d] : 1.0;
     const double pm = desc->pca_mean ? desc->pca_mean[d] : 0.0;
@@ -164,7 +172,7 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
     }
     double mx = 0.0;
     for (int d = 0; d < D; ++d) {
-      if (!std::isfinite(col[d])) { delete m; return EF_ERR_INVALID; }
+      if (!std::isfinite(col[d])) { ef_model_destroy(m); return EF_ERR_INVALID; }
       mx = std::fmax(mx, std::fabs(col[d]));
     }
     int e = 0;
@@ -188,24 +196,26 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
     }
     m->c0 = (double)c0;
     if (desc->scale) {
-      std::vector<double> qq(D);
+      qq.resize(D);
       for (int d = 0; d < D; ++d) qq[d] = 1.0 / (desc->scale[d] * desc->scale[d]);
-      int st = upload(m->qq, qq.data(), sizeof(double) * D);
-      if (st != EF_OK) { delete m; return st; }
+      int st = upload(m->qq, qq.data(), sizeof(double) * D, m->stream);
+      if (st != EF_OK) { ef_model_destroy(m); return st; }
     }
   }
 
-  int st = upload(m->wq, wq.data(), wq.size());
-  if (st == EF_OK) st = upload(m->col_exp, col_exp.data(), sizeof(int32_t) * col_exp.size());
-  if (st == EF_OK) st = upload(m->bias, bias.data(), sizeof(double) * bias.size());
-  if (st == EF_OK && desc->labels) st = upload(m->labels, desc->labels, sizeof(int32_t) * (size_t)desc->n_gallery);
+  int st = upload(m->wq, wq.data(), wq.size(), m->stream);
+  if (st == EF_OK) st = upload(m->col_exp, col_exp.data(), sizeof(int32_t) * col_exp.size(), m->stream);
+  if (st == EF_OK) st = upload(m->bias, bias.data(), sizeof(double) * bias.size(), m->stream);
+  if (st == EF_OK && desc->labels)
+    st = upload(m->labels, desc->labels, sizeof(int32_t) * (size_t)desc->n_gallery, m->stream);
   // gallery: upload raw (compacted to ld = k), prepare on the device
   ef::DevBuf raw;
+  std::vector<double> g;
   if (st == EF_OK) {
-    std::vector<double> g((size_t)desc->n_gallery * k);
+    g.resize((size_t)desc->n_gallery * k);
     for (int64_t j = 0; j < desc->n_gallery; ++j)
       memcpy(&g[(size_t)j * k], desc->gallery + j * desc->gallery_ld, sizeof(double) * k);
-    st = upload(raw, g.data(), sizeof(double) * g.size());
+    st = upload(raw, g.data(), sizeof(double) * g.size(), m->stream);
   }
   m->kpad = ef::fused_epilogue_supported(k, desc->n_gallery) ? ef::fused_epilogue_kpad(k) : k;
   const size_t gp_bytes = sizeof(double) * (size_t)desc->n_gallery * m->kpad;
@@ -214,14 +224,11 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
   if (st == EF_OK) st = m->gnorm.ensure(gn_bytes);
   if (st == EF_OK) st = m->ginv.ensure(gn_bytes);
   if (st == EF_OK) {
-    cudaError_t e = cudaMemset(m->gp.p, 0, gp_bytes);
-    if (e == cudaSuccess) e = cudaMemset(m->gnorm.p, 0, gn_bytes);
-    if (e == cudaSuccess) e = cudaMemset(m->ginv.p, 0, gn_bytes);
-    if (e != cudaSuccess) { ef::set_error_detail("cudaMemset", e); st = EF_ERR_CUDA; }
-  }
-  if (st == EF_OK) {
-    cudaError_t e = cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking);
-    if (e != cudaSuccess) { ef::set_error_detail("cudaStreamCreate", e); st = EF_ERR_CUDA; }
+    // zero padding of the prepared gallery: on the stream gallery_prepare runs on, so that it cannot race the kernel
+    cudaError_t e = cudaMemsetAsync(m->gp.p, 0, gp_bytes, m->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->gnorm.p, 0, gn_bytes, m->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(m->ginv.p, 0, gn_bytes, m->stream);
+    if (e != cudaSuccess) { ef::set_error_detail("cudaMemsetAsync", e); st = EF_ERR_CUDA; }
   }
   if (st == EF_OK)
     st = ef::gallery_prepare(raw.as<double>(), k, desc->n_gallery, k, m->metric, m->gp.as<double>(), m->kpad,
@@ -330,6 +337,9 @@ int ef_model_reserve(ef_model_t* m, int32_t max_batch) {
   EF_TRY(m->score.ensure(sizeof(double) * B));
   EF_TRY(m->index64.ensure(sizeof(int64_t) * B));
   EF_TRY(m->match_work.ensure(ef::match_work_bytes(max_batch, m->n_gallery) + 16));
+  // the zero fills above ran on the legacy default stream, the kernels that rely on them run on non-blocking streams
+  // (the model's own or the caller's), which do not order against it: finish them here (reserve is rare)
+  EF_CUDA(cudaDeviceSynchronize());
   m->reserved = max_batch;
   return EF_OK;
 }
@@ -530,7 +540,11 @@ static int host_reserve(ef_model_t* m, int32_t B) {
   EF_TRY(m->resid_dev.ensure(sizeof(double) * (size_t)B));
   EF_TRY(m->index32_dev.ensure(sizeof(int32_t) * (size_t)B));
   EF_TRY(m->label_dev.ensure(sizeof(int32_t) * (size_t)B));
-  EF_TRY(m->bad_dev.ensure(16));
+  if (!m->bad_dev.p) {
+    EF_TRY(m->bad_dev.ensure(16));
+    EF_CUDA(cudaMemset(m->bad_dev.p, 0, 16));
+    EF_CUDA(cudaDeviceSynchronize());
+  }
   m->host_reserved = B;
   return EF_OK;
 }
@@ -705,9 +719,22 @@ int ef_model_recognize_boxes_device(ef_model_t* m, const uint8_t* frames, int64_
   if ((int64_t)dw * dh != m->D) return EF_ERR_INVALID;
   if (n_boxes == 0) return EF_OK;
   EF_TRY(host_reserve(m, n_boxes));
+  // boxes outside their frame (or with w, h <= 0, or a bad frame index) become all-zero crops AND are counted: the host
+  // entry point turns a non-zero count into EF_ERR_INVALID, device callers read it with ef_model_bad_boxes
   EF_TRY(ef_preprocess(frames, frame_stride, pitch, width, height, channels, n_frames, boxes, n_boxes, dw, dh,
-                       m->x_dev.as<uint8_t>(), m->x_ld, nullptr, stream));
+                       m->x_dev.as<uint8_t>(), m->x_ld, m->bad_dev.as<int32_t>(), stream));
   return ef_model_recognize_device(m, m->x_dev.as<uint8_t>(), m->x_ld, n_boxes, threshold, out, stream);
+}
+
+int ef_model_bad_boxes(ef_model_t* m, ef_stream_t stream, int32_t* count) {
+  if (!m || !count) return EF_ERR_INVALID;
+  *count = 0;
+  if (!m->bad_dev.p) return EF_OK;
+  cudaStream_t st = ef::as_stream(stream);
+  EF_CUDA(cudaMemcpyAsync(count, m->bad_dev.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemsetAsync(m->bad_dev.p, 0, sizeof(int32_t), st));
+  EF_CUDA(cudaStreamSynchronize(st));
+  return EF_OK;
 }
 
 int ef_model_recognize_boxes_host(ef_model_t* m, const uint8_t* frames, int64_t frame_stride, int32_t pitch,
@@ -731,7 +758,21 @@ int ef_model_recognize_boxes_host(ef_model_t* m, const uint8_t* frames, int64_t 
   dev.resid2 = out->resid2 ? m->resid_dev.as<double>() : nullptr;
   EF_TRY(ef_model_recognize_boxes_device(m, m->frames_dev.as<uint8_t>(), frame_stride, pitch, width, height, channels,
                                          n_frames, m->boxes_dev.as<ef_box_t>(), n_boxes, dw, dh, threshold, &dev, st));
-  return copy_results_back(m, n_boxes, out, dev);
+  EF_TRY(ensure_pinned(&m->pinned, &m->pinned_bytes, result_block_bytes(m, (size_t)n_boxes)));
+  EF_TRY(enqueue_results(m, n_boxes, out->proj != nullptr, out->resid2 != nullptr, out->label != nullptr, dev, m->pinned));
+  int32_t* bad_host = carve(m, m->pinned, (size_t)n_boxes).flag + 1;
+  EF_CUDA(cudaMemcpyAsync(bad_host, m->bad_dev.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemsetAsync(m->bad_dev.p, 0, sizeof(int32_t), st));
+  EF_CUDA(cudaStreamSynchronize(st));
+  if (*bad_host != 0) {
+    // the reference would clip the slice or raise inside cv2.resize; a black crop with a normal-looking label is never
+    // returned silently
+    char msg[96];
+    snprintf(msg, sizeof(msg), "%d of %d boxes are not inside their frame", *bad_host, n_boxes);
+    ef::set_error_detail(msg, cudaErrorInvalidValue);
+    return EF_ERR_INVALID;
+  }
+  return scatter_results(m, n_boxes, out, m->pinned);
 }
 
 }  // extern "C"

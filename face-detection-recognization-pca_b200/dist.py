@@ -151,10 +151,18 @@ class ShardedGallery:
                                       index.data_ptr(), self._work.data_ptr(), stream), "ef_match_device")
         return score, index
 
-    def match(self, features):
+    def match(self, features, timings=False):
+        ph = _Phases(timings)
+        ph.mark("start")
         score, index = self.match_local(features)
+        ph.mark("local_top1")
         scores, idxs = allgather_candidates(score, index, self.group)        # B x 16 bytes per rank over NVLink
-        return reduce_candidates(scores, idxs, self.metric)
+        ph.mark("allgather")
+        out = reduce_candidates(scores, idxs, self.metric)
+        ph.mark("reduce")
+        if timings:
+            self.last_timings = ph.result()
+        return out
 
 
 
@@ -294,7 +302,33 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=
     return lam[:k].clone(), Q[:, :k].contiguous(), info
 
 
-def fit_gen1_sharded(X_local, n_total, n_components, group=None, solver="auto"):
+class _Phases:
+    """CUDA-event stopwatch for the phases of a multi-step device routine (events on torch's current stream; a NCCL
+    collective issued through torch.distributed is ordered with that stream, so it is timed like a kernel)."""
+
+    def __init__(self, enabled):
+        self.enabled, self.marks = enabled, []
+
+    def mark(self, name):
+        if self.enabled:
+            import torch
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            self.marks.append((name, e))
+
+    def result(self):
+        if not self.enabled or len(self.marks) < 2:
+            return {}
+        import torch
+        torch.cuda.synchronize()
+        out = {}
+        for (_, a), (name, b) in zip(self.marks[:-1], self.marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b) * 1e-3
+        out["total"] = self.marks[0][1].elapsed_time(self.marks[-1][1]) * 1e-3
+        return out
+
+
+def fit_gen1_sharded(X_local, n_total, n_components, group=None, solver="auto", timings=False):
     """Row-sharded manual_pca (useless/train.py:56-128) for N >= D (the covariance branch, e.g. 100 000 x 4096):
     every rank holds X_local uint8 [N_r, D] on its GPU.  Returns (eigenfaces [D,k], mean [D], projected_local [N_r,k],
     eigenvalues [k]) as CUDA float64 tensors; eigenfaces / mean / eigenvalues are identical on every rank.
@@ -309,8 +343,10 @@ def fit_gen1_sharded(X_local, n_total, n_components, group=None, solver="auto"):
     if n_total < D:
         raise ValueError("fit_gen1_sharded covers the N >= D branch; small training sets fit on one GPU (fit_gen1)")
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    ph = _Phases(timings)
     buf = torch.zeros(D * D + D, dtype=torch.int64, device=dev)
     G, colsum = buf[:D * D], buf[D * D:]
+    ph.mark("start")
     if Nr:
         check(L.ef_colsum_u8_device(X_local.data_ptr(), X_local.stride(0), Nr, D, colsum.data_ptr(), stream), "colsum")
         # exact integer X_r^T X_r on tensor cores (tcgen05 kind::i8); the dp4a kernel covers unaligned buffers
@@ -321,10 +357,13 @@ def fit_gen1_sharded(X_local, n_total, n_components, group=None, solver="auto"):
         if st_g == _lib.EF_ERR_UNSUPPORTED:
             st_g = L.ef_gram_u8_device(X_local.data_ptr(), X_local.stride(0), Nr, D, 0, D, 1, G.data_ptr(), stream)
         check(st_g, "gram")
+    ph.mark("gram")
     allreduce_exact(buf, group)
+    ph.mark("allreduce")
     cov = torch.empty((D, D), dtype=torch.float64, device=dev)
     check(L.ef_gram_center_device(G.data_ptr(), D, 1, colsum.data_ptr(), int(n_total), 1.0 / (n_total - 1),
                                   cov.data_ptr(), None, stream), "center")
+    ph.mark("center")
     k = min(int(n_components), D)
     if solver == "subspace" or (solver == "auto" and D > 2048):
         # large D (config 4: 10 000 pixels): only the top k eigenpairs, by filtered subspace iteration
@@ -337,6 +376,7 @@ def fit_gen1_sharded(X_local, n_total, n_components, group=None, solver="auto"):
         work = torch.empty(int(L.ef_eigh_work_bytes(D)), dtype=torch.uint8, device=dev)
         check(L.ef_eigh_jacobi_device(cov.data_ptr(), D, evals.data_ptr(), evecs.data_ptr(), work.data_ptr(), 0, 0.0, None,
                                       None, stream), "jacobi")
+    ph.mark("solver")
     # tensor divisor: torch turns division by a Python scalar into a multiplication by the reciprocal on CUDA, which is
     # not the correctly rounded quotient np.mean (and the single-GPU fit) returns
     mean = colsum.to(torch.float64) / torch.full((1,), float(n_total), dtype=torch.float64, device=dev)
@@ -348,4 +388,6 @@ def fit_gen1_sharded(X_local, n_total, n_components, group=None, solver="auto"):
                                          Z.data_ptr(), D, stream), "center rows")
         check(L.ef_dgemm_device(Nr, k, D, 1.0, Z.data_ptr(), D, 1, E.data_ptr(), k, 1, 0.0, proj.data_ptr(), k, stream),
               "project")
+    ph.mark("projection")
+    fit_gen1_sharded.last_timings = ph.result()
     return E, mean, proj, evals[:k].clone()

@@ -87,6 +87,11 @@ class Recognizer:
         check(self._L.ef_model_status(self._h, C.byref(n)), "ef_model_status")
         return n.value
 
+    def serving_path(self):
+        """Kernel path the last recognise / submit call took: 4 persistent stream kernel, 3 pipelined kernel, 2 single
+        cluster kernel, 1 tcgen05 projection + epilogue kernels, 0 dp4a."""
+        return self.kernel_timing_read()[2]
+
     def kernel_timing(self, enable=True):
         check(self._L.ef_model_kernel_timing(self._h, 1 if enable else 0), "ef_model_kernel_timing")
 
@@ -232,8 +237,27 @@ class Recognizer:
         stream = torch.cuda.current_stream(device).cuda_stream
         check(self._L.ef_model_flush_device(self._h, C.c_void_p(stream)), "ef_model_flush_device")
 
+    def bad_boxes(self, device=None):
+        """Boxes outside their frame seen by recognize_boxes_device since the last call (synchronises torch's current
+        stream; clears the counter).  Their results are those of an all-zero crop and must be discarded."""
+        import torch
+        n = C.c_int32()
+        stream = torch.cuda.current_stream(device).cuda_stream
+        check(self._L.ef_model_bad_boxes(self._h, C.c_void_p(stream), C.byref(n)), "ef_model_bad_boxes")
+        return n.value
+
+    def check_device_results(self, device=None):
+        """Call after synchronising on results of the device entry points: raises when a box lay outside its frame or
+        when a tcgen05 pipeline wait timed out (the kernels drain instead of hanging and only set a flag)."""
+        bad = self.bad_boxes(device)
+        if bad:
+            raise _lib.EigenfacesError(_lib.EF_ERR_INVALID, "recognize_boxes_device", f"{bad} boxes are not inside their frame")
+        if self.pipeline_timeouts():
+            raise _lib.EigenfacesError(_lib.EF_ERR_CUDA, "recognize_device", "tcgen05 pipeline timed out")
+
     def recognize_boxes_device(self, frames, boxes, side, threshold=0.7, out=None, want_residual=None):
-        """frames: torch uint8 CUDA [F, H, W] / [F, H, W, 3]; boxes: torch int32 CUDA [B, 5] (frame, x, y, w, h)."""
+        """frames: torch uint8 CUDA [F, H, W] / [F, H, W, 3]; boxes: torch int32 CUDA [B, 5] (frame, x, y, w, h).
+        Asynchronous; boxes outside their frame are counted, see check_device_results()."""
         import torch
         channels = 3 if frames.dim() == 4 else 1
         F, H, W = frames.shape[:3]
@@ -257,8 +281,11 @@ class Recognizer:
         return out
 
 
-def preprocess_device(frames, boxes, side, out=None):
-    """K1 alone on torch CUDA tensors: returns uint8 [B, ld] with ld = side*side rounded up to 128."""
+def preprocess_device(frames, boxes, side, out=None, bad=None):
+    """K1 alone on torch CUDA tensors: returns uint8 [B, ld] with ld = side*side rounded up to 128.
+    bad: optional int32 CUDA tensor [1] that accumulates the number of boxes outside their frame (asynchronous use: the
+    caller checks it when it synchronises anyway).  Without it the call checks for itself -- one synchronisation -- and
+    raises: a black crop is never returned silently."""
     import torch
     channels = 3 if frames.dim() == 4 else 1
     F, H, W = frames.shape[:3]
@@ -266,10 +293,15 @@ def preprocess_device(frames, boxes, side, out=None):
     ld = (side * side + 127) // 128 * 128
     if out is None:
         out = torch.zeros((B, ld), dtype=torch.uint8, device=frames.device)
+    counter = bad if bad is not None else torch.zeros(1, dtype=torch.int32, device=frames.device)
     stream = torch.cuda.current_stream(frames.device).cuda_stream
     check(_lib.lib().ef_preprocess(frames.data_ptr(), frames.stride(0), frames.stride(1), W, H, channels, F,
-                                   boxes.data_ptr(), B, side, side, out.data_ptr(), out.stride(0), None,
+                                   boxes.data_ptr(), B, side, side, out.data_ptr(), out.stride(0), counter.data_ptr(),
                                    C.c_void_p(stream)), "ef_preprocess")
+    if bad is None and B:
+        n_bad = int(counter.item())
+        if n_bad:
+            raise _lib.EigenfacesError(_lib.EF_ERR_INVALID, "ef_preprocess", f"{n_bad} of {B} boxes are not inside their frame")
     return out
 
 

@@ -165,7 +165,12 @@ int ef_model_submit_host(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B
                          int32_t* ticket);
 int ef_model_wait_host(ef_model_t* m, int32_t ticket, const ef_result_t* out);
 
-/* Same, starting from frames + boxes (K1 then K2).  Host variant copies the frames and boxes in. */
+/* Same, starting from frames + boxes (K1 then K2).  Host variant copies the frames and boxes in.
+ * Every box must lie inside its frame (the reference slices numpy arrays, scan-template-v4.py:360,390: an out-of-frame
+ * box there is clipped or makes cv2.resize raise).  Here a bad box is never recognised silently: the host variant
+ * returns EF_ERR_INVALID (ef_last_error_detail() says how many), the asynchronous device variant writes an all-zero
+ * crop's results and counts the box; ef_model_bad_boxes synchronises `stream`, returns the count accumulated by the
+ * device-variant calls enqueued on it so far and clears it. */
 int ef_model_recognize_boxes_device(ef_model_t* model, const uint8_t* frames, int64_t frame_stride, int32_t pitch,
                                     int32_t width, int32_t height, int32_t channels, int32_t n_frames,
                                     const ef_box_t* boxes, int32_t n_boxes, int32_t dw, int32_t dh,
@@ -174,6 +179,8 @@ int ef_model_recognize_boxes_host(ef_model_t* model, const uint8_t* frames, int6
                                   int32_t width, int32_t height, int32_t channels, int32_t n_frames,
                                   const ef_box_t* boxes, int32_t n_boxes, int32_t dw, int32_t dh,
                                   double threshold, const ef_result_t* out);
+
+int ef_model_bad_boxes(ef_model_t* model, ef_stream_t stream, int32_t* count);
 
 /* Nearest-gallery search on already projected features (device pointers).  Used for the sharded gallery:
  * every rank prepares and matches against its shard, then the (score, index) pairs are all-gathered (NCCL) and

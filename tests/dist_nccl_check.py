@@ -19,6 +19,16 @@ def main():
     torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
     dev = torch.device("cuda", torch.cuda.current_device())
     dist.init_process_group("nccl", device_id=dev)
+    run_checks(rank, world, dev)
+    dist.barrier()
+    if rank == 0:
+        print(f"dist_nccl_check ok (world {world})", flush=True)
+    dist.destroy_process_group()
+
+
+def run_checks(rank, world, dev):
+    """The assertions proper; needs an initialised NCCL process group (bench.py --gpus N calls this too, so that the
+    driver's scaling run proves them on its own box)."""
     rng = np.random.default_rng(3)                        # identical data on every rank
     # ---- sharded gallery (BASELINE config 3 in miniature)
     n, k, B = 200_003, 128, 512
@@ -66,10 +76,6 @@ def main():
     gathered = [torch.empty_like(ev) for _ in range(world)]
     dist.all_gather(gathered, ev)
     assert all(torch.equal(g, ev) for g in gathered), "eigenvalues must be bit identical on every rank"
-    dist.barrier()
-    if rank == 0:
-        print(f"dist_nccl_check ok (world {world})", flush=True)
-    dist.destroy_process_group()
 
 
 if __name__ == "__main__":

@@ -22,7 +22,7 @@ def _declared():
 def test_library_exports_every_declared_symbol():
     names = _declared()
     assert len(names) >= 30
-    lib = C.CDLL(ef._lib._build.LIB)
+    lib = C.CDLL(ef._lib._build.build())                  # incremental: rebuilds only what changed
     missing = [n for n in names if not hasattr(lib, n)]
     assert not missing, f"declared in the header but not exported: {missing}"
 
