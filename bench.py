@@ -298,6 +298,7 @@ def run_ours(args, rank, world):
         block_launches.append(ef.launch_count() - launches0)
         block_ms.append(e0.elapsed_time(e1))
     barrier()
+    serving_path = rec.serving_path()                       # kernel path the submits of the timed blocks took
     block_ms = max_over_ranks(block_ms)
     ms = statistics.median(block_ms)
     launches = int(statistics.median(block_launches))
@@ -426,7 +427,6 @@ def run_ours(args, rank, world):
                      2: "recognize_cluster_kernel: TMA + tcgen05 kind::i8 + DSMEM push + tcgen05 f16 filter + exact f64 re-score (1 launch/step, PDL)",
                      1: "project_tc_kernel (tcgen05 kind::i8, stream-K) + fused_epilogue_kernel",
                      0: "project_dp4a_kernel (CUDA cores) + fused_epilogue_kernel"}
-        serving_path = rec.serving_path() if hasattr(rec, "serving_path") else (3 if launches == args.steps + 1 else int(used_tc))
         line = {
             "metric": METRIC, "value": value, "unit": "crops/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",

@@ -63,6 +63,7 @@ SIGNATURES = {
     "ef_model_recognize_device": (C.c_int, [c_void, c_void, c_i64, c_i32, c_dbl, C.POINTER(Result), c_void]),
     "ef_model_submit_device": (C.c_int, [c_void, c_void, c_i64, c_i32, c_dbl, C.POINTER(Result), c_void]),
     "ef_model_flush_device": (C.c_int, [c_void, c_void]),
+    "ef_model_set_serving": (C.c_int, [c_void, c_i32, c_i32]),
     "ef_model_recognize_host": (C.c_int, [c_void, c_void, c_i64, c_i32, c_dbl, C.POINTER(Result)]),
     "ef_model_submit_host": (C.c_int, [c_void, c_void, c_i64, c_i32, c_dbl, c_i32, p_i32]),
     "ef_model_wait_host": (C.c_int, [c_void, c_i32, C.POINTER(Result)]),

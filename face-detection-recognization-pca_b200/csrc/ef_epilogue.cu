@@ -34,12 +34,7 @@ __device__ __forceinline__ double combine_planes(int32_t* __restrict__ acc_t, in
 #pragma unroll
   for (int s = 0; s < 8; ++s)
     if (s < S) __stcg(acc_t + (size_t)(s * kq + c) * ld_acc + b, 0);
-  double v = 0.0;
-#pragma unroll
-  for (int s = 7; s >= 0; --s)
-    // exact: |acc| < 2^31 and the scale is a power of two
-    if (s < S) v += (double)plane[s] * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
-  return ldexp(v, exp_c);
+  return ldexp(ef::planes_to_double(plane), exp_c);     // planes >= S are zero
 }
 
 template <int METRIC>
@@ -249,10 +244,7 @@ finalize_combine_kernel(int32_t* __restrict__ acc_t, int ld_acc, int B, int k, i
     const int c = c_base + cy;
     double v = 0.0;
     if (b < B && c < kq) {
-#pragma unroll
-      for (int s = 7; s >= 0; --s)                                     // small planes first, like combine_planes
-        if (s < S) v += (double)plane[it][s] * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
-      v = ldexp(v, col_exp[c]);
+      v = ldexp(ef::planes_to_double(plane[it]), col_exp[c]);          // same combination as combine_planes
       if (c < k) v -= bias[c];
       else if (xu_out) xu_out[b] = v;                                  // the residual column x . u~
     }
@@ -305,11 +297,7 @@ finalize_slabs_kernel(const int32_t* __restrict__ part, int splits, long long sl
     for (int s = 0; s < 8; ++s)
       if (s < S) plane[s] += __ldcg(src + s * kq);
   }
-  double v = 0.0;
-#pragma unroll
-  for (int s = 7; s >= 0; --s)                                         // small planes first, like combine_planes
-    if (s < S) v += (double)plane[s] * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
-  v = ldexp(v, col_exp[c]);
+  double v = ldexp(ef::planes_to_double(plane), col_exp[c]);            // same combination as combine_planes
   if (c < k) proj[(size_t)b * ldp + c] = v - bias[c];
   else if (xu_out) xu_out[b] = v;                                      // the residual column x . u~
 }

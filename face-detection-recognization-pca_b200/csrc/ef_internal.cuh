@@ -6,6 +6,27 @@
 
 namespace ef {
 
+#ifdef __CUDACC__
+// Digit planes -> float64, the ONE place every kernel path goes through: v = sum_s plane[s] 2^-(7s+6) with exact integer
+// plane sums (|plane[s]| < 2^31).  Planes 0..3 and 4..7 are first combined as exact 64-bit integers,
+//   hi = sum_{s<4} plane[s] 2^(7(3-s)),  lo = sum_{s>=4} plane[s] 2^(7(7-s))   (|hi|, |lo| < 2^53),
+// so that partial (hi, lo) pairs of K ranges / CTAs / GPUs add exactly; each converts to float64 exactly and
+// v = hi 2^-27 + lo 2^-55 is rounded ONCE: the correctly rounded value of the exact sum, whatever the split.
+__device__ __forceinline__ void planes_to_hilo(const int32_t (&plane)[8], long long& hi, long long& lo) {
+  hi = ((long long)plane[0] << 21) + ((long long)plane[1] << 14) + ((long long)plane[2] << 7) + (long long)plane[3];
+  lo = ((long long)plane[4] << 21) + ((long long)plane[5] << 14) + ((long long)plane[6] << 7) + (long long)plane[7];
+}
+__device__ __forceinline__ double hilo_to_double(long long hi, long long lo) {
+  // 2^-27 = 0x3E40..., 2^-55 = 0x3C80...: power-of-two scalings are exact, the fma rounds once
+  return fma((double)lo, __longlong_as_double(0x3C80000000000000ll), (double)hi * __longlong_as_double(0x3E40000000000000ll));
+}
+__device__ __forceinline__ double planes_to_double(const int32_t (&plane)[8]) {
+  long long hi, lo;
+  planes_to_hilo(plane, hi, lo);
+  return hilo_to_double(hi, lo);
+}
+#endif
+
 // Accumulator convention shared by all projection / epilogue kernels: int32 acc_t[NC][ld_acc] (plane-major, crop b in
 // column b), all zero on entry to a projection kernel, consumed AND cleared by the epilogue kernels.
 
@@ -43,6 +64,28 @@ int recognize_pipe(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq
                    int32_t* out_index, int32_t* out_label, double threshold, const double* gp_padded, int kpad,
                    const double* gnorm, const double* ginv, const void* gimg, int64_t n, const int32_t* labels,
                    int metric, int* status, cudaStream_t stream);
+// ef_recognize_stream.cu -- persistent serving kernel over a queue of batches (ef_model_submit_device / _flush_device):
+// loads, MMAs, cluster exchange, features and matching of consecutive batches overlap inside ONE launch.  Wfm is the
+// FEATURE-MAJOR copy of the digit planes: row c * stream_plane_stride(S) + s holds plane s of column c.
+constexpr int kStreamMaxBatches = 8;
+struct StreamBatchDesc {
+  const uint8_t* x;
+  int64_t ldx;
+  int B;
+  const double* sumsq_ext;     // weighted sum of squares (standardised models with residual) or null
+  double* out_proj;
+  double* out_resid;
+  double* out_score;
+  int32_t* out_index;
+  int32_t* out_label;
+  double threshold;
+};
+int stream_plane_stride(int S);
+bool stream_supported(int D, int k, int kq, int S, int metric, int64_t n);
+int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t* Wfm, int64_t ldw, int wfm_rows, int k,
+                     int kq, int S, const int32_t* col_exp, const double* bias, double c0, const double* gp_padded,
+                     int kpad, const double* gnorm, const double* ginv, const void* gimg, int64_t n,
+                     const int32_t* labels, int metric, int* status, cudaStream_t stream);
 // float16 [g_hi | g_lo | g_hi] image of a prepared gallery for the tensor-core filter of the cluster kernel
 size_t gallery_image_bytes(int k, int64_t n);
 int gallery_image(const double* gp, int kr, const double* ginv, int64_t n, int k, int metric, void* img,

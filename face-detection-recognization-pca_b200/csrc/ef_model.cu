@@ -62,6 +62,16 @@ struct ef_model {
     bool busy = false, want_proj = false, want_resid = false, want_label = false;
   } hslot[2];
   int next_slot = 0;
+  // queued submission (ef_model_submit_device with the persistent serving kernel): descriptors of the batches waiting
+  // for their launch, all submitted on queue_stream; launched when queue_depth of them are waiting or at flush
+  ef::DevBuf wq_fm;                // feature-major copy of the digit planes (row c * PS + s), read by the serving kernel
+  int nc_fm = 0;
+  std::vector<ef::StreamBatchDesc> queue;
+  cudaStream_t queue_stream = nullptr;
+  int queue_depth = ef::kStreamMaxBatches;
+  int serving_kernel = 0;          // 0 persistent stream kernel, 1 pipelined kernel (one launch per batch)
+  bool stream_ok = false;          // the persistent kernel covers this model's shape (decided once at create)
+  ef::DevBuf sumsq_q[ef::kStreamMaxBatches];
   int ld_acc = 0;
   int tc_mode = 2;                 // 0 dp4a, 1 tcgen05 stream-K + epilogue kernels, 2 single cluster kernel
   int last_path = 0;
@@ -203,7 +213,15 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
     }
   }
 
+  // feature-major copy for the serving kernel: all planes of a column in adjacent rows
+  const int PS = ef::stream_plane_stride(m->S);
+  m->nc_fm = (int)ef::round_up((int64_t)m->kq * PS, 16);
+  std::vector<int8_t> wfm((size_t)m->nc_fm * m->ldw, 0);
+  for (int c = 0; c < m->kq; ++c)
+    for (int sl = 0; sl < m->S; ++sl)
+      memcpy(&wfm[(size_t)(c * PS + sl) * m->ldw], &wq[(size_t)(sl * m->kq + c) * m->ldw], (size_t)m->ldw);
   int st = upload(m->wq, wq.data(), wq.size(), m->stream);
+  if (st == EF_OK) st = upload(m->wq_fm, wfm.data(), wfm.size(), m->stream);
   if (st == EF_OK) st = upload(m->col_exp, col_exp.data(), sizeof(int32_t) * col_exp.size(), m->stream);
   if (st == EF_OK) st = upload(m->bias, bias.data(), sizeof(double) * bias.size(), m->stream);
   if (st == EF_OK && desc->labels)
@@ -245,6 +263,7 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
     if (e != cudaSuccess) { ef::set_error_detail("gallery_prepare", e); st = EF_ERR_CUDA; }
   }
   if (st != EF_OK) { ef_model_destroy(m); return st; }
+  m->stream_ok = ef::stream_supported(m->D, m->k, m->kq, m->S, m->metric, m->n_gallery);
   *out = m;
   return EF_OK;
 }
@@ -352,7 +371,8 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
   if (out->resid2 && !m->with_residual) return EF_ERR_INVALID;
   if (B == 0) return EF_OK;
   EF_TRY(ef_model_reserve(m, B));
-  if (m->pending.B > 0) EF_TRY(ef_model_flush_device(m, stream));   // results of a pipelined batch come out first
+  if (m->pending.B > 0 || !m->queue.empty())
+    EF_TRY(ef_model_flush_device(m, stream));                       // results of queued / pipelined batches come out first
   cudaStream_t st = ef::as_stream(stream);
   int32_t* acc = m->acc.as<int32_t>();
   // 1. exact integer digit-plane dot products
@@ -496,21 +516,76 @@ static int pipe_launch(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, 
   return EF_OK;
 }
 
+// Launch the queued batches: ONE persistent kernel over all of them, on the stream they were submitted on.
+static int queue_launch(ef_model_t* m) {
+  if (m->queue.empty()) return EF_OK;
+  const int32_t* labels = m->labels.p ? m->labels.as<int32_t>() : nullptr;
+  const int nb = (int)m->queue.size();
+  const int stq = ef::recognize_stream(m->queue.data(), nb, m->D, m->wq_fm.as<int8_t>(), m->ldw, m->nc_fm, m->k, m->kq,
+                                       m->S, m->col_exp.as<int32_t>(), m->bias.as<double>(), m->c0, m->gp.as<double>(),
+                                       m->kpad, m->gnorm.as<double>(), m->ginv.as<double>(), m->gimg.p, m->n_gallery,
+                                       labels, m->metric, m->status.as<int>(), m->queue_stream);
+  m->queue.clear();
+  if (stq == EF_OK) {
+    m->last_used_tc = true;
+    m->last_path = 4;
+  }
+  return stq;
+}
+
+int ef_model_set_serving(ef_model_t* m, int32_t kernel, int32_t queue_depth) {
+  if (!m || kernel < 0 || kernel > 1) return EF_ERR_INVALID;
+  if (m->pending.B > 0 || !m->queue.empty()) return EF_ERR_INVALID;      // flush first
+  m->serving_kernel = kernel;
+  if (queue_depth > 0) m->queue_depth = queue_depth > ef::kStreamMaxBatches ? ef::kStreamMaxBatches : queue_depth;
+  return EF_OK;
+}
+
 int ef_model_submit_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
                            const ef_result_t* out, ef_stream_t stream) {
   if (m && B == 0) return EF_OK;
   if (!m || !x || !out || B < 0 || ldx < m->D || !out->score || !out->index) return EF_ERR_INVALID;
   if (out->resid2 && !m->with_residual) return EF_ERR_INVALID;
   const bool aligned = !(ldx & 15) && !(reinterpret_cast<uintptr_t>(x) & 15);
+  cudaStream_t st = ef::as_stream(stream);
+  if (m->serving_kernel == 0 && m->tc_mode >= 2 && aligned && m->gimg.p && m->stream_ok) {
+    // persistent serving kernel: the batch joins the queue; the launch happens when the queue is full or at flush
+    if (m->pending.B > 0) EF_TRY(ef_model_flush_device(m, stream));
+    if (!m->queue.empty() && m->queue_stream != st) EF_TRY(ef_model_flush_device(m, stream));
+    if (!m->status.p) EF_TRY(ef_model_reserve(m, 128));
+    ef::StreamBatchDesc d{};
+    d.x = x; d.ldx = ldx; d.B = B;
+    d.out_proj = out->proj; d.out_resid = out->resid2; d.out_score = out->score; d.out_index = out->index;
+    d.out_label = out->label; d.threshold = threshold;
+    if (out->resid2 && m->has_scale) {
+      ef::DevBuf& sq = m->sumsq_q[m->queue.size()];
+      EF_TRY(sq.ensure(sizeof(double) * ((size_t)B + 32)));
+      EF_TRY(ef::row_sumsq(x, ldx, B, m->D, m->qq.as<double>(), sq.as<double>(), st));
+      d.sumsq_ext = sq.as<double>();
+    }
+    m->queue.push_back(d);
+    m->queue_stream = st;
+    if ((int)m->queue.size() >= m->queue_depth) return queue_launch(m);
+    return EF_OK;
+  }
   if (m->tc_mode < 2 || !aligned || !m->gimg.p || !ef::pipe_supported(m->k, m->NC, m->metric, m->n_gallery))
     return ef_model_recognize_device(m, x, ldx, B, threshold, out, stream);    // not pipelined: results right away
   EF_TRY(ef_model_reserve(m, B));
-  if (m->pending.B > 0 && m->pending.stream != ef::as_stream(stream)) EF_TRY(ef_model_flush_device(m, stream));
-  return pipe_launch(m, x, ldx, B, threshold, out, ef::as_stream(stream));
+  if (m->pending.B > 0 && m->pending.stream != st) EF_TRY(ef_model_flush_device(m, stream));
+  return pipe_launch(m, x, ldx, B, threshold, out, st);
 }
 
 int ef_model_flush_device(ef_model_t* m, ef_stream_t stream) {
   if (!m) return EF_ERR_INVALID;
+  if (!m->queue.empty()) {
+    cudaStream_t want = ef::as_stream(stream), owner = m->queue_stream;
+    EF_TRY(queue_launch(m));
+    if (want != owner) {
+      if (!m->flush_ev) EF_CUDA(cudaEventCreateWithFlags(&m->flush_ev, cudaEventDisableTiming));
+      EF_CUDA(cudaEventRecord(m->flush_ev, owner));
+      EF_CUDA(cudaStreamWaitEvent(want, m->flush_ev, 0));
+    }
+  }
   if (m->pending.B <= 0) return EF_OK;
   // The matching launch reads the rows carried by the submit launch, so it runs on the stream of that submit; when the
   // caller flushes from another stream (e.g. a host-buffer call on the model's own stream), that stream is made to wait.

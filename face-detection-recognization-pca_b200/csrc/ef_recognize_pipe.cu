@@ -331,14 +331,18 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
         if (c >= KR) break;
         double v = 0.0;
         if (c < a.kq) {
-          for (int s = a.S - 1; s >= 0; --s) {
-            const int32_t* src = recv + (s * a.kq + c) * 32 + lane;
-            int sum = 0;
+          int32_t plane[8];
 #pragma unroll
-            for (int q = 0; q < kCluster; ++q) sum += src[q * a.nc_pad * 32];
-            v += (double)sum * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
+          for (int s = 0; s < 8; ++s) {
+            int sum = 0;
+            if (s < a.S) {
+              const int32_t* src = recv + (s * a.kq + c) * 32 + lane;
+#pragma unroll
+              for (int q = 0; q < kCluster; ++q) sum += src[q * a.nc_pad * 32];     // exact: |full-K sum| < 2^31
+            }
+            plane[s] = sum;
           }
-          v = ldexp(v, my_exp[it]);
+          v = ldexp(ef::planes_to_double(plane), my_exp[it]);
         }
         if (c < a.k) {
           v -= my_bias[it];
@@ -350,14 +354,18 @@ recognize_pipe_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_c
       if (KR < a.kq && warp == 0) {
         for (int c = KR; c < a.kq; ++c) {
           double v = 0.0;
-          for (int s = a.S - 1; s >= 0; --s) {
-            const int32_t* src = recv + (s * a.kq + c) * 32 + lane;
-            int sum = 0;
+          int32_t plane[8];
 #pragma unroll
-            for (int q = 0; q < kCluster; ++q) sum += src[q * a.nc_pad * 32];
-            v += (double)sum * __longlong_as_double((long long)(1023 - (7 * s + 6)) << 52);
+          for (int s = 0; s < 8; ++s) {
+            int sum = 0;
+            if (s < a.S) {
+              const int32_t* src = recv + (s * a.kq + c) * 32 + lane;
+#pragma unroll
+              for (int q = 0; q < kCluster; ++q) sum += src[q * a.nc_pad * 32];     // exact: |full-K sum| < 2^31
+            }
+            plane[s] = sum;
           }
-          sh->xu[lane] = ldexp(v, a.col_exp[c]);
+          sh->xu[lane] = ldexp(ef::planes_to_double(plane), a.col_exp[c]);
         }
       }
       bar_stream();

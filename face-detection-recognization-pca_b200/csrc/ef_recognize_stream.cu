@@ -1,0 +1,813 @@
+// K2s, the serving kernel: ONE persistent launch recognises a QUEUE of batches (ef_model_submit_device x n, then
+// ef_model_flush_device), streaming them back to back.
+//
+// recognize_pipe_kernel overlaps the match of batch i-1 with the stream of batch i, but every launch still pays its
+// prologue, the cluster exchange + float64 combine after its stream (HBM idle) and the launch gap: 16.6 us per 41 MB
+// batch against 6.3 us of HBM time.  Here the roles of a CTA are decoupled by mbarriers instead of CTA / cluster-wide
+// barriers, so the loads never stop between batches:
+//   warp 0        TMA producer: crop tile + basis tile per 128-byte K block, batch after batch through one stage ring
+//   warp 1        tcgen05.mma kind::i8 issuer; TWO TMEM accumulators (item it -> buffer it & 1): the MMAs of batch i+1
+//                 start while batch i is still being drained
+//   warps 2..5    exact sum of squares of every crop from the staged tiles (dp4a), pushed to the owning CTA per item
+//   warp 6        float16 gallery image -> shared memory (resident when it fits, else a cp.async.bulk ring)
+//   warp 7        tcgen05.mma kind::f16 issuer of the nearest-row filter (two TMEM score buffers)
+//   warps 8..11   drain: TMEM -> registers -> digit planes combined to TWO exact int64 per column (ef::planes_to_hilo:
+//                 2.2 x fewer bytes than the eight int32 planes) -> 16-byte st.shared::cluster into the receive buffer of
+//                 the CTA that owns those 32 crops -> remote mbarrier arrive (release.cluster)
+//   warps 12..15  finish: wait for the four partial slabs of MY 32 crops (acquire.cluster), exact integer sum, float64
+//                 features (+ reconstruction error), float16 [hi|hi|lo] filter operand, then the two scanning passes
+//                 over the filter scores, the exact float64 re-score and score / index / label -- all while warps 0..11
+//                 already work on the next batch.
+// A cluster of 4 CTAs owns crop tile `m` of EVERY queued batch (CTA r streams K quarter r and finishes crops 32r..32r+31),
+// so the per-CTA state machines of a cluster advance through the same item sequence and the cross-CTA barriers need no
+// item tags.  All arithmetic is the one of recognize_cluster_kernel / recognize_pipe_kernel (same integers, same
+// combination, same filter band, same fma order): every output is bit identical to them.
+//
+// The basis is read in FEATURE-MAJOR plane order (row c * PS + s, PS = 4 or 8 planes per column; ef_model keeps this
+// second copy) so that one 16-column tcgen05.ld holds all planes of its columns.
+//
+// Replaces, like the other K2 kernels, project_face_to_eigenspace + recognize_face (useless/scan.py:80-132) and
+// scaler.transform + pca.transform + recognize_face_with_model (scan-template-v4.py:265-287) for a stream of batches.
+#include <climits>
+#include <cstdlib>
+#include <vector>
+#include <cuda_fp16.h>
+#include <math_constants.h>
+
+#include "ef_common.cuh"
+#include "ef_internal.cuh"
+#include "ef_tc_common.cuh"
+
+namespace {
+
+using namespace ef_tc;
+
+constexpr int kCluster = 4;
+constexpr int kWarps = 16;
+constexpr int kThreads = kWarps * 32;
+constexpr int QB = BLOCK_M / kCluster;      // crops finished by each CTA (one per lane)
+static_assert(QB == 32, "one crop per lane");
+constexpr int kGalTile = 128;               // gallery rows per filter MMA
+constexpr int kMaxRing = 16;                // gallery tiles in shared memory (resident gallery: up to 2048 rows)
+constexpr int kListCap = 128;
+constexpr int kFinishWarps = 4;
+constexpr int kFinishThreads = kFinishWarps * 32;
+constexpr int kAccCols = 128;               // TMEM columns per accumulator buffer (nc_pad <= 128)
+constexpr float kFilterEps = 5e-5f;         // same bound as recognize_cluster_kernel
+
+struct StreamBatch {
+  CUtensorMap map;             // crops of this batch: [B][ldx] bytes, box 128 rows x 128 bytes, SWIZZLE_128B
+  int B, pad_;
+  const double* sumsq_ext;     // weighted sum of squares (standardised models) or null
+  double* out_proj;
+  double* out_resid;
+  double* out_score;
+  int32_t* out_index;
+  int32_t* out_label;
+  double threshold;
+};
+
+struct StreamArgs {
+  StreamBatch batch[ef::kStreamMaxBatches];
+  CUtensorMap map_w;           // feature-major digit planes [nc_pad][ldw]
+  int nb, D, nc_pad, k, kq, S, PS, kb_total, stages, recv_bufs;
+  const int32_t* col_exp;
+  const double* bias;
+  double c0;
+  const double* gp;
+  const double* gnorm;
+  const double* ginv;
+  const int32_t* labels;
+  int n, kf, ring, g_tiles, resident;
+  const __half* gimg;
+  int* status;
+  int off_recv, off_ps, off_pe, off_aimg, off_gal, off_sh;
+  unsigned long long* probe;   // debugging aid (EF_TC_PROBE): [grid][8] globaltimer stamps
+};
+
+struct StreamShared {
+  unsigned long long full_bar[kMaxStages];
+  unsigned long long empty_bar[kMaxStages];
+  unsigned long long acc_full[2];
+  unsigned long long acc_empty[2];
+  unsigned long long recv_full[2];            // arrived on by the drain + sum-of-squares lanes of all four CTAs
+  unsigned long long push_ok[2][kCluster];    // [receive buffer][owner]: owner consumed that buffer (remote arrive)
+  unsigned long long gal_full[kMaxRing];
+  unsigned long long gal_empty[kMaxRing];
+  unsigned long long score_full[2];
+  unsigned long long score_empty[2];
+  unsigned long long aimg_ready;
+  uint32_t tmem_base;
+  int failed;
+  int list_cnt, overflow;
+  double pn[QB];
+  double xu[QB];
+  unsigned long long ssq_recv[2][kCluster][QB];
+  float fmax_s[kFinishWarps][QB];
+  int list_L[kListCap], list_j[kListCap], list_label[kListCap];
+  double list_key[kListCap], list_score[kListCap];
+  int red_l[kFinishWarps][QB];
+  double red_s[kFinishWarps][QB];
+  double red_d[kFinishWarps][QB];
+  int red_i[kFinishWarps][QB];
+};
+
+template <int METRIC>
+__device__ __forceinline__ bool better(double s, int i, double bs, int bi) {
+  return s > bs || (s == bs && i < bi);
+}
+
+__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+// Exact float64 score of gallery row j for the crop in column L of pe; same fma order as the full float64 scan.
+template <int METRIC, int KR>
+__device__ __forceinline__ void exact_entry(const double* __restrict__ gp, const double* __restrict__ ginv,
+                                            const double* __restrict__ gnorm, const int32_t* __restrict__ labels,
+                                            const double* pe, int L, int j, double pn, double& key, double& score,
+                                            int& label) {
+  const double2* g = reinterpret_cast<const double2*>(gp + (size_t)j * KR);
+  double d = 0.0;
+#pragma unroll
+  for (int c = 0; c < KR; c += 2) {
+    const double2 gv = __ldg(g + (c >> 1));
+    d = fma(pe[c * QB + L], gv.x, d);
+    d = fma(pe[(c + 1) * QB + L], gv.y, d);
+  }
+  if (METRIC == EF_METRIC_COSINE_G1) {
+    const double gi = __ldg(ginv + j), gn = __ldg(gnorm + j);
+    key = d * gi;
+    score = (pn == 0.0 || gn == 0.0) ? 0.0 : d / (pn * gn);       // useless/scan.py:70-77
+  } else {
+    key = d;
+    score = d;
+  }
+  label = labels ? __ldg(labels + j) : j;
+}
+
+__device__ __forceinline__ void bar_finish() { asm volatile("bar.sync 5, 128;" ::: "memory"); }
+
+template <int PS>
+__device__ __forceinline__ void push_chunk(const uint32_t (&v)[16], int c0, int kq, uint32_t dst) {
+#pragma unroll
+  for (int f = 0; f < 16 / PS; ++f) {
+    const int c = c0 / PS + f;
+    if (c < kq) {
+      int32_t plane[8];
+#pragma unroll
+      for (int s = 0; s < 8; ++s) plane[s] = s < PS ? (int32_t)v[f * PS + s] : 0;
+      long long hi, lo;
+      ef::planes_to_hilo(plane, hi, lo);
+      st_cluster_v2_u64(dst + (uint32_t)c * (QB * 16u), (unsigned long long)hi, (unsigned long long)lo);
+    }
+  }
+}
+
+template <int METRIC, int KR>
+__global__ void __launch_bounds__(kThreads, 1)
+recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if ((smem_u32(smem) & 1023u) != 0u) {
+    if (threadIdx.x == 0) atomicExch(a.status, 2);
+    return;
+  }
+  const int b_stage_bytes = a.nc_pad * BLOCK_K;
+  const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + (size_t)a.stages * A_STAGE_BYTES;
+  uint8_t* recv = smem + a.off_recv;                              // [recv_bufs][4 sources][kq][32 crops] (hi, lo) int64
+  double* ps = reinterpret_cast<double*>(smem + a.off_ps);        // [KR][QB] features of the item being finished
+  double* pe = reinterpret_cast<double*>(smem + a.off_pe);        // [KR][QB] the same as the exact scorer uses them
+  uint8_t* aimg = smem + a.off_aimg;
+  uint8_t* gal = smem + a.off_gal;
+  StreamShared* sh = reinterpret_cast<StreamShared*>(smem + a.off_sh);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int m_tile = blockIdx.x / kCluster;
+  const int row0 = m_tile * BLOCK_M;
+  const int kb0 = (int)((long long)a.kb_total * rank / kCluster);
+  const int kb1 = (int)((long long)a.kb_total * (rank + 1) / kCluster);
+  const int row_bytes = a.kf * 2;
+  const uint32_t gal_tile_bytes = (uint32_t)kGalTile * (uint32_t)row_bytes;
+  const int n_seq = 2 * a.g_tiles;
+  const uint32_t recv_buf_bytes = (uint32_t)(kCluster * a.kq * QB * 16);
+
+  if (tid == 0) {
+    for (int s = 0; s < a.stages; ++s) {
+      mbar_init(&sh->full_bar[s], 1);
+      mbar_init(&sh->empty_bar[s], 5);             // MMA commit + the four sum-of-squares warps
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&sh->acc_full[s], 1);
+      mbar_init(&sh->acc_empty[s], 4);
+      mbar_init(&sh->recv_full[s], kCluster * 2 * QB);   // 4 sources x (32 drain lanes + 32 sum-of-squares lanes)
+      for (int q = 0; q < kCluster; ++q) mbar_init(&sh->push_ok[s][q], 1);
+      mbar_init(&sh->score_full[s], 1);
+      mbar_init(&sh->score_empty[s], kFinishWarps);
+    }
+    for (int s = 0; s < kMaxRing; ++s) {
+      mbar_init(&sh->gal_full[s], 1);
+      mbar_init(&sh->gal_empty[s], 1);
+    }
+    mbar_init(&sh->aimg_ready, 1);
+    sh->failed = 0;
+    sh->list_cnt = 0;
+    sh->overflow = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
+                 "r"(512u)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  cluster_sync_all();                               // every CTA of the cluster runs: its barriers and buffers exist
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory"); // the crops may have been written by the previous kernel
+  const uint32_t tmem_base = sh->tmem_base;
+  volatile int* failed = &sh->failed;
+  unsigned long long* probe = a.probe ? a.probe + (size_t)blockIdx.x * 8 : nullptr;
+  if (probe && tid == 0) probe[0] = globaltimer();
+
+  if (warp == 0) {
+    // =================================================================== TMA producer
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.map_w) : "memory");
+      int stage = 0;
+      uint32_t phase = 0;
+      bool ok = true;
+      for (int g = 0; g < a.nb && ok; ++g) {
+        if (row0 >= a.batch[g].B) continue;
+        const CUtensorMap* mx = &a.batch[g].map;
+        asm volatile("prefetch.tensormap [%0];" ::"l"(mx) : "memory");
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (!mbar_wait(&sh->empty_bar[stage], phase ^ 1, failed)) { ok = false; break; }
+          mbar_arrive_expect_tx(&sh->full_bar[stage], (uint32_t)stage_bytes);
+          tma_load_2d(sA + (size_t)stage * A_STAGE_BYTES, mx, &sh->full_bar[stage], kb * BLOCK_K, row0);
+          tma_load_2d(sB + (size_t)stage * b_stage_bytes, &a.map_w, &sh->full_bar[stage], kb * BLOCK_K, 0);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =================================================================== projection MMA issuer
+    if (lane == 0) {
+      int stage = 0, it = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc = umma_idesc_i8(a.nc_pad);
+      bool ok = true;
+      for (int g = 0; g < a.nb && ok; ++g) {
+        if (row0 >= a.batch[g].B) continue;
+        const int buf = it & 1;
+        if (!mbar_wait(&sh->acc_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), failed)) break;
+        tc_fence_after();
+        const uint32_t d_addr = tmem_base + (uint32_t)(buf * kAccCols);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          if (!mbar_wait(&sh->full_bar[stage], phase, failed)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
+          const uint32_t b_addr = smem_u32(sB + (size_t)stage * b_stage_bytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_i8(d_addr, umma_desc_sw128(a_addr + k * UMMA_K), umma_desc_sw128(b_addr + k * UMMA_K), idesc,
+                    (kb > kb0 || k > 0) ? 1u : 0u);
+          umma_commit(&sh->empty_bar[stage]);
+          if (++stage == a.stages) { stage = 0; phase ^= 1; }
+        }
+        if (ok) umma_commit(&sh->acc_full[buf]);
+        if (probe) probe[it == 0 ? 1 : 2] = globaltimer();
+        ++it;
+      }
+    }
+    __syncwarp();
+  } else if (warp < 6) {
+    // =================================================================== exact sum of squares of the staged crop rows
+    const int owner = warp & 3;                      // rows 32 owner .. 32 owner + 31 of the tile belong to CTA `owner`
+    const int row_in_tile = owner * 32 + lane;
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    bool ok = true;
+    for (int g = 0; g < a.nb; ++g) {
+      if (row0 >= a.batch[g].B) continue;
+      unsigned long long ssq = 0;
+      for (int kb = kb0; kb < kb1 && ok; ++kb) {
+        ok = __all_sync(0xffffffffu, mbar_wait(&sh->full_bar[stage], phase, failed));
+        if (!ok) break;
+        const uint4* line = reinterpret_cast<const uint4*>(sA + (size_t)stage * A_STAGE_BYTES + row_in_tile * BLOCK_K);
+        unsigned int partial = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 v = line[(j + row_in_tile) & 7];
+          partial = __dp4a(v.x, v.x, partial);
+          partial = __dp4a(v.y, v.y, partial);
+          partial = __dp4a(v.z, v.z, partial);
+          partial = __dp4a(v.w, v.w, partial);
+        }
+        ssq += partial;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->empty_bar[stage]);
+        if (++stage == a.stages) { stage = 0; phase ^= 1; }
+      }
+      if (!ok) break;
+      const int rb = it % a.recv_bufs, use = it / a.recv_bufs;
+      ok = __all_sync(0xffffffffu, mbar_wait_cluster(&sh->push_ok[rb][owner], (uint32_t)((use & 1) ^ 1), failed));
+      if (!ok) break;
+      st_cluster_u64(map_to_cta(smem_u32(&sh->ssq_recv[rb][rank][lane]), (uint32_t)owner), ssq);
+      mbar_arrive_remote(map_to_cta(smem_u32(&sh->recv_full[rb]), (uint32_t)owner));
+      ++it;
+    }
+  } else if (warp == 6) {
+    // =================================================================== float16 gallery image -> shared memory
+    if (lane == 0) {
+      int n_items = 0;
+      for (int g = 0; g < a.nb; ++g) n_items += row0 < a.batch[g].B ? 1 : 0;
+      const uint8_t* img = reinterpret_cast<const uint8_t*>(a.gimg);
+      if (a.resident) {
+        if (n_items > 0)
+          for (int t = 0; t < a.g_tiles; ++t) {
+            mbar_arrive_expect_tx(&sh->gal_full[t], gal_tile_bytes);
+            bulk_load(gal + (size_t)t * gal_tile_bytes, img + (size_t)t * gal_tile_bytes, gal_tile_bytes, &sh->gal_full[t]);
+          }
+      } else {
+        const long long total = (long long)n_items * n_seq;
+        int slot = 0, t = 0;
+        uint32_t use_parity = 1;                     // parity of the (use - 1)-th release; a fresh barrier passes parity 1
+        for (long long s = 0; s < total; ++s) {
+          if (!mbar_wait(&sh->gal_empty[slot], use_parity, failed)) break;
+          mbar_arrive_expect_tx(&sh->gal_full[slot], gal_tile_bytes);
+          bulk_load(gal + (size_t)slot * gal_tile_bytes, img + (size_t)t * gal_tile_bytes, gal_tile_bytes, &sh->gal_full[slot]);
+          if (++slot == a.ring) { slot = 0; use_parity ^= 1; }
+          if (++t == a.g_tiles) t = 0;
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 7) {
+    // =================================================================== filter MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(kGalTile);
+      const int n_ks = a.kf >> 4;
+      const int swb = row_bytes < 128 ? row_bytes : 128;
+      const int pa_mask = (swb >> 5) - 1;            // k-steps per swizzle atom - 1 (row_bytes <= 128: one atom)
+      const uint64_t adesc0 = umma_desc_swz(smem_u32(aimg), 0, row_bytes, BLOCK_M);
+      const uint64_t bdesc0 = umma_desc_swz(smem_u32(gal), 0, row_bytes, kGalTile);
+      const uint64_t slot_step = (uint64_t)(gal_tile_bytes >> 4);
+      int it = 0, slot = 0;
+      uint32_t gphase = 0;
+      unsigned int gs = 0;                           // filter tiles issued since the kernel started
+      bool ok = true;
+      for (int g = 0; g < a.nb && ok; ++g) {
+        if (row0 >= a.batch[g].B) continue;
+        if (!mbar_wait(&sh->aimg_ready, (uint32_t)(it & 1), failed)) break;
+        for (int s = 0; s < n_seq; ++s, ++gs) {
+          const int sbuf = (int)(gs & 1u);
+          if (a.resident) {
+            slot = s < a.g_tiles ? s : s - a.g_tiles;
+            if (!mbar_wait(&sh->gal_full[slot], 0u, failed)) { ok = false; break; }
+          } else {
+            if (!mbar_wait(&sh->gal_full[slot], gphase, failed)) { ok = false; break; }
+          }
+          if (!mbar_wait(&sh->score_empty[sbuf], (uint32_t)(((gs >> 1) & 1u) ^ 1u), failed)) { ok = false; break; }
+          tc_fence_after();
+          const uint32_t d_addr = tmem_base + 2u * kAccCols + (uint32_t)sbuf * kGalTile;
+          const uint64_t bslot = bdesc0 + (uint64_t)slot * slot_step;
+#pragma unroll 1
+          for (int ks = 0; ks < n_ks; ++ks) {
+            const uint64_t koff = (uint64_t)((ks & pa_mask) << 1);
+            umma_f16(d_addr, adesc0 + koff, bslot + koff, idesc, ks > 0 ? 1u : 0u);
+          }
+          if (!a.resident) {
+            umma_commit(&sh->gal_empty[slot]);
+            if (++slot == a.ring) { slot = 0; gphase ^= 1; }
+          }
+          umma_commit(&sh->score_full[sbuf]);
+        }
+        ++it;
+      }
+    }
+    __syncwarp();
+  } else if (warp < 12) {
+    // =================================================================== drain: TMEM -> (hi, lo) -> owner's receive buffer
+    const int q = warp & 3;                          // TMEM lane quarter = crops 32 q .. 32 q + 31 = CTA q's crops
+    int it = 0;
+    bool ok = true;
+    for (int g = 0; g < a.nb; ++g) {
+      if (row0 >= a.batch[g].B) continue;
+      const int buf = it & 1;
+      ok = __all_sync(0xffffffffu, mbar_wait(&sh->acc_full[buf], (uint32_t)((it >> 1) & 1), failed));
+      if (!ok) break;
+      tc_fence_after();
+      const int rb = it % a.recv_bufs, use = it / a.recv_bufs;
+      ok = __all_sync(0xffffffffu, mbar_wait_cluster(&sh->push_ok[rb][q], (uint32_t)((use & 1) ^ 1), failed));
+      if (!ok) break;
+      const uint32_t dst = map_to_cta(smem_u32(recv) + (uint32_t)rb * recv_buf_bytes +
+                                          (uint32_t)((int)rank * a.kq * QB + lane) * 16u,
+                                      (uint32_t)q);
+      const uint32_t src = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccCols);
+      for (int c0 = 0; c0 < a.nc_pad; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(src + (uint32_t)c0, v);
+        if (a.PS == 8) push_chunk<8>(v, c0, a.kq, dst); else push_chunk<4>(v, c0, a.kq, dst);
+      }
+      mbar_arrive_remote(map_to_cta(smem_u32(&sh->recv_full[rb]), (uint32_t)q));
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sh->acc_empty[buf]);
+      if (probe && q == 0 && lane == 0) probe[3] = globaltimer();
+      ++it;
+    }
+  } else {
+    // =================================================================== finish: features, filter scan, exact re-score
+    const int fw = warp - (kWarps - kFinishWarps), ftid = tid - (kWarps - kFinishWarps) * 32;
+    const int q = warp & 3;                          // == fw: TMEM lane quarter of this warp
+    const int KC = a.kf >> 3;
+    const int kc_log2 = 31 - __clz(KC);
+    int it = 0;
+    unsigned int gs = 0;
+    bool ok = true;
+    for (int g = 0; g < a.nb; ++g) {
+      const StreamBatch& bt = a.batch[g];
+      if (row0 >= bt.B) continue;
+      const int b = row0 + (int)rank * QB + lane;    // the crop this lane finishes
+      const bool live = b < bt.B;
+      const bool want_resid = bt.out_resid != nullptr;
+      const int rb = it % a.recv_bufs, use = it / a.recv_bufs;
+      ok = __all_sync(0xffffffffu, ok && mbar_wait_cluster(&sh->recv_full[rb], (uint32_t)(use & 1), failed));
+      // ---- exact integer sum of the four K quarters, float64 features (columns fw, fw + 4, ...)
+      const longlong2* rbase = reinterpret_cast<const longlong2*>(recv + (size_t)rb * recv_buf_bytes) + lane;
+      for (int c = fw; c < max(a.kq, KR); c += kFinishWarps) {
+        double v = 0.0;
+        if (c < a.kq && ok) {
+          long long hi = 0, lo = 0;
+#pragma unroll
+          for (int src = 0; src < kCluster; ++src) {
+            const longlong2 p = rbase[(src * a.kq + c) * QB];
+            hi += p.x;
+            lo += p.y;
+          }
+          v = ldexp(ef::hilo_to_double(hi, lo), __ldg(a.col_exp + c));
+          if (c < a.k) {
+            v -= __ldg(a.bias + c);
+            if (bt.out_proj && live) bt.out_proj[(size_t)b * a.k + c] = v;
+          } else {
+            sh->xu[lane] = v;                        // residual column x . u~
+          }
+        }
+        if (c < KR) ps[c * QB + lane] = c < a.k ? v : 0.0;   // padding columns (k .. KR) must be exact zeros
+      }
+      unsigned long long ssq_total = 0;
+      if (fw == 0) {
+#pragma unroll
+        for (int src = 0; src < kCluster; ++src) ssq_total += sh->ssq_recv[rb][src][lane];
+        if (lane == 0) { sh->list_cnt = 0; sh->overflow = 0; }
+      }
+      bar_finish();                                  // receive buffer consumed; features complete
+      if (fw == 1 && lane < kCluster)                // hand the buffer back to the four sources
+        mbar_arrive_remote(map_to_cta(smem_u32(&sh->push_ok[rb][rank]), (uint32_t)lane));
+      double n2 = 0.0;
+      for (int c = 0; c < a.k; ++c) n2 = fma(ps[c * QB + lane], ps[c * QB + lane], n2);
+      double pn = sqrt(n2);
+      if (METRIC == EF_METRIC_COSINE_SK && pn == 0.0) pn = 1.0;
+      for (int c = fw; c < KR; c += kFinishWarps) {
+        double v = ps[c * QB + lane];
+        if (METRIC == EF_METRIC_COSINE_SK) v = v / pn;
+        pe[c * QB + lane] = v;
+      }
+      if (fw == 0) {
+        sh->pn[lane] = pn;
+        if (want_resid && live) {
+          const double sq = bt.sumsq_ext ? bt.sumsq_ext[b] : (double)ssq_total;
+          const double r = sq - 2.0 * sh->xu[lane] + a.c0 - n2;
+          bt.out_resid[b] = r > 0.0 ? r : 0.0;
+        }
+      }
+      {
+        // filter A operand: rows lane + 32 q' all hold crop `lane` (the four TMEM lane quarters see the same 32 crops)
+        const float rinv = n2 > 0.0 ? rsqrtf((float)n2) : 0.f;
+        for (int e = fw; e < 4 * KC; e += kFinishWarps) {
+          const int qq = e >> kc_log2, kc = e & (KC - 1), r = lane + 32 * qq;
+          __align__(16) __half h[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int kk = kc * 8 + i;
+            const int seg = kk >= 3 * a.k ? 3 : (kk >= 2 * a.k ? 2 : (kk >= a.k ? 1 : 0));
+            __half hi = __float2half_rn(0.f), lo = hi;
+            if (seg < 3) split_half((float)ps[(kk - seg * a.k) * QB + lane] * rinv, hi, lo);
+            h[i] = seg < 2 ? hi : lo;
+          }
+          *reinterpret_cast<uint4*>(aimg + swz_chunk_offset(r, kc, row_bytes, BLOCK_M)) = *reinterpret_cast<const uint4*>(h);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      }
+      bar_finish();
+      if (ftid == 0) mbar_arrive(&sh->aimg_ready);
+      // ---- two passes over the filter scores: approximate maximum, then the rows inside the band
+      double best = -CUDART_INF, best_score = 0.0;
+      int best_i = INT_MAX, best_label = -1;
+      auto consider = [&](double key, double score, int label, int j) {
+        if (better<METRIC>(key, j, best, best_i)) { best = key; best_score = score; best_label = label; best_i = j; }
+      };
+      float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F, thr = 0.f;
+      int t = -1, pass = 0;
+      for (int s = 0; s < n_seq; ++s, ++gs) {
+        const int sbuf = (int)(gs & 1u);
+        if (++t == a.g_tiles) { t = 0; pass = 1; }
+        if (pass == 1 && t == 0) {
+          sh->fmax_s[fw][lane] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+          bar_finish();
+          float M = sh->fmax_s[0][lane];
+#pragma unroll
+          for (int w = 1; w < kFinishWarps; ++w) M = fmaxf(M, sh->fmax_s[w][lane]);
+          thr = M - 2.f * kFilterEps;
+        }
+        ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->score_full[sbuf], (uint32_t)((gs >> 1) & 1u), failed));
+        if (!ok) continue;
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 2u * kAccCols + (uint32_t)(sbuf * kGalTile + q * 32), v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->score_empty[sbuf]);
+        const int j0 = t * kGalTile + q * 32;
+        const int valid = min(32, a.n - j0);
+        if (valid <= 0) continue;
+        if (pass == 0) {
+          if (valid == 32) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              m0 = fmaxf(m0, __uint_as_float(v[i]));
+              m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+              m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+              m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < valid) m0 = fmaxf(m0, __uint_as_float(v[i]));
+          }
+        } else {
+          unsigned mask = 0u;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(v[i]) >= thr ? 1u : 0u) << i;
+          if (valid < 32) mask &= (1u << valid) - 1u;
+          while (mask) {
+            const int i = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            const int slot = atomicAdd(&sh->list_cnt, 1);
+            if (slot < kListCap) {
+              sh->list_L[slot] = lane;
+              sh->list_j[slot] = j0 + i;
+            } else {
+              sh->overflow = 1;
+            }
+          }
+        }
+      }
+      __threadfence_block();
+      bar_finish();
+      const bool overflow = *reinterpret_cast<volatile int*>(&sh->overflow) != 0;
+      const int total = overflow ? 0 : min(*reinterpret_cast<volatile int*>(&sh->list_cnt), kListCap);
+      for (int e = ftid; e < total; e += kFinishThreads) {
+        const int L = sh->list_L[e];
+        double key, score; int label;
+        exact_entry<METRIC, KR>(a.gp, a.ginv, a.gnorm, a.labels, pe, L, sh->list_j[e], sh->pn[L], key, score, label);
+        sh->list_key[e] = key;
+        sh->list_score[e] = score;
+        sh->list_label[e] = label;
+      }
+      bar_finish();
+      for (int e = fw; e < total; e += kFinishWarps)
+        if (sh->list_L[e] == lane) consider(sh->list_key[e], sh->list_score[e], sh->list_label[e], sh->list_j[e]);
+      if (overflow) {
+        for (int j = fw; j < a.n; j += kFinishWarps) {
+          double key, score; int label;
+          exact_entry<METRIC, KR>(a.gp, a.ginv, a.gnorm, a.labels, pe, lane, j, pn, key, score, label);
+          consider(key, score, label, j);
+        }
+      }
+      sh->red_s[fw][lane] = best;
+      sh->red_d[fw][lane] = best_score;
+      sh->red_i[fw][lane] = best_i;
+      sh->red_l[fw][lane] = best_label;
+      bar_finish();
+      if (fw == 0 && live) {
+        double bs = sh->red_s[0][lane], score = sh->red_d[0][lane];
+        int bi = sh->red_i[0][lane], bl = sh->red_l[0][lane];
+        for (int w = 1; w < kFinishWarps; ++w)
+          if (better<METRIC>(sh->red_s[w][lane], sh->red_i[w][lane], bs, bi)) {
+            bs = sh->red_s[w][lane];
+            score = sh->red_d[w][lane];
+            bi = sh->red_i[w][lane];
+            bl = sh->red_l[w][lane];
+          }
+        if (bi == INT_MAX) { bi = 0; bl = -1; }      // only after a pipeline failure (the status flag is raised below)
+        bt.out_score[b] = score;
+        bt.out_index[b] = bi;
+        if (bt.out_label) bt.out_label[b] = score >= bt.threshold ? bl : -1;
+      }
+      if (probe && ftid == 0) probe[it == 0 ? 4 : 5] = globaltimer();
+      bar_finish();                                  // red_* / list_* / pn are rewritten by the next item
+      ++it;
+    }
+  }
+
+  // ======================================================================= teardown
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                               // no CTA leaves while a peer may still write or arrive into it
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+  if (tid == 0 && sh->failed) atomicExch(a.status, 1);
+  if (probe && tid == 0) probe[6] = globaltimer();
+}
+
+struct StreamLayout {
+  int stages, recv_bufs, ring, resident;
+  int off_recv, off_ps, off_pe, off_aimg, off_gal, off_sh;
+  size_t smem;
+};
+
+// Shared-memory plan: the deepest stage ring with the gallery image resident comes first.
+bool plan_layout(int nc_pad, int kq, int kr, int kf, int g_tiles, StreamLayout* out) {
+  const size_t stage_bytes = (size_t)A_STAGE_BYTES + (size_t)nc_pad * BLOCK_K;
+  const size_t tile_bytes = (size_t)kGalTile * kf * 2;
+  const size_t aimg_bytes = (size_t)ef::round_up((int64_t)BLOCK_M * kf * 2, 1024);
+  struct Cand { int stages, recv_bufs, resident, ring; };
+  const Cand cands[] = {{4, 2, 1, 0}, {4, 1, 1, 0}, {3, 2, 1, 0}, {3, 1, 1, 0}, {4, 2, 0, 4},
+                        {4, 1, 0, 4}, {3, 2, 0, 4}, {3, 1, 0, 3}, {3, 1, 0, 2}, {2, 1, 0, 2}};
+  const char* e_st = getenv("EF_STREAM_STAGES");
+  const char* e_res = getenv("EF_STREAM_RESIDENT");
+  const char* e_rb = getenv("EF_STREAM_RECV_BUFS");
+  for (const Cand& c : cands) {
+    if (e_st && atoi(e_st) != c.stages) continue;
+    if (e_res && atoi(e_res) != c.resident) continue;
+    if (e_rb && atoi(e_rb) != c.recv_bufs) continue;
+    int ring = c.resident ? g_tiles : std::min(c.ring, 2 * g_tiles);
+    if (ring > kMaxRing || ring < 1) continue;
+    if (!c.resident && ring < 2) continue;
+    size_t off = (size_t)c.stages * stage_bytes;
+    StreamLayout L{};
+    L.stages = c.stages; L.recv_bufs = c.recv_bufs; L.ring = ring; L.resident = c.resident;
+    L.off_recv = (int)off; off += (size_t)c.recv_bufs * kCluster * kq * QB * 16;
+    L.off_ps = (int)off;   off += sizeof(double) * kr * QB;
+    L.off_pe = (int)off;   off += sizeof(double) * kr * QB;
+    off = (size_t)ef::round_up((int64_t)off, 1024);
+    L.off_aimg = (int)off; off += aimg_bytes;
+    L.off_gal = (int)off;  off += (size_t)ring * tile_bytes;
+    off = (size_t)ef::round_up((int64_t)off, 128);
+    L.off_sh = (int)off;
+    L.smem = off + sizeof(StreamShared);
+    if (L.smem <= (size_t)kSmemLimit) { *out = L; return true; }
+  }
+  return false;
+}
+
+template <int METRIC, int KR>
+int launch_stream(StreamArgs& a, const StreamLayout& L, int m_tiles, cudaStream_t stream) {
+  // one attribute call per (device, instantiation): a second device in the same process gets its own
+  static size_t attr[64] = {0};
+  int dev = 0;
+  EF_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return EF_ERR_UNSUPPORTED;
+  if (L.smem > attr[dev]) {
+    EF_CUDA(cudaFuncSetAttribute(recognize_stream_kernel<METRIC, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)L.smem));
+    attr[dev] = L.smem;
+  }
+  static unsigned long long* probe_buf[64] = {nullptr};
+  const bool probing = getenv("EF_TC_PROBE") != nullptr;
+  const int grid_n = m_tiles * kCluster;
+  a.probe = nullptr;
+  if (probing && grid_n <= 4096) {
+    if (!probe_buf[dev]) EF_CUDA(cudaMalloc(&probe_buf[dev], sizeof(unsigned long long) * 8 * 4096));
+    EF_CUDA(cudaMemsetAsync(probe_buf[dev], 0, sizeof(unsigned long long) * 8 * 4096, stream));
+    a.probe = probe_buf[dev];
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid_n);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = L.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attrs[2];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = kCluster;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attrs[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = getenv("EF_NO_PDL") ? 1 : 2;
+  EF_CUDA(cudaLaunchKernelEx(&cfg, recognize_stream_kernel<METRIC, KR>, a));
+  ef::g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (a.probe) {
+    std::vector<unsigned long long> h((size_t)grid_n * 8);
+    EF_CUDA(cudaStreamSynchronize(stream));
+    EF_CUDA(cudaMemcpy(h.data(), probe_buf[dev], h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long t0 = ~0ull;
+    for (int c = 0; c < grid_n; ++c) if (h[(size_t)c * 8] && h[(size_t)c * 8] < t0) t0 = h[(size_t)c * 8];
+    const char* names[8] = {"start", "mma_first_item", "mma_last_item", "last_push", "first_item_out", "last_item_out",
+                            "end", "-"};
+    fprintf(stderr, "[ef_stream_probe] grid %d batches %d stages %d recv_bufs %d ring %d resident %d smem %zu; us since first CTA start (mean/max):",
+            grid_n, a.nb, a.stages, a.recv_bufs, a.ring, a.resident, L.smem);
+    for (int i = 0; i < 8; ++i) {
+      if (names[i][0] == '-') continue;
+      double sum = 0, mx = 0;
+      int cnt = 0;
+      for (int c = 0; c < grid_n; ++c) {
+        if (!h[(size_t)c * 8 + i]) continue;
+        const double v = (double)(h[(size_t)c * 8 + i] - t0) * 1e-3;
+        sum += v;
+        ++cnt;
+        if (v > mx) mx = v;
+      }
+      fprintf(stderr, " %s %.2f/%.2f", names[i], cnt ? sum / cnt : 0.0, mx);
+    }
+    fprintf(stderr, "\n");
+  }
+  return EF_OK;
+}
+
+template <int METRIC>
+int dispatch_kr(StreamArgs& a, const StreamLayout& L, int kr, int m_tiles, cudaStream_t st) {
+  switch (kr) {
+    case 4: return launch_stream<METRIC, 4>(a, L, m_tiles, st);
+    case 8: return launch_stream<METRIC, 8>(a, L, m_tiles, st);
+    case 12: return launch_stream<METRIC, 12>(a, L, m_tiles, st);
+    case 16: return launch_stream<METRIC, 16>(a, L, m_tiles, st);
+    default: return launch_stream<METRIC, 24>(a, L, m_tiles, st);
+  }
+}
+
+}  // namespace
+
+namespace ef {
+
+int stream_plane_stride(int S) { return S <= 4 ? 4 : 8; }
+
+bool stream_supported(int D, int k, int kq, int S, int metric, int64_t n) {
+  const int nc_pad = (int)round_up((int64_t)kq * stream_plane_stride(S), 16);
+  if (metric == EF_METRIC_L2 || k > 21 || nc_pad > kAccCols || n <= 0 || n >= (1ll << 31) - 512) return false;
+  if (filter_kf(k) > 64 || ceil_div(D, BLOCK_K) < kCluster) return false;
+  StreamLayout L;
+  return plan_layout(nc_pad, kq, fused_epilogue_kpad(k), filter_kf(k), (int)ceil_div(n, kGalTile), &L);
+}
+
+// One persistent launch over nb <= kStreamMaxBatches queued batches.  EF_ERR_UNSUPPORTED outside the kernel's coverage.
+int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t* Wfm, int64_t ldw, int wfm_rows, int k,
+                     int kq, int S, const int32_t* col_exp, const double* bias, double c0, const double* gp_padded,
+                     int kpad, const double* gnorm, const double* ginv, const void* gimg, int64_t n,
+                     const int32_t* labels, int metric, int* status, cudaStream_t stream) {
+  using namespace ef_tc;
+  if (nb <= 0) return EF_OK;
+  if (nb > kStreamMaxBatches) return EF_ERR_INVALID;
+  if (!stream_supported(D, k, kq, S, metric, n) || kpad != fused_epilogue_kpad(k)) return EF_ERR_UNSUPPORTED;
+  const int PS = stream_plane_stride(S);
+  const int nc_pad = (int)round_up((int64_t)kq * PS, 16);
+  if (nc_pad > wfm_rows || (ldw & 15) || (reinterpret_cast<uintptr_t>(Wfm) & 15)) return EF_ERR_UNSUPPORTED;
+  if (!encode_fn()) return EF_ERR_UNSUPPORTED;
+  StreamArgs a{};
+  int max_B = 0;
+  for (int g = 0; g < nb; ++g) {
+    const StreamBatchDesc& d = batches[g];
+    if (d.B <= 0 || !d.x || (d.ldx & 15) || (reinterpret_cast<uintptr_t>(d.x) & 15)) return EF_ERR_UNSUPPORTED;
+    StreamBatch& b = a.batch[g];
+    if (!make_map(&b.map, d.x, (uint64_t)D, (uint64_t)d.B, (uint64_t)d.ldx, BLOCK_M)) return EF_ERR_UNSUPPORTED;
+    b.B = d.B;
+    b.sumsq_ext = d.sumsq_ext;
+    b.out_proj = d.out_proj; b.out_resid = d.out_resid; b.out_score = d.out_score; b.out_index = d.out_index;
+    b.out_label = d.out_label; b.threshold = d.threshold;
+    max_B = std::max(max_B, d.B);
+  }
+  if (!make_map(&a.map_w, Wfm, (uint64_t)ldw, (uint64_t)wfm_rows, (uint64_t)ldw, (uint32_t)nc_pad)) return EF_ERR_UNSUPPORTED;
+  StreamLayout L;
+  const int g_tiles = (int)ceil_div(n, kGalTile);
+  if (!plan_layout(nc_pad, kq, kpad, filter_kf(k), g_tiles, &L)) return EF_ERR_UNSUPPORTED;
+  a.nb = nb; a.D = D; a.nc_pad = nc_pad; a.k = k; a.kq = kq; a.S = S; a.PS = PS;
+  a.kb_total = (int)ceil_div(D, BLOCK_K);
+  a.stages = L.stages; a.recv_bufs = L.recv_bufs; a.ring = L.ring; a.resident = L.resident;
+  a.col_exp = col_exp; a.bias = bias; a.c0 = c0;
+  a.gp = gp_padded; a.gnorm = gnorm; a.ginv = ginv; a.labels = labels; a.n = (int)n;
+  a.kf = filter_kf(k); a.g_tiles = g_tiles;
+  a.gimg = reinterpret_cast<const __half*>(gimg);
+  a.status = status;
+  a.off_recv = L.off_recv; a.off_ps = L.off_ps; a.off_pe = L.off_pe; a.off_aimg = L.off_aimg; a.off_gal = L.off_gal;
+  a.off_sh = L.off_sh;
+  const int m_tiles = (int)ceil_div(max_B, BLOCK_M);
+  switch (metric) {
+    case EF_METRIC_COSINE_SK: return dispatch_kr<EF_METRIC_COSINE_SK>(a, L, kpad, m_tiles, stream);
+    case EF_METRIC_COSINE_G1: return dispatch_kr<EF_METRIC_COSINE_G1>(a, L, kpad, m_tiles, stream);
+    default: return EF_ERR_UNSUPPORTED;
+  }
+}
+
+}  // namespace ef

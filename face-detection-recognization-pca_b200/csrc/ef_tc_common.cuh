@@ -70,6 +70,39 @@ __device__ __forceinline__ bool mbar_wait(unsigned long long* bar, uint32_t pari
   }
 }
 
+// Cluster-scope variants for barriers that are arrived on by OTHER CTAs of the cluster after they wrote this CTA's shared
+// memory (st.shared::cluster): the wait acquires at cluster scope, the remote arrive releases at cluster scope.
+__device__ __forceinline__ bool mbar_try_wait_cluster(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ bool mbar_wait_cluster(unsigned long long* bar, uint32_t parity, volatile int* failed) {
+  unsigned long long t0 = 0;
+  for (unsigned int polls = 1;; ++polls) {
+    if (mbar_try_wait_cluster(bar, parity)) return true;
+    if ((polls & 1023u) == 0) {
+      if (*failed) return false;
+      const unsigned long long now = globaltimer();
+      if (t0 == 0) t0 = now;
+      if (now - t0 > kTimeoutNs) {
+        *failed = 1;
+        return false;
+      }
+    }
+  }
+}
+// arrive on a barrier in another CTA's shared memory (address from map_to_cta)
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c_inner,
                                             int c_outer) {
   asm volatile(
@@ -213,6 +246,10 @@ __device__ __forceinline__ void st_cluster_u32(uint32_t addr, uint32_t v) {
 }
 __device__ __forceinline__ void st_cluster_u64(uint32_t addr, unsigned long long v) {
   asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void st_cluster_v2_u64(uint32_t addr, unsigned long long a, unsigned long long b) {
+  asm volatile("st.shared::cluster.v2.u64 [%0], {%1, %2};" ::"r"(addr), "l"(a), "l"(b) : "memory");
 }
 
 // K-major operand image with the widest swizzle that fits the row: rows of row_bytes in {32, 64, 128, 256} bytes

@@ -81,6 +81,11 @@ class Recognizer:
         """2 (default): single cluster kernel; 1 / True: tcgen05 stream-K projection + epilogue kernels; 0 / False: dp4a."""
         check(self._L.ef_model_set_tensor_cores(self._h, int(mode)), "ef_model_set_tensor_cores")
 
+    def set_serving(self, kernel=0, queue_depth=0):
+        """submit_device's kernel: 0 = persistent queue kernel (default), 1 = pipelined kernel (one launch per submit);
+        queue_depth 1..8 batches per persistent launch (0 keeps the current value)."""
+        check(self._L.ef_model_set_serving(self._h, int(kernel), int(queue_depth)), "ef_model_set_serving")
+
     def pipeline_timeouts(self):
         """Non-zero when the tcgen05 projection kernel hit a bounded-wait timeout (synchronous read)."""
         n = C.c_int32()
@@ -208,9 +213,10 @@ class Recognizer:
         return out
 
     def submit_device(self, x, threshold=0.7, out=None, want_residual=None):
-        """Pipelined form of recognize_device for a stream of batches (ef_model_submit_device): features / resid2 of
-        this batch are produced by this call's launch, score / index / label by the NEXT submit_device or by
-        flush_device().  Returns the dict of output tensors (keep it alive until then)."""
+        """Queued form of recognize_device for a stream of batches (ef_model_submit_device): the batch joins the model's
+        queue; one persistent kernel recognises the queued batches back to back when the queue is full or at
+        flush_device().  x and the returned dict of output tensors must stay alive and untouched until then (the
+        Recognizer keeps references to them until the next flush_device)."""
         import torch
         if not (x.is_cuda and x.dtype == torch.uint8 and x.dim() == 2 and x.stride(1) == 1):
             raise ValueError("x must be a 2-D uint8 CUDA tensor with unit inner stride")
@@ -229,6 +235,11 @@ class Recognizer:
         stream = torch.cuda.current_stream(x.device).cuda_stream
         check(self._L.ef_model_submit_device(self._h, x.data_ptr(), x.stride(0), B, float(threshold), C.byref(res),
                                              C.c_void_p(stream)), "ef_model_submit_device")
+        # the launch may come later (queue): keep the tensors away from torch's caching allocator until the flush
+        held = self.__dict__.setdefault("_held", [])
+        held.append((x, out))
+        if len(held) > 64:
+            del held[:-16]                 # older batches were launched long ago (queue depth <= 8, stream ordered)
         return out
 
     def flush_device(self, device=None):
@@ -236,6 +247,7 @@ class Recognizer:
         import torch
         stream = torch.cuda.current_stream(device).cuda_stream
         check(self._L.ef_model_flush_device(self._h, C.c_void_p(stream)), "ef_model_flush_device")
+        self.__dict__.pop("_held", None)   # everything queued has been launched; stream order protects the tensors now
 
     def bad_boxes(self, device=None):
         """Boxes outside their frame seen by recognize_boxes_device since the last call (synchronises torch's current

@@ -142,19 +142,24 @@ int ef_model_recognize_device(ef_model_t* model, const uint8_t* x, int64_t ldx, 
                               const ef_result_t* out, ef_stream_t stream);
 int ef_model_recognize_host(ef_model_t* model, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
                             const ef_result_t* out);
-/* Pipelined submission for a STREAM of batches on one CUDA stream (serving loop; replaces the same reference lines as
- * ef_model_recognize_device).  Each launch streams the batch submitted now AND matches the batch submitted before, on
- * different warps of the same kernel, so HBM streaming of batch i overlaps the nearest-gallery search of batch i-1.
- *   - out->proj and out->resid2 of a batch are written by the launch of its own submit call;
- *   - out->score / out->index / out->label of a batch are written by the NEXT ef_model_submit_device on the model, or by
- *     ef_model_flush_device: the arrays must stay valid (and are complete in stream order) until then;
+/* Queued submission for a STREAM of batches on one CUDA stream (serving loop; replaces the same reference lines as
+ * ef_model_recognize_device).  A submitted batch joins a queue; when queue_depth batches (default and maximum 8) are
+ * waiting, or at ef_model_flush_device, ONE persistent kernel recognises all of them back to back: its loads, tensor-core
+ * projections, cluster exchange, float64 features and nearest-gallery search run on different warps and overlap ACROSS
+ * consecutive batches, so HBM streams without a pause between them.
+ *   - x and every array of out must stay valid and unmodified until ef_model_flush_device (or the next
+ *     ef_model_recognize_* call on the model) has been enqueued; all results are complete, in stream order, after it;
  *   - every value is bit identical to ef_model_recognize_device.
- * Shapes outside the pipelined kernel (L2 metric, k > 21, more than 128 digit-plane columns, unaligned crops) are
- * recognised immediately, exactly like ef_model_recognize_device.  Any other recognise call on the model flushes a
- * pending batch first.  All calls of one pipeline must use the same stream. */
+ * Shapes outside the serving kernels (L2 metric, k > 21, more than 128 digit-plane columns, unaligned crops) are
+ * recognised immediately, exactly like ef_model_recognize_device.  Any other recognise call on the model flushes the
+ * queue first.  All calls of one queue must use the same stream (a submit on another stream flushes first).
+ * ef_model_set_serving: kernel 0 (default) = the persistent queue kernel, 1 = the pipelined kernel of round 1 (one launch
+ * per submit: streams batch i and matches batch i-1; out->proj / out->resid2 written by the batch's own launch, the rest by
+ * the next submit or the flush); queue_depth 1..8 (0 keeps the current value).  Only with nothing queued. */
 int ef_model_submit_device(ef_model_t* model, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
                            const ef_result_t* out, ef_stream_t stream);
 int ef_model_flush_device(ef_model_t* model, ef_stream_t stream);
+int ef_model_set_serving(ef_model_t* model, int32_t kernel, int32_t queue_depth);
 /* Asynchronous form of ef_model_recognize_host for a serving loop: at most two batches in flight.  submit enqueues the
  * chunked host->device copy, the kernels and the device->host copy of the results and returns a ticket (0 or 1); wait
  * blocks until that batch is done and fills the caller's arrays.  The copy of batch i+1 overlaps the kernels and the

@@ -59,10 +59,34 @@ def test_full_size_frame_1080p_and_bad_box():
     rng = np.random.default_rng(5150)
     frame = rng.integers(0, 256, (1, 1080, 1920, 3), dtype=np.uint8)
     boxes = [(0, 1920 - 300, 1080 - 300, 300, 300), (0, 0, 0, 1920, 1080), (0, 1900, 1000, 64, 128), (0, 5, 5, 0, 10)]
-    got = _run(frame, boxes, 64)
+    torch = require_gpu()
+    fr = torch.from_numpy(frame).cuda()
+    bx = torch.tensor(boxes, dtype=torch.int32, device="cuda")
+    # asynchronous form: the caller owns the counter of bad boxes; their crops are all zero
+    bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+    got = ef.preprocess_device(fr, bx, 64, bad=bad)[:, :4096].cpu().numpy()
+    assert int(bad.item()) == 2
     assert np.array_equal(got[0], preprocess.preprocess_crop(frame[0, 780:, 1620:], 64, 64))
     assert np.array_equal(got[1], preprocess.preprocess_crop(frame[0], 64, 64))
     assert not got[2].any() and not got[3].any()
+    # checking form (no counter passed): a black crop is never returned silently
+    with pytest.raises(ef.EigenfacesError, match="2 of 4 boxes"):
+        ef.preprocess_device(fr, bx, 64)
+    # host entry point of a model: EF_ERR_INVALID instead of a normal-looking label for a black crop
+    rng2 = np.random.default_rng(1)
+    E = np.linalg.qr(rng2.normal(size=(4096, 6)))[0]
+    rec = ef.Recognizer(E, rng2.uniform(0, 255, 4096), rng2.normal(size=(9, 6)))
+    with pytest.raises(ef.EigenfacesError, match="not inside their frame"):
+        rec.recognize_boxes(frame[0], [b[1:] for b in boxes], 64)
+    ok = rec.recognize_boxes(frame[0], [b[1:] for b in boxes[:2]], 64)
+    assert ok.index.shape == (2,)
+    # device entry point: counted, read (and cleared) by bad_boxes()
+    rec.recognize_boxes_device(fr, bx, 64)
+    assert rec.bad_boxes() == 2 and rec.bad_boxes() == 0
+    with pytest.raises(ef.EigenfacesError):
+        rec.recognize_boxes_device(fr, bx, 64)
+        rec.check_device_results()
+    rec.close()
 
 
 def test_empty_batch():

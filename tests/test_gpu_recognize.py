@@ -329,11 +329,13 @@ def test_tensor_core_filter_is_exact_on_adversarial_galleries(metric, k, n_galle
     np.testing.assert_allclose(outs[1].score, sims.max(1), atol=SCORE_ATOL)
 
 
+@pytest.mark.parametrize("serving", [(0, 8), (0, 3), (0, 1), (1, 0)])
 @pytest.mark.parametrize("metric", [ef.METRIC_COSINE_G1, ef.METRIC_COSINE_SK])
-def test_pipelined_submission_is_bit_identical(metric, light_model, golden):
-    """ef_model_submit_device / ef_model_flush_device (streaming half of batch i and matching half of batch i-1 in one
-    launch) return exactly what ef_model_recognize_device returns, for batches of changing sizes, including ragged
-    tiles, a batch larger and one smaller than its predecessor, a single crop, and an interleaved ordinary call."""
+def test_pipelined_submission_is_bit_identical(metric, serving, light_model, golden):
+    """ef_model_submit_device / ef_model_flush_device return exactly what ef_model_recognize_device returns, for batches
+    of changing sizes, including ragged tiles, a batch larger and one smaller than its predecessor, a single crop, and
+    an interleaved ordinary call -- through the persistent queue kernel (serving kernel 0: all queued batches in one
+    launch, queue depths 8 / 3 / 1) and through the pipelined kernel (1: stream of batch i + match of batch i-1)."""
     torch = require_gpu()
     X = golden("gen1_light.npz")["X_u8"]
     rng = np.random.default_rng(77 + metric)
@@ -344,6 +346,7 @@ def test_pipelined_submission_is_bit_identical(metric, light_model, golden):
     if metric == ef.METRIC_COSINE_SK:
         kw = dict(scale=rng.uniform(20.0, 60.0, 10000), pca_mean=rng.normal(0, 1e-3, 10000))
     rec = ef.Recognizer(E, light_model["mean_face"], G, metric=metric, labels=np.arange(len(G)) % 3, **kw)
+    rec.set_serving(*serving)
     sizes = [300, 1000, 129, 1, 640, 128, 4096]
     batches = []
     for n in sizes:
@@ -356,9 +359,24 @@ def test_pipelined_submission_is_bit_identical(metric, light_model, golden):
     rec.flush_device()
     torch.cuda.synchronize()
     assert rec.pipeline_timeouts() == 0
+    assert rec.serving_path() == (4 if serving[0] == 0 else 3)
     for i, (o, w) in enumerate(zip(outs, want)):
         for f in ("features", "score", "index", "label", "resid2"):
             assert torch.equal(o[f], w[f]), (i, sizes[i], f)
+    # the same queue twice more (buffers, barriers and TMEM of a fresh launch), then a long queue of equal batches
+    for _ in range(2):
+        outs = [rec.submit_device(xb, 0.8) for xb in batches]
+        rec.flush_device()
+    big = [rec.submit_device(batches[6], 0.8) for _ in range(19)]
+    rec.flush_device()
+    torch.cuda.synchronize()
+    assert rec.pipeline_timeouts() == 0
+    for i, (o, w) in enumerate(zip(outs, want)):
+        for f in ("features", "score", "index", "label", "resid2"):
+            assert torch.equal(o[f], w[f]), ("second round", i, sizes[i], f)
+    for o in big:
+        for f in ("features", "score", "index", "label", "resid2"):
+            assert torch.equal(o[f], want[6][f]), ("long queue", f)
     # an ordinary call in the middle of a pipeline flushes the pending batch first
     o1 = rec.submit_device(batches[0], 0.8)
     mid = rec.recognize_device(batches[1], 0.8)

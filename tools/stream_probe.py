@@ -1,0 +1,90 @@
+"""Debugging aid for the persistent serving kernel (recognize_stream_kernel) on the bench shape (C2): steady-state time per
+4096-crop batch for several queue depths and shared-memory plans, the pipelined kernel of round 1 beside it, the in-kernel
+phase stamps (EF_TC_PROBE) and the host cost of one submit call.  Not a bench line."""
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import eigenfaces_b200 as ef  # noqa: E402
+
+B, D, k, ng = 4096, 10000, 10, 1024
+rng = np.random.default_rng(0)
+E = np.linalg.qr(rng.normal(size=(D, k)))[0]
+rec = ef.Recognizer(E, rng.uniform(60, 200, D), rng.normal(size=(ng, k)) * 100, metric=ef.METRIC_COSINE_G1,
+                    labels=np.arange(ng) % 4)
+ld = (D + 127) // 128 * 128
+xs = [torch.randint(0, 256, (B, ld), dtype=torch.uint8, device="cuda") for _ in range(8)]
+outs = [rec.recognize_device(x, 0.8) for x in xs]
+want = [{f: v.clone() for f, v in o.items()} for o in outs]
+torch.cuda.synchronize()
+
+
+def run(steps):
+    for i in range(steps):
+        rec.submit_device(xs[i % 8], 0.8, out=outs[i % 8])
+    rec.flush_device()
+
+
+def timed(steps=200, reps=5):
+    run(40)
+    torch.cuda.synchronize()
+    best = 1e9
+    for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run(steps)
+        e1.record()
+        torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / steps)
+    return best * 1e3
+
+
+def check():
+    for o, w in zip(outs, want):
+        for f in ("features", "score", "index", "label", "resid2"):
+            if not torch.equal(o[f], w[f]):
+                return f"MISMATCH in {f}: {(o[f] != w[f]).sum().item()} of {o[f].numel()}"
+    return "bit identical"
+
+
+algo = (D + 4 * k + 8) * B
+configs = [({}, "default plan")]
+if len(sys.argv) > 1 and sys.argv[1] == "sweep":
+    configs += [({"EF_STREAM_RESIDENT": "0"}, "gallery ring"), ({"EF_STREAM_STAGES": "3"}, "3 stages"),
+                ({"EF_STREAM_STAGES": "3", "EF_STREAM_RECV_BUFS": "2"}, "3 stages, 2 receive buffers")]
+for env, name in configs:
+    for kk in ("EF_STREAM_RESIDENT", "EF_STREAM_STAGES", "EF_STREAM_RECV_BUFS"):
+        os.environ.pop(kk, None)
+    os.environ.update(env)
+    for depth in (8, 4, 2, 1):
+        rec.set_serving(0, depth)
+        for o in outs:
+            for v in o.values():
+                if v is not None:
+                    v.zero_()
+        us = timed()
+        print(f"stream kernel [{name}] depth {depth}: {us:7.2f} us per batch = {algo / us / 1e3:7.1f} GB/s = "
+              f"{algo / us / 1e3 / 6550.1:.3f} of HBM peak; {check()}; timeouts {rec.pipeline_timeouts()}", flush=True)
+for kk in ("EF_STREAM_RESIDENT", "EF_STREAM_STAGES", "EF_STREAM_RECV_BUFS"):
+    os.environ.pop(kk, None)
+rec.set_serving(1, 0)
+us = timed()
+print(f"pipelined kernel (round 1): {us:7.2f} us per batch = {algo / us / 1e3 / 6550.1:.3f} of HBM peak; {check()}", flush=True)
+rec.set_serving(0, 8)
+# host cost of a submit call (python + ctypes + descriptor encode), nothing launched until the queue fills
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+run(800)
+host_us = (time.perf_counter() - t0) / 800 * 1e6
+torch.cuda.synchronize()
+print(f"host time per submit_device call (incl. 1 launch per 8): {host_us:.2f} us", flush=True)
+os.environ["EF_TC_PROBE"] = "1"
+run(8)
+torch.cuda.synchronize()
+run(8)
+torch.cuda.synchronize()
+os.environ.pop("EF_TC_PROBE")
