@@ -89,6 +89,9 @@ SIGNATURES = {
     "ef_fit_gen1_host": (C.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_void, c_void, c_void,
                                    C.POINTER(FitInfo)]),
     "ef_fit_gen2_host": (C.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, C.POINTER(Gen2Fit), C.POINTER(FitInfo)]),
+    "ef_fit_manual_host": (C.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, C.POINTER(Gen2Fit), C.POINTER(FitInfo)]),
+    "ef_pca_fit_f64_host": (C.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, C.POINTER(Gen2Fit), C.POINTER(FitInfo)]),
+    "ef_scaler_fit_u8_host": (C.c_int, [c_void, c_i64, c_i32, c_i32, c_i32, c_void, c_void, c_void]),
     "ef_colsum_u8_device": (C.c_int, [c_void, c_i64, c_i64, c_i32, c_void, c_void]),
     "ef_gram_u8_device": (C.c_int, [c_void, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_void, c_void]),
     "ef_gram_u8_tc_work_bytes": (C.c_size_t, [c_i64, c_i32, c_i32]),

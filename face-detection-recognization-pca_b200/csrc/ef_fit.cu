@@ -45,6 +45,25 @@ __global__ void scaler_var_kernel(const uint8_t* __restrict__ X, int64_t ldx, in
   scale[d] = sc;
 }
 
+// ManualStandardScaler.fit (scripts/manual/train-v2.py:57-63): np.std (population) per column, exact zeros -> 1.
+__global__ void scaler_var_manual_kernel(const uint8_t* __restrict__ X, int64_t ldx, int64_t N, int D,
+                                         const double* __restrict__ mean, double* __restrict__ var,
+                                         double* __restrict__ scale) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d >= D) return;
+  const double T = mean[d];
+  double s2 = 0.0;
+  for (int64_t n = 0; n < N; ++n) {
+    const double t = (double)X[n * ldx + d] - T;
+    s2 += t * t;
+  }
+  const double v = s2 / (double)N;
+  var[d] = v;
+  double sc = sqrt(v);
+  if (sc == 0.0) sc = 1.0;
+  scale[d] = sc;
+}
+
 // column means of a float64 matrix, sequential over rows (np.mean(axis=0) order), then subtract in place
 __global__ void colmean_center_kernel(double* __restrict__ Z, int64_t ldz, int64_t N, int D,
                                       double* __restrict__ mean_out) {
@@ -248,13 +267,17 @@ int ef_fit_gen1_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
   return EF_OK;
 }
 
-int ef_fit_gen2_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_t k, const ef_gen2_fit_t* out,
-                     ef_fit_info_t* info) {
-  if (!X || !out || N < 2 || D <= 0 || ldx < D || k <= 0) return EF_ERR_INVALID;
-  if (!out->mean_face || !out->scaler_mean || !out->scaler_var || !out->scaler_scale || !out->pca_mean ||
-      !out->components || !out->explained_variance || !out->explained_variance_ratio || !out->singular_values ||
-      !out->noise_variance || !out->features)
+// flavour 0: sklearn StandardScaler + PCA(full) (train-v5.py:349-385); flavour 1: ManualStandardScaler + ManualPCA
+// (scripts/manual/train-v2.py:9-72: np.std with exact zeros -> 1; np.cov + eigh, whose top-k eigenvectors are the same
+// directions as the SVD's -- the reference leaves their signs to LAPACK, here they follow the svd_flip rule).
+// Zh != null: PCA only, of a float64 host matrix (what PCA.fit / ManualPCA.fit receive); the scaler outputs are unused.
+static int fit_gen2_impl(const uint8_t* X, const double* Zh, int64_t ldx, int32_t N, int32_t D, int32_t k, int flavour,
+                         const ef_gen2_fit_t* out, ef_fit_info_t* info) {
+  if ((!X && !Zh) || !out || N < 2 || D <= 0 || ldx < D || k <= 0) return EF_ERR_INVALID;
+  if (!out->pca_mean || !out->components || !out->explained_variance || !out->explained_variance_ratio ||
+      !out->singular_values || !out->noise_variance || !out->features)
     return EF_ERR_INVALID;
+  if (X && (!out->mean_face || !out->scaler_mean || !out->scaler_var || !out->scaler_scale)) return EF_ERR_INVALID;
   const bool snapshot = N <= D;
   const int n = snapshot ? N : D;
   if (n > 4096) return EF_ERR_UNSUPPORTED;
@@ -293,17 +316,27 @@ int ef_fit_gen2_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
   EF_TRY(dS.ensure(sizeof(double) * n));
   EF_TRY(dsign.ensure(sizeof(double) * k));
   EF_TRY(dF.ensure(sizeof(double) * (size_t)N * k));
-  EF_CUDA(cudaMemcpy2DAsync(dX.p, ldxd, X, ldx, D, N, cudaMemcpyHostToDevice, st));
-  EF_CUDA(cudaEventRecord(tm.a, st));
-
-  // pixel mean (:366) == StandardScaler.mean_ ; var_, scale_ (:370)
-  EF_TRY(ef_colsum_u8_device(dX.as<uint8_t>(), ldxd, N, D, dsum.as<int64_t>(), st));
-  EF_LAUNCH(mean_from_colsum_kernel, (unsigned)ef::ceil_div(D, 256), 256, 0, st, dsum.as<long long>(), D, (long long)N,
-            dmean.as<double>());
-  EF_LAUNCH(scaler_var_kernel, (unsigned)ef::ceil_div(D, 128), 128, 0, st, dX.as<uint8_t>(), ldxd, (int64_t)N, D,
-            dmean.as<double>(), dvar.as<double>(), dscale.as<double>());
   double* Z = dZ.as<double>();
-  EF_TRY(ef_standardize_u8_device(dX.as<uint8_t>(), ldxd, N, D, dmean.as<double>(), dscale.as<double>(), nullptr, Z, D, st));
+  if (X) {
+    EF_CUDA(cudaMemcpy2DAsync(dX.p, ldxd, X, ldx, D, N, cudaMemcpyHostToDevice, st));
+    EF_CUDA(cudaEventRecord(tm.a, st));
+    // pixel mean (:366) == StandardScaler.mean_ ; var_, scale_ (:370)
+    EF_TRY(ef_colsum_u8_device(dX.as<uint8_t>(), ldxd, N, D, dsum.as<int64_t>(), st));
+    EF_LAUNCH(mean_from_colsum_kernel, (unsigned)ef::ceil_div(D, 256), 256, 0, st, dsum.as<long long>(), D, (long long)N,
+              dmean.as<double>());
+    if (flavour == 1) {
+      EF_LAUNCH(scaler_var_manual_kernel, (unsigned)ef::ceil_div(D, 128), 128, 0, st, dX.as<uint8_t>(), ldxd, (int64_t)N, D,
+                dmean.as<double>(), dvar.as<double>(), dscale.as<double>());
+    } else {
+      EF_LAUNCH(scaler_var_kernel, (unsigned)ef::ceil_div(D, 128), 128, 0, st, dX.as<uint8_t>(), ldxd, (int64_t)N, D,
+                dmean.as<double>(), dvar.as<double>(), dscale.as<double>());
+    }
+    EF_TRY(ef_standardize_u8_device(dX.as<uint8_t>(), ldxd, N, D, dmean.as<double>(), dscale.as<double>(), nullptr, Z, D, st));
+  } else {
+    EF_CUDA(cudaMemcpy2DAsync(Z, sizeof(double) * D, Zh, sizeof(double) * ldx, sizeof(double) * D, N,
+                              cudaMemcpyHostToDevice, st));
+    EF_CUDA(cudaEventRecord(tm.a, st));
+  }
   // PCA: centre (mean_ of the standardised data is ~1e-16 but sklearn subtracts it), :373
   EF_LAUNCH(colmean_center_kernel, (unsigned)ef::ceil_div(D, 128), 128, 0, st, Z, (int64_t)D, (int64_t)N, D,
             dpm.as<double>());
@@ -369,10 +402,12 @@ int ef_fit_gen2_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
   }
   EF_CUDA(cudaEventRecord(tm.b, st));
 
-  EF_CUDA(cudaMemcpyAsync(out->mean_face, dmean.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
-  EF_CUDA(cudaMemcpyAsync(out->scaler_mean, dmean.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
-  EF_CUDA(cudaMemcpyAsync(out->scaler_var, dvar.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
-  EF_CUDA(cudaMemcpyAsync(out->scaler_scale, dscale.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  if (X) {
+    EF_CUDA(cudaMemcpyAsync(out->mean_face, dmean.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+    EF_CUDA(cudaMemcpyAsync(out->scaler_mean, dmean.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+    EF_CUDA(cudaMemcpyAsync(out->scaler_var, dvar.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+    EF_CUDA(cudaMemcpyAsync(out->scaler_scale, dscale.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  }
   EF_CUDA(cudaMemcpyAsync(out->pca_mean, dpm.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
   EF_CUDA(cudaMemcpyAsync(out->components, Vt, sizeof(double) * (size_t)k * D, cudaMemcpyDeviceToHost, st));
   EF_CUDA(cudaMemcpyAsync(out->features, dF.p, sizeof(double) * (size_t)N * k, cudaMemcpyDeviceToHost, st));
@@ -398,6 +433,55 @@ int ef_fit_gen2_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
     info->off_norm = off;
     info->gpu_ms = ms;
   }
+  return EF_OK;
+}
+
+int ef_fit_gen2_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_t k, const ef_gen2_fit_t* out,
+                     ef_fit_info_t* info) {
+  if (!X) return EF_ERR_INVALID;
+  return fit_gen2_impl(X, nullptr, ldx, N, D, k, 0, out, info);
+}
+
+int ef_fit_manual_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_t k, const ef_gen2_fit_t* out,
+                       ef_fit_info_t* info) {
+  if (!X) return EF_ERR_INVALID;
+  return fit_gen2_impl(X, nullptr, ldx, N, D, k, 1, out, info);
+}
+
+int ef_pca_fit_f64_host(const double* Z, int64_t ldz, int32_t N, int32_t D, int32_t k, const ef_gen2_fit_t* out,
+                        ef_fit_info_t* info) {
+  if (!Z) return EF_ERR_INVALID;
+  return fit_gen2_impl(nullptr, Z, ldz, N, D, k, 0, out, info);
+}
+
+int ef_scaler_fit_u8_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_t flavour, double* mean, double* var,
+                          double* scale) {
+  if (!X || !mean || !var || !scale || N < 1 || D <= 0 || ldx < D || flavour < 0 || flavour > 1) return EF_ERR_INVALID;
+  cudaStream_t st = nullptr;
+  EF_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{st};
+  ef::DevBuf dX, dsum, dmean, dvar, dscale;
+  const int64_t ldxd = ef::round_up(D, 16);
+  EF_TRY(dX.ensure((size_t)N * ldxd));
+  EF_TRY(dsum.ensure(sizeof(int64_t) * D));
+  EF_TRY(dmean.ensure(sizeof(double) * D));
+  EF_TRY(dvar.ensure(sizeof(double) * D));
+  EF_TRY(dscale.ensure(sizeof(double) * D));
+  EF_CUDA(cudaMemcpy2DAsync(dX.p, ldxd, X, ldx, D, N, cudaMemcpyHostToDevice, st));
+  EF_TRY(ef_colsum_u8_device(dX.as<uint8_t>(), ldxd, N, D, dsum.as<int64_t>(), st));
+  EF_LAUNCH(mean_from_colsum_kernel, (unsigned)ef::ceil_div(D, 256), 256, 0, st, dsum.as<long long>(), D, (long long)N,
+            dmean.as<double>());
+  if (flavour == 1) {
+    EF_LAUNCH(scaler_var_manual_kernel, (unsigned)ef::ceil_div(D, 128), 128, 0, st, dX.as<uint8_t>(), ldxd, (int64_t)N, D,
+              dmean.as<double>(), dvar.as<double>(), dscale.as<double>());
+  } else {
+    EF_LAUNCH(scaler_var_kernel, (unsigned)ef::ceil_div(D, 128), 128, 0, st, dX.as<uint8_t>(), ldxd, (int64_t)N, D,
+              dmean.as<double>(), dvar.as<double>(), dscale.as<double>());
+  }
+  EF_CUDA(cudaMemcpyAsync(mean, dmean.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(var, dvar.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaMemcpyAsync(scale, dscale.p, sizeof(double) * D, cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaStreamSynchronize(st));
   return EF_OK;
 }
 

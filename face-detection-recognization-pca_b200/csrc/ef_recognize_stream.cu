@@ -9,15 +9,20 @@
 //   warp 1        tcgen05.mma kind::i8 issuer; TWO TMEM accumulators (item it -> buffer it & 1): the MMAs of batch i+1
 //                 start while batch i is still being drained
 //   warps 2..5    exact sum of squares of every crop from the staged tiles (dp4a), pushed to the owning CTA per item
-//   warp 6        float16 gallery image -> shared memory (resident when it fits, else a cp.async.bulk ring)
-//   warp 7        tcgen05.mma kind::f16 issuer of the nearest-row filter (two TMEM score buffers)
+//   warp 6        float32 image of the normalised gallery -> shared memory (resident when it fits, else a
+//                 cp.async.bulk ring)
 //   warps 8..11   drain: TMEM -> registers -> digit planes combined to TWO exact int64 per column (ef::planes_to_hilo:
 //                 2.2 x fewer bytes than the eight int32 planes) -> 16-byte st.shared::cluster into the receive buffer of
 //                 the CTA that owns those 32 crops -> remote mbarrier arrive (release.cluster)
 //   warps 12..15  finish: wait for the four partial slabs of MY 32 crops (acquire.cluster), exact integer sum, float64
-//                 features (+ reconstruction error), float16 [hi|hi|lo] filter operand, then the two scanning passes
-//                 over the filter scores, the exact float64 re-score and score / index / label -- all while warps 0..11
-//                 already work on the next batch.
+//                 features (+ reconstruction error), ONE pass of a float32 CUDA-core filter over the gallery (lane =
+//                 crop, features in registers, gallery rows broadcast from shared memory, running maximum + the rows
+//                 within the error band of it), the exact float64 re-score of those rows and score / index / label --
+//                 all while warps 0..11 already work on the next batch.
+// (The first version ran the filter as tcgen05 kind::f16 MMAs like recognize_pipe_kernel.  Measured: every filter MMA
+// queues behind the projection MMAs of the following batches in the one tensor pipe, 16 dependent round trips of ~0.8 us
+// per item made the finish warps the bottleneck at 13-15 us per batch.  The filter is 0.3 MFLOP per crop: on the idle
+// FP32 pipe it needs no round trips at all.)
 // A cluster of 4 CTAs owns crop tile `m` of EVERY queued batch (CTA r streams K quarter r and finishes crops 32r..32r+31),
 // so the per-CTA state machines of a cluster advance through the same item sequence and the cross-CTA barriers need no
 // item tags.  All arithmetic is the one of recognize_cluster_kernel / recognize_pipe_kernel (same integers, same
@@ -53,7 +58,12 @@ constexpr int kListCap = 128;
 constexpr int kFinishWarps = 4;
 constexpr int kFinishThreads = kFinishWarps * 32;
 constexpr int kAccCols = 128;               // TMEM columns per accumulator buffer (nc_pad <= 128)
-constexpr float kFilterEps = 5e-5f;         // same bound as recognize_cluster_kernel
+constexpr int kCandCap = 8;                 // filter candidates a thread keeps (pruned against the running maximum)
+// Filter error bound: features and gallery rows are unit vectors rounded to float32 (2^-24 relative per component), the
+// k <= 24 products are accumulated with fmaf (2^-24 relative per step), the feature normalisation uses rsqrtf (one
+// common factor 1 + 2^-22 on all scores of a crop): |s~ - cos| < 4e-6.  5e-5 (the band of the tensor-core filters) covers
+// it with a wide margin; a too-large value only costs extra float64 re-scores, never correctness.
+constexpr float kFilterEps = 5e-5f;
 
 struct StreamBatch {
   CUtensorMap map;             // crops of this batch: [B][ldx] bytes, box 128 rows x 128 bytes, SWIZZLE_128B
@@ -78,10 +88,10 @@ struct StreamArgs {
   const double* gnorm;
   const double* ginv;
   const int32_t* labels;
-  int n, kf, ring, g_tiles, resident;
-  const __half* gimg;
+  int n, ring, g_tiles, resident;
+  const float* gimg;           // float32 image of the normalised gallery [g_tiles * 128][KR]
   int* status;
-  int off_recv, off_ps, off_pe, off_aimg, off_gal, off_sh;
+  int off_recv, off_ps, off_pe, off_gal, off_sh;
   unsigned long long* probe;   // debugging aid (EF_TC_PROBE): [grid][8] globaltimer stamps
 };
 
@@ -94,9 +104,6 @@ struct StreamShared {
   unsigned long long push_ok[2][kCluster];    // [receive buffer][owner]: owner consumed that buffer (remote arrive)
   unsigned long long gal_full[kMaxRing];
   unsigned long long gal_empty[kMaxRing];
-  unsigned long long score_full[2];
-  unsigned long long score_empty[2];
-  unsigned long long aimg_ready;
   uint32_t tmem_base;
   int failed;
   int list_cnt, overflow;
@@ -104,6 +111,8 @@ struct StreamShared {
   double xu[QB];
   unsigned long long ssq_recv[2][kCluster][QB];
   float fmax_s[kFinishWarps][QB];
+  int cand_j[kCandCap][kFinishThreads];          // per-thread candidate rows of the filter pass ([slot][thread]: no conflicts)
+  float cand_s[kCandCap][kFinishThreads];
   int list_L[kListCap], list_j[kListCap], list_label[kListCap];
   double list_key[kListCap], list_score[kListCap];
   int red_l[kFinishWarps][QB];
@@ -115,11 +124,6 @@ struct StreamShared {
 template <int METRIC>
 __device__ __forceinline__ bool better(double s, int i, double bs, int bi) {
   return s > bs || (s == bs && i < bi);
-}
-
-__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
-  hi = __float2half_rn(v);
-  lo = __float2half_rn(v - __half2float(hi));
 }
 
 // Exact float64 score of gallery row j for the crop in column L of pe; same fma order as the full float64 scan.
@@ -180,7 +184,6 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   uint8_t* recv = smem + a.off_recv;                              // [recv_bufs][4 sources][kq][32 crops] (hi, lo) int64
   double* ps = reinterpret_cast<double*>(smem + a.off_ps);        // [KR][QB] features of the item being finished
   double* pe = reinterpret_cast<double*>(smem + a.off_pe);        // [KR][QB] the same as the exact scorer uses them
-  uint8_t* aimg = smem + a.off_aimg;
   uint8_t* gal = smem + a.off_gal;
   StreamShared* sh = reinterpret_cast<StreamShared*>(smem + a.off_sh);
 
@@ -190,9 +193,8 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   const int row0 = m_tile * BLOCK_M;
   const int kb0 = (int)((long long)a.kb_total * rank / kCluster);
   const int kb1 = (int)((long long)a.kb_total * (rank + 1) / kCluster);
-  const int row_bytes = a.kf * 2;
-  const uint32_t gal_tile_bytes = (uint32_t)kGalTile * (uint32_t)row_bytes;
-  const int n_seq = 2 * a.g_tiles;
+  const uint32_t gal_tile_bytes = (uint32_t)(kGalTile * KR * sizeof(float));
+  const int n_seq = a.g_tiles;                     // one filter pass over the gallery per item
   const uint32_t recv_buf_bytes = (uint32_t)(kCluster * a.kq * QB * 16);
 
   if (tid == 0) {
@@ -205,14 +207,11 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       mbar_init(&sh->acc_empty[s], 4);
       mbar_init(&sh->recv_full[s], kCluster * 2 * QB);   // 4 sources x (32 drain lanes + 32 sum-of-squares lanes)
       for (int q = 0; q < kCluster; ++q) mbar_init(&sh->push_ok[s][q], 1);
-      mbar_init(&sh->score_full[s], 1);
-      mbar_init(&sh->score_empty[s], kFinishWarps);
     }
     for (int s = 0; s < kMaxRing; ++s) {
       mbar_init(&sh->gal_full[s], 1);
-      mbar_init(&sh->gal_empty[s], 1);
+      mbar_init(&sh->gal_empty[s], kFinishWarps);
     }
-    mbar_init(&sh->aimg_ready, 1);
     sh->failed = 0;
     sh->list_cnt = 0;
     sh->overflow = 0;
@@ -221,7 +220,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
-                 "r"(512u)
+                 "r"(2u * kAccCols)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -329,7 +328,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
     if (lane == 0) {
       int n_items = 0;
       for (int g = 0; g < a.nb; ++g) n_items += row0 < a.batch[g].B ? 1 : 0;
-      const uint8_t* img = reinterpret_cast<const uint8_t*>(a.gimg);
+      const uint8_t* img = reinterpret_cast<const uint8_t*>(a.gimg);   // [g_tiles] tiles of 128 rows x KR floats
       if (a.resident) {
         if (n_items > 0)
           for (int t = 0; t < a.g_tiles; ++t) {
@@ -351,49 +350,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
     }
     __syncwarp();
   } else if (warp == 7) {
-    // =================================================================== filter MMA issuer
-    if (lane == 0) {
-      const uint32_t idesc = umma_idesc_f16(kGalTile);
-      const int n_ks = a.kf >> 4;
-      const int swb = row_bytes < 128 ? row_bytes : 128;
-      const int pa_mask = (swb >> 5) - 1;            // k-steps per swizzle atom - 1 (row_bytes <= 128: one atom)
-      const uint64_t adesc0 = umma_desc_swz(smem_u32(aimg), 0, row_bytes, BLOCK_M);
-      const uint64_t bdesc0 = umma_desc_swz(smem_u32(gal), 0, row_bytes, kGalTile);
-      const uint64_t slot_step = (uint64_t)(gal_tile_bytes >> 4);
-      int it = 0, slot = 0;
-      uint32_t gphase = 0;
-      unsigned int gs = 0;                           // filter tiles issued since the kernel started
-      bool ok = true;
-      for (int g = 0; g < a.nb && ok; ++g) {
-        if (row0 >= a.batch[g].B) continue;
-        if (!mbar_wait(&sh->aimg_ready, (uint32_t)(it & 1), failed)) break;
-        for (int s = 0; s < n_seq; ++s, ++gs) {
-          const int sbuf = (int)(gs & 1u);
-          if (a.resident) {
-            slot = s < a.g_tiles ? s : s - a.g_tiles;
-            if (!mbar_wait(&sh->gal_full[slot], 0u, failed)) { ok = false; break; }
-          } else {
-            if (!mbar_wait(&sh->gal_full[slot], gphase, failed)) { ok = false; break; }
-          }
-          if (!mbar_wait(&sh->score_empty[sbuf], (uint32_t)(((gs >> 1) & 1u) ^ 1u), failed)) { ok = false; break; }
-          tc_fence_after();
-          const uint32_t d_addr = tmem_base + 2u * kAccCols + (uint32_t)sbuf * kGalTile;
-          const uint64_t bslot = bdesc0 + (uint64_t)slot * slot_step;
-#pragma unroll 1
-          for (int ks = 0; ks < n_ks; ++ks) {
-            const uint64_t koff = (uint64_t)((ks & pa_mask) << 1);
-            umma_f16(d_addr, adesc0 + koff, bslot + koff, idesc, ks > 0 ? 1u : 0u);
-          }
-          if (!a.resident) {
-            umma_commit(&sh->gal_empty[slot]);
-            if (++slot == a.ring) { slot = 0; gphase ^= 1; }
-          }
-          umma_commit(&sh->score_full[sbuf]);
-        }
-        ++it;
-      }
-    }
-    __syncwarp();
+    // spare warp
   } else if (warp < 12) {
     // =================================================================== drain: TMEM -> (hi, lo) -> owner's receive buffer
     const int q = warp & 3;                          // TMEM lane quarter = crops 32 q .. 32 q + 31 = CTA q's crops
@@ -427,9 +384,6 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   } else {
     // =================================================================== finish: features, filter scan, exact re-score
     const int fw = warp - (kWarps - kFinishWarps), ftid = tid - (kWarps - kFinishWarps) * 32;
-    const int q = warp & 3;                          // == fw: TMEM lane quarter of this warp
-    const int KC = a.kf >> 3;
-    const int kc_log2 = 31 - __clz(KC);
     int it = 0;
     unsigned int gs = 0;
     bool ok = true;
@@ -489,82 +443,86 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
           bt.out_resid[b] = r > 0.0 ? r : 0.0;
         }
       }
-      {
-        // filter A operand: rows lane + 32 q' all hold crop `lane` (the four TMEM lane quarters see the same 32 crops)
-        const float rinv = n2 > 0.0 ? rsqrtf((float)n2) : 0.f;
-        for (int e = fw; e < 4 * KC; e += kFinishWarps) {
-          const int qq = e >> kc_log2, kc = e & (KC - 1), r = lane + 32 * qq;
-          __align__(16) __half h[8];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int kk = kc * 8 + i;
-            const int seg = kk >= 3 * a.k ? 3 : (kk >= 2 * a.k ? 2 : (kk >= a.k ? 1 : 0));
-            __half hi = __float2half_rn(0.f), lo = hi;
-            if (seg < 3) split_half((float)ps[(kk - seg * a.k) * QB + lane] * rinv, hi, lo);
-            h[i] = seg < 2 ? hi : lo;
-          }
-          *reinterpret_cast<uint4*>(aimg + swz_chunk_offset(r, kc, row_bytes, BLOCK_M)) = *reinterpret_cast<const uint4*>(h);
-        }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-      }
-      bar_finish();
-      if (ftid == 0) mbar_arrive(&sh->aimg_ready);
-      // ---- two passes over the filter scores: approximate maximum, then the rows inside the band
       double best = -CUDART_INF, best_score = 0.0;
       int best_i = INT_MAX, best_label = -1;
       auto consider = [&](double key, double score, int label, int j) {
         if (better<METRIC>(key, j, best, best_i)) { best = key; best_score = score; best_label = label; best_i = j; }
       };
-      float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F, thr = 0.f;
-      int t = -1, pass = 0;
-      for (int s = 0; s < n_seq; ++s, ++gs) {
-        const int sbuf = (int)(gs & 1u);
-        if (++t == a.g_tiles) { t = 0; pass = 1; }
-        if (pass == 1 && t == 0) {
-          sh->fmax_s[fw][lane] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-          bar_finish();
-          float M = sh->fmax_s[0][lane];
+      // ---- float32 filter, one pass: running maximum of this warp's rows and the rows within the band of it
+      float ph[KR];
+      {
+        const float rinv = n2 > 0.0 ? rsqrtf((float)n2) : 0.f;
 #pragma unroll
-          for (int w = 1; w < kFinishWarps; ++w) M = fmaxf(M, sh->fmax_s[w][lane]);
-          thr = M - 2.f * kFilterEps;
-        }
-        ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->score_full[sbuf], (uint32_t)((gs >> 1) & 1u), failed));
+        for (int c = 0; c < KR; ++c) ph[c] = (float)ps[c * QB + lane] * rinv;
+      }
+      const float band = 2.f * kFilterEps;
+      float m = -CUDART_INF_F;
+      int cnt = 0;
+      bool spill = false;
+      for (int t = 0; t < n_seq; ++t, ++gs) {
+        int slot;
+        uint32_t par;
+        if (a.resident) { slot = t; par = 0u; } else { slot = (int)(gs % (unsigned)a.ring); par = (gs / (unsigned)a.ring) & 1u; }
+        ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->gal_full[slot], par, failed));
         if (!ok) continue;
-        tc_fence_after();
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + 2u * kAccCols + (uint32_t)(sbuf * kGalTile + q * 32), v);
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sh->score_empty[sbuf]);
-        const int j0 = t * kGalTile + q * 32;
-        const int valid = min(32, a.n - j0);
-        if (valid <= 0) continue;
-        if (pass == 0) {
-          if (valid == 32) {
+        const float* gt = reinterpret_cast<const float*>(gal + (size_t)slot * gal_tile_bytes) + (size_t)(fw * 32) * KR;
+        const int j0 = t * kGalTile + fw * 32;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const float4* g4 = reinterpret_cast<const float4*>(gt + r * KR);
+          float sc = 0.f;
 #pragma unroll
-            for (int i = 0; i < 32; i += 4) {
-              m0 = fmaxf(m0, __uint_as_float(v[i]));
-              m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
-              m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
-              m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (i < valid) m0 = fmaxf(m0, __uint_as_float(v[i]));
+          for (int c4 = 0; c4 < KR / 4; ++c4) {
+            const float4 gv = g4[c4];                // all lanes read the same row: shared-memory broadcast
+            sc = fmaf(ph[4 * c4], gv.x, sc);
+            sc = fmaf(ph[4 * c4 + 1], gv.y, sc);
+            sc = fmaf(ph[4 * c4 + 2], gv.z, sc);
+            sc = fmaf(ph[4 * c4 + 3], gv.w, sc);
           }
-        } else {
-          unsigned mask = 0u;
+          const int j = j0 + r;
+          if (j < a.n && sc >= m - band) {           // rare after the first rows
+            if (sc > m) m = sc;
+            if (cnt == kCandCap) {                   // drop what fell out of the band of the running maximum
+              const float lim = m - band;
+              int w = 0;
+              for (int i = 0; i < kCandCap; ++i) {
+                const float cs = sh->cand_s[i][ftid];
+                if (cs >= lim) {
+                  sh->cand_s[w][ftid] = cs;
+                  sh->cand_j[w][ftid] = sh->cand_j[i][ftid];
+                  ++w;
+                }
+              }
+              cnt = w;
+            }
+            if (cnt < kCandCap) {
+              sh->cand_s[cnt][ftid] = sc;
+              sh->cand_j[cnt][ftid] = j;
+              ++cnt;
+            } else {
+              spill = true;                          // more than kCandCap rows of one crop inside the band: exact scan
+            }
+          }
+        }
+        if (!a.resident) {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sh->gal_empty[slot]);
+        }
+      }
+      sh->fmax_s[fw][lane] = m;
+      if (spill) sh->overflow = 1;
+      bar_finish();
+      {
+        float M = sh->fmax_s[0][lane];
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(v[i]) >= thr ? 1u : 0u) << i;
-          if (valid < 32) mask &= (1u << valid) - 1u;
-          while (mask) {
-            const int i = __ffs(mask) - 1;
-            mask &= mask - 1u;
+        for (int w = 1; w < kFinishWarps; ++w) M = fmaxf(M, sh->fmax_s[w][lane]);
+        const float thr = M - band;
+        for (int i = 0; i < cnt; ++i) {
+          if (sh->cand_s[i][ftid] >= thr) {
             const int slot = atomicAdd(&sh->list_cnt, 1);
             if (slot < kListCap) {
               sh->list_L[slot] = lane;
-              sh->list_j[slot] = j0 + i;
+              sh->list_j[slot] = sh->cand_j[i][ftid];
             } else {
               sh->overflow = 1;
             }
@@ -625,7 +583,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   cluster_sync_all();                               // no CTA leaves while a peer may still write or arrive into it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kAccCols) : "memory");
   }
   if (tid == 0 && sh->failed) atomicExch(a.status, 1);
   if (probe && tid == 0) probe[6] = globaltimer();
@@ -633,17 +591,16 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
 
 struct StreamLayout {
   int stages, recv_bufs, ring, resident;
-  int off_recv, off_ps, off_pe, off_aimg, off_gal, off_sh;
+  int off_recv, off_ps, off_pe, off_gal, off_sh;
   size_t smem;
 };
 
 // Shared-memory plan: the deepest stage ring with the gallery image resident comes first.
-bool plan_layout(int nc_pad, int kq, int kr, int kf, int g_tiles, StreamLayout* out) {
+bool plan_layout(int nc_pad, int kq, int kr, int g_tiles, StreamLayout* out) {
   const size_t stage_bytes = (size_t)A_STAGE_BYTES + (size_t)nc_pad * BLOCK_K;
-  const size_t tile_bytes = (size_t)kGalTile * kf * 2;
-  const size_t aimg_bytes = (size_t)ef::round_up((int64_t)BLOCK_M * kf * 2, 1024);
+  const size_t tile_bytes = (size_t)kGalTile * kr * sizeof(float);
   struct Cand { int stages, recv_bufs, resident, ring; };
-  const Cand cands[] = {{4, 2, 1, 0}, {4, 1, 1, 0}, {3, 2, 1, 0}, {3, 1, 1, 0}, {4, 2, 0, 4},
+  const Cand cands[] = {{5, 2, 1, 0}, {4, 2, 1, 0}, {4, 1, 1, 0}, {3, 2, 1, 0}, {3, 1, 1, 0}, {4, 2, 0, 4},
                         {4, 1, 0, 4}, {3, 2, 0, 4}, {3, 1, 0, 3}, {3, 1, 0, 2}, {2, 1, 0, 2}};
   const char* e_st = getenv("EF_STREAM_STAGES");
   const char* e_res = getenv("EF_STREAM_RESIDENT");
@@ -652,17 +609,16 @@ bool plan_layout(int nc_pad, int kq, int kr, int kf, int g_tiles, StreamLayout* 
     if (e_st && atoi(e_st) != c.stages) continue;
     if (e_res && atoi(e_res) != c.resident) continue;
     if (e_rb && atoi(e_rb) != c.recv_bufs) continue;
-    int ring = c.resident ? g_tiles : std::min(c.ring, 2 * g_tiles);
+    int ring = c.resident ? g_tiles : std::min(c.ring, g_tiles);
     if (ring > kMaxRing || ring < 1) continue;
-    if (!c.resident && ring < 2) continue;
+    if (!c.resident && ring < 2 && g_tiles >= 2) continue;
     size_t off = (size_t)c.stages * stage_bytes;
     StreamLayout L{};
     L.stages = c.stages; L.recv_bufs = c.recv_bufs; L.ring = ring; L.resident = c.resident;
     L.off_recv = (int)off; off += (size_t)c.recv_bufs * kCluster * kq * QB * 16;
     L.off_ps = (int)off;   off += sizeof(double) * kr * QB;
     L.off_pe = (int)off;   off += sizeof(double) * kr * QB;
-    off = (size_t)ef::round_up((int64_t)off, 1024);
-    L.off_aimg = (int)off; off += aimg_bytes;
+    off = (size_t)ef::round_up((int64_t)off, 128);
     L.off_gal = (int)off;  off += (size_t)ring * tile_bytes;
     off = (size_t)ef::round_up((int64_t)off, 128);
     L.off_sh = (int)off;
@@ -670,6 +626,16 @@ bool plan_layout(int nc_pad, int kq, int kr, int kf, int g_tiles, StreamLayout* 
     if (L.smem <= (size_t)kSmemLimit) { *out = L; return true; }
   }
   return false;
+}
+
+// prepared gallery -> float32 unit rows [n_pad][kr] (zero rows / zero padding stay zero)
+__global__ void stream_gallery_kernel(const double* __restrict__ gp, int kr, const double* __restrict__ ginv, int n, int k,
+                                      int metric, float* __restrict__ img) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (long long)n * kr) return;
+  const int j = (int)(e / kr), c = (int)(e - (long long)j * kr);
+  const double scale = metric == EF_METRIC_COSINE_G1 ? ginv[j] : 1.0;
+  img[e] = c < k ? (float)(gp[e] * scale) : 0.f;
 }
 
 template <int METRIC, int KR>
@@ -756,10 +722,24 @@ int stream_plane_stride(int S) { return S <= 4 ? 4 : 8; }
 
 bool stream_supported(int D, int k, int kq, int S, int metric, int64_t n) {
   const int nc_pad = (int)round_up((int64_t)kq * stream_plane_stride(S), 16);
-  if (metric == EF_METRIC_L2 || k > 21 || nc_pad > kAccCols || n <= 0 || n >= (1ll << 31) - 512) return false;
-  if (filter_kf(k) > 64 || ceil_div(D, BLOCK_K) < kCluster) return false;
+  if (metric == EF_METRIC_L2 || k > 24 || nc_pad > kAccCols || n <= 0 || n >= (1ll << 31) - 512) return false;
+  if (ceil_div(D, BLOCK_K) < kCluster) return false;
   StreamLayout L;
-  return plan_layout(nc_pad, kq, fused_epilogue_kpad(k), filter_kf(k), (int)ceil_div(n, kGalTile), &L);
+  return plan_layout(nc_pad, kq, fused_epilogue_kpad(k), (int)ceil_div(n, kGalTile), &L);
+}
+
+size_t stream_gallery_bytes(int k, int64_t n) {
+  return (size_t)ceil_div(n, kGalTile) * kGalTile * (size_t)fused_epilogue_kpad(k) * sizeof(float);
+}
+
+// float32 image of a prepared gallery (gp [n][kr], rows normalised for COSINE_SK; ginv = 1/|g| for COSINE_G1)
+int stream_gallery_image(const double* gp, int kr, const double* ginv, int64_t n, int k, int metric, void* img,
+                         cudaStream_t stream) {
+  if (n <= 0) return EF_OK;
+  EF_CUDA(cudaMemsetAsync(img, 0, stream_gallery_bytes(k, n), stream));
+  EF_LAUNCH(stream_gallery_kernel, (unsigned)ceil_div(n * kr, 256), 256, 0, stream, gp, kr, ginv, (int)n, k, metric,
+            reinterpret_cast<float*>(img));
+  return EF_OK;
 }
 
 // One persistent launch over nb <= kStreamMaxBatches queued batches.  EF_ERR_UNSUPPORTED outside the kernel's coverage.
@@ -770,7 +750,7 @@ int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t
   using namespace ef_tc;
   if (nb <= 0) return EF_OK;
   if (nb > kStreamMaxBatches) return EF_ERR_INVALID;
-  if (!stream_supported(D, k, kq, S, metric, n) || kpad != fused_epilogue_kpad(k)) return EF_ERR_UNSUPPORTED;
+  if (!stream_supported(D, k, kq, S, metric, n) || kpad != fused_epilogue_kpad(k) || kpad > 24) return EF_ERR_UNSUPPORTED;
   const int PS = stream_plane_stride(S);
   const int nc_pad = (int)round_up((int64_t)kq * PS, 16);
   if (nc_pad > wfm_rows || (ldw & 15) || (reinterpret_cast<uintptr_t>(Wfm) & 15)) return EF_ERR_UNSUPPORTED;
@@ -791,17 +771,16 @@ int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t
   if (!make_map(&a.map_w, Wfm, (uint64_t)ldw, (uint64_t)wfm_rows, (uint64_t)ldw, (uint32_t)nc_pad)) return EF_ERR_UNSUPPORTED;
   StreamLayout L;
   const int g_tiles = (int)ceil_div(n, kGalTile);
-  if (!plan_layout(nc_pad, kq, kpad, filter_kf(k), g_tiles, &L)) return EF_ERR_UNSUPPORTED;
+  if (!plan_layout(nc_pad, kq, kpad, g_tiles, &L)) return EF_ERR_UNSUPPORTED;
   a.nb = nb; a.D = D; a.nc_pad = nc_pad; a.k = k; a.kq = kq; a.S = S; a.PS = PS;
   a.kb_total = (int)ceil_div(D, BLOCK_K);
   a.stages = L.stages; a.recv_bufs = L.recv_bufs; a.ring = L.ring; a.resident = L.resident;
   a.col_exp = col_exp; a.bias = bias; a.c0 = c0;
   a.gp = gp_padded; a.gnorm = gnorm; a.ginv = ginv; a.labels = labels; a.n = (int)n;
-  a.kf = filter_kf(k); a.g_tiles = g_tiles;
-  a.gimg = reinterpret_cast<const __half*>(gimg);
+  a.g_tiles = g_tiles;
+  a.gimg = reinterpret_cast<const float*>(gimg);
   a.status = status;
-  a.off_recv = L.off_recv; a.off_ps = L.off_ps; a.off_pe = L.off_pe; a.off_aimg = L.off_aimg; a.off_gal = L.off_gal;
-  a.off_sh = L.off_sh;
+  a.off_recv = L.off_recv; a.off_ps = L.off_ps; a.off_pe = L.off_pe; a.off_gal = L.off_gal; a.off_sh = L.off_sh;
   const int m_tiles = (int)ceil_div(max_B, BLOCK_M);
   switch (metric) {
     case EF_METRIC_COSINE_SK: return dispatch_kr<EF_METRIC_COSINE_SK>(a, L, kpad, m_tiles, stream);

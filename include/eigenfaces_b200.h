@@ -284,6 +284,25 @@ typedef struct ef_gen2_fit {
 int ef_fit_gen2_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_t k, const ef_gen2_fit_t* out,
                      ef_fit_info_t* info);
 
+/* The scripts/manual generation of the same trainer -- ManualStandardScaler + ManualPCA.fit_transform,
+ * scripts/manual/train-v2.py:9-72, called at :189-193 -- on uint8 crops.  Differences to ef_fit_gen2_host: scale_ is
+ * np.std (population) with EXACT zeros mapped to 1 (:61-62; sklearn also maps near-constant columns), and the components
+ * are the leading eigenvectors of np.cov (:25-36), i.e. the same directions as the SVD's with the sign left to LAPACK by
+ * the reference (here: the svd_flip rule, so results are deterministic).  explained_variance_ratio = lambda_i / sum of ALL
+ * eigenvalues (:39-40).  k <= min(N, D): beyond the rank the reference returns arbitrary null-space vectors.  scaler_var
+ * receives scale_^2 before the zero rule. */
+int ef_fit_manual_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_t k, const ef_gen2_fit_t* out,
+                       ef_fit_info_t* info);
+/* PCA(k, solver full).fit_transform / ManualPCA.fit_transform of an arbitrary float64 host matrix Z [N][ldz] (what the
+ * estimator objects receive when a caller scales the data itself: train-v5.py:373, scripts/manual/train-v2.py:193).
+ * Only pca_mean, components, explained_variance(_ratio), singular_values, noise_variance, features of `out` are
+ * written (the other pointers may be NULL). */
+int ef_pca_fit_f64_host(const double* Z, int64_t ldz, int32_t N, int32_t D, int32_t k, const ef_gen2_fit_t* out,
+                        ef_fit_info_t* info);
+/* StandardScaler.fit (flavour 0) / ManualStandardScaler.fit (flavour 1) alone, on uint8 crops: mean, var, scale [D]. */
+int ef_scaler_fit_u8_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_t flavour, double* mean,
+                          double* var, double* scale);
+
 /* ----------------------------------------------------------------- fit building blocks (device pointers) */
 /* Used by the row-sharded multi-GPU fit: each rank calls these on its rows, the partial sums are
  * all-reduced (NCCL) between the calls. */
