@@ -467,40 +467,54 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
         if (!ok) continue;
         const float* gt = reinterpret_cast<const float*>(gal + (size_t)slot * gal_tile_bytes) + (size_t)(fw * 32) * KR;
         const int j0 = t * kGalTile + fw * 32;
-#pragma unroll 4
-        for (int r = 0; r < 32; ++r) {
-          const float4* g4 = reinterpret_cast<const float4*>(gt + r * KR);
-          float sc = 0.f;
+        // groups of 8 rows: the 8 scores are formed first (independent fmaf chains, no side effects, so the loads and
+        // the arithmetic of a group pipeline freely), one comparison of their maximum against the band decides whether
+        // the rare candidate bookkeeping (shared-memory stores the compiler must order against the gallery loads) runs
+#pragma unroll 1
+        for (int r0 = 0; r0 < 32; r0 += 8) {
+          float sc[8];
 #pragma unroll
-          for (int c4 = 0; c4 < KR / 4; ++c4) {
-            const float4 gv = g4[c4];                // all lanes read the same row: shared-memory broadcast
-            sc = fmaf(ph[4 * c4], gv.x, sc);
-            sc = fmaf(ph[4 * c4 + 1], gv.y, sc);
-            sc = fmaf(ph[4 * c4 + 2], gv.z, sc);
-            sc = fmaf(ph[4 * c4 + 3], gv.w, sc);
+          for (int u = 0; u < 8; ++u) {
+            const float4* g4 = reinterpret_cast<const float4*>(gt + (r0 + u) * KR);
+            float acc = 0.f;
+#pragma unroll
+            for (int c4 = 0; c4 < KR / 4; ++c4) {
+              const float4 gv = g4[c4];              // all lanes read the same row: shared-memory broadcast
+              acc = fmaf(ph[4 * c4], gv.x, acc);
+              acc = fmaf(ph[4 * c4 + 1], gv.y, acc);
+              acc = fmaf(ph[4 * c4 + 2], gv.z, acc);
+              acc = fmaf(ph[4 * c4 + 3], gv.w, acc);
+            }
+            sc[u] = acc;
           }
-          const int j = j0 + r;
-          if (j < a.n && sc >= m - band) {           // rare after the first rows
-            if (sc > m) m = sc;
-            if (cnt == kCandCap) {                   // drop what fell out of the band of the running maximum
-              const float lim = m - band;
-              int w = 0;
-              for (int i = 0; i < kCandCap; ++i) {
-                const float cs = sh->cand_s[i][ftid];
-                if (cs >= lim) {
-                  sh->cand_s[w][ftid] = cs;
-                  sh->cand_j[w][ftid] = sh->cand_j[i][ftid];
-                  ++w;
+          const float gm = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])), fmaxf(fmaxf(sc[4], sc[5]), fmaxf(sc[6], sc[7])));
+          if (gm >= m - band) {                      // rare after the first rows
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+              const int j = j0 + r0 + u;
+              if (j < a.n && sc[u] >= m - band) {
+                if (sc[u] > m) m = sc[u];
+                if (cnt == kCandCap) {               // drop what fell out of the band of the running maximum
+                  const float lim = m - band;
+                  int w = 0;
+                  for (int i = 0; i < kCandCap; ++i) {
+                    const float cs = sh->cand_s[i][ftid];
+                    if (cs >= lim) {
+                      sh->cand_s[w][ftid] = cs;
+                      sh->cand_j[w][ftid] = sh->cand_j[i][ftid];
+                      ++w;
+                    }
+                  }
+                  cnt = w;
+                }
+                if (cnt < kCandCap) {
+                  sh->cand_s[cnt][ftid] = sc[u];
+                  sh->cand_j[cnt][ftid] = j;
+                  ++cnt;
+                } else {
+                  spill = true;                      // more than kCandCap rows of one crop inside the band: exact scan
                 }
               }
-              cnt = w;
-            }
-            if (cnt < kCandCap) {
-              sh->cand_s[cnt][ftid] = sc;
-              sh->cand_j[cnt][ftid] = j;
-              ++cnt;
-            } else {
-              spill = true;                          // more than kCandCap rows of one crop inside the band: exact scan
             }
           }
         }

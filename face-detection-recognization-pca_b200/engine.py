@@ -347,8 +347,7 @@ def fit_gen1(X, n_components=None):
                                                       "off_norm": info.off_norm, "gpu_ms": info.gpu_ms}
 
 
-def fit_gen2(X, n_components):
-    """Device StandardScaler + PCA(full) (train-v5.py:349-385).  Returns a dict of float64 arrays + info."""
+def _fit_gen2_like(entry, X, n_components):
     X = _check_u8(X)
     N, D = X.shape
     k = int(n_components)
@@ -360,7 +359,84 @@ def fit_gen2(X, n_components):
     }
     g = Gen2Fit(**{name: _ptr(arr) for name, arr in out.items()})
     info = FitInfo()
-    check(_lib.lib().ef_fit_gen2_host(_ptr(X), X.strides[0], N, D, k, C.byref(g), C.byref(info)), "ef_fit_gen2_host")
+    check(getattr(_lib.lib(), entry)(_ptr(X), X.strides[0], N, D, k, C.byref(g), C.byref(info)), entry)
     out["noise_variance"] = float(out["noise_variance"][0])
     out["info"] = {"sweeps": info.sweeps, "branch": info.branch, "off_norm": info.off_norm, "gpu_ms": info.gpu_ms}
     return out
+
+
+def fit_gen2(X, n_components):
+    """Device StandardScaler + PCA(full) (train-v5.py:349-385).  Returns a dict of float64 arrays + info."""
+    return _fit_gen2_like("ef_fit_gen2_host", X, n_components)
+
+
+def fit_manual(X, n_components):
+    """Device ManualStandardScaler + ManualPCA (scripts/manual/train-v2.py:9-72, :189-193).  Same dict as fit_gen2."""
+    return _fit_gen2_like("ef_fit_manual_host", X, n_components)
+
+
+def pca_fit_f64(Z, n_components):
+    """PCA(k, full).fit_transform / ManualPCA.fit_transform of a float64 matrix on the device (ef_pca_fit_f64_host)."""
+    Z = np.ascontiguousarray(np.asarray(Z, dtype=np.float64))
+    if Z.ndim != 2:
+        raise ValueError("data matrix must be [N, D]")
+    N, D = Z.shape
+    k = int(n_components)
+    out = {"pca_mean": np.empty(D), "components": np.empty((k, D)), "explained_variance": np.empty(k),
+           "explained_variance_ratio": np.empty(k), "singular_values": np.empty(k), "noise_variance": np.empty(1),
+           "features": np.empty((N, k))}
+    g = Gen2Fit(**{name: _ptr(arr) for name, arr in out.items()})
+    info = FitInfo()
+    check(_lib.lib().ef_pca_fit_f64_host(_ptr(Z), Z.strides[0] // 8, N, D, k, C.byref(g), C.byref(info)), "ef_pca_fit_f64_host")
+    out["noise_variance"] = float(out["noise_variance"][0])
+    out["info"] = {"sweeps": info.sweeps, "branch": info.branch, "off_norm": info.off_norm, "gpu_ms": info.gpu_ms}
+    return out
+
+
+def scaler_fit_u8(X, flavour=0):
+    """StandardScaler.fit (flavour 0) / ManualStandardScaler.fit (1) on 8-bit crops: (mean, var, scale)."""
+    X = _check_u8(X)
+    N, D = X.shape
+    mean, var, scale = np.empty(D), np.empty(D), np.empty(D)
+    check(_lib.lib().ef_scaler_fit_u8_host(_ptr(X), X.strides[0], N, D, int(flavour), _ptr(mean), _ptr(var), _ptr(scale)),
+          "ef_scaler_fit_u8_host")
+    return mean, var, scale
+
+
+def standardize_u8(X, mean, scale=None):
+    """(X - mean) / scale of 8-bit crops on the device (ef_standardize_u8_device) -> float64 [N, D] numpy."""
+    import torch
+    X = _check_u8(X)
+    N, D = X.shape
+    dev = torch.device("cuda", torch.cuda.current_device())
+    xd = torch.from_numpy(X).to(dev)
+    md = torch.from_numpy(_f64(mean)).to(dev)
+    sd = torch.from_numpy(_f64(scale)).to(dev) if scale is not None else None
+    z = torch.empty((N, D), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    check(_lib.lib().ef_standardize_u8_device(xd.data_ptr(), xd.stride(0), N, D, md.data_ptr(),
+                                              sd.data_ptr() if sd is not None else None, None, z.data_ptr(), D,
+                                              C.c_void_p(stream)), "ef_standardize_u8_device")
+    return z.cpu().numpy()
+
+
+def project_f64(Z, components, mean):
+    """(Z - mean) . components^T on the device (two ef_dgemm_device calls: Z C^T, then the rank-one mean term)."""
+    import torch
+    Z = np.atleast_2d(np.asarray(Z, dtype=np.float64))
+    Cm = _f64(components)
+    k, D = Cm.shape
+    N = Z.shape[0]
+    dev = torch.device("cuda", torch.cuda.current_device())
+    zd = torch.from_numpy(np.ascontiguousarray(Z)).to(dev)
+    cd = torch.from_numpy(Cm).to(dev)
+    md = torch.from_numpy(_f64(mean)).reshape(1, D).to(dev)
+    ones = torch.ones((N, 1), dtype=torch.float64, device=dev)
+    bias = torch.empty((1, k), dtype=torch.float64, device=dev)
+    out = torch.empty((N, k), dtype=torch.float64, device=dev)
+    L = _lib.lib()
+    stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    check(L.ef_dgemm_device(1, k, D, 1.0, md.data_ptr(), D, 1, cd.data_ptr(), 1, D, 0.0, bias.data_ptr(), k, stream), "dgemm")
+    check(L.ef_dgemm_device(N, k, D, 1.0, zd.data_ptr(), D, 1, cd.data_ptr(), 1, D, 0.0, out.data_ptr(), k, stream), "dgemm")
+    check(L.ef_dgemm_device(N, k, 1, -1.0, ones.data_ptr(), 1, 1, bias.data_ptr(), k, 1, 1.0, out.data_ptr(), k, stream), "dgemm")
+    return out.cpu().numpy()

@@ -51,8 +51,21 @@ def _model_arrays(model_data):
     return pca, scaler
 
 
+_CACHE_MAX = 32
+
+
+def _cache_put(key, entry):
+    """Bounded cache (a long-running scanner reloads its models: load_all_models unpickles new dicts every time): the
+    oldest entry goes first and its device model is released."""
+    while len(_CACHE) >= _CACHE_MAX:
+        old = _CACHE.pop(next(iter(_CACHE)))
+        if len(old) > 1 and hasattr(old[1], "close"):
+            old[1].close()
+    _CACHE[key] = entry
+
+
 def recognizer_for(model_data, n_slices=0):
-    """Device model for a Gen-2 model dict (cached per dict object)."""
+    """Device model for a Gen-2 model dict (cached per dict object, bounded)."""
     key = (id(model_data), n_slices)
     hit = _CACHE.get(key)
     if hit is not None and hit[0] is model_data:
@@ -61,7 +74,7 @@ def recognizer_for(model_data, n_slices=0):
     rec = engine.Recognizer(pca.components_, scaler.mean_, model_data['face_features'], scale=scaler.scale_,
                             pca_mean=pca.mean_, labels=model_data['face_labels'], metric=METRIC_COSINE_SK,
                             basis_is_components=True, n_slices=n_slices, with_residual=True)
-    _CACHE[key] = (model_data, rec)
+    _cache_put(key, (model_data, rec))
     return rec
 
 
@@ -441,30 +454,34 @@ class MultiModelFaceScanner:
         return best_id.tolist(), best_name.tolist(), best_conf.tolist()
 
 
-def match_features(features, model_data):
-    """features [B,k] float64 -> (score [B], index [B]) with sklearn-cosine argmax on the device."""
+def match_features(features, model_data, metric=METRIC_COSINE_SK, cache=True):
+    """features [B,k] float64 -> (score [B], index [B]) with the cosine argmax of `metric` on the device (sklearn rule by
+    default; METRIC_COSINE_G1 = dot / (|a| |b|) with zero norm -> 0.0, the manual scripts' rule)."""
     import ctypes as C
     import torch
     from . import _lib
     L = _lib.lib()
     dev = torch.device("cuda", torch.cuda.current_device())
-    key = ("gal", id(model_data))
-    hit = _CACHE.get(key)
+    key = ("gal", id(model_data), metric)
+    hit = _CACHE.get(key) if cache else None
     gal = np.asarray(model_data['face_features'], dtype=np.float64)
     n, k = gal.shape
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     if hit is None or hit[0] is not model_data:
         g = torch.from_numpy(np.ascontiguousarray(gal)).to(dev)
         gp = torch.empty_like(g)
-        _lib.check(L.ef_gallery_prepare_device(g.data_ptr(), k, n, k, METRIC_COSINE_SK, gp.data_ptr(), k, None, stream),
+        gn = torch.zeros(n, dtype=torch.float64, device=dev)
+        _lib.check(L.ef_gallery_prepare_device(g.data_ptr(), k, n, k, metric, gp.data_ptr(), k, gn.data_ptr(), stream),
                    "ef_gallery_prepare_device")
-        _CACHE[key] = hit = (model_data, gp)
-    gp = hit[1]
+        hit = (model_data, gp, gn)
+        if cache:
+            _cache_put(key, hit)
+    gp, gn = hit[1], hit[2]
     p = torch.from_numpy(np.ascontiguousarray(features, dtype=np.float64)).to(dev)
     B = p.shape[0]
     score = torch.empty(B, dtype=torch.float64, device=dev)
     index = torch.empty(B, dtype=torch.int64, device=dev)
-    _lib.check(L.ef_match_device(p.data_ptr(), k, B, k, gp.data_ptr(), k, None, n, 0, METRIC_COSINE_SK,
+    _lib.check(L.ef_match_device(p.data_ptr(), k, B, k, gp.data_ptr(), k, gn.data_ptr(), n, 0, metric,
                                  score.data_ptr(), index.data_ptr(), None, stream), "ef_match_device")
     return score.cpu().numpy(), index.cpu().numpy()
 
