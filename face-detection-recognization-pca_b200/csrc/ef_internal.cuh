@@ -81,9 +81,7 @@ struct StreamBatchDesc {
   double threshold;
 };
 int stream_plane_stride(int S);
-size_t stream_gallery_bytes(int k, int64_t n);      // float32 unit-row image of the prepared gallery, read by the filter
-int stream_gallery_image(const double* gp, int kr, const double* ginv, int64_t n, int k, int metric, void* img,
-                         cudaStream_t stream);
+
 bool stream_supported(int D, int k, int kq, int S, int metric, int64_t n);
 int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t* Wfm, int64_t ldw, int wfm_rows, int k,
                      int kq, int S, const int32_t* col_exp, const double* bias, double c0, const double* gp_padded,

@@ -65,7 +65,6 @@ struct ef_model {
   // queued submission (ef_model_submit_device with the persistent serving kernel): descriptors of the batches waiting
   // for their launch, all submitted on queue_stream; launched when queue_depth of them are waiting or at flush
   ef::DevBuf wq_fm;                // feature-major copy of the digit planes (row c * PS + s), read by the serving kernel
-  ef::DevBuf gimg32;               // float32 unit-row image of the gallery for the serving kernel's filter
   int nc_fm = 0;
   std::vector<ef::StreamBatchDesc> queue;
   cudaStream_t queue_stream = nullptr;
@@ -259,14 +258,7 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
       st = ef::gallery_image(m->gp.as<double>(), m->kpad, m->ginv.as<double>(), desc->n_gallery, k, m->metric,
                              m->gimg.p, m->stream);
   }
-  if (st == EF_OK && m->metric != EF_METRIC_L2 && ef::fused_epilogue_supported(k, desc->n_gallery) &&
-      ef::stream_supported(D, k, m->kq, m->S, m->metric, desc->n_gallery)) {
-    st = m->gimg32.ensure(ef::stream_gallery_bytes(k, desc->n_gallery));
-    if (st == EF_OK)
-      st = ef::stream_gallery_image(m->gp.as<double>(), m->kpad, m->ginv.as<double>(), desc->n_gallery, k, m->metric,
-                                    m->gimg32.p, m->stream);
-    m->stream_ok = st == EF_OK;
-  }
+  m->stream_ok = st == EF_OK && m->gimg.p && ef::stream_supported(D, k, m->kq, m->S, m->metric, desc->n_gallery);
   if (st == EF_OK) {
     cudaError_t e = cudaStreamSynchronize(m->stream);
     if (e != cudaSuccess) { ef::set_error_detail("gallery_prepare", e); st = EF_ERR_CUDA; }
@@ -531,7 +523,7 @@ static int queue_launch(ef_model_t* m) {
   const int nb = (int)m->queue.size();
   const int stq = ef::recognize_stream(m->queue.data(), nb, m->D, m->wq_fm.as<int8_t>(), m->ldw, m->nc_fm, m->k, m->kq,
                                        m->S, m->col_exp.as<int32_t>(), m->bias.as<double>(), m->c0, m->gp.as<double>(),
-                                       m->kpad, m->gnorm.as<double>(), m->ginv.as<double>(), m->gimg32.p, m->n_gallery,
+                                       m->kpad, m->gnorm.as<double>(), m->ginv.as<double>(), m->gimg.p, m->n_gallery,
                                        labels, m->metric, m->status.as<int>(), m->queue_stream);
   m->queue.clear();
   if (stq == EF_OK) {
@@ -556,7 +548,7 @@ int ef_model_submit_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t
   if (out->resid2 && !m->with_residual) return EF_ERR_INVALID;
   const bool aligned = !(ldx & 15) && !(reinterpret_cast<uintptr_t>(x) & 15);
   cudaStream_t st = ef::as_stream(stream);
-  if (m->serving_kernel == 0 && m->tc_mode >= 2 && aligned && m->gimg32.p && m->stream_ok) {
+  if (m->serving_kernel == 0 && m->tc_mode >= 2 && aligned && m->gimg.p && m->stream_ok) {
     // persistent serving kernel: the batch joins the queue; the launch happens when the queue is full or at flush
     if (m->pending.B > 0) EF_TRY(ef_model_flush_device(m, stream));
     if (!m->queue.empty() && m->queue_stream != st) EF_TRY(ef_model_flush_device(m, stream));

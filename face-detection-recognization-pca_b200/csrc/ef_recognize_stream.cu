@@ -9,20 +9,24 @@
 //   warp 1        tcgen05.mma kind::i8 issuer; TWO TMEM accumulators (item it -> buffer it & 1): the MMAs of batch i+1
 //                 start while batch i is still being drained
 //   warps 2..5    exact sum of squares of every crop from the staged tiles (dp4a), pushed to the owning CTA per item
-//   warp 6        float32 image of the normalised gallery -> shared memory (resident when it fits, else a
-//                 cp.async.bulk ring)
+//   warp 6        float16 [g_hi | g_lo | g_hi] image of the gallery -> shared memory, once per launch (resident)
+//   warp 7        tcgen05.mma kind::f16 issuer of the nearest-row filter
 //   warps 8..11   drain: TMEM -> registers -> digit planes combined to TWO exact int64 per column (ef::planes_to_hilo:
 //                 2.2 x fewer bytes than the eight int32 planes) -> 16-byte st.shared::cluster into the receive buffer of
 //                 the CTA that owns those 32 crops -> remote mbarrier arrive (release.cluster)
 //   warps 12..15  finish: wait for the four partial slabs of MY 32 crops (acquire.cluster), exact integer sum, float64
-//                 features (+ reconstruction error), ONE pass of a float32 CUDA-core filter over the gallery (lane =
-//                 crop, features in registers, gallery rows broadcast from shared memory, running maximum + the rows
-//                 within the error band of it), the exact float64 re-score of those rows and score / index / label --
-//                 all while warps 0..11 already work on the next batch.
-// (The first version ran the filter as tcgen05 kind::f16 MMAs like recognize_pipe_kernel.  Measured: every filter MMA
-// queues behind the projection MMAs of the following batches in the one tensor pipe, 16 dependent round trips of ~0.8 us
-// per item made the finish warps the bottleneck at 13-15 us per batch.  The filter is 0.3 MFLOP per crop: on the idle
-// FP32 pipe it needs no round trips at all.)
+//                 features (+ reconstruction error), the float16 [hi|hi|lo] filter operand of MY 32 crops, then -- after
+//                 ONE round trip to the tensor pipe -- the scan of the filter scores in TMEM, the exact float64 re-score
+//                 of the rows inside the error band and score / index / label; all while warps 0..11 already work on
+//                 the next batch.
+// The filter is laid out the other way round than in recognize_cluster_kernel / recognize_pipe_kernel: the GALLERY rows
+// are the M operand (128 rows per MMA, straight from the resident image) and the CTA's 32 crops the N operand, so the
+// scores of one item against up to 1024 gallery rows are 8 MMA blocks of 32 TMEM columns = 256 columns, issued back to
+// back and committed once.  Measured reasons: (1) with the crops on M (replicated 4 x to fill 128 lanes) every 128-row
+// gallery tile was its own MMA -> commit -> scan -> release round trip behind the queued projection MMAs of the
+// following batches, 16 of them per item (13-15 us per batch); (2) the replicated scores cost 4 x the TMEM read bandwidth
+// (64 B / clk / SM); (3) a float32 CUDA-core filter from shared memory starves: TMA writes, MMA operand reads and the
+// sum-of-squares reads of the stream already keep the shared-memory port ~90 % busy (20 us per item for the scan alone).
 // A cluster of 4 CTAs owns crop tile `m` of EVERY queued batch (CTA r streams K quarter r and finishes crops 32r..32r+31),
 // so the per-CTA state machines of a cluster advance through the same item sequence and the cross-CTA barriers need no
 // item tags.  All arithmetic is the one of recognize_cluster_kernel / recognize_pipe_kernel (same integers, same
@@ -53,17 +57,13 @@ constexpr int kThreads = kWarps * 32;
 constexpr int QB = BLOCK_M / kCluster;      // crops finished by each CTA (one per lane)
 static_assert(QB == 32, "one crop per lane");
 constexpr int kGalTile = 128;               // gallery rows per filter MMA
-constexpr int kMaxRing = 16;                // gallery tiles in shared memory (resident gallery: up to 2048 rows)
+constexpr int kMaxGalBlocks = 8;            // 128-row blocks of the resident gallery image: 8 x 32 score columns of TMEM
 constexpr int kListCap = 128;
 constexpr int kFinishWarps = 4;
 constexpr int kFinishThreads = kFinishWarps * 32;
 constexpr int kAccCols = 128;               // TMEM columns per accumulator buffer (nc_pad <= 128)
-constexpr int kCandCap = 8;                 // filter candidates a thread keeps (pruned against the running maximum)
-// Filter error bound: features and gallery rows are unit vectors rounded to float32 (2^-24 relative per component), the
-// k <= 24 products are accumulated with fmaf (2^-24 relative per step), the feature normalisation uses rsqrtf (one
-// common factor 1 + 2^-22 on all scores of a crop): |s~ - cos| < 4e-6.  5e-5 (the band of the tensor-core filters) covers
-// it with a wide margin; a too-large value only costs extra float64 re-scores, never correctness.
-constexpr float kFilterEps = 5e-5f;
+constexpr float kFilterEps = 5e-5f;         // same bound as recognize_cluster_kernel (derived there)
+constexpr int kScoreCol0 = 2 * kAccCols;    // TMEM columns 256..511: 8 blocks (128 gallery rows each) x 32 crops
 
 struct StreamBatch {
   CUtensorMap map;             // crops of this batch: [B][ldx] bytes, box 128 rows x 128 bytes, SWIZZLE_128B
@@ -88,10 +88,10 @@ struct StreamArgs {
   const double* gnorm;
   const double* ginv;
   const int32_t* labels;
-  int n, ring, g_tiles, resident;
-  const float* gimg;           // float32 image of the normalised gallery [g_tiles * 128][KR]
+  int n, kf, g_tiles;
+  const __half* gimg;          // float16 [g_hi | g_lo | g_hi] image of the prepared gallery (gallery_image)
   int* status;
-  int off_recv, off_ps, off_pe, off_gal, off_sh;
+  int off_recv, off_ps, off_pe, off_bop, off_gal, off_sh;
   unsigned long long* probe;   // debugging aid (EF_TC_PROBE): [grid][8] globaltimer stamps
 };
 
@@ -102,8 +102,9 @@ struct StreamShared {
   unsigned long long acc_empty[2];
   unsigned long long recv_full[2];            // arrived on by the drain + sum-of-squares lanes of all four CTAs
   unsigned long long push_ok[2][kCluster];    // [receive buffer][owner]: owner consumed that buffer (remote arrive)
-  unsigned long long gal_full[kMaxRing];
-  unsigned long long gal_empty[kMaxRing];
+  unsigned long long gal_full;                // the resident gallery image has landed (once per launch)
+  unsigned long long bop_ready;               // finish warps: the filter operand of the next item is in place
+  unsigned long long scores_full;             // filter MMAs of the item committed
   uint32_t tmem_base;
   int failed;
   int list_cnt, overflow;
@@ -111,8 +112,7 @@ struct StreamShared {
   double xu[QB];
   unsigned long long ssq_recv[2][kCluster][QB];
   float fmax_s[kFinishWarps][QB];
-  int cand_j[kCandCap][kFinishThreads];          // per-thread candidate rows of the filter pass ([slot][thread]: no conflicts)
-  float cand_s[kCandCap][kFinishThreads];
+  alignas(16) float thr_s[QB];
   int list_L[kListCap], list_j[kListCap], list_label[kListCap];
   double list_key[kListCap], list_score[kListCap];
   int red_l[kFinishWarps][QB];
@@ -151,6 +151,20 @@ __device__ __forceinline__ void exact_entry(const double* __restrict__ gp, const
   label = labels ? __ldg(labels + j) : j;
 }
 
+__device__ __forceinline__ void split_half(float v, __half& hi, __half& lo) {
+  hi = __float2half_rn(v);
+  lo = __float2half_rn(v - __half2float(hi));
+}
+
+// order-preserving map float -> unsigned (for redux.sync max)
+__device__ __forceinline__ unsigned f2ord(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
+
 __device__ __forceinline__ void bar_finish() { asm volatile("bar.sync 5, 128;" ::: "memory"); }
 
 template <int PS>
@@ -184,7 +198,8 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   uint8_t* recv = smem + a.off_recv;                              // [recv_bufs][4 sources][kq][32 crops] (hi, lo) int64
   double* ps = reinterpret_cast<double*>(smem + a.off_ps);        // [KR][QB] features of the item being finished
   double* pe = reinterpret_cast<double*>(smem + a.off_pe);        // [KR][QB] the same as the exact scorer uses them
-  uint8_t* gal = smem + a.off_gal;
+  uint8_t* bop = smem + a.off_bop;                                // filter N operand: my 32 crops x kf float16 [hi|hi|lo]
+  uint8_t* gal = smem + a.off_gal;                                // resident gallery image: g_tiles x 128 rows x kf float16
   StreamShared* sh = reinterpret_cast<StreamShared*>(smem + a.off_sh);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -193,8 +208,8 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   const int row0 = m_tile * BLOCK_M;
   const int kb0 = (int)((long long)a.kb_total * rank / kCluster);
   const int kb1 = (int)((long long)a.kb_total * (rank + 1) / kCluster);
-  const uint32_t gal_tile_bytes = (uint32_t)(kGalTile * KR * sizeof(float));
-  const int n_seq = a.g_tiles;                     // one filter pass over the gallery per item
+  const int row_bytes = a.kf * 2;
+  const uint32_t gal_tile_bytes = (uint32_t)kGalTile * (uint32_t)row_bytes;
   const uint32_t recv_buf_bytes = (uint32_t)(kCluster * a.kq * QB * 16);
 
   if (tid == 0) {
@@ -208,10 +223,9 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       mbar_init(&sh->recv_full[s], kCluster * 2 * QB);   // 4 sources x (32 drain lanes + 32 sum-of-squares lanes)
       for (int q = 0; q < kCluster; ++q) mbar_init(&sh->push_ok[s][q], 1);
     }
-    for (int s = 0; s < kMaxRing; ++s) {
-      mbar_init(&sh->gal_full[s], 1);
-      mbar_init(&sh->gal_empty[s], kFinishWarps);
-    }
+    mbar_init(&sh->gal_full, 1);
+    mbar_init(&sh->bop_ready, 1);
+    mbar_init(&sh->scores_full, 1);
     sh->failed = 0;
     sh->list_cnt = 0;
     sh->overflow = 0;
@@ -220,7 +234,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
-                 "r"(2u * kAccCols)
+                 "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -232,7 +246,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   asm volatile("griddepcontrol.wait;" ::: "memory"); // the crops may have been written by the previous kernel
   const uint32_t tmem_base = sh->tmem_base;
   volatile int* failed = &sh->failed;
-  unsigned long long* probe = a.probe ? a.probe + (size_t)blockIdx.x * 8 : nullptr;
+  unsigned long long* probe = a.probe ? a.probe + (size_t)blockIdx.x * 16 : nullptr;
   if (probe && tid == 0) probe[0] = globaltimer();
 
   if (warp == 0) {
@@ -324,33 +338,48 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       ++it;
     }
   } else if (warp == 6) {
-    // =================================================================== float16 gallery image -> shared memory
+    // =================================================================== float16 gallery image -> shared memory (once)
     if (lane == 0) {
       int n_items = 0;
       for (int g = 0; g < a.nb; ++g) n_items += row0 < a.batch[g].B ? 1 : 0;
-      const uint8_t* img = reinterpret_cast<const uint8_t*>(a.gimg);   // [g_tiles] tiles of 128 rows x KR floats
-      if (a.resident) {
-        if (n_items > 0)
-          for (int t = 0; t < a.g_tiles; ++t) {
-            mbar_arrive_expect_tx(&sh->gal_full[t], gal_tile_bytes);
-            bulk_load(gal + (size_t)t * gal_tile_bytes, img + (size_t)t * gal_tile_bytes, gal_tile_bytes, &sh->gal_full[t]);
-          }
-      } else {
-        const long long total = (long long)n_items * n_seq;
-        int slot = 0, t = 0;
-        uint32_t use_parity = 1;                     // parity of the (use - 1)-th release; a fresh barrier passes parity 1
-        for (long long s = 0; s < total; ++s) {
-          if (!mbar_wait(&sh->gal_empty[slot], use_parity, failed)) break;
-          mbar_arrive_expect_tx(&sh->gal_full[slot], gal_tile_bytes);
-          bulk_load(gal + (size_t)slot * gal_tile_bytes, img + (size_t)t * gal_tile_bytes, gal_tile_bytes, &sh->gal_full[slot]);
-          if (++slot == a.ring) { slot = 0; use_parity ^= 1; }
-          if (++t == a.g_tiles) t = 0;
-        }
+      if (n_items > 0) {
+        const uint32_t bytes = (uint32_t)a.g_tiles * gal_tile_bytes;
+        mbar_arrive_expect_tx(&sh->gal_full, bytes);
+        bulk_load(gal, a.gimg, bytes, &sh->gal_full);
       }
     }
     __syncwarp();
   } else if (warp == 7) {
-    // spare warp
+    // =================================================================== filter MMA issuer: one burst per item
+    if (lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(QB);     // M = 128 gallery rows, N = 32 crops
+      const int n_ks = a.kf >> 4;
+      const int swb = row_bytes < 128 ? row_bytes : 128;
+      const int pa_mask = (swb >> 5) - 1;            // k-steps per swizzle atom - 1 (row_bytes <= 128: one atom)
+      const uint64_t gdesc0 = umma_desc_swz(smem_u32(gal), 0, row_bytes, kGalTile);
+      const uint64_t cdesc0 = umma_desc_swz(smem_u32(bop), 0, row_bytes, QB);
+      const uint64_t tile_step = (uint64_t)(gal_tile_bytes >> 4);
+      int it = 0;
+      bool ok = true;
+      for (int g = 0; g < a.nb && ok; ++g) {
+        if (row0 >= a.batch[g].B) continue;
+        if (it == 0 && !mbar_wait(&sh->gal_full, 0u, failed)) break;
+        if (!mbar_wait(&sh->bop_ready, (uint32_t)(it & 1), failed)) break;
+        tc_fence_after();
+        for (int blk = 0; blk < a.g_tiles; ++blk) {
+          const uint32_t d_addr = tmem_base + (uint32_t)(kScoreCol0 + blk * QB);
+          const uint64_t gd = gdesc0 + (uint64_t)blk * tile_step;
+#pragma unroll 1
+          for (int ks = 0; ks < n_ks; ++ks) {
+            const uint64_t koff = (uint64_t)((ks & pa_mask) << 1);
+            umma_f16(d_addr, gd + koff, cdesc0 + koff, idesc, ks > 0 ? 1u : 0u);
+          }
+        }
+        umma_commit(&sh->scores_full);
+        ++it;
+      }
+    }
+    __syncwarp();
   } else if (warp < 12) {
     // =================================================================== drain: TMEM -> (hi, lo) -> owner's receive buffer
     const int q = warp & 3;                          // TMEM lane quarter = crops 32 q .. 32 q + 31 = CTA q's crops
@@ -385,7 +414,6 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
     // =================================================================== finish: features, filter scan, exact re-score
     const int fw = warp - (kWarps - kFinishWarps), ftid = tid - (kWarps - kFinishWarps) * 32;
     int it = 0;
-    unsigned int gs = 0;
     bool ok = true;
     for (int g = 0; g < a.nb; ++g) {
       const StreamBatch& bt = a.batch[g];
@@ -395,6 +423,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       const bool want_resid = bt.out_resid != nullptr;
       const int rb = it % a.recv_bufs, use = it / a.recv_bufs;
       ok = __all_sync(0xffffffffu, ok && mbar_wait_cluster(&sh->recv_full[rb], (uint32_t)(use & 1), failed));
+      if (probe && ftid == 0 && (it == 0 || it == 4)) probe[it == 0 ? 7 : 11] = globaltimer();
       // ---- exact integer sum of the four K quarters, float64 features (columns fw, fw + 4, ...)
       const longlong2* rbase = reinterpret_cast<const longlong2*>(recv + (size_t)rb * recv_buf_bytes) + lane;
       for (int c = fw; c < max(a.kq, KR); c += kFinishWarps) {
@@ -448,95 +477,86 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       auto consider = [&](double key, double score, int label, int j) {
         if (better<METRIC>(key, j, best, best_i)) { best = key; best_score = score; best_label = label; best_i = j; }
       };
-      // ---- float32 filter, one pass: running maximum of this warp's rows and the rows within the band of it
-      float ph[KR];
       {
+        // filter N operand: row `lane` = my crop, K = [hi | hi | lo] of the unit feature vector (float32 is plenty: the
+        // filter is approximate by construction); chunks of 8 halfs, warp fw writes chunks fw, fw + 4, ...
         const float rinv = n2 > 0.0 ? rsqrtf((float)n2) : 0.f;
+        const int KC = a.kf >> 3;
+        for (int kc = fw; kc < KC; kc += kFinishWarps) {
+          __align__(16) __half h[8];
 #pragma unroll
-        for (int c = 0; c < KR; ++c) ph[c] = (float)ps[c * QB + lane] * rinv;
-      }
-      const float band = 2.f * kFilterEps;
-      float m = -CUDART_INF_F;
-      int cnt = 0;
-      bool spill = false;
-      for (int t = 0; t < n_seq; ++t, ++gs) {
-        int slot;
-        uint32_t par;
-        if (a.resident) { slot = t; par = 0u; } else { slot = (int)(gs % (unsigned)a.ring); par = (gs / (unsigned)a.ring) & 1u; }
-        ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->gal_full[slot], par, failed));
-        if (!ok) continue;
-        const float* gt = reinterpret_cast<const float*>(gal + (size_t)slot * gal_tile_bytes) + (size_t)(fw * 32) * KR;
-        const int j0 = t * kGalTile + fw * 32;
-        // groups of 8 rows: the 8 scores are formed first (independent fmaf chains, no side effects, so the loads and
-        // the arithmetic of a group pipeline freely), one comparison of their maximum against the band decides whether
-        // the rare candidate bookkeeping (shared-memory stores the compiler must order against the gallery loads) runs
-#pragma unroll 1
-        for (int r0 = 0; r0 < 32; r0 += 8) {
-          float sc[8];
-#pragma unroll
-          for (int u = 0; u < 8; ++u) {
-            const float4* g4 = reinterpret_cast<const float4*>(gt + (r0 + u) * KR);
-            float acc = 0.f;
-#pragma unroll
-            for (int c4 = 0; c4 < KR / 4; ++c4) {
-              const float4 gv = g4[c4];              // all lanes read the same row: shared-memory broadcast
-              acc = fmaf(ph[4 * c4], gv.x, acc);
-              acc = fmaf(ph[4 * c4 + 1], gv.y, acc);
-              acc = fmaf(ph[4 * c4 + 2], gv.z, acc);
-              acc = fmaf(ph[4 * c4 + 3], gv.w, acc);
-            }
-            sc[u] = acc;
+          for (int i = 0; i < 8; ++i) {
+            const int kk = kc * 8 + i;
+            const int seg = kk >= 3 * a.k ? 3 : (kk >= 2 * a.k ? 2 : (kk >= a.k ? 1 : 0));
+            __half hi = __float2half_rn(0.f), lo = hi;
+            if (seg < 3) split_half((float)ps[(kk - seg * a.k) * QB + lane] * rinv, hi, lo);
+            h[i] = seg < 2 ? hi : lo;
           }
-          const float gm = fmaxf(fmaxf(fmaxf(sc[0], sc[1]), fmaxf(sc[2], sc[3])), fmaxf(fmaxf(sc[4], sc[5]), fmaxf(sc[6], sc[7])));
-          if (gm >= m - band) {                      // rare after the first rows
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-              const int j = j0 + r0 + u;
-              if (j < a.n && sc[u] >= m - band) {
-                if (sc[u] > m) m = sc[u];
-                if (cnt == kCandCap) {               // drop what fell out of the band of the running maximum
-                  const float lim = m - band;
-                  int w = 0;
-                  for (int i = 0; i < kCandCap; ++i) {
-                    const float cs = sh->cand_s[i][ftid];
-                    if (cs >= lim) {
-                      sh->cand_s[w][ftid] = cs;
-                      sh->cand_j[w][ftid] = sh->cand_j[i][ftid];
-                      ++w;
-                    }
-                  }
-                  cnt = w;
-                }
-                if (cnt < kCandCap) {
-                  sh->cand_s[cnt][ftid] = sc[u];
-                  sh->cand_j[cnt][ftid] = j;
-                  ++cnt;
-                } else {
-                  spill = true;                      // more than kCandCap rows of one crop inside the band: exact scan
-                }
-              }
-            }
-          }
+          *reinterpret_cast<uint4*>(bop + swz_chunk_offset(lane, kc, row_bytes, QB)) = *reinterpret_cast<const uint4*>(h);
         }
-        if (!a.resident) {
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&sh->gal_empty[slot]);
-        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
-      sh->fmax_s[fw][lane] = m;
-      if (spill) sh->overflow = 1;
+      tc_fence_before();                             // the score columns of the previous item have been read (pass B)
       bar_finish();
+      if (ftid == 0) mbar_arrive(&sh->bop_ready);
+      if (probe && ftid == 0 && (it == 0 || it == 4)) probe[it == 0 ? 8 : 12] = globaltimer();
+      // ---- scores[gallery row][crop] are in TMEM: lane = gallery row 32 fw + lane of every 128-row block
+      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->scores_full, (uint32_t)(it & 1), failed));
+      tc_fence_after();
+      const uint32_t sc_addr = tmem_base + ((uint32_t)(fw * 32) << 16) + (uint32_t)kScoreCol0;
       {
+        // pass A: approximate maximum per crop over my rows, then over the warp (redux) and the four warps
+        float mx[QB];
+#pragma unroll
+        for (int c = 0; c < QB; ++c) mx[c] = -CUDART_INF_F;
+        for (int blk = 0; blk < a.g_tiles && ok; ++blk) {
+          uint32_t v[32];
+          tmem_ld32(sc_addr + (uint32_t)(blk * QB), v);
+          if (blk * kGalTile + fw * 32 + lane < a.n) {
+#pragma unroll
+            for (int c = 0; c < QB; ++c) mx[c] = fmaxf(mx[c], __uint_as_float(v[c]));
+          }
+        }
+        float mine = -CUDART_INF_F;
+#pragma unroll
+        for (int c = 0; c < QB; ++c) {
+          const unsigned r = __reduce_max_sync(0xffffffffu, f2ord(mx[c]));
+          if (c == lane) mine = ord2f(r);
+        }
+        sh->fmax_s[fw][lane] = mine;                 // maximum of crop `lane` over this warp's rows
+      }
+      bar_finish();
+      if (fw == 0) {
         float M = sh->fmax_s[0][lane];
 #pragma unroll
         for (int w = 1; w < kFinishWarps; ++w) M = fmaxf(M, sh->fmax_s[w][lane]);
-        const float thr = M - band;
-        for (int i = 0; i < cnt; ++i) {
-          if (sh->cand_s[i][ftid] >= thr) {
+        sh->thr_s[lane] = M - 2.f * kFilterEps;
+      }
+      bar_finish();
+      if (probe && ftid == 0 && (it == 0 || it == 4)) probe[it == 0 ? 9 : 13] = globaltimer();
+      {
+        // pass B: rows inside the band of the maximum -> re-score list
+        float thr[QB];
+#pragma unroll
+        for (int c4 = 0; c4 < QB / 4; ++c4) {
+          const float4 t4 = reinterpret_cast<const float4*>(sh->thr_s)[c4];
+          thr[4 * c4] = t4.x; thr[4 * c4 + 1] = t4.y; thr[4 * c4 + 2] = t4.z; thr[4 * c4 + 3] = t4.w;
+        }
+        for (int blk = 0; blk < a.g_tiles && ok; ++blk) {
+          uint32_t v[32];
+          tmem_ld32(sc_addr + (uint32_t)(blk * QB), v);
+          const int j = blk * kGalTile + fw * 32 + lane;
+          unsigned mask = 0u;
+#pragma unroll
+          for (int c = 0; c < QB; ++c) mask |= (__uint_as_float(v[c]) >= thr[c] ? 1u : 0u) << c;
+          if (j >= a.n) mask = 0u;
+          while (mask) {
+            const int c = __ffs(mask) - 1;
+            mask &= mask - 1u;
             const int slot = atomicAdd(&sh->list_cnt, 1);
             if (slot < kListCap) {
-              sh->list_L[slot] = lane;
-              sh->list_j[slot] = sh->cand_j[i][ftid];
+              sh->list_L[slot] = c;
+              sh->list_j[slot] = j;
             } else {
               sh->overflow = 1;
             }
@@ -565,6 +585,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
           consider(key, score, label, j);
         }
       }
+      if (probe && ftid == 0 && (it == 0 || it == 4)) probe[it == 0 ? 10 : 14] = globaltimer();
       sh->red_s[fw][lane] = best;
       sh->red_d[fw][lane] = best_score;
       sh->red_i[fw][lane] = best_i;
@@ -586,6 +607,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
         if (bt.out_label) bt.out_label[b] = score >= bt.threshold ? bl : -1;
       }
       if (probe && ftid == 0) probe[it == 0 ? 4 : 5] = globaltimer();
+      if (probe && ftid == 0 && it == 4) probe[15] = globaltimer();
       bar_finish();                                  // red_* / list_* / pn are rewritten by the next item
       ++it;
     }
@@ -597,59 +619,45 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   cluster_sync_all();                               // no CTA leaves while a peer may still write or arrive into it
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * kAccCols) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
   if (tid == 0 && sh->failed) atomicExch(a.status, 1);
   if (probe && tid == 0) probe[6] = globaltimer();
 }
 
 struct StreamLayout {
-  int stages, recv_bufs, ring, resident;
-  int off_recv, off_ps, off_pe, off_gal, off_sh;
+  int stages, recv_bufs;
+  int off_recv, off_ps, off_pe, off_bop, off_gal, off_sh;
   size_t smem;
 };
 
-// Shared-memory plan: the deepest stage ring with the gallery image resident comes first.
-bool plan_layout(int nc_pad, int kq, int kr, int g_tiles, StreamLayout* out) {
+// Shared-memory plan: the deepest stage ring that leaves room for the resident gallery image.
+bool plan_layout(int nc_pad, int kq, int kr, int kf, int g_tiles, StreamLayout* out) {
   const size_t stage_bytes = (size_t)A_STAGE_BYTES + (size_t)nc_pad * BLOCK_K;
-  const size_t tile_bytes = (size_t)kGalTile * kr * sizeof(float);
-  struct Cand { int stages, recv_bufs, resident, ring; };
-  const Cand cands[] = {{5, 2, 1, 0}, {4, 2, 1, 0}, {4, 1, 1, 0}, {3, 2, 1, 0}, {3, 1, 1, 0}, {4, 2, 0, 4},
-                        {4, 1, 0, 4}, {3, 2, 0, 4}, {3, 1, 0, 3}, {3, 1, 0, 2}, {2, 1, 0, 2}};
+  const size_t tile_bytes = (size_t)kGalTile * kf * 2;
+  const size_t bop_bytes = (size_t)ef::round_up((int64_t)QB * kf * 2, 1024);
+  struct Cand { int stages, recv_bufs; };
+  const Cand cands[] = {{5, 2}, {4, 2}, {4, 1}, {3, 2}, {3, 1}, {2, 1}};
   const char* e_st = getenv("EF_STREAM_STAGES");
-  const char* e_res = getenv("EF_STREAM_RESIDENT");
   const char* e_rb = getenv("EF_STREAM_RECV_BUFS");
   for (const Cand& c : cands) {
     if (e_st && atoi(e_st) != c.stages) continue;
-    if (e_res && atoi(e_res) != c.resident) continue;
     if (e_rb && atoi(e_rb) != c.recv_bufs) continue;
-    int ring = c.resident ? g_tiles : std::min(c.ring, g_tiles);
-    if (ring > kMaxRing || ring < 1) continue;
-    if (!c.resident && ring < 2 && g_tiles >= 2) continue;
     size_t off = (size_t)c.stages * stage_bytes;
     StreamLayout L{};
-    L.stages = c.stages; L.recv_bufs = c.recv_bufs; L.ring = ring; L.resident = c.resident;
+    L.stages = c.stages; L.recv_bufs = c.recv_bufs;
     L.off_recv = (int)off; off += (size_t)c.recv_bufs * kCluster * kq * QB * 16;
     L.off_ps = (int)off;   off += sizeof(double) * kr * QB;
     L.off_pe = (int)off;   off += sizeof(double) * kr * QB;
-    off = (size_t)ef::round_up((int64_t)off, 128);
-    L.off_gal = (int)off;  off += (size_t)ring * tile_bytes;
+    off = (size_t)ef::round_up((int64_t)off, 1024);
+    L.off_bop = (int)off;  off += bop_bytes;
+    L.off_gal = (int)off;  off += (size_t)g_tiles * tile_bytes;
     off = (size_t)ef::round_up((int64_t)off, 128);
     L.off_sh = (int)off;
     L.smem = off + sizeof(StreamShared);
     if (L.smem <= (size_t)kSmemLimit) { *out = L; return true; }
   }
   return false;
-}
-
-// prepared gallery -> float32 unit rows [n_pad][kr] (zero rows / zero padding stay zero)
-__global__ void stream_gallery_kernel(const double* __restrict__ gp, int kr, const double* __restrict__ ginv, int n, int k,
-                                      int metric, float* __restrict__ img) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (e >= (long long)n * kr) return;
-  const int j = (int)(e / kr), c = (int)(e - (long long)j * kr);
-  const double scale = metric == EF_METRIC_COSINE_G1 ? ginv[j] : 1.0;
-  img[e] = c < k ? (float)(gp[e] * scale) : 0.f;
 }
 
 template <int METRIC, int KR>
@@ -669,8 +677,8 @@ int launch_stream(StreamArgs& a, const StreamLayout& L, int m_tiles, cudaStream_
   const int grid_n = m_tiles * kCluster;
   a.probe = nullptr;
   if (probing && grid_n <= 4096) {
-    if (!probe_buf[dev]) EF_CUDA(cudaMalloc(&probe_buf[dev], sizeof(unsigned long long) * 8 * 4096));
-    EF_CUDA(cudaMemsetAsync(probe_buf[dev], 0, sizeof(unsigned long long) * 8 * 4096, stream));
+    if (!probe_buf[dev]) EF_CUDA(cudaMalloc(&probe_buf[dev], sizeof(unsigned long long) * 16 * 4096));
+    EF_CUDA(cudaMemsetAsync(probe_buf[dev], 0, sizeof(unsigned long long) * 16 * 4096, stream));
     a.probe = probe_buf[dev];
   }
   cudaLaunchConfig_t cfg{};
@@ -690,22 +698,23 @@ int launch_stream(StreamArgs& a, const StreamLayout& L, int m_tiles, cudaStream_
   EF_CUDA(cudaLaunchKernelEx(&cfg, recognize_stream_kernel<METRIC, KR>, a));
   ef::g_launches.fetch_add(1, std::memory_order_relaxed);
   if (a.probe) {
-    std::vector<unsigned long long> h((size_t)grid_n * 8);
+    std::vector<unsigned long long> h((size_t)grid_n * 16);
     EF_CUDA(cudaStreamSynchronize(stream));
     EF_CUDA(cudaMemcpy(h.data(), probe_buf[dev], h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     unsigned long long t0 = ~0ull;
-    for (int c = 0; c < grid_n; ++c) if (h[(size_t)c * 8] && h[(size_t)c * 8] < t0) t0 = h[(size_t)c * 8];
-    const char* names[8] = {"start", "mma_first_item", "mma_last_item", "last_push", "first_item_out", "last_item_out",
-                            "end", "-"};
-    fprintf(stderr, "[ef_stream_probe] grid %d batches %d stages %d recv_bufs %d ring %d resident %d smem %zu; us since first CTA start (mean/max):",
-            grid_n, a.nb, a.stages, a.recv_bufs, a.ring, a.resident, L.smem);
-    for (int i = 0; i < 8; ++i) {
+    for (int c = 0; c < grid_n; ++c) if (h[(size_t)c * 16] && h[(size_t)c * 16] < t0) t0 = h[(size_t)c * 16];
+    const char* names[16] = {"start", "mma_first_item", "mma_last_item", "last_push", "first_item_out", "last_item_out",
+                             "end", "i0_recv", "i0_features", "i0_scanned", "i0_rescored", "i4_recv", "i4_features",
+                             "i4_scanned", "i4_rescored", "i4_out"};
+    fprintf(stderr, "[ef_stream_probe] grid %d batches %d stages %d recv_bufs %d gallery blocks %d smem %zu; us since first CTA start (mean/max):",
+            grid_n, a.nb, a.stages, a.recv_bufs, a.g_tiles, L.smem);
+    for (int i = 0; i < 16; ++i) {
       if (names[i][0] == '-') continue;
       double sum = 0, mx = 0;
       int cnt = 0;
       for (int c = 0; c < grid_n; ++c) {
-        if (!h[(size_t)c * 8 + i]) continue;
-        const double v = (double)(h[(size_t)c * 8 + i] - t0) * 1e-3;
+        if (!h[(size_t)c * 16 + i]) continue;
+        const double v = (double)(h[(size_t)c * 16 + i] - t0) * 1e-3;
         sum += v;
         ++cnt;
         if (v > mx) mx = v;
@@ -736,24 +745,10 @@ int stream_plane_stride(int S) { return S <= 4 ? 4 : 8; }
 
 bool stream_supported(int D, int k, int kq, int S, int metric, int64_t n) {
   const int nc_pad = (int)round_up((int64_t)kq * stream_plane_stride(S), 16);
-  if (metric == EF_METRIC_L2 || k > 24 || nc_pad > kAccCols || n <= 0 || n >= (1ll << 31) - 512) return false;
-  if (ceil_div(D, BLOCK_K) < kCluster) return false;
+  if (metric == EF_METRIC_L2 || k > 21 || nc_pad > kAccCols || n <= 0 || n > (int64_t)kMaxGalBlocks * kGalTile) return false;
+  if (filter_kf(k) > 64 || ceil_div(D, BLOCK_K) < kCluster) return false;
   StreamLayout L;
-  return plan_layout(nc_pad, kq, fused_epilogue_kpad(k), (int)ceil_div(n, kGalTile), &L);
-}
-
-size_t stream_gallery_bytes(int k, int64_t n) {
-  return (size_t)ceil_div(n, kGalTile) * kGalTile * (size_t)fused_epilogue_kpad(k) * sizeof(float);
-}
-
-// float32 image of a prepared gallery (gp [n][kr], rows normalised for COSINE_SK; ginv = 1/|g| for COSINE_G1)
-int stream_gallery_image(const double* gp, int kr, const double* ginv, int64_t n, int k, int metric, void* img,
-                         cudaStream_t stream) {
-  if (n <= 0) return EF_OK;
-  EF_CUDA(cudaMemsetAsync(img, 0, stream_gallery_bytes(k, n), stream));
-  EF_LAUNCH(stream_gallery_kernel, (unsigned)ceil_div(n * kr, 256), 256, 0, stream, gp, kr, ginv, (int)n, k, metric,
-            reinterpret_cast<float*>(img));
-  return EF_OK;
+  return plan_layout(nc_pad, kq, fused_epilogue_kpad(k), filter_kf(k), (int)ceil_div(n, kGalTile), &L);
 }
 
 // One persistent launch over nb <= kStreamMaxBatches queued batches.  EF_ERR_UNSUPPORTED outside the kernel's coverage.
@@ -765,6 +760,7 @@ int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t
   if (nb <= 0) return EF_OK;
   if (nb > kStreamMaxBatches) return EF_ERR_INVALID;
   if (!stream_supported(D, k, kq, S, metric, n) || kpad != fused_epilogue_kpad(k) || kpad > 24) return EF_ERR_UNSUPPORTED;
+  if (reinterpret_cast<uintptr_t>(gimg) & 15) return EF_ERR_UNSUPPORTED;
   const int PS = stream_plane_stride(S);
   const int nc_pad = (int)round_up((int64_t)kq * PS, 16);
   if (nc_pad > wfm_rows || (ldw & 15) || (reinterpret_cast<uintptr_t>(Wfm) & 15)) return EF_ERR_UNSUPPORTED;
@@ -785,16 +781,17 @@ int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t
   if (!make_map(&a.map_w, Wfm, (uint64_t)ldw, (uint64_t)wfm_rows, (uint64_t)ldw, (uint32_t)nc_pad)) return EF_ERR_UNSUPPORTED;
   StreamLayout L;
   const int g_tiles = (int)ceil_div(n, kGalTile);
-  if (!plan_layout(nc_pad, kq, kpad, g_tiles, &L)) return EF_ERR_UNSUPPORTED;
+  if (!plan_layout(nc_pad, kq, kpad, filter_kf(k), g_tiles, &L)) return EF_ERR_UNSUPPORTED;
   a.nb = nb; a.D = D; a.nc_pad = nc_pad; a.k = k; a.kq = kq; a.S = S; a.PS = PS;
   a.kb_total = (int)ceil_div(D, BLOCK_K);
-  a.stages = L.stages; a.recv_bufs = L.recv_bufs; a.ring = L.ring; a.resident = L.resident;
+  a.stages = L.stages; a.recv_bufs = L.recv_bufs;
   a.col_exp = col_exp; a.bias = bias; a.c0 = c0;
   a.gp = gp_padded; a.gnorm = gnorm; a.ginv = ginv; a.labels = labels; a.n = (int)n;
-  a.g_tiles = g_tiles;
-  a.gimg = reinterpret_cast<const float*>(gimg);
+  a.kf = filter_kf(k); a.g_tiles = g_tiles;
+  a.gimg = reinterpret_cast<const __half*>(gimg);
   a.status = status;
-  a.off_recv = L.off_recv; a.off_ps = L.off_ps; a.off_pe = L.off_pe; a.off_gal = L.off_gal; a.off_sh = L.off_sh;
+  a.off_recv = L.off_recv; a.off_ps = L.off_ps; a.off_pe = L.off_pe; a.off_bop = L.off_bop; a.off_gal = L.off_gal;
+  a.off_sh = L.off_sh;
   const int m_tiles = (int)ceil_div(max_B, BLOCK_M);
   switch (metric) {
     case EF_METRIC_COSINE_SK: return dispatch_kr<EF_METRIC_COSINE_SK>(a, L, kpad, m_tiles, stream);
