@@ -11,14 +11,16 @@
 //   warps 2..5    exact sum of squares of every crop from the staged tiles (dp4a), pushed to the owning CTA per item
 //   warp 6        float16 [g_hi | g_lo | g_hi] image of the gallery -> shared memory, once per launch (resident)
 //   warp 7        tcgen05.mma kind::f16 issuer of the nearest-row filter
-//   warps 8..11   drain: TMEM -> registers -> digit planes combined to TWO exact int64 per column (ef::planes_to_hilo:
-//                 2.2 x fewer bytes than the eight int32 planes) -> 16-byte st.shared::cluster into the receive buffer of
-//                 the CTA that owns those 32 crops -> remote mbarrier arrive (release.cluster)
-//   warps 12..15  finish: wait for the four partial slabs of MY 32 crops (acquire.cluster), exact integer sum, float64
-//                 features (+ reconstruction error), the float16 [hi|hi|lo] filter operand of MY 32 crops, then -- after
-//                 ONE round trip to the tensor pipe -- the scan of the filter scores in TMEM, the exact float64 re-score
-//                 of the rows inside the error band and score / index / label; all while warps 0..11 already work on
-//                 the next batch.
+//   warps 8..11   drain + combine: TMEM -> registers -> digit planes combined to TWO exact int64 per column
+//                 (ef::planes_to_hilo: 2.2 x fewer bytes than the eight int32 planes) -> 16-byte st.shared::cluster into
+//                 the receive buffer of the CTA that owns those 32 crops -> remote mbarrier arrive (release.cluster);
+//                 then, for MY 32 crops: wait for the four partial slabs (acquire.cluster), exact integer sum, float64
+//                 features (+ reconstruction error), exact-scorer vectors and the float16 [hi|hi|lo] filter operand
+//                 (double buffered)
+//   warps 12..15  match: after ONE round trip to the tensor pipe per item the scan of the filter scores in TMEM
+//                 (approximate maximum per crop, then the rows inside the error band), the exact float64 re-score of
+//                 those rows, best row per crop through shared-memory atomics, score / index / label
+// -- three pipeline stages per CTA (stream, combine, match) working on three consecutive batches at a time.
 // The filter is laid out the other way round than in recognize_cluster_kernel / recognize_pipe_kernel: the GALLERY rows
 // are the M operand (128 rows per MMA, straight from the resident image) and the CTA's 32 crops the N operand, so the
 // scores of one item against up to 1024 gallery rows are 8 MMA blocks of 32 TMEM columns = 256 columns, issued back to
@@ -60,7 +62,6 @@ constexpr int kGalTile = 128;               // gallery rows per filter MMA
 constexpr int kMaxGalBlocks = 8;            // 128-row blocks of the resident gallery image: 8 x 32 score columns of TMEM
 constexpr int kListCap = 128;
 constexpr int kFinishWarps = 4;
-constexpr int kFinishThreads = kFinishWarps * 32;
 constexpr int kAccCols = 128;               // TMEM columns per accumulator buffer (nc_pad <= 128)
 constexpr float kFilterEps = 5e-5f;         // same bound as recognize_cluster_kernel (derived there)
 constexpr int kScoreCol0 = 2 * kAccCols;    // TMEM columns 256..511: 8 blocks (128 gallery rows each) x 32 crops
@@ -103,22 +104,22 @@ struct StreamShared {
   unsigned long long recv_full[2];            // arrived on by the drain + sum-of-squares lanes of all four CTAs
   unsigned long long push_ok[2][kCluster];    // [receive buffer][owner]: owner consumed that buffer (remote arrive)
   unsigned long long gal_full;                // the resident gallery image has landed (once per launch)
-  unsigned long long bop_ready;               // finish warps: the filter operand of the next item is in place
+  unsigned long long bop_ready[2];            // combine warps: the filter operand of item it is in place ([it & 1])
   unsigned long long scores_full;             // filter MMAs of the item committed
+  unsigned long long scores_free;             // match warps: the score columns have been read
+  unsigned long long feat_ready[2];           // combine warps: exact-scorer vectors + norms of item it ([it & 1])
+  unsigned long long feat_free[2];            // match warps: done with feature buffer [it & 1]
+  unsigned long long best_key[QB];            // per crop: ordered-integer image of the best exact key of the item
+  int best_j[QB];
   uint32_t tmem_base;
   int failed;
   int list_cnt, overflow;
-  double pn[QB];
+  double pn[2][QB];
   double xu[QB];
   unsigned long long ssq_recv[2][kCluster][QB];
   float fmax_s[kFinishWarps][QB];
   alignas(16) float thr_s[QB];
-  int list_L[kListCap], list_j[kListCap], list_label[kListCap];
-  double list_key[kListCap], list_score[kListCap];
-  int red_l[kFinishWarps][QB];
-  double red_s[kFinishWarps][QB];
-  double red_d[kFinishWarps][QB];
-  int red_i[kFinishWarps][QB];
+  int list_L[kListCap], list_j[kListCap];
 };
 
 template <int METRIC>
@@ -165,7 +166,14 @@ __device__ __forceinline__ float ord2f(unsigned u) {
   return __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
 }
 
-__device__ __forceinline__ void bar_finish() { asm volatile("bar.sync 5, 128;" ::: "memory"); }
+// order-preserving map double -> unsigned 64-bit (for atomicMax on the exact keys)
+__device__ __forceinline__ unsigned long long d2ord(double d) {
+  const unsigned long long u = (unsigned long long)__double_as_longlong(d);
+  return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ void bar_finish() { asm volatile("bar.sync 5, 128;" ::: "memory"); }   // match warps
+__device__ __forceinline__ void bar_front() { asm volatile("bar.sync 6, 128;" ::: "memory"); }    // drain + combine warps
 
 template <int PS>
 __device__ __forceinline__ void push_chunk(const uint32_t (&v)[16], int c0, int kq, uint32_t dst) {
@@ -210,6 +218,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   const int kb1 = (int)((long long)a.kb_total * (rank + 1) / kCluster);
   const int row_bytes = a.kf * 2;
   const uint32_t gal_tile_bytes = (uint32_t)kGalTile * (uint32_t)row_bytes;
+  const uint32_t bop_bytes = ((uint32_t)(QB * row_bytes) + 1023u) & ~1023u;     // one of the two filter-operand buffers
   const uint32_t recv_buf_bytes = (uint32_t)(kCluster * a.kq * QB * 16);
 
   if (tid == 0) {
@@ -224,8 +233,14 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       for (int q = 0; q < kCluster; ++q) mbar_init(&sh->push_ok[s][q], 1);
     }
     mbar_init(&sh->gal_full, 1);
-    mbar_init(&sh->bop_ready, 1);
+    mbar_init(&sh->bop_ready[0], 1);
+    mbar_init(&sh->bop_ready[1], 1);
     mbar_init(&sh->scores_full, 1);
+    mbar_init(&sh->scores_free, 1);
+    mbar_init(&sh->feat_ready[0], 1);
+    mbar_init(&sh->feat_ready[1], 1);
+    mbar_init(&sh->feat_free[0], 1);
+    mbar_init(&sh->feat_free[1], 1);
     sh->failed = 0;
     sh->list_cnt = 0;
     sh->overflow = 0;
@@ -364,15 +379,17 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       for (int g = 0; g < a.nb && ok; ++g) {
         if (row0 >= a.batch[g].B) continue;
         if (it == 0 && !mbar_wait(&sh->gal_full, 0u, failed)) break;
-        if (!mbar_wait(&sh->bop_ready, (uint32_t)(it & 1), failed)) break;
+        if (!mbar_wait(&sh->bop_ready[it & 1], (uint32_t)((it >> 1) & 1), failed)) break;
+        if (!mbar_wait(&sh->scores_free, (uint32_t)((it & 1) ^ 1), failed)) break;   // match warps read item it - 1
         tc_fence_after();
+        const uint64_t cdesc = cdesc0 + (uint64_t)((it & 1) * (bop_bytes >> 4));
         for (int blk = 0; blk < a.g_tiles; ++blk) {
           const uint32_t d_addr = tmem_base + (uint32_t)(kScoreCol0 + blk * QB);
           const uint64_t gd = gdesc0 + (uint64_t)blk * tile_step;
 #pragma unroll 1
           for (int ks = 0; ks < n_ks; ++ks) {
             const uint64_t koff = (uint64_t)((ks & pa_mask) << 1);
-            umma_f16(d_addr, gd + koff, cdesc0 + koff, idesc, ks > 0 ? 1u : 0u);
+            umma_f16(d_addr, gd + koff, cdesc + koff, idesc, ks > 0 ? 1u : 0u);
           }
         }
         umma_commit(&sh->scores_full);
@@ -381,108 +398,117 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
     }
     __syncwarp();
   } else if (warp < 12) {
-    // =================================================================== drain: TMEM -> (hi, lo) -> owner's receive buffer
+    // =================================================================== drain + combine (warps 8..11, lane = crop)
+    // (1) TMEM -> (hi, lo) -> receive buffer of the CTA that owns the 32 crops of my TMEM lane quarter;
+    // (2) for MY CTA's 32 crops: exact integer sum of the four K quarters, float64 features, reconstruction error,
+    //     exact-scorer vector + norm and the float16 filter operand, double buffered for the match warps.
     const int q = warp & 3;                          // TMEM lane quarter = crops 32 q .. 32 q + 31 = CTA q's crops
-    int it = 0;
-    bool ok = true;
-    for (int g = 0; g < a.nb; ++g) {
-      if (row0 >= a.batch[g].B) continue;
-      const int buf = it & 1;
-      ok = __all_sync(0xffffffffu, mbar_wait(&sh->acc_full[buf], (uint32_t)((it >> 1) & 1), failed));
-      if (!ok) break;
-      tc_fence_after();
-      const int rb = it % a.recv_bufs, use = it / a.recv_bufs;
-      ok = __all_sync(0xffffffffu, mbar_wait_cluster(&sh->push_ok[rb][q], (uint32_t)((use & 1) ^ 1), failed));
-      if (!ok) break;
-      const uint32_t dst = map_to_cta(smem_u32(recv) + (uint32_t)rb * recv_buf_bytes +
-                                          (uint32_t)((int)rank * a.kq * QB + lane) * 16u,
-                                      (uint32_t)q);
-      const uint32_t src = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccCols);
-      for (int c0 = 0; c0 < a.nc_pad; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld16(src + (uint32_t)c0, v);
-        if (a.PS == 8) push_chunk<8>(v, c0, a.kq, dst); else push_chunk<4>(v, c0, a.kq, dst);
-      }
-      mbar_arrive_remote(map_to_cta(smem_u32(&sh->recv_full[rb]), (uint32_t)q));
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&sh->acc_empty[buf]);
-      if (probe && q == 0 && lane == 0) probe[3] = globaltimer();
-      ++it;
+    const int fw = q;                                // this warp combines columns fw, fw + 4, ...
+    constexpr int kColIters = 6;                     // columns per thread: kq <= 16, KR <= 24
+    double col_scale[kColIters], col_bias[kColIters];
+#pragma unroll
+    for (int i = 0; i < kColIters; ++i) {
+      const int c = fw + 4 * i;
+      // 2^e as a double: v * 2^e == ldexp(v, e) exactly (no overflow / underflow at these magnitudes)
+      col_scale[i] = c < a.kq ? __longlong_as_double((long long)(1023 + __ldg(a.col_exp + c)) << 52) : 0.0;
+      col_bias[i] = c < a.k ? __ldg(a.bias + c) : 0.0;
     }
-  } else {
-    // =================================================================== finish: features, filter scan, exact re-score
-    const int fw = warp - (kWarps - kFinishWarps), ftid = tid - (kWarps - kFinishWarps) * 32;
     int it = 0;
     bool ok = true;
     for (int g = 0; g < a.nb; ++g) {
       const StreamBatch& bt = a.batch[g];
       if (row0 >= bt.B) continue;
+      const int buf = it & 1;
+      // (after a failed wait the warp keeps walking through the items without touching the pipeline, so that the four
+      // warps still meet at every named barrier: a timeout must end in the status flag, never in a hang)
+      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->acc_full[buf], (uint32_t)((it >> 1) & 1), failed));
+      tc_fence_after();
+      const int rb = it % a.recv_bufs, use = it / a.recv_bufs;
+      ok = __all_sync(0xffffffffu, ok && mbar_wait_cluster(&sh->push_ok[rb][q], (uint32_t)((use & 1) ^ 1), failed));
+      if (ok) {
+        const uint32_t dst = map_to_cta(smem_u32(recv) + (uint32_t)rb * recv_buf_bytes +
+                                            (uint32_t)((int)rank * a.kq * QB + lane) * 16u,
+                                        (uint32_t)q);
+        const uint32_t src = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccCols);
+        for (int c0 = 0; c0 < a.nc_pad; c0 += 16) {
+          uint32_t v[16];
+          tmem_ld16(src + (uint32_t)c0, v);
+          if (a.PS == 8) push_chunk<8>(v, c0, a.kq, dst); else push_chunk<4>(v, c0, a.kq, dst);
+        }
+        mbar_arrive_remote(map_to_cta(smem_u32(&sh->recv_full[rb]), (uint32_t)q));
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh->acc_empty[buf]);
+        if (probe && q == 0 && lane == 0) probe[3] = globaltimer();
+      }
+      // ---- my CTA's 32 crops of this item
       const int b = row0 + (int)rank * QB + lane;    // the crop this lane finishes
       const bool live = b < bt.B;
-      const bool want_resid = bt.out_resid != nullptr;
-      const int rb = it % a.recv_bufs, use = it / a.recv_bufs;
+      const int fb = it & 1;                         // feature buffer handed to the match warps
       ok = __all_sync(0xffffffffu, ok && mbar_wait_cluster(&sh->recv_full[rb], (uint32_t)(use & 1), failed));
-      if (probe && ftid == 0 && (it == 0 || it == 4)) probe[it == 0 ? 7 : 11] = globaltimer();
-      // ---- exact integer sum of the four K quarters, float64 features (columns fw, fw + 4, ...)
+      if (probe && tid == 8 * 32 && (it == 0 || it == 4)) probe[it == 0 ? 7 : 11] = globaltimer();
       const longlong2* rbase = reinterpret_cast<const longlong2*>(recv + (size_t)rb * recv_buf_bytes) + lane;
-      for (int c = fw; c < max(a.kq, KR); c += kFinishWarps) {
-        double v = 0.0;
-        if (c < a.kq && ok) {
-          long long hi = 0, lo = 0;
 #pragma unroll
-          for (int src = 0; src < kCluster; ++src) {
-            const longlong2 p = rbase[(src * a.kq + c) * QB];
-            hi += p.x;
-            lo += p.y;
+      for (int i = 0; i < kColIters; ++i) {
+        const int c = fw + 4 * i;
+        if (c < max(a.kq, KR)) {
+          double v = 0.0;
+          if (c < a.kq && ok) {
+            long long hi = 0, lo = 0;
+#pragma unroll
+            for (int src = 0; src < kCluster; ++src) {
+              const longlong2 p = rbase[(src * a.kq + c) * QB];
+              hi += p.x;
+              lo += p.y;
+            }
+            v = ef::hilo_to_double(hi, lo) * col_scale[i];
+            if (c < a.k) {
+              v -= col_bias[i];
+              if (bt.out_proj && live) bt.out_proj[(size_t)b * a.k + c] = v;
+            } else {
+              sh->xu[lane] = v;                      // residual column x . u~
+            }
           }
-          v = ldexp(ef::hilo_to_double(hi, lo), __ldg(a.col_exp + c));
-          if (c < a.k) {
-            v -= __ldg(a.bias + c);
-            if (bt.out_proj && live) bt.out_proj[(size_t)b * a.k + c] = v;
-          } else {
-            sh->xu[lane] = v;                        // residual column x . u~
-          }
+          if (c < KR) ps[c * QB + lane] = c < a.k ? v : 0.0;   // padding columns (k .. KR) must be exact zeros
         }
-        if (c < KR) ps[c * QB + lane] = c < a.k ? v : 0.0;   // padding columns (k .. KR) must be exact zeros
       }
       unsigned long long ssq_total = 0;
       if (fw == 0) {
 #pragma unroll
         for (int src = 0; src < kCluster; ++src) ssq_total += sh->ssq_recv[rb][src][lane];
-        if (lane == 0) { sh->list_cnt = 0; sh->overflow = 0; }
       }
-      bar_finish();                                  // receive buffer consumed; features complete
+      bar_front();                                   // receive buffer consumed; features complete
       if (fw == 1 && lane < kCluster)                // hand the buffer back to the four sources
         mbar_arrive_remote(map_to_cta(smem_u32(&sh->push_ok[rb][rank]), (uint32_t)lane));
+      // the match warps are done with feature buffer fb (item it - 2)?
+      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->feat_free[fb], (uint32_t)(((it >> 1) & 1) ^ 1), failed));
+      double pv[KR];
+#pragma unroll
+      for (int c = 0; c < KR; ++c) pv[c] = ps[c * QB + lane];     // independent loads, then the ordered fma chain
       double n2 = 0.0;
-      for (int c = 0; c < a.k; ++c) n2 = fma(ps[c * QB + lane], ps[c * QB + lane], n2);
+#pragma unroll
+      for (int c = 0; c < KR; ++c) n2 = fma(pv[c], pv[c], n2);    // columns >= k are exact zeros: same sum as c < k
       double pn = sqrt(n2);
       if (METRIC == EF_METRIC_COSINE_SK && pn == 0.0) pn = 1.0;
-      for (int c = fw; c < KR; c += kFinishWarps) {
-        double v = ps[c * QB + lane];
-        if (METRIC == EF_METRIC_COSINE_SK) v = v / pn;
-        pe[c * QB + lane] = v;
-      }
+      double* pe_b = pe + (size_t)fb * KR * QB;
+#pragma unroll
+      for (int c = 0; c < KR; ++c)
+        if ((c & 3) == fw) pe_b[c * QB + lane] = METRIC == EF_METRIC_COSINE_SK ? pv[c] / pn : pv[c];
       if (fw == 0) {
-        sh->pn[lane] = pn;
-        if (want_resid && live) {
+        sh->pn[fb][lane] = pn;
+        if (bt.out_resid && live) {
           const double sq = bt.sumsq_ext ? bt.sumsq_ext[b] : (double)ssq_total;
           const double r = sq - 2.0 * sh->xu[lane] + a.c0 - n2;
           bt.out_resid[b] = r > 0.0 ? r : 0.0;
         }
       }
-      double best = -CUDART_INF, best_score = 0.0;
-      int best_i = INT_MAX, best_label = -1;
-      auto consider = [&](double key, double score, int label, int j) {
-        if (better<METRIC>(key, j, best, best_i)) { best = key; best_score = score; best_label = label; best_i = j; }
-      };
       {
         // filter N operand: row `lane` = my crop, K = [hi | hi | lo] of the unit feature vector (float32 is plenty: the
         // filter is approximate by construction); chunks of 8 halfs, warp fw writes chunks fw, fw + 4, ...
         const float rinv = n2 > 0.0 ? rsqrtf((float)n2) : 0.f;
         const int KC = a.kf >> 3;
-        for (int kc = fw; kc < KC; kc += kFinishWarps) {
+        uint8_t* bop_b = bop + (size_t)fb * bop_bytes;
+        for (int kc = fw; kc < KC; kc += 4) {
           __align__(16) __half h[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -492,14 +518,30 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
             if (seg < 3) split_half((float)ps[(kk - seg * a.k) * QB + lane] * rinv, hi, lo);
             h[i] = seg < 2 ? hi : lo;
           }
-          *reinterpret_cast<uint4*>(bop + swz_chunk_offset(lane, kc, row_bytes, QB)) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(bop_b + swz_chunk_offset(lane, kc, row_bytes, QB)) = *reinterpret_cast<const uint4*>(h);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
-      tc_fence_before();                             // the score columns of the previous item have been read (pass B)
-      bar_finish();
-      if (ftid == 0) mbar_arrive(&sh->bop_ready);
-      if (probe && ftid == 0 && (it == 0 || it == 4)) probe[it == 0 ? 8 : 12] = globaltimer();
+      bar_front();                                   // pe / pn / filter operand of buffer fb complete; ps free again
+      if (tid == 8 * 32 && ok) {
+        mbar_arrive(&sh->bop_ready[fb]);             // -> filter MMA issuer
+        mbar_arrive(&sh->feat_ready[fb]);            // -> match warps (exact-scorer vectors)
+      }
+      if (probe && tid == 8 * 32 && (it == 0 || it == 4)) probe[it == 0 ? 8 : 12] = globaltimer();
+      ++it;
+    }
+  } else {
+    // =================================================================== match (warps 12..15): filter scan, exact re-score
+    const int fw = warp - (kWarps - kFinishWarps), ftid = tid - (kWarps - kFinishWarps) * 32;
+    int it = 0;
+    bool ok = true;
+    for (int g = 0; g < a.nb; ++g) {
+      const StreamBatch& bt = a.batch[g];
+      if (row0 >= bt.B) continue;
+      const int fb = it & 1;
+      const double* pe_b = pe + (size_t)fb * KR * QB;
+      if (ftid < QB) { sh->best_key[ftid] = 0ull; sh->best_j[ftid] = INT_MAX; }
+      if (ftid == 0) { sh->list_cnt = 0; sh->overflow = 0; }
       // ---- scores[gallery row][crop] are in TMEM: lane = gallery row 32 fw + lane of every 128-row block
       ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->scores_full, (uint32_t)(it & 1), failed));
       tc_fence_after();
@@ -563,52 +605,63 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
           }
         }
       }
+      tc_fence_before();                             // the score columns have been read: the next item's MMAs may land
       __threadfence_block();
       bar_finish();
+      if (ftid == 0) mbar_arrive(&sh->scores_free);
+      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->feat_ready[fb], (uint32_t)((it >> 1) & 1), failed));
       const bool overflow = *reinterpret_cast<volatile int*>(&sh->overflow) != 0;
       const int total = overflow ? 0 : min(*reinterpret_cast<volatile int*>(&sh->list_cnt), kListCap);
-      for (int e = ftid; e < total; e += kFinishThreads) {
-        const int L = sh->list_L[e];
-        double key, score; int label;
-        exact_entry<METRIC, KR>(a.gp, a.ginv, a.gnorm, a.labels, pe, L, sh->list_j[e], sh->pn[L], key, score, label);
-        sh->list_key[e] = key;
-        sh->list_score[e] = score;
-        sh->list_label[e] = label;
-      }
-      bar_finish();
-      for (int e = fw; e < total; e += kFinishWarps)
-        if (sh->list_L[e] == lane) consider(sh->list_key[e], sh->list_score[e], sh->list_label[e], sh->list_j[e]);
-      if (overflow) {
-        for (int j = fw; j < a.n; j += kFinishWarps) {
-          double key, score; int label;
-          exact_entry<METRIC, KR>(a.gp, a.ginv, a.gnorm, a.labels, pe, lane, j, pn, key, score, label);
-          consider(key, score, label, j);
+      // ---- exact float64 score of every surviving row (one per thread), best per crop through shared-memory atomics:
+      // highest key first, then the lowest gallery row (np.argmax's first maximum), then the winner writes the outputs
+      int L = -1, j = INT_MAX, label = -1;
+      double key = 0.0, score = 0.0;
+      if (ok) {
+        if (!overflow) {
+          if (ftid < total) {
+            L = sh->list_L[ftid];
+            j = sh->list_j[ftid];
+            exact_entry<METRIC, KR>(a.gp, a.ginv, a.gnorm, a.labels, pe_b, L, j, sh->pn[fb][L], key, score, label);
+          }
+        } else {
+          // degenerate gallery (more rows inside the band than list entries): exact scan of every row, lane = crop
+          const double pn = sh->pn[fb][lane];
+          double best = -CUDART_INF;
+          for (int jj = fw; jj < a.n; jj += kFinishWarps) {
+            double kk, ss; int ll;
+            exact_entry<METRIC, KR>(a.gp, a.ginv, a.gnorm, a.labels, pe_b, lane, jj, pn, kk, ss, ll);
+            if (better<METRIC>(kk, jj, best, j)) { best = kk; key = kk; score = ss; label = ll; j = jj; }
+          }
+          if (j != INT_MAX) L = lane;
         }
       }
-      if (probe && ftid == 0 && (it == 0 || it == 4)) probe[it == 0 ? 10 : 14] = globaltimer();
-      sh->red_s[fw][lane] = best;
-      sh->red_d[fw][lane] = best_score;
-      sh->red_i[fw][lane] = best_i;
-      sh->red_l[fw][lane] = best_label;
+      if (key == 0.0) key = 0.0;                     // -0.0 -> +0.0: equal keys must compare equal as ordered integers
+      const unsigned long long okey = d2ord(key);
+      if (L >= 0) atomicMax(&sh->best_key[L], okey);
       bar_finish();
-      if (fw == 0 && live) {
-        double bs = sh->red_s[0][lane], score = sh->red_d[0][lane];
-        int bi = sh->red_i[0][lane], bl = sh->red_l[0][lane];
-        for (int w = 1; w < kFinishWarps; ++w)
-          if (better<METRIC>(sh->red_s[w][lane], sh->red_i[w][lane], bs, bi)) {
-            bs = sh->red_s[w][lane];
-            score = sh->red_d[w][lane];
-            bi = sh->red_i[w][lane];
-            bl = sh->red_l[w][lane];
-          }
-        if (bi == INT_MAX) { bi = 0; bl = -1; }      // only after a pipeline failure (the status flag is raised below)
-        bt.out_score[b] = score;
-        bt.out_index[b] = bi;
-        if (bt.out_label) bt.out_label[b] = score >= bt.threshold ? bl : -1;
+      if (L >= 0 && okey == sh->best_key[L]) atomicMin(&sh->best_j[L], j);
+      bar_finish();
+      if (probe && ftid == 0 && (it == 0 || it == 4)) probe[it == 0 ? 10 : 14] = globaltimer();
+      if (L >= 0 && okey == sh->best_key[L] && j == sh->best_j[L]) {
+        const int b = row0 + (int)rank * QB + L;
+        if (b < bt.B) {
+          bt.out_score[b] = score;
+          bt.out_index[b] = j;
+          if (bt.out_label) bt.out_label[b] = score >= bt.threshold ? label : -1;
+        }
+      }
+      if (ftid < QB && sh->best_j[ftid] == INT_MAX) {  // only after a pipeline failure (the status flag is raised below)
+        const int b = row0 + (int)rank * QB + ftid;
+        if (b < bt.B) {
+          bt.out_score[b] = 0.0;
+          bt.out_index[b] = 0;
+          if (bt.out_label) bt.out_label[b] = -1;
+        }
       }
       if (probe && ftid == 0) probe[it == 0 ? 4 : 5] = globaltimer();
       if (probe && ftid == 0 && it == 4) probe[15] = globaltimer();
-      bar_finish();                                  // red_* / list_* / pn are rewritten by the next item
+      bar_finish();                                  // best_* / list_* are re-initialised for the next item
+      if (ftid == 0) mbar_arrive(&sh->feat_free[fb]);
       ++it;
     }
   }
@@ -648,9 +701,9 @@ bool plan_layout(int nc_pad, int kq, int kr, int kf, int g_tiles, StreamLayout* 
     L.stages = c.stages; L.recv_bufs = c.recv_bufs;
     L.off_recv = (int)off; off += (size_t)c.recv_bufs * kCluster * kq * QB * 16;
     L.off_ps = (int)off;   off += sizeof(double) * kr * QB;
-    L.off_pe = (int)off;   off += sizeof(double) * kr * QB;
+    L.off_pe = (int)off;   off += 2 * sizeof(double) * kr * QB;
     off = (size_t)ef::round_up((int64_t)off, 1024);
-    L.off_bop = (int)off;  off += bop_bytes;
+    L.off_bop = (int)off;  off += 2 * bop_bytes;
     L.off_gal = (int)off;  off += (size_t)g_tiles * tile_bytes;
     off = (size_t)ef::round_up((int64_t)off, 128);
     L.off_sh = (int)off;
