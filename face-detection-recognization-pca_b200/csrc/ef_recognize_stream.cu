@@ -109,17 +109,18 @@ struct StreamShared {
   unsigned long long scores_free;             // match warps: the score columns have been read
   unsigned long long feat_ready[2];           // combine warps: exact-scorer vectors + norms of item it ([it & 1])
   unsigned long long feat_free[2];            // match warps: done with feature buffer [it & 1]
+  unsigned long long list_ready[2];           // scan warps: the re-score list [it & 1] of item it is complete
+  unsigned long long list_free[2];            // re-score warp: done with list [it & 1]
   unsigned long long best_key[QB];            // per crop: ordered-integer image of the best exact key of the item
   int best_j[QB];
   uint32_t tmem_base;
   int failed;
-  int list_cnt, overflow;
+  int list_cnt[2], overflow[2];
   double pn[2][QB];
   double xu[QB];
   unsigned long long ssq_recv[2][kCluster][QB];
-  float fmax_s[kFinishWarps][QB];
-  alignas(16) float thr_s[QB];
-  int list_L[kListCap], list_j[kListCap];
+  alignas(16) float fmax_s[kFinishWarps][QB];
+  int list_L[2][kListCap], list_j[2][kListCap];
 };
 
 template <int METRIC>
@@ -239,11 +240,12 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
     mbar_init(&sh->scores_free, 1);
     mbar_init(&sh->feat_ready[0], 1);
     mbar_init(&sh->feat_ready[1], 1);
-    mbar_init(&sh->feat_free[0], 1);
-    mbar_init(&sh->feat_free[1], 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sh->feat_free[i], 1);
+      mbar_init(&sh->list_ready[i], 1);
+      mbar_init(&sh->list_free[i], 1);
+    }
     sh->failed = 0;
-    sh->list_cnt = 0;
-    sh->overflow = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -353,17 +355,98 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       ++it;
     }
   } else if (warp == 6) {
-    // =================================================================== float16 gallery image -> shared memory (once)
-    if (lane == 0) {
+    // =================================================================== warp 6: gallery image -> shared memory (once),
+    // then the last pipeline stage of every item: exact float64 re-score of the listed rows, best row per crop, outputs
+    {
       int n_items = 0;
       for (int g = 0; g < a.nb; ++g) n_items += row0 < a.batch[g].B ? 1 : 0;
-      if (n_items > 0) {
+      if (lane == 0 && n_items > 0) {
         const uint32_t bytes = (uint32_t)a.g_tiles * gal_tile_bytes;
         mbar_arrive_expect_tx(&sh->gal_full, bytes);
         bulk_load(gal, a.gimg, bytes, &sh->gal_full);
       }
+      __syncwarp();
     }
-    __syncwarp();
+    constexpr int kRounds = kListCap / 32;
+    int it = 0;
+    bool ok = true;
+    for (int g = 0; g < a.nb; ++g) {
+      const StreamBatch& bt = a.batch[g];
+      if (row0 >= bt.B) continue;
+      const int fb = it & 1;
+      const uint32_t par = (uint32_t)((it >> 1) & 1);
+      const double* pe_b = pe + (size_t)fb * KR * QB;
+      sh->best_key[lane] = 0ull;
+      sh->best_j[lane] = INT_MAX;
+      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->list_ready[fb], par, failed));
+      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->feat_ready[fb], par, failed));
+      const bool overflow = *reinterpret_cast<volatile int*>(&sh->overflow[fb]) != 0;
+      const int total = overflow ? 0 : min(*reinterpret_cast<volatile int*>(&sh->list_cnt[fb]), kListCap);
+      // highest exact key first, then the lowest gallery row (np.argmax's first maximum); the winner writes the outputs
+      int eL[kRounds], ej[kRounds], elab[kRounds];
+      double ekey[kRounds], escore[kRounds];
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        const int e = r * 32 + lane;
+        eL[r] = -1; ej[r] = INT_MAX; elab[r] = -1; ekey[r] = 0.0; escore[r] = 0.0;
+        if (ok && e < total) {
+          eL[r] = sh->list_L[fb][e];
+          ej[r] = sh->list_j[fb][e];
+          exact_entry<METRIC, KR>(a.gp, a.ginv, a.gnorm, a.labels, pe_b, eL[r], ej[r], sh->pn[fb][eL[r]], ekey[r], escore[r],
+                                  elab[r]);
+        }
+      }
+      if (ok && overflow) {
+        // degenerate gallery (more rows inside the band than list entries): exact scan of every row, lane = crop
+        const double pn = sh->pn[fb][lane];
+        double best = -CUDART_INF;
+        for (int jj = 0; jj < a.n; ++jj) {
+          double kk, ss; int ll;
+          exact_entry<METRIC, KR>(a.gp, a.ginv, a.gnorm, a.labels, pe_b, lane, jj, pn, kk, ss, ll);
+          if (better<METRIC>(kk, jj, best, ej[0])) { best = kk; ekey[0] = kk; escore[0] = ss; elab[0] = ll; ej[0] = jj; }
+        }
+        if (ej[0] != INT_MAX) eL[0] = lane;
+      }
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        if (ekey[r] == 0.0) ekey[r] = 0.0;           // -0.0 -> +0.0: equal keys must compare equal as ordered integers
+        if (eL[r] >= 0) atomicMax(&sh->best_key[eL[r]], d2ord(ekey[r]));
+      }
+      __syncwarp();
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r)
+        if (eL[r] >= 0 && d2ord(ekey[r]) == sh->best_key[eL[r]]) atomicMin(&sh->best_j[eL[r]], ej[r]);
+      __syncwarp();
+      if (probe && lane == 0 && (it == 0 || it == 4)) probe[it == 0 ? 10 : 14] = globaltimer();
+#pragma unroll
+      for (int r = 0; r < kRounds; ++r) {
+        if (eL[r] >= 0 && d2ord(ekey[r]) == sh->best_key[eL[r]] && ej[r] == sh->best_j[eL[r]]) {
+          const int b = row0 + (int)rank * QB + eL[r];
+          if (b < bt.B) {
+            bt.out_score[b] = escore[r];
+            bt.out_index[b] = ej[r];
+            if (bt.out_label) bt.out_label[b] = escore[r] >= bt.threshold ? elab[r] : -1;
+          }
+        }
+      }
+      if (sh->best_j[lane] == INT_MAX) {             // only after a pipeline failure (the status flag is raised below)
+        const int b = row0 + (int)rank * QB + lane;
+        if (b < bt.B) {
+          bt.out_score[b] = 0.0;
+          bt.out_index[b] = 0;
+          if (bt.out_label) bt.out_label[b] = -1;
+        }
+      }
+      if (probe && lane == 0) probe[it == 0 ? 4 : 5] = globaltimer();
+      if (probe && lane == 0 && it == 4) probe[15] = globaltimer();
+      __syncwarp();
+      if (lane == 0 && ok) {
+        mbar_arrive(&sh->list_free[fb]);
+        mbar_arrive(&sh->feat_free[fb]);
+      }
+      ++it;
+    }
   } else if (warp == 7) {
     // =================================================================== filter MMA issuer: one burst per item
     if (lane == 0) {
@@ -531,17 +614,17 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       ++it;
     }
   } else {
-    // =================================================================== match (warps 12..15): filter scan, exact re-score
+    // =================================================================== scan (warps 12..15): filter scores -> re-score list
     const int fw = warp - (kWarps - kFinishWarps), ftid = tid - (kWarps - kFinishWarps) * 32;
     int it = 0;
     bool ok = true;
     for (int g = 0; g < a.nb; ++g) {
       const StreamBatch& bt = a.batch[g];
       if (row0 >= bt.B) continue;
-      const int fb = it & 1;
-      const double* pe_b = pe + (size_t)fb * KR * QB;
-      if (ftid < QB) { sh->best_key[ftid] = 0ull; sh->best_j[ftid] = INT_MAX; }
-      if (ftid == 0) { sh->list_cnt = 0; sh->overflow = 0; }
+      const int lb = it & 1;
+      // the re-score warp is done with list lb (item it - 2)?
+      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->list_free[lb], (uint32_t)(((it >> 1) & 1) ^ 1), failed));
+      if (ftid == 0) { sh->list_cnt[lb] = 0; sh->overflow[lb] = 0; }
       // ---- scores[gallery row][crop] are in TMEM: lane = gallery row 32 fw + lane of every 128-row block
       ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->scores_full, (uint32_t)(it & 1), failed));
       tc_fence_after();
@@ -568,21 +651,23 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
         sh->fmax_s[fw][lane] = mine;                 // maximum of crop `lane` over this warp's rows
       }
       bar_finish();
-      if (fw == 0) {
-        float M = sh->fmax_s[0][lane];
-#pragma unroll
-        for (int w = 1; w < kFinishWarps; ++w) M = fmaxf(M, sh->fmax_s[w][lane]);
-        sh->thr_s[lane] = M - 2.f * kFilterEps;
-      }
-      bar_finish();
       if (probe && ftid == 0 && (it == 0 || it == 4)) probe[it == 0 ? 9 : 13] = globaltimer();
       {
         // pass B: rows inside the band of the maximum -> re-score list
+        // every thread needs the thresholds of all 32 crops: broadcast 16-byte loads of the four warps' maxima
         float thr[QB];
 #pragma unroll
         for (int c4 = 0; c4 < QB / 4; ++c4) {
-          const float4 t4 = reinterpret_cast<const float4*>(sh->thr_s)[c4];
-          thr[4 * c4] = t4.x; thr[4 * c4 + 1] = t4.y; thr[4 * c4 + 2] = t4.z; thr[4 * c4 + 3] = t4.w;
+          float4 M = reinterpret_cast<const float4*>(sh->fmax_s[0])[c4];
+#pragma unroll
+          for (int w = 1; w < kFinishWarps; ++w) {
+            const float4 o = reinterpret_cast<const float4*>(sh->fmax_s[w])[c4];
+            M.x = fmaxf(M.x, o.x); M.y = fmaxf(M.y, o.y); M.z = fmaxf(M.z, o.z); M.w = fmaxf(M.w, o.w);
+          }
+          thr[4 * c4] = M.x - 2.f * kFilterEps;
+          thr[4 * c4 + 1] = M.y - 2.f * kFilterEps;
+          thr[4 * c4 + 2] = M.z - 2.f * kFilterEps;
+          thr[4 * c4 + 3] = M.w - 2.f * kFilterEps;
         }
         for (int blk = 0; blk < a.g_tiles && ok; ++blk) {
           uint32_t v[32];
@@ -595,73 +680,23 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
           while (mask) {
             const int c = __ffs(mask) - 1;
             mask &= mask - 1u;
-            const int slot = atomicAdd(&sh->list_cnt, 1);
+            const int slot = atomicAdd(&sh->list_cnt[lb], 1);
             if (slot < kListCap) {
-              sh->list_L[slot] = c;
-              sh->list_j[slot] = j;
+              sh->list_L[lb][slot] = c;
+              sh->list_j[lb][slot] = j;
             } else {
-              sh->overflow = 1;
+              sh->overflow[lb] = 1;
             }
           }
         }
       }
       tc_fence_before();                             // the score columns have been read: the next item's MMAs may land
       __threadfence_block();
-      bar_finish();
-      if (ftid == 0) mbar_arrive(&sh->scores_free);
-      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->feat_ready[fb], (uint32_t)((it >> 1) & 1), failed));
-      const bool overflow = *reinterpret_cast<volatile int*>(&sh->overflow) != 0;
-      const int total = overflow ? 0 : min(*reinterpret_cast<volatile int*>(&sh->list_cnt), kListCap);
-      // ---- exact float64 score of every surviving row (one per thread), best per crop through shared-memory atomics:
-      // highest key first, then the lowest gallery row (np.argmax's first maximum), then the winner writes the outputs
-      int L = -1, j = INT_MAX, label = -1;
-      double key = 0.0, score = 0.0;
-      if (ok) {
-        if (!overflow) {
-          if (ftid < total) {
-            L = sh->list_L[ftid];
-            j = sh->list_j[ftid];
-            exact_entry<METRIC, KR>(a.gp, a.ginv, a.gnorm, a.labels, pe_b, L, j, sh->pn[fb][L], key, score, label);
-          }
-        } else {
-          // degenerate gallery (more rows inside the band than list entries): exact scan of every row, lane = crop
-          const double pn = sh->pn[fb][lane];
-          double best = -CUDART_INF;
-          for (int jj = fw; jj < a.n; jj += kFinishWarps) {
-            double kk, ss; int ll;
-            exact_entry<METRIC, KR>(a.gp, a.ginv, a.gnorm, a.labels, pe_b, lane, jj, pn, kk, ss, ll);
-            if (better<METRIC>(kk, jj, best, j)) { best = kk; key = kk; score = ss; label = ll; j = jj; }
-          }
-          if (j != INT_MAX) L = lane;
-        }
+      bar_finish();                                  // list complete; fmax_s free for the next item
+      if (ftid == 0 && ok) {
+        mbar_arrive(&sh->scores_free);
+        mbar_arrive(&sh->list_ready[lb]);
       }
-      if (key == 0.0) key = 0.0;                     // -0.0 -> +0.0: equal keys must compare equal as ordered integers
-      const unsigned long long okey = d2ord(key);
-      if (L >= 0) atomicMax(&sh->best_key[L], okey);
-      bar_finish();
-      if (L >= 0 && okey == sh->best_key[L]) atomicMin(&sh->best_j[L], j);
-      bar_finish();
-      if (probe && ftid == 0 && (it == 0 || it == 4)) probe[it == 0 ? 10 : 14] = globaltimer();
-      if (L >= 0 && okey == sh->best_key[L] && j == sh->best_j[L]) {
-        const int b = row0 + (int)rank * QB + L;
-        if (b < bt.B) {
-          bt.out_score[b] = score;
-          bt.out_index[b] = j;
-          if (bt.out_label) bt.out_label[b] = score >= bt.threshold ? label : -1;
-        }
-      }
-      if (ftid < QB && sh->best_j[ftid] == INT_MAX) {  // only after a pipeline failure (the status flag is raised below)
-        const int b = row0 + (int)rank * QB + ftid;
-        if (b < bt.B) {
-          bt.out_score[b] = 0.0;
-          bt.out_index[b] = 0;
-          if (bt.out_label) bt.out_label[b] = -1;
-        }
-      }
-      if (probe && ftid == 0) probe[it == 0 ? 4 : 5] = globaltimer();
-      if (probe && ftid == 0 && it == 4) probe[15] = globaltimer();
-      bar_finish();                                  // best_* / list_* are re-initialised for the next item
-      if (ftid == 0) mbar_arrive(&sh->feat_free[fb]);
       ++it;
     }
   }
