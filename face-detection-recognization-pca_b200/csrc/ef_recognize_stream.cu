@@ -89,7 +89,7 @@ struct StreamArgs {
   const double* gnorm;
   const double* ginv;
   const int32_t* labels;
-  int n, kf, g_tiles;
+  int n, kf, g_tiles, debug_no_ssq, prefetch, xbox;
   const __half* gimg;          // float16 [g_hi | g_lo | g_hi] image of the prepared gallery (gallery_image)
   int* status;
   int off_recv, off_ps, off_pe, off_bop, off_gal, off_sh;
@@ -171,6 +171,16 @@ __device__ __forceinline__ float ord2f(unsigned u) {
 __device__ __forceinline__ unsigned long long d2ord(double d) {
   const unsigned long long u = (unsigned long long)__double_as_longlong(d);
   return (u >> 63) ? ~u : (u | 0x8000000000000000ull);
+}
+
+// mbar_wait with the time spent waiting added to a probe slot (debugging aid; slot == nullptr: plain wait)
+__device__ __forceinline__ bool timed_wait(unsigned long long* bar, uint32_t parity, volatile int* failed,
+                                           unsigned long long* slot, bool cluster_scope = false) {
+  if (!slot) return cluster_scope ? mbar_wait_cluster(bar, parity, failed) : mbar_wait(bar, parity, failed);
+  const unsigned long long t0 = globaltimer();
+  const bool ok = cluster_scope ? mbar_wait_cluster(bar, parity, failed) : mbar_wait(bar, parity, failed);
+  *slot += globaltimer() - t0;
+  return ok;
 }
 
 __device__ __forceinline__ void bar_finish() { asm volatile("bar.sync 5, 128;" ::: "memory"); }   // match warps
@@ -263,7 +273,9 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   asm volatile("griddepcontrol.wait;" ::: "memory"); // the crops may have been written by the previous kernel
   const uint32_t tmem_base = sh->tmem_base;
   volatile int* failed = &sh->failed;
-  unsigned long long* probe = a.probe ? a.probe + (size_t)blockIdx.x * 16 : nullptr;
+  unsigned long long* probe = a.probe ? a.probe + (size_t)blockIdx.x * 32 : nullptr;
+  // per-stage trace of CTA 0 (first 64 stages): [0..63] TMA issue, [64..127] data landed (MMA thread), behind all CTAs' slots
+  unsigned long long* trace = (a.probe && blockIdx.x == 0) ? a.probe + (size_t)gridDim.x * 32 : nullptr;
   if (probe && tid == 0) probe[0] = globaltimer();
 
   if (warp == 0) {
@@ -273,14 +285,37 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       int stage = 0;
       uint32_t phase = 0;
       bool ok = true;
+      // Optional L2 prefetch cursor (EF_STREAM_PREFETCH = K blocks ahead of the loads, cp.async.bulk.prefetch.tensor).
+      // Off by default.  Measured: a stage lands 1.0-1.4 us after its issue, four stages in flight give one stage per
+      // ~350 ns (81 GB/s per SM); prefetching the crop boxes into L2 did not shorten that (the same holds with the whole
+      // batch L2 resident, and with half the SMs idle) and costs 4-30 % through the extra requests.
+      int n_issued = 0;
+      const int pf_dist = a.prefetch;
+      int pg = 0, pkb = kb0;
+      auto pf_valid = [&]() {
+        while (pg < a.nb && row0 >= a.batch[pg].B) ++pg;
+        return pg < a.nb;
+      };
+      auto pf_step = [&]() {
+        if (!pf_valid()) return;
+        tma_prefetch_2d(&a.batch[pg].map, pkb * BLOCK_K, row0);
+        if (++pkb == kb1) { pkb = kb0; ++pg; }
+      };
+      for (int i = 0; i < pf_dist; ++i) pf_step();
       for (int g = 0; g < a.nb && ok; ++g) {
         if (row0 >= a.batch[g].B) continue;
         const CUtensorMap* mx = &a.batch[g].map;
         asm volatile("prefetch.tensormap [%0];" ::"l"(mx) : "memory");
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (!mbar_wait(&sh->empty_bar[stage], phase ^ 1, failed)) { ok = false; break; }
+          if (pf_dist > 0) pf_step();
+          if (!timed_wait(&sh->empty_bar[stage], phase ^ 1, failed, probe ? probe + 16 : nullptr)) { ok = false; break; }
           mbar_arrive_expect_tx(&sh->full_bar[stage], (uint32_t)stage_bytes);
-          tma_load_2d(sA + (size_t)stage * A_STAGE_BYTES, mx, &sh->full_bar[stage], kb * BLOCK_K, row0);
+          if (trace && n_issued < 64) trace[n_issued++] = globaltimer();
+          // (EF_STREAM_XBOX splits the crop tile into several boxes.  Measured: every extra TMA instruction costs ~40 ns
+          // of the producer's time and nothing is gained, 128-row boxes are the fastest)
+          for (int r = 0; r < BLOCK_M; r += a.xbox)
+            tma_load_2d(sA + (size_t)stage * A_STAGE_BYTES + (size_t)r * BLOCK_K, mx, &sh->full_bar[stage], kb * BLOCK_K,
+                        row0 + r);
           tma_load_2d(sB + (size_t)stage * b_stage_bytes, &a.map_w, &sh->full_bar[stage], kb * BLOCK_K, 0);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
@@ -290,18 +325,19 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   } else if (warp == 1) {
     // =================================================================== projection MMA issuer
     if (lane == 0) {
-      int stage = 0, it = 0;
+      int stage = 0, it = 0, n_landed = 0;
       uint32_t phase = 0;
       const uint32_t idesc = umma_idesc_i8(a.nc_pad);
       bool ok = true;
       for (int g = 0; g < a.nb && ok; ++g) {
         if (row0 >= a.batch[g].B) continue;
         const int buf = it & 1;
-        if (!mbar_wait(&sh->acc_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), failed)) break;
+        if (!timed_wait(&sh->acc_empty[buf], (uint32_t)(((it >> 1) & 1) ^ 1), failed, probe ? probe + 18 : nullptr)) break;
         tc_fence_after();
         const uint32_t d_addr = tmem_base + (uint32_t)(buf * kAccCols);
         for (int kb = kb0; kb < kb1; ++kb) {
-          if (!mbar_wait(&sh->full_bar[stage], phase, failed)) { ok = false; break; }
+          if (!timed_wait(&sh->full_bar[stage], phase, failed, probe ? probe + 17 : nullptr)) { ok = false; break; }
+          if (trace && n_landed < 64) trace[64 + n_landed++] = globaltimer();
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + (size_t)stage * b_stage_bytes);
@@ -333,6 +369,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
         if (!ok) break;
         const uint4* line = reinterpret_cast<const uint4*>(sA + (size_t)stage * A_STAGE_BYTES + row_in_tile * BLOCK_K);
         unsigned int partial = 0;
+        if (!a.debug_no_ssq)                         // EF_STREAM_NO_SSQ (measurement only: the residual is then wrong)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint4 v = line[(j + row_in_tile) & 7];
@@ -378,7 +415,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       const double* pe_b = pe + (size_t)fb * KR * QB;
       sh->best_key[lane] = 0ull;
       sh->best_j[lane] = INT_MAX;
-      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->list_ready[fb], par, failed));
+      ok = __all_sync(0xffffffffu, ok && timed_wait(&sh->list_ready[fb], par, failed, (probe && lane == 0) ? probe + 25 : nullptr));
       ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->feat_ready[fb], par, failed));
       const bool overflow = *reinterpret_cast<volatile int*>(&sh->overflow[fb]) != 0;
       const int total = overflow ? 0 : min(*reinterpret_cast<volatile int*>(&sh->list_cnt[fb]), kListCap);
@@ -462,8 +499,8 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       for (int g = 0; g < a.nb && ok; ++g) {
         if (row0 >= a.batch[g].B) continue;
         if (it == 0 && !mbar_wait(&sh->gal_full, 0u, failed)) break;
-        if (!mbar_wait(&sh->bop_ready[it & 1], (uint32_t)((it >> 1) & 1), failed)) break;
-        if (!mbar_wait(&sh->scores_free, (uint32_t)((it & 1) ^ 1), failed)) break;   // match warps read item it - 1
+        if (!timed_wait(&sh->bop_ready[it & 1], (uint32_t)((it >> 1) & 1), failed, probe ? probe + 26 : nullptr)) break;
+        if (!timed_wait(&sh->scores_free, (uint32_t)((it & 1) ^ 1), failed, probe ? probe + 27 : nullptr)) break;   // scan warps read item it - 1
         tc_fence_after();
         const uint64_t cdesc = cdesc0 + (uint64_t)((it & 1) * (bop_bytes >> 4));
         for (int blk = 0; blk < a.g_tiles; ++blk) {
@@ -504,10 +541,12 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       const int buf = it & 1;
       // (after a failed wait the warp keeps walking through the items without touching the pipeline, so that the four
       // warps still meet at every named barrier: a timeout must end in the status flag, never in a hang)
-      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->acc_full[buf], (uint32_t)((it >> 1) & 1), failed));
+      unsigned long long* wslot = (probe && tid == 8 * 32) ? probe + 19 : nullptr;
+      ok = __all_sync(0xffffffffu, ok && timed_wait(&sh->acc_full[buf], (uint32_t)((it >> 1) & 1), failed, wslot));
       tc_fence_after();
       const int rb = it % a.recv_bufs, use = it / a.recv_bufs;
-      ok = __all_sync(0xffffffffu, ok && mbar_wait_cluster(&sh->push_ok[rb][q], (uint32_t)((use & 1) ^ 1), failed));
+      ok = __all_sync(0xffffffffu, ok && timed_wait(&sh->push_ok[rb][q], (uint32_t)((use & 1) ^ 1), failed,
+                                                   wslot ? wslot + 1 : nullptr, true));
       if (ok) {
         const uint32_t dst = map_to_cta(smem_u32(recv) + (uint32_t)rb * recv_buf_bytes +
                                             (uint32_t)((int)rank * a.kq * QB + lane) * 16u,
@@ -528,7 +567,8 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       const int b = row0 + (int)rank * QB + lane;    // the crop this lane finishes
       const bool live = b < bt.B;
       const int fb = it & 1;                         // feature buffer handed to the match warps
-      ok = __all_sync(0xffffffffu, ok && mbar_wait_cluster(&sh->recv_full[rb], (uint32_t)(use & 1), failed));
+      ok = __all_sync(0xffffffffu, ok && timed_wait(&sh->recv_full[rb], (uint32_t)(use & 1), failed,
+                                                   wslot ? wslot + 2 : nullptr, true));
       if (probe && tid == 8 * 32 && (it == 0 || it == 4)) probe[it == 0 ? 7 : 11] = globaltimer();
       const longlong2* rbase = reinterpret_cast<const longlong2*>(recv + (size_t)rb * recv_buf_bytes) + lane;
 #pragma unroll
@@ -564,7 +604,8 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       if (fw == 1 && lane < kCluster)                // hand the buffer back to the four sources
         mbar_arrive_remote(map_to_cta(smem_u32(&sh->push_ok[rb][rank]), (uint32_t)lane));
       // the match warps are done with feature buffer fb (item it - 2)?
-      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->feat_free[fb], (uint32_t)(((it >> 1) & 1) ^ 1), failed));
+      ok = __all_sync(0xffffffffu, ok && timed_wait(&sh->feat_free[fb], (uint32_t)(((it >> 1) & 1) ^ 1), failed,
+                                                   wslot ? wslot + 3 : nullptr));
       double pv[KR];
 #pragma unroll
       for (int c = 0; c < KR; ++c) pv[c] = ps[c * QB + lane];     // independent loads, then the ordered fma chain
@@ -623,10 +664,12 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       if (row0 >= bt.B) continue;
       const int lb = it & 1;
       // the re-score warp is done with list lb (item it - 2)?
-      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->list_free[lb], (uint32_t)(((it >> 1) & 1) ^ 1), failed));
+      unsigned long long* wslot = (probe && ftid == 0) ? probe + 23 : nullptr;
+      ok = __all_sync(0xffffffffu, ok && timed_wait(&sh->list_free[lb], (uint32_t)(((it >> 1) & 1) ^ 1), failed,
+                                                   wslot ? wslot + 1 : nullptr));
       if (ftid == 0) { sh->list_cnt[lb] = 0; sh->overflow[lb] = 0; }
       // ---- scores[gallery row][crop] are in TMEM: lane = gallery row 32 fw + lane of every 128-row block
-      ok = __all_sync(0xffffffffu, ok && mbar_wait(&sh->scores_full, (uint32_t)(it & 1), failed));
+      ok = __all_sync(0xffffffffu, ok && timed_wait(&sh->scores_full, (uint32_t)(it & 1), failed, wslot));
       tc_fence_after();
       const uint32_t sc_addr = tmem_base + ((uint32_t)(fw * 32) << 16) + (uint32_t)kScoreCol0;
       {
@@ -765,8 +808,8 @@ int launch_stream(StreamArgs& a, const StreamLayout& L, int m_tiles, cudaStream_
   const int grid_n = m_tiles * kCluster;
   a.probe = nullptr;
   if (probing && grid_n <= 4096) {
-    if (!probe_buf[dev]) EF_CUDA(cudaMalloc(&probe_buf[dev], sizeof(unsigned long long) * 16 * 4096));
-    EF_CUDA(cudaMemsetAsync(probe_buf[dev], 0, sizeof(unsigned long long) * 16 * 4096, stream));
+    if (!probe_buf[dev]) EF_CUDA(cudaMalloc(&probe_buf[dev], sizeof(unsigned long long) * 32 * 4096));
+    EF_CUDA(cudaMemsetAsync(probe_buf[dev], 0, sizeof(unsigned long long) * 32 * 4096, stream));
     a.probe = probe_buf[dev];
   }
   cudaLaunchConfig_t cfg{};
@@ -786,11 +829,11 @@ int launch_stream(StreamArgs& a, const StreamLayout& L, int m_tiles, cudaStream_
   EF_CUDA(cudaLaunchKernelEx(&cfg, recognize_stream_kernel<METRIC, KR>, a));
   ef::g_launches.fetch_add(1, std::memory_order_relaxed);
   if (a.probe) {
-    std::vector<unsigned long long> h((size_t)grid_n * 16);
+    std::vector<unsigned long long> h((size_t)grid_n * 32 + 128);
     EF_CUDA(cudaStreamSynchronize(stream));
     EF_CUDA(cudaMemcpy(h.data(), probe_buf[dev], h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     unsigned long long t0 = ~0ull;
-    for (int c = 0; c < grid_n; ++c) if (h[(size_t)c * 16] && h[(size_t)c * 16] < t0) t0 = h[(size_t)c * 16];
+    for (int c = 0; c < grid_n; ++c) if (h[(size_t)c * 32] && h[(size_t)c * 32] < t0) t0 = h[(size_t)c * 32];
     const char* names[16] = {"start", "mma_first_item", "mma_last_item", "last_push", "first_item_out", "last_item_out",
                              "end", "i0_recv", "i0_features", "i0_scanned", "i0_rescored", "i4_recv", "i4_features",
                              "i4_scanned", "i4_rescored", "i4_out"};
@@ -801,13 +844,33 @@ int launch_stream(StreamArgs& a, const StreamLayout& L, int m_tiles, cudaStream_
       double sum = 0, mx = 0;
       int cnt = 0;
       for (int c = 0; c < grid_n; ++c) {
-        if (!h[(size_t)c * 16 + i]) continue;
-        const double v = (double)(h[(size_t)c * 16 + i] - t0) * 1e-3;
+        if (!h[(size_t)c * 32 + i]) continue;
+        const double v = (double)(h[(size_t)c * 32 + i] - t0) * 1e-3;
         sum += v;
         ++cnt;
         if (v > mx) mx = v;
       }
       fprintf(stderr, " %s %.2f/%.2f", names[i], cnt ? sum / cnt : 0.0, mx);
+    }
+    {
+      const unsigned long long* tr = h.data() + (size_t)grid_n * 32;
+      fprintf(stderr, "\n[ef_stream_probe] CTA 0, first stages: issue time / landed time (ns since first issue):");
+      for (int i = 0; i < 48; ++i)
+        if (tr[i] && tr[64 + i]) fprintf(stderr, " %llu/%llu", tr[i] - tr[0], tr[64 + i] - tr[0]);
+    }
+    // accumulated wait times of the roles (slots 16..): where each pipeline stage spends its idle time
+    const char* wnames[12] = {"tma:empty", "mma:full", "mma:acc_empty", "drain:acc_full", "drain:push_ok", "comb:recv_full",
+                              "comb:feat_free", "scan:scores_full", "scan:list_free", "rescore:list_ready", "fmma:bop_ready",
+                              "fmma:scores_free"};
+    fprintf(stderr, "\n[ef_stream_probe] waits, us per launch (mean/max over CTAs):");
+    for (int i = 0; i < 12; ++i) {
+      double sum = 0, mx = 0;
+      for (int c = 0; c < grid_n; ++c) {
+        const double v = (double)h[(size_t)c * 32 + 16 + i] * 1e-3;
+        sum += v;
+        if (v > mx) mx = v;
+      }
+      fprintf(stderr, " %s %.1f/%.1f", wnames[i], sum / grid_n, mx);
     }
     fprintf(stderr, "\n");
   }
@@ -854,12 +917,17 @@ int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t
   if (nc_pad > wfm_rows || (ldw & 15) || (reinterpret_cast<uintptr_t>(Wfm) & 15)) return EF_ERR_UNSUPPORTED;
   if (!encode_fn()) return EF_ERR_UNSUPPORTED;
   StreamArgs a{};
+  a.xbox = BLOCK_M;                                  // rows per TMA box of the crop tile (multiple of 8, divides 128)
+  if (const char* e = getenv("EF_STREAM_XBOX")) {
+    const int v = atoi(e);
+    if (v == 8 || v == 16 || v == 32 || v == 64 || v == 128) a.xbox = v;
+  }
   int max_B = 0;
   for (int g = 0; g < nb; ++g) {
     const StreamBatchDesc& d = batches[g];
     if (d.B <= 0 || !d.x || (d.ldx & 15) || (reinterpret_cast<uintptr_t>(d.x) & 15)) return EF_ERR_UNSUPPORTED;
     StreamBatch& b = a.batch[g];
-    if (!make_map(&b.map, d.x, (uint64_t)D, (uint64_t)d.B, (uint64_t)d.ldx, BLOCK_M)) return EF_ERR_UNSUPPORTED;
+    if (!make_map(&b.map, d.x, (uint64_t)D, (uint64_t)d.B, (uint64_t)d.ldx, (uint32_t)a.xbox)) return EF_ERR_UNSUPPORTED;
     b.B = d.B;
     b.sumsq_ext = d.sumsq_ext;
     b.out_proj = d.out_proj; b.out_resid = d.out_resid; b.out_score = d.out_score; b.out_index = d.out_index;
@@ -876,6 +944,9 @@ int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t
   a.col_exp = col_exp; a.bias = bias; a.c0 = c0;
   a.gp = gp_padded; a.gnorm = gnorm; a.ginv = ginv; a.labels = labels; a.n = (int)n;
   a.kf = filter_kf(k); a.g_tiles = g_tiles;
+  a.debug_no_ssq = getenv("EF_STREAM_NO_SSQ") ? 1 : 0;
+  a.prefetch = 0;                                    // K blocks (16 KB crop boxes) the L2 prefetch cursor runs ahead
+  if (const char* e = getenv("EF_STREAM_PREFETCH")) a.prefetch = std::max(0, std::min(64, atoi(e)));
   a.gimg = reinterpret_cast<const __half*>(gimg);
   a.status = status;
   a.off_recv = L.off_recv; a.off_ps = L.off_ps; a.off_pe = L.off_pe; a.off_bop = L.off_bop; a.off_gal = L.off_gal;

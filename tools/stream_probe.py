@@ -71,6 +71,60 @@ for env, name in configs:
               f"{algo / us / 1e3 / 6550.1:.3f} of HBM peak; {check()}; timeouts {rec.pipeline_timeouts()}", flush=True)
 for kk in ("EF_STREAM_RESIDENT", "EF_STREAM_STAGES", "EF_STREAM_RECV_BUFS"):
     os.environ.pop(kk, None)
+if len(sys.argv) > 1 and sys.argv[1] == "l2":
+    # the same 41 MB batch every time: the crops come from L2 (126 MB) instead of HBM
+    rec.set_serving(0, 8)
+    os.environ["EF_STREAM_PREFETCH"] = "0"
+    keep = xs
+    print(f"stream kernel, 8 distinct batches (HBM), depth 8: {timed():7.2f} us per batch", flush=True)
+    xs = [keep[0]] * 8
+    print(f"stream kernel, ONE batch re-used (L2 resident), depth 8: {timed():7.2f} us per batch", flush=True)
+    half = [keep[0][:2048], keep[1][:2048]] * 4
+    xs = half
+    outs_keep = outs
+    outs = [{f: (v[:2048] if v is not None else None) for f, v in o.items()} for o in outs]
+    print(f"stream kernel, 2048-crop batches (16 clusters = 64 SMs), depth 8: {timed():7.2f} us per batch", flush=True)
+    xs, outs = keep, outs_keep
+    os.environ.pop("EF_STREAM_PREFETCH")
+if len(sys.argv) > 1 and sys.argv[1] == "stages":
+    rec.set_serving(0, 8)
+    for st in (2, 3, 4):
+        os.environ["EF_STREAM_STAGES"] = str(st)
+        us = timed()
+        print(f"stream kernel, {st} stages, depth 8: {us:7.2f} us per batch = {algo / us / 1e3 / 6550.1:.3f} of HBM peak; {check()}", flush=True)
+    os.environ.pop("EF_STREAM_STAGES")
+if len(sys.argv) > 1 and sys.argv[1] == "xbox":
+    rec.set_serving(0, 8)
+    for xb in (128, 64, 32, 16, 8):
+        os.environ["EF_STREAM_XBOX"] = str(xb)
+        us = timed()
+        print(f"stream kernel, crop tile as {128 // xb} TMA boxes of {xb} rows, depth 8: {us:7.2f} us per batch = {algo / us / 1e3 / 6550.1:.3f} of HBM peak; {check()}", flush=True)
+    os.environ.pop("EF_STREAM_XBOX")
+if len(sys.argv) > 1 and sys.argv[1] == "prefetch":
+    rec.set_serving(0, 8)
+    for pf in (0, 4, 8, 12, 16, 24, 40):
+        os.environ["EF_STREAM_PREFETCH"] = str(pf)
+        us = timed()
+        print(f"stream kernel, L2 prefetch {pf:2d} K blocks ahead, depth 8: {us:7.2f} us per batch = {algo / us / 1e3 / 6550.1:.3f} of HBM peak; {check()}", flush=True)
+    os.environ.pop("EF_STREAM_PREFETCH")
+if len(sys.argv) > 1 and sys.argv[1] == "limits":
+    # where does the stream time go?  (a) without the sum-of-squares reads of the staged tiles (results then differ),
+    # (b) with half the digit planes (S = 4: half the basis traffic and half the MMA operand reads)
+    rec.set_serving(0, 8)
+    os.environ["EF_STREAM_NO_SSQ"] = "1"
+    print(f"stream kernel, no sum-of-squares reads, depth 8: {timed():7.2f} us per batch", flush=True)
+    os.environ.pop("EF_STREAM_NO_SSQ")
+    rec4 = ef.Recognizer(E, rng.uniform(60, 200, D), rng.normal(size=(ng, k)) * 100, metric=ef.METRIC_COSINE_G1,
+                         labels=np.arange(ng) % 4, n_slices=4)
+    o4 = [rec4.recognize_device(x, 0.8) for x in xs]
+    keep, rec = rec, rec4
+    outs_keep, outs = outs, o4
+    rec.set_serving(0, 8)
+    print(f"stream kernel, S = 4 digit planes, depth 8: {timed():7.2f} us per batch", flush=True)
+    os.environ["EF_STREAM_NO_SSQ"] = "1"
+    print(f"stream kernel, S = 4, no sum-of-squares reads, depth 8: {timed():7.2f} us per batch", flush=True)
+    os.environ.pop("EF_STREAM_NO_SSQ")
+    rec, outs = keep, outs_keep
 rec.set_serving(1, 0)
 us = timed()
 print(f"pipelined kernel (round 1): {us:7.2f} us per batch = {algo / us / 1e3 / 6550.1:.3f} of HBM peak; {check()}", flush=True)
