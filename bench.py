@@ -256,12 +256,14 @@ def run_ours(args, rank, world):
         sampler.start()
         time.sleep(0.3)
 
+    cur_stream = torch.cuda.current_stream(dev).cuda_stream
+
     def step(i):
         rec.recognize_device(batches[i % N_BATCHES], THRESHOLD, out=out)
 
     def step_pipelined(i):
         # serving loop (ef_model_submit_device): batches are queued and streamed back to back by a persistent launch
-        rec.submit_device(batches[i % N_BATCHES], THRESHOLD, out=outs[i % N_BATCHES])
+        rec.submit_device(batches[i % N_BATCHES], THRESHOLD, out=outs[i % N_BATCHES], stream=cur_stream)
 
     # ---- device-resident throughput, one call = one complete batch (results of batch i ready after call i)
     for i in range(args.warmup):

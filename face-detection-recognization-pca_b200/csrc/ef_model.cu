@@ -69,6 +69,9 @@ struct ef_model {
   std::vector<ef::StreamBatchDesc> queue;
   cudaStream_t queue_stream = nullptr;
   int queue_depth = ef::kStreamMaxBatches;
+  cudaEvent_t queue_ev = nullptr;  // recorded behind every queue launch: "is the previous launch still running?"
+  bool queue_ev_pending = false;
+  bool queue_adaptive = true;
   int serving_kernel = 0;          // 0 persistent stream kernel, 1 pipelined kernel (one launch per batch)
   bool stream_ok = false;          // the persistent kernel covers this model's shape (decided once at create)
   ef::DevBuf sumsq_q[ef::kStreamMaxBatches];
@@ -278,6 +281,7 @@ void ef_model_destroy(ef_model_t* m) {
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->pinned) cudaFreeHost(m->pinned);
   if (m->flush_ev) cudaEventDestroy(m->flush_ev);
+  if (m->queue_ev) cudaEventDestroy(m->queue_ev);
   for (cudaEvent_t e : m->chunk_ev) cudaEventDestroy(e);
   for (auto& hs : m->hslot) {
     if (hs.pinned) cudaFreeHost(hs.pinned);
@@ -529,6 +533,9 @@ static int queue_launch(ef_model_t* m) {
   if (stq == EF_OK) {
     m->last_used_tc = true;
     m->last_path = 4;
+    if (!m->queue_ev) EF_CUDA(cudaEventCreateWithFlags(&m->queue_ev, cudaEventDisableTiming));
+    EF_CUDA(cudaEventRecord(m->queue_ev, m->queue_stream));
+    m->queue_ev_pending = true;
   }
   return stq;
 }
@@ -538,6 +545,8 @@ int ef_model_set_serving(ef_model_t* m, int32_t kernel, int32_t queue_depth) {
   if (m->pending.B > 0 || !m->queue.empty()) return EF_ERR_INVALID;      // flush first
   m->serving_kernel = kernel;
   if (queue_depth > 0) m->queue_depth = queue_depth > ef::kStreamMaxBatches ? ef::kStreamMaxBatches : queue_depth;
+  m->queue_adaptive = queue_depth >= 0;               // negative: fixed depth (launch only when full or flushed)
+  if (queue_depth < 0) m->queue_depth = -queue_depth > ef::kStreamMaxBatches ? ef::kStreamMaxBatches : -queue_depth;
   return EF_OK;
 }
 
@@ -566,6 +575,11 @@ int ef_model_submit_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t
     m->queue.push_back(d);
     m->queue_stream = st;
     if ((int)m->queue.size() >= m->queue_depth) return queue_launch(m);
+    // adaptive depth: while the previous launch is still running the queue keeps growing (nothing would start earlier
+    // anyway); once it has finished the queued batches go out at once, so a stream that starts from an idle GPU is
+    // not held back until queue_depth batches have been submitted
+    if (m->queue_ev_pending && cudaEventQuery(m->queue_ev) == cudaSuccess) m->queue_ev_pending = false;
+    if (m->queue_adaptive && !m->queue_ev_pending) return queue_launch(m);
     return EF_OK;
   }
   if (m->tc_mode < 2 || !aligned || !m->gimg.p || !ef::pipe_supported(m->k, m->NC, m->metric, m->n_gallery))

@@ -83,7 +83,8 @@ class Recognizer:
 
     def set_serving(self, kernel=0, queue_depth=0):
         """submit_device's kernel: 0 = persistent queue kernel (default), 1 = pipelined kernel (one launch per submit);
-        queue_depth 1..8 batches per persistent launch (0 keeps the current value)."""
+        queue_depth 1..16 batches per persistent launch (0 keeps the current value, -d = fixed depth d without the
+        adaptive early launch)."""
         check(self._L.ef_model_set_serving(self._h, int(kernel), int(queue_depth)), "ef_model_set_serving")
 
     def pipeline_timeouts(self):
@@ -212,7 +213,7 @@ class Recognizer:
                                                 C.c_void_p(stream)), "ef_model_recognize_device")
         return out
 
-    def submit_device(self, x, threshold=0.7, out=None, want_residual=None):
+    def submit_device(self, x, threshold=0.7, out=None, want_residual=None, stream=None):
         """Queued form of recognize_device for a stream of batches (ef_model_submit_device): the batch joins the model's
         queue; one persistent kernel recognises the queued batches back to back when the queue is full or at
         flush_device().  x and the returned dict of output tensors must stay alive and untouched until then (the
@@ -230,9 +231,13 @@ class Recognizer:
                 "label": torch.empty(B, dtype=torch.int32, device=x.device),
                 "resid2": torch.empty(B, dtype=torch.float64, device=x.device) if want_residual else None,
             }
-        res = Result(out["features"].data_ptr(), out["score"].data_ptr(), out["index"].data_ptr(),
-                     out["label"].data_ptr(), out["resid2"].data_ptr() if out.get("resid2") is not None else None)
-        stream = torch.cuda.current_stream(x.device).cuda_stream
+        res = out.get("_res")                       # the ctypes view of a re-used output dict is built once
+        if res is None:
+            res = Result(out["features"].data_ptr(), out["score"].data_ptr(), out["index"].data_ptr(),
+                         out["label"].data_ptr(), out["resid2"].data_ptr() if out.get("resid2") is not None else None)
+            out["_res"] = res
+        if stream is None:                          # (a caller in a tight loop passes the raw handle: the lookup costs ~1.5 us)
+            stream = torch.cuda.current_stream(x.device).cuda_stream
         check(self._L.ef_model_submit_device(self._h, x.data_ptr(), x.stride(0), B, float(threshold), C.byref(res),
                                              C.c_void_p(stream)), "ef_model_submit_device")
         # the launch may come later (queue): keep the tensors away from torch's caching allocator until the flush

@@ -143,10 +143,11 @@ int ef_model_recognize_device(ef_model_t* model, const uint8_t* x, int64_t ldx, 
 int ef_model_recognize_host(ef_model_t* model, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
                             const ef_result_t* out);
 /* Queued submission for a STREAM of batches on one CUDA stream (serving loop; replaces the same reference lines as
- * ef_model_recognize_device).  A submitted batch joins a queue; when queue_depth batches (default and maximum 8) are
- * waiting, or at ef_model_flush_device, ONE persistent kernel recognises all of them back to back: its loads, tensor-core
- * projections, cluster exchange, float64 features and nearest-gallery search run on different warps and overlap ACROSS
- * consecutive batches, so HBM streams without a pause between them.
+ * ef_model_recognize_device).  A submitted batch joins a queue; ONE persistent kernel recognises all queued batches back
+ * to back: its loads, tensor-core projections, cluster exchange, float64 features and nearest-gallery search run on
+ * different warps and overlap ACROSS consecutive batches, so HBM streams without a pause between them.  The queue is
+ * launched when queue_depth batches (default and maximum 16) are waiting, at ef_model_flush_device, and -- adaptive
+ * depth -- as soon as the previous launch of the queue has finished (an idle GPU never waits for the queue to fill).
  *   - x and every array of out must stay valid and unmodified until ef_model_flush_device (or the next
  *     ef_model_recognize_* call on the model) has been enqueued; all results are complete, in stream order, after it;
  *   - every value is bit identical to ef_model_recognize_device.
@@ -155,7 +156,9 @@ int ef_model_recognize_host(ef_model_t* model, const uint8_t* x, int64_t ldx, in
  * queue first.  All calls of one queue must use the same stream (a submit on another stream flushes first).
  * ef_model_set_serving: kernel 0 (default) = the persistent queue kernel, 1 = the pipelined kernel of round 1 (one launch
  * per submit: streams batch i and matches batch i-1; out->proj / out->resid2 written by the batch's own launch, the rest by
- * the next submit or the flush); queue_depth 1..8 (0 keeps the current value).  Only with nothing queued. */
+ * the next submit or the flush); queue_depth 1..16 (0 keeps the current value; a negative value -d sets depth d and
+ * switches the adaptive early launch off: the queue then goes out only when full or flushed).  Only with nothing
+ * queued. */
 int ef_model_submit_device(ef_model_t* model, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
                            const ef_result_t* out, ef_stream_t stream);
 int ef_model_flush_device(ef_model_t* model, ef_stream_t stream);

@@ -329,13 +329,13 @@ def test_tensor_core_filter_is_exact_on_adversarial_galleries(metric, k, n_galle
     np.testing.assert_allclose(outs[1].score, sims.max(1), atol=SCORE_ATOL)
 
 
-@pytest.mark.parametrize("serving", [(0, 8), (0, 3), (0, 1), (1, 0)])
+@pytest.mark.parametrize("serving", [(0, 16), (0, -16), (0, -8), (0, -3), (0, 1), (1, 0)])
 @pytest.mark.parametrize("metric", [ef.METRIC_COSINE_G1, ef.METRIC_COSINE_SK])
 def test_pipelined_submission_is_bit_identical(metric, serving, light_model, golden):
     """ef_model_submit_device / ef_model_flush_device return exactly what ef_model_recognize_device returns, for batches
     of changing sizes, including ragged tiles, a batch larger and one smaller than its predecessor, a single crop, and
     an interleaved ordinary call -- through the persistent queue kernel (serving kernel 0: all queued batches in one
-    launch, queue depths 8 / 3 / 1) and through the pipelined kernel (1: stream of batch i + match of batch i-1)."""
+    launch: adaptive depth 16, fixed depths 16 / 8 / 3, depth 1) and through the pipelined kernel (1: stream of batch i + match of batch i-1)."""
     torch = require_gpu()
     X = golden("gen1_light.npz")["X_u8"]
     rng = np.random.default_rng(77 + metric)

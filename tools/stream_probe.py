@@ -60,14 +60,14 @@ for env, name in configs:
     for kk in ("EF_STREAM_RESIDENT", "EF_STREAM_STAGES", "EF_STREAM_RECV_BUFS"):
         os.environ.pop(kk, None)
     os.environ.update(env)
-    for depth in (8, 4, 2, 1):
+    for depth in (16, -16, -8, -4, -2, -1):          # 16 = adaptive (default); negative = fixed depth
         rec.set_serving(0, depth)
         for o in outs:
-            for v in o.values():
-                if v is not None:
+            for name, v in o.items():
+                if v is not None and not name.startswith("_"):
                     v.zero_()
         us = timed()
-        print(f"stream kernel [{name}] depth {depth}: {us:7.2f} us per batch = {algo / us / 1e3:7.1f} GB/s = "
+        print(f"stream kernel [{name}] depth {depth if depth > 0 else str(-depth) + ' fixed'}: {us:7.2f} us per batch = {algo / us / 1e3:7.1f} GB/s = "
               f"{algo / us / 1e3 / 6550.1:.3f} of HBM peak; {check()}; timeouts {rec.pipeline_timeouts()}", flush=True)
 for kk in ("EF_STREAM_RESIDENT", "EF_STREAM_STAGES", "EF_STREAM_RECV_BUFS"):
     os.environ.pop(kk, None)
@@ -82,7 +82,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "l2":
     half = [keep[0][:2048], keep[1][:2048]] * 4
     xs = half
     outs_keep = outs
-    outs = [{f: (v[:2048] if v is not None else None) for f, v in o.items()} for o in outs]
+    outs = [{f: (v[:2048] if v is not None else None) for f, v in o.items() if not f.startswith("_")} for o in outs]
     print(f"stream kernel, 2048-crop batches (16 clusters = 64 SMs), depth 8: {timed():7.2f} us per batch", flush=True)
     xs, outs = keep, outs_keep
     os.environ.pop("EF_STREAM_PREFETCH")
