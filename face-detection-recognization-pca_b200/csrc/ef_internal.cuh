@@ -69,6 +69,7 @@ int recognize_pipe(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq
 // FEATURE-MAJOR copy of the digit planes: row c * stream_plane_stride(S) + s holds plane s of column c.
 constexpr int kStreamMaxBatches = 16;
 struct StreamBatchDesc {
+  alignas(64) unsigned char tmap[128];   // CUtensorMap of the crops, encoded at submit time (stream_encode_batch)
   const uint8_t* x;
   int64_t ldx;
   int B;
@@ -81,6 +82,8 @@ struct StreamBatchDesc {
   double threshold;
 };
 int stream_plane_stride(int S);
+// fills d->tmap from d->x / d->ldx / d->B (host work of ~1 us per batch, spread over the submits instead of the launch)
+int stream_encode_batch(StreamBatchDesc* d, int D);
 
 bool stream_supported(int D, int k, int kq, int S, int metric, int64_t n);
 int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t* Wfm, int64_t ldw, int wfm_rows, int k,

@@ -572,6 +572,7 @@ int ef_model_submit_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t
       EF_TRY(ef::row_sumsq(x, ldx, B, m->D, m->qq.as<double>(), sq.as<double>(), st));
       d.sumsq_ext = sq.as<double>();
     }
+    EF_TRY(ef::stream_encode_batch(&d, m->D));
     m->queue.push_back(d);
     m->queue_stream = st;
     if ((int)m->queue.size() >= m->queue_depth) return queue_launch(m);

@@ -902,6 +902,16 @@ bool stream_supported(int D, int k, int kq, int S, int metric, int64_t n) {
   return plan_layout(nc_pad, kq, fused_epilogue_kpad(k), filter_kf(k), (int)ceil_div(n, kGalTile), &L);
 }
 
+int stream_encode_batch(StreamBatchDesc* d, int D) {
+  using namespace ef_tc;
+  if (!d || d->B <= 0 || !d->x || (d->ldx & 15) || (reinterpret_cast<uintptr_t>(d->x) & 15)) return EF_ERR_UNSUPPORTED;
+  if (!encode_fn()) return EF_ERR_UNSUPPORTED;
+  CUtensorMap m;
+  if (!make_map(&m, d->x, (uint64_t)D, (uint64_t)d->B, (uint64_t)d->ldx, BLOCK_M)) return EF_ERR_UNSUPPORTED;
+  memcpy(d->tmap, &m, sizeof(m));
+  return EF_OK;
+}
+
 // One persistent launch over nb <= kStreamMaxBatches queued batches.  EF_ERR_UNSUPPORTED outside the kernel's coverage.
 int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t* Wfm, int64_t ldw, int wfm_rows, int k,
                      int kq, int S, const int32_t* col_exp, const double* bias, double c0, const double* gp_padded,
@@ -927,7 +937,12 @@ int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t
     const StreamBatchDesc& d = batches[g];
     if (d.B <= 0 || !d.x || (d.ldx & 15) || (reinterpret_cast<uintptr_t>(d.x) & 15)) return EF_ERR_UNSUPPORTED;
     StreamBatch& b = a.batch[g];
-    if (!make_map(&b.map, d.x, (uint64_t)D, (uint64_t)d.B, (uint64_t)d.ldx, (uint32_t)a.xbox)) return EF_ERR_UNSUPPORTED;
+    static_assert(sizeof(CUtensorMap) == sizeof(d.tmap), "tensor map blob");
+    if (a.xbox == BLOCK_M) {
+      memcpy(&b.map, d.tmap, sizeof(CUtensorMap));   // encoded at submit time
+    } else if (!make_map(&b.map, d.x, (uint64_t)D, (uint64_t)d.B, (uint64_t)d.ldx, (uint32_t)a.xbox)) {
+      return EF_ERR_UNSUPPORTED;
+    }
     b.B = d.B;
     b.sumsq_ext = d.sumsq_ext;
     b.out_proj = d.out_proj; b.out_resid = d.out_resid; b.out_score = d.out_score; b.out_index = d.out_index;

@@ -63,6 +63,7 @@ class Recognizer:
         handle = C.c_void_p()
         check(L.ef_model_create(C.byref(handle), C.byref(desc)), "ef_model_create")
         self._h, self._L = handle, L
+        self._held = []
         self.D, self.k, self.n_gallery, self.metric = D, k, gal.shape[0], metric
         self.with_residual = with_residual
         self._keep = None
@@ -215,15 +216,16 @@ class Recognizer:
 
     def submit_device(self, x, threshold=0.7, out=None, want_residual=None, stream=None):
         """Queued form of recognize_device for a stream of batches (ef_model_submit_device): the batch joins the model's
-        queue; one persistent kernel recognises the queued batches back to back when the queue is full or at
-        flush_device().  x and the returned dict of output tensors must stay alive and untouched until then (the
-        Recognizer keeps references to them until the next flush_device)."""
-        import torch
-        if not (x.is_cuda and x.dtype == torch.uint8 and x.dim() == 2 and x.stride(1) == 1):
-            raise ValueError("x must be a 2-D uint8 CUDA tensor with unit inner stride")
-        B = x.shape[0]
-        want_residual = self.with_residual if want_residual is None else want_residual
+        queue; one persistent kernel recognises the queued batches back to back when the queue is full, when the
+        previous launch has finished, or at flush_device().  x and the returned dict of output tensors must stay alive
+        and untouched until then (the Recognizer keeps references to them until the next flush_device).
+        stream: raw CUDA stream handle (default: torch's current stream; the lookup costs ~1.5 us per call)."""
         if out is None:
+            import torch
+            if not (x.is_cuda and x.dtype == torch.uint8 and x.dim() == 2 and x.stride(1) == 1):
+                raise ValueError("x must be a 2-D uint8 CUDA tensor with unit inner stride")
+            B = x.shape[0]
+            want_residual = self.with_residual if want_residual is None else want_residual
             out = {
                 "features": torch.empty((B, self.k), dtype=torch.float64, device=x.device),
                 "score": torch.empty(B, dtype=torch.float64, device=x.device),
@@ -233,18 +235,24 @@ class Recognizer:
             }
         res = out.get("_res")                       # the ctypes view of a re-used output dict is built once
         if res is None:
-            res = Result(out["features"].data_ptr(), out["score"].data_ptr(), out["index"].data_ptr(),
-                         out["label"].data_ptr(), out["resid2"].data_ptr() if out.get("resid2") is not None else None)
+            import torch
+            if not (x.is_cuda and x.dtype == torch.uint8 and x.dim() == 2 and x.stride(1) == 1):
+                raise ValueError("x must be a 2-D uint8 CUDA tensor with unit inner stride")
+            res = C.byref(Result(out["features"].data_ptr(), out["score"].data_ptr(), out["index"].data_ptr(),
+                                 out["label"].data_ptr(),
+                                 out["resid2"].data_ptr() if out.get("resid2") is not None else None))
             out["_res"] = res
-        if stream is None:                          # (a caller in a tight loop passes the raw handle: the lookup costs ~1.5 us)
+        if stream is None:
+            import torch
             stream = torch.cuda.current_stream(x.device).cuda_stream
-        check(self._L.ef_model_submit_device(self._h, x.data_ptr(), x.stride(0), B, float(threshold), C.byref(res),
-                                             C.c_void_p(stream)), "ef_model_submit_device")
+        status = self._L.ef_model_submit_device(self._h, x.data_ptr(), x.stride(0), x.shape[0], threshold, res, stream)
+        if status:
+            check(status, "ef_model_submit_device")
         # the launch may come later (queue): keep the tensors away from torch's caching allocator until the flush
-        held = self.__dict__.setdefault("_held", [])
+        held = self._held
         held.append((x, out))
         if len(held) > 64:
-            del held[:-16]                 # older batches were launched long ago (queue depth <= 8, stream ordered)
+            del held[:-32]                 # older batches were launched long ago (queue depth <= 16, stream ordered)
         return out
 
     def flush_device(self, device=None):
@@ -252,7 +260,7 @@ class Recognizer:
         import torch
         stream = torch.cuda.current_stream(device).cuda_stream
         check(self._L.ef_model_flush_device(self._h, C.c_void_p(stream)), "ef_model_flush_device")
-        self.__dict__.pop("_held", None)   # everything queued has been launched; stream order protects the tensors now
+        self._held = []                    # everything queued has been launched; stream order protects the tensors now
 
     def bad_boxes(self, device=None):
         """Boxes outside their frame seen by recognize_boxes_device since the last call (synchronises torch's current
