@@ -258,11 +258,20 @@ def process_video(video_path, scanner, output_json=None, output_video=None, thre
     cap.release()
     if writer is not None:
         writer.release()
-    summary = {"video_path": video_path, "total_frames": frame_number, "fps": fps, "threshold": threshold,
-               "total_detections": len(results), "recognized_detections": int(recognised),
-               "recognition_rate": (recognised / len(results)) if results else 0.0,
-               "processing_date": datetime.now().isoformat(), "models": sorted(scanner.models), "rank": rank,
-               "world_size": world, "detections": results}
+    # recognition_results.json of the reference (scripts/auto/scan-template-v2.py:442-502): the six top-level keys and, per
+    # result, frame_number / timestamp / x / y / width / height / person_id / person_name / confidence /
+    # template_match_confidence / ref_frame_diff.  This loop detects with the Haar cascade instead of the reference's
+    # template tracker, so the two tracker fields carry their neutral values (1.0: the detector gives no score; 0: the
+    # box comes from the frame itself); `recognized` and the run summary are additional keys readers may ignore.
+    for d in results:
+        d.setdefault("template_match_confidence", 1.0)
+        d.setdefault("ref_frame_diff", 0)
+    summary = {"video_path": video_path, "total_frames": total_frames if total_frames > 0 else frame_number, "fps": fps,
+               "total_recognitions": len(results), "processing_date": datetime.now().isoformat(), "results": results,
+               "summary": {"frames_processed": frame_number, "threshold": threshold,
+                           "recognized_detections": int(recognised),
+                           "recognition_rate": (recognised / len(results)) if results else 0.0,
+                           "models": sorted(scanner.models), "rank": rank, "world_size": world}}
     if output_json:
         with open(output_json, "w", encoding="utf-8") as f:
             json.dump(summary, f, indent=2, ensure_ascii=False)

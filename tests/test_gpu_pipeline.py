@@ -89,10 +89,13 @@ def test_video_loop_on_a_synthetic_clip(tmp_path, golden):
     res = ef.pipeline.process_video(clip, scanner, out, None, 0.5)
     assert res is not None and res["total_frames"] == 6 and os.path.exists(out)
     saved = json.load(open(out))
-    assert saved["total_detections"] == len(saved["detections"])
-    for d in saved["detections"]:                                         # Haar may or may not fire on this clip
-        assert {"x", "y", "width", "height", "person_id", "person_name", "confidence", "recognized", "frame_number"} <= set(d)
+    # the reference's recognition_results.json schema (scripts/auto/scan-template-v2.py:442-502)
+    assert {"video_path", "total_frames", "fps", "total_recognitions", "processing_date", "results"} <= set(saved)
+    assert saved["total_recognitions"] == len(saved["results"])
+    for d in saved["results"]:                                            # Haar may or may not fire on this clip
+        assert {"frame_number", "timestamp", "x", "y", "width", "height", "person_id", "person_name", "confidence",
+                "template_match_confidence", "ref_frame_diff"} <= set(d)
     # frames dealt over two ranks cover the same detections as one rank
     r0 = ef.pipeline.process_video(clip, scanner, None, None, 0.5, rank=0, world=2)
     r1 = ef.pipeline.process_video(clip, scanner, None, None, 0.5, rank=1, world=2)
-    assert r0["total_detections"] + r1["total_detections"] == res["total_detections"]
+    assert r0["total_recognitions"] + r1["total_recognitions"] == res["total_recognitions"]
