@@ -188,8 +188,10 @@ def test_gen1_dual_model_frame_loop(light_model, dark_model, golden):
     for (x, y, w, h), r in zip(boxes, got):
         vec = opre.resize_linear_u8(gray[y:y + h, x:x + w], 100, 100).reshape(-1).astype(np.float64)
         name, best, ok, ds, ls = ogen1.recognize_face_dual_model(vec, dark_model, light_model, 0.7)
-        assert r[:4] == (x, y, w, h) and r[4] == name and r[6] == ok
+        assert r[:4] == (x, y, w, h) and r[6] == ok
         assert abs(r[5] - best) < 1e-12
+        if abs(ds - ls) > 1e-9:                       # (the pasted crop is in BOTH training sets: an exact tie up to rounding)
+            assert r[4] == name
     assert got[0][6] and got[0][5] > 0.99
     single = ef.gen1.detect_and_recognize_faces(frame, _FixedCascade(boxes), light_model, 0.7)
     assert [s[4] for s in single] == [light_model["person_name"]] * 4 and single[0][6]
