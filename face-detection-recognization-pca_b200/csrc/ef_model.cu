@@ -580,7 +580,8 @@ int ef_model_submit_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int32_t
     // anyway); once it has finished the queued batches go out at once, so a stream that starts from an idle GPU is
     // not held back until queue_depth batches have been submitted
     if (m->queue_ev_pending && cudaEventQuery(m->queue_ev) == cudaSuccess) m->queue_ev_pending = false;
-    if (m->queue_adaptive && !m->queue_ev_pending) return queue_launch(m);
+    // (a launch costs ~14 us on top of ~8.4 us per batch: a lone batch waits for a second one, or for the flush)
+    if (m->queue_adaptive && !m->queue_ev_pending && m->queue.size() >= 2) return queue_launch(m);
     return EF_OK;
   }
   if (m->tc_mode < 2 || !aligned || !m->gimg.p || !ef::pipe_supported(m->k, m->NC, m->metric, m->n_gallery))
