@@ -434,7 +434,12 @@ class MultiModelFaceScanner:
         if bx.shape[1] == 4:
             bx = np.concatenate([np.zeros((B, 1), np.int32), bx], axis=1)
         dev = torch.device("cuda", torch.cuda.current_device())
-        crops = engine.preprocess_device(torch.from_numpy(frames).to(dev), torch.from_numpy(np.ascontiguousarray(bx)).to(dev), 64)
+        bad = torch.zeros(1, dtype=torch.int32, device=dev)
+        crops = engine.preprocess_device(torch.from_numpy(frames).to(dev), torch.from_numpy(np.ascontiguousarray(bx)).to(dev), 64,
+                                         bad=bad)
+        # every model's K2 is enqueued first (no host synchronisation in between), then ONE device -> host read of all
+        # scores and labels: the reference's per-model loop (scan-template-v4.py:297-314) costs one round trip in total
+        launched = []
         for person_name, info in self.models.items():
             model_data = info['model_data']
             if model_data is None:
@@ -442,10 +447,18 @@ class MultiModelFaceScanner:
             try:
                 rec = recognizer_for(model_data)
                 out = rec.recognize_device(crops, threshold, want_residual=False)
-                score, label = out["score"].cpu().numpy(), out["label"].cpu().numpy()
+                launched.append((person_name, model_data, rec, out))
             except Exception as e:
                 print(f"Error recognizing with model {person_name}: {e}")
-                continue
+        if not launched:
+            return best_id.tolist(), best_name.tolist(), best_conf.tolist()
+        scores = torch.stack([o["score"] for _, _, _, o in launched] + [bad.to(torch.float64).expand(B)]).cpu().numpy()
+        labels_all = torch.stack([o["label"] for _, _, _, o in launched]).cpu().numpy()
+        if scores[-1, 0] != 0:
+            raise engine._lib.EigenfacesError(engine._lib.EF_ERR_INVALID, "recognize_faces_all_models",
+                                              f"{int(scores[-1, 0])} of {B} boxes are not inside their frame")
+        for i, (person_name, model_data, rec, _) in enumerate(launched):
+            score, label = scores[i], labels_all[i]
             names = _names_for(label, model_data)
             better = score > best_conf
             best_conf = np.where(better, score, best_conf)
