@@ -97,6 +97,8 @@ SIGNATURES = {
     "ef_gram_u8_tc_work_bytes": (C.c_size_t, [c_i64, c_i32, c_i32]),
     "ef_gram_u8_tc_device": (C.c_int, [c_void, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_void, c_void, C.c_size_t,
                                        c_void]),
+    "ef_gram_u8_tc_store_device": (C.c_int, [c_void, c_i64, c_i64, c_i32, c_i32, c_i32, c_i32, c_void, c_void, C.c_size_t,
+                                             c_void]),
     "ef_gram_center_work_bytes": (C.c_size_t, [c_i32]),
     "ef_gram_center_device": (C.c_int, [c_void, c_i32, c_i32, c_void, c_i64, c_dbl, c_void, c_void, c_void]),
     "ef_eigh_work_bytes": (C.c_size_t, [c_i32]),

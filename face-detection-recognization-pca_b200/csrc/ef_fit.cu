@@ -218,10 +218,11 @@ int ef_fit_gen1_host(const uint8_t* X, int64_t ldx, int32_t N, int32_t D, int32_
   // cov = Xc Xc^T / (N-1)  (:84)  or  Xc^T Xc / (N-1)  (:99): exact integer Gram of the raw pixels on tensor cores,
   // centred on the small matrix with an exact integer numerator (one rounding per entry)
   const int side = snapshot ? 0 : 1;
-  EF_CUDA(cudaMemsetAsync(dG.p, 0, sizeof(int64_t) * (size_t)n * n, st));
-  int gst = ef_gram_u8_tc_device(dX.as<uint8_t>(), ldxd, N, D, 0, D, side, dG.as<int64_t>(), dgw.p, dgw.bytes, st);
-  if (gst == EF_ERR_UNSUPPORTED)
+  int gst = ef_gram_u8_tc_store_device(dX.as<uint8_t>(), ldxd, N, D, 0, D, side, dG.as<int64_t>(), dgw.p, dgw.bytes, st);
+  if (gst == EF_ERR_UNSUPPORTED) {
+    EF_CUDA(cudaMemsetAsync(dG.p, 0, sizeof(int64_t) * (size_t)n * n, st));
     gst = ef_gram_u8_device(dX.as<uint8_t>(), ldxd, N, D, 0, D, side, dG.as<int64_t>(), st);
+  }
   EF_TRY(gst);
   EF_TRY(ef_gram_center_device(dG.as<int64_t>(), n, side, dsum.as<int64_t>(), N, alpha, dA.as<double>(), dcw.p, st));
   int sweeps = 0;

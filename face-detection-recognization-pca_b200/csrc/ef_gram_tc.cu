@@ -36,6 +36,7 @@ constexpr int kAccStages = 2;
 
 struct GramArgs {
   int n, kb_total, block_n, m_tiles, n_tiles, stages, whole, tmem_cols;
+  int overwrite;                       // G = A A^T instead of +=: the first K segment of a tile stores (both triangles)
   long long tiles;                     // tiles touching the upper triangle
   unsigned long long* G;
   long long ldg;
@@ -232,7 +233,22 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int j = 0; j < 32; ++j) my_stage[lane * 33 + j] = v[j];       // row = lane, column = j
         __syncwarp();
         const int c = cg0 + lane;
-        if (a.whole) {
+        if (a.whole && a.overwrite && kb0 == 0) {
+          // fresh result: plain stores, no read of G; the block goes out twice -- as it is (upper triangle, a warp writes
+          // 256 contiguous bytes of a row) and transposed (lower triangle: row cg0 + j, columns r0 .. r0 + 31), so that
+          // no mirror pass has to read the upper triangle back
+#pragma unroll 8
+          for (int rr = 0; rr < 32; ++rr) {
+            const int r = r0 + rr;
+            if (c < a.n && r < a.n && c >= r) __stcg(a.G + (long long)r * a.ldg + c, (unsigned long long)my_stage[rr * 33 + lane]);
+          }
+          const int cm = r0 + lane;
+#pragma unroll 8
+          for (int j = 0; j < 32; ++j) {
+            const int rm = cg0 + j;
+            if (rm < a.n && cm < a.n && rm > cm) __stcg(a.G + (long long)rm * a.ldg + cm, (unsigned long long)my_stage[lane * 33 + j]);
+          }
+        } else if (a.whole) {
           // exclusive owner of this tile: read-add-write, the 16 loads of a half block in flight together
 #pragma unroll
           for (int half = 0; half < 2; ++half) {
@@ -323,7 +339,7 @@ using namespace ef_tc;
 // G[n][ldg] (int64) += A A^T restricted to the upper triangle, then mirrored.  A: uint8 [n][lda] K-major with K valid
 // bytes per row.  EF_ERR_UNSUPPORTED when the TMA alignment rules are not met.
 int gram_tc(const uint8_t* A, int64_t lda, int64_t n, int64_t K, int64_t* G, int64_t ldg, int* status,
-            cudaStream_t stream) {
+            cudaStream_t stream, bool overwrite) {
   if (n <= 0 || K <= 0) return EF_OK;
   if ((lda & 15) || (reinterpret_cast<uintptr_t>(A) & 15) || n > (1 << 20) || K > (1ll << 31) - 256)
     return EF_ERR_UNSUPPORTED;
@@ -348,6 +364,12 @@ int gram_tc(const uint8_t* A, int64_t lda, int64_t n, int64_t K, int64_t* G, int
   if (a.stages < 2) return EF_ERR_UNSUPPORTED;
   const int sms = sm_count();
   a.whole = tiles >= 2ll * sms ? 1 : 0;
+  a.overwrite = overwrite ? 1 : 0;
+  if (overwrite && !a.whole) {
+    // stream-K (small n) accumulates partial tiles with atomics: a fresh result starts from zero
+    EF_CUDA(cudaMemsetAsync(G, 0, sizeof(int64_t) * (size_t)n * (size_t)ldg, stream));
+    a.overwrite = 0;
+  }
   a.G = reinterpret_cast<unsigned long long*>(G);
   a.ldg = ldg;
   a.status = status;
@@ -369,6 +391,7 @@ int gram_tc(const uint8_t* A, int64_t lda, int64_t n, int64_t K, int64_t* G, int
     attr_smem = smem;
   }
   EF_LAUNCH(gram_tc_kernel, grid, kThreads, smem, stream, ma, mb, a);
+  if (a.overwrite && a.kb_total <= kSegKb) return EF_OK;      // every tile had ONE segment: both triangles are written
   dim3 mg((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n, 32));
   EF_LAUNCH(gram_mirror_kernel, mg, 256, 0, stream, a.G, a.n, (long long)ldg);
   return EF_OK;
@@ -392,8 +415,8 @@ size_t ef_gram_u8_tc_work_bytes(int64_t N, int32_t D, int32_t side) {
   return 256 + (side == 1 ? (size_t)D * (size_t)ef::round_up(N, 128) : 0);
 }
 
-int ef_gram_u8_tc_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int32_t d0, int32_t d1, int32_t side,
-                         int64_t* G, void* work, size_t work_bytes, ef_stream_t stream) {
+static int gram_u8_tc_impl(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int32_t d0, int32_t d1, int32_t side,
+                           int64_t* G, void* work, size_t work_bytes, ef_stream_t stream, bool overwrite) {
   if (!X || !G || !work || N < 0 || D <= 0 || ldx < D || d0 < 0 || d1 > D || d0 > d1 || (side != 0 && side != 1))
     return EF_ERR_INVALID;
   if (work_bytes < ef_gram_u8_tc_work_bytes(N, D, side) || (reinterpret_cast<uintptr_t>(work) & 255))
@@ -401,17 +424,30 @@ int ef_gram_u8_tc_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, in
   cudaStream_t st = ef::as_stream(stream);
   int* status = reinterpret_cast<int*>(work);
   EF_CUDA(cudaMemsetAsync(status, 0, 16, st));
-  if (N == 0) return EF_OK;
+  const int64_t n_out = side == 0 ? N : D;
+  if (N == 0 || (side == 0 && d1 == d0)) {
+    if (overwrite && n_out > 0) EF_CUDA(cudaMemsetAsync(G, 0, sizeof(int64_t) * (size_t)n_out * (size_t)n_out, st));
+    return EF_OK;
+  }
   if (side == 0) {
-    if (d1 == d0) return EF_OK;
     if (d0 & 15) return EF_ERR_UNSUPPORTED;
-    return ef::gram_tc(X + d0, ldx, N, d1 - d0, G, N, status, st);
+    return ef::gram_tc(X + d0, ldx, N, d1 - d0, G, N, status, st, overwrite);
   }
   if (d0 != 0 || d1 != D) return EF_ERR_UNSUPPORTED;
   uint8_t* XT = reinterpret_cast<uint8_t*>(work) + 256;
   const int64_t ldt = ef::round_up(N, 128);
   EF_TRY(ef::transpose_u8(X, ldx, N, D, XT, ldt, st));
-  return ef::gram_tc(XT, ldt, D, N, G, D, status, st);
+  return ef::gram_tc(XT, ldt, D, N, G, D, status, st, overwrite);
+}
+
+int ef_gram_u8_tc_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int32_t d0, int32_t d1, int32_t side,
+                         int64_t* G, void* work, size_t work_bytes, ef_stream_t stream) {
+  return gram_u8_tc_impl(X, ldx, N, D, d0, d1, side, G, work, work_bytes, stream, false);
+}
+
+int ef_gram_u8_tc_store_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int32_t d0, int32_t d1, int32_t side,
+                               int64_t* G, void* work, size_t work_bytes, ef_stream_t stream) {
+  return gram_u8_tc_impl(X, ldx, N, D, d0, d1, side, G, work, work_bytes, stream, true);
 }
 
 }  // extern "C"

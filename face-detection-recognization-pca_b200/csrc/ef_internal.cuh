@@ -135,8 +135,9 @@ int match_small(const double* proj, int64_t ldp, int B, int k, const double* gp,
                 double* out_score, int32_t* out_index, int32_t* out_label, cudaStream_t stream);
 
 // ef_gram_tc.cu -- exact integer Gram A A^T of uint8 rows on tensor cores (upper triangle + mirror), G int64 += .
+// overwrite: G = A A^T (previous content ignored; no read of G, both triangles written by the tile epilogues)
 int gram_tc(const uint8_t* A, int64_t lda, int64_t n, int64_t K, int64_t* G, int64_t ldg, int* status,
-            cudaStream_t stream);
+            cudaStream_t stream, bool overwrite = false);
 int transpose_u8(const uint8_t* in, int64_t ldi, int64_t rows, int cols, uint8_t* out, int64_t ldo, cudaStream_t stream);
 
 }  // namespace ef

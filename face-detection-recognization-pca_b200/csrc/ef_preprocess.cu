@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(kThreads, 4)
 preprocess_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int pitch, int width, int height,
                   int channels, int n_frames, const ef_box_t* __restrict__ boxes, int n_boxes, int dw, int dh,
                   uint8_t* __restrict__ out, int64_t out_stride, int* __restrict__ bad_boxes, int stage_bytes,
-                  unsigned int* __restrict__ next_box) {
+                  unsigned int* __restrict__ next_box, int debug_flags) {
   extern __shared__ __align__(16) int tab[];
   __shared__ double scales[2];
   int* xs0 = tab;
@@ -143,7 +143,7 @@ preprocess_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int 
       const int phase = vec ? (int)((reinterpret_cast<uintptr_t>(src)) & 15) : 0;
       // colour frames: every row of the ROI starts at the same offset inside a 32-bit word when the pitches are multiples
       // of four -- the staging then works on aligned words
-      const bool bgr_vec = channels == 3 && (pitch % 4 == 0) && (frame_stride % 4 == 0) &&
+      const bool bgr_vec = !(debug_flags & 2) && channels == 3 && (pitch % 4 == 0) && (frame_stride % 4 == 0) &&
                            ((reinterpret_cast<uintptr_t>(frames) & 3) == 0);
       const int bgr_align = bgr_vec ? (int)(reinterpret_cast<uintptr_t>(src) & 3) : 0;
       const uint8_t* frames_end = frames + (int64_t)n_frames * frame_stride;
@@ -245,7 +245,7 @@ preprocess_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int 
             }
           }
           __syncthreads();
-          if (worker && quad && w >= dw && h >= dh) {
+          if (worker && quad && w >= dw && h >= dh && !(debug_flags & 1)) {
             // Downscale (or equal on one axis): no tap is ever clamped to a DIFFERENT pixel -- x1 = x0 + 1 and
             // y1 = y0 + 1 except where float rounding pushed s onto the last index, and there OpenCV zeroes the
             // fraction, so the weight of the second tap is exactly 0 (the byte read in its place -- one past the row /
@@ -315,6 +315,8 @@ extern "C" int ef_preprocess(const uint8_t* frames, int64_t frame_stride, int32_
   // coefficient tables + a 48 KB staging buffer for the source rows of a band: four CTAs per SM (64 registers)
   int kStageBytes = 48 * 1024;                      // four CTAs per SM; a 220 x 220 ROI fits one band
   if (const char* e = getenv("EF_PRE_STAGE_KB")) { const int v = atoi(e); if (v >= 8 && v <= 96) kStageBytes = v * 1024; }
+  int debug_flags = 0;                              // EF_PRE_DEBUG: 1 = no downscale fast path, 2 = scalar BGR staging
+  if (const char* e = getenv("EF_PRE_DEBUG")) debug_flags = atoi(e);
   const size_t tables = sizeof(int) * (4 * (size_t)(dw + dh) + 4);
   // + slack: the downscale path reads (with weight 0) one byte past a staged row and one row past a staged band
   const size_t smem = tables + kStageBytes + 2048;
@@ -340,6 +342,7 @@ extern "C" int ef_preprocess(const uint8_t* frames, int64_t frame_stride, int32_
   unsigned int* counter = counters_of[dev] + (next_slot.fetch_add(1) & 255u);
   EF_CUDA(cudaMemsetAsync(counter, 0, sizeof(unsigned int), ef::as_stream(stream)));
   EF_LAUNCH(preprocess_kernel, grid, kThreads, smem, ef::as_stream(stream), frames, frame_stride, pitch, width,
-            height, channels, n_frames, boxes, n_boxes, dw, dh, out, out_stride, bad_boxes, kStageBytes, counter);
+            height, channels, n_frames, boxes, n_boxes, dw, dh, out, out_stride, bad_boxes, kStageBytes, counter,
+            debug_flags);
   return EF_OK;
 }

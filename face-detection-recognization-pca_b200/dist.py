@@ -344,19 +344,23 @@ def fit_gen1_sharded(X_local, n_total, n_components, group=None, solver="auto", 
         raise ValueError("fit_gen1_sharded covers the N >= D branch; small training sets fit on one GPU (fit_gen1)")
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     ph = _Phases(timings)
-    buf = torch.zeros(D * D + D, dtype=torch.int64, device=dev)
+    buf = torch.empty(D * D + D, dtype=torch.int64, device=dev)
     G, colsum = buf[:D * D], buf[D * D:]
     ph.mark("start")
     if Nr:
         check(L.ef_colsum_u8_device(X_local.data_ptr(), X_local.stride(0), Nr, D, colsum.data_ptr(), stream), "colsum")
-        # exact integer X_r^T X_r on tensor cores (tcgen05 kind::i8); the dp4a kernel covers unaligned buffers
+        # exact integer X_r^T X_r on tensor cores (tcgen05 kind::i8), stored (no zero fill, no read-add-write of the
+        # 8 D^2-byte result); the dp4a kernel covers unaligned buffers
         wb = int(L.ef_gram_u8_tc_work_bytes(Nr, D, 1))
         gwork = torch.empty(wb, dtype=torch.uint8, device=dev)
-        st_g = L.ef_gram_u8_tc_device(X_local.data_ptr(), X_local.stride(0), Nr, D, 0, D, 1, G.data_ptr(),
-                                      gwork.data_ptr(), wb, stream)
+        st_g = L.ef_gram_u8_tc_store_device(X_local.data_ptr(), X_local.stride(0), Nr, D, 0, D, 1, G.data_ptr(),
+                                            gwork.data_ptr(), wb, stream)
         if st_g == _lib.EF_ERR_UNSUPPORTED:
+            G.zero_()
             st_g = L.ef_gram_u8_device(X_local.data_ptr(), X_local.stride(0), Nr, D, 0, D, 1, G.data_ptr(), stream)
         check(st_g, "gram")
+    else:
+        buf.zero_()
     ph.mark("gram")
     allreduce_exact(buf, group)
     ph.mark("allreduce")

@@ -326,6 +326,11 @@ int ef_gram_u8_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int32
  * pixel sub-range.  Replaces np.dot(Xc, Xc.T) / np.cov(Xc.T) at useless/train.py:84,99 together with
  * ef_gram_center_device. */
 size_t ef_gram_u8_tc_work_bytes(int64_t N, int32_t D, int32_t side);
+/* ef_gram_u8_tc_store_device: the same call with G = (instead of +=): whatever G held is ignored, so a fresh Gram matrix
+ * needs neither a zero fill nor the int64 read-add-write of the result (800 MB each for D = 10 000), and the tile
+ * epilogues write the lower triangle themselves instead of a mirror pass reading the upper one back. */
+int ef_gram_u8_tc_store_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int32_t d0, int32_t d1, int32_t side,
+                               int64_t* G, void* work, size_t work_bytes, ef_stream_t stream);
 int ef_gram_u8_tc_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int32_t d0, int32_t d1, int32_t side,
                          int64_t* G, void* work, size_t work_bytes, ef_stream_t stream);
 /* Centre an integer Gram into the float64 covariance-like matrix with an exact integer numerator:
