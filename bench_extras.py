@@ -107,18 +107,31 @@ def gram_section(ef, torch, dev, peaks):
     work = torch.empty(wb, dtype=torch.uint8, device=dev)
     st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
 
-    def run():
+    def run_acc():
         ef._lib.check(L.ef_gram_u8_tc_device(x.data_ptr(), x.stride(0), N, Dg, 0, Dg, 1, G.data_ptr(), work.data_ptr(),
                                              wb, st), "ef_gram_u8_tc_device")
+
+    def run():
+        ef._lib.check(L.ef_gram_u8_tc_store_device(x.data_ptr(), x.stride(0), N, Dg, 0, Dg, 1, G.data_ptr(), work.data_ptr(),
+                                                   wb, st), "ef_gram_u8_tc_store_device")
+    ms_acc = _time_loop(torch, run_acc, 5)
     ms = _time_loop(torch, run, 5)
+    # the stored result against the accumulated one (G was zero before the first accumulating call: 7 calls in total)
+    Gs = G.clone()
+    G.zero_()
+    run_acc()
+    torch.cuda.synchronize()
+    store_equals_accumulate = bool(torch.equal(Gs, G))
+    del Gs
     tiles = sum(min((256 * tj + 255) // 128 + 1, (Dg + 127) // 128) for tj in range((Dg + 255) // 256))
     executed = 2.0 * tiles * 128 * 256 * ((N + 127) // 128 * 128)
     algorithmic = 2.0 * Dg * Dg * N / 2.0
     bf16_peak = peaks.get("bf16_tflops", 1590.0)
     i8_peak = int8_peak_probe(torch, dev)
-    out = {"what": f"ef_gram_u8_tc_device side 1: X^T X of u8[{N},{Dg}] -> int64[{Dg},{Dg}] (tcgen05 kind::i8 SYRK, upper "
-                   "triangle + mirror), exact; whole call",
-           "ms": ms, "algorithmic_tops": algorithmic / ms / 1e9, "executed_tops": executed / ms / 1e9,
+    out = {"what": f"ef_gram_u8_tc_store_device side 1: X^T X of u8[{N},{Dg}] -> int64[{Dg},{Dg}] (transpose + tcgen05 kind::i8 "
+                   "SYRK of the upper-triangle tiles, both triangles stored by the tile epilogues), exact; whole call",
+           "ms": ms, "ms_accumulating_call": ms_acc, "store_equals_accumulate": store_equals_accumulate,
+           "algorithmic_tops": algorithmic / ms / 1e9, "executed_tops": executed / ms / 1e9,
            "roofline": {"bound": "tensor", "achieved": algorithmic / ms / 1e9, "peak": bf16_peak,
                         "unit": "TOP/s (algorithmic N*D^2 int8 ops, symmetric half) vs measured bf16 TFLOP/s",
                         "frac": algorithmic / ms / 1e9 / bf16_peak,

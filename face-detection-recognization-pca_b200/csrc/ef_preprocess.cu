@@ -146,7 +146,8 @@ preprocess_kernel(const uint8_t* __restrict__ frames, int64_t frame_stride, int 
       const bool bgr_vec = !(debug_flags & 2) && channels == 3 && (pitch % 4 == 0) && (frame_stride % 4 == 0) &&
                            ((reinterpret_cast<uintptr_t>(frames) & 3) == 0);
       const int bgr_align = bgr_vec ? (int)(reinterpret_cast<uintptr_t>(src) & 3) : 0;
-      const uint8_t* frames_end = frames + (int64_t)n_frames * frame_stride;
+      // end of the last frame's rows (frame_stride may be 0 for a single frame: a size-1 axis has an arbitrary stride)
+      const uint8_t* frames_end = frames + (int64_t)(n_frames - 1) * frame_stride + (int64_t)height * pitch;
       const int wp = ((phase + w + 15) & ~15);
       const int rows_fit = stage_bytes / wp;
       if (rows_fit < 2 || dw > kThreads) {
