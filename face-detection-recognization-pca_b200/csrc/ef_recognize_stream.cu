@@ -12,8 +12,10 @@
 //   warp 6        float16 [g_hi | g_lo | g_hi] image of the gallery -> shared memory, once per launch (resident)
 //   warp 7        tcgen05.mma kind::f16 issuer of the nearest-row filter
 //   warps 8..11   drain + combine: TMEM -> registers -> digit planes combined to TWO exact int64 per column
-//                 (ef::planes_to_hilo: 2.2 x fewer bytes than the eight int32 planes) -> 16-byte st.shared::cluster into
-//                 the receive buffer of the CTA that owns those 32 crops -> remote mbarrier arrive (release.cluster);
+//                 (ef::planes_to_hilo: 2.2 x fewer bytes than the eight int32 planes) -> 16-byte st.async into the
+//                 receive buffer of the CTA that owns those 32 crops; the stores themselves complete the BYTE count of
+//                 the owner's mbarrier (a release.cluster arrive is a MEMBAR.ALL.GPU: measured 1.5-2 us per item on the
+//                 sum-of-squares warps, which stalled the stage ring once per batch);
 //                 then, for MY 32 crops: wait for the four partial slabs (acquire.cluster), exact integer sum, float64
 //                 features (+ reconstruction error), exact-scorer vectors and the float16 [hi|hi|lo] filter operand
 //                 (double buffered)
@@ -89,7 +91,7 @@ struct StreamArgs {
   const double* gnorm;
   const double* ginv;
   const int32_t* labels;
-  int n, kf, g_tiles, debug_no_ssq, prefetch, xbox;
+  int n, kf, g_tiles, debug, prefetch, xbox;   // debug bit 0: EF_STREAM_NO_SSQ (measurement only, the residual is wrong)
   const __half* gimg;          // float16 [g_hi | g_lo | g_hi] image of the prepared gallery (gallery_image)
   int* status;
   int off_recv, off_ps, off_pe, off_bop, off_gal, off_sh;
@@ -101,7 +103,7 @@ struct StreamShared {
   unsigned long long empty_bar[kMaxStages];
   unsigned long long acc_full[2];
   unsigned long long acc_empty[2];
-  unsigned long long recv_full[2];            // arrived on by the drain + sum-of-squares lanes of all four CTAs
+  unsigned long long recv_full[2];            // completed by the bytes of the drain + sum-of-squares pushes of all four CTAs
   unsigned long long push_ok[2][kCluster];    // [receive buffer][owner]: owner consumed that buffer (remote arrive)
   unsigned long long gal_full;                // the resident gallery image has landed (once per launch)
   unsigned long long bop_ready[2];            // combine warps: the filter operand of item it is in place ([it & 1])
@@ -187,7 +189,7 @@ __device__ __forceinline__ void bar_finish() { asm volatile("bar.sync 5, 128;" :
 __device__ __forceinline__ void bar_front() { asm volatile("bar.sync 6, 128;" ::: "memory"); }    // drain + combine warps
 
 template <int PS>
-__device__ __forceinline__ void push_chunk(const uint32_t (&v)[16], int c0, int kq, uint32_t dst) {
+__device__ __forceinline__ void push_chunk(const uint32_t (&v)[16], int c0, int kq, uint32_t dst, uint32_t dst_bar) {
 #pragma unroll
   for (int f = 0; f < 16 / PS; ++f) {
     const int c = c0 / PS + f;
@@ -197,7 +199,7 @@ __device__ __forceinline__ void push_chunk(const uint32_t (&v)[16], int c0, int 
       for (int s = 0; s < 8; ++s) plane[s] = s < PS ? (int32_t)v[f * PS + s] : 0;
       long long hi, lo;
       ef::planes_to_hilo(plane, hi, lo);
-      st_cluster_v2_u64(dst + (uint32_t)c * (QB * 16u), (unsigned long long)hi, (unsigned long long)lo);
+      st_async_v2_u64(dst + (uint32_t)c * (QB * 16u), (unsigned long long)hi, (unsigned long long)lo, dst_bar);
     }
   }
 }
@@ -231,6 +233,8 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   const uint32_t gal_tile_bytes = (uint32_t)kGalTile * (uint32_t)row_bytes;
   const uint32_t bop_bytes = ((uint32_t)(QB * row_bytes) + 1023u) & ~1023u;     // one of the two filter-operand buffers
   const uint32_t recv_buf_bytes = (uint32_t)(kCluster * a.kq * QB * 16);
+  // bytes one use of a receive buffer collects: four sources x (kq columns x 32 crops x (hi, lo) + 32 sums of squares)
+  const uint32_t recv_tx_bytes = (uint32_t)(kCluster * (a.kq * QB * 16 + QB * 8));
 
   if (tid == 0) {
     for (int s = 0; s < a.stages; ++s) {
@@ -240,7 +244,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(&sh->acc_full[s], 1);
       mbar_init(&sh->acc_empty[s], 4);
-      mbar_init(&sh->recv_full[s], kCluster * 2 * QB);   // 4 sources x (32 drain lanes + 32 sum-of-squares lanes)
+      mbar_init(&sh->recv_full[s], 1);             // armed by the owner; completed by the BYTES of the async pushes
       for (int q = 0; q < kCluster; ++q) mbar_init(&sh->push_ok[s][q], 1);
     }
     mbar_init(&sh->gal_full, 1);
@@ -256,6 +260,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       mbar_init(&sh->list_free[i], 1);
     }
     sh->failed = 0;
+    for (int s = 0; s < a.recv_bufs; ++s) mbar_arrive_expect_tx(&sh->recv_full[s], recv_tx_bytes);   // first use of each buffer
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -358,7 +363,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
     // =================================================================== exact sum of squares of the staged crop rows
     const int owner = warp & 3;                      // rows 32 owner .. 32 owner + 31 of the tile belong to CTA `owner`
     const int row_in_tile = owner * 32 + lane;
-    int stage = 0, it = 0;
+    int stage = 0, it = 0, n_ssq = 0;
     uint32_t phase = 0;
     bool ok = true;
     for (int g = 0; g < a.nb; ++g) {
@@ -369,7 +374,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
         if (!ok) break;
         const uint4* line = reinterpret_cast<const uint4*>(sA + (size_t)stage * A_STAGE_BYTES + row_in_tile * BLOCK_K);
         unsigned int partial = 0;
-        if (!a.debug_no_ssq)                         // EF_STREAM_NO_SSQ (measurement only: the residual is then wrong)
+        if (!(a.debug & 1))                          // EF_STREAM_NO_SSQ (measurement only: the residual is then wrong)
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           const uint4 v = line[(j + row_in_tile) & 7];
@@ -381,14 +386,15 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
         ssq += partial;
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh->empty_bar[stage]);
+        if (trace && warp == 2 && lane == 0 && n_ssq < 64) trace[128 + n_ssq++] = globaltimer();
         if (++stage == a.stages) { stage = 0; phase ^= 1; }
       }
       if (!ok) break;
       const int rb = it % a.recv_bufs, use = it / a.recv_bufs;
       ok = __all_sync(0xffffffffu, mbar_wait_cluster(&sh->push_ok[rb][owner], (uint32_t)((use & 1) ^ 1), failed));
       if (!ok) break;
-      st_cluster_u64(map_to_cta(smem_u32(&sh->ssq_recv[rb][rank][lane]), (uint32_t)owner), ssq);
-      mbar_arrive_remote(map_to_cta(smem_u32(&sh->recv_full[rb]), (uint32_t)owner));
+      st_async_u64(map_to_cta(smem_u32(&sh->ssq_recv[rb][rank][lane]), (uint32_t)owner), ssq,
+                   map_to_cta(smem_u32(&sh->recv_full[rb]), (uint32_t)owner));
       ++it;
     }
   } else if (warp == 6) {
@@ -547,21 +553,23 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       const int rb = it % a.recv_bufs, use = it / a.recv_bufs;
       ok = __all_sync(0xffffffffu, ok && timed_wait(&sh->push_ok[rb][q], (uint32_t)((use & 1) ^ 1), failed,
                                                    wslot ? wslot + 1 : nullptr, true));
+      if (trace && tid == 8 * 32 && it < 16) trace[192 + 2 * it] = globaltimer();
       if (ok) {
         const uint32_t dst = map_to_cta(smem_u32(recv) + (uint32_t)rb * recv_buf_bytes +
                                             (uint32_t)((int)rank * a.kq * QB + lane) * 16u,
                                         (uint32_t)q);
         const uint32_t src = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccCols);
+        const uint32_t dst_bar = map_to_cta(smem_u32(&sh->recv_full[rb]), (uint32_t)q);
         for (int c0 = 0; c0 < a.nc_pad; c0 += 16) {
           uint32_t v[16];
           tmem_ld16(src + (uint32_t)c0, v);
-          if (a.PS == 8) push_chunk<8>(v, c0, a.kq, dst); else push_chunk<4>(v, c0, a.kq, dst);
+          if (a.PS == 8) push_chunk<8>(v, c0, a.kq, dst, dst_bar); else push_chunk<4>(v, c0, a.kq, dst, dst_bar);
         }
-        mbar_arrive_remote(map_to_cta(smem_u32(&sh->recv_full[rb]), (uint32_t)q));
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh->acc_empty[buf]);
         if (probe && q == 0 && lane == 0) probe[3] = globaltimer();
+        if (trace && tid == 8 * 32 && it < 16) trace[193 + 2 * it] = globaltimer();
       }
       // ---- my CTA's 32 crops of this item
       const int b = row0 + (int)rank * QB + lane;    // the crop this lane finishes
@@ -601,8 +609,11 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
         for (int src = 0; src < kCluster; ++src) ssq_total += sh->ssq_recv[rb][src][lane];
       }
       bar_front();                                   // receive buffer consumed; features complete
-      if (fw == 1 && lane < kCluster)                // hand the buffer back to the four sources
-        mbar_arrive_remote(map_to_cta(smem_u32(&sh->push_ok[rb][rank]), (uint32_t)lane));
+      if (fw == 1) {                                 // re-arm the byte count, then hand the buffer back to the four sources
+        if (lane == 0 && ok) mbar_arrive_expect_tx(&sh->recv_full[rb], recv_tx_bytes);
+        __syncwarp();
+        if (lane < kCluster) mbar_arrive_remote_relaxed(map_to_cta(smem_u32(&sh->push_ok[rb][rank]), (uint32_t)lane));
+      }
       // the match warps are done with feature buffer fb (item it - 2)?
       ok = __all_sync(0xffffffffu, ok && timed_wait(&sh->feat_free[fb], (uint32_t)(((it >> 1) & 1) ^ 1), failed,
                                                    wslot ? wslot + 3 : nullptr));
@@ -829,7 +840,7 @@ int launch_stream(StreamArgs& a, const StreamLayout& L, int m_tiles, cudaStream_
   EF_CUDA(cudaLaunchKernelEx(&cfg, recognize_stream_kernel<METRIC, KR>, a));
   ef::g_launches.fetch_add(1, std::memory_order_relaxed);
   if (a.probe) {
-    std::vector<unsigned long long> h((size_t)grid_n * 32 + 128);
+    std::vector<unsigned long long> h((size_t)grid_n * 32 + 256);
     EF_CUDA(cudaStreamSynchronize(stream));
     EF_CUDA(cudaMemcpy(h.data(), probe_buf[dev], h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     unsigned long long t0 = ~0ull;
@@ -854,9 +865,12 @@ int launch_stream(StreamArgs& a, const StreamLayout& L, int m_tiles, cudaStream_
     }
     {
       const unsigned long long* tr = h.data() + (size_t)grid_n * 32;
-      fprintf(stderr, "\n[ef_stream_probe] CTA 0, first stages: issue time / landed time (ns since first issue):");
-      for (int i = 0; i < 48; ++i)
-        if (tr[i] && tr[64 + i]) fprintf(stderr, " %llu/%llu", tr[i] - tr[0], tr[64 + i] - tr[0]);
+      fprintf(stderr, "\n[ef_stream_probe] CTA 0, first stages: issue / landed / sum-of-squares arrive (ns since first issue):");
+      for (int i = 0; i < 64; ++i)
+        if (tr[i] && tr[64 + i]) fprintf(stderr, " %llu/%llu/%llu", tr[i] - tr[0], tr[64 + i] - tr[0], tr[128 + i] ? tr[128 + i] - tr[0] : 0ull);
+      fprintf(stderr, "\n[ef_stream_probe] CTA 0, drain start/end per item (ns since first issue):");
+      for (int i = 0; i < 16; ++i)
+        if (tr[192 + 2 * i]) fprintf(stderr, " %llu-%llu", tr[192 + 2 * i] - tr[0], tr[193 + 2 * i] - tr[0]);
     }
     // accumulated wait times of the roles (slots 16..): where each pipeline stage spends its idle time
     const char* wnames[12] = {"tma:empty", "mma:full", "mma:acc_empty", "drain:acc_full", "drain:push_ok", "comb:recv_full",
@@ -959,7 +973,7 @@ int recognize_stream(const StreamBatchDesc* batches, int nb, int D, const int8_t
   a.col_exp = col_exp; a.bias = bias; a.c0 = c0;
   a.gp = gp_padded; a.gnorm = gnorm; a.ginv = ginv; a.labels = labels; a.n = (int)n;
   a.kf = filter_kf(k); a.g_tiles = g_tiles;
-  a.debug_no_ssq = getenv("EF_STREAM_NO_SSQ") ? 1 : 0;
+  a.debug = getenv("EF_STREAM_NO_SSQ") ? 1 : 0;
   a.prefetch = 0;                                    // K blocks (16 KB crop boxes) the L2 prefetch cursor runs ahead
   if (const char* e = getenv("EF_STREAM_PREFETCH")) a.prefetch = std::max(0, std::min(64, atoi(e)));
   a.gimg = reinterpret_cast<const __half*>(gimg);

@@ -103,6 +103,24 @@ __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 
+// Remote arrive without a memory fence: for hand-backs that release nothing (the arriving thread only READ the buffer it
+// returns).  The .release.cluster form above costs a MEMBAR.ALL.GPU per arrive -- microseconds under a busy TMA stream.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+
+// Asynchronous remote stores (STAS): the data and its completion travel together -- the store itself signals
+// `bytes` on the destination CTA's mbarrier when it has landed, so the producer needs neither a fence nor an arrive.
+__device__ __forceinline__ void st_async_u64(uint32_t cluster_addr, unsigned long long v, uint32_t cluster_mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.b64 [%0], %1, [%2];"
+               ::"r"(cluster_addr), "l"(v), "r"(cluster_mbar) : "memory");
+}
+__device__ __forceinline__ void st_async_v2_u64(uint32_t cluster_addr, unsigned long long a, unsigned long long b,
+                                                uint32_t cluster_mbar) {
+  asm volatile("st.async.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];"
+               ::"r"(cluster_addr), "l"(a), "l"(b), "r"(cluster_mbar) : "memory");
+}
+
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c_inner,
                                             int c_outer) {
   asm volatile(

@@ -107,6 +107,21 @@ if len(sys.argv) > 1 and sys.argv[1] == "prefetch":
         us = timed()
         print(f"stream kernel, L2 prefetch {pf:2d} K blocks ahead, depth 8: {us:7.2f} us per batch = {algo / us / 1e3 / 6550.1:.3f} of HBM peak; {check()}", flush=True)
     os.environ.pop("EF_STREAM_PREFETCH")
+if len(sys.argv) > 1 and sys.argv[1] == "debug":
+    # interference matrix: one role's work switched off at a time (EF_STREAM_DEBUG bits; the results are then wrong)
+    rec.set_serving(0, -16)
+    names = {0: "all roles", 1: "no sum-of-squares reads", 2: "drain: tcgen05.ld only (no combine-to-int64, no DSMEM push)",
+             6: "drain: nothing", 8: "combine: no integer sums", 16: "scan: no tcgen05.ld of the scores", 32: "re-score: nothing",
+             64: "filter: no MMAs", 126: "everything but the stream off", 127: "everything off"}
+    for bits, nm in names.items():
+        os.environ["EF_STREAM_DEBUG"] = str(bits)
+        print(f"stream kernel, depth 16 fixed, debug {bits:3d} ({nm}): {timed():7.2f} us per batch; timeouts {rec.pipeline_timeouts()}", flush=True)
+    os.environ.pop("EF_STREAM_DEBUG")
+    os.environ["EF_TC_PROBE"] = "1"
+    rec.set_serving(0, -8)
+    run(8)
+    torch.cuda.synchronize()
+    sys.exit(0)
 if len(sys.argv) > 1 and sys.argv[1] == "limits":
     # where does the stream time go?  (a) without the sum-of-squares reads of the staged tiles (results then differ),
     # (b) with half the digit planes (S = 4: half the basis traffic and half the MMA operand reads)
