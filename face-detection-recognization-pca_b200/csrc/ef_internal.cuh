@@ -67,7 +67,7 @@ int recognize_pipe(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq
 // ef_recognize_stream.cu -- persistent serving kernel over a queue of batches (ef_model_submit_device / _flush_device):
 // loads, MMAs, cluster exchange, features and matching of consecutive batches overlap inside ONE launch.  Wfm is the
 // FEATURE-MAJOR copy of the digit planes: row c * stream_plane_stride(S) + s holds plane s of column c.
-constexpr int kStreamMaxBatches = 16;
+constexpr int kStreamMaxBatches = 32;
 struct StreamBatchDesc {
   alignas(64) unsigned char tmap[128];   // CUtensorMap of the crops, encoded at submit time (stream_encode_batch)
   const uint8_t* x;

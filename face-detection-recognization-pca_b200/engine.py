@@ -84,7 +84,7 @@ class Recognizer:
 
     def set_serving(self, kernel=0, queue_depth=0):
         """submit_device's kernel: 0 = persistent queue kernel (default), 1 = pipelined kernel (one launch per submit);
-        queue_depth 1..16 batches per persistent launch (0 keeps the current value, -d = fixed depth d without the
+        queue_depth 1..32 batches per persistent launch (0 keeps the current value, -d = fixed depth d without the
         adaptive early launch)."""
         check(self._L.ef_model_set_serving(self._h, int(kernel), int(queue_depth)), "ef_model_set_serving")
 
@@ -252,7 +252,7 @@ class Recognizer:
         held = self._held
         held.append((x, out))
         if len(held) > 64:
-            del held[:-32]                 # older batches were launched long ago (queue depth <= 16, stream ordered)
+            del held[:-32]                 # older batches were launched long ago (queue depth <= 32, stream ordered)
         return out
 
     def flush_device(self, device=None):

@@ -156,7 +156,7 @@ int ef_model_recognize_host(ef_model_t* model, const uint8_t* x, int64_t ldx, in
  * queue first.  All calls of one queue must use the same stream (a submit on another stream flushes first).
  * ef_model_set_serving: kernel 0 (default) = the persistent queue kernel, 1 = the pipelined kernel of round 1 (one launch
  * per submit: streams batch i and matches batch i-1; out->proj / out->resid2 written by the batch's own launch, the rest by
- * the next submit or the flush); queue_depth 1..16 (0 keeps the current value; a negative value -d sets depth d and
+ * the next submit or the flush); queue_depth 1..32 (0 keeps the current value; a negative value -d sets depth d and
  * switches the adaptive early launch off: the queue then goes out only when full or flushed).  Only with nothing
  * queued. */
 int ef_model_submit_device(ef_model_t* model, const uint8_t* x, int64_t ldx, int32_t B, double threshold,
