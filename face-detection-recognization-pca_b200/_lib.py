@@ -103,6 +103,7 @@ SIGNATURES = {
     "ef_gram_center_device": (C.c_int, [c_void, c_i32, c_i32, c_void, c_i64, c_dbl, c_void, c_void, c_void]),
     "ef_eigh_work_bytes": (C.c_size_t, [c_i32]),
     "ef_eigh_jacobi_device": (C.c_int, [c_void, c_i32, c_void, c_void, c_void, c_i32, c_dbl, p_i32, p_dbl, c_void]),
+    "ef_chol_inverse_device": (C.c_int, [c_void, c_i32, c_void, c_void, c_void]),
     "ef_dgemm_device": (C.c_int, [c_i32, c_i32, c_i32, c_dbl, c_void, c_i64, c_i64, c_void, c_i64, c_i64, c_dbl, c_void,
                                   c_i64, c_void]),
     "ef_standardize_u8_device": (C.c_int, [c_void, c_i64, c_i64, c_i32, c_void, c_void, c_void, c_void, c_i64, c_void]),

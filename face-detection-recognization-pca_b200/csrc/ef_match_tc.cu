@@ -5,10 +5,15 @@
 //   * queries and gallery rows are normalised and split into float16 hi + lo; s~ = q_hi.g_hi + q_hi.g_lo + q_lo.g_hi
 //     is a tcgen05.mma kind::f16 GEMM (M = 128 queries, N = 256 gallery rows, K = 3k padded to slabs of 64) with
 //     float32 accumulation in TMEM; |s~ - cos| <= kEps (3k <= 384 products: 384 * 2^-22 accumulation + 2e-6 split);
-//   * pass 0 reduces the approximate maximum per (query, gallery chunk); pass 1 recomputes the tiles and appends every
-//     row with s~ >= M - 2 kEps to a candidate list; the candidates are scored in float64 with EXACTLY the arithmetic
-//     of match_kernel (same norm, same sequential fma order, same tie rule), so score and index are bit identical to
-//     the float64 scan.  A candidate-list overflow (degenerate galleries) reports EF_ERR_UNSUPPORTED at the next
+//   * ONE pass over the gallery image: every scanning thread (= one query) keeps the running maximum of the scores
+//     it has seen, publishes it to a per-query word in global memory (atomicMax) and picks up what the CTAs working
+//     on other gallery chunks published at every tile boundary; a row goes to the candidate list when
+//     s~ >= (best maximum known so far) - 2 kEps.  The known maximum only grows towards the final maximum M, so the list
+//     is a superset of {s~ >= M - 2 kEps} (which contains the exact arg-max and all exact ties); entries below the
+//     FINAL threshold are dropped by their stored s~ before the float64 work.  (Round 1 read the 768 MB image twice:
+//     pass 0 for M, pass 1 for the rows.)  The survivors are scored in float64 with EXACTLY the arithmetic of
+//     match_kernel (same norm, same sequential fma order, same tie rule), so score and index are bit identical to the
+//     float64 scan.  A candidate-list overflow (degenerate galleries) reports EF_ERR_UNSUPPORTED at the next
 //     synchronisation point of the caller through the flag word; the Python wrapper then runs the float64 scan.
 // Blackwell mapping: the float16 gallery image streams as 32 KB (256 rows x one 128-byte K slab, SWIZZLE_128B) blocks
 // through a cp.async.bulk ring; the query tile is resident in shared memory; two 256-column TMEM accumulators alternate
@@ -45,12 +50,23 @@ struct MatchTcArgs {
   int g_tiles, tiles_per_chunk, b_pad;
   float* cmax;                 // [chunks][b_pad]           (pass 0 out)
   const float* thr;            // [b_pad]                   (pass 1 in)
+  unsigned int* gmax;          // [b_pad] ordered-integer image of the best approximate score known per query (pass 2)
   int* cand_q;
   long long* cand_j;
+  float* cand_f;               // approximate score of the candidate (pass 2: pruned against the final threshold)
   unsigned int* counter;       // [0] candidates, [1] overflow flag
   unsigned int cap;
   int* status;
 };
+
+// order-preserving map float <-> unsigned (atomicMax on scores); 0 is below every finite score
+__device__ __forceinline__ unsigned f2ord(float f) {
+  const unsigned u = __float_as_uint(f);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float ord2f(unsigned u) {
+  return u == 0u ? -CUDART_INF_F : __uint_as_float((u & 0x80000000u) ? (u & 0x7fffffffu) : ~u);
+}
 
 struct MatchTcShared {
   unsigned long long full_bar[kMaxStages];
@@ -178,7 +194,8 @@ match_tc_kernel(const MatchTcArgs a) {
     const int q = qt * BLOCK_M + lane_group * 32 + lane;         // this thread's query
     const bool live = q < a.B;
     float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
-    const float thr = (a.pass == 1 && live) ? a.thr[q] : CUDART_INF_F;
+    float thr = (a.pass == 1 && live) ? a.thr[q] : CUDART_INF_F;
+    float runmax = -CUDART_INF_F, published = -CUDART_INF_F;     // pass 2: this thread's running maximum
     int acc = 0;
     uint32_t fphase = 0;
     bool ok = true;
@@ -187,6 +204,11 @@ match_tc_kernel(const MatchTcArgs a) {
       if (!ok) break;
       tc_fence_after();
       const long long jbase = (long long)gt * BN;
+      if (a.pass == 2 && live) {
+        // what the CTAs of the other gallery chunks have found so far (a plain L2 read: any earlier value is valid)
+        const float known = ord2f(*reinterpret_cast<volatile unsigned int*>(a.gmax + q));
+        thr = fmaxf(runmax, known) - 2.f * kEps;
+      }
       for (int c0 = 0; c0 < BN; c0 += 32) {
         const long long j0 = jbase + c0;
         if (j0 >= a.n) break;                      // warp uniform
@@ -206,6 +228,48 @@ match_tc_kernel(const MatchTcArgs a) {
 #pragma unroll
             for (int i = 0; i < 32; ++i)
               if (i < valid) m0 = fmaxf(m0, __uint_as_float(v[i]));
+          }
+        } else if (a.pass == 2) {
+          unsigned mask = 0u;
+          float vm = -CUDART_INF_F;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            const float f = __uint_as_float(v[i]);
+            mask |= (f >= thr ? 1u : 0u) << i;
+            if (valid == 32 || i < valid) vm = fmaxf(vm, f);
+          }
+          if (valid < 32) mask &= (1u << valid) - 1u;
+          if (!live) mask = 0u;
+          // one reservation per warp and column group: the lanes' counts are prefix-summed with shuffles
+          if (__any_sync(0xffffffffu, mask != 0u)) {
+            const int cnt = __popc(mask);
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+              const int t = __shfl_up_sync(0xffffffffu, incl, o);
+              if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            unsigned base = 0u;
+            if (lane == 0) base = atomicAdd(a.counter, (unsigned)total);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            unsigned slot = base + (unsigned)(incl - cnt);
+            while (mask) {
+              const int i = __ffs(mask) - 1;
+              mask &= mask - 1u;
+              if (slot < a.cap) {
+                a.cand_q[slot] = q;
+                a.cand_j[slot] = j0 + i;
+                a.cand_f[slot] = __uint_as_float(v[i]);
+              } else {
+                a.counter[1] = 1u;
+              }
+              ++slot;
+            }
+          }
+          if (vm > runmax) {
+            runmax = vm;
+            thr = fmaxf(thr, runmax - 2.f * kEps);
           }
         } else {
           unsigned mask = 0u;
@@ -229,6 +293,10 @@ match_tc_kernel(const MatchTcArgs a) {
       __syncwarp();
       if (lane == 0) mbar_arrive(&sh->tmem_empty_bar[acc]);
       if (++acc == 2) { acc = 0; fphase ^= 1; }
+      if (a.pass == 2 && live && runmax > published) {
+        atomicMax(a.gmax + q, f2ord(runmax));
+        published = runmax;
+      }
     }
     if (a.pass == 0 && q < a.b_pad)
       a.cmax[(size_t)chunk * a.b_pad + q] = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));

@@ -183,19 +183,38 @@ def _jacobi(L, stream, H, work):
     return evals, evecs
 
 
-def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=1234, group=None):
+def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=None, block=None, seed=1234, group=None, orth_method=None,
+                     lock=None):
     """Largest k eigenpairs of a symmetric positive semi-definite CUDA float64 matrix Cm [n, n] that is too large for the
     Jacobi solver (config 4: the 10 000 x 10 000 covariance, k = 256): Chebyshev-filtered subspace iteration with
-    Rayleigh-Ritz (Zhou & Saad's scaled filter).  Every dense product is ef_dgemm_device, every small eigenproblem
-    (block x block, block <= 320) the cluster-resident Jacobi kernel; torch only allocates and does O(n block) vector work.
-    Replaces np.linalg.eigh(cov) + descending sort + top-k of useless/train.py:103-116 for large D.
-    Stops when max_i |C q_i - theta_i q_i| <= tol * theta_1, after max_outer outer iterations, or when the residual
-    stagnates (info["stagnated"]: near-degenerate trailing eigenvalues, e.g. planted factors below the noise floor).
-    With a process group the dominant cost -- the n x n by n x block covariance products -- is SHARDED: rank r multiplies
-    its contiguous block of rows of C and one all-gather (n x block float64 over NVLink) reassembles the product; every
-    element is computed by the same kernel with the same summation order whoever owns its row, so all ranks hold
-    bit-identical iterates (and the same result as a single GPU).  The block x block work stays replicated.
+    Rayleigh-Ritz and LOCKING (Zhou & Saad's scaled filter).  Replaces np.linalg.eigh(cov) + descending sort + top-k of
+    useless/train.py:103-116 for large D.
+
+    Every dense product is ef_dgemm_device, every small eigenproblem (block x block, block <= 320) the cluster-resident
+    Jacobi kernel, the re-orthonormalisation after a filter application CholeskyQR2 (ef_chol_inverse_device: one CTA,
+    ~0.1 ms; the Gram-matrix Jacobi route -- robust against rank loss, 10 ms per pass -- takes over when a pivot is not
+    positive); torch only allocates and does O(n block) vector work.
+
+    Locking: the leading run of Ritz pairs whose residual is below the tolerance leaves the block; the remaining
+    columns iterate on the DEFLATED operator C - Ql diag(theta_l) Ql^T (two thin products per application), whose locked
+    directions sit at eigenvalue ~0, inside the damped interval.  That is what makes a high filter degree usable: the
+    filter's dynamic range is T_d(t_top) / T_d(t_wanted) with t = 2 lambda / beta - 1, and with the few large outliers of
+    a face covariance (lambda_1 / lambda_256 = 60 on config 4) still in the block anything above degree 8 pushes the
+    rounding-level components along them past the wanted ones (measured: degrees 12 ... 48 never converge).  Once the
+    outliers are locked the top of the active block is within 10 % of beta and the degree is chosen from the range the
+    float64 mantissa allows (`degree` = None: exp(30) of dynamic range, between 8 and 40; an int or a sequence -- last
+    entry repeating -- fixes it per outer iteration).
+
+    Stops when k pairs are locked (|C q - theta q| <= tol * theta_1 each), after max_outer outer iterations, or when the
+    residual stagnates (info["stagnated"]: near-degenerate trailing eigenvalues, e.g. planted factors below the noise
+    floor).  With a process group the dominant cost -- the n x n by n x block covariance products -- is SHARDED: rank r
+    multiplies its contiguous block of rows of C and one all-gather (n x block float64 over NVLink) reassembles the
+    product; every element is computed by the same kernel with the same summation order whoever owns its row, so all
+    ranks hold bit-identical iterates (and the same result as a single GPU).  The block x block work stays replicated.
     Returns (evals [k] descending, evecs [n, k] orthonormal columns, info dict)."""
+    import math
+    import os
+
     import torch
     L = _lib.lib()
     dev = Cm.device
@@ -209,17 +228,33 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=
     stream = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     work = torch.empty(int(L.ef_eigh_work_bytes(m)), dtype=torch.uint8, device=dev)
     f64 = dict(dtype=torch.float64, device=dev)
-
-    gather_buf = torch.empty((world * rows_per, m), **f64) if world > 1 else None
+    method = orth_method or os.environ.get("EF_SUBSPACE_ORTH", "chol")
+    if lock is None:
+        lock = os.environ.get("EF_SUBSPACE_LOCK", "1") != "0"
+    if degree is None and os.environ.get("EF_SUBSPACE_DEGREES"):
+        degree = os.environ["EF_SUBSPACE_DEGREES"]
+    if isinstance(degree, str):
+        degree = [int(v) for v in degree.split(",")]
+    degrees = None if degree is None else ([int(degree)] if isinstance(degree, int) else [int(v) for v in degree])
+    if degrees is None and not lock:
+        degrees = [8]
+    info = {"outer": 0, "products": 0, "product_columns": 0, "block": m, "residual": None, "stagnated": False,
+            "degrees": [], "locked_per_outer": []}
+    gather_bufs = {}
 
     def cprod(alpha, Yin, beta, Yout):
-        """Yout = alpha * C Yin + beta * Yout, rows of C sharded over the group."""
+        """Yout = alpha * C Yin + beta * Yout (any block width), rows of C sharded over the group."""
+        w = int(Yin.shape[1])
+        info["product_columns"] += w
         if world == 1:
-            _dgemm(L, stream, n, m, n, alpha, Cm, n, 1, Yin, m, 1, beta, Yout, m)
+            _dgemm(L, stream, n, w, n, alpha, Cm, n, 1, Yin, w, 1, beta, Yout, w)
             return
         import torch.distributed as dist
         if hi > lo:
-            _dgemm(L, stream, hi - lo, m, n, alpha, Cm[lo:hi], n, 1, Yin, m, 1, beta, Yout[lo:hi], m)
+            _dgemm(L, stream, hi - lo, w, n, alpha, Cm[lo:hi], n, 1, Yin, w, 1, beta, Yout[lo:hi], w)
+        if w not in gather_bufs:
+            gather_bufs[w] = torch.empty((world * rows_per, w), **f64)
+        gather_buf = gather_bufs[w]
         mine = gather_buf[rank * rows_per:(rank + 1) * rows_per]
         mine.zero_()
         mine[:hi - lo].copy_(Yout[lo:hi])
@@ -227,20 +262,45 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=
         Yout.copy_(gather_buf[:n])
         info["allgathers"] = info.get("allgathers", 0) + 1
 
+    Ql = torch.empty((n, 0), **f64)          # locked Ritz vectors (columns) and values
+    thl = torch.empty(0, **f64)
+
+    def project_locked(Y, scale=None, alpha=-1.0):
+        """Y += alpha * Ql diag(scale) Ql^T Y (scale None: the plain projector)."""
+        nl, w = int(Ql.shape[1]), int(Y.shape[1])
+        if nl == 0:
+            return
+        T = torch.empty((nl, w), **f64)
+        _dgemm(L, stream, nl, w, n, 1.0, Ql, 1, nl, Y, w, 1, 0.0, T, w)             # Ql^T Y
+        if scale is not None:
+            T.mul_(scale[:, None])
+        _dgemm(L, stream, n, w, nl, alpha, Ql, nl, 1, T, w, 1, 1.0, Y, w)           # Y += alpha Ql T
+
+    def dprod(alpha, Yin, beta, Yout):
+        """Product with the deflated operator C - Ql diag(thl) Ql^T."""
+        cprod(alpha, Yin, beta, Yout)
+        nl, w = int(Ql.shape[1]), int(Yin.shape[1])
+        if nl:
+            T = torch.empty((nl, w), **f64)
+            _dgemm(L, stream, nl, w, n, 1.0, Ql, 1, nl, Yin, w, 1, 0.0, T, w)
+            T.mul_(thl[:, None])
+            _dgemm(L, stream, n, w, nl, -alpha, Ql, nl, 1, T, w, 1, 1.0, Yout, w)
+
     def orth(Y):
         """Orthonormal basis of span(Y): G = Y^T Y = W^T diag(g) W, Q = Y W^T diag(g^-1/2).  The columns are brought
         to unit norm first: after the filter they are nearly orthogonal Ritz directions whose NORMS span many orders of
         magnitude, and the Gram matrix of the unscaled block would lose the small ones."""
+        w = int(Y.shape[1])
         norms = Y.norm(dim=0)
         Y = (Y / torch.where(norms > 0, norms, torch.ones_like(norms))[None, :]).contiguous()
-        G = torch.empty((m, m), **f64)
-        _dgemm(L, stream, m, m, n, 1.0, Y, 1, m, Y, m, 1, 0.0, G, m)                # Y^T Y
+        G = torch.empty((w, w), **f64)
+        _dgemm(L, stream, w, w, n, 1.0, Y, 1, w, Y, w, 1, 0.0, G, w)                # Y^T Y
         g, W = _jacobi(L, stream, G, work)
         dead = g <= g[0] * 1e-28                                                    # directions lost to rounding
         scale = torch.where(dead, torch.zeros_like(g), g.clamp_min(1e-300).rsqrt())
         Ws = (W * scale[:, None]).contiguous()                                      # row i scaled by g_i^-1/2
-        Q = torch.empty((n, m), **f64)
-        _dgemm(L, stream, n, m, m, 1.0, Y, m, 1, Ws, 1, m, 0.0, Q, m)               # Y Ws^T
+        Q = torch.empty((n, w), **f64)
+        _dgemm(L, stream, n, w, w, 1.0, Y, w, 1, Ws, 1, w, 0.0, Q, w)               # Y Ws^T
         n_dead = int(dead.sum())
         if n_dead:
             # rank loss: fresh random directions keep the block at full rank (zero columns would stay zero for ever);
@@ -248,58 +308,120 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=8, block=None, seed=
             Q[:, dead] = torch.randn((n, n_dead), generator=gen, **f64)
         return Q
 
+    info_dev = torch.zeros(2, dtype=torch.int32, device=dev)
+
+    def orth_chol(Y, slot):
+        """One CholeskyQR pass: unit columns, G = Y^T Y = L L^T, Q = Y L^-T.  The pivot flag stays on the device."""
+        w = int(Y.shape[1])
+        norms = Y.norm(dim=0)
+        Y = (Y / torch.where(norms > 0, norms, torch.ones_like(norms))[None, :]).contiguous()
+        G = torch.empty((w, w), **f64)
+        _dgemm(L, stream, w, w, n, 1.0, Y, 1, w, Y, w, 1, 0.0, G, w)                # Y^T Y
+        Linv = torch.empty((w, w), **f64)
+        check(L.ef_chol_inverse_device(G.data_ptr(), w, Linv.data_ptr(), info_dev[slot:].data_ptr(), stream),
+              "ef_chol_inverse_device")
+        Q = torch.empty((n, w), **f64)
+        _dgemm(L, stream, n, w, w, 1.0, Y, w, 1, Linv, 1, w, 0.0, Q, w)             # Y L^-T
+        return Q
+
     def orth2(Y):
-        """Two passes: the Gram-matrix route squares the condition number, the second pass (like CholQR2) restores
+        """Two passes: the Gram-matrix route squares the condition number, the second pass (CholQR2) restores
         orthonormality to rounding -- one pass leaves ~1e-9, which would floor the Ritz residual above the tolerance."""
+        if method != "jacobi" and int(Y.shape[1]) <= 640:
+            Q = orth_chol(orth_chol(Y, 0), 1)
+            if not bool(info_dev.any()):                # one host read for both passes
+                info["chol_orth"] = info.get("chol_orth", 0) + 1
+                return Q
+            info["chol_breakdowns"] = info.get("chol_breakdowns", 0) + 1
+            info_dev.zero_()
         return orth(orth(Y))
 
     gen = torch.Generator(device=dev)
     gen.manual_seed(seed)
-    info = {"outer": 0, "products": 0, "block": m, "residual": None, "stagnated": False}
     history = []
     Q = orth2(torch.randn((n, m), generator=gen, **f64))
-    Y = torch.empty((n, m), **f64)
     lam = None
+    theta1 = None
     for outer in range(max_outer):
-        cprod(1.0, Q, 0.0, Y)                                                       # Y = C Q
-        H = torch.empty((m, m), **f64)
-        _dgemm(L, stream, m, m, n, 1.0, Q, 1, m, Y, m, 1, 0.0, H, m)                # H = Q^T C Q
+        w = int(Q.shape[1])
+        nl = int(Ql.shape[1])
+        Y = torch.empty((n, w), **f64)
+        dprod(1.0, Q, 0.0, Y)                                                       # Y = C' Q
+        info["products"] += 1
+        H = torch.empty((w, w), **f64)
+        _dgemm(L, stream, w, w, n, 1.0, Q, 1, w, Y, w, 1, 0.0, H, w)                # H = Q^T C' Q
         H = ((H + H.T) * 0.5).contiguous()
         lam, W = _jacobi(L, stream, H, work)
-        Qr = torch.empty((n, m), **f64)
-        Yr = torch.empty((n, m), **f64)
-        _dgemm(L, stream, n, m, m, 1.0, Q, m, 1, W, 1, m, 0.0, Qr, m)               # Ritz vectors Q W^T
-        _dgemm(L, stream, n, m, m, 1.0, Y, m, 1, W, 1, m, 0.0, Yr, m)               # C (Q W^T)
-        res = float((Yr[:, :k] - Qr[:, :k] * lam[None, :k]).norm(dim=0).max() / lam[0].clamp_min(1e-300))
-        info.update(outer=outer + 1, products=info["products"] + 1, residual=res)
+        Qr = torch.empty((n, w), **f64)
+        Yr = torch.empty((n, w), **f64)
+        _dgemm(L, stream, n, w, w, 1.0, Q, w, 1, W, 1, w, 0.0, Qr, w)               # Ritz vectors Q W^T
+        _dgemm(L, stream, n, w, w, 1.0, Y, w, 1, W, 1, w, 0.0, Yr, w)               # C' (Q W^T)
+        if theta1 is None:
+            theta1 = lam[0].clamp_min(1e-300).clone()
+        want = k - nl                                                               # wanted pairs still in the block
+        resid = (Yr[:, :want] - Qr[:, :want] * lam[None, :want]).norm(dim=0) / theta1
+        res = float(resid.max())
+        info.update(outer=outer + 1, residual=res)
         history.append(res)
         Q = Qr
-        if res <= tol or m == n:
+        if res <= tol or w == n - nl:
+            Ql = torch.cat([Ql, Qr[:, :want]], dim=1)
+            thl = torch.cat([thl, lam[:want]])
             break
+        n_lock = 0
+        if lock:
+            # leading run of converged pairs leaves the block
+            ok = (resid <= tol).to(torch.int64)
+            n_lock = int(torch.cumprod(ok, 0).sum())
+            if n_lock:
+                Ql = torch.cat([Ql, Qr[:, :n_lock]], dim=1).contiguous()
+                thl = torch.cat([thl, lam[:n_lock]])
+                Q = Qr[:, n_lock:].contiguous()
+                Yr = Yr[:, n_lock:].contiguous()
+                # the freshly locked directions leave C': C' q = C q - theta (q . q_l) q_l ~ C q for q orthogonal to them
+                lam = lam[n_lock:]
+                w -= n_lock
+                history.clear()
+        info["locked_per_outer"].append(n_lock)
         # stagnation: eigenvalues buried in a flat noise floor (gap << rounding of the products) cannot be resolved any
         # further; their invariant subspace is already captured to the reported residual
         if len(history) >= 10 and res > 0.9 * history[-7]:
             info["stagnated"] = True
+            Ql = torch.cat([Ql, Q[:, :k - int(Ql.shape[1])]], dim=1)
+            thl = torch.cat([thl, lam[:k - int(thl.shape[0])]])
             break
-        # scaled Chebyshev filter of degree `degree`: damps the unwanted interval [0, beta], beta = smallest Ritz value
-        beta, top = float(lam[m - 1]), float(lam[0])
+        # scaled Chebyshev filter: damps the unwanted interval [0, beta], beta = smallest Ritz value of the block
+        beta, top = float(lam[w - 1]), float(lam[0])
         if not (top > beta > 0.0):
             beta = max(beta, 0.0) + 1e-3 * top
+        if degrees is not None:
+            deg = degrees[min(outer, len(degrees) - 1)]
+        else:
+            growth = math.acosh(max(2.0 * top / beta - 1.0, 1.0 + 1e-9))            # ln of the top's gain per degree
+            deg = max(8, min(40, int(30.0 / growth)))
+        info["degrees"].append(deg)
         e = c = 0.5 * beta
         sigma = e / (top - c)
         sigma1 = sigma
         Y1 = Yr.clone()
-        Y1.sub_(Q * c).mul_(sigma1 / e)                                             # (C Q - c Q) sigma1 / e
+        Y1.sub_(Q * c).mul_(sigma1 / e)                                             # (C' Q - c Q) sigma1 / e
         Qp = Q
-        for _ in range(2, degree + 1):
+        for _ in range(2, deg + 1):
             sigma_new = 1.0 / (2.0 / sigma1 - sigma)
             Y2 = (Qp * (-sigma * sigma_new)).contiguous()
             Y2.sub_(Y1 * (2.0 * sigma_new * c / e))
-            cprod(2.0 * sigma_new / e, Y1, 1.0, Y2)
+            dprod(2.0 * sigma_new / e, Y1, 1.0, Y2)
             info["products"] += 1
             Qp, Y1, sigma = Y1, Y2, sigma_new
+        project_locked(Y1)
         Q = orth2(Y1)
-    return lam[:k].clone(), Q[:, :k].contiguous(), info
+        project_locked(Q)                                                           # locked directions out to rounding
+    else:
+        Ql = torch.cat([Ql, Q[:, :k - int(Ql.shape[1])]], dim=1)
+        thl = torch.cat([thl, lam[:k - int(thl.shape[0])]])
+    info["locked"] = int(Ql.shape[1])
+    order = torch.argsort(thl[:k], descending=True, stable=True)                    # locking order is by convergence
+    return thl[:k][order].clone(), Ql[:, :k][:, order].contiguous(), info
 
 
 class _Phases:

@@ -345,6 +345,12 @@ int ef_gram_center_device(const int64_t* G, int32_t n, int32_t side, const int64
 size_t ef_eigh_work_bytes(int32_t n);
 int ef_eigh_jacobi_device(double* A, int32_t n, double* evals, double* evecs, void* work, int32_t max_sweeps,
                           double tol, int32_t* sweeps_used, double* off_norm, ef_stream_t stream);
+/* Cholesky factor and its inverse of a symmetric positive definite matrix (the CholeskyQR orthonormalisation of the
+ * subspace solver that stands in for np.linalg.eigh of a 10 000 x 10 000 covariance, useless/train.py:103):
+ * G [m][m] float64 row-major, lower triangle read, overwritten by L (G = L L^T); Linv [m][m] = L^-1 (lower triangular).
+ * info (device int): 0, or 1 + the column at which a pivot was not positive (G is then partly overwritten, Linv
+ * undefined).  m <= 640; one CTA. */
+int ef_chol_inverse_device(double* G, int32_t m, double* Linv, int32_t* info, ef_stream_t stream);
 /* General strided float64 GEMM: C[m][n] = alpha * sum_k A(m,k) B(k,n) + beta * C[m][n],
  * A(m,k) = A[m*sam + k*sak], B(k,n) = B[k*sbk + n*sbn], C row-major with ldc. */
 int ef_dgemm_device(int32_t M, int32_t N, int32_t K, double alpha, const double* A, int64_t sam, int64_t sak,
