@@ -41,6 +41,31 @@ void set_error_detail(const char* what, cudaError_t e);
     }                                                                     \
   } while (0)
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: one process may drive several GPUs, so the "already
+// raised to N bytes" bookkeeping is kept per device ordinal (one static table per call site / template instantiation).
+#define EF_ENSURE_SMEM(kernel, bytes)                                                                           \
+  do {                                                                                                          \
+    static size_t attr__[64] = {0};                                                                             \
+    int dev__ = 0;                                                                                              \
+    EF_CUDA(cudaGetDevice(&dev__));                                                                             \
+    if (dev__ < 0 || dev__ >= 64) return EF_ERR_UNSUPPORTED;                                                    \
+    if ((size_t)(bytes) > attr__[dev__]) {                                                                      \
+      EF_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));         \
+      attr__[dev__] = (size_t)(bytes);                                                                          \
+    }                                                                                                           \
+  } while (0)
+
+// One-time per-device setup block: `if (EF_FIRST_ON_DEVICE()) { ... }`
+#define EF_FIRST_ON_DEVICE()                                                \
+  ([]() -> bool {                                                           \
+    static bool done__[64] = {false};                                       \
+    int dev__ = 0;                                                          \
+    if (cudaGetDevice(&dev__) != cudaSuccess || dev__ < 0 || dev__ >= 64) return true; \
+    if (done__[dev__]) return false;                                        \
+    done__[dev__] = true;                                                   \
+    return true;                                                            \
+  }())
+
 static inline cudaStream_t as_stream(ef_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 static inline int64_t round_up(int64_t a, int64_t b) { return (a + b - 1) / b * b; }
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

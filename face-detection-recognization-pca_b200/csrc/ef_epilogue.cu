@@ -311,11 +311,8 @@ int launch_fused(EpiArgs& a, cudaStream_t stream) {
   if (rows > n4) rows = n4;
   a.tile_rows = rows;
   const size_t smem = sizeof(double) * ((size_t)KR * QB + (size_t)rows * (KR + 1)) + 64;
-  static size_t attr = 0;
-  if (smem > attr) {   // always: dynamic + ~11 KB of static shared memory crosses the 48 KB default well below 48 KB dynamic
-    EF_CUDA(cudaFuncSetAttribute(fused_epilogue_kernel<METRIC, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  // always: dynamic + ~11 KB of static shared memory crosses the 48 KB default well below 48 KB dynamic
+  EF_ENSURE_SMEM((fused_epilogue_kernel<METRIC, KR>), smem);
   EF_LAUNCH((fused_epilogue_kernel<METRIC, KR>), (unsigned)ef::ceil_div(a.B, QB), kThreads, smem, stream, a);
   return EF_OK;
 }

@@ -536,11 +536,9 @@ int launch_jacobi_cluster(double* A, double* Vt, int n, JacobiCtl* ctl, int max_
   const int wpc = (int)ef::ceil_div(np, jc::kClusterCtas);
   const size_t smem = (size_t)wpc * sizeof(JcMailbox<EPL>) + sizeof(unsigned long long) * (jc::kClusterCtas + 2);
   if (wpc > 10 || smem > 227 * 1024) return EF_ERR_UNSUPPORTED;
-  static bool configured = false;
-  if (!configured) {
+  if (EF_FIRST_ON_DEVICE()) {
     EF_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<EPL>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
     EF_CUDA(cudaFuncSetAttribute(jacobi_cluster_kernel<EPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured = true;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(jc::kClusterCtas);

@@ -297,11 +297,7 @@ size_t smem_bytes(int qt, int kc_total) {
 template <int METRIC, int QPT>
 int launch_q(const MsArgs& a, cudaStream_t stream) {
   const size_t smem = smem_bytes(4 * QPT, a.kc_total);
-  static size_t attr = 0;
-  if (smem > attr) {
-    EF_CUDA(cudaFuncSetAttribute(match_small_kernel<METRIC, QPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  EF_ENSURE_SMEM((match_small_kernel<METRIC, QPT>), smem);
   EF_LAUNCH((match_small_kernel<METRIC, QPT>), (unsigned)ef::ceil_div(a.B, 4 * QPT), kThreads, smem, stream, a);
   return EF_OK;
 }

@@ -21,7 +21,9 @@
 //
 // Replaces cosine_similarity + np.argmax of scan-template-v4.py:274-276 (and the loop of useless/scan.py:121-127) for a
 // gallery far larger than the reference ever held.
+#include <algorithm>
 #include <climits>
+#include <cstdlib>
 #include <cuda_fp16.h>
 #include <math_constants.h>
 
@@ -230,18 +232,34 @@ match_tc_kernel(const MatchTcArgs a) {
               if (i < valid) m0 = fmaxf(m0, __uint_as_float(v[i]));
           }
         } else if (a.pass == 2) {
-          unsigned mask = 0u;
-          float vm = -CUDART_INF_F;
+          // maximum of the group first (four independent chains), threshold tightened with it, and only a group that
+          // reaches the band is looked at entry by entry: in steady state that is ~ln(rows) groups per query
+          float g0 = -CUDART_INF_F, g1 = -CUDART_INF_F, g2 = -CUDART_INF_F, g3 = -CUDART_INF_F;
+          if (valid == 32) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) {
-            const float f = __uint_as_float(v[i]);
-            mask |= (f >= thr ? 1u : 0u) << i;
-            if (valid == 32 || i < valid) vm = fmaxf(vm, f);
+            for (int i = 0; i < 32; i += 4) {
+              g0 = fmaxf(g0, __uint_as_float(v[i]));
+              g1 = fmaxf(g1, __uint_as_float(v[i + 1]));
+              g2 = fmaxf(g2, __uint_as_float(v[i + 2]));
+              g3 = fmaxf(g3, __uint_as_float(v[i + 3]));
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (i < valid) g0 = fmaxf(g0, __uint_as_float(v[i]));
           }
-          if (valid < 32) mask &= (1u << valid) - 1u;
-          if (!live) mask = 0u;
-          // one reservation per warp and column group: the lanes' counts are prefix-summed with shuffles
-          if (__any_sync(0xffffffffu, mask != 0u)) {
+          const float vm = fmaxf(fmaxf(g0, g1), fmaxf(g2, g3));
+          runmax = fmaxf(runmax, vm);
+          thr = fmaxf(thr, runmax - 2.f * kEps);
+          const bool hit = live && vm >= thr;
+          if (__any_sync(0xffffffffu, hit)) {
+            unsigned mask = 0u;
+            if (hit) {
+#pragma unroll
+              for (int i = 0; i < 32; ++i) mask |= (__uint_as_float(v[i]) >= thr ? 1u : 0u) << i;
+              if (valid < 32) mask &= (1u << valid) - 1u;
+            }
+            // one reservation per warp and column group: the lanes' counts are prefix-summed with shuffles
             const int cnt = __popc(mask);
             int incl = cnt;
 #pragma unroll
@@ -254,22 +272,19 @@ match_tc_kernel(const MatchTcArgs a) {
             if (lane == 0) base = atomicAdd(a.counter, (unsigned)total);
             base = __shfl_sync(0xffffffffu, base, 0);
             unsigned slot = base + (unsigned)(incl - cnt);
-            while (mask) {
-              const int i = __ffs(mask) - 1;
-              mask &= mask - 1u;
-              if (slot < a.cap) {
-                a.cand_q[slot] = q;
-                a.cand_j[slot] = j0 + i;
-                a.cand_f[slot] = __uint_as_float(v[i]);
-              } else {
-                a.counter[1] = 1u;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {             // unrolled: v[] stays in registers (no dynamic index)
+              if (mask & (1u << i)) {
+                if (slot < a.cap) {
+                  a.cand_q[slot] = q;
+                  a.cand_j[slot] = j0 + i;
+                  a.cand_f[slot] = __uint_as_float(v[i]);
+                } else {
+                  a.counter[1] = 1u;
+                }
+                ++slot;
               }
-              ++slot;
             }
-          }
-          if (vm > runmax) {
-            runmax = vm;
-            thr = fmaxf(thr, runmax - 2.f * kEps);
           }
         } else {
           unsigned mask = 0u;
@@ -353,6 +368,13 @@ __global__ void match_tc_thr_kernel(const float* __restrict__ cmax, int chunks, 
   thr[q] = q < B ? m - 2.f * kEps : CUDART_INF_F;
 }
 
+// single pass: thr[q] = final maximum (published by every scanning thread) - 2 eps
+__global__ void match_tc_thr_gmax_kernel(const unsigned int* __restrict__ gmax, int b_pad, int B, float* __restrict__ thr) {
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= b_pad) return;
+  thr[q] = q < B ? ord2f(gmax[q]) - 2.f * kEps : CUDART_INF_F;
+}
+
 // query norms with the arithmetic of match_kernel (lane-strided partial sums, xor-shuffle tree)
 __global__ void match_tc_norm_kernel(const double* __restrict__ P, long long ldp, int B, int k, int metric,
                                      double* __restrict__ pn, unsigned long long* __restrict__ best_key,
@@ -383,12 +405,19 @@ __device__ __forceinline__ unsigned long long order_key(double s) {
 // exact float64 score of every candidate, arithmetic of match_kernel: sequential fma over the components
 __global__ void match_tc_rescore_kernel(const double* __restrict__ P, long long ldp, int k, const double* __restrict__ G,
                                         long long ldg, const double* __restrict__ gnorm, const double* __restrict__ pn,
-                                        const int* __restrict__ cand_q, const long long* __restrict__ cand_j,
-                                        const unsigned int* __restrict__ counter, unsigned int cap, int metric,
-                                        double* __restrict__ cand_s, unsigned long long* __restrict__ best_key) {
+                                        int* cand_q, const long long* __restrict__ cand_j,
+                                        const unsigned int* counter, unsigned int cap, int metric,
+                                        double* __restrict__ cand_s, unsigned long long* __restrict__ best_key,
+                                        const float* __restrict__ cand_f, const float* __restrict__ thr,
+                                        unsigned int* kept) {
   const unsigned int total = min(counter[0], cap);
   for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int q = cand_q[e];
+    if (cand_f && cand_f[e] < thr[q]) {              // entered against an earlier, lower maximum: outside the final band
+      cand_q[e] = -1;
+      continue;
+    }
+    if (kept) atomicAdd(kept, 1u);
     const long long j = cand_j[e];
     const double* p = P + (long long)q * ldp;
     const double* g = G + j * ldg;
@@ -413,6 +442,7 @@ __global__ void match_tc_pick_kernel(const int* __restrict__ cand_q, const long 
   const unsigned int total = min(counter[0], cap);
   for (unsigned int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
     const int q = cand_q[e];
+    if (q < 0) continue;                             // pruned
     if (order_key(cand_s[e]) == best_key[q]) atomicMin(reinterpret_cast<unsigned long long*>(best_idx + q),
                                                        (unsigned long long)cand_j[e]);
   }
@@ -432,7 +462,7 @@ __global__ void match_tc_final_kernel(const unsigned long long* __restrict__ bes
 int n_slabs_for(int k) { return (int)ef::ceil_div(3 * (int64_t)k, kSlab); }
 
 struct Layout {
-  size_t cmax, thr, pn, best_key, best_idx, counter, cand_q, cand_j, cand_s, status, total;
+  size_t cmax, thr, gmax, pn, best_key, best_idx, counter, cand_q, cand_j, cand_s, cand_f, status, total;
   int chunks, tiles_per_chunk, b_pad;
   unsigned int cap;
 };
@@ -441,25 +471,37 @@ Layout work_layout(int B, int64_t n, int k) {
   Layout L{};
   const int q_tiles = (int)ef::ceil_div(B, BLOCK_M);
   const int g_tiles = (int)ef::ceil_div(n, BN);
-  int chunks = (int)ef::ceil_div(2 * (int64_t)ef::sm_count(), q_tiles);
+  // gallery chunks per query tile: whole waves of CTAs (one CTA per SM).  32 query tiles x 10 chunks = 320 CTAs were
+  // 2.16 waves on 148 SMs -- the third wave ran 16 % full; the wave count in 2..8 that fills its last wave best wins
+  // (32 x 37 = 1184 = 8 x 148)
+  const int64_t sms = ef::sm_count();
+  int chunks = 1;
+  double best_fill = 0.0;
+  for (int waves = 2; waves <= 8; ++waves) {
+    const int64_t c = std::max<int64_t>(1, (waves * sms) / q_tiles);
+    const double fill = (double)(c * q_tiles) / (double)(ef::ceil_div(c * q_tiles, sms) * sms);
+    if (fill > best_fill + 1e-9) { best_fill = fill; chunks = (int)c; }
+  }
   if (chunks > g_tiles) chunks = g_tiles;
   if (chunks < 1) chunks = 1;
   L.tiles_per_chunk = (int)ef::ceil_div(g_tiles, chunks);
   L.chunks = (int)ef::ceil_div(g_tiles, L.tiles_per_chunk);
   L.b_pad = q_tiles * BLOCK_M;
-  L.cap = (unsigned int)std::max<int64_t>(1 << 16, std::min<int64_t>((int64_t)B * 256, 1 << 26));
+  L.cap = (unsigned int)std::max<int64_t>(1 << 20, std::min<int64_t>((int64_t)B * 512, 1 << 26));
   size_t off = 0;
   auto take = [&](size_t bytes) { const size_t o = off; off += (bytes + 255) & ~(size_t)255; return o; };
   L.status = take(256);
   L.counter = take(256);
   L.cmax = take(sizeof(float) * (size_t)L.chunks * L.b_pad);
   L.thr = take(sizeof(float) * L.b_pad);
+  L.gmax = take(sizeof(unsigned int) * L.b_pad);
   L.pn = take(sizeof(double) * B);
   L.best_key = take(sizeof(unsigned long long) * B);
   L.best_idx = take(sizeof(long long) * B);
   L.cand_q = take(sizeof(int) * (size_t)L.cap);
   L.cand_j = take(sizeof(long long) * (size_t)L.cap);
   L.cand_s = take(sizeof(double) * (size_t)L.cap);
+  L.cand_f = take(sizeof(float) * (size_t)L.cap);
   L.total = off;
   return L;
 }
@@ -514,6 +556,8 @@ int ef_match_tc_device(const double* p, int64_t ldp, int32_t B, int32_t k, const
   a.thr = reinterpret_cast<const float*>(w + L.thr);
   a.cand_q = reinterpret_cast<int*>(w + L.cand_q);
   a.cand_j = reinterpret_cast<long long*>(w + L.cand_j);
+  a.cand_f = reinterpret_cast<float*>(w + L.cand_f);
+  a.gmax = reinterpret_cast<unsigned int*>(w + L.gmax);
   a.counter = reinterpret_cast<unsigned int*>(w + L.counter);
   a.cap = L.cap;
   a.status = reinterpret_cast<int*>(w + L.status);
@@ -521,10 +565,13 @@ int ef_match_tc_device(const double* p, int64_t ldp, int32_t B, int32_t k, const
   a.stages = (int)std::min<size_t>(kMaxStages, ((size_t)ef_tc::kSmemLimit - fixed) / kSlabBytesB);
   if (a.stages < 2) return EF_ERR_UNSUPPORTED;
   const size_t smem = fixed + (size_t)a.stages * kSlabBytesB;
-  static size_t attr = 0;
-  if (smem > attr) {
+  static size_t attr[64] = {0};                      // per device: a second GPU in the same process needs its own call
+  int dev = 0;
+  EF_CUDA(cudaGetDevice(&dev));
+  if (dev < 0 || dev >= 64) return EF_ERR_UNSUPPORTED;
+  if (smem > attr[dev]) {
     EF_CUDA(cudaFuncSetAttribute(match_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
+    attr[dev] = smem;
   }
   const dim3 grid((unsigned)ef::ceil_div(B, BLOCK_M), (unsigned)L.chunks);
   double* pn = reinterpret_cast<double*>(w + L.pn);
@@ -534,15 +581,27 @@ int ef_match_tc_device(const double* p, int64_t ldp, int32_t B, int32_t k, const
 
   EF_LAUNCH(match_tc_norm_kernel, (unsigned)ef::ceil_div((int64_t)B * 32, 256), 256, 0, st, p, (long long)ldp, B, k,
             metric, pn, best_key, best_idx);
-  a.pass = 0;
-  EF_LAUNCH(match_tc_kernel, grid, kThreads, smem, st, a);
-  EF_LAUNCH(match_tc_thr_kernel, (unsigned)ef::ceil_div(L.b_pad, 256), 256, 0, st, a.cmax, L.chunks, L.b_pad, B,
-            reinterpret_cast<float*>(w + L.thr));
-  a.pass = 1;
-  EF_LAUNCH(match_tc_kernel, grid, kThreads, smem, st, a);
   const unsigned rgrid = (unsigned)std::min<int64_t>(4096, ef::ceil_div((int64_t)L.cap, 256));
-  EF_LAUNCH(match_tc_rescore_kernel, rgrid, 256, 0, st, p, (long long)ldp, k, prepared, (long long)ldg, norms, pn,
-            a.cand_q, a.cand_j, a.counter, a.cap, metric, cand_s, best_key);
+  if (getenv("EF_MATCH_TC_TWO_PASS")) {
+    // round-1 schedule (kept for A/B measurements): pass 0 = maxima, pass 1 = rows inside the band
+    a.pass = 0;
+    EF_LAUNCH(match_tc_kernel, grid, kThreads, smem, st, a);
+    EF_LAUNCH(match_tc_thr_kernel, (unsigned)ef::ceil_div(L.b_pad, 256), 256, 0, st, a.cmax, L.chunks, L.b_pad, B,
+              reinterpret_cast<float*>(w + L.thr));
+    a.pass = 1;
+    EF_LAUNCH(match_tc_kernel, grid, kThreads, smem, st, a);
+    EF_LAUNCH(match_tc_rescore_kernel, rgrid, 256, 0, st, p, (long long)ldp, k, prepared, (long long)ldg, norms, pn,
+              a.cand_q, a.cand_j, a.counter, a.cap, metric, cand_s, best_key, (const float*)nullptr,
+              (const float*)nullptr, (unsigned int*)nullptr);
+  } else {
+    EF_CUDA(cudaMemsetAsync(w + L.gmax, 0, sizeof(unsigned int) * L.b_pad, st));
+    a.pass = 2;
+    EF_LAUNCH(match_tc_kernel, grid, kThreads, smem, st, a);
+    EF_LAUNCH(match_tc_thr_gmax_kernel, (unsigned)ef::ceil_div(L.b_pad, 256), 256, 0, st, a.gmax, L.b_pad, B,
+              reinterpret_cast<float*>(w + L.thr));
+    EF_LAUNCH(match_tc_rescore_kernel, rgrid, 256, 0, st, p, (long long)ldp, k, prepared, (long long)ldg, norms, pn,
+              a.cand_q, a.cand_j, a.counter, a.cap, metric, cand_s, best_key, a.cand_f, a.thr, a.counter + 2);
+  }
   EF_LAUNCH(match_tc_pick_kernel, rgrid, 256, 0, st, a.cand_q, a.cand_j, cand_s, a.counter, a.cap, best_key, best_idx);
   EF_LAUNCH(match_tc_final_kernel, (unsigned)ef::ceil_div(B, 256), 256, 0, st, best_key, best_idx, B,
             (long long)index_base, out_score, reinterpret_cast<long long*>(out_index));
@@ -555,10 +614,10 @@ int ef_match_tc_flags(const void* work, int32_t* flags3) {
   if (!work || !flags3) return EF_ERR_INVALID;
   const char* w = reinterpret_cast<const char*>(work);
   const Layout L = work_layout(1, 1, 1);             // status / counter offsets do not depend on the shape
-  unsigned int c[2] = {0, 0};
+  unsigned int c[3] = {0, 0, 0};                     // listed, overflow, kept after the final threshold (single pass)
   EF_CUDA(cudaMemcpy(&flags3[0], w + L.status, sizeof(int32_t), cudaMemcpyDeviceToHost));
   EF_CUDA(cudaMemcpy(c, w + L.counter, sizeof(c), cudaMemcpyDeviceToHost));
-  flags3[1] = (int32_t)std::min<unsigned int>(c[0], 0x7fffffffu);
+  flags3[1] = (int32_t)std::min<unsigned int>(c[2] ? c[2] : c[0], 0x7fffffffu);
   flags3[2] = (int32_t)c[1];
   return EF_OK;
 }

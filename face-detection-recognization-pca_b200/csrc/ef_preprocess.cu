@@ -335,13 +335,11 @@ extern "C" int ef_preprocess(const uint8_t* frames, int64_t frame_stride, int32_
   const size_t tables = sizeof(int) * (4 * (size_t)(dw + dh) + 4);
   // + slack: the downscale path reads (with weight 0) one byte past a staged row and one row past a staged band
   const size_t smem = tables + kStageBytes + 2048;
-  static bool configured = false;
-  if (!configured) {
+  if (EF_FIRST_ON_DEVICE()) {
     EF_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     // four CTAs of 52 KB per SM need the largest shared-memory carve-out (the default heuristic settles for less)
     EF_CUDA(cudaFuncSetAttribute(preprocess_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared));
-    configured = true;
   }
   const int64_t per_sm = std::max<int64_t>(1, std::min<int64_t>(8, (220 * 1024) / (int64_t)(smem + 1024)));
   const int64_t resident = (int64_t)ef::sm_count() * per_sm;

@@ -245,11 +245,7 @@ int launch_dp4a(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, i
                 int ld_acc, cudaStream_t stream) {
   constexpr int BN = 16 * CN;
   const size_t smem = (size_t)kStages * (BM + BN) * LDS_ROW;
-  static bool attr_done = false;
-  if (!attr_done) {
-    EF_CUDA(cudaFuncSetAttribute(project_dp4a_kernel<CN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
-  }
+  EF_ENSURE_SMEM(project_dp4a_kernel<CN>, smem);
   const int mt = (B + BM - 1) / BM, nt = (NC + BN - 1) / BN;
   const int total_k_tiles = (D + BK - 1) / BK;
   int ksplit = (int)ef::ceil_div(2 * (int64_t)ef::sm_count(), (int64_t)mt * nt);

@@ -802,12 +802,7 @@ int launch_cluster(const CUtensorMap& mx, const CUtensorMap& mw, ClusterArgs& a,
   a.off_sh = (int)off;
   const size_t smem = off + sizeof(ClusterShared);
   if (smem > (size_t)kSmemLimit) return EF_ERR_UNSUPPORTED;
-  static size_t attr = 0;
-  if (smem > attr) {
-    EF_CUDA(cudaFuncSetAttribute(recognize_cluster_kernel<METRIC, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    attr = smem;
-  }
+  EF_ENSURE_SMEM((recognize_cluster_kernel<METRIC, KR>), smem);
   static unsigned long long* probe_buf = nullptr;
   const bool probing = getenv("EF_TC_PROBE") != nullptr;
   const int grid_n = m_tiles * kCluster;

@@ -635,12 +635,7 @@ int launch_pipe(const CUtensorMap& mx, const CUtensorMap& mw, PipeArgs& a, int m
   a.off_sh = (int)off;
   const size_t smem = off + sizeof(PipeShared);
   if (smem > (size_t)kSmemLimit) return EF_ERR_UNSUPPORTED;
-  static size_t attr = 0;
-  if (smem > attr) {
-    EF_CUDA(cudaFuncSetAttribute(recognize_pipe_kernel<METRIC, KR>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    attr = smem;
-  }
+  EF_ENSURE_SMEM((recognize_pipe_kernel<METRIC, KR>), smem);
   static unsigned long long* probe_buf = nullptr;
   const bool probing = getenv("EF_TC_PROBE") != nullptr;
   const int grid_n = m_tiles * kCluster;

@@ -402,11 +402,7 @@ int ef_template_match_device(const uint8_t* frame, int64_t ldf, int32_t W, int32
     if (words > max_words) max_words = words;
   }
   const size_t smem = sizeof(uint32_t) * (size_t)max_words;
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    EF_CUDA(cudaFuncSetAttribute(tm_corr_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr = smem;
-  }
+  if (smem > 48 * 1024) EF_ENSURE_SMEM(tm_corr_kernel, smem);
   EF_LAUNCH(tm_row_prefix_kernel, (unsigned)ef::ceil_div(H, 8), 256, 0, st, frame, (long long)ldf, W, H,
             const_cast<long long*>(a.S1), const_cast<unsigned long long*>(a.S2));
   EF_LAUNCH(tm_col_prefix_kernel, (unsigned)ef::ceil_div(W + 1, 32), dim3(32, 32), 0, st, W, H,

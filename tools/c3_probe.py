@@ -34,7 +34,7 @@ for metric in (ef.METRIC_COSINE_SK,):
         s, i = sg.match_local(P)
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
-    flops = 2.0 * 2 * B * n * 384                       # two passes over K = 3k float16 products
+    flops = 2.0 * B * n * 384 * (2 if os.environ.get("EF_MATCH_TC_TWO_PASS") else 1)   # K = 3k float16 products per pass
     print(f"n={n} k={k} B={B}: {ms:.2f} ms per batch = {B / ms * 1e3 / 1e6:.2f} M queries/s; filter {flops / ms / 1e9:.0f} TFLOP/s (f16); "
           f"flags {sg.last_flags}; accuracy vs planted {float((i == truth).double().mean()):.4f}", flush=True)
     # float64 scan on a subsample for the timing comparison and an equality check
