@@ -106,6 +106,9 @@ SIGNATURES = {
     "ef_chol_inverse_device": (C.c_int, [c_void, c_i32, c_void, c_void, c_void]),
     "ef_dgemm_device": (C.c_int, [c_i32, c_i32, c_i32, c_dbl, c_void, c_i64, c_i64, c_void, c_i64, c_i64, c_dbl, c_void,
                                   c_i64, c_void]),
+    "ef_dgemm_tc_work_bytes": (C.c_size_t, [c_i32, c_i32, c_i32]),
+    "ef_dgemm_tc_device": (C.c_int, [c_i32, c_i32, c_i32, c_dbl, c_void, c_i64, c_i64, c_void, c_i64, c_i64, c_dbl, c_void,
+                                     c_i64, c_i32, c_void, c_void]),
     "ef_standardize_u8_device": (C.c_int, [c_void, c_i64, c_i64, c_i32, c_void, c_void, c_void, c_void, c_i64, c_void]),
 }
 

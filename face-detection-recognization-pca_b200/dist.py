@@ -167,7 +167,28 @@ class ShardedGallery:
 
 
 # ------------------------------------------------------------------------------ top-k eigenpairs of a large matrix
-def _dgemm(L, stream, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, Cm, ldc):
+_TC_WORK = {}
+
+
+def _dgemm(L, stream, M, N, K, alpha, A, sam, sak, B, sbk, sbn, beta, Cm, ldc, split=False):
+    """C = alpha A B + beta C (strided views).  FP64 tensor-core kernel (ef_dgemm_tc_device) unless EF_DGEMM_TC=0 or no
+    stride of an operand is 1; split=True lets a small output with a long K use split-K (never for the row-sharded
+    covariance products: their summation order must not depend on how the rows are distributed)."""
+    import os
+    if os.environ.get("EF_DGEMM_TC", "1") != "0" and (sak == 1 or sam == 1) and (sbk == 1 or sbn == 1):
+        splits, work = 1, None
+        tiles = -(-M // 128) * -(-N // 128)
+        if split and tiles < 74 and K >= 1024:
+            import torch
+            splits = max(1, min(K // 256, -(-148 // tiles)))
+            need = int(L.ef_dgemm_tc_work_bytes(M, N, splits))
+            key = (Cm.device.index, )
+            if key not in _TC_WORK or _TC_WORK[key].numel() < need:
+                _TC_WORK[key] = torch.empty(max(need, 1 << 22), dtype=torch.uint8, device=Cm.device)
+            work = _TC_WORK[key].data_ptr()
+        check(L.ef_dgemm_tc_device(M, N, K, float(alpha), A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, float(beta),
+                                   Cm.data_ptr(), ldc, splits, work, stream), "ef_dgemm_tc_device")
+        return
     check(L.ef_dgemm_device(M, N, K, float(alpha), A.data_ptr(), sam, sak, B.data_ptr(), sbk, sbn, float(beta),
                             Cm.data_ptr(), ldc, stream), "ef_dgemm_device")
 
@@ -190,7 +211,7 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=None, block=None, se
     Rayleigh-Ritz and LOCKING (Zhou & Saad's scaled filter).  Replaces np.linalg.eigh(cov) + descending sort + top-k of
     useless/train.py:103-116 for large D.
 
-    Every dense product is ef_dgemm_device, every small eigenproblem (block x block, block <= 320) the cluster-resident
+    Every dense product is ef_dgemm_tc_device (FP64 tensor-core path), every small eigenproblem (block x block, block <= 320) the cluster-resident
     Jacobi kernel, the re-orthonormalisation after a filter application CholeskyQR2 (ef_chol_inverse_device: one CTA,
     ~0.1 ms; the Gram-matrix Jacobi route -- robust against rank loss, 10 ms per pass -- takes over when a pivot is not
     positive); torch only allocates and does O(n block) vector work.
@@ -271,7 +292,7 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=None, block=None, se
         if nl == 0:
             return
         T = torch.empty((nl, w), **f64)
-        _dgemm(L, stream, nl, w, n, 1.0, Ql, 1, nl, Y, w, 1, 0.0, T, w)             # Ql^T Y
+        _dgemm(L, stream, nl, w, n, 1.0, Ql, 1, nl, Y, w, 1, 0.0, T, w, split=True)  # Ql^T Y
         if scale is not None:
             T.mul_(scale[:, None])
         _dgemm(L, stream, n, w, nl, alpha, Ql, nl, 1, T, w, 1, 1.0, Y, w)           # Y += alpha Ql T
@@ -282,7 +303,7 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=None, block=None, se
         nl, w = int(Ql.shape[1]), int(Yin.shape[1])
         if nl:
             T = torch.empty((nl, w), **f64)
-            _dgemm(L, stream, nl, w, n, 1.0, Ql, 1, nl, Yin, w, 1, 0.0, T, w)
+            _dgemm(L, stream, nl, w, n, 1.0, Ql, 1, nl, Yin, w, 1, 0.0, T, w, split=True)
             T.mul_(thl[:, None])
             _dgemm(L, stream, n, w, nl, -alpha, Ql, nl, 1, T, w, 1, 1.0, Yout, w)
 
@@ -294,7 +315,7 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=None, block=None, se
         norms = Y.norm(dim=0)
         Y = (Y / torch.where(norms > 0, norms, torch.ones_like(norms))[None, :]).contiguous()
         G = torch.empty((w, w), **f64)
-        _dgemm(L, stream, w, w, n, 1.0, Y, 1, w, Y, w, 1, 0.0, G, w)                # Y^T Y
+        _dgemm(L, stream, w, w, n, 1.0, Y, 1, w, Y, w, 1, 0.0, G, w, split=True)    # Y^T Y
         g, W = _jacobi(L, stream, G, work)
         dead = g <= g[0] * 1e-28                                                    # directions lost to rounding
         scale = torch.where(dead, torch.zeros_like(g), g.clamp_min(1e-300).rsqrt())
@@ -316,7 +337,7 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=None, block=None, se
         norms = Y.norm(dim=0)
         Y = (Y / torch.where(norms > 0, norms, torch.ones_like(norms))[None, :]).contiguous()
         G = torch.empty((w, w), **f64)
-        _dgemm(L, stream, w, w, n, 1.0, Y, 1, w, Y, w, 1, 0.0, G, w)                # Y^T Y
+        _dgemm(L, stream, w, w, n, 1.0, Y, 1, w, Y, w, 1, 0.0, G, w, split=True)    # Y^T Y
         Linv = torch.empty((w, w), **f64)
         check(L.ef_chol_inverse_device(G.data_ptr(), w, Linv.data_ptr(), info_dev[slot:].data_ptr(), stream),
               "ef_chol_inverse_device")
@@ -349,7 +370,7 @@ def eigh_topk_device(Cm, k, tol=1e-11, max_outer=40, degree=None, block=None, se
         dprod(1.0, Q, 0.0, Y)                                                       # Y = C' Q
         info["products"] += 1
         H = torch.empty((w, w), **f64)
-        _dgemm(L, stream, w, w, n, 1.0, Q, 1, w, Y, w, 1, 0.0, H, w)                # H = Q^T C' Q
+        _dgemm(L, stream, w, w, n, 1.0, Q, 1, w, Y, w, 1, 0.0, H, w, split=True)    # H = Q^T C' Q
         H = ((H + H.T) * 0.5).contiguous()
         lam, W = _jacobi(L, stream, H, work)
         Qr = torch.empty((n, w), **f64)
@@ -512,8 +533,7 @@ def fit_gen1_sharded(X_local, n_total, n_components, group=None, solver="auto", 
     if Nr:
         check(L.ef_standardize_u8_device(X_local.data_ptr(), X_local.stride(0), Nr, D, mean.data_ptr(), None, None,
                                          Z.data_ptr(), D, stream), "center rows")
-        check(L.ef_dgemm_device(Nr, k, D, 1.0, Z.data_ptr(), D, 1, E.data_ptr(), k, 1, 0.0, proj.data_ptr(), k, stream),
-              "project")
+        _dgemm(L, stream, Nr, k, D, 1.0, Z, D, 1, E, k, 1, 0.0, proj, k)
     ph.mark("projection")
     fit_gen1_sharded.last_timings = ph.result()
     return E, mean, proj, evals[:k].clone()

@@ -356,6 +356,14 @@ int ef_chol_inverse_device(double* G, int32_t m, double* Linv, int32_t* info, ef
 int ef_dgemm_device(int32_t M, int32_t N, int32_t K, double alpha, const double* A, int64_t sam, int64_t sak,
                     const double* B, int64_t sbk, int64_t sbn, double beta, double* C, int64_t ldc,
                     ef_stream_t stream);
+/* The same product on the FP64 tensor-core path (mma.sync m8n8k4 f64, 128 x 128 x 16 tiles): one of the two strides of
+ * each operand must be 1.  splits > 1 cuts K into that many ranges whose partial products (work: device scratch of
+ * ef_dgemm_tc_work_bytes(M, N, splits)) are added in ascending order -- for small outputs with a long K.  The
+ * summation order of an output element does not depend on M, N or the tile it falls in. */
+size_t ef_dgemm_tc_work_bytes(int32_t M, int32_t N, int32_t splits);
+int ef_dgemm_tc_device(int32_t M, int32_t N, int32_t K, double alpha, const double* A, int64_t sam, int64_t sak,
+                       const double* B, int64_t sbk, int64_t sbn, double beta, double* C, int64_t ldc, int32_t splits,
+                       void* work, ef_stream_t stream);
 /* Z[n][d] = (X[n][d] - mean[d]) / scale[d] - shift[d]   (scale, shift may be NULL); Z float64 [N][ldz]. */
 int ef_standardize_u8_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, const double* mean,
                              const double* scale, const double* shift, double* Z, int64_t ldz,

@@ -32,6 +32,66 @@ def test_dgemm_strided_layouts():
                 np.testing.assert_allclose(c.cpu().numpy(), 0.5 * A @ B + 2.0 * C0, rtol=1e-12, atol=1e-12)
 
 
+def test_dgemm_tensor_core_layouts_edges_and_split_k():
+    """ef_dgemm_tc_device (mma.sync m8n8k4 f64) against numpy: all four operand layouts, ragged M / N / K, odd leading
+    strides (8-byte copies), split-K with its ordered reduction; sharding the rows of A must not change a single bit."""
+    torch = require_gpu()
+    L = ef._lib.lib()
+    rng = np.random.default_rng(1)
+    for (M, N, K, splits) in ((70, 33, 129, 1), (256, 256, 64, 1), (5, 300, 1000, 4), (1, 1, 1, 1), (320, 320, 4099, 16),
+                              (1000, 130, 17, 1), (129, 257, 3, 1)):
+        A = rng.normal(size=(M, K)); B = rng.normal(size=(K, N)); C0 = rng.normal(size=(M, N))
+        for ta in (False, True):
+            for tb in (False, True):
+                a = torch.from_numpy(np.ascontiguousarray(A.T if ta else A)).cuda()
+                b = torch.from_numpy(np.ascontiguousarray(B.T if tb else B)).cuda()
+                c = torch.from_numpy(C0.copy()).cuda()
+                sam, sak = (1, M) if ta else (K, 1)
+                sbk, sbn = (1, K) if tb else (N, 1)
+                wb = int(L.ef_dgemm_tc_work_bytes(M, N, splits))
+                work = torch.empty(max(wb, 16), dtype=torch.uint8, device="cuda")
+                ef._lib.check(L.ef_dgemm_tc_device(M, N, K, 0.5, a.data_ptr(), sam, sak, b.data_ptr(), sbk, sbn, 2.0,
+                                                   c.data_ptr(), N, splits, work.data_ptr(), _stream(torch)), "dgemm_tc")
+                np.testing.assert_allclose(c.cpu().numpy(), 0.5 * A @ B + 2.0 * C0, rtol=1e-12, atol=1e-11)
+    # rows of A sharded 3 ways: every output element is computed in the same order whoever owns its row
+    M, N, K = 1000, 200, 777
+    a = torch.from_numpy(rng.normal(size=(M, K))).cuda(); b = torch.from_numpy(rng.normal(size=(K, N))).cuda()
+    whole = torch.empty((M, N), dtype=torch.float64, device="cuda")
+    parts = torch.empty((M, N), dtype=torch.float64, device="cuda")
+    ef._lib.check(L.ef_dgemm_tc_device(M, N, K, 1.0, a.data_ptr(), K, 1, b.data_ptr(), N, 1, 0.0, whole.data_ptr(), N, 1, None,
+                                       _stream(torch)), "dgemm_tc")
+    for lo, hi in ((0, 333), (333, 334), (334, 1000)):
+        ef._lib.check(L.ef_dgemm_tc_device(hi - lo, N, K, 1.0, a[lo:hi].data_ptr(), K, 1, b.data_ptr(), N, 1, 0.0,
+                                           parts[lo:hi].data_ptr(), N, 1, None, _stream(torch)), "dgemm_tc")
+    assert torch.equal(whole, parts)
+
+
+def test_cholesky_inverse_kernel():
+    """ef_chol_inverse_device: G = L L^T and L^-1 against numpy, ragged sizes; a non-positive pivot is reported."""
+    torch = require_gpu()
+    L = ef._lib.lib()
+    rng = np.random.default_rng(2)
+    for m in (1, 7, 32, 33, 100, 320, 417):
+        Y = rng.normal(size=(m + 50, m))
+        G = Y.T @ Y
+        g = torch.from_numpy(G.copy()).cuda()
+        linv = torch.empty((m, m), dtype=torch.float64, device="cuda")
+        info = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+        ef._lib.check(L.ef_chol_inverse_device(g.data_ptr(), m, linv.data_ptr(), info.data_ptr(), _stream(torch)), "chol")
+        assert int(info) == 0
+        Lref = np.linalg.cholesky(G)
+        np.testing.assert_allclose(np.tril(g.cpu().numpy()), Lref, rtol=1e-10, atol=1e-10)
+        Li = linv.cpu().numpy()
+        assert np.abs(np.triu(Li, 1)).max() == 0.0
+        np.testing.assert_allclose(Li @ G @ Li.T, np.eye(m), atol=1e-9)
+    bad = np.eye(40); bad[17, 17] = -1.0
+    g = torch.from_numpy(bad).cuda()
+    linv = torch.empty((40, 40), dtype=torch.float64, device="cuda")
+    info = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ef._lib.check(L.ef_chol_inverse_device(g.data_ptr(), 40, linv.data_ptr(), info.data_ptr(), _stream(torch)), "chol")
+    assert int(info) == 18
+
+
 @pytest.mark.parametrize("n", [1, 2, 3, 17, 64, 229, 300])
 def test_jacobi_eigensolver(n):
     torch = require_gpu()
