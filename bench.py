@@ -424,7 +424,7 @@ def run_ours(args, rank, world):
                    "sample": f"{len(times)} batches of {B} crops (same workload) through oracle/gen1.py:recognize_batch "
                              "(batched numpy port of useless/scan.py:recognize_face), all host cores via BLAS",
                    "literal_per_crop_crops_s": cpu_literal_time(model, Q)}
-        path_name = {4: "recognize_stream_kernel: persistent launch over a queue of batches -- TMA + tcgen05 kind::i8 run ahead into double-buffered TMEM accumulators, int64 DSMEM exchange with remote mbarriers; f64 features, tcgen05 f16 filter (gallery rows on M, all scores of a batch in TMEM, one round trip) + exact f64 re-score of batch i overlap the stream of batch i+1",
+        path_name = {4: "recognize_stream_kernel: persistent launch over a queue of batches -- TMA + tcgen05 kind::i8 run ahead into double-buffered TMEM accumulators, int64 DSMEM exchange by st.async with byte-counted mbarriers; f64 features, tcgen05 f16 filter (gallery rows on M, all scores of a batch in TMEM, one round trip) + exact f64 re-score of batch i overlap the stream of batch i+1",
                      3: "recognize_pipe_kernel: stream half (TMA + tcgen05 kind::i8 + DSMEM push + f64 features) of batch i and match half (tcgen05 f16 filter + exact f64 re-score) of batch i-1 in one launch, PDL",
                      2: "recognize_cluster_kernel: TMA + tcgen05 kind::i8 + DSMEM push + tcgen05 f16 filter + exact f64 re-score (1 launch/step, PDL)",
                      1: "project_tc_kernel (tcgen05 kind::i8, stream-K) + fused_epilogue_kernel",
@@ -472,8 +472,10 @@ def run_ours(args, rank, world):
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per step of the serving kernel (ncu --set full; see profiles/)
-TRAFFIC_PER_STEP = {3: 43332864}
-TRAFFIC_SOURCE = {3: "profiles/r1_h_summary.md (ncu --set full, recognize_pipe_kernel<1,12>, bytes per launch)"}
+TRAFFIC_PER_STEP = {3: 43332864, 4: 43664384}
+TRAFFIC_SOURCE = {3: "profiles/r1_h_summary.md (ncu --set full, recognize_pipe_kernel<1,12>, bytes per launch)",
+                  4: "profiles/r2_summary.md (ncu --set full, recognize_stream_kernel<1,12>, 2-batch launch: (84.09 MB read + "
+                     "3.24 MB written) / 2 batches)"}
 
 
 def main():

@@ -51,6 +51,42 @@ def test_row_sharded_fit_world1_matches_oracle():
     np.testing.assert_allclose(proj.cpu().numpy() * sign, proj_ref, atol=1e-6)
 
 
+def test_two_devices_one_process():
+    """One process driving two GPUs: the per-device cudaFuncSetAttribute bookkeeping (EF_ENSURE_SMEM) must give the
+    second device its shared-memory attributes too; the same model on cuda:0 and cuda:1 returns identical results
+    through the serving kernel, the cluster kernel and K1."""
+    torch = require_gpu()
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs in one process")
+    rng = np.random.default_rng(3)
+    D, k, ng, B = 4096, 10, 300, 512
+    E = np.linalg.qr(rng.normal(size=(D, k)))[0]
+    mean = rng.uniform(60, 200, D)
+    gal = rng.normal(size=(ng, k)) * 100
+    x = rng.integers(0, 256, (B, D), dtype=np.uint8)
+    frames = rng.integers(0, 256, (2, 240, 320), dtype=np.uint8)
+    boxes = np.array([[i % 2, 5 + i, 7 + i, 100 + i, 90 + i] for i in range(40)], dtype=np.int32)
+    got = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            rec = ef.Recognizer(E, mean, gal, metric=ef.METRIC_COSINE_G1, labels=np.arange(ng) % 4)
+            xd = torch.from_numpy(x).cuda()
+            one = rec.recognize_device(xd, 0.5)
+            outs = [rec.submit_device(xd, 0.5) for _ in range(3)]
+            rec.flush_device()
+            crops = ef.engine.preprocess_device(torch.from_numpy(frames).cuda(), torch.from_numpy(boxes).cuda(), 64)
+            torch.cuda.synchronize()
+            assert rec.pipeline_timeouts() == 0
+            for o in outs:
+                for f in ("score", "index", "label", "resid2"):
+                    assert torch.equal(o[f], one[f]), f
+            got.append(({f: one[f].cpu() for f in ("score", "index", "label", "resid2")}, crops.cpu()))
+            rec.close()
+    for f in got[0][0]:
+        assert torch.equal(got[0][0][f], got[1][0][f]), f
+    assert torch.equal(got[0][1], got[1][1])
+
+
 def test_nccl_two_ranks_bit_identical():
     torch = require_gpu()
     if torch.cuda.device_count() < 2:
