@@ -71,6 +71,8 @@ SIGNATURES = {
                                                   c_i32, c_i32, c_i32, c_dbl, C.POINTER(Result), c_void]),
     "ef_model_recognize_boxes_host": (C.c_int, [c_void, c_void, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_void,
                                                 c_i32, c_i32, c_i32, c_dbl, C.POINTER(Result)]),
+    "ef_models_recognize_boxes_host": (C.c_int, [c_void, c_i32, c_void, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_void,
+                                                 c_i32, c_i32, c_i32, c_dbl, c_void, c_void, c_void]),
     "ef_model_bad_boxes": (C.c_int, [c_void, c_void, p_i32]),
     "ef_match_work_bytes": (C.c_size_t, [c_i32, c_i64]),
     "ef_gallery_prepare_device": (C.c_int, [c_void, c_i64, c_i64, c_i32, c_i32, c_void, c_i64, c_void, c_void]),

@@ -4,6 +4,7 @@
 // and sklearn cosine_similarity + np.argmax (scan-template-v4.py:274-276).  A small float64 GEMM
 // (32 queries x 128 gallery rows per CTA, k in chunks of 16 through shared memory) with the arg-best reduction
 // fused in the epilogue: scores never touch HBM.
+#include <algorithm>
 #include <climits>
 #include <math_constants.h>
 
@@ -164,6 +165,106 @@ match_kernel(const double* __restrict__ P, int64_t ldp, int B, int k, const doub
   }
 }
 
+// A few queries (the reference's own call pattern is ONE face per call) against a gallery of any size: the tiled kernel
+// above would run one query tile per gallery split through 37 load -> sync -> multiply rounds (110 us for 1 x 590 x 590).
+// Here a thread owns a gallery ROW and streams it once from global memory against all (<= 8) queries held in shared
+// memory -- the same ascending fma chain per (query, row) as match_kernel, so every score is bit identical to it.
+constexpr int FQ = 8;        // queries per call of the few-query kernel
+constexpr int FT = 64;       // gallery rows (threads) per CTA
+
+template <int METRIC>
+__global__ void __launch_bounds__(FT)
+match_few_kernel(const double* __restrict__ P, int64_t ldp, int B, int k, const double* __restrict__ G, int64_t ldg,
+                 const double* __restrict__ gnorm, int64_t n, int64_t index_base, double* __restrict__ out_score,
+                 int64_t* __restrict__ out_index) {
+  extern __shared__ double qs[];                   // [B][k]
+  __shared__ double pnorm[FQ];
+  __shared__ double red_s[FT / 32][FQ];
+  __shared__ long long red_i[FT / 32][FQ];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int qi = warp; qi < B; qi += FT / 32) {
+    double s = 0.0;
+    for (int c = lane; c < k; c += 32) {
+      const double v = P[(int64_t)qi * ldp + c];
+      s += v * v;
+    }
+    s = ef::warp_sum(s);
+    if (lane == 0) {
+      double nrm = sqrt(s);
+      if (METRIC == EF_METRIC_COSINE_SK && nrm == 0.0) nrm = 1.0;
+      pnorm[qi] = nrm;
+    }
+  }
+  __syncthreads();
+  for (int e = tid; e < B * k; e += FT) {
+    const int qi = e / k, c = e - qi * k;
+    double v = P[(int64_t)qi * ldp + c];
+    if (METRIC == EF_METRIC_COSINE_SK) v = v / pnorm[qi];
+    qs[e] = v;
+  }
+  __syncthreads();
+  const int64_t row = (int64_t)blockIdx.x * FT + tid;
+  double acc[FQ];
+#pragma unroll
+  for (int i = 0; i < FQ; ++i) acc[i] = 0.0;
+  if (row < n) {
+    const double* g = G + row * ldg;
+#pragma unroll 4
+    for (int c = 0; c < k; ++c) {
+      const double gv = g[c];
+#pragma unroll
+      for (int i = 0; i < FQ; ++i) {
+        if (i < B) {
+          if (METRIC == EF_METRIC_L2) {
+            const double d = qs[i * k + c] - gv;
+            acc[i] = fma(d, d, acc[i]);
+          } else {
+            acc[i] = fma(qs[i * k + c], gv, acc[i]);
+          }
+        }
+      }
+    }
+  }
+  double gn = 1.0;
+  if (METRIC == EF_METRIC_COSINE_G1 && row < n) gn = gnorm[row];
+#pragma unroll
+  for (int i = 0; i < FQ; ++i) {
+    if (i >= B) break;
+    double s = acc[i];
+    long long idx = row < n ? row : LLONG_MAX;
+    if (row >= n) s = (METRIC == EF_METRIC_L2) ? CUDART_INF : -CUDART_INF;
+    else if (METRIC == EF_METRIC_COSINE_G1) {
+      const double pn = pnorm[i];
+      s = (pn == 0.0 || gn == 0.0) ? 0.0 : s / (pn * gn);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double s2 = __shfl_xor_sync(0xffffffffu, s, o);
+      const long long i2 = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (better<METRIC>(s2, i2, s, idx)) {
+        s = s2;
+        idx = i2;
+      }
+    }
+    if (lane == 0) {
+      red_s[warp][i] = s;
+      red_i[warp][i] = idx;
+    }
+  }
+  __syncthreads();
+  if (tid < B) {
+    double s = red_s[0][tid];
+    long long idx = red_i[0][tid];
+    for (int w = 1; w < FT / 32; ++w)
+      if (better<METRIC>(red_s[w][tid], red_i[w][tid], s, idx)) {
+        s = red_s[w][tid];
+        idx = red_i[w][tid];
+      }
+    out_score[(int64_t)blockIdx.x * B + tid] = s;
+    out_index[(int64_t)blockIdx.x * B + tid] = (idx == LLONG_MAX) ? -1 : idx + index_base;
+  }
+}
+
 template <int METRIC>
 __global__ void match_reduce_kernel(const double* __restrict__ scores, const int64_t* __restrict__ indices, int R,
                                     int B, double* __restrict__ out_score, int64_t* __restrict__ out_index) {
@@ -237,15 +338,30 @@ int gallery_prepare(const double* g, int64_t ldg, int64_t n, int k, int metric, 
   return EF_OK;
 }
 
+static bool few_queries(int B, int k) { return B <= FQ && (size_t)B * k * sizeof(double) <= 48 * 1024; }
+
 size_t match_work_bytes(int B, int64_t n) {
   const int splits = gallery_splits(B, n);
-  return splits > 1 ? (size_t)splits * B * (sizeof(double) + sizeof(int64_t)) : 0;
+  size_t bytes = splits > 1 ? (size_t)splits * B * (sizeof(double) + sizeof(int64_t)) : 0;
+  if (B <= FQ) bytes = std::max(bytes, (size_t)ceil_div(n, FT) * B * (sizeof(double) + sizeof(int64_t)));
+  return bytes;
 }
 
 template <int METRIC>
 static int match_impl(const double* p, int64_t ldp, int B, int k, const double* gp, int64_t ldgp, const double* gnorm,
                       int64_t n, int64_t index_base, double* out_score, int64_t* out_index, void* work,
                       cudaStream_t stream) {
+  if (work && few_queries(B, k) && n > FT) {
+    // one gallery row per thread, per-CTA bests reduced by match_reduce_kernel
+    const int ctas = (int)ceil_div(n, FT);
+    double* ws = reinterpret_cast<double*>(work);
+    int64_t* wi = reinterpret_cast<int64_t*>(ws + (size_t)ctas * B);
+    EF_LAUNCH(match_few_kernel<METRIC>, (unsigned)ctas, FT, sizeof(double) * (size_t)B * k, stream, p, ldp, B, k, gp, ldgp,
+              gnorm, n, index_base, ws, wi);
+    EF_LAUNCH(match_reduce_kernel<METRIC>, (unsigned)ceil_div(B, 256), 256, 0, stream, ws, wi, ctas, B, out_score,
+              out_index);
+    return EF_OK;
+  }
   const int splits = work ? gallery_splits(B, n) : 1;
   const int64_t rows_per_split = round_up(ceil_div(n, splits), GT);
   const int real_splits = (int)ceil_div(n, rows_per_split);

@@ -48,6 +48,7 @@ struct ef_model {
   cudaEvent_t flush_ev = nullptr;
   void* pinned = nullptr;                             // owned page-locked staging for the results of the host path
   size_t pinned_bytes = 0;
+  ef::DevBuf multi_dev;                               // ef_models_recognize_boxes_host: [n_models][n_boxes] results
   cudaStream_t copy_stream = nullptr;                 // owned: chunked H2D of the host path runs ahead of the kernels
   std::vector<cudaEvent_t> chunk_ev;                  // one per in-flight H2D chunk
   // asynchronous host path (ef_model_submit_host / ef_model_wait_host): two batches in flight, each with its own crop
@@ -446,7 +447,11 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
   } else {
     // 3. planes -> float64 features (+ residual); 4. nearest gallery row; 5. threshold + label
     double* proj = out->proj ? out->proj : m->proj.as<double>();
-    const bool small = ef::match_small_supported(B, m->k, m->n_gallery) && !getenv("EF_NO_MATCH_SMALL");
+    bool small = ef::match_small_supported(B, m->k, m->n_gallery) && !getenv("EF_NO_MATCH_SMALL");
+    // A handful of crops against a long gallery (the reference's own call pattern: ONE face per call, k = N = 590): the
+    // one or two CTAs of match_small_kernel would sweep the whole gallery alone (218 us at B = 1, 590 x 590); the split
+    // chain spreads the gallery rows over the SMs instead.
+    if (small && ef::ceil_div(B, 32) * 8 < ef::sm_count() && (int64_t)m->n_gallery * m->k >= 16384) small = false;
     if (m->last_used_tc && part) {
       int splits = 1, ld_part = 0;
       ef::project_tc_split_shape(B, m->D, m->NC, &splits, &ld_part);
@@ -864,6 +869,75 @@ int ef_model_recognize_boxes_host(ef_model_t* m, const uint8_t* frames, int64_t 
     return EF_ERR_INVALID;
   }
   return scatter_results(m, n_boxes, out, m->pinned);
+}
+
+// M3 in one call: every person's model on the same boxes (recognize_face_all_models, scan-template-v4.py:289-319, calls
+// extract_face_features + recognize_face_with_model once per model and per face).  Frames and boxes go up once, K1 runs
+// once, every model's K2 writes its (score, index, label) rows into ONE device block, ONE device->host copy and ONE
+// synchronisation bring everything back: the per-face latency is a handful of launches, not a Python loop of tensors.
+int ef_models_recognize_boxes_host(ef_model_t* const* models, int32_t n_models, const uint8_t* frames,
+                                   int64_t frame_stride, int32_t pitch, int32_t width, int32_t height, int32_t channels,
+                                   int32_t n_frames, const ef_box_t* boxes, int32_t n_boxes, int32_t dw, int32_t dh,
+                                   double threshold, double* score, int32_t* index, int32_t* label) {
+  if (!models || n_models <= 0 || !frames || !boxes || !score || !index || !label || n_boxes < 0 || n_frames <= 0)
+    return EF_ERR_INVALID;
+  if (n_boxes == 0) return EF_OK;
+  ef_model_t* m0 = models[0];
+  for (int i = 0; i < n_models; ++i) {
+    if (!models[i] || (int64_t)dw * dh != models[i]->D) return EF_ERR_INVALID;
+    if (models[i]->pending.B > 0 || !models[i]->queue.empty()) return EF_ERR_INVALID;     // flush the serving queue first
+    EF_TRY(host_reserve(models[i], n_boxes));
+    if (i > 0) EF_CUDA(cudaStreamSynchronize(models[i]->stream));     // its own (normally idle) stream owes us nothing
+  }
+  cudaStream_t st = m0->stream;
+  const size_t nB = (size_t)n_boxes, rows = (size_t)n_models * nB;
+  const size_t frame_bytes = (size_t)frame_stride * n_frames;
+  const size_t block = rows * (sizeof(double) + 2 * sizeof(int32_t)) + 16;
+  EF_TRY(m0->frames_dev.ensure(frame_bytes));
+  EF_TRY(m0->boxes_dev.ensure(sizeof(ef_box_t) * nB));
+  EF_TRY(m0->multi_dev.ensure(block));
+  const size_t status_off = ef::round_up((int64_t)block, 16);
+  EF_TRY(ensure_pinned(&m0->pinned, &m0->pinned_bytes,
+                       std::max(status_off + sizeof(int32_t) * (size_t)n_models, result_block_bytes(m0, nB))));
+  EF_CUDA(cudaMemcpyAsync(m0->frames_dev.p, frames, frame_bytes, cudaMemcpyHostToDevice, st));
+  EF_CUDA(cudaMemcpyAsync(m0->boxes_dev.p, boxes, sizeof(ef_box_t) * nB, cudaMemcpyHostToDevice, st));
+  char* d = m0->multi_dev.as<char>();
+  double* d_score = reinterpret_cast<double*>(d);
+  int32_t* d_index = reinterpret_cast<int32_t*>(d + rows * sizeof(double));
+  int32_t* d_label = d_index + rows;
+  int32_t* d_bad = d_label + rows;                                    // 4-byte aligned tail word
+  EF_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int32_t), st));
+  EF_TRY(ef_preprocess(m0->frames_dev.as<uint8_t>(), frame_stride, pitch, width, height, channels, n_frames,
+                       m0->boxes_dev.as<ef_box_t>(), n_boxes, dw, dh, m0->x_dev.as<uint8_t>(), m0->x_ld, d_bad, st));
+  for (int i = 0; i < n_models; ++i) {
+    ef_result_t dev{};
+    dev.score = d_score + (size_t)i * nB;
+    dev.index = d_index + (size_t)i * nB;
+    dev.label = d_label + (size_t)i * nB;
+    EF_TRY(ef_model_recognize_device(models[i], m0->x_dev.as<uint8_t>(), m0->x_ld, n_boxes, threshold, &dev, st));
+  }
+  EF_CUDA(cudaMemcpyAsync(m0->pinned, d, block, cudaMemcpyDeviceToHost, st));
+  int32_t* h_status = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(m0->pinned) + status_off);
+  for (int i = 0; i < n_models; ++i)                                  // tcgen05 pipeline-timeout flags of the models
+    EF_CUDA(cudaMemcpyAsync(h_status + i, models[i]->status.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+  EF_CUDA(cudaStreamSynchronize(st));
+  const char* h = reinterpret_cast<const char*>(m0->pinned);
+  const int32_t bad = *reinterpret_cast<const int32_t*>(h + rows * (sizeof(double) + 2 * sizeof(int32_t)));
+  if (bad != 0) {
+    char msg[96];
+    snprintf(msg, sizeof(msg), "%d of %d boxes are not inside their frame", bad, n_boxes);
+    ef::set_error_detail(msg, cudaErrorInvalidValue);
+    return EF_ERR_INVALID;
+  }
+  for (int i = 0; i < n_models; ++i)
+    if (h_status[i] != 0) {                                           // a pipeline timed out: never garbage as a result
+      ef::set_error_detail("tcgen05 pipeline timeout (ef_models_recognize_boxes_host)", cudaErrorLaunchTimeout);
+      return EF_ERR_CUDA;
+    }
+  memcpy(score, h, rows * sizeof(double));
+  memcpy(index, h + rows * sizeof(double), rows * sizeof(int32_t));
+  memcpy(label, h + rows * (sizeof(double) + sizeof(int32_t)), rows * sizeof(int32_t));
+  return EF_OK;
 }
 
 }  // extern "C"

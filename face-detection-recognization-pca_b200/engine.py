@@ -306,6 +306,39 @@ class Recognizer:
         return out
 
 
+def recognize_boxes_all_models(recognizers, frames, boxes, side, threshold=0.7):
+    """The same boxes against several models in ONE C-ABI call (ef_models_recognize_boxes_host): frames / boxes as in
+    Recognizer.recognize_boxes.  Returns (score [M, B] float64, index [M, B] int32, label [M, B] int32) as numpy arrays.
+    The single-crop pattern of the reference (recognize_face_all_models, scan-template-v4.py:289-319) costs one upload,
+    K1 once, one download and one synchronisation instead of a round trip per model."""
+    recs = list(recognizers)
+    if not recs:
+        raise ValueError("no models")
+    fr = np.ascontiguousarray(frames)
+    if fr.dtype != np.uint8:
+        raise ValueError("frames must be uint8")
+    if fr.ndim == 2 or (fr.ndim == 3 and fr.shape[2] == 3):
+        fr = fr[None]
+    channels = 3 if fr.ndim == 4 else 1
+    F, H, W = fr.shape[:3]
+    bx = np.asarray(boxes, dtype=np.int32).reshape(-1, np.asarray(boxes).shape[-1])
+    if bx.shape[1] == 4:
+        bx = np.concatenate([np.zeros((len(bx), 1), np.int32), bx], axis=1)
+    bx = np.ascontiguousarray(bx)
+    B, M = len(bx), len(recs)
+    if any(side * side != r.D for r in recs):
+        raise ValueError("side*side must equal every model's dimension")
+    score = np.empty((M, B), dtype=np.float64)
+    index = np.empty((M, B), dtype=np.int32)
+    label = np.empty((M, B), dtype=np.int32)
+    handles = (C.c_void_p * M)(*[r._h for r in recs])
+    L = recs[0]._L
+    check(L.ef_models_recognize_boxes_host(handles, M, _ptr(fr), H * W * channels, W * channels, W, H, channels, F,
+                                           _ptr(bx), B, side, side, float(threshold), _ptr(score), _ptr(index),
+                                           _ptr(label)), "ef_models_recognize_boxes_host")
+    return score, index, label
+
+
 def preprocess_device(frames, boxes, side, out=None, bad=None):
     """K1 alone on torch CUDA tensors: returns uint8 [B, ld] with ld = side*side rounded up to 128.
     bad: optional int32 CUDA tensor [1] that accumulates the number of boxes outside their frame (asynchronous use: the

@@ -415,7 +415,6 @@ class MultiModelFaceScanner:
         """All detections of a frame (or clip) against every loaded model; keeps the best confidence per detection
         with the reference's rules (strict >, first model wins ties, below-threshold name falls back to the model's
         person; scan-template-v4.py:297-319).  boxes None = the whole image is one crop."""
-        import torch
         frames = np.ascontiguousarray(frames)
         if boxes is None:
             h, w = frames.shape[:2]
@@ -426,37 +425,21 @@ class MultiModelFaceScanner:
         best_name = np.array(["unknown"] * B, dtype=object)
         if B == 0:
             return [], [], []
-        # K1 once for all models (every model of the reference uses the same 64 x 64 gray crop, scan-template-v4.py:262):
-        # frames and boxes go up once, the preprocessed crops stay on the device and feed every model's K2
-        if frames.ndim == 2 or (frames.ndim == 3 and frames.shape[2] == 3):
-            frames = frames[None]
-        bx = np.asarray(boxes, dtype=np.int32).reshape(B, -1)
-        if bx.shape[1] == 4:
-            bx = np.concatenate([np.zeros((B, 1), np.int32), bx], axis=1)
-        dev = torch.device("cuda", torch.cuda.current_device())
-        bad = torch.zeros(1, dtype=torch.int32, device=dev)
-        crops = engine.preprocess_device(torch.from_numpy(frames).to(dev), torch.from_numpy(np.ascontiguousarray(bx)).to(dev), 64,
-                                         bad=bad)
-        # every model's K2 is enqueued first (no host synchronisation in between), then ONE device -> host read of all
-        # scores and labels: the reference's per-model loop (scan-template-v4.py:297-314) costs one round trip in total
+        # K1 once for all models (every model of the reference uses the same 64 x 64 gray crop, scan-template-v4.py:262)
+        # and every model's K2 in ONE C-ABI call: frames and boxes go up once, all scores and labels come back with one
+        # copy and one synchronisation -- the reference's per-model loop (scan-template-v4.py:297-314) costs one round trip
         launched = []
         for person_name, info in self.models.items():
             model_data = info['model_data']
             if model_data is None:
                 continue
             try:
-                rec = recognizer_for(model_data)
-                out = rec.recognize_device(crops, threshold, want_residual=False)
-                launched.append((person_name, model_data, rec, out))
+                launched.append((person_name, model_data, recognizer_for(model_data), None))
             except Exception as e:
                 print(f"Error recognizing with model {person_name}: {e}")
         if not launched:
             return best_id.tolist(), best_name.tolist(), best_conf.tolist()
-        scores = torch.stack([o["score"] for _, _, _, o in launched] + [bad.to(torch.float64).expand(B)]).cpu().numpy()
-        labels_all = torch.stack([o["label"] for _, _, _, o in launched]).cpu().numpy()
-        if scores[-1, 0] != 0:
-            raise engine._lib.EigenfacesError(engine._lib.EF_ERR_INVALID, "recognize_faces_all_models",
-                                              f"{int(scores[-1, 0])} of {B} boxes are not inside their frame")
+        scores, _, labels_all = engine.recognize_boxes_all_models([r for _, _, r, _ in launched], frames, boxes, 64, threshold)
         for i, (person_name, model_data, rec, _) in enumerate(launched):
             score, label = scores[i], labels_all[i]
             names = _names_for(label, model_data)

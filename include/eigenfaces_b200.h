@@ -187,6 +187,15 @@ int ef_model_recognize_boxes_host(ef_model_t* model, const uint8_t* frames, int6
                                   int32_t width, int32_t height, int32_t channels, int32_t n_frames,
                                   const ef_box_t* boxes, int32_t n_boxes, int32_t dw, int32_t dh,
                                   double threshold, const ef_result_t* out);
+/* recognize_face_all_models (scan-template-v4.py:289-319) in ONE call: the same boxes against every model of `models`
+ * (all with D = dw * dh).  Frames and boxes are uploaded once, K1 runs once, one device->host copy and one
+ * synchronisation return score / index / label as [n_models][n_boxes] row-major host arrays (label = -1 below the
+ * threshold).  The keep-the-best / name fallback rules of the reference stay with the caller (they need the pickles'
+ * person_id_map).  Uses models[0]'s stream and staging; no model may have batches queued on its serving queue. */
+int ef_models_recognize_boxes_host(ef_model_t* const* models, int32_t n_models, const uint8_t* frames,
+                                   int64_t frame_stride, int32_t pitch, int32_t width, int32_t height, int32_t channels,
+                                   int32_t n_frames, const ef_box_t* boxes, int32_t n_boxes, int32_t dw, int32_t dh,
+                                   double threshold, double* score, int32_t* index, int32_t* label);
 
 int ef_model_bad_boxes(ef_model_t* model, ef_stream_t stream, int32_t* count);
 
