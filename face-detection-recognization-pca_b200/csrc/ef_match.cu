@@ -166,50 +166,61 @@ match_kernel(const double* __restrict__ P, int64_t ldp, int B, int k, const doub
 }
 
 // A few queries (the reference's own call pattern is ONE face per call) against a gallery of any size: the tiled kernel
-// above would run one query tile per gallery split through 37 load -> sync -> multiply rounds (110 us for 1 x 590 x 590).
-// Here a thread owns a gallery ROW and streams it once from global memory against all (<= 8) queries held in shared
-// memory -- the same ascending fma chain per (query, row) as match_kernel, so every score is bit identical to it.
+// above would run one query tile per gallery split through 37 load -> sync -> multiply rounds (110 us for 1 x 590 x 590),
+// and so does any thread that walks its gallery row straight from global memory (every load its own cache line, 19
+// warps on the whole GPU: 3 us per 16 elements).  Here a warp first pulls its 16 / 32 gallery rows WHOLE into shared
+// memory with coalesced cp.async (all of the tile in flight at once: one memory latency), then lane r runs the same
+// ascending fma chain per (query, row) as match_kernel over its row -- every score is bit identical to it.
 constexpr int FQ = 8;        // queries per call of the few-query kernel
-constexpr int FT = 64;       // gallery rows (threads) per CTA
 
 template <int METRIC>
-__global__ void __launch_bounds__(FT)
+__global__ void __launch_bounds__(32)
 match_few_kernel(const double* __restrict__ P, int64_t ldp, int B, int k, const double* __restrict__ G, int64_t ldg,
-                 const double* __restrict__ gnorm, int64_t n, int64_t index_base, double* __restrict__ out_score,
-                 int64_t* __restrict__ out_index) {
-  extern __shared__ double qs[];                   // [B][k]
+                 const double* __restrict__ gnorm, int64_t n, int64_t index_base, int rows_per_cta,
+                 double* __restrict__ out_score, int64_t* __restrict__ out_index) {
+  extern __shared__ double fsm[];
+  double* qs = fsm;                                // [B][k] queries (divided by their norm for the sklearn metric)
+  const int kp = k | 1;                            // odd row pitch: lanes reading one column of 32 rows hit 32 banks
+  double* tile = fsm + (size_t)B * k;              // [rows_per_cta][kp]
   __shared__ double pnorm[FQ];
-  __shared__ double red_s[FT / 32][FQ];
-  __shared__ long long red_i[FT / 32][FQ];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int qi = warp; qi < B; qi += FT / 32) {
+  const int lane = threadIdx.x;
+  const int64_t row0 = (int64_t)blockIdx.x * rows_per_cta;
+  const int rows = (int)min((int64_t)rows_per_cta, n - row0);
+  // gallery rows -> shared memory, element by element (8-byte copies: any ld, any alignment), coalesced along a row
+  {
+    const unsigned t0 = (unsigned)__cvta_generic_to_shared(tile);
+    for (int r = 0; r < rows; ++r) {
+      const double* g = G + (row0 + r) * ldg;
+      for (int c = lane; c < k; c += 32)
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(t0 + 8u * (unsigned)(r * kp + c)), "l"(g + c));
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+  for (int qi = 0; qi < B; ++qi) {                 // norms with match_kernel's arithmetic (lane-strided sums, xor tree)
     double s = 0.0;
     for (int c = lane; c < k; c += 32) {
       const double v = P[(int64_t)qi * ldp + c];
       s += v * v;
     }
     s = ef::warp_sum(s);
-    if (lane == 0) {
-      double nrm = sqrt(s);
-      if (METRIC == EF_METRIC_COSINE_SK && nrm == 0.0) nrm = 1.0;
-      pnorm[qi] = nrm;
+    double nrm = sqrt(s);
+    if (METRIC == EF_METRIC_COSINE_SK && nrm == 0.0) nrm = 1.0;
+    if (lane == 0) pnorm[qi] = nrm;
+    for (int c = lane; c < k; c += 32) {
+      double v = P[(int64_t)qi * ldp + c];
+      if (METRIC == EF_METRIC_COSINE_SK) v = v / nrm;
+      qs[qi * k + c] = v;
     }
   }
-  __syncthreads();
-  for (int e = tid; e < B * k; e += FT) {
-    const int qi = e / k, c = e - qi * k;
-    double v = P[(int64_t)qi * ldp + c];
-    if (METRIC == EF_METRIC_COSINE_SK) v = v / pnorm[qi];
-    qs[e] = v;
-  }
-  __syncthreads();
-  const int64_t row = (int64_t)blockIdx.x * FT + tid;
+  asm volatile("cp.async.wait_group 0;\n" ::);
+  __syncwarp();
+  const bool live = lane < rows;
+  const int64_t row = row0 + lane;
   double acc[FQ];
 #pragma unroll
   for (int i = 0; i < FQ; ++i) acc[i] = 0.0;
-  if (row < n) {
-    const double* g = G + row * ldg;
-#pragma unroll 4
+  if (live) {
+    const double* g = tile + (size_t)lane * kp;
     for (int c = 0; c < k; ++c) {
       const double gv = g[c];
 #pragma unroll
@@ -226,13 +237,13 @@ match_few_kernel(const double* __restrict__ P, int64_t ldp, int B, int k, const 
     }
   }
   double gn = 1.0;
-  if (METRIC == EF_METRIC_COSINE_G1 && row < n) gn = gnorm[row];
+  if (METRIC == EF_METRIC_COSINE_G1 && live) gn = gnorm[row];
 #pragma unroll
   for (int i = 0; i < FQ; ++i) {
     if (i >= B) break;
     double s = acc[i];
-    long long idx = row < n ? row : LLONG_MAX;
-    if (row >= n) s = (METRIC == EF_METRIC_L2) ? CUDART_INF : -CUDART_INF;
+    long long idx = live ? row : LLONG_MAX;
+    if (!live) s = (METRIC == EF_METRIC_L2) ? CUDART_INF : -CUDART_INF;
     else if (METRIC == EF_METRIC_COSINE_G1) {
       const double pn = pnorm[i];
       s = (pn == 0.0 || gn == 0.0) ? 0.0 : s / (pn * gn);
@@ -247,21 +258,9 @@ match_few_kernel(const double* __restrict__ P, int64_t ldp, int B, int k, const 
       }
     }
     if (lane == 0) {
-      red_s[warp][i] = s;
-      red_i[warp][i] = idx;
+      out_score[(int64_t)blockIdx.x * B + i] = s;
+      out_index[(int64_t)blockIdx.x * B + i] = (idx == LLONG_MAX) ? -1 : idx + index_base;
     }
-  }
-  __syncthreads();
-  if (tid < B) {
-    double s = red_s[0][tid];
-    long long idx = red_i[0][tid];
-    for (int w = 1; w < FT / 32; ++w)
-      if (better<METRIC>(red_s[w][tid], red_i[w][tid], s, idx)) {
-        s = red_s[w][tid];
-        idx = red_i[w][tid];
-      }
-    out_score[(int64_t)blockIdx.x * B + tid] = s;
-    out_index[(int64_t)blockIdx.x * B + tid] = (idx == LLONG_MAX) ? -1 : idx + index_base;
   }
 }
 
@@ -338,12 +337,19 @@ int gallery_prepare(const double* g, int64_t ldg, int64_t n, int k, int metric, 
   return EF_OK;
 }
 
-static bool few_queries(int B, int k) { return B <= FQ && (size_t)B * k * sizeof(double) <= 48 * 1024; }
+// few-query kernel: rows per CTA so that the tile + the queries fit shared memory (k <= 1024: 16 rows, k <= 448: 32)
+static int few_rows(int B, int k) {
+  const size_t q = sizeof(double) * (size_t)B * k;
+  for (int rows : {32, 16, 8})
+    if (q + sizeof(double) * (size_t)rows * (k | 1) <= 200 * 1024) return rows;
+  return 0;
+}
+static bool few_queries(int B, int k) { return B <= FQ && few_rows(B, k) > 0; }
 
 size_t match_work_bytes(int B, int64_t n) {
   const int splits = gallery_splits(B, n);
   size_t bytes = splits > 1 ? (size_t)splits * B * (sizeof(double) + sizeof(int64_t)) : 0;
-  if (B <= FQ) bytes = std::max(bytes, (size_t)ceil_div(n, FT) * B * (sizeof(double) + sizeof(int64_t)));
+  if (B <= FQ) bytes = std::max(bytes, (size_t)ceil_div(n, 8) * B * (sizeof(double) + sizeof(int64_t)));
   return bytes;
 }
 
@@ -351,13 +357,16 @@ template <int METRIC>
 static int match_impl(const double* p, int64_t ldp, int B, int k, const double* gp, int64_t ldgp, const double* gnorm,
                       int64_t n, int64_t index_base, double* out_score, int64_t* out_index, void* work,
                       cudaStream_t stream) {
-  if (work && few_queries(B, k) && n > FT) {
-    // one gallery row per thread, per-CTA bests reduced by match_reduce_kernel
-    const int ctas = (int)ceil_div(n, FT);
+  if (work && few_queries(B, k) && n > 32) {
+    // 8 / 16 / 32 gallery rows per one-warp CTA, per-CTA bests reduced by match_reduce_kernel
+    const int rows = few_rows(B, k);
+    const int ctas = (int)ceil_div(n, rows);
+    const size_t smem = sizeof(double) * ((size_t)B * k + (size_t)rows * (k | 1));
     double* ws = reinterpret_cast<double*>(work);
     int64_t* wi = reinterpret_cast<int64_t*>(ws + (size_t)ctas * B);
-    EF_LAUNCH(match_few_kernel<METRIC>, (unsigned)ctas, FT, sizeof(double) * (size_t)B * k, stream, p, ldp, B, k, gp, ldgp,
-              gnorm, n, index_base, ws, wi);
+    EF_ENSURE_SMEM(match_few_kernel<METRIC>, smem);
+    EF_LAUNCH(match_few_kernel<METRIC>, (unsigned)ctas, 32, smem, stream, p, ldp, B, k, gp, ldgp, gnorm, n, index_base, rows,
+              ws, wi);
     EF_LAUNCH(match_reduce_kernel<METRIC>, (unsigned)ceil_div(B, 256), 256, 0, stream, ws, wi, ctas, B, out_score,
               out_index);
     return EF_OK;
