@@ -10,6 +10,8 @@
 //
 // Blackwell mapping (sm_100a):
 //   * both operands are tiles of the SAME matrix, staged by TMA (SWIZZLE_128B) into a 4-stage shared-memory ring;
+//     X X^T takes K-major tiles (a vector per row); X^T X takes the SAME row-major X as MN-major operands (TMA boxes
+//     of 128 samples x 128 pixel bytes, UMMA descriptors with the transpose bits set) -- no transposed copy of X;
 //     tcgen05.mma kind::i8 multiplies u8 x u8 into s32 TMEM accumulators, tile 128 x 256 (UMMA M = 128, N = 256);
 //   * an s32 accumulator holds at most 256 K blocks (32768 x 255^2 < 2^31): longer K runs are cut into segments, each
 //     flushed into the int64 result;
@@ -21,6 +23,8 @@
 //     atomics (bit reproducible, integer addition is associative);
 //   * the epilogue transposes each 32 x 32 block through shared memory so that a warp writes 256 contiguous bytes.
 #include <cuda.h>
+
+#include <cstdlib>
 
 #include "ef_common.cuh"
 #include "ef_internal.cuh"
@@ -37,6 +41,7 @@ constexpr int kAccStages = 2;
 struct GramArgs {
   int n, kb_total, block_n, m_tiles, n_tiles, stages, whole, tmem_cols;
   int overwrite;                       // G = A A^T instead of +=: the first K segment of a tile stores (both triangles)
+  int mn_major;                        // operand = X [K samples][n pixels] as it lies in memory (MN-major UMMA operands)
   long long tiles;                     // tiles touching the upper triangle
   unsigned long long* G;
   long long ldg;
@@ -55,6 +60,19 @@ struct GramShared {
 // Instruction descriptor: D = s32, A = u8, B = u8, both K-major, M = 128, N = n.
 __host__ __device__ constexpr uint32_t umma_idesc_u8u8(int n) {
   return (2u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
+}
+
+// MN-major SWIZZLE_128B operand (the pixel axis contiguous, as X lies in memory): a TMA box of 128 samples x 128 pixel
+// bytes is 16 swizzle atoms of (8 samples x 128 pixels), 1024 bytes apart along K (stride byte offset); a second block of
+// 128 pixels (N = 256) starts `lbo` bytes further (leading byte offset).
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
 }
 
 // Upper-triangle tiles in column-block-major order: column block tj holds row tiles 0 .. min(m_tiles, w tj + w) - 1
@@ -167,8 +185,16 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         for (int kb = kb0; kb < kb1; ++kb) {
           if (!mbar_wait(&sh->empty_bar[stage], phase ^ 1, failed)) { ok = false; break; }
           mbar_arrive_expect_tx(&sh->full_bar[stage], stage_bytes);
-          tma_load_2d(sA + (size_t)stage * A_STAGE_BYTES, &tmap_a, &sh->full_bar[stage], kb * BLOCK_K, ti * BLOCK_M);
-          tma_load_2d(sB + (size_t)stage * b_stage_bytes, &tmap_b, &sh->full_bar[stage], kb * BLOCK_K, tj * a.block_n);
+          if (a.mn_major) {
+            // boxes of 128 samples x 128 pixel bytes straight from X: no transposed copy
+            tma_load_2d(sA + (size_t)stage * A_STAGE_BYTES, &tmap_a, &sh->full_bar[stage], ti * BLOCK_M, kb * BLOCK_K);
+            for (int h = 0; h < a.block_n / BLOCK_M; ++h)
+              tma_load_2d(sB + (size_t)stage * b_stage_bytes + (size_t)h * A_STAGE_BYTES, &tmap_a, &sh->full_bar[stage],
+                          tj * a.block_n + h * BLOCK_M, kb * BLOCK_K);
+          } else {
+            tma_load_2d(sA + (size_t)stage * A_STAGE_BYTES, &tmap_a, &sh->full_bar[stage], kb * BLOCK_K, ti * BLOCK_M);
+            tma_load_2d(sB + (size_t)stage * b_stage_bytes, &tmap_b, &sh->full_bar[stage], kb * BLOCK_K, tj * a.block_n);
+          }
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -179,7 +205,7 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       uint32_t seg = 0;
-      const uint32_t idesc = umma_idesc_u8u8(a.block_n);
+      const uint32_t idesc = umma_idesc_u8u8(a.block_n) | (a.mn_major ? ((1u << 15) | (1u << 16)) : 0u);
       SegIter it(a);
       long long tile;
       int kb0, kb1;
@@ -194,10 +220,18 @@ gram_tc_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           tc_fence_after();
           const uint32_t a_addr = smem_u32(sA + (size_t)stage * A_STAGE_BYTES);
           const uint32_t b_addr = smem_u32(sB + (size_t)stage * b_stage_bytes);
+          if (a.mn_major) {
+            // K advances by 32 samples = 32 rows of 128 bytes per MMA
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
-            umma_i8(d_addr, umma_desc_sw128(a_addr + k * UMMA_K), umma_desc_sw128(b_addr + k * UMMA_K), idesc,
-                    (kb > kb0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_i8(d_addr, umma_desc_sw128_mn(a_addr + k * UMMA_K * 128, A_STAGE_BYTES),
+                      umma_desc_sw128_mn(b_addr + k * UMMA_K * 128, A_STAGE_BYTES), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_i8(d_addr, umma_desc_sw128(a_addr + k * UMMA_K), umma_desc_sw128(b_addr + k * UMMA_K), idesc,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
+          }
           umma_commit(&sh->empty_bar[stage]);
           if (++stage == a.stages) { stage = 0; phase ^= 1; }
         }
@@ -339,8 +373,9 @@ using namespace ef_tc;
 // G[n][ldg] (int64) += A A^T restricted to the upper triangle, then mirrored.  A: uint8 [n][lda] K-major with K valid
 // bytes per row.  EF_ERR_UNSUPPORTED when the TMA alignment rules are not met.
 int gram_tc(const uint8_t* A, int64_t lda, int64_t n, int64_t K, int64_t* G, int64_t ldg, int* status,
-            cudaStream_t stream, bool overwrite) {
+            cudaStream_t stream, bool overwrite, bool mn_major) {
   if (n <= 0 || K <= 0) return EF_OK;
+  if (mn_major && n < 256) return EF_ERR_UNSUPPORTED;      // MN-major tiles are whole 128-pixel blocks (block_n = 256)
   if ((lda & 15) || (reinterpret_cast<uintptr_t>(A) & 15) || n > (1 << 20) || K > (1ll << 31) - 256)
     return EF_ERR_UNSUPPORTED;
   if (!encode_fn()) return EF_ERR_UNSUPPORTED;
@@ -365,6 +400,7 @@ int gram_tc(const uint8_t* A, int64_t lda, int64_t n, int64_t K, int64_t* G, int
   const int sms = sm_count();
   a.whole = tiles >= 2ll * sms ? 1 : 0;
   a.overwrite = overwrite ? 1 : 0;
+  a.mn_major = mn_major ? 1 : 0;
   if (overwrite && !a.whole) {
     // stream-K (small n) accumulates partial tiles with atomics: a fresh result starts from zero
     EF_CUDA(cudaMemsetAsync(G, 0, sizeof(int64_t) * (size_t)n * (size_t)ldg, stream));
@@ -382,14 +418,16 @@ int gram_tc(const uint8_t* A, int64_t lda, int64_t n, int64_t K, int64_t* G, int
     grid = (int)std::max<long long>(1, std::min<long long>(sms, units / 8));
   }
   CUtensorMap ma, mb;
-  if (!make_map(&ma, A, (uint64_t)K, (uint64_t)n, (uint64_t)lda, BLOCK_M)) return EF_ERR_UNSUPPORTED;
-  if (!make_map(&mb, A, (uint64_t)K, (uint64_t)n, (uint64_t)lda, (uint32_t)a.block_n)) return EF_ERR_UNSUPPORTED;
-  const size_t smem = (size_t)a.stages * stage_bytes + fixed;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    EF_CUDA(cudaFuncSetAttribute(gram_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
+  if (mn_major) {
+    // A = X [K samples][lda], n pixels per row: one map, boxes of 128 pixel bytes x 128 samples
+    if (!make_map(&ma, A, (uint64_t)n, (uint64_t)K, (uint64_t)lda, BLOCK_K)) return EF_ERR_UNSUPPORTED;
+    mb = ma;
+  } else {
+    if (!make_map(&ma, A, (uint64_t)K, (uint64_t)n, (uint64_t)lda, BLOCK_M)) return EF_ERR_UNSUPPORTED;
+    if (!make_map(&mb, A, (uint64_t)K, (uint64_t)n, (uint64_t)lda, (uint32_t)a.block_n)) return EF_ERR_UNSUPPORTED;
   }
+  const size_t smem = (size_t)a.stages * stage_bytes + fixed;
+  EF_ENSURE_SMEM(gram_tc_kernel, smem);
   EF_LAUNCH(gram_tc_kernel, grid, kThreads, smem, stream, ma, mb, a);
   if (a.overwrite && a.kb_total <= kSegKb) return EF_OK;      // every tile had ONE segment: both triangles are written
   dim3 mg((unsigned)ceil_div(n, 32), (unsigned)ceil_div(n, 32));
@@ -431,13 +469,20 @@ static int gram_u8_tc_impl(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, 
   }
   if (side == 0) {
     if (d0 & 15) return EF_ERR_UNSUPPORTED;
-    return ef::gram_tc(X + d0, ldx, N, d1 - d0, G, N, status, st, overwrite);
+    return ef::gram_tc(X + d0, ldx, N, d1 - d0, G, N, status, st, overwrite, false);
   }
   if (d0 != 0 || d1 != D) return EF_ERR_UNSUPPORTED;
+  // X^T X straight from the row-major X: the pixel axis is the contiguous one, i.e. MN-major UMMA operands (TMA boxes of
+  // 128 samples x 128 pixel bytes).  The transposed copy (one more pass over X) is only the fallback for D < 256 or an
+  // unaligned X.
+  if (D >= 256 && (ldx & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && !getenv("EF_GRAM_TRANSPOSE")) {
+    const int rc = ef::gram_tc(X, ldx, D, N, G, D, status, st, overwrite, true);
+    if (rc != EF_ERR_UNSUPPORTED) return rc;
+  }
   uint8_t* XT = reinterpret_cast<uint8_t*>(work) + 256;
   const int64_t ldt = ef::round_up(N, 128);
   EF_TRY(ef::transpose_u8(X, ldx, N, D, XT, ldt, st));
-  return ef::gram_tc(XT, ldt, D, N, G, D, status, st, overwrite);
+  return ef::gram_tc(XT, ldt, D, N, G, D, status, st, overwrite, false);
 }
 
 int ef_gram_u8_tc_device(const uint8_t* X, int64_t ldx, int64_t N, int32_t D, int32_t d0, int32_t d1, int32_t side,

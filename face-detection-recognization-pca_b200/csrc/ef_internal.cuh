@@ -136,8 +136,9 @@ int match_small(const double* proj, int64_t ldp, int B, int k, const double* gp,
 
 // ef_gram_tc.cu -- exact integer Gram A A^T of uint8 rows on tensor cores (upper triangle + mirror), G int64 += .
 // overwrite: G = A A^T (previous content ignored; no read of G, both triangles written by the tile epilogues)
+// mn_major: A is X [K][lda] with the n outputs' axis contiguous (no transposed copy; n >= 256)
 int gram_tc(const uint8_t* A, int64_t lda, int64_t n, int64_t K, int64_t* G, int64_t ldg, int* status,
-            cudaStream_t stream, bool overwrite = false);
+            cudaStream_t stream, bool overwrite = false, bool mn_major = false);
 int transpose_u8(const uint8_t* in, int64_t ldi, int64_t rows, int cols, uint8_t* out, int64_t ldo, cudaStream_t stream);
 
 }  // namespace ef

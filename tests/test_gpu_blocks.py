@@ -203,6 +203,9 @@ def _gram_tc(torch, L, x, N, D, side, G, d0=0, d1=None):
     (1, 16, 0), (5, 33, 1), (130, 257, 0), (300, 4096, 1),      # ragged tiles, K tails, n = 1
     (64, 70000, 0),       # K > 32768: s32 segments flushed into int64
     (40, 5000, 1),        # D x D = 5000 x 5000: whole-tile schedule (>= 2 tiles per SM), exclusive read-add-write
+    (1000, 640, 1),       # MN-major operands straight from X: several K stages, ragged pixel blocks (640 = 2.5 x 256)
+    (40000, 512, 1),      # MN-major, K = 40000 samples > 32768: two s32 segments per tile
+    (700, 200, 1),        # D < 256: the transposed-copy fallback
 ])
 def test_tensor_core_gram_is_exact(N, D, side):
     """tcgen05 kind::i8 SYRK == numpy int64 X X^T / X^T X, bit for bit, including the += contract."""
@@ -215,9 +218,10 @@ def test_tensor_core_gram_is_exact(N, D, side):
     if N >= 64 and side == 0:
         Xp[3, :D] = 255                                  # worst case magnitude on a full row
     x = torch.from_numpy(Xp).cuda()[:, :D]
-    Xi = Xp[:, :D].astype(np.int64)
+    # reference through float64 BLAS: every sum is < 255^2 * 70 000 < 2^53, so the float64 product is the exact integer
+    Xi = Xp[:, :D].astype(np.float64)
     n = N if side == 0 else D
-    want = Xi @ Xi.T if side == 0 else Xi.T @ Xi
+    want = (Xi @ Xi.T if side == 0 else Xi.T @ Xi).astype(np.int64)
     G = torch.zeros((n, n), dtype=torch.int64, device="cuda")
     _gram_tc(torch, L, x, N, D, side, G)
     assert np.array_equal(G.cpu().numpy(), want)
