@@ -128,7 +128,7 @@ def gram_section(ef, torch, dev, peaks):
     algorithmic = 2.0 * Dg * Dg * N / 2.0
     bf16_peak = peaks.get("bf16_tflops", 1590.0)
     i8_peak = int8_peak_probe(torch, dev)
-    out = {"what": f"ef_gram_u8_tc_store_device side 1: X^T X of u8[{N},{Dg}] -> int64[{Dg},{Dg}] (transpose + tcgen05 kind::i8 "
+    out = {"what": f"ef_gram_u8_tc_store_device side 1: X^T X of u8[{N},{Dg}] -> int64[{Dg},{Dg}] (MN-major operands straight from the row-major X, tcgen05 kind::i8 "
                    "SYRK of the upper-triangle tiles, both triangles stored by the tile epilogues), exact; whole call",
            "ms": ms, "ms_accumulating_call": ms_acc, "store_equals_accumulate": store_equals_accumulate,
            "algorithmic_tops": algorithmic / ms / 1e9, "executed_tops": executed / ms / 1e9,
