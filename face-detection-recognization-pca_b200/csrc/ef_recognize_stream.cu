@@ -120,7 +120,7 @@ struct StreamShared {
   int list_cnt[2], overflow[2];
   double pn[2][QB];
   double xu[QB];
-  unsigned long long ssq_recv[2][QB];        // sum of squares of my 32 crops, ADDED by the four K quarters (red.async)
+  unsigned long long ssq_recv[2][kCluster][QB];
   alignas(16) float fmax_s[kFinishWarps][QB];
   int list_L[2][kListCap], list_j[2][kListCap];
 };
@@ -199,8 +199,7 @@ __device__ __forceinline__ void push_chunk(const uint32_t (&v)[16], int c0, int 
       for (int s = 0; s < 8; ++s) plane[s] = s < PS ? (int32_t)v[f * PS + s] : 0;
       long long hi, lo;
       ef::planes_to_hilo(plane, hi, lo);
-      red_async_add_u64(dst + (uint32_t)c * (QB * 16u), (unsigned long long)hi, dst_bar);
-      red_async_add_u64(dst + (uint32_t)c * (QB * 16u) + 8u, (unsigned long long)lo, dst_bar);
+      st_async_v2_u64(dst + (uint32_t)c * (QB * 16u), (unsigned long long)hi, (unsigned long long)lo, dst_bar);
     }
   }
 }
@@ -217,7 +216,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   const int stage_bytes = A_STAGE_BYTES + b_stage_bytes;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)a.stages * A_STAGE_BYTES;
-  uint8_t* recv = smem + a.off_recv;                              // [recv_bufs][kq][32 crops] (hi, lo) int64, ADDED by 4 sources
+  uint8_t* recv = smem + a.off_recv;                              // [recv_bufs][4 sources][kq][32 crops] (hi, lo) int64
   double* ps = reinterpret_cast<double*>(smem + a.off_ps);        // [KR][QB] features of the item being finished
   double* pe = reinterpret_cast<double*>(smem + a.off_pe);        // [KR][QB] the same as the exact scorer uses them
   uint8_t* bop = smem + a.off_bop;                                // filter N operand: my 32 crops x kf float16 [hi|hi|lo]
@@ -233,7 +232,7 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
   const int row_bytes = a.kf * 2;
   const uint32_t gal_tile_bytes = (uint32_t)kGalTile * (uint32_t)row_bytes;
   const uint32_t bop_bytes = ((uint32_t)(QB * row_bytes) + 1023u) & ~1023u;     // one of the two filter-operand buffers
-  const uint32_t recv_buf_bytes = (uint32_t)(a.kq * QB * 16);
+  const uint32_t recv_buf_bytes = (uint32_t)(kCluster * a.kq * QB * 16);
   // bytes one use of a receive buffer collects: four sources x (kq columns x 32 crops x (hi, lo) + 32 sums of squares)
   const uint32_t recv_tx_bytes = (uint32_t)(kCluster * (a.kq * QB * 16 + QB * 8));
 
@@ -265,10 +264,6 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  // the receive buffers ACCUMULATE (remote red.async adds): they start at zero and are zeroed again by their readers
-  for (uint32_t i = tid; i < (uint32_t)a.recv_bufs * recv_buf_bytes / 8u; i += kThreads)
-    reinterpret_cast<unsigned long long*>(recv)[i] = 0ull;
-  if (tid < 2 * QB) (&sh->ssq_recv[0][0])[tid] = 0ull;
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
                  "r"(512u)
@@ -398,8 +393,8 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       const int rb = it % a.recv_bufs, use = it / a.recv_bufs;
       ok = __all_sync(0xffffffffu, mbar_wait_cluster(&sh->push_ok[rb][owner], (uint32_t)((use & 1) ^ 1), failed));
       if (!ok) break;
-      red_async_add_u64(map_to_cta(smem_u32(&sh->ssq_recv[rb][lane]), (uint32_t)owner), ssq,
-                        map_to_cta(smem_u32(&sh->recv_full[rb]), (uint32_t)owner));
+      st_async_u64(map_to_cta(smem_u32(&sh->ssq_recv[rb][rank][lane]), (uint32_t)owner), ssq,
+                   map_to_cta(smem_u32(&sh->recv_full[rb]), (uint32_t)owner));
       ++it;
     }
   } else if (warp == 6) {
@@ -560,7 +555,9 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
                                                    wslot ? wslot + 1 : nullptr, true));
       if (trace && tid == 8 * 32 && it < 16) trace[192 + 2 * it] = globaltimer();
       if (ok) {
-        const uint32_t dst = map_to_cta(smem_u32(recv) + (uint32_t)rb * recv_buf_bytes + (uint32_t)lane * 16u, (uint32_t)q);
+        const uint32_t dst = map_to_cta(smem_u32(recv) + (uint32_t)rb * recv_buf_bytes +
+                                            (uint32_t)((int)rank * a.kq * QB + lane) * 16u,
+                                        (uint32_t)q);
         const uint32_t src = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * kAccCols);
         const uint32_t dst_bar = map_to_cta(smem_u32(&sh->recv_full[rb]), (uint32_t)q);
         for (int c0 = 0; c0 < a.nc_pad; c0 += 16) {
@@ -581,17 +578,20 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       ok = __all_sync(0xffffffffu, ok && timed_wait(&sh->recv_full[rb], (uint32_t)(use & 1), failed,
                                                    wslot ? wslot + 2 : nullptr, true));
       if (probe && tid == 8 * 32 && (it == 0 || it == 4)) probe[it == 0 ? 7 : 11] = globaltimer();
-      longlong2* rbase = reinterpret_cast<longlong2*>(recv + (size_t)rb * recv_buf_bytes) + lane;
+      const longlong2* rbase = reinterpret_cast<const longlong2*>(recv + (size_t)rb * recv_buf_bytes) + lane;
 #pragma unroll
       for (int i = 0; i < kColIters; ++i) {
         const int c = fw + 4 * i;
         if (c < max(a.kq, KR)) {
           double v = 0.0;
           if (c < a.kq && ok) {
-            // the four K quarters have been added up on arrival (exact: integer addition commutes); read and clear
-            const longlong2 p = rbase[c * QB];
-            rbase[c * QB] = make_longlong2(0, 0);
-            const long long hi = p.x, lo = p.y;
+            long long hi = 0, lo = 0;
+#pragma unroll
+            for (int src = 0; src < kCluster; ++src) {
+              const longlong2 p = rbase[(src * a.kq + c) * QB];
+              hi += p.x;
+              lo += p.y;
+            }
             v = ef::hilo_to_double(hi, lo) * col_scale[i];
             if (c < a.k) {
               v -= col_bias[i];
@@ -605,8 +605,8 @@ recognize_stream_kernel(const __grid_constant__ StreamArgs a) {
       }
       unsigned long long ssq_total = 0;
       if (fw == 0) {
-        ssq_total = sh->ssq_recv[rb][lane];
-        sh->ssq_recv[rb][lane] = 0ull;
+#pragma unroll
+        for (int src = 0; src < kCluster; ++src) ssq_total += sh->ssq_recv[rb][src][lane];
       }
       bar_front();                                   // receive buffer consumed; features complete
       if (fw == 1) {                                 // re-arm the byte count, then hand the buffer back to the four sources
@@ -779,7 +779,7 @@ bool plan_layout(int nc_pad, int kq, int kr, int kf, int g_tiles, StreamLayout* 
   const size_t tile_bytes = (size_t)kGalTile * kf * 2;
   const size_t bop_bytes = (size_t)ef::round_up((int64_t)QB * kf * 2, 1024);
   struct Cand { int stages, recv_bufs; };
-  const Cand cands[] = {{6, 2}, {6, 1}, {5, 2}, {5, 1}, {4, 2}, {4, 1}, {3, 2}, {3, 1}, {2, 1}};
+  const Cand cands[] = {{5, 2}, {4, 2}, {4, 1}, {3, 2}, {3, 1}, {2, 1}};
   const char* e_st = getenv("EF_STREAM_STAGES");
   const char* e_rb = getenv("EF_STREAM_RECV_BUFS");
   for (const Cand& c : cands) {
@@ -788,7 +788,7 @@ bool plan_layout(int nc_pad, int kq, int kr, int kf, int g_tiles, StreamLayout* 
     size_t off = (size_t)c.stages * stage_bytes;
     StreamLayout L{};
     L.stages = c.stages; L.recv_bufs = c.recv_bufs;
-    L.off_recv = (int)off; off += (size_t)c.recv_bufs * kq * QB * 16;
+    L.off_recv = (int)off; off += (size_t)c.recv_bufs * kCluster * kq * QB * 16;
     L.off_ps = (int)off;   off += sizeof(double) * kr * QB;
     L.off_pe = (int)off;   off += 2 * sizeof(double) * kr * QB;
     off = (size_t)ef::round_up((int64_t)off, 1024);

@@ -121,13 +121,6 @@ __device__ __forceinline__ void st_async_v2_u64(uint32_t cluster_addr, unsigned 
                ::"r"(cluster_addr), "l"(a), "l"(b), "r"(cluster_mbar) : "memory");
 }
 
-// Remote 64-bit integer ADD with the same completion mechanism (REDAS.ADD.64): four CTAs accumulate their partial sums
-// straight into ONE buffer of the owner instead of four receive slabs.
-__device__ __forceinline__ void red_async_add_u64(uint32_t cluster_addr, unsigned long long v, uint32_t cluster_mbar) {
-  asm volatile("red.async.relaxed.cluster.mbarrier::complete_tx::bytes.shared::cluster.add.u64 [%0], %1, [%2];"
-               ::"r"(cluster_addr), "l"(v), "r"(cluster_mbar) : "memory");
-}
-
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c_inner,
                                             int c_outer) {
   asm volatile(

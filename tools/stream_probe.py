@@ -88,7 +88,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "l2":
     os.environ.pop("EF_STREAM_PREFETCH")
 if len(sys.argv) > 1 and sys.argv[1] == "stages":
     rec.set_serving(0, 8)
-    for st in (3, 4, 5, 6):
+    for st in (2, 3, 4):
         os.environ["EF_STREAM_STAGES"] = str(st)
         us = timed()
         print(f"stream kernel, {st} stages, depth 8: {us:7.2f} us per batch = {algo / us / 1e3 / 6550.1:.3f} of HBM peak; {check()}", flush=True)
