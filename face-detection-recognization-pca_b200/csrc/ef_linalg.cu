@@ -575,6 +575,262 @@ int jacobi_cluster(double* A, double* Vt, int n, JacobiCtl* ctl, int max_sweeps,
   return launch_jacobi_cluster<10>(A, Vt, n, ctl, max_sweeps, tol, st);
 }
 
+// ------------------------------------------------------------------------------------- blocked cluster Jacobi
+// 320 < n <= 640 (the 512-crop dark model, the 590-face Gen-2 model): the players no longer fit one 16-CTA cluster (two
+// rows of n doubles per player in registers), and the grid-barrier kernel pays 4 us per round (58 ms at n = 512).  The
+// players are cut into four groups; a sweep is three CROSS launches (two clusters each, one group pair per cluster:
+// group a's players stay on top, group b's move one pair further every round -- after s rounds every cross pair has
+// met exactly once) and one INTRA launch (four clusters, one Brent-Luk tournament per group).  Every pair of the sweep
+// is rotated exactly once, as in the one-cluster kernel, with the same rotation arithmetic; rounds are separated by the
+// hardware cluster barrier (~1.5 us), launches by the kernel boundary; rows travel through L2 between launches.
+template <int EPL>
+struct JbMailbox {                       // cross mode: only the bottom player moves
+  double data[2][2][EPL][32];            // [buffer][B row | V row]
+  int id[2];
+  int pad[2];
+};
+
+struct JbGroups {
+  int ga[8], gb[8];                      // per cluster: the group pair (cross) or the group (intra, gb unused)
+};
+
+template <int EPL>
+__device__ __forceinline__ void jb_rotate(double (&bt)[EPL], double (&vt)[EPL], double (&bb)[EPL], double (&vb)[EPL],
+                                          int id_t, int id_b, double fro2, double rot_tol2, double& local_off2) {
+  double alpha = 0.0, beta = 0.0, gamma = 0.0;
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    alpha = fma(bt[e], bt[e], alpha);
+    beta = fma(bb[e], bb[e], beta);
+    gamma = fma(bt[e], bb[e], gamma);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    alpha += __shfl_xor_sync(0xffffffffu, alpha, o);
+    beta += __shfl_xor_sync(0xffffffffu, beta, o);
+    gamma += __shfl_xor_sync(0xffffffffu, gamma, o);
+  }
+  const double d2 = (alpha + beta + 2.0 * sqrt(alpha * beta)) * fro2;
+  if (d2 > 0.0 && gamma != 0.0) {
+    const double g2 = gamma * gamma;
+    if (g2 > local_off2 * d2) local_off2 = g2 / d2;
+    if (g2 > rot_tol2 * d2) {
+      const bool t_first = id_t < id_b;            // same orientation as the other Jacobi kernels
+      const double delta = t_first ? beta - alpha : alpha - beta;
+      const double root = sqrt(fma(delta, delta, 4.0 * g2));
+      const double t = (delta == 0.0) ? copysign(1.0, gamma) : (2.0 * gamma) / (delta + copysign(root, delta));
+      const double c = rsqrt(fma(t, t, 1.0));
+      const double sn = c * t;
+#pragma unroll
+      for (int e = 0; e < EPL; ++e) {
+        const double xp = t_first ? bt[e] : bb[e], xq = t_first ? bb[e] : bt[e];
+        const double np_ = c * xp - sn * xq, nq_ = sn * xp + c * xq;
+        bt[e] = t_first ? np_ : nq_;
+        bb[e] = t_first ? nq_ : np_;
+        const double up = t_first ? vt[e] : vb[e], uq = t_first ? vb[e] : vt[e];
+        const double mp_ = c * up - sn * uq, mq_ = sn * up + c * uq;
+        vt[e] = t_first ? mp_ : mq_;
+        vb[e] = t_first ? mq_ : mp_;
+      }
+    }
+  }
+}
+
+template <int EPL, int MODE>
+__global__ void __launch_bounds__(320, 1)
+jacobi_block_kernel(double* __restrict__ Bt, double* __restrict__ Vt, int n, int ld, JacobiCtl* ctl, double tol, int s,
+                    JbGroups groups, int warps_per_cta) {
+  extern __shared__ __align__(16) unsigned char jb_smem[];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t rank = jc::cluster_rank();
+  const int cl = blockIdx.x / jc::kClusterCtas;
+  const int ga = groups.ga[cl], gb = groups.gb[cl];
+  const int np = MODE == 0 ? s : (s + 1) / 2;      // pairs of this cluster
+  const int g = (int)rank * warps_per_cta + warp;
+  const bool active = g < np;
+  const double fro = ctl->fro;
+  const double fro2 = fro * fro, rot_tol2 = (tol * 0.25) * (tol * 0.25);
+  const int hi_a = min(n, (ga + 1) * s), hi_b = min(n, (gb + 1) * s);
+  int id_t, id_b;
+  if (MODE == 0) { id_t = ga * s + g; id_b = gb * s + g; if (id_t >= hi_a) id_t = INT_MAX; if (id_b >= hi_b) id_b = INT_MAX; }
+  else { id_t = ga * s + 2 * g; id_b = ga * s + 2 * g + 1; if (id_t >= hi_a) id_t = INT_MAX; if (id_b >= hi_a) id_b = INT_MAX; }
+  if (!active) id_t = id_b = INT_MAX;
+  double bt[EPL], vt[EPL], bb[EPL], vb[EPL];
+#pragma unroll
+  for (int e = 0; e < EPL; ++e) {
+    const int i = lane + 32 * e;
+    const bool in = i < n;
+    bt[e] = (in && id_t != INT_MAX) ? Bt[(int64_t)id_t * ld + i] : 0.0;
+    vt[e] = (in && id_t != INT_MAX) ? Vt[(int64_t)id_t * ld + i] : 0.0;
+    bb[e] = (in && id_b != INT_MAX) ? Bt[(int64_t)id_b * ld + i] : 0.0;
+    vb[e] = (in && id_b != INT_MAX) ? Vt[(int64_t)id_b * ld + i] : 0.0;
+  }
+  jc::cluster_barrier();                           // every CTA of the cluster runs: remote mailboxes exist
+  double local_off2 = 0.0;
+  unsigned step = 0;
+  if (MODE == 0) {
+    JbMailbox<EPL>* box = reinterpret_cast<JbMailbox<EPL>*>(jb_smem);
+    const int gd = (g + 1) % np;                   // the bottom player moves one pair further
+    const uint32_t d_base = jc::mapa(jc::smem_addr(box) + (uint32_t)((gd % warps_per_cta) * sizeof(JbMailbox<EPL>)),
+                                     (uint32_t)(gd / warps_per_cta));
+    constexpr uint32_t kBufBytes = 2 * EPL * 32 * 8, kIdOff = 2 * kBufBytes;
+    for (int round = 0; round < np; ++round, ++step) {
+      if (active) {
+        if (id_t != INT_MAX && id_b != INT_MAX) jb_rotate<EPL>(bt, vt, bb, vb, id_t, id_b, fro2, rot_tol2, local_off2);
+        const uint32_t buf = step & 1u;
+        const uint32_t pb = d_base + buf * kBufBytes + (uint32_t)lane * 8u;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          jc::st_remote_f64(pb + (uint32_t)e * 256u, bb[e]);
+          jc::st_remote_f64(pb + (uint32_t)(EPL + e) * 256u, vb[e]);
+        }
+        if (lane == 0) jc::st_remote_u32(d_base + kIdOff + buf * 4u, (unsigned)id_b);
+      }
+      jc::cluster_barrier();
+      if (active) {
+        const uint32_t buf = step & 1u;
+        const JbMailbox<EPL>& mine = box[warp];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          bb[e] = mine.data[buf][0][e][lane];
+          vb[e] = mine.data[buf][1][e][lane];
+        }
+        id_b = mine.id[buf];
+      }
+    }
+  } else {
+    JcMailbox<EPL>* box = reinterpret_cast<JcMailbox<EPL>*>(jb_smem);
+    int dt_g, dt_slot, db_g, db_slot;              // Brent-Luk shift, as in jacobi_cluster_kernel
+    if (g == 0) { dt_g = 0; dt_slot = 0; } else if (g == np - 1) { dt_g = g; dt_slot = 1; } else { dt_g = g + 1; dt_slot = 0; }
+    if (g == 0) { db_g = np > 1 ? 1 : 0; db_slot = np > 1 ? 0 : 1; } else { db_g = g - 1; db_slot = 1; }
+    const uint32_t box_local = jc::smem_addr(box);
+    const uint32_t dt_base = jc::mapa(box_local + (uint32_t)((dt_g % warps_per_cta) * sizeof(JcMailbox<EPL>)),
+                                      (uint32_t)(dt_g / warps_per_cta));
+    const uint32_t db_base = jc::mapa(box_local + (uint32_t)((db_g % warps_per_cta) * sizeof(JcMailbox<EPL>)),
+                                      (uint32_t)(db_g / warps_per_cta));
+    constexpr uint32_t kSlotBytes = 2 * EPL * 32 * 8, kBufBytes = 2 * kSlotBytes, kIdOff = 2 * kBufBytes;
+    for (int round = 0; round < 2 * np - 1; ++round, ++step) {
+      if (active) {
+        if (id_t != INT_MAX && id_b != INT_MAX) jb_rotate<EPL>(bt, vt, bb, vb, id_t, id_b, fro2, rot_tol2, local_off2);
+        const uint32_t buf = step & 1u;
+        const uint32_t pt = dt_base + buf * kBufBytes + (uint32_t)dt_slot * kSlotBytes + (uint32_t)lane * 8u;
+        const uint32_t pb = db_base + buf * kBufBytes + (uint32_t)db_slot * kSlotBytes + (uint32_t)lane * 8u;
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          jc::st_remote_f64(pt + (uint32_t)e * 256u, bt[e]);
+          jc::st_remote_f64(pt + (uint32_t)(EPL + e) * 256u, vt[e]);
+          jc::st_remote_f64(pb + (uint32_t)e * 256u, bb[e]);
+          jc::st_remote_f64(pb + (uint32_t)(EPL + e) * 256u, vb[e]);
+        }
+        if (lane == 0) {
+          jc::st_remote_u32(dt_base + kIdOff + (buf * 2u + (uint32_t)dt_slot) * 4u, (unsigned)id_t);
+          jc::st_remote_u32(db_base + kIdOff + (buf * 2u + (uint32_t)db_slot) * 4u, (unsigned)id_b);
+        }
+      }
+      jc::cluster_barrier();
+      if (active) {
+        const uint32_t buf = step & 1u;
+        const JcMailbox<EPL>& mine = box[warp];
+#pragma unroll
+        for (int e = 0; e < EPL; ++e) {
+          bt[e] = mine.data[buf][0][0][e][lane];
+          vt[e] = mine.data[buf][0][1][e][lane];
+          bb[e] = mine.data[buf][1][0][e][lane];
+          vb[e] = mine.data[buf][1][1][e][lane];
+        }
+        id_t = mine.id[buf][0];
+        id_b = mine.id[buf][1];
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int e = 0; e < EPL; ++e) {
+      const int i = lane + 32 * e;
+      if (i < n) {
+        if (id_t != INT_MAX) { Bt[(int64_t)id_t * ld + i] = bt[e]; Vt[(int64_t)id_t * ld + i] = vt[e]; }
+        if (id_b != INT_MAX) { Bt[(int64_t)id_b * ld + i] = bb[e]; Vt[(int64_t)id_b * ld + i] = vb[e]; }
+      }
+    }
+    if (lane == 0 && local_off2 > 0.0)
+      atomicMax(reinterpret_cast<unsigned long long*>(&ctl->off_bits),
+                (unsigned long long)__double_as_longlong(sqrt(local_off2)));
+  }
+  jc::cluster_barrier();                           // no CTA leaves while a peer may still write into its mailboxes
+}
+
+template <int EPL, int MODE>
+int launch_jacobi_block(double* A, double* Vt, int n, JacobiCtl* ctl, double tol, int s, const JbGroups& groups,
+                        int clusters, cudaStream_t st) {
+  const int np = MODE == 0 ? s : (s + 1) / 2;
+  const int wpc = (int)ef::ceil_div(np, jc::kClusterCtas);
+  const size_t smem = (size_t)wpc * (MODE == 0 ? sizeof(JbMailbox<EPL>) : sizeof(JcMailbox<EPL>));
+  if (wpc > 10 || smem > 227 * 1024) return EF_ERR_UNSUPPORTED;
+  if (EF_FIRST_ON_DEVICE()) {
+    EF_CUDA(cudaFuncSetAttribute(jacobi_block_kernel<EPL, MODE>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+    EF_CUDA(cudaFuncSetAttribute(jacobi_block_kernel<EPL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(clusters * jc::kClusterCtas));
+  cfg.blockDim = dim3((unsigned)wpc * 32);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attrs[1];
+  attrs[0].id = cudaLaunchAttributeClusterDimension;
+  attrs[0].val.clusterDim.x = jc::kClusterCtas;
+  attrs[0].val.clusterDim.y = 1;
+  attrs[0].val.clusterDim.z = 1;
+  cfg.attrs = attrs;
+  cfg.numAttrs = 1;
+  int max_clusters = 0;
+  if (cudaOccupancyMaxActiveClusters(&max_clusters, jacobi_block_kernel<EPL, MODE>, &cfg) != cudaSuccess ||
+      max_clusters < clusters) {
+    cudaGetLastError();
+    return EF_ERR_UNSUPPORTED;
+  }
+  int ld = n;
+  EF_CUDA(cudaLaunchKernelEx(&cfg, jacobi_block_kernel<EPL, MODE>, A, Vt, n, ld, ctl, tol, s, groups, wpc));
+  ef::g_launches.fetch_add(1, std::memory_order_relaxed);
+  return EF_OK;
+}
+
+__global__ void jacobi_block_finish_kernel(JacobiCtl* ctl, int sweeps, int converged) {
+  ctl->sweeps = sweeps;
+  ctl->converged = converged;
+  ctl->off_final = __longlong_as_double((long long)ctl->off_bits);
+}
+
+template <int EPL>
+int jacobi_blocked_epl(double* A, double* Vt, int n, JacobiCtl* ctl, int max_sweeps, double tol, cudaStream_t st) {
+  const int s = (n + 3) / 4;                        // four groups
+  JbGroups cross[3] = {{{0, 2}, {1, 3}}, {{0, 1}, {2, 3}}, {{0, 1}, {3, 2}}};
+  JbGroups intra = {{0, 1, 2, 3}, {0, 0, 0, 0}};
+  int sweeps = 0, converged = 0;
+  for (int sweep = 0; sweep < max_sweeps && !converged; ++sweep) {
+    EF_CUDA(cudaMemsetAsync(&ctl->off_bits, 0, sizeof(unsigned long long), st));
+    for (int r = 0; r < 3; ++r) EF_TRY((launch_jacobi_block<EPL, 0>(A, Vt, n, ctl, tol, s, cross[r], 2, st)));
+    EF_TRY((launch_jacobi_block<EPL, 1>(A, Vt, n, ctl, tol, s, intra, 4, st)));
+    unsigned long long bits = 0;
+    EF_CUDA(cudaMemcpyAsync(&bits, &ctl->off_bits, sizeof(bits), cudaMemcpyDeviceToHost, st));
+    EF_CUDA(cudaStreamSynchronize(st));
+    double off;
+    memcpy(&off, &bits, sizeof(off));
+    sweeps = sweep + 1;
+    converged = off <= tol ? 1 : 0;
+  }
+  EF_LAUNCH(jacobi_block_finish_kernel, 1, 1, 0, st, ctl, sweeps, converged);
+  return EF_OK;
+}
+
+// EF_ERR_UNSUPPORTED outside 320 < n <= 640 or when the device cannot place four 16-CTA clusters
+int jacobi_blocked(double* A, double* Vt, int n, JacobiCtl* ctl, int max_sweeps, double tol, cudaStream_t st) {
+  if (n <= 320 || n > 640 || getenv("EF_NO_CLUSTER_JACOBI") || getenv("EF_NO_BLOCK_JACOBI")) return EF_ERR_UNSUPPORTED;
+  const int epl = (n + 31) / 32;
+  if (epl <= 12) return jacobi_blocked_epl<12>(A, Vt, n, ctl, max_sweeps, tol, st);
+  if (epl <= 16) return jacobi_blocked_epl<16>(A, Vt, n, ctl, max_sweeps, tol, st);
+  return jacobi_blocked_epl<20>(A, Vt, n, ctl, max_sweeps, tol, st);
+}
+
 // |A|_F with a fixed summation order (one CTA), so that the stopping threshold is bit-reproducible
 __global__ void jacobi_fro_kernel(const double* __restrict__ A, int64_t count, JacobiCtl* ctl) {
   __shared__ double red[32];
@@ -824,6 +1080,7 @@ int ef_eigh_jacobi_device(double* A, int32_t n, double* evals, double* evecs, vo
   EF_LAUNCH(jacobi_fro_kernel, 1, 1024, 0, st, A, (int64_t)n * n, ctl);
   int st_cluster = EF_ERR_UNSUPPORTED;
   if (n > 1) st_cluster = jacobi_cluster(A, Vt, n, ctl, max_sweeps, tol, st);
+  if (st_cluster == EF_ERR_UNSUPPORTED && n > 320) st_cluster = jacobi_blocked(A, Vt, n, ctl, max_sweeps, tol, st);
   if (st_cluster != EF_OK && st_cluster != EF_ERR_UNSUPPORTED) return st_cluster;
   if (n > 1 && st_cluster != EF_OK) {
     int per_sm = 0;

@@ -92,7 +92,7 @@ def test_cholesky_inverse_kernel():
     assert int(info) == 18
 
 
-@pytest.mark.parametrize("n", [1, 2, 3, 17, 64, 229, 300])
+@pytest.mark.parametrize("n", [1, 2, 3, 17, 64, 229, 300, 321, 512, 590, 640, 700])
 def test_jacobi_eigensolver(n):
     torch = require_gpu()
     L = ef._lib.lib()
@@ -112,7 +112,7 @@ def test_jacobi_eigensolver(n):
     assert np.all(np.diff(w) <= 1e-9 * max(1.0, abs(w[0])))                    # descending
     np.testing.assert_allclose(V @ V.T, np.eye(n), atol=1e-11)
     np.testing.assert_allclose(V @ A @ V.T, np.diag(w), atol=1e-9 * max(1.0, abs(w_ref[0])))
-    assert sweeps.value <= 20
+    assert sweeps.value <= (20 if n <= 320 else 32)        # the blocked ordering (n > 320) needs more sweeps on a rank-deficient matrix
 
 
 def test_integer_gram_colsum_and_centring():

@@ -21,8 +21,8 @@ for N, D, side in shapes:
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
     def run():
-        ef._lib.check(L.ef_gram_u8_tc_device(x.data_ptr(), x.stride(0), N, D, 0, D, side, G.data_ptr(), work.data_ptr(),
-                                             wb, st), "gram")
+        fn = L.ef_gram_u8_tc_store_device if os.environ.get("EF_GRAM_PROBE_STORE") else L.ef_gram_u8_tc_device
+        ef._lib.check(fn(x.data_ptr(), x.stride(0), N, D, 0, D, side, G.data_ptr(), work.data_ptr(), wb, st), "gram")
     for _ in range(2):
         run()
     torch.cuda.synchronize()
