@@ -598,3 +598,33 @@ def test_few_query_match_is_bit_identical_to_the_batched_kernels():
                 assert np.array_equal(getattr(few, f), getattr(big, f)[:b]), (D, k, n, metric, b, f)
         rec.close()
 
+
+def test_all_models_one_call_equals_per_model_calls():
+    """ef_models_recognize_boxes_host (one upload, K1 once, every model's K2, one download) returns, model by model, exactly
+    what ef_model_recognize_boxes_host returns for that model alone; a box outside its frame is refused, not recognised."""
+    require_gpu()
+    rng = np.random.default_rng(2024)
+    D = 64 * 64
+    recs = []
+    for k, n, metric in ((40, 178, ef.METRIC_COSINE_SK), (60, 300, ef.METRIC_COSINE_SK), (10, 500, ef.METRIC_COSINE_G1)):
+        E = np.linalg.qr(rng.normal(size=(D, k)))[0]
+        kw = dict(scale=rng.uniform(5.0, 80.0, D), pca_mean=rng.normal(0, 1e-3, D)) if metric == ef.METRIC_COSINE_SK else {}
+        recs.append(ef.Recognizer(E, rng.uniform(40, 210, D), rng.normal(size=(n, k)) * 30, metric=metric,
+                                  labels=rng.integers(0, 5, n), **kw))
+    frames = rng.integers(0, 256, (3, 240, 320, 3), dtype=np.uint8)
+    for B in (1, 5, 70):
+        boxes = np.stack([rng.integers(0, 3, B), rng.integers(0, 100, B), rng.integers(0, 60, B), rng.integers(40, 200, B),
+                          rng.integers(40, 170, B)], axis=1).astype(np.int32)
+        score, index, label = ef.engine.recognize_boxes_all_models(recs, frames, boxes, 64, 0.3)
+        assert score.shape == (3, B)
+        for i, rec in enumerate(recs):
+            one = rec.recognize_boxes(frames, boxes, 64, 0.3, want_features=False, want_residual=False)
+            assert np.array_equal(score[i], one.score) and np.array_equal(index[i], one.index) and np.array_equal(label[i], one.label)
+    bad = np.array([[0, 300, 10, 64, 64]], dtype=np.int32)               # reaches past the right edge of the frame
+    with pytest.raises(ef.EigenfacesError):
+        ef.engine.recognize_boxes_all_models(recs, frames, bad, 64, 0.3)
+    score, _, _ = ef.engine.recognize_boxes_all_models(recs, frames, boxes, 64, 0.3)     # and the models still work
+    assert np.isfinite(score).all()
+    for rec in recs:
+        rec.close()
+
