@@ -79,6 +79,7 @@ SIGNATURES = {
     "ef_match_device": (C.c_int, [c_void, c_i64, c_i32, c_i32, c_void, c_i64, c_void, c_i64, c_i64, c_i32, c_void,
                                   c_void, c_void, c_void]),
     "ef_match_tc_image_bytes": (C.c_size_t, [c_i64, c_i32]),
+    "ef_match_tc_image_bytes_metric": (C.c_size_t, [c_i64, c_i32, c_i32]),
     "ef_match_tc_prepare_device": (C.c_int, [c_void, c_i64, c_void, c_i64, c_i32, c_i32, c_void, c_void]),
     "ef_match_tc_work_bytes": (C.c_size_t, [c_i32, c_i64, c_i32]),
     "ef_match_tc_device": (C.c_int, [c_void, c_i64, c_i32, c_i32, c_void, c_i64, c_void, c_void, c_i64, c_i64, c_i32,

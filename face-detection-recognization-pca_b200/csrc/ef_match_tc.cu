@@ -15,6 +15,11 @@
 //     match_kernel (same norm, same sequential fma order, same tie rule), so score and index are bit identical to the
 //     float64 scan.  A candidate-list overflow (degenerate galleries) reports EF_ERR_UNSUPPORTED at the next
 //     synchronisation point of the caller through the flag word; the Python wrapper then runs the float64 scan.
+// Euclidean distance (the reference's first-generation matcher variant) rides the same GEMM with ONE extra component:
+//   |p - g|^2 / (2 |p| G) = |p| / (2 G)  -  ( p^ . g/G  -  r c ),   r = G / (2 |p|),  c = |g|^2 / G^2,  G = max |g|
+// so arg-min of the distance = arg-max of key = [p^, -r] . [g/G, c]; both augmented rows are scaled to components
+// <= 1 (the query side by t = 1 / max(1, r) > 0, which does not move the arg-max) and split hi/lo like the cosine
+// operands.  The survivors are re-scored as sum (p - g)^2 in the float64 order of match_kernel.
 // Blackwell mapping: the float16 gallery image streams as 32 KB (256 rows x one 128-byte K slab, SWIZZLE_128B) blocks
 // through a cp.async.bulk ring; the query tile is resident in shared memory; two 256-column TMEM accumulators alternate
 // between the MMA warp and four scanning warps (TMEM lane = query, tcgen05.ld x32 per 32 gallery rows).
@@ -40,8 +45,10 @@ constexpr int BN = 256;                     // gallery rows per tile (UMMA N)
 constexpr int kSlab = 64;                   // halfs of K per slab = one 128-byte swizzle row
 constexpr int kSlabBytesA = BLOCK_M * 128;  // 16 KB
 constexpr int kSlabBytesB = BN * 128;       // 32 KB
-constexpr int kMaxSlabs = 6;                // 3k <= 384
-constexpr float kEps = 2e-4f;
+constexpr int kMaxSlabs = 7;                // 3k <= 384 (cosine), 3(k + 1) <= 387 (L2: one extra component)
+constexpr float kEps = 2e-4f;               // cosine: unit rows
+constexpr float kEpsL2 = 4e-4f;             // L2: augmented rows of norm <= sqrt(2) on both sides
+constexpr size_t kTrailer = 256;            // after the image: [0] double G = largest gallery norm (L2 only)
 
 struct MatchTcArgs {
   const double* P;
@@ -59,6 +66,8 @@ struct MatchTcArgs {
   unsigned int* counter;       // [0] candidates, [1] overflow flag
   unsigned int cap;
   int* status;
+  const double* gscale;        // L2: largest gallery norm G (image trailer)
+  float eps;                   // |approximate key - exact key| bound of this metric
 };
 
 // order-preserving map float <-> unsigned (atomicMax on scores); 0 is below every finite score
@@ -116,6 +125,9 @@ match_tc_kernel(const MatchTcArgs a) {
   // ---- query tile -> float16 [hi | hi | lo] operand, rows normalised (float32 arithmetic: the filter is approximate)
   {
     const int KF = a.n_slabs * kSlab;
+    const bool l2 = a.metric == EF_METRIC_L2;
+    const int ka = l2 ? a.k + 1 : a.k;               // components per segment
+    const double G = l2 ? *a.gscale : 0.0;
     for (int r = warp; r < BLOCK_M; r += kThreads / 32) {
       const int q = qt * BLOCK_M + r;
       double s2 = 0.0;
@@ -125,12 +137,21 @@ match_tc_kernel(const MatchTcArgs a) {
           s2 += v * v;
         }
       s2 = ef::warp_sum(s2);
-      const float rinv = s2 > 0.0 ? rsqrtf((float)s2) : 0.f;
+      float rinv = s2 > 0.0 ? rsqrtf((float)s2) : 0.f;
+      float last = 0.f;                              // L2: the extra query component -t r
+      if (l2) {
+        const double dinv = s2 > 0.0 ? 1.0 / sqrt(s2) : 0.0;
+        const double rq = s2 > 0.0 ? 0.5 * G * dinv : 1.0;      // a zero query: key = -c (distance = |g|^2)
+        const double t = rq > 1.0 ? 1.0 / rq : 1.0;
+        rinv = (float)(dinv * t);
+        last = -(float)(rq * t);
+      }
       for (int kk = lane; kk < KF; kk += 32) {
-        const int seg = kk >= 3 * a.k ? 3 : (kk >= 2 * a.k ? 2 : (kk >= a.k ? 1 : 0));
+        const int seg = kk >= 3 * ka ? 3 : (kk >= 2 * ka ? 2 : (kk >= ka ? 1 : 0));
         __half h = __float2half_rn(0.f);
         if (seg < 3 && q < a.B) {
-          const float v = (float)a.P[(long long)q * a.ldp + (kk - seg * a.k)] * rinv;
+          const int c = kk - seg * ka;
+          const float v = c < a.k ? (float)a.P[(long long)q * a.ldp + c] * rinv : last;
           const __half hi = __float2half_rn(v);
           h = seg < 2 ? hi : __float2half_rn(v - __half2float(hi));
         }
@@ -209,7 +230,7 @@ match_tc_kernel(const MatchTcArgs a) {
       if (a.pass == 2 && live) {
         // what the CTAs of the other gallery chunks have found so far (a plain L2 read: any earlier value is valid)
         const float known = ord2f(*reinterpret_cast<volatile unsigned int*>(a.gmax + q));
-        thr = fmaxf(runmax, known) - 2.f * kEps;
+        thr = fmaxf(runmax, known) - 2.f * a.eps;
       }
       for (int c0 = 0; c0 < BN; c0 += 32) {
         const long long j0 = jbase + c0;
@@ -250,7 +271,7 @@ match_tc_kernel(const MatchTcArgs a) {
           }
           const float vm = fmaxf(fmaxf(g0, g1), fmaxf(g2, g3));
           runmax = fmaxf(runmax, vm);
-          thr = fmaxf(thr, runmax - 2.f * kEps);
+          thr = fmaxf(thr, runmax - 2.f * a.eps);
           const bool hit = live && vm >= thr;
           if (__any_sync(0xffffffffu, hit)) {
             unsigned mask = 0u;
@@ -326,27 +347,46 @@ match_tc_kernel(const MatchTcArgs a) {
   if (tid == 0 && sh->failed) atomicExch(a.status, 1);
 }
 
+// largest gallery norm (norms are >= 0: their bit patterns order like the values)
+__global__ void match_tc_maxnorm_kernel(const double* __restrict__ norms, long long n, unsigned long long* out) {
+  double m = 0.0;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += (long long)gridDim.x * blockDim.x)
+    m = fmax(m, norms[j]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
 // gallery rows -> float16 [g_hi | g_lo | g_hi] image: [tile of 256 rows][slab][256 rows x 128 B, SWIZZLE_128B]
 __global__ void match_tc_image_kernel(const double* __restrict__ gp, long long ldg, const double* __restrict__ norms,
-                                      long long n, int k, int n_slabs, int metric, uint8_t* __restrict__ img) {
+                                      long long n, int k, int n_slabs, int metric, uint8_t* __restrict__ img,
+                                      const double* __restrict__ gscale) {
   const int chunks_per_row = n_slabs * 8;          // 16-byte chunks of 8 halfs
   const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (e >= n * chunks_per_row) return;
   const long long j = e / chunks_per_row;
   const int ck = (int)(e - j * chunks_per_row);
-  double scale = 1.0;
+  const bool l2 = metric == EF_METRIC_L2;
+  const int ka = l2 ? k + 1 : k;
+  double scale = 1.0, extra = 0.0;
   if (metric == EF_METRIC_COSINE_G1) {
     const double nr = norms[j];
     scale = nr == 0.0 ? 0.0 : 1.0 / nr;
+  } else if (l2) {
+    const double G = *gscale;
+    scale = G == 0.0 ? 0.0 : 1.0 / G;
+    const double u = norms[j] * scale;
+    extra = u * u;                                 // c = |g|^2 / G^2 in [0, 1]
   }
   __align__(16) __half h[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int kk = ck * 8 + i;
-    const int seg = kk >= 3 * k ? 3 : (kk >= 2 * k ? 2 : (kk >= k ? 1 : 0));
+    const int seg = kk >= 3 * ka ? 3 : (kk >= 2 * ka ? 2 : (kk >= ka ? 1 : 0));
     __half hi = __float2half_rn(0.f), lo = hi;
     if (seg < 3) {
-      const double v = gp[j * ldg + (kk - seg * k)] * scale;
+      const int c = kk - seg * ka;
+      const double v = c < k ? gp[j * ldg + c] * scale : extra;
       hi = __double2half(v);
       lo = __double2half(v - (double)__half2float(hi));
     }
@@ -360,19 +400,21 @@ __global__ void match_tc_image_kernel(const double* __restrict__ gp, long long l
 }
 
 // thr[q] = max over chunks of cmax - 2 eps
-__global__ void match_tc_thr_kernel(const float* __restrict__ cmax, int chunks, int b_pad, int B, float* __restrict__ thr) {
+__global__ void match_tc_thr_kernel(const float* __restrict__ cmax, int chunks, int b_pad, int B, float* __restrict__ thr,
+                                    float eps) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= b_pad) return;
   float m = -CUDART_INF_F;
   for (int c = 0; c < chunks; ++c) m = fmaxf(m, cmax[(size_t)c * b_pad + q]);
-  thr[q] = q < B ? m - 2.f * kEps : CUDART_INF_F;
+  thr[q] = q < B ? m - 2.f * eps : CUDART_INF_F;
 }
 
 // single pass: thr[q] = final maximum (published by every scanning thread) - 2 eps
-__global__ void match_tc_thr_gmax_kernel(const unsigned int* __restrict__ gmax, int b_pad, int B, float* __restrict__ thr) {
+__global__ void match_tc_thr_gmax_kernel(const unsigned int* __restrict__ gmax, int b_pad, int B, float* __restrict__ thr,
+                                         float eps) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= b_pad) return;
-  thr[q] = q < B ? ord2f(gmax[q]) - 2.f * kEps : CUDART_INF_F;
+  thr[q] = q < B ? ord2f(gmax[q]) - 2.f * eps : CUDART_INF_F;
 }
 
 // query norms with the arithmetic of match_kernel (lane-strided partial sums, xor-shuffle tree)
@@ -423,7 +465,13 @@ __global__ void match_tc_rescore_kernel(const double* __restrict__ P, long long 
     const double* g = G + j * ldg;
     const double nq = pn[q];
     double acc = 0.0;
-    if (metric == EF_METRIC_COSINE_SK) {
+    if (metric == EF_METRIC_L2) {
+      for (int c = 0; c < k; ++c) {
+        const double d = p[c] - g[c];
+        acc = fma(d, d, acc);
+      }
+      acc = -acc;                                    // the lists and keys hold "higher is better"
+    } else if (metric == EF_METRIC_COSINE_SK) {
       for (int c = 0; c < k; ++c) acc = fma(p[c] / nq, g[c], acc);
     } else {
       for (int c = 0; c < k; ++c) acc = fma(p[c], g[c], acc);
@@ -449,17 +497,21 @@ __global__ void match_tc_pick_kernel(const int* __restrict__ cand_q, const long 
 }
 
 __global__ void match_tc_final_kernel(const unsigned long long* __restrict__ best_key, const long long* __restrict__ best_idx,
-                                      int B, long long index_base, double* __restrict__ out_score,
+                                      int B, long long index_base, int metric, double* __restrict__ out_score,
                                       long long* __restrict__ out_index) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= B) return;
   const unsigned long long kbits = best_key[q];
   const long long bits = (kbits >> 63) ? (long long)(kbits & 0x7fffffffffffffffull) : (long long)~kbits;
-  out_score[q] = kbits == 0ull ? -CUDART_INF : __longlong_as_double(bits);
+  const double s = kbits == 0ull ? -CUDART_INF : __longlong_as_double(bits);
+  out_score[q] = metric == EF_METRIC_L2 ? -s : s;
   out_index[q] = best_idx[q] == LLONG_MAX ? -1 : best_idx[q] + index_base;
 }
 
-int n_slabs_for(int k) { return (int)ef::ceil_div(3 * (int64_t)k, kSlab); }
+int n_slabs_for(int k, int metric) { return (int)ef::ceil_div(3 * (int64_t)(metric == EF_METRIC_L2 ? k + 1 : k), kSlab); }
+size_t image_body_bytes(int64_t n, int k, int metric) {
+  return (size_t)ef::ceil_div(n, BN) * n_slabs_for(k, metric) * kSlabBytesB;
+}
 
 struct Layout {
   size_t cmax, thr, gmax, pn, best_key, best_idx, counter, cand_q, cand_j, cand_s, cand_f, status, total;
@@ -510,22 +562,30 @@ Layout work_layout(int B, int64_t n, int k) {
 
 extern "C" {
 
-size_t ef_match_tc_image_bytes(int64_t n, int32_t k) {
+size_t ef_match_tc_image_bytes_metric(int64_t n, int32_t k, int32_t metric) {
   if (n <= 0 || k <= 0) return 0;
-  return (size_t)ef::ceil_div(n, BN) * n_slabs_for(k) * kSlabBytesB;
+  return image_body_bytes(n, k, metric) + kTrailer;
 }
+
+size_t ef_match_tc_image_bytes(int64_t n, int32_t k) { return ef_match_tc_image_bytes_metric(n, k, EF_METRIC_COSINE_SK); }
 
 int ef_match_tc_prepare_device(const double* prepared, int64_t ldg, const double* norms, int64_t n, int32_t k,
                                int32_t metric, void* image, ef_stream_t stream) {
   if (!prepared || !image || n <= 0 || k <= 0 || ldg < k) return EF_ERR_INVALID;
-  if (metric == EF_METRIC_L2 || k > 128) return EF_ERR_UNSUPPORTED;
-  if (metric == EF_METRIC_COSINE_G1 && !norms) return EF_ERR_INVALID;
+  if (metric < EF_METRIC_COSINE_SK || metric > EF_METRIC_L2) return EF_ERR_INVALID;
+  if (k > 128) return EF_ERR_UNSUPPORTED;
+  if (metric != EF_METRIC_COSINE_SK && !norms) return EF_ERR_INVALID;
   cudaStream_t st = ef::as_stream(stream);
-  EF_CUDA(cudaMemsetAsync(image, 0, ef_match_tc_image_bytes(n, k), st));
-  const int ns = n_slabs_for(k);
+  const size_t body = image_body_bytes(n, k, metric);
+  EF_CUDA(cudaMemsetAsync(image, 0, body + kTrailer, st));
+  double* gscale = reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(image) + body);
+  if (metric == EF_METRIC_L2)
+    EF_LAUNCH(match_tc_maxnorm_kernel, (unsigned)std::min<int64_t>(1024, ef::ceil_div(n, 256)), 256, 0, st, norms,
+              (long long)n, reinterpret_cast<unsigned long long*>(gscale));
+  const int ns = n_slabs_for(k, metric);
   const int64_t work = n * ns * 8;
   EF_LAUNCH(match_tc_image_kernel, (unsigned)ef::ceil_div(work, 256), 256, 0, st, prepared, (long long)ldg, norms,
-            (long long)n, k, ns, metric, reinterpret_cast<uint8_t*>(image));
+            (long long)n, k, ns, metric, reinterpret_cast<uint8_t*>(image), (const double*)gscale);
   return EF_OK;
 }
 
@@ -539,7 +599,8 @@ int ef_match_tc_device(const double* p, int64_t ldp, int32_t B, int32_t k, const
                        double* out_score, int64_t* out_index, void* work, size_t work_bytes, ef_stream_t stream) {
   if (!p || !prepared || !image || !out_score || !out_index || !work || B < 0 || k <= 0 || ldp < k || ldg < k || n <= 0)
     return EF_ERR_INVALID;
-  if (metric == EF_METRIC_L2 || k > 128) return EF_ERR_UNSUPPORTED;
+  if (metric < EF_METRIC_COSINE_SK || metric > EF_METRIC_L2) return EF_ERR_INVALID;
+  if (k > 128) return EF_ERR_UNSUPPORTED;
   if (metric == EF_METRIC_COSINE_G1 && !norms) return EF_ERR_INVALID;
   if (B == 0) return EF_OK;
   const Layout L = work_layout(B, n, k);
@@ -549,7 +610,9 @@ int ef_match_tc_device(const double* p, int64_t ldp, int32_t B, int32_t k, const
   EF_CUDA(cudaMemsetAsync(w + L.status, 0, 512, st));           // status + counter words
 
   MatchTcArgs a{};
-  a.P = p; a.ldp = ldp; a.B = B; a.k = k; a.n_slabs = n_slabs_for(k); a.metric = metric;
+  a.P = p; a.ldp = ldp; a.B = B; a.k = k; a.n_slabs = n_slabs_for(k, metric); a.metric = metric;
+  a.eps = metric == EF_METRIC_L2 ? kEpsL2 : kEps;
+  a.gscale = reinterpret_cast<const double*>(reinterpret_cast<const uint8_t*>(image) + image_body_bytes(n, k, metric));
   a.img = reinterpret_cast<const __half*>(image);
   a.n = n; a.g_tiles = (int)ef::ceil_div(n, BN); a.tiles_per_chunk = L.tiles_per_chunk; a.b_pad = L.b_pad;
   a.cmax = reinterpret_cast<float*>(w + L.cmax);
@@ -587,7 +650,7 @@ int ef_match_tc_device(const double* p, int64_t ldp, int32_t B, int32_t k, const
     a.pass = 0;
     EF_LAUNCH(match_tc_kernel, grid, kThreads, smem, st, a);
     EF_LAUNCH(match_tc_thr_kernel, (unsigned)ef::ceil_div(L.b_pad, 256), 256, 0, st, a.cmax, L.chunks, L.b_pad, B,
-              reinterpret_cast<float*>(w + L.thr));
+              reinterpret_cast<float*>(w + L.thr), a.eps);
     a.pass = 1;
     EF_LAUNCH(match_tc_kernel, grid, kThreads, smem, st, a);
     EF_LAUNCH(match_tc_rescore_kernel, rgrid, 256, 0, st, p, (long long)ldp, k, prepared, (long long)ldg, norms, pn,
@@ -598,13 +661,13 @@ int ef_match_tc_device(const double* p, int64_t ldp, int32_t B, int32_t k, const
     a.pass = 2;
     EF_LAUNCH(match_tc_kernel, grid, kThreads, smem, st, a);
     EF_LAUNCH(match_tc_thr_gmax_kernel, (unsigned)ef::ceil_div(L.b_pad, 256), 256, 0, st, a.gmax, L.b_pad, B,
-              reinterpret_cast<float*>(w + L.thr));
+              reinterpret_cast<float*>(w + L.thr), a.eps);
     EF_LAUNCH(match_tc_rescore_kernel, rgrid, 256, 0, st, p, (long long)ldp, k, prepared, (long long)ldg, norms, pn,
               a.cand_q, a.cand_j, a.counter, a.cap, metric, cand_s, best_key, a.cand_f, a.thr, a.counter + 2);
   }
   EF_LAUNCH(match_tc_pick_kernel, rgrid, 256, 0, st, a.cand_q, a.cand_j, cand_s, a.counter, a.cap, best_key, best_idx);
   EF_LAUNCH(match_tc_final_kernel, (unsigned)ef::ceil_div(B, 256), 256, 0, st, best_key, best_idx, B,
-            (long long)index_base, out_score, reinterpret_cast<long long*>(out_index));
+            (long long)index_base, (int)metric, out_score, reinterpret_cast<long long*>(out_index));
   return EF_OK;
 }
 

@@ -105,11 +105,12 @@ class ShardedGallery:
             check(L.ef_gallery_prepare_device(g.data_ptr(), self.k, self.n, self.k, metric, self.prepared.data_ptr(),
                                               self.k, self.norms.data_ptr(), stream), "ef_gallery_prepare_device")
         self._L, self._work = L, None
-        # tensor-core filter (cosine metrics, k <= 128): float16 image of this shard, built once
+        # tensor-core filter (k <= 128): float16 image of this shard, built once
         self.image = None
         self.last_flags = None
-        if use_tensor_cores and self.n and metric != METRIC_L2 and self.k <= 128:
-            self.image = torch.empty(int(L.ef_match_tc_image_bytes(self.n, self.k)), dtype=torch.uint8, device=dev)
+        if use_tensor_cores and self.n and self.k <= 128:
+            self.image = torch.empty(int(L.ef_match_tc_image_bytes_metric(self.n, self.k, metric)), dtype=torch.uint8,
+                                     device=dev)
             check(L.ef_match_tc_prepare_device(self.prepared.data_ptr(), self.k, self.norms.data_ptr(), self.n, self.k,
                                                metric, self.image.data_ptr(), stream), "ef_match_tc_prepare_device")
             self._work_tc = None

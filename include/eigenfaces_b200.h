@@ -213,18 +213,21 @@ int ef_gallery_prepare_device(const double* gallery, int64_t ldg, int64_t n, int
 int ef_match_device(const double* p, int64_t ldp, int32_t B, int32_t k, const double* prepared, int64_t ldg,
                     const double* norms, int64_t n, int64_t index_base, int32_t metric, double* out_score,
                     int64_t* out_index, void* work, ef_stream_t stream);
-/* The same search on TENSOR CORES for large galleries and the cosine metrics (k <= 128): a float16 hi/lo filter GEMM
+/* The same search on TENSOR CORES for large galleries (k <= 128, all three metrics): a float16 hi/lo filter GEMM
  * (tcgen05.mma kind::f16, float32 accumulation in TMEM) finds, per query, every gallery row within a proven error band
  * of the approximate maximum; only those rows are scored in float64, with exactly the arithmetic of ef_match_device, so
  * out_score / out_index are bit identical to it.
- *   image: device buffer of ef_match_tc_image_bytes(n, k) bytes filled once per gallery (shard) by
- *          ef_match_tc_prepare_device from the prepared rows (+ norms for COSINE_G1);
+ *   image: device buffer of ef_match_tc_image_bytes_metric(n, k, metric) bytes (ef_match_tc_image_bytes(n, k) = the
+ *          cosine size) filled once per gallery (shard) by ef_match_tc_prepare_device from the prepared rows (+ norms
+ *          for COSINE_G1 and L2).  EF_METRIC_L2 carries one extra component (|g|^2 against the largest gallery norm)
+ *          so that the same GEMM orders rows by distance; scores are sum (p - g)^2 as in ef_match_device;
  *   work:  device scratch of ef_match_tc_work_bytes(B, n, k) bytes, 256-byte aligned.  After the call has completed,
  *          ef_match_tc_flags(work, flags) reads {pipeline timeout, candidates re-scored, candidate-list overflow};
  *          on overflow (thousands of rows of every query inside the band: degenerate gallery) the outputs are
  *          incomplete and the caller must use ef_match_device.
- * EF_ERR_UNSUPPORTED for EF_METRIC_L2 or k > 128. */
+ * EF_ERR_UNSUPPORTED for k > 128. */
 size_t ef_match_tc_image_bytes(int64_t n, int32_t k);
+size_t ef_match_tc_image_bytes_metric(int64_t n, int32_t k, int32_t metric);
 int ef_match_tc_prepare_device(const double* prepared, int64_t ldg, const double* norms, int64_t n, int32_t k,
                                int32_t metric, void* image, ef_stream_t stream);
 size_t ef_match_tc_work_bytes(int32_t B, int64_t n, int32_t k);

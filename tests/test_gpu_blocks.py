@@ -248,11 +248,12 @@ def test_tensor_core_gram_matches_cuda_core_gram_all_255():
     assert torch.equal(G1, G2) and int(G1[0, 0].item()) == D * 255 * 255
 
 
-@pytest.mark.parametrize("metric", [ef.METRIC_COSINE_SK, ef.METRIC_COSINE_G1])
+@pytest.mark.parametrize("metric", [ef.METRIC_COSINE_SK, ef.METRIC_COSINE_G1, ef.METRIC_L2])
 @pytest.mark.parametrize("n,k,B", [(30_000, 128, 300), (5000, 24, 77), (1, 7, 3), (257, 1, 129), (70_001, 50, 40)])
 def test_tensor_core_matcher_equals_float64_scan(metric, n, k, B):
     """ef_match_tc_device (float16 tcgen05 filter + exact re-score) returns bit-identical (score, index) to the float64
-    scan ef_match_device, including duplicates (lowest index), near-duplicates, zero rows and a zero query."""
+    scan ef_match_device, including duplicates (lowest index), near-duplicates, zero rows and a zero query.  The L2
+    metric (sum of squared differences, lowest wins) goes through the same GEMM with one extra component."""
     torch = require_gpu()
     L = ef._lib.lib()
     rng = np.random.default_rng(n + 31 * k + metric)
@@ -261,9 +262,10 @@ def test_tensor_core_matcher_equals_float64_scan(metric, n, k, B):
         G[4000] = G[100]; G[n - 1] = G[100]                    # exact duplicates
         G[200] = G[300] * (1 + 1e-9); G[201] = G[300] + 1e-7 * rng.normal(size=k)   # near duplicates
         G[400] = 0.0                                            # zero row
-        G[401] = G[402] * 1e6
+        G[401] = G[402] * (3.0 if metric == ef.METRIC_L2 else 1e6)   # (L2 keys are relative to the largest norm)
     P = G[rng.integers(0, n, B)] + 0.02 * rng.normal(size=(B, k)) / np.arange(1, k + 1)
     zero_query = B > 2 and n <= 60_000                          # (it ties with every row: n candidates of the 65 536 list)
+    cosine = metric != ef.METRIC_L2
     if B > 2:
         if zero_query:
             P[1] = 0.0
@@ -277,7 +279,8 @@ def test_tensor_core_matcher_equals_float64_scan(metric, n, k, B):
     ef._lib.check(L.ef_match_device(p.data_ptr(), k, B, k, gp.data_ptr(), k, gn.data_ptr(), n, 1000, metric, s_ref.data_ptr(),
                                     i_ref.data_ptr(), work.data_ptr(), _stream(torch)), "match")
     # tensor-core filter + exact re-score
-    img = torch.empty(L.ef_match_tc_image_bytes(n, k), dtype=torch.uint8, device="cuda")
+    img = torch.empty(L.ef_match_tc_image_bytes_metric(n, k, metric), dtype=torch.uint8, device="cuda")
+    assert L.ef_match_tc_image_bytes(n, k) == L.ef_match_tc_image_bytes_metric(n, k, ef.METRIC_COSINE_G1)
     ef._lib.check(L.ef_match_tc_prepare_device(gp.data_ptr(), k, gn.data_ptr(), n, k, metric, img.data_ptr(), _stream(torch)), "tc prep")
     wb = L.ef_match_tc_work_bytes(B, n, k)
     wtc = torch.empty(wb, dtype=torch.uint8, device="cuda")
@@ -291,8 +294,10 @@ def test_tensor_core_matcher_equals_float64_scan(metric, n, k, B):
     assert torch.equal(i_tc, i_ref)
     assert torch.equal(s_tc, s_ref)
     # the zero query ties with every row (all cosines are 0), everything else keeps a handful of survivors
+    # (a zero query under L2 is not a tie: its distance to row j is |g_j|^2)
     if k > 1:                                                    # with k = 1 every cosine is +-1: half the gallery ties
-        assert flags[1] < 50 * B + 2000 + (n if zero_query else 0), f"filter too loose: {flags[1]} candidates for {B} queries"
+        assert flags[1] < 50 * B + 2000 + (n if zero_query and cosine else 0), \
+            f"filter too loose: {flags[1]} candidates for {B} queries"
 
 
 def test_tensor_core_matcher_overflow_falls_back():
@@ -306,3 +311,33 @@ def test_tensor_core_matcher_overflow_falls_back():
     score, index = sg.match_local(torch.from_numpy(P).cuda())
     assert sg.last_flags["overflow"] == 1
     assert torch.all(index == 7) and torch.allclose(score, torch.ones_like(score), atol=1e-12)
+
+
+def test_tensor_core_matcher_l2_sharded_gallery_and_outlier_norm():
+    """ShardedGallery with the L2 metric uses the tensor-core filter and answers exactly like the float64 scan; one gallery
+    row with a norm 10^6 times the others squeezes every other key into the error band -- the list overflows and the
+    float64 scan answers (same results, slower)."""
+    torch = require_gpu()
+    rng = np.random.default_rng(99)
+    n, k, B = 200_000, 64, 500
+    G = rng.normal(size=(n, k)) / np.sqrt(np.arange(1, k + 1))
+    P = G[rng.integers(0, n, B)] + 0.05 * rng.normal(size=(B, k))
+    P[3] *= 1e-3; P[4] *= 40.0                                   # queries far inside / outside the gallery's shell
+    p = torch.from_numpy(P).cuda()
+    ref = ef.dist.ShardedGallery(G, 11, ef.METRIC_L2, use_tensor_cores=False)
+    s_ref, i_ref = ref.match_local(p)
+    sg = ef.dist.ShardedGallery(G, 11, ef.METRIC_L2)
+    assert sg.image is not None
+    s, i = sg.match_local(p)
+    assert sg.last_flags == {"timeout": 0, "candidates": sg.last_flags["candidates"], "overflow": 0}
+    assert sg.last_flags["candidates"] < 20 * B
+    assert torch.equal(i, i_ref) and torch.equal(s, s_ref)
+    d2 = ((P - G[i_ref.cpu().numpy() - 11]) ** 2).sum(-1)
+    np.testing.assert_allclose(s.cpu().numpy(), d2, rtol=1e-12)
+    G[777] *= 1e6
+    sg2 = ef.dist.ShardedGallery(G, 11, ef.METRIC_L2)
+    ref2 = ef.dist.ShardedGallery(G, 11, ef.METRIC_L2, use_tensor_cores=False)
+    s2, i2 = sg2.match_local(p)
+    s2r, i2r = ref2.match_local(p)
+    assert sg2.last_flags["overflow"] == 1
+    assert torch.equal(i2, i2r) and torch.equal(s2, s2r)

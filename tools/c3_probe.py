@@ -19,7 +19,8 @@ lam = (torch.arange(1, k + 1, device=dev, dtype=torch.float64)) ** -2.0
 G = torch.randn((n, k), generator=gen, device=dev, dtype=torch.float64) * lam.sqrt()
 truth = torch.randint(0, n, (B,), generator=gen, device=dev)
 P = G[truth] + 0.05 * torch.randn((B, k), generator=gen, device=dev, dtype=torch.float64) * lam.sqrt()
-for metric in (ef.METRIC_COSINE_SK,):
+metrics = {"sk": ef.METRIC_COSINE_SK, "g1": ef.METRIC_COSINE_G1, "l2": ef.METRIC_L2}
+for metric in [metrics[m] for m in os.environ.get("EF_C3_METRICS", "sk").split(",")]:
     t0 = time.perf_counter()
     sg = ef.dist.ShardedGallery(G, 0, metric)
     torch.cuda.synchronize()
@@ -35,7 +36,7 @@ for metric in (ef.METRIC_COSINE_SK,):
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     flops = 2.0 * B * n * 384 * (2 if os.environ.get("EF_MATCH_TC_TWO_PASS") else 1)   # K = 3k float16 products per pass
-    print(f"n={n} k={k} B={B}: {ms:.2f} ms per batch = {B / ms * 1e3 / 1e6:.2f} M queries/s; filter {flops / ms / 1e9:.0f} TFLOP/s (f16); "
+    print(f"metric {metric} n={n} k={k} B={B}: {ms:.2f} ms per batch = {B / ms * 1e3 / 1e6:.2f} M queries/s; filter {flops / ms / 1e9:.0f} TFLOP/s (f16); "
           f"flags {sg.last_flags}; accuracy vs planted {float((i == truth).double().mean()):.4f}", flush=True)
     # float64 scan on a subsample for the timing comparison and an equality check
     sub = 64
