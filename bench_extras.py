@@ -471,9 +471,31 @@ def large_gallery_sharded(ef, torch, dist, dev, rank, world, peaks, cpu_leg=True
         for kname, v in sg.last_timings.items():
             phases[kname] = phases.get(kname, 0.0) + v * 1e3 / 3
     phases = {kname: _max_over_ranks(torch, dist, world, dev, v) for kname, v in sorted(phases.items())}
+    # the same shards under the Euclidean metric (the reference's first matcher variant): one extra GEMM component
+    sg_l2 = ef.dist.ShardedGallery(G3[lo:hi], lo, ef.METRIC_L2)
+    for _ in range(2):
+        sg_l2.match(P3)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0.record()
+    for _ in range(reps):
+        s3e, i3e = sg_l2.match(P3, timings=False)
+    e1.record()
+    torch.cuda.synchronize()
+    ms_l2 = _max_over_ranks(torch, dist, world, dev, e0.elapsed_time(e1) / reps)
+    l2_flags = sg_l2.last_flags
+    del sg_l2
     out = None
     identical, score_diff, acc = None, None, None
     if rank == 0:
+        sg64 = ef.dist.ShardedGallery(G3, 0, ef.METRIC_L2, use_tensor_cores=False)
+        s64, i64 = sg64.match_local(P3[:64])
+        l2 = {"ms_per_batch": ms_l2, "queries_per_s": B3 / ms_l2 * 1e3,
+              "bit_identical_to_float64_scan_on_64_queries": bool(torch.equal(i64, i3e[:64]) and torch.equal(s64, s3e[:64])),
+              "top1_accuracy_vs_planted": float((i3e == truth).double().mean()),
+              "candidates_rescored_on_rank0_shard": l2_flags["candidates"] if l2_flags else None}
+        del sg64
         whole = ef.dist.ShardedGallery(G3, 0, ef.METRIC_COSINE_SK) if world > 1 else sg
         ws, wi = whole.match_local(P3)
         identical = bool(torch.equal(wi, i3) and torch.equal(ws, s3))
@@ -499,6 +521,7 @@ def large_gallery_sharded(ef, torch, dist, dev, rank, world, peaks, cpu_leg=True
                "bit_identical_to_single_shard": identical, "queries_compared": B3, "score_max_abs_diff": score_diff,
                "bit_identical_to_float64_scan_on_64_queries": scan_identical,
                "top1_accuracy_vs_planted": acc, "candidates_rescored_on_rank0_shard": sg.last_flags["candidates"] if sg.last_flags else None,
+               "euclidean_metric": l2,
                "roofline": {"bound": "tensor", "achieved": alg_flops / ms / 1e9, "peak": bf16_peak * world,
                             "unit": "TFLOP/s algorithmic (2*B*Ng*k) vs measured bf16 peak x GPUs",
                             "frac": alg_flops / ms / 1e9 / (bf16_peak * world)}}

@@ -134,6 +134,28 @@ int match_small(const double* proj, int64_t ldp, int B, int k, const double* gp,
                 int64_t n, const int32_t* labels, int metric, double threshold, double* sumsq, double c0, double* resid2,
                 double* out_score, int32_t* out_index, int32_t* out_label, cudaStream_t stream);
 
+// ef_match_small_tc.cu -- the same one-launch residual + match + threshold/label with the all-pairs scan on tensor cores
+// (float16 hi/lo filter, exact float64 re-score of the rows inside the error band): 3 (k + 1) <= 576, n <= 4096.
+// image = ef_match_tc_prepare_device's image of the prepared gallery; work = match_small_tc_work_bytes(cap_B) (256-byte
+// aligned), zero before the first launch, the same cap_B >= B at every launch; status[0] is set when the tcgen05 pipeline timed out.
+bool match_small_tc_supported(int k, int64_t n, int metric);
+size_t match_small_tc_image_bytes(int k, int64_t n, int metric);
+int match_small_tc_image(const double* gp, int64_t ldgp, const double* gnorm, int64_t n, int k, int metric, void* image,
+                         cudaStream_t stream);
+size_t match_small_tc_work_bytes(int cap_B, int64_t n, int k, int metric);
+// slabs != null: proj is an OUTPUT -- the query kernel forms the features from the split-K slabs of project_tc itself
+// (what project_finalize_slabs does, one launch less) and leaves x . u~ in resid2 before the residual pass.
+struct MatchSmallTcSlabs {
+  const int32_t* part;
+  int splits, ld_part, kq, S;
+  const int32_t* col_exp;
+  const double* bias;
+};
+int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, int64_t ldgp, const double* gnorm,
+                   const void* image, int64_t n, const int32_t* labels, int metric, double threshold, double* sumsq,
+                   double c0, double* resid2, double* out_score, int32_t* out_index, int32_t* out_label, void* work,
+                   int cap_B, int* status, cudaStream_t stream, const MatchSmallTcSlabs* slabs = nullptr);
+
 // ef_gram_tc.cu -- exact integer Gram A A^T of uint8 rows on tensor cores (upper triangle + mirror), G int64 += .
 // overwrite: G = A A^T (previous content ignored; no read of G, both triangles written by the tile epilogues)
 // mn_major: A is X [K][lda] with the n outputs' axis contiguous (no transposed copy; n >= 256)

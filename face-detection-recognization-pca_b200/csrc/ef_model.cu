@@ -25,6 +25,8 @@ struct ef_model {
   // workspaces (sized by reserve)
   int reserved = 0;
   ef::DevBuf acc, proj, sumsq, score, index64, match_work, status;
+  ef::DevBuf mst_img, mst_work;     // tensor-core matcher of the shipped shapes (ef_match_small_tc.cu)
+  int mst_cap = 0;                  // batch capacity mst_work is laid out for
   ef::DevBuf part;                 // split-K slabs of the tensor-core projection (k > 32)
   int nc_pad = 0;
   bool dirty = false;
@@ -262,6 +264,14 @@ int ef_model_create(ef_model_t** out, const ef_model_desc_t* desc) {
       st = ef::gallery_image(m->gp.as<double>(), m->kpad, m->ginv.as<double>(), desc->n_gallery, k, m->metric,
                              m->gimg.p, m->stream);
   }
+  // ... and for the one-launch matcher of the shapes those kernels do not cover (k = 50 ... 178, <= 4096 rows)
+  if (st == EF_OK && !ef::fused_epilogue_supported(k, desc->n_gallery) &&
+      ef::match_small_tc_supported(k, desc->n_gallery, m->metric)) {
+    st = m->mst_img.ensure(ef::match_small_tc_image_bytes(k, desc->n_gallery, m->metric));
+    if (st == EF_OK)
+      st = ef::match_small_tc_image(m->gp.as<double>(), m->kpad, m->gnorm.as<double>(), desc->n_gallery, k, m->metric,
+                                    m->mst_img.p, m->stream);
+  }
   m->stream_ok = st == EF_OK && m->gimg.p && ef::stream_supported(D, k, m->kq, m->S, m->metric, desc->n_gallery);
   if (st == EF_OK) {
     cudaError_t e = cudaStreamSynchronize(m->stream);
@@ -361,6 +371,12 @@ int ef_model_reserve(ef_model_t* m, int32_t max_batch) {
   EF_TRY(m->score.ensure(sizeof(double) * B));
   EF_TRY(m->index64.ensure(sizeof(int64_t) * B));
   EF_TRY(m->match_work.ensure(ef::match_work_bytes(max_batch, m->n_gallery) + 16));
+  if (m->mst_img.p) {
+    const size_t wb = ef::match_small_tc_work_bytes((int)B, m->n_gallery, m->k, m->metric);
+    EF_TRY(m->mst_work.ensure(wb));
+    EF_CUDA(cudaMemset(m->mst_work.p, 0, wb));                // counters and image padding start (and stay) zero
+    m->mst_cap = (int)B;
+  }
   // the zero fills above ran on the legacy default stream, the kernels that rely on them run on non-blocking streams
   // (the model's own or the caller's), which do not order against it: finish them here (reserve is rare)
   EF_CUDA(cudaDeviceSynchronize());
@@ -452,19 +468,37 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
     // one or two CTAs of match_small_kernel would sweep the whole gallery alone (218 us at B = 1, 590 x 590); the split
     // chain spreads the gallery rows over the SMs instead.
     if (small && ef::ceil_div(B, 32) * 8 < ef::sm_count() && (int64_t)m->n_gallery * m->k >= 16384) small = false;
+    // tensor-core filter + exact re-score in one launch (same results, bit for bit): takes over from both
+    const bool small_tc = m->mst_img.p && m->mst_work.p && !getenv("EF_NO_MATCH_SMALL_TC") && !getenv("EF_NO_MATCH_SMALL");
+    if (small_tc) small = true;
+    ef::MatchSmallTcSlabs slabs{};
+    bool fused_finalize = false;
     if (m->last_used_tc && part) {
       int splits = 1, ld_part = 0;
       ef::project_tc_split_shape(B, m->D, m->NC, &splits, &ld_part);
-      EF_TRY(ef::project_finalize_slabs(part, splits, ld_part, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(),
-                                        m->bias.as<double>(), proj, m->k, want_resid ? out->resid2 : nullptr, st));
-      if (!small && want_resid)
-        EF_TRY(ef::project_resid(proj, m->k, B, m->k, sumsq, m->c0, out->resid2, st));
+      if (small_tc && m->S <= 8 && getenv("EF_MST_FUSED_FINALIZE")) {
+        // the matcher's query kernel can form the features from the slabs itself (one launch less).  Opt-in: measured
+        // SLOWER -- a warp per crop walks splits x planes loads per column in sequence: 15.6 us against 6.2 + 3.8 us
+        // for finalize_slabs_kernel (a thread per column) + the query kernel at k = 50
+        slabs = ef::MatchSmallTcSlabs{part, splits, ld_part, m->kq, m->S, m->col_exp.as<int32_t>(), m->bias.as<double>()};
+        fused_finalize = true;
+      } else {
+        EF_TRY(ef::project_finalize_slabs(part, splits, ld_part, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(),
+                                          m->bias.as<double>(), proj, m->k, want_resid ? out->resid2 : nullptr, st));
+        if (!small && want_resid)
+          EF_TRY(ef::project_resid(proj, m->k, B, m->k, sumsq, m->c0, out->resid2, st));
+      }
     } else {
       EF_TRY(ef::project_finalize(acc, m->ld_acc, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(),
                                   m->bias.as<double>(), proj, m->k, sumsq, m->c0, want_resid ? out->resid2 : nullptr,
                                   !small, st));
     }
-    if (small) {
+    if (small_tc) {
+      EF_TRY(ef::match_small_tc(proj, m->k, B, m->k, m->gp.as<double>(), m->kpad, m->gnorm.as<double>(), m->mst_img.p,
+                                m->n_gallery, labels, m->metric, threshold, sumsq, m->c0,
+                                want_resid ? out->resid2 : nullptr, out->score, out->index, out->label, m->mst_work.p,
+                                m->mst_cap, m->status.as<int>(), st, fused_finalize ? &slabs : nullptr));
+    } else if (small) {
       EF_TRY(ef::match_small(proj, m->k, B, m->k, m->gp.as<double>(), m->kpad, m->gnorm.as<double>(), m->n_gallery,
                              labels, m->metric, threshold, sumsq, m->c0, want_resid ? out->resid2 : nullptr, out->score,
                              out->index, out->label, st));

@@ -484,6 +484,74 @@ def test_small_gallery_fused_match_equals_generic_chain():
         rec.close()
 
 
+@pytest.mark.parametrize("metric", [ef.METRIC_COSINE_G1, ef.METRIC_COSINE_SK, ef.METRIC_L2])
+def test_tensor_core_small_matcher_equals_float64_kernels(metric):
+    """k = 33 ... 191, galleries of <= 4096 rows (the shipped model shapes): the one-launch matcher whose all-pairs scan
+    runs on tensor cores (ef_match_small_tc.cu: float16 hi/lo filter, float64 re-score of the rows inside the error
+    band) against the float64 one-launch kernel (EF_NO_MATCH_SMALL_TC=1) and the generic chain (EF_NO_MATCH_SMALL=1):
+    features, score, index, label and residual bit for bit -- on galleries with exact duplicates, near-duplicates
+    (1e-9 ... 1e-13 relative), zero rows, rows of very different norms, and a batch with zero / duplicated crops."""
+    import os
+    require_gpu()
+    rng = np.random.default_rng(1234 + metric)
+    cases = [(1600, 50, 229, 4096, False), (1024, 178, 178, 300, True), (1024, 50, 590, 513, True),
+             (900, 33, 1, 40, False), (640, 97, 1000, 1, True), (2048, 64, 257, 129, True), (512, 191, 64, 128, False),
+             (512, 40, 4096, 200, False), (700, 50, 65, 5, False)]
+    for D, k, n, B, scaled in cases:
+        if metric == ef.METRIC_L2 and k == 191:
+            k = 190                                                # one extra component: 3 (k + 1) <= 576
+        E = np.linalg.qr(rng.normal(size=(D, k)))[0]
+        mean = rng.uniform(40, 210, D)
+        kw = dict(scale=rng.uniform(5.0, 80.0, D), pca_mean=rng.normal(0, 1e-2, D)) if scaled else {}
+        X = rng.integers(0, 256, (B, D), dtype=np.uint8)
+        if B > 4:
+            X[1] = X[0]
+            X[2] = np.round(mean).astype(np.uint8)                 # (almost) the mean face: features near zero
+        # gallery = projections of crops like the queries (so that the matches are close), then the adversarial rows
+        Xg = rng.integers(0, 256, (n, D), dtype=np.uint8)
+        if n >= B:
+            Xg[rng.permutation(n)[:B]] = X
+        A = (Xg.astype(np.float64) - mean)
+        if scaled:
+            A = A / kw["scale"] - kw["pca_mean"]
+        G = A @ E
+        if n > 40:
+            G[n - 2] = G[3]                                        # exact duplicate: the lower index wins
+            G[7] = 0.0
+            G[11] = G[12] * (1 + 1e-9); G[13] = G[14] * (1 + 1e-13); G[15] = G[16] + 1e-11 * rng.normal(size=k)
+            if metric != ef.METRIC_L2:
+                G[20] = G[21] * 1e6; G[22] = G[23] * 1e-6          # same direction, other norms (cosine ties)
+            else:
+                G[20] = G[21] * 3.0
+        rec = ef.Recognizer(E, mean, G, metric=metric, labels=rng.integers(0, 9, n), **kw)
+        thr = 0.1 if metric != ef.METRIC_L2 else 1e12
+        outs = []
+        for env in (None, "EF_NO_MATCH_SMALL_TC", "EF_NO_MATCH_SMALL", "EF_MST_FUSED_FINALIZE", "EF_MST_NO_BULK"):
+            if env:
+                os.environ[env] = "1"
+            try:
+                l0 = ef.launch_count()
+                outs.append((rec.recognize(X, thr), ef.launch_count() - l0))
+            finally:
+                if env:
+                    os.environ.pop(env, None)
+        (a, la), (b, lb), (c, lc), (d, ld), (e, le) = outs
+        assert la <= lc and lb <= lc                          # (two launches: query operand + filter / re-score)
+        for f in ("features", "score", "index", "label", "resid2"):
+            assert np.array_equal(getattr(a, f), getattr(b, f)), (D, k, n, B, metric, f, "tc vs float64 one-launch")
+            assert np.array_equal(getattr(a, f), getattr(c, f)), (D, k, n, B, metric, f, "tc vs generic chain")
+            assert np.array_equal(getattr(a, f), getattr(d, f)), (D, k, n, B, metric, f, "features formed by the query kernel")
+            assert np.array_equal(getattr(a, f), getattr(e, f)), (D, k, n, B, metric, f, "rows staged by cp.async")
+        # a shorter batch after a longer one through the same scratch buffers (layout by capacity, stale rows zeroed)
+        for b in (1, 3, 130):
+            if b < B:
+                few = rec.recognize(X[:b], thr)
+                for f in ("features", "score", "index", "label", "resid2"):
+                    assert np.array_equal(getattr(few, f), getattr(a, f)[:b]), (D, k, n, B, metric, f, b)
+        assert rec.pipeline_timeouts() == 0
+        rec.close()
+
+
 def test_split_k_slabs_equal_stream_k_atomics():
     """k > 32 on tensor cores: the split-K schedule that STORES partial tiles into slabs (default) against the stream-K
     schedule that merges them with int32 RED atomics (EF_NO_SLABS=1) and against the CUDA-core path (mode 0)."""
