@@ -41,6 +41,30 @@ void set_error_detail(const char* what, cudaError_t e);
     }                                                                     \
   } while (0)
 
+// The same launch with programmatic stream serialization: the grid may be SCHEDULED while the previous kernel of the
+// stream is still running (once all of that kernel's CTAs have executed griddepcontrol.launch_dependents or exited); the
+// kernel must execute griddepcontrol.wait before it touches anything an earlier kernel of the stream writes.
+// EF_NO_PDL=1 launches normally.
+#define EF_LAUNCH_PDL(kernel, grid, block, smem, stream, ...)                                   \
+  do {                                                                                          \
+    cudaLaunchConfig_t cfg__{};                                                                 \
+    cfg__.gridDim = dim3(grid);                                                                 \
+    cfg__.blockDim = dim3(block);                                                               \
+    cfg__.dynamicSmemBytes = (smem);                                                            \
+    cfg__.stream = (stream);                                                                    \
+    cudaLaunchAttribute attr__[1];                                                              \
+    attr__[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                          \
+    attr__[0].val.programmaticStreamSerializationAllowed = 1;                                   \
+    cfg__.attrs = attr__;                                                                       \
+    cfg__.numAttrs = getenv("EF_NO_PDL") ? 0 : 1;                                               \
+    cudaError_t e__ = cudaLaunchKernelEx(&cfg__, kernel, __VA_ARGS__);                          \
+    ::ef::g_launches.fetch_add(1, std::memory_order_relaxed);                                   \
+    if (e__ != cudaSuccess) {                                                                   \
+      ::ef::set_error_detail(#kernel, e__);                                                     \
+      return EF_ERR_CUDA;                                                                       \
+    }                                                                                           \
+  } while (0)
+
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE: one process may drive several GPUs, so the "already
 // raised to N bytes" bookkeeping is kept per device ordinal (one static table per call site / template instantiation).
 #define EF_ENSURE_SMEM(kernel, bytes)                                                                           \

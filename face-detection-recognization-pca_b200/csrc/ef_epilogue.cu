@@ -283,6 +283,10 @@ __global__ void __launch_bounds__(256)
 finalize_slabs_kernel(const int32_t* __restrict__ part, int splits, long long slab_stride, int ld_part, int B, int k,
                       int kq, int S, const int32_t* __restrict__ col_exp, const double* __restrict__ bias,
                       double* __restrict__ proj, int64_t ldp, double* __restrict__ xu_out) {
+  // programmatic dependent launch on both sides: scheduled behind the projection (or the row sums), and the matcher's
+  // query kernel may be scheduled behind this one
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   // flattened (crop, column) index: every lane is busy whatever kq is; runs of kq consecutive lanes read one crop
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;          // B * kq < 2^31 (checked by the launcher)
   const int b = (int)(idx / (unsigned)kq);                             // 32-bit division: the 64-bit one costs more
@@ -365,8 +369,8 @@ int project_finalize_slabs(const int32_t* part, int splits, int ld_part, int B, 
   if (B <= 0) return EF_OK;
   if (S > 8 || (int64_t)B * kq >= (1ll << 31) - 256) return EF_ERR_INVALID;
   const unsigned grid = (unsigned)ceil_div((int64_t)B * kq, 256);
-  EF_LAUNCH(finalize_slabs_kernel, grid, 256, 0, stream, part, splits, (long long)B * ld_part, ld_part, B, k, kq, S,
-            col_exp, bias, proj, ldp, (kq > k) ? resid2 : nullptr);
+  EF_LAUNCH_PDL(finalize_slabs_kernel, grid, 256, 0, stream, part, splits, (long long)B * ld_part, ld_part, B, k, kq, S,
+                col_exp, bias, proj, (int64_t)ldp, (kq > k) ? resid2 : (double*)nullptr);
   return EF_OK;
 }
 

@@ -176,6 +176,10 @@ struct MstQueryArgs {
 
 __global__ void __launch_bounds__(256)
 mst_query_kernel(const MstQueryArgs a) {
+  // programmatic dependent launch: the matcher's CTAs may be scheduled (barriers, TMEM, shared-memory carve-out) while
+  // this grid runs; they wait for its completion (griddepcontrol.wait) before they read what it writes
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");              // (itself launched early behind the features' producer)
   const int q = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
   if (q >= a.b_pad) return;
@@ -292,22 +296,29 @@ match_small_tc_kernel(const MstArgs a) {
     sh->is_last = 0;
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    // the query tile (all K slabs, pre-swizzled by mst_query_kernel) and this CTA's 64 rows of every gallery K slab
-    const int tile = row_base / kTileRows, sub = (row_base % kTileRows) / BNP;
-    mbar_arrive_expect_tx(&sh->full_bar, (uint32_t)(a.n_slabs * (kSlabBytesA + kPieceBytes)));
-    for (int slab = 0; slab < a.n_slabs; ++slab) {
-      bulk_load(sA + (size_t)slab * kSlabBytesA, a.qimg + ((size_t)qt * a.n_slabs + slab) * kSlabBytesA,
-                (uint32_t)kSlabBytesA, &sh->full_bar);
-      bulk_load(sB + (size_t)slab * kPieceBytes,
-                a.img + ((size_t)tile * a.n_slabs + slab) * kTileSlabBytes + (size_t)sub * kPieceBytes,
-                (uint32_t)kPieceBytes, &sh->full_bar);
-    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
                  "r"(64u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // everything up to griddepcontrol.wait overlaps the tail of mst_query_kernel (programmatic dependent launch),
+  // including the loads of this CTA's 64 rows of every gallery K slab (the gallery image is static); after it the
+  // kernel's outputs (query image, |p|, rows of the exact chain) are complete and visible
+  if (tid == 0) {
+    const int tile = row_base / kTileRows, sub = (row_base % kTileRows) / BNP;
+    mbar_arrive_expect_tx(&sh->full_bar, (uint32_t)(a.n_slabs * (kSlabBytesA + kPieceBytes)));
+    for (int slab = 0; slab < a.n_slabs; ++slab)
+      bulk_load(sB + (size_t)slab * kPieceBytes,
+                a.img + ((size_t)tile * a.n_slabs + slab) * kTileSlabBytes + (size_t)sub * kPieceBytes,
+                (uint32_t)kPieceBytes, &sh->full_bar);
+  }
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (tid == 0) {
+    for (int slab = 0; slab < a.n_slabs; ++slab)                 // the query tile, pre-swizzled by mst_query_kernel
+      bulk_load(sA + (size_t)slab * kSlabBytesA, a.qimg + ((size_t)qt * a.n_slabs + slab) * kSlabBytesA,
+                (uint32_t)kSlabBytesA, &sh->full_bar);
   }
   tc_fence_before();
   __syncthreads();
@@ -605,7 +616,7 @@ int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, in
   qa.pn = reinterpret_cast<double*>(w + L.pn);
   qa.pe = reinterpret_cast<double*>(w + L.phat);
   qa.lde = k | 1;
-  EF_LAUNCH(mst_query_kernel, (unsigned)ceil_div((int64_t)a.b_pad * 32, 256), 256, 0, stream, qa);
+  EF_LAUNCH_PDL(mst_query_kernel, (unsigned)ceil_div((int64_t)a.b_pad * 32, 256), 256, 0, stream, qa);
 
   // float64 staging area of the exact chain (reuses the operand tiles): all of k when (128 + 64) rows fit 200 KB
   // staging area of the exact chain (reuses the operand tiles): the gallery piece + as many query rows as fit 200 KB.
@@ -627,7 +638,7 @@ int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, in
     if (!trace_buf) EF_CUDA(cudaMalloc(&trace_buf, sizeof(long long) * 8 * 65536));
     if (n_cta <= 65536) a.trace = trace_buf;
   }
-  EF_LAUNCH(match_small_tc_kernel, grid, kThreads, smem, stream, a);
+  EF_LAUNCH_PDL(match_small_tc_kernel, grid, kThreads, smem, stream, a);
   if (a.trace) {
     EF_CUDA(cudaStreamSynchronize(stream));
     std::vector<long long> h(n_cta * 8);

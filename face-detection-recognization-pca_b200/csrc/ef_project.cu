@@ -186,6 +186,7 @@ __global__ void __launch_bounds__(256, 2)
 rowsumsq_weighted_kernel(const uint8_t* __restrict__ X, int64_t ldx, int B, int D, const double* __restrict__ qq,
                          double* __restrict__ out) {
   __shared__ double part[kRowsW][8];
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // finalize_slabs_kernel may be scheduled behind it
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int row0 = blockIdx.x * kRowsW;
   for (int base = 0; base < D; base += 4096) {

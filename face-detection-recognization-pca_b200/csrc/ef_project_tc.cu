@@ -78,6 +78,9 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
     if (threadIdx.x == 0) atomicExch(a.status, 2);
     return;
   }
+  // the kernel that consumes the partial tiles (finalize_slabs_kernel) may be scheduled while this one runs: its CTAs
+  // wait for this grid's completion before they read (programmatic dependent launch)
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int b_stage_bytes = a.block_n * BLOCK_K;
   uint8_t* sA = smem;
   uint8_t* sB = smem + (size_t)a.stages * A_STAGE_BYTES;
