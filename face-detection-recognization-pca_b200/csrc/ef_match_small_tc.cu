@@ -38,10 +38,9 @@ namespace {
 using namespace ef_tc;
 
 constexpr int kThreads = 192;               // warp 0 bulk loads, warp 1 MMA + TMEM, warps 2..5 scan and re-score
-constexpr int BNP = 64;                     // gallery rows per CTA
+constexpr int BNP = 64;                     // smallest piece of gallery rows per CTA (64, 128 or 256: MstArgs::bnp)
 constexpr int kSlab = 64;                   // halfs of K per slab = one 128-byte swizzle row
 constexpr int kSlabBytesA = BLOCK_M * 128;  // 16 KB
-constexpr int kPieceBytes = BNP * 128;      // 8 KB: 64 rows of one slab
 constexpr int kTileRows = 256;              // rows per tile of the ef_match_tc image
 constexpr int kTileSlabBytes = kTileRows * 128;
 constexpr int kMaxSlabs = 9;                // 3 (k + 1) <= 576
@@ -65,6 +64,7 @@ struct MstArgs {
   int32_t* out_index;
   int32_t* out_label;            // nullable
   int sh_off;                    // byte offset of MstShared behind the operand tiles / the staging area
+  int bnp;                       // gallery rows per CTA = UMMA N = TMEM columns
   int pieces, b_pad, rows_round, bulk;   // staged float64 rows: query rows per round; bulk copies possible
   double* part_s;                // [pieces][b_pad]
   int* part_i;                   // [pieces][b_pad]
@@ -280,11 +280,12 @@ match_small_tc_kernel(const MstArgs a) {
     return;
   }
   uint8_t* sA = smem;                                            // [n_slabs][128 rows][128 B]
-  uint8_t* sB = smem + (size_t)a.n_slabs * kSlabBytesA;          // [n_slabs][64 rows][128 B]
+  uint8_t* sB = smem + (size_t)a.n_slabs * kSlabBytesA;          // [n_slabs][bnp rows][128 B]
+  const int kPieceBytes = a.bnp * 128;
   MstShared* sh = reinterpret_cast<MstShared*>(smem + a.sh_off);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x, piece = blockIdx.y;
-  const int row_base = piece * BNP;
+  const int row_base = piece * a.bnp;
   long long* tr = a.trace ? a.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
 #define MST_STAMP(i) if (tr && threadIdx.x == 64) tr[i] = clock64()
   MST_STAMP(0);
@@ -299,7 +300,7 @@ match_small_tc_kernel(const MstArgs a) {
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sh->tmem_base)),
-                 "r"(64u)
+                 "r"((uint32_t)a.bnp)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -307,11 +308,11 @@ match_small_tc_kernel(const MstArgs a) {
   // including the loads of this CTA's 64 rows of every gallery K slab (the gallery image is static); after it the
   // kernel's outputs (query image, |p|, rows of the exact chain) are complete and visible
   if (tid == 0) {
-    const int tile = row_base / kTileRows, sub = (row_base % kTileRows) / BNP;
+    const int tile = row_base / kTileRows, sub_bytes = (row_base % kTileRows) * 128;
     mbar_arrive_expect_tx(&sh->full_bar, (uint32_t)(a.n_slabs * (kSlabBytesA + kPieceBytes)));
     for (int slab = 0; slab < a.n_slabs; ++slab)
       bulk_load(sB + (size_t)slab * kPieceBytes,
-                a.img + ((size_t)tile * a.n_slabs + slab) * kTileSlabBytes + (size_t)sub * kPieceBytes,
+                a.img + ((size_t)tile * a.n_slabs + slab) * kTileSlabBytes + (size_t)sub_bytes,
                 (uint32_t)kPieceBytes, &sh->full_bar);
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
@@ -328,7 +329,7 @@ match_small_tc_kernel(const MstArgs a) {
 
   if (warp == 1 && lane == 0 && mbar_wait(&sh->full_bar, 0, failed)) {
     tc_fence_after();
-    const uint32_t idesc = umma_idesc_f16(BNP);
+    const uint32_t idesc = umma_idesc_f16(a.bnp);
     for (int slab = 0; slab < a.n_slabs; ++slab) {
       const uint32_t a_addr = smem_u32(sA + (size_t)slab * kSlabBytesA);
       const uint32_t b_addr = smem_u32(sB + (size_t)slab * kPieceBytes);
@@ -347,40 +348,49 @@ match_small_tc_kernel(const MstArgs a) {
   const int r = lane_group * 32 + lane;
   const int q = qt * BLOCK_M + r;                                 // a scanning thread's query
   const bool live = scanning && q < a.B;
-  const int valid = min(BNP, a.n - row_base);
+  const int valid = min(a.bnp, a.n - row_base);
   MST_STAMP(1);
   const bool ok = __syncthreads_and(mbar_wait(&sh->tmem_full_bar, 0, failed)) != 0;
   MST_STAMP(2);
   double best = (a.metric == EF_METRIC_L2) ? CUDART_INF : -CUDART_INF;
   int best_i = INT_MAX;
-  unsigned long long mask = 0ull;
+  unsigned mask[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};            // candidate rows of this thread's query, 32 per word
+  const int groups = a.bnp >> 5;
   if (ok && scanning) {
     tc_fence_after();
-    uint32_t v0[32], v1[32];
-    tmem_ld32(tmem_base + ((uint32_t)(lane_group * 32) << 16), v0);
-    tmem_ld32(tmem_base + ((uint32_t)(lane_group * 32) << 16) + 32u, v1);
+    const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
+    // pass 1: the approximate maximum over the piece (four independent chains)
     float m0 = -CUDART_INF_F, m1 = -CUDART_INF_F, m2 = -CUDART_INF_F, m3 = -CUDART_INF_F;
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-      if (i < valid) m0 = fmaxf(m0, __uint_as_float(v0[i]));
-      if (i + 1 < valid) m1 = fmaxf(m1, __uint_as_float(v0[i + 1]));
-      if (i + 2 < valid) m2 = fmaxf(m2, __uint_as_float(v0[i + 2]));
-      if (i + 3 < valid) m3 = fmaxf(m3, __uint_as_float(v0[i + 3]));
-      if (i + 32 < valid) m0 = fmaxf(m0, __uint_as_float(v1[i]));
-      if (i + 33 < valid) m1 = fmaxf(m1, __uint_as_float(v1[i + 1]));
-      if (i + 34 < valid) m2 = fmaxf(m2, __uint_as_float(v1[i + 2]));
-      if (i + 35 < valid) m3 = fmaxf(m3, __uint_as_float(v1[i + 3]));
+    for (int g = 0; g < 8; ++g) {
+      if (g < groups && g * 32 < valid) {                          // warp uniform
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(g * 32), v);
+        const int vg = valid - g * 32;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+          if (i < vg) m0 = fmaxf(m0, __uint_as_float(v[i]));
+          if (i + 1 < vg) m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+          if (i + 2 < vg) m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+          if (i + 3 < vg) m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+        }
+      }
     }
     const float thr = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) - 2.f * a.eps;
-    unsigned lo = 0u, hi = 0u;
+    // pass 2: the rows inside the band (the accumulator is read again: 16 cycles per 32 columns)
 #pragma unroll
-    for (int i = 0; i < 32; ++i) {
-      lo |= (__uint_as_float(v0[i]) >= thr ? 1u : 0u) << i;
-      hi |= (__uint_as_float(v1[i]) >= thr ? 1u : 0u) << i;
+    for (int g = 0; g < 8; ++g) {
+      if (g < groups && g * 32 < valid) {
+        uint32_t v[32];
+        tmem_ld32(taddr + (uint32_t)(g * 32), v);
+        unsigned mk = 0u;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mk |= (__uint_as_float(v[i]) >= thr ? 1u : 0u) << i;
+        const int vg = valid - g * 32;
+        if (vg < 32) mk &= (1u << vg) - 1u;
+        mask[g] = live ? mk : 0u;
+      }
     }
-    mask = ((unsigned long long)hi << 32) | lo;
-    if (valid < 64) mask &= (1ull << valid) - 1ull;
-    if (!live) mask = 0ull;
   }
   MST_STAMP(3);
   if (ok) {
@@ -394,8 +404,11 @@ match_small_tc_kernel(const MstArgs a) {
     // copy each; when 128 query rows do not fit next to the piece they come in rounds of 64 / 32 rows.  (One bulk copy
     // per row costs ~60 cycles of issue each: 192 copies = 10.8 k cycles at k = 50 -- EF_MST_TRACE.)
     double* Gs = reinterpret_cast<double*>(smem);
-    double* Ps = Gs + (((size_t)BNP * a.k + 1) & ~(size_t)1);
-    const int first = mask ? __ffsll((long long)mask) - 1 : -1;
+    double* Ps = Gs + (((size_t)a.bnp * a.k + 1) & ~(size_t)1);
+    int first = -1;
+#pragma unroll
+    for (int g = 7; g >= 0; --g)
+      if (mask[g]) first = g * 32 + __ffs((int)mask[g]) - 1;
     const int rows_q = min(BLOCK_M, a.B - qt * BLOCK_M);
     // the norms of the quotient: requested before the staging so that they are there when the chain ends
     const double pn = first >= 0 ? a.pn[q] : 1.0;
@@ -455,16 +468,20 @@ match_small_tc_kernel(const MstArgs a) {
       if (a.metric == EF_METRIC_COSINE_G1) s = (pn == 0.0 || gn_first == 0.0) ? 0.0 : acc / (pn * gn_first);
       best = s;
       best_i = j;
-      mask &= mask - 1ull;
       // further rows inside the band (duplicates, near-duplicates, an all-zero query): straight from global memory
       const double* __restrict__ p = a.Pe + (int64_t)q * a.lde;
-      while (mask) {                                               // ascending rows: the first best wins
-        const int i = __ffsll((long long)mask) - 1;
-        mask &= mask - 1ull;
-        const double s2 = exact_score(a, p, pn, row_base + i);
-        if (better(a.metric, s2, row_base + i, best, best_i)) {
-          best = s2;
-          best_i = row_base + i;
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        unsigned mk = mask[g];
+        if (g == (first >> 5)) mk &= mk - 1u;                      // (the first candidate is the lowest bit set)
+        while (mk) {                                               // ascending rows: the first best wins
+          const int i = g * 32 + __ffs((int)mk) - 1;
+          mk &= mk - 1u;
+          const double s2 = exact_score(a, p, pn, row_base + i);
+          if (better(a.metric, s2, row_base + i, best, best_i)) {
+            best = s2;
+            best_i = row_base + i;
+          }
         }
       }
     }
@@ -518,7 +535,7 @@ match_small_tc_kernel(const MstArgs a) {
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(64u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)a.bnp) : "memory");
   }
   if (tid == 0 && sh->failed) atomicExch(a.status, 1);
 }
@@ -589,7 +606,6 @@ int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, in
   a.G = gp; a.ldg = ldgp; a.gnorm = gnorm; a.n = (int)n;
   a.labels = labels; a.threshold = threshold;
   a.out_score = out_score; a.out_index = out_index; a.out_label = out_label;
-  a.pieces = (int)ceil_div(n, BNP);
   a.b_pad = (int)round_up(B, BLOCK_M);
   a.counters = reinterpret_cast<unsigned int*>(w + L.counters);
   a.part_s = reinterpret_cast<double*>(w + L.part_s);
@@ -619,18 +635,35 @@ int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, in
   EF_LAUNCH_PDL(mst_query_kernel, (unsigned)ceil_div((int64_t)a.b_pad * 32, 256), 256, 0, stream, qa);
 
   // float64 staging area of the exact chain (reuses the operand tiles): all of k when (128 + 64) rows fit 200 KB
-  // staging area of the exact chain (reuses the operand tiles): the gallery piece + as many query rows as fit 200 KB.
-  // Bulk copies need 16-byte aligned blocks of a multiple of 16 bytes: k even and a packed gallery (ldgp == k)
+  // Bulk copies of the float64 rows need 16-byte aligned blocks of a multiple of 16 bytes: k even, a packed gallery
   a.bulk = (k % 2 == 0) && ldgp == k && ((reinterpret_cast<uintptr_t>(gp) & 15) == 0) && !getenv("EF_MST_NO_BULK");
-  const size_t g_bytes = (((size_t)BNP * k + 1) & ~(size_t)1) * sizeof(double);
-  a.rows_round = BLOCK_M;
-  while (a.rows_round > 8 && g_bytes + (size_t)a.rows_round * a.lde * sizeof(double) > 200 * 1024) a.rows_round /= 2;
-  const size_t operands = (size_t)a.n_slabs * (kSlabBytesA + kPieceBytes);
-  const size_t staging = g_bytes + (size_t)a.rows_round * a.lde * sizeof(double);
+  // Gallery rows per CTA: the smallest piece whose grid is one wave of resident CTAs (more, smaller pieces = more SMs at
+  // work), else the largest that fits shared memory (fewer pieces = fewer redundant copies of the query rows, fewer
+  // exact chains).  Shared memory holds the operand tiles, then (reusing them) the float64 rows of the exact chain:
+  // the gallery piece + as many query rows as fit.
+  const int q_tiles = a.b_pad / BLOCK_M;
+  size_t operands = 0, staging = 0;
+  a.bnp = 0;
+  int forced = 0;
+  if (const char* e = getenv("EF_MST_BNP")) forced = atoi(e);
+  for (int bnp : {64, 128, 256}) {
+    const size_t ops = (size_t)a.n_slabs * (kSlabBytesA + (size_t)bnp * 128);
+    const size_t g_bytes = (((size_t)bnp * k + 1) & ~(size_t)1) * sizeof(double);
+    int rows = BLOCK_M;
+    while (rows > 8 && g_bytes + (size_t)rows * a.lde * sizeof(double) > 200 * 1024) rows /= 2;
+    const size_t stg = g_bytes + (size_t)rows * a.lde * sizeof(double);
+    if (std::max(ops, stg) > 216 * 1024) break;
+    a.bnp = bnp; a.rows_round = rows; operands = ops; staging = stg;
+    if (forced == bnp) break;
+    const int64_t occ = std::max<int64_t>(1, std::min<int64_t>(512 / bnp, (220 * 1024) / (int64_t)(std::max(ops, stg) + 2048)));
+    if (!forced && (int64_t)q_tiles * ceil_div(n, bnp) <= (int64_t)sm_count() * occ) break;
+  }
+  if (!a.bnp) return EF_ERR_UNSUPPORTED;
+  a.pieces = (int)ceil_div(n, a.bnp);
   const size_t smem = std::max(operands, (staging + 15) & ~(size_t)15) + sizeof(MstShared) + 64;
   a.sh_off = (int)std::max(operands, (staging + 15) & ~(size_t)15);
   EF_ENSURE_SMEM(match_small_tc_kernel, smem);
-  const dim3 grid((unsigned)(a.b_pad / BLOCK_M), (unsigned)a.pieces);
+  const dim3 grid((unsigned)q_tiles, (unsigned)a.pieces);
   static long long* trace_buf = nullptr;
   const bool trace = getenv("EF_MST_TRACE") != nullptr;
   const size_t n_cta = (size_t)grid.x * grid.y;

@@ -526,22 +526,24 @@ def test_tensor_core_small_matcher_equals_float64_kernels(metric):
         rec = ef.Recognizer(E, mean, G, metric=metric, labels=rng.integers(0, 9, n), **kw)
         thr = 0.1 if metric != ef.METRIC_L2 else 1e12
         outs = []
-        for env in (None, "EF_NO_MATCH_SMALL_TC", "EF_NO_MATCH_SMALL", "EF_MST_FUSED_FINALIZE", "EF_MST_NO_BULK"):
-            if env:
-                os.environ[env] = "1"
+        variants = [{}, {"EF_NO_MATCH_SMALL_TC": "1"}, {"EF_NO_MATCH_SMALL": "1"}, {"EF_MST_FUSED_FINALIZE": "1"},
+                    {"EF_MST_NO_BULK": "1"}, {"EF_MST_BNP": "64"}, {"EF_MST_BNP": "128"}, {"EF_MST_BNP": "256"},
+                    {"EF_NO_PDL": "1"}]
+        for env in variants:
+            os.environ.update(env)
             try:
                 l0 = ef.launch_count()
                 outs.append((rec.recognize(X, thr), ef.launch_count() - l0))
             finally:
-                if env:
-                    os.environ.pop(env, None)
-        (a, la), (b, lb), (c, lc), (d, ld), (e, le) = outs
-        assert la <= lc and lb <= lc                          # (two launches: query operand + filter / re-score)
-        for f in ("features", "score", "index", "label", "resid2"):
-            assert np.array_equal(getattr(a, f), getattr(b, f)), (D, k, n, B, metric, f, "tc vs float64 one-launch")
-            assert np.array_equal(getattr(a, f), getattr(c, f)), (D, k, n, B, metric, f, "tc vs generic chain")
-            assert np.array_equal(getattr(a, f), getattr(d, f)), (D, k, n, B, metric, f, "features formed by the query kernel")
-            assert np.array_equal(getattr(a, f), getattr(e, f)), (D, k, n, B, metric, f, "rows staged by cp.async")
+                for name in env:
+                    os.environ.pop(name, None)
+        a, la = outs[0]
+        assert la <= outs[2][1] and outs[1][1] <= outs[2][1]     # (two launches: query operand + filter / re-score)
+        what = ["", "float64 one-launch kernel", "generic chain", "features formed by the query kernel",
+                "rows staged by cp.async", "64-row pieces", "128-row pieces", "256-row pieces", "no dependent launches"]
+        for (o, _), w in zip(outs[1:], what[1:]):
+            for f in ("features", "score", "index", "label", "resid2"):
+                assert np.array_equal(getattr(a, f), getattr(o, f)), (D, k, n, B, metric, f, "tc vs " + w)
         # a shorter batch after a longer one through the same scratch buffers (layout by capacity, stale rows zeroed)
         for b in (1, 3, 130):
             if b < B:
