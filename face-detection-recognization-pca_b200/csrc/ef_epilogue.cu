@@ -306,6 +306,29 @@ finalize_slabs_kernel(const int32_t* __restrict__ part, int splits, long long sl
   else if (xu_out) xu_out[b] = v;                                      // the residual column x . u~
 }
 
+// The same for COMBINED slabs (project_tc with combine: long long part[split][crop][ld_part / 4], component c at
+// [2c] = hi, [2c + 1] = lo): the pairs of the splits add exactly, one rounding in hilo_to_double -- the same value.
+__global__ void __launch_bounds__(256)
+finalize_slabs_hilo_kernel(const long long* __restrict__ part, int splits, long long slab_stride, int ld64, int B, int k,
+                           int kq, const int32_t* __restrict__ col_exp, const double* __restrict__ bias,
+                           double* __restrict__ proj, int64_t ldp, double* __restrict__ xu_out) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = (int)(idx / (unsigned)kq);
+  const int c = (int)(idx - (unsigned)b * (unsigned)kq);
+  if (b >= B) return;
+  long long hi = 0, lo = 0;
+  for (int sp = 0; sp < splits; ++sp) {
+    const longlong2 v = __ldcg(reinterpret_cast<const longlong2*>(part + (size_t)sp * slab_stride + (size_t)b * ld64) + c);
+    hi += v.x;
+    lo += v.y;
+  }
+  double v = ldexp(ef::hilo_to_double(hi, lo), col_exp[c]);
+  if (c < k) proj[(size_t)b * ldp + c] = v - bias[c];
+  else if (xu_out) xu_out[b] = v;
+}
+
 template <int METRIC, int KR>
 int launch_fused(EpiArgs& a, cudaStream_t stream) {
   // gallery tile: as many rows as fit (the whole gallery for the shipped sizes), multiple of 4
@@ -365,10 +388,17 @@ int fused_epilogue(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, cons
 
 int project_finalize_slabs(const int32_t* part, int splits, int ld_part, int B, int k, int kq, int S,
                            const int32_t* col_exp, const double* bias, double* proj, int64_t ldp, double* resid2,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, bool combined) {
   if (B <= 0) return EF_OK;
   if (S > 8 || (int64_t)B * kq >= (1ll << 31) - 256) return EF_ERR_INVALID;
   const unsigned grid = (unsigned)ceil_div((int64_t)B * kq, 256);
+  if (combined) {
+    if (S != 8 || (ld_part & 3)) return EF_ERR_INVALID;
+    EF_LAUNCH_PDL(finalize_slabs_hilo_kernel, grid, 256, 0, stream, reinterpret_cast<const long long*>(part), splits,
+                  (long long)B * (ld_part / 4), ld_part / 4, B, k, kq, col_exp, bias, proj, (int64_t)ldp,
+                  (kq > k) ? resid2 : (double*)nullptr);
+    return EF_OK;
+  }
   EF_LAUNCH_PDL(finalize_slabs_kernel, grid, 256, 0, stream, part, splits, (long long)B * ld_part, ld_part, B, k, kq, S,
                 col_exp, bias, proj, (int64_t)ldp, (kq > k) ? resid2 : (double*)nullptr);
   return EF_OK;

@@ -40,8 +40,11 @@ int row_sumsq(const uint8_t* X, int64_t ldx, int B, int D, const double* qq, dou
 // part == null: stream-K schedule, partial tiles merged into acc_t with int32 RED atomics.
 // part != null: split-K schedule, partial tiles STORED row-major as part[split][crop][ld_part] (shape from
 // project_tc_split_shape, bytes from project_tc_part_bytes); acc_t is not touched; project_finalize_slabs consumes it.
+// combine (S = 8, Wq FEATURE-major: plane s of component c in row c * 8 + s): the slabs hold the exact (hi, lo) int64 pair
+// of every component instead of its eight int32 planes (half the bytes): long long [split][crop][ld_part / 4].
 int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int wq_rows,
-               int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream, int32_t* part = nullptr);
+               int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream, int32_t* part = nullptr,
+               bool combine = false);
 void project_tc_split_shape(int B, int D, int NC, int* splits, int* ld_part);
 size_t project_tc_part_bytes(int B, int D, int NC);
 
@@ -110,7 +113,7 @@ int project_finalize(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, co
 // split-K slabs of project_tc -> float64 features (and x . u~ into resid2 when kq > k); nothing to clear
 int project_finalize_slabs(const int32_t* part, int splits, int ld_part, int B, int k, int kq, int S,
                            const int32_t* col_exp, const double* bias, double* proj, int64_t ldp, double* resid2,
-                           cudaStream_t stream);
+                           cudaStream_t stream, bool combined = false);
 
 int project_resid(const double* proj, int64_t ldp, int B, int k, double* sumsq, double c0, double* resid2,
                   cudaStream_t stream);

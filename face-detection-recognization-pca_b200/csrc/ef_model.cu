@@ -441,9 +441,14 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
   int st_tc = EF_ERR_UNSUPPORTED;
   // k > 32: split-K slabs (plain stores, no accumulator invariants) instead of stream-K + int32 RED atomics
   int32_t* part = (m->part.p && !getenv("EF_NO_SLABS")) ? m->part.as<int32_t>() : nullptr;
+  // ... holding, for S = 8, the (hi, lo) int64 pair of every component instead of its eight int32 planes: the
+  // feature-major basis puts the planes of a component into adjacent accumulator columns (half the slab bytes)
+  const bool combine = part && m->S == 8 && m->NC == 8 * m->kq && m->nc_fm >= m->NC && !getenv("EF_NO_SLAB_COMBINE");
   if (m->tc_mode >= 1)
-    st_tc = ef::project_tc(x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, m->nc_pad, acc, m->ld_acc,
-                           tc_sumsq ? sumsq : nullptr, m->status.as<int>(), st, part);
+    st_tc = combine ? ef::project_tc(x, ldx, B, m->D, m->wq_fm.as<int8_t>(), m->ldw, m->NC, m->nc_fm, acc, m->ld_acc,
+                                     tc_sumsq ? sumsq : nullptr, m->status.as<int>(), st, part, true)
+                    : ef::project_tc(x, ldx, B, m->D, m->wq.as<int8_t>(), m->ldw, m->NC, m->nc_pad, acc, m->ld_acc,
+                                     tc_sumsq ? sumsq : nullptr, m->status.as<int>(), st, part);
   m->last_used_tc = st_tc == EF_OK;
   m->last_path = m->last_used_tc ? 1 : 0;
   if (st_tc != EF_OK) {
@@ -476,7 +481,7 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
     if (m->last_used_tc && part) {
       int splits = 1, ld_part = 0;
       ef::project_tc_split_shape(B, m->D, m->NC, &splits, &ld_part);
-      if (small_tc && m->S <= 8 && getenv("EF_MST_FUSED_FINALIZE")) {
+      if (small_tc && m->S <= 8 && !combine && getenv("EF_MST_FUSED_FINALIZE")) {
         // the matcher's query kernel can form the features from the slabs itself (one launch less).  Opt-in: measured
         // SLOWER -- a warp per crop walks splits x planes loads per column in sequence: 15.6 us against 6.2 + 3.8 us
         // for finalize_slabs_kernel (a thread per column) + the query kernel at k = 50
@@ -484,7 +489,8 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
         fused_finalize = true;
       } else {
         EF_TRY(ef::project_finalize_slabs(part, splits, ld_part, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(),
-                                          m->bias.as<double>(), proj, m->k, want_resid ? out->resid2 : nullptr, st));
+                                          m->bias.as<double>(), proj, m->k, want_resid ? out->resid2 : nullptr, st,
+                                          combine));
         if (!small && want_resid)
           EF_TRY(ef::project_resid(proj, m->k, B, m->k, sumsq, m->c0, out->resid2, st));
       }

@@ -40,6 +40,10 @@ struct Args {
   // STORED row-major into slab `split` (part[split][row][ld_part]) -- no atomics, no zero-initialised accumulators
   int32_t* part;
   int splits, ld_part;
+  // combine != 0 (feature-major basis: the eight digit planes of a component in adjacent columns): the epilogue folds
+  // them into the exact (hi, lo) int64 pair of ef::planes_to_hilo before the store -- 16 bytes per component instead of
+  // 32, in slabs of long long [split][row][ld_part / 4]
+  int combine;
   long long slab_stride;
   // split-K mode with mcast > 1: clusters of `mcast` consecutive crop tiles of the same (column tile, K range) share the
   // basis tile -- every CTA fetches 1/mcast of it and TMA-multicasts that part into the shared memory of all of them
@@ -252,7 +256,23 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       for (int c0 = 0; c0 < a.block_n; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)c0, v);
-        if (a.part) {
+        if (a.part && a.combine) {
+          if (row < a.B) {
+            int32_t pl[8];
+            long long h0, l0, h1, l1;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pl[j] = (int32_t)v[j];
+            ef::planes_to_hilo(pl, h0, l0);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) pl[j] = (int32_t)v[8 + j];
+            ef::planes_to_hilo(pl, h1, l1);
+            longlong2* dst = reinterpret_cast<longlong2*>(
+                reinterpret_cast<long long*>(a.part) + ((size_t)split * a.slab_stride + (size_t)row * a.ld_part) / 4 +
+                (size_t)((n_tile * a.block_n + c0) >> 2));
+            __stcg(dst, make_longlong2(h0, l0));
+            __stcg(dst + 1, make_longlong2(h1, l1));
+          }
+        } else if (a.part) {
           if (row < a.B) {
             uint4* dst = reinterpret_cast<uint4*>(a.part + (size_t)split * a.slab_stride + (size_t)row * a.ld_part +
                                                   n_tile * a.block_n + c0);
@@ -376,8 +396,10 @@ size_t project_tc_part_bytes(int B, int D, int NC) {
 }
 
 int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int wq_rows,
-               int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream, int32_t* part) {
+               int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream, int32_t* part,
+               bool combine) {
   if (B <= 0) return EF_OK;
+  if (combine && !part) return EF_ERR_INVALID;
   if ((ldx & 15) || (reinterpret_cast<uintptr_t>(X) & 15) || (ldw & 15) || (reinterpret_cast<uintptr_t>(Wq) & 15))
     return EF_ERR_UNSUPPORTED;
   if (!encode_fn()) return EF_ERR_UNSUPPORTED;
@@ -403,6 +425,7 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
   a.ld_acc = ld_acc;
   a.acc_t = acc_t;
   a.part = part;
+  a.combine = combine ? 1 : 0;
   a.mcast = 1;
   if (part) {
     split_shape(B, D, NC, &a.splits, &a.ld_part, &a.mcast, &a.m_tiles_pad);
@@ -421,11 +444,7 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
   if (!make_map(&mw, Wq, (uint64_t)ldw, (uint64_t)wq_rows, (uint64_t)ldw, (uint32_t)a.box_rows)) return EF_ERR_UNSUPPORTED;
 
   const size_t smem = (size_t)a.stages * stage_bytes + sizeof(Shared) + 1024;
-  static size_t attr_smem = 0;
-  if (smem > attr_smem) {
-    EF_CUDA(cudaFuncSetAttribute(project_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_smem = smem;
-  }
+  EF_ENSURE_SMEM(project_tc_kernel, smem);
   const long long total_units = (long long)a.n_tiles * a.m_tiles * a.kb_total;
   int grid = sm_count();
   if (const char* e = getenv("EF_TC_GRID")) { const int v = atoi(e); if (v >= 1) grid = v; }
