@@ -146,11 +146,12 @@ size_t match_small_tc_image_bytes(int k, int64_t n, int metric);
 int match_small_tc_image(const double* gp, int64_t ldgp, const double* gnorm, int64_t n, int k, int metric, void* image,
                          cudaStream_t stream);
 size_t match_small_tc_work_bytes(int cap_B, int64_t n, int k, int metric);
-// slabs != null: proj is an OUTPUT -- the query kernel forms the features from the split-K slabs of project_tc itself
-// (what project_finalize_slabs does, one launch less) and leaves x . u~ in resid2 before the residual pass.
+// slabs != null: proj is an OUTPUT -- the query kernel forms the features from the COMBINED split-K slabs of project_tc
+// itself (what project_finalize_slabs does, one launch less) and leaves x . u~ in resid2 before the residual pass.
 struct MatchSmallTcSlabs {
   const int32_t* part;
   int splits, ld_part, kq, S;
+  bool combined;
   const int32_t* col_exp;
   const double* bias;
 };

@@ -153,11 +153,11 @@ __device__ __forceinline__ double exact_score(const MstArgs& a, const double* __
 // B .. b_pad of the last tile are written as zeros (a shorter batch after a longer one); the K padding of the image is
 // zero from the reservation and never written.
 struct MstQueryArgs {
-  // split-K slabs of the projection (part != null): the kernel first forms the float64 features itself -- the work of
-  // finalize_slabs_kernel (ef_epilogue.cu: integer sum over the splits, then the same float64 combination), one warp
-  // per crop -- and writes them to P
-  const int32_t* part;
-  int splits, ld_part, kq, S;
+  // COMBINED split-K slabs of the projection (part != null; long long [split][crop][ld_part], component c at [2c] = hi,
+  // [2c + 1] = lo): the kernel first forms the float64 features itself -- the work of finalize_slabs_hilo_kernel
+  // (ef_epilogue.cu: exact sum of the pairs over the splits, one rounding), one warp per crop -- and writes them to P
+  const long long* part;
+  int splits, ld_part, kq;
   long long slab_stride;
   const int32_t* col_exp;
   const double* bias;
@@ -195,16 +195,14 @@ mst_query_kernel(const MstQueryArgs a) {
       const int c = lane + 32 * i;
       double v = 0.0;
       if (live && c < a.kq) {
-        int32_t plane[8];
-#pragma unroll
-        for (int sl = 0; sl < 8; ++sl) plane[sl] = 0;
+        long long hi = 0, lo = 0;
         for (int sp = 0; sp < a.splits; ++sp) {
-          const int32_t* src = a.part + (size_t)sp * a.slab_stride + (size_t)q * a.ld_part + c;
-#pragma unroll
-          for (int sl = 0; sl < 8; ++sl)
-            if (sl < a.S) plane[sl] += __ldcg(src + sl * a.kq);
+          const longlong2 t = __ldcg(reinterpret_cast<const longlong2*>(a.part + (size_t)sp * a.slab_stride +
+                                                                          (size_t)q * a.ld_part) + c);
+          hi += t.x;
+          lo += t.y;
         }
-        v = ldexp(ef::planes_to_double(plane), a.col_exp[c]);
+        v = ldexp(ef::hilo_to_double(hi, lo), a.col_exp[c]);
         if (c < a.k) {
           v = v - a.bias[c];
           p[c] = v;
@@ -593,7 +591,8 @@ int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, in
                    int cap_B, int* status, cudaStream_t stream, const MatchSmallTcSlabs* slabs) {
   if (B <= 0) return EF_OK;
   if (B > cap_B) return EF_ERR_INVALID;
-  if (slabs && (slabs->S > 8 || slabs->kq > 224 || slabs->kq < k)) return EF_ERR_INVALID;
+  if (slabs && (slabs->S != 8 || !slabs->combined || (slabs->ld_part & 3) || slabs->kq > 224 || slabs->kq < k))
+    return EF_ERR_INVALID;
   if (!match_small_tc_supported(k, n, metric) || !image || !work || !status) return EF_ERR_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(work) & 255) return EF_ERR_INVALID;
   const MstLayout L = mst_layout(cap_B, n, k, metric);
@@ -621,8 +620,9 @@ int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, in
 
   MstQueryArgs qa{};
   if (slabs) {
-    qa.part = slabs->part; qa.splits = slabs->splits; qa.ld_part = slabs->ld_part; qa.kq = slabs->kq; qa.S = slabs->S;
-    qa.slab_stride = (long long)B * slabs->ld_part;
+    qa.part = reinterpret_cast<const long long*>(slabs->part); qa.splits = slabs->splits;
+    qa.ld_part = slabs->ld_part / 4; qa.kq = slabs->kq;
+    qa.slab_stride = (long long)B * (slabs->ld_part / 4);
     qa.col_exp = slabs->col_exp; qa.bias = slabs->bias;
   }
   qa.P = proj; qa.ldp = ldp; qa.B = B; qa.b_pad = a.b_pad; qa.k = k; qa.ka = a.ka; qa.n_slabs = a.n_slabs;

@@ -481,11 +481,12 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
     if (m->last_used_tc && part) {
       int splits = 1, ld_part = 0;
       ef::project_tc_split_shape(B, m->D, m->NC, &splits, &ld_part);
-      if (small_tc && m->S <= 8 && !combine && getenv("EF_MST_FUSED_FINALIZE")) {
-        // the matcher's query kernel can form the features from the slabs itself (one launch less).  Opt-in: measured
-        // SLOWER -- a warp per crop walks splits x planes loads per column in sequence: 15.6 us against 6.2 + 3.8 us
-        // for finalize_slabs_kernel (a thread per column) + the query kernel at k = 50
-        slabs = ef::MatchSmallTcSlabs{part, splits, ld_part, m->kq, m->S, m->col_exp.as<int32_t>(), m->bias.as<double>()};
+      if (small_tc && combine && !getenv("EF_MST_NO_FUSED_FINALIZE")) {
+        // the matcher's query kernel forms the features from the (hi, lo) slabs itself: one launch less, the features
+        // stay in its registers.  (With int32 plane slabs -- eight loads per component and split -- a warp per crop was
+        // slower than the thread-per-component finalize: 15.6 us against 6.2 + 3.8.)
+        slabs = ef::MatchSmallTcSlabs{part, splits, ld_part, m->kq, m->S, true, m->col_exp.as<int32_t>(),
+                                      m->bias.as<double>()};
         fused_finalize = true;
       } else {
         EF_TRY(ef::project_finalize_slabs(part, splits, ld_part, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(),

@@ -526,7 +526,7 @@ def test_tensor_core_small_matcher_equals_float64_kernels(metric):
         rec = ef.Recognizer(E, mean, G, metric=metric, labels=rng.integers(0, 9, n), **kw)
         thr = 0.1 if metric != ef.METRIC_L2 else 1e12
         outs = []
-        variants = [{}, {"EF_NO_MATCH_SMALL_TC": "1"}, {"EF_NO_MATCH_SMALL": "1"}, {"EF_MST_FUSED_FINALIZE": "1"},
+        variants = [{}, {"EF_NO_MATCH_SMALL_TC": "1"}, {"EF_NO_MATCH_SMALL": "1"}, {"EF_MST_NO_FUSED_FINALIZE": "1"},
                     {"EF_MST_NO_BULK": "1"}, {"EF_MST_BNP": "64"}, {"EF_MST_BNP": "128"}, {"EF_MST_BNP": "256"},
                     {"EF_NO_PDL": "1"}, {"EF_NO_SLAB_COMBINE": "1"}]
         for env in variants:
@@ -539,7 +539,7 @@ def test_tensor_core_small_matcher_equals_float64_kernels(metric):
                     os.environ.pop(name, None)
         a, la = outs[0]
         assert la <= outs[2][1] and outs[1][1] <= outs[2][1]     # (two launches: query operand + filter / re-score)
-        what = ["", "float64 one-launch kernel", "generic chain", "features formed by the query kernel",
+        what = ["", "float64 one-launch kernel", "generic chain", "features formed by the slab finalize kernel",
                 "rows staged by cp.async", "64-row pieces", "128-row pieces", "256-row pieces", "no dependent launches",
                 "int32 plane slabs"]
         for (o, _), w in zip(outs[1:], what[1:]):
