@@ -33,7 +33,11 @@ __device__ __forceinline__ double planes_to_double(const int32_t (&plane)[8]) {
 // ef_project.cu -- CUDA-core exact-integer projection (reference implementation of the integer semantics)
 int project_dp4a(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, int64_t ldw, int NC, int32_t* acc_t,
                  int ld_acc, cudaStream_t stream);
-int row_sumsq(const uint8_t* X, int64_t ldx, int B, int D, const double* qq, double* out, cudaStream_t stream);
+// overlap: the kernel launched just before on this stream (project_tc: it lets its dependents be scheduled at once) only
+// READS what this one reads and does not touch `out` -- the weighted kernel then runs concurrently with it and waits for
+// it at its end (programmatic dependent launch); never set it behind a kernel that still reads `out`.
+int row_sumsq(const uint8_t* X, int64_t ldx, int B, int D, const double* qq, double* out, cudaStream_t stream,
+              bool overlap = false);
 
 // ef_project_tc.cu -- tcgen05 kind::i8 projection (same integers as project_dp4a); sumsq (may be null) receives
 // += sum_d x^2 per crop.  Returns EF_ERR_UNSUPPORTED when the buffers do not meet the TMA alignment rules.

@@ -458,7 +458,8 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
   if (eb) EF_CUDA(cudaEventRecord(eb, st));
   // 2. residual ingredient not produced by the projection kernel (weighted for the standardised models)
   if (want_resid && !(m->last_used_tc && tc_sumsq))
-    EF_TRY(ef::row_sumsq(x, ldx, B, m->D, m->has_scale ? m->qq.as<double>() : nullptr, sumsq, st));
+    EF_TRY(ef::row_sumsq(x, ldx, B, m->D, m->has_scale ? m->qq.as<double>() : nullptr, sumsq, st,
+                         m->last_used_tc && !getenv("EF_NO_SUMSQ_OVERLAP")));
   if (ef::fused_epilogue_supported(m->k, m->n_gallery)) {
     // 3. one launch: planes -> features (+ residual) -> nearest gallery row -> threshold / label
     EF_TRY(ef::fused_epilogue(acc, m->ld_acc, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(), m->bias.as<double>(),

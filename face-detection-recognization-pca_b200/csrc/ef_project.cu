@@ -239,6 +239,10 @@ rowsumsq_weighted_kernel(const uint8_t* __restrict__ X, int64_t ldx, int B, int 
     for (int w8 = 1; w8 < 8; ++w8) s += part[tid][w8];
     out[row0 + tid] = s;
   }
+  // Launched with programmatic stream serialization behind the projection (row_sumsq(..., overlap)) this grid RUNS
+  // CONCURRENTLY with it -- both only read the crops -- and waits for it here, at its end: a later kernel that waits
+  // for this grid then also has the projection's results.  (A no-op for a normal launch.)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 }
 
 template <int CN>
@@ -279,13 +283,17 @@ int project_dp4a(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, 
   }
 }
 
-int row_sumsq(const uint8_t* X, int64_t ldx, int B, int D, const double* qq, double* out, cudaStream_t stream) {
+int row_sumsq(const uint8_t* X, int64_t ldx, int B, int D, const double* qq, double* out, cudaStream_t stream,
+              bool overlap) {
   if (B <= 0) return EF_OK;
   const int threads = 256;
   const int grid = (int)ceil_div((int64_t)B * 32, threads);
   if (qq && D % 16 == 0 && (ldx & 15) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 &&
       (reinterpret_cast<uintptr_t>(qq) & 15) == 0) {
-    EF_LAUNCH(rowsumsq_weighted_kernel, (unsigned)ceil_div(B, kRowsW), 256, 0, stream, X, ldx, B, D, qq, out);
+    if (overlap)
+      EF_LAUNCH_PDL(rowsumsq_weighted_kernel, (unsigned)ceil_div(B, kRowsW), 256, 0, stream, X, ldx, B, D, qq, out);
+    else
+      EF_LAUNCH(rowsumsq_weighted_kernel, (unsigned)ceil_div(B, kRowsW), 256, 0, stream, X, ldx, B, D, qq, out);
     return EF_OK;
   }
   EF_LAUNCH(rowsumsq_kernel, grid, threads, 0, stream, X, ldx, B, D, qq, out);
