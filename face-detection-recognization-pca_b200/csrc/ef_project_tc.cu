@@ -482,7 +482,9 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
     std::vector<unsigned long long> h(8 * (size_t)(probe_grid + 1));
     EF_CUDA(cudaStreamSynchronize(stream));
     EF_CUDA(cudaMemcpy(h.data(), probe_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    const unsigned long long t0 = h[(size_t)probe_grid * 8];
+    unsigned long long t0 = ~0ull;                       // the first CTA's setup stamp
+    for (int c = 0; c < probe_grid; ++c)
+      if (h[(size_t)c * 8 + 1] && h[(size_t)c * 8 + 1] < t0) t0 = h[(size_t)c * 8 + 1];
     double mx_[6] = {0}, sum_[6] = {0};
     for (int c = 0; c < probe_grid; ++c)
       for (int i = 1; i < 6; ++i) {
