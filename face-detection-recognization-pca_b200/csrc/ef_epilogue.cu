@@ -260,6 +260,8 @@ finalize_combine_kernel(int32_t* __restrict__ acc_t, int ld_acc, int B, int k, i
 __global__ void __launch_bounds__(256)
 finalize_resid_kernel(const double* __restrict__ proj, int64_t ldp, int B, int k, double* __restrict__ sumsq, double c0,
                       double* __restrict__ resid2) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch on both sides
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (b >= B) return;
@@ -408,8 +410,8 @@ int project_finalize_slabs(const int32_t* part, int splits, int ld_part, int B, 
 int project_resid(const double* proj, int64_t ldp, int B, int k, double* sumsq, double c0, double* resid2,
                   cudaStream_t stream) {
   if (B <= 0) return EF_OK;
-  EF_LAUNCH(finalize_resid_kernel, (unsigned)ceil_div((int64_t)B * 32, 256), 256, 0, stream, proj, ldp, B, k, sumsq, c0,
-            resid2);
+  EF_LAUNCH_PDL(finalize_resid_kernel, (unsigned)ceil_div((int64_t)B * 32, 256), 256, 0, stream, proj, (int64_t)ldp, B, k,
+                sumsq, c0, resid2);
   return EF_OK;
 }
 

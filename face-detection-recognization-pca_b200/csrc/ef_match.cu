@@ -178,6 +178,8 @@ __global__ void __launch_bounds__(32)
 match_few_kernel(const double* __restrict__ P, int64_t ldp, int B, int k, const double* __restrict__ G, int64_t ldg,
                  const double* __restrict__ gnorm, int64_t n, int64_t index_base, int rows_per_cta,
                  double* __restrict__ out_score, int64_t* __restrict__ out_index) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch on both sides
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   extern __shared__ double fsm[];
   double* qs = fsm;                                // [B][k] queries (divided by their norm for the sklearn metric)
   const int kp = k | 1;                            // odd row pitch: lanes reading one column of 32 rows hit 32 banks
@@ -267,6 +269,8 @@ match_few_kernel(const double* __restrict__ P, int64_t ldp, int B, int k, const 
 template <int METRIC>
 __global__ void match_reduce_kernel(const double* __restrict__ scores, const int64_t* __restrict__ indices, int R,
                                     int B, double* __restrict__ out_score, int64_t* __restrict__ out_index) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch on both sides
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= B) return;
   double bs = (METRIC == EF_METRIC_L2) ? CUDART_INF : -CUDART_INF;
@@ -304,6 +308,8 @@ __global__ void gallery_prepare_kernel(const double* __restrict__ g, int64_t ldg
 __global__ void label_kernel(const double* __restrict__ score, const int64_t* __restrict__ index, int B,
                              const int32_t* __restrict__ labels, int metric, double threshold,
                              int32_t* __restrict__ out_index, int32_t* __restrict__ out_label) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // programmatic dependent launch on both sides
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= B) return;
   const long long idx = index[q];
@@ -365,10 +371,12 @@ static int match_impl(const double* p, int64_t ldp, int B, int k, const double* 
     double* ws = reinterpret_cast<double*>(work);
     int64_t* wi = reinterpret_cast<int64_t*>(ws + (size_t)ctas * B);
     EF_ENSURE_SMEM(match_few_kernel<METRIC>, smem);
-    EF_LAUNCH(match_few_kernel<METRIC>, (unsigned)ctas, 32, smem, stream, p, ldp, B, k, gp, ldgp, gnorm, n, index_base, rows,
-              ws, wi);
-    EF_LAUNCH(match_reduce_kernel<METRIC>, (unsigned)ceil_div(B, 256), 256, 0, stream, ws, wi, ctas, B, out_score,
-              out_index);
+    // the one-face chain (residual -> few-query match -> reduce -> label) is launch bound: every kernel of it may be
+    // scheduled while its predecessor drains (programmatic dependent launch; each waits before it reads)
+    EF_LAUNCH_PDL(match_few_kernel<METRIC>, (unsigned)ctas, 32, smem, stream, p, ldp, B, k, gp, ldgp, gnorm, n, index_base,
+                  rows, ws, wi);
+    EF_LAUNCH_PDL(match_reduce_kernel<METRIC>, (unsigned)ceil_div(B, 256), 256, 0, stream, (const double*)ws,
+                  (const int64_t*)wi, ctas, B, out_score, out_index);
     return EF_OK;
   }
   const int splits = work ? gallery_splits(B, n) : 1;
@@ -408,8 +416,8 @@ int match(const double* p, int64_t ldp, int B, int k, const double* gp, int64_t 
 int label_lookup(const double* score, const int64_t* index, int B, const int32_t* labels, int metric, double threshold,
                  int32_t* out_index32, int32_t* out_label, cudaStream_t stream) {
   if (B <= 0) return EF_OK;
-  EF_LAUNCH(label_kernel, (unsigned)ceil_div(B, 256), 256, 0, stream, score, index, B, labels, metric, threshold,
-            out_index32, out_label);
+  EF_LAUNCH_PDL(label_kernel, (unsigned)ceil_div(B, 256), 256, 0, stream, score, index, B, labels, metric, threshold,
+                out_index32, out_label);
   return EF_OK;
 }
 
