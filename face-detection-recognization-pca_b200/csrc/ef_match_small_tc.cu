@@ -64,6 +64,8 @@ struct MstArgs {
   int32_t* out_index;
   int32_t* out_label;            // nullable
   int sh_off;                    // byte offset of MstShared behind the operand tiles / the staging area
+  int cluster;                   // the CTAs of a query tile (one per gallery piece) form a thread-block cluster
+  int ex_off;                    // cluster mode: byte offset of the exchange area [pieces][128] (double, then int)
   int bnp;                       // gallery rows per CTA = UMMA N = TMEM columns
   int pieces, b_pad, rows_round, bulk;   // staged float64 rows: query rows per round; bulk copies possible
   double* part_s;                // [pieces][b_pad]
@@ -485,8 +487,33 @@ match_small_tc_kernel(const MstArgs a) {
     }
   }
   MST_STAMP(6);
+  if (a.cluster) {
+    // ---- the per-piece winners meet in the shared memory of the cluster's first CTA (DSMEM stores, one cluster
+    // barrier) instead of global memory + a counter (two fences, an atomic round trip, L2 reads: 4-5 k cycles)
+    const uint32_t rank = cluster_ctarank();
+    double* ex_s = reinterpret_cast<double*>(smem + a.ex_off);
+    int* ex_i = reinterpret_cast<int*>(ex_s + (size_t)a.pieces * BLOCK_M);
+    if (scanning && rank != 0) {
+      st_cluster_u64(map_to_cta(smem_u32(ex_s + (size_t)rank * BLOCK_M + r), 0),
+                     (unsigned long long)__double_as_longlong(best));
+      st_cluster_u32(map_to_cta(smem_u32(ex_i + (size_t)rank * BLOCK_M + r), 0), (uint32_t)best_i);
+    }
+    cluster_arrive();
+    cluster_wait();
+    if (rank != 0) best_i = -2;                                    // the first CTA writes the results
+    else if (live) {
+      for (int pc = 1; pc < a.pieces; ++pc) {
+        const double s = ex_s[(size_t)pc * BLOCK_M + r];
+        const int i = ex_i[(size_t)pc * BLOCK_M + r];
+        if (i != INT_MAX && better(a.metric, s, i, best, best_i)) {
+          best = s;
+          best_i = i;
+        }
+      }
+    }
+  }
   if (scanning) {
-    if (a.pieces > 1) {
+    if (a.pieces > 1 && !a.cluster) {
       if (live) {
         a.part_s[(size_t)piece * a.b_pad + q] = best;
         a.part_i[(size_t)piece * a.b_pad + q] = best_i;
@@ -660,8 +687,15 @@ int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, in
   }
   if (!a.bnp) return EF_ERR_UNSUPPORTED;
   a.pieces = (int)ceil_div(n, a.bnp);
-  const size_t smem = std::max(operands, (staging + 15) & ~(size_t)15) + sizeof(MstShared) + 64;
+  size_t smem = std::max(operands, (staging + 15) & ~(size_t)15) + sizeof(MstShared) + 64;
   a.sh_off = (int)std::max(operands, (staging + 15) & ~(size_t)15);
+  // the CTAs of a query tile as one cluster (portable size, exchange area fits): winners meet through DSMEM
+  const size_t ex_bytes = (size_t)a.pieces * BLOCK_M * (sizeof(double) + sizeof(int));
+  a.cluster = a.pieces > 1 && a.pieces <= 8 && smem + ex_bytes <= (size_t)kSmemLimit && !getenv("EF_MST_NO_CLUSTER");
+  if (a.cluster) {
+    a.ex_off = (int)((smem + 15) & ~(size_t)15);
+    smem = (size_t)a.ex_off + ex_bytes;
+  }
   EF_ENSURE_SMEM(match_small_tc_kernel, smem);
   const dim3 grid((unsigned)q_tiles, (unsigned)a.pieces);
   static long long* trace_buf = nullptr;
@@ -671,7 +705,27 @@ int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, in
     if (!trace_buf) EF_CUDA(cudaMalloc(&trace_buf, sizeof(long long) * 8 * 65536));
     if (n_cta <= 65536) a.trace = trace_buf;
   }
-  EF_LAUNCH_PDL(match_small_tc_kernel, grid, kThreads, smem, stream, a);
+  if (a.cluster) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attrs[2];
+    attrs[0].id = cudaLaunchAttributeClusterDimension;
+    attrs[0].val.clusterDim.x = 1;
+    attrs[0].val.clusterDim.y = (unsigned)a.pieces;
+    attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attrs;
+    cfg.numAttrs = getenv("EF_NO_PDL") ? 1 : 2;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, match_small_tc_kernel, a);
+    ef::g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (e != cudaSuccess) { ef::set_error_detail("match_small_tc_kernel (cluster)", e); return EF_ERR_CUDA; }
+  } else {
+    EF_LAUNCH_PDL(match_small_tc_kernel, grid, kThreads, smem, stream, a);
+  }
   if (a.trace) {
     EF_CUDA(cudaStreamSynchronize(stream));
     std::vector<long long> h(n_cta * 8);

@@ -528,7 +528,7 @@ def test_tensor_core_small_matcher_equals_float64_kernels(metric):
         outs = []
         variants = [{}, {"EF_NO_MATCH_SMALL_TC": "1"}, {"EF_NO_MATCH_SMALL": "1"}, {"EF_MST_NO_FUSED_FINALIZE": "1"},
                     {"EF_MST_NO_BULK": "1"}, {"EF_MST_BNP": "64"}, {"EF_MST_BNP": "128"}, {"EF_MST_BNP": "256"},
-                    {"EF_NO_PDL": "1"}, {"EF_NO_SLAB_COMBINE": "1"}]
+                    {"EF_NO_PDL": "1"}, {"EF_NO_SLAB_COMBINE": "1"}, {"EF_MST_NO_CLUSTER": "1"}]
         for env in variants:
             os.environ.update(env)
             try:
@@ -541,7 +541,7 @@ def test_tensor_core_small_matcher_equals_float64_kernels(metric):
         assert la <= outs[2][1] and outs[1][1] <= outs[2][1]     # (two launches: query operand + filter / re-score)
         what = ["", "float64 one-launch kernel", "generic chain", "features formed by the slab finalize kernel",
                 "rows staged by cp.async", "64-row pieces", "128-row pieces", "256-row pieces", "no dependent launches",
-                "int32 plane slabs"]
+                "int32 plane slabs", "winners through global memory"]
         for (o, _), w in zip(outs[1:], what[1:]):
             for f in ("features", "score", "index", "label", "resid2"):
                 assert np.array_equal(getattr(a, f), getattr(o, f)), (D, k, n, B, metric, f, "tc vs " + w)
