@@ -286,6 +286,9 @@ match_small_tc_kernel(const MstArgs a) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int qt = blockIdx.x, piece = blockIdx.y;
   const int row_base = piece * a.bnp;
+  // the next kernel of the stream (the projection of the following batch: it only reads until its own
+  // griddepcontrol.wait) may be scheduled on SMs this grid leaves free
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   long long* tr = a.trace ? a.trace + ((size_t)blockIdx.y * gridDim.x + blockIdx.x) * 8 : nullptr;
 #define MST_STAMP(i) if (tr && threadIdx.x == 64) tr[i] = clock64()
   MST_STAMP(0);

@@ -253,6 +253,10 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
       }
       if (!mbar_wait(&sh->tmem_full_bar, seg & 1, failed)) { ok = false; break; }
       tc_fence_after();
+      // Launched with programmatic stream serialization, the main loop above (it only READS crops and basis) may have
+      // run while the previous kernel of the stream was still draining; everything this kernel WRITES (slabs,
+      // accumulators, sums of squares) waits for that kernel here.
+      asm volatile("griddepcontrol.wait;" ::: "memory");
       for (int c0 = 0; c0 < a.block_n; c0 += 16) {
         uint32_t v[16];
         tmem_ld16(tmem_base + ((uint32_t)(lane_group * 32) << 16) + (uint32_t)c0, v);
@@ -465,17 +469,19 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attrs[1];
+    cudaLaunchAttribute attrs[2];
     attrs[0].id = cudaLaunchAttributeClusterDimension;
     attrs[0].val.clusterDim.x = (unsigned)a.mcast;
     attrs[0].val.clusterDim.y = 1;
     attrs[0].val.clusterDim.z = 1;
+    attrs[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attrs;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = getenv("EF_NO_PDL") ? 1 : 2;
     EF_CUDA(cudaLaunchKernelEx(&cfg, project_tc_kernel, mx, mw, a));
     ef::g_launches.fetch_add(1, std::memory_order_relaxed);
   } else {
-    EF_LAUNCH(project_tc_kernel, grid, kThreads, smem, stream, mx, mw, a);
+    EF_LAUNCH_PDL(project_tc_kernel, grid, kThreads, smem, stream, mx, mw, a);
   }
   if (probing) {
     // debugging aid: per-CTA phase timestamps relative to the first CTA entering the kernel
