@@ -72,6 +72,8 @@ struct EpiArgs {
 template <int METRIC, int KR>
 __global__ void __launch_bounds__(kThreads)
 fused_epilogue_kernel(const EpiArgs a) {
+  // the projection of the next batch reads only until its own griddepcontrol.wait: it may be scheduled while this drains
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   extern __shared__ __align__(16) double sm[];
   double* ps = sm;                                // [KR][QB] features
   double* gs = ps + KR * QB;                      // [tile_rows][KR] gallery tile

@@ -62,6 +62,9 @@ __device__ __forceinline__ void cp_async8(void* smem, const void* gmem) {
 template <int METRIC, int QPT>
 __global__ void __launch_bounds__(kThreads)
 match_small_kernel(const MsArgs a) {
+  // the projection of the next batch (launched with programmatic stream serialization: it only reads until its own
+  // griddepcontrol.wait) may be scheduled while this grid drains
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   constexpr int QT = 4 * QPT;
   constexpr int kWarps = kThreads / 32;
   extern __shared__ __align__(16) double sm[];

@@ -43,7 +43,10 @@ constexpr int kSlab = 64;                   // halfs of K per slab = one 128-byt
 constexpr int kSlabBytesA = BLOCK_M * 128;  // 16 KB
 constexpr int kTileRows = 256;              // rows per tile of the ef_match_tc image
 constexpr int kTileSlabBytes = kTileRows * 128;
-constexpr int kMaxSlabs = 9;                // 3 (k + 1) <= 576
+constexpr int kMaxSlabs = 9;                // resident operand tiles: 3 (k + 1) <= 576
+constexpr int kMaxSlabsStream = 49;         // operand tiles streamed through a ring: k <= 1024
+constexpr int kListCap = 512;                // streaming mode: (query, candidate) pairs listed per CTA
+constexpr int kRing = 6;                    // most stages of that ring (MstArgs::ring of them in use)
 constexpr int kMaxRows = 4096;              // 64 pieces
 
 struct MstArgs {
@@ -64,8 +67,14 @@ struct MstArgs {
   int32_t* out_index;
   int32_t* out_label;            // nullable
   int sh_off;                    // byte offset of MstShared behind the operand tiles / the staging area
+  int stream;                    // n_slabs > 9: the K slabs of both operands stream through a ring of kRing stages and the
+                                 // exact chains read global memory (the float64 rows of k > 191 do not fit beside each other)
   int cluster;                   // the CTAs of a query tile (one per gallery piece) form a thread-block cluster
   int ex_off;                    // cluster mode: byte offset of the exchange area [pieces][128] (double, then int)
+  int exm_off;                   // ... and of the approximate maxima [pieces][128] float
+  int ring;                      // streaming mode: stages of the ring
+  int slots;                     // streaming mode: (query, candidate) pairs staged per round
+  int list_off;                  // streaming mode: byte offset of the pair list
   int bnp;                       // gallery rows per CTA = UMMA N = TMEM columns
   int pieces, b_pad, rows_round, bulk;   // staged float64 rows: query rows per round; bulk copies possible
   double* part_s;                // [pieces][b_pad]
@@ -78,6 +87,8 @@ struct MstArgs {
 
 struct MstShared {
   unsigned long long full_bar;
+  unsigned long long ring_full[kRing];       // streaming mode: stage filled / drained
+  unsigned long long ring_empty[kRing];
   unsigned long long tmem_full_bar;
   uint32_t tmem_base;
   int failed;
@@ -272,6 +283,62 @@ mst_query_kernel(const MstQueryArgs a) {
   }
 }
 
+// The same for k > 192 (the row does not fit the registers of a warp: two passes over it, no slab finalize)
+__global__ void __launch_bounds__(256)
+mst_query_big_kernel(const MstQueryArgs a) {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  const int q = (int)((blockIdx.x * (unsigned)blockDim.x + threadIdx.x) >> 5);
+  const int lane = threadIdx.x & 31;
+  if (q >= a.b_pad) return;
+  const bool live = q < a.B;
+  const double* __restrict__ p = a.P + (int64_t)q * a.ldp;
+  double acc = 0.0;
+  if (live)
+    for (int c = lane; c < a.k; c += 32) {
+      const double v = p[c];
+      acc = fma(v, v, acc);
+    }
+  const double s2 = ef::warp_sum(acc);
+  double pn = sqrt(s2);
+  if (a.metric == EF_METRIC_COSINE_SK && pn == 0.0) pn = 1.0;
+  if (lane == 0) {
+    a.pn[q] = pn;
+    if (a.resid2 && live) {
+      const double rr = a.sumsq[q] - 2.0 * a.resid2[q] + a.c0 - s2;
+      a.resid2[q] = rr > 0.0 ? rr : 0.0;
+      a.sumsq[q] = 0.0;
+    }
+  }
+  const double dinv = s2 > 0.0 ? 1.0 / sqrt(s2) : 0.0;
+  float rinv = (float)dinv;
+  float last = 0.f;
+  if (a.metric == EF_METRIC_L2) {
+    const double G = *a.gscale;
+    const double rq = s2 > 0.0 ? 0.5 * G * dinv : 1.0;
+    const double t = rq > 1.0 ? 1.0 / rq : 1.0;
+    rinv = (float)(dinv * t);
+    last = live ? -(float)(rq * t) : 0.f;
+  }
+  const int tile = q / BLOCK_M, r = q - tile * BLOCK_M;
+  uint8_t* __restrict__ row = a.qimg + (size_t)tile * a.n_slabs * kSlabBytesA + (size_t)r * 128;
+  const int rx = r & 7;
+  for (int c = lane; c < a.ka; c += 32) {
+    const double pc = (live && c < a.k) ? p[c] : 0.0;
+    if (live && c < a.k) a.pe[(int64_t)q * a.lde + c] = a.metric == EF_METRIC_COSINE_SK ? pc / pn : pc;
+    const float v = c < a.k ? (float)pc * rinv : last;
+    const __half hi = __float2half_rn(v);
+    const __half lo = __float2half_rn(v - __half2float(hi));
+#pragma unroll
+    for (int seg = 0; seg < 3; ++seg) {
+      const int kk = c + seg * a.ka;
+      const int slab = kk >> 6, kin = kk & 63;
+      *reinterpret_cast<__half*>(row + (size_t)slab * kSlabBytesA + ((((kin >> 3) ^ rx)) << 4) + (kin & 7) * 2) =
+          seg < 2 ? hi : lo;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1)
 match_small_tc_kernel(const MstArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -295,6 +362,10 @@ match_small_tc_kernel(const MstArgs a) {
 
   if (tid == 0) {
     mbar_init(&sh->full_bar, 1);
+    for (int st = 0; st < kRing; ++st) {
+      mbar_init(&sh->ring_full[st], 1);
+      mbar_init(&sh->ring_empty[st], 1);
+    }
     mbar_init(&sh->tmem_full_bar, 1);
     sh->failed = 0;
     sh->is_last = 0;
@@ -310,7 +381,7 @@ match_small_tc_kernel(const MstArgs a) {
   // everything up to griddepcontrol.wait overlaps the tail of mst_query_kernel (programmatic dependent launch),
   // including the loads of this CTA's 64 rows of every gallery K slab (the gallery image is static); after it the
   // kernel's outputs (query image, |p|, rows of the exact chain) are complete and visible
-  if (tid == 0) {
+  if (tid == 0 && !a.stream) {
     const int tile = row_base / kTileRows, sub_bytes = (row_base % kTileRows) * 128;
     mbar_arrive_expect_tx(&sh->full_bar, (uint32_t)(a.n_slabs * (kSlabBytesA + kPieceBytes)));
     for (int slab = 0; slab < a.n_slabs; ++slab)
@@ -319,7 +390,7 @@ match_small_tc_kernel(const MstArgs a) {
                 (uint32_t)kPieceBytes, &sh->full_bar);
   }
   asm volatile("griddepcontrol.wait;" ::: "memory");
-  if (tid == 0) {
+  if (tid == 0 && !a.stream) {
     for (int slab = 0; slab < a.n_slabs; ++slab)                 // the query tile, pre-swizzled by mst_query_kernel
       bulk_load(sA + (size_t)slab * kSlabBytesA, a.qimg + ((size_t)qt * a.n_slabs + slab) * kSlabBytesA,
                 (uint32_t)kSlabBytesA, &sh->full_bar);
@@ -330,7 +401,42 @@ match_small_tc_kernel(const MstArgs a) {
   const uint32_t tmem_base = sh->tmem_base;
   volatile int* failed = &sh->failed;
 
-  if (warp == 1 && lane == 0 && mbar_wait(&sh->full_bar, 0, failed)) {
+  if (a.stream) {
+    // ---- k > 191: one K slab of the query tile (16 KB) + the piece's rows of the same slab of the gallery per stage
+    const int stage_bytes = kSlabBytesA + kPieceBytes;
+    if (warp == 0 && lane == 0) {
+      const int tile = row_base / kTileRows, sub_bytes = (row_base % kTileRows) * 128;
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int slab = 0; slab < a.n_slabs; ++slab) {
+        if (!mbar_wait(&sh->ring_empty[stage], phase ^ 1, failed)) break;
+        mbar_arrive_expect_tx(&sh->ring_full[stage], (uint32_t)stage_bytes);
+        uint8_t* dst = smem + (size_t)stage * stage_bytes;
+        bulk_load(dst, a.qimg + ((size_t)qt * a.n_slabs + slab) * kSlabBytesA, (uint32_t)kSlabBytesA, &sh->ring_full[stage]);
+        bulk_load(dst + kSlabBytesA, a.img + ((size_t)tile * a.n_slabs + slab) * kTileSlabBytes + (size_t)sub_bytes,
+                  (uint32_t)kPieceBytes, &sh->ring_full[stage]);
+        if (++stage == a.ring) { stage = 0; phase ^= 1; }
+      }
+    } else if (warp == 1 && lane == 0) {
+      const uint32_t idesc = umma_idesc_f16(a.bnp);
+      int stage = 0;
+      uint32_t phase = 0;
+      bool fed = true;
+      for (int slab = 0; slab < a.n_slabs; ++slab) {
+        if (!mbar_wait(&sh->ring_full[stage], phase, failed)) { fed = false; break; }
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + (size_t)stage * stage_bytes);
+        const uint32_t b_addr = a_addr + kSlabBytesA;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+          umma_f16(tmem_base, umma_desc_sw128(a_addr + ks * 32), umma_desc_sw128(b_addr + ks * 32), idesc,
+                   (slab > 0 || ks > 0) ? 1u : 0u);
+        umma_commit(&sh->ring_empty[stage]);
+        if (++stage == a.ring) { stage = 0; phase ^= 1; }
+      }
+      if (fed) umma_commit(&sh->tmem_full_bar);
+    }
+  } else if (warp == 1 && lane == 0 && mbar_wait(&sh->full_bar, 0, failed)) {
     tc_fence_after();
     const uint32_t idesc = umma_idesc_f16(a.bnp);
     for (int slab = 0; slab < a.n_slabs; ++slab) {
@@ -359,6 +465,7 @@ match_small_tc_kernel(const MstArgs a) {
   int best_i = INT_MAX;
   unsigned mask[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};            // candidate rows of this thread's query, 32 per word
   const int groups = a.bnp >> 5;
+  float amax = -CUDART_INF_F;                                     // approximate maximum of this thread's query
   if (ok && scanning) {
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
@@ -379,7 +486,26 @@ match_small_tc_kernel(const MstArgs a) {
         }
       }
     }
-    const float thr = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) - 2.f * a.eps;
+    amax = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  }
+  if (a.cluster) {
+    // ---- the pieces of a query tile tell each other their approximate maxima (DSMEM, one cluster barrier): a row is
+    // a candidate only inside the band of the maximum over the WHOLE gallery, so a query costs ~one exact chain in
+    // the cluster instead of one per piece (the same argument as the shared running maxima of ef_match_tc.cu)
+    float* ex_m = reinterpret_cast<float*>(smem + a.exm_off);     // [pieces][128]: row `rank` is written by CTA `rank`
+    const uint32_t rank = cluster_ctarank();
+    if (scanning) {
+      const uint32_t mine = smem_u32(ex_m + (size_t)rank * BLOCK_M + r);
+      for (int pc = 0; pc < a.pieces; ++pc) st_cluster_u32(map_to_cta(mine, (uint32_t)pc), __float_as_uint(amax));
+    }
+    cluster_arrive();
+    cluster_wait();
+    if (scanning)
+      for (int pc = 0; pc < a.pieces; ++pc) amax = fmaxf(amax, ex_m[(size_t)pc * BLOCK_M + r]);
+  }
+  if (ok && scanning) {
+    const uint32_t taddr = tmem_base + ((uint32_t)(lane_group * 32) << 16);
+    const float thr = amax - 2.f * a.eps;
     // pass 2: the rows inside the band (the accumulator is read again: 16 cycles per 32 columns)
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -396,7 +522,7 @@ match_small_tc_kernel(const MstArgs a) {
     }
   }
   MST_STAMP(3);
-  if (ok) {
+  if (ok && !a.stream) {
     // ---- exact score of every thread's FIRST candidate (for all but near-duplicate galleries: its only one) from
     // shared memory: the 128 query rows and the 64 gallery rows are staged with coalesced cp.async (row pitch odd:
     // conflict-free 64-bit reads down a row per thread), in one or two K segments.  Straight from global memory the
@@ -484,6 +610,100 @@ match_small_tc_kernel(const MstArgs a) {
           if (better(a.metric, s2, row_base + i, best, best_i)) {
             best = s2;
             best_i = row_base + i;
+          }
+        }
+      }
+    }
+  }
+  if (a.stream) {
+    // ---- k > 191: the rows of a (query, candidate) pair do not fit shared memory for all 128 queries, and a chain that
+    // reads them from global memory waits for L2 once per sixteen steps (30 k cycles per chain, EF_MST_TRACE).  After
+    // the exchange of the maxima a CTA holds ~128 / pieces candidates: they are listed in shared memory and scored in
+    // rounds of `slots` pairs -- ALL threads copy the two rows of every pair of the round into the dead ring
+    // (coalesced 8-byte cp.async), then one thread per pair runs the chain from shared memory.
+    __shared__ int list_n;
+    double* list_s = reinterpret_cast<double*>(smem + a.list_off);  // [kListCap] scores, then the pairs
+    short* list_q = reinterpret_cast<short*>(list_s + kListCap);
+    short* list_j = list_q + kListCap;
+    if (tid == 0) list_n = 0;
+    __syncthreads();
+    bool overflow = false;
+    if (ok && live) {
+#pragma unroll
+      for (int g = 0; g < 8; ++g) {
+        unsigned mk = mask[g];
+        while (mk) {
+          const int i = g * 32 + __ffs((int)mk) - 1;
+          mk &= mk - 1u;
+          const int e = atomicAdd(&list_n, 1);
+          if (e < kListCap) { list_q[e] = (short)r; list_j[e] = (short)i; }
+          else overflow = true;
+        }
+      }
+    }
+    __syncthreads();
+    const int n_list = min(list_n, kListCap);
+    const int pitch = a.k | 1;                                     // doubles per staged row (odd: no bank conflicts)
+    double* rows = reinterpret_cast<double*>(smem);                // [slots][2][pitch]
+    for (int e0 = 0; e0 < n_list; e0 += a.slots) {
+      const int ne = min(a.slots, n_list - e0);
+      for (int w = warp; w < 2 * ne; w += kThreads / 32) {         // a warp per row: coalesced
+        const int e = e0 + (w >> 1);
+        const double* src = (w & 1) ? a.G + (int64_t)(row_base + list_j[e]) * a.ldg
+                                    : a.Pe + (int64_t)(qt * BLOCK_M + list_q[e]) * a.lde;
+        const uint32_t dst = smem_u32(rows + (size_t)w * pitch);
+        for (int c = lane; c < a.k; c += 32)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8u * c), "l"(src + c) : "memory");
+      }
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+      __syncthreads();
+      if (tid < ne) {
+        const int e = e0 + tid;
+        const double* __restrict__ ps = rows + (size_t)(2 * tid) * pitch;
+        const double* __restrict__ gs = ps + pitch;
+        double acc = 0.0;
+        if (a.metric == EF_METRIC_L2) {
+#pragma unroll 8
+          for (int c = 0; c < a.k; ++c) {
+            const double d = ps[c] - gs[c];
+            acc = fma(d, d, acc);
+          }
+        } else {
+#pragma unroll 8
+          for (int c = 0; c < a.k; ++c) acc = fma(ps[c], gs[c], acc);
+        }
+        if (a.metric == EF_METRIC_COSINE_G1) {
+          const double pn = a.pn[qt * BLOCK_M + list_q[e]], gn = a.gnorm[row_base + list_j[e]];
+          acc = (pn == 0.0 || gn == 0.0) ? 0.0 : acc / (pn * gn);
+        }
+        list_s[e] = acc;
+      }
+      __syncthreads();
+    }
+    if (ok && live) {
+      for (int e = 0; e < n_list; ++e)
+        if (list_q[e] == r) {
+          const int j = row_base + list_j[e];
+          if (better(a.metric, list_s[e], j, best, best_i)) {
+            best = list_s[e];
+            best_i = j;
+          }
+        }
+      if (overflow) {                                              // (degenerate: hundreds of rows inside the band)
+        const double* __restrict__ p = a.Pe + (int64_t)q * a.lde;
+        const double pn = a.pn[q];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          unsigned mk = mask[g];
+          while (mk) {
+            const int i = g * 32 + __ffs((int)mk) - 1;
+            mk &= mk - 1u;
+            const double s2 = exact_score(a, p, pn, row_base + i);
+            if (better(a.metric, s2, row_base + i, best, best_i)) {
+              best = s2;
+              best_i = row_base + i;
+            }
           }
         }
       }
@@ -599,7 +819,7 @@ namespace ef {
 bool match_small_tc_supported(int k, int64_t n, int metric) {
   if (k <= 0 || n <= 0 || n > kMaxRows) return false;
   if (metric < EF_METRIC_COSINE_SK || metric > EF_METRIC_L2) return false;
-  return n_slabs_for(k, metric) <= kMaxSlabs;
+  return n_slabs_for(k, metric) <= kMaxSlabsStream;
 }
 
 size_t match_small_tc_image_bytes(int k, int64_t n, int metric) { return ef_match_tc_image_bytes_metric(n, k, metric); }
@@ -621,7 +841,8 @@ int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, in
                    int cap_B, int* status, cudaStream_t stream, const MatchSmallTcSlabs* slabs) {
   if (B <= 0) return EF_OK;
   if (B > cap_B) return EF_ERR_INVALID;
-  if (slabs && (slabs->S != 8 || !slabs->combined || (slabs->ld_part & 3) || slabs->kq > 224 || slabs->kq < k))
+  if (slabs && (slabs->S != 8 || !slabs->combined || (slabs->ld_part & 3) || slabs->kq > 224 || slabs->kq < k ||
+                n_slabs_for(k, metric) > kMaxSlabs))
     return EF_ERR_INVALID;
   if (!match_small_tc_supported(k, n, metric) || !image || !work || !status) return EF_ERR_UNSUPPORTED;
   if (reinterpret_cast<uintptr_t>(work) & 255) return EF_ERR_INVALID;
@@ -647,6 +868,11 @@ int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, in
   // |approximate key - exact key|: 3 ka float16 products accumulated in float32 (see ef_match_tc.cu)
   const bool deep = 3 * a.ka > 384;
   a.eps = metric == EF_METRIC_L2 ? (deep ? 6e-4f : 4e-4f) : (deep ? 3e-4f : 2e-4f);
+  a.stream = a.n_slabs > kMaxSlabs ? 1 : 0;
+  if (a.stream) {                                     // 3 ka products of <= 2^-22 each + the split error, 25 % margin
+    const float e = 3.f * (float)a.ka * 3e-7f + 2e-5f;
+    a.eps = metric == EF_METRIC_L2 ? 2.f * e : e;
+  }
 
   MstQueryArgs qa{};
   if (slabs) {
@@ -662,7 +888,10 @@ int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, in
   qa.pn = reinterpret_cast<double*>(w + L.pn);
   qa.pe = reinterpret_cast<double*>(w + L.phat);
   qa.lde = k | 1;
-  EF_LAUNCH_PDL(mst_query_kernel, (unsigned)ceil_div((int64_t)a.b_pad * 32, 256), 256, 0, stream, qa);
+  if (a.stream)
+    EF_LAUNCH_PDL(mst_query_big_kernel, (unsigned)ceil_div((int64_t)a.b_pad * 32, 256), 256, 0, stream, qa);
+  else
+    EF_LAUNCH_PDL(mst_query_kernel, (unsigned)ceil_div((int64_t)a.b_pad * 32, 256), 256, 0, stream, qa);
 
   // float64 staging area of the exact chain (reuses the operand tiles): all of k when (128 + 64) rows fit 200 KB
   // Bulk copies of the float64 rows need 16-byte aligned blocks of a multiple of 16 bytes: k even, a packed gallery
@@ -677,27 +906,47 @@ int match_small_tc(double* proj, int64_t ldp, int B, int k, const double* gp, in
   int forced = 0;
   if (const char* e = getenv("EF_MST_BNP")) forced = atoi(e);
   for (int bnp : {64, 128, 256}) {
-    const size_t ops = (size_t)a.n_slabs * (kSlabBytesA + (size_t)bnp * 128);
-    const size_t g_bytes = (((size_t)bnp * k + 1) & ~(size_t)1) * sizeof(double);
+    size_t ops, stg;
     int rows = BLOCK_M;
-    while (rows > 8 && g_bytes + (size_t)rows * a.lde * sizeof(double) > 200 * 1024) rows /= 2;
-    const size_t stg = g_bytes + (size_t)rows * a.lde * sizeof(double);
+    int ring = 0;
+    if (a.stream) {
+      // two CTAs per SM for the smaller pieces (ring <= ~100 KB), four stages alone on the SM for 256-row pieces
+      const size_t stage_bytes = kSlabBytesA + (size_t)bnp * 128;
+      ring = bnp == 256 ? 4 : (int)std::min<size_t>(kRing, (100 * 1024) / stage_bytes);
+      ops = (size_t)ring * stage_bytes;
+      stg = 0;
+    } else {
+      ops = (size_t)a.n_slabs * (kSlabBytesA + (size_t)bnp * 128);
+      const size_t g_bytes = (((size_t)bnp * k + 1) & ~(size_t)1) * sizeof(double);
+      while (rows > 8 && g_bytes + (size_t)rows * a.lde * sizeof(double) > 200 * 1024) rows /= 2;
+      stg = g_bytes + (size_t)rows * a.lde * sizeof(double);
+    }
     if (std::max(ops, stg) > 216 * 1024) break;
-    a.bnp = bnp; a.rows_round = rows; operands = ops; staging = stg;
+    a.bnp = bnp; a.rows_round = rows; a.ring = ring; operands = ops; staging = stg;
     if (forced == bnp) break;
     const int64_t occ = std::max<int64_t>(1, std::min<int64_t>(512 / bnp, (220 * 1024) / (int64_t)(std::max(ops, stg) + 2048)));
     if (!forced && (int64_t)q_tiles * ceil_div(n, bnp) <= (int64_t)sm_count() * occ) break;
   }
   if (!a.bnp) return EF_ERR_UNSUPPORTED;
+  if (a.stream) {
+    a.slots = (int)std::min<size_t>(kThreads, operands / (2 * (size_t)(k | 1) * sizeof(double)));
+    if (a.slots < 1) return EF_ERR_UNSUPPORTED;
+  }
   a.pieces = (int)ceil_div(n, a.bnp);
   size_t smem = std::max(operands, (staging + 15) & ~(size_t)15) + sizeof(MstShared) + 64;
   a.sh_off = (int)std::max(operands, (staging + 15) & ~(size_t)15);
   // the CTAs of a query tile as one cluster (portable size, exchange area fits): winners meet through DSMEM
-  const size_t ex_bytes = (size_t)a.pieces * BLOCK_M * (sizeof(double) + sizeof(int));
+  const size_t ex_bytes = (size_t)a.pieces * BLOCK_M * (sizeof(double) + sizeof(int) + sizeof(float));
   a.cluster = a.pieces > 1 && a.pieces <= 8 && smem + ex_bytes <= (size_t)kSmemLimit && !getenv("EF_MST_NO_CLUSTER");
   if (a.cluster) {
     a.ex_off = (int)((smem + 15) & ~(size_t)15);
+    a.exm_off = a.ex_off + (int)((size_t)a.pieces * BLOCK_M * (sizeof(double) + sizeof(int)));
     smem = (size_t)a.ex_off + ex_bytes;
+  }
+  if (a.stream) {
+    a.list_off = (int)((smem + 15) & ~(size_t)15);
+    smem = (size_t)a.list_off + (size_t)kListCap * (sizeof(double) + 2 * sizeof(short));
+    if (smem > (size_t)kSmemLimit) return EF_ERR_UNSUPPORTED;
   }
   EF_ENSURE_SMEM(match_small_tc_kernel, smem);
   const dim3 grid((unsigned)q_tiles, (unsigned)a.pieces);

@@ -573,7 +573,7 @@ int ef_match_tc_prepare_device(const double* prepared, int64_t ldg, const double
                                int32_t metric, void* image, ef_stream_t stream) {
   if (!prepared || !image || n <= 0 || k <= 0 || ldg < k) return EF_ERR_INVALID;
   if (metric < EF_METRIC_COSINE_SK || metric > EF_METRIC_L2) return EF_ERR_INVALID;
-  if (n_slabs_for(k, metric) > 9) return EF_ERR_UNSUPPORTED;     // (ef_match_tc_device itself takes k <= 128)
+  if (n_slabs_for(k, metric) > 49) return EF_ERR_UNSUPPORTED;    // k <= 1024 (ef_match_tc_device itself takes k <= 128)
   if (metric != EF_METRIC_COSINE_SK && !norms) return EF_ERR_INVALID;
   cudaStream_t st = ef::as_stream(stream);
   const size_t body = image_body_bytes(n, k, metric);

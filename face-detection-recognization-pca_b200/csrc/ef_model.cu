@@ -482,7 +482,7 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
     if (m->last_used_tc && part) {
       int splits = 1, ld_part = 0;
       ef::project_tc_split_shape(B, m->D, m->NC, &splits, &ld_part);
-      if (small_tc && combine && !getenv("EF_MST_NO_FUSED_FINALIZE")) {
+      if (small_tc && combine && m->k <= 191 && !getenv("EF_MST_NO_FUSED_FINALIZE")) {
         // the matcher's query kernel forms the features from the (hi, lo) slabs itself: one launch less, the features
         // stay in its registers.  (With int32 plane slabs -- eight loads per component and split -- a warp per crop was
         // slower than the thread-per-component finalize: 15.6 us against 6.2 + 3.8.)

@@ -486,7 +486,7 @@ def test_small_gallery_fused_match_equals_generic_chain():
 
 @pytest.mark.parametrize("metric", [ef.METRIC_COSINE_G1, ef.METRIC_COSINE_SK, ef.METRIC_L2])
 def test_tensor_core_small_matcher_equals_float64_kernels(metric):
-    """k = 33 ... 191, galleries of <= 4096 rows (the shipped model shapes): the one-launch matcher whose all-pairs scan
+    """k = 33 ... 1024, galleries of <= 4096 rows (the shipped model shapes): the one-launch matcher whose all-pairs scan
     runs on tensor cores (ef_match_small_tc.cu: float16 hi/lo filter, float64 re-score of the rows inside the error
     band) against the float64 one-launch kernel (EF_NO_MATCH_SMALL_TC=1) and the generic chain (EF_NO_MATCH_SMALL=1):
     features, score, index, label and residual bit for bit -- on galleries with exact duplicates, near-duplicates
@@ -496,7 +496,8 @@ def test_tensor_core_small_matcher_equals_float64_kernels(metric):
     rng = np.random.default_rng(1234 + metric)
     cases = [(1600, 50, 229, 4096, False), (1024, 178, 178, 300, True), (1024, 50, 590, 513, True),
              (900, 33, 1, 40, False), (640, 97, 1000, 1, True), (2048, 64, 257, 129, True), (512, 191, 64, 128, False),
-             (512, 40, 4096, 200, False), (700, 50, 65, 5, False)]
+             (512, 40, 4096, 200, False), (700, 50, 65, 5, False),
+             (1024, 300, 500, 300, True), (1200, 590, 590, 200, True), (1100, 1024, 70, 140, False)]   # streamed K slabs
     for D, k, n, B, scaled in cases:
         if metric == ef.METRIC_L2 and k == 191:
             k = 190                                                # one extra component: 3 (k + 1) <= 576

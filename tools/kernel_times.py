@@ -17,6 +17,7 @@ only = sys.argv[1] if len(sys.argv) > 1 else ""
 for name, D, k, ng, metric, scaled in (("Gen-1 shipped (100x100, k=50, 229 rows)", 10000, 50, 229, ef.METRIC_COSINE_G1, False),
                                        ("Gen-2 train-v5 (64x64, k=178, 178 rows)", 4096, 178, 178, ef.METRIC_COSINE_SK, True),
                                        ("Gen-2 train-v4 (64x64, k=50, 590 rows)", 4096, 50, 590, ef.METRIC_COSINE_SK, True),
+                                       ("Gen-2 full-k (64x64, k=590, 590 rows)", 4096, 590, 590, ef.METRIC_COSINE_SK, True),
                                        ("bench C2 (100x100, k=10, 1024 rows)", 10000, 10, 1024, ef.METRIC_COSINE_G1, False)):
     if only and only not in name:
         continue

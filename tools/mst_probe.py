@@ -12,7 +12,8 @@ rng = np.random.default_rng(0)
 B = 4096
 for name, D, k, ng, metric, scaled in (("k=50 n=229", 10000, 50, 229, ef.METRIC_COSINE_G1, False),
                                        ("k=178 n=178", 4096, 178, 178, ef.METRIC_COSINE_SK, True),
-                                       ("k=50 n=590", 4096, 50, 590, ef.METRIC_COSINE_SK, True)):
+                                       ("k=50 n=590", 4096, 50, 590, ef.METRIC_COSINE_SK, True),
+                                       ("k=590 n=590", 4096, 590, 590, ef.METRIC_COSINE_SK, True)):
     E = np.linalg.qr(rng.normal(size=(D, k)))[0]
     kw = dict(scale=rng.uniform(20, 60, D), pca_mean=rng.normal(0, 1e-3, D)) if scaled else {}
     rec = ef.Recognizer(E, rng.uniform(60, 200, D), rng.normal(size=(ng, k)) * 100, metric=metric, **kw)
