@@ -215,11 +215,12 @@ def template_section(ef, torch, dev):
 
 SHIPPED = (("gen1_k50_229rows_100x100", 10000, 50, 229, 1, False),
            ("trainv5_k178_178rows_64x64", 4096, 178, 178, 0, True),
-           ("trainv4_k50_590rows_64x64", 4096, 50, 590, 0, True))
+           ("trainv4_k50_590rows_64x64", 4096, 50, 590, 0, True),
+           ("trainv5_fullk_k590_590rows_64x64", 4096, 590, 590, 0, True))   # train-v5 keeps k = N: its largest person
 
 
 def shipped_shapes_section(ef, torch, dev):
-    """Device-resident recognition time per 4096 crops for the model shapes the reference ships (k = 50 ... 178)."""
+    """Device-resident recognition time per 4096 crops for the model shapes the reference ships (k = 50 ... 590)."""
     rng = np.random.default_rng(0)
     B = 4096
     out = {"what": "ef_model_recognize_device, 4096 device-resident crops per call, the model shapes the reference ships",
