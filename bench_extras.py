@@ -270,6 +270,8 @@ def c1_section(ef, torch, dev):
     for _ in range(5):
         r = rec.recognize(X, 0.7, want_features=False)
     batch_s = (time.perf_counter() - t0) / 5
+    for i in range(4):                                        # (first launches of the one-crop kernels: lazy module load)
+        rec.recognize(X[i:i + 1], 0.7, want_features=False)
     t0 = time.perf_counter()
     for i in range(32):
         rec.recognize(X[i:i + 1], 0.7, want_features=False)
