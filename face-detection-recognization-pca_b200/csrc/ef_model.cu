@@ -48,6 +48,7 @@ struct ef_model {
     cudaStream_t stream = nullptr;                    // the stream the pending batch was submitted on
   } pending;
   cudaEvent_t flush_ev = nullptr;
+  cudaEvent_t fan_ev = nullptr;     // multi-model fan-out: crops ready (first model) / this model's chain done
   void* pinned = nullptr;                             // owned page-locked staging for the results of the host path
   size_t pinned_bytes = 0;
   ef::DevBuf multi_dev;                               // ef_models_recognize_boxes_host: [n_models][n_boxes] results
@@ -292,6 +293,7 @@ void ef_model_destroy(ef_model_t* m) {
   if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
   if (m->pinned) cudaFreeHost(m->pinned);
   if (m->flush_ev) cudaEventDestroy(m->flush_ev);
+  if (m->fan_ev) cudaEventDestroy(m->fan_ev);
   if (m->queue_ev) cudaEventDestroy(m->queue_ev);
   for (cudaEvent_t e : m->chunk_ev) cudaEventDestroy(e);
   for (auto& hs : m->hslot) {
@@ -951,13 +953,30 @@ int ef_models_recognize_boxes_host(ef_model_t* const* models, int32_t n_models, 
   EF_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int32_t), st));
   EF_TRY(ef_preprocess(m0->frames_dev.as<uint8_t>(), frame_stride, pitch, width, height, channels, n_frames,
                        m0->boxes_dev.as<ef_box_t>(), n_boxes, dw, dh, m0->x_dev.as<uint8_t>(), m0->x_ld, d_bad, st));
+  // A handful of crops (the reference's pattern: ONE face per call) leaves the GPU almost empty and every model's chain of
+  // 3-4 kernels is latency: the models then run side by side, each on its own stream, between two events (crops ready /
+  // chain done).  Large batches fill the GPU model by model and stay on one stream.
+  const bool fan = n_models > 1 && n_boxes <= 256 && !getenv("EF_NO_FANOUT_STREAMS");
+  if (fan) {
+    if (!m0->fan_ev) EF_CUDA(cudaEventCreateWithFlags(&m0->fan_ev, cudaEventDisableTiming));
+    EF_CUDA(cudaEventRecord(m0->fan_ev, st));
+  }
   for (int i = 0; i < n_models; ++i) {
     ef_result_t dev{};
     dev.score = d_score + (size_t)i * nB;
     dev.index = d_index + (size_t)i * nB;
     dev.label = d_label + (size_t)i * nB;
-    EF_TRY(ef_model_recognize_device(models[i], m0->x_dev.as<uint8_t>(), m0->x_ld, n_boxes, threshold, &dev, st));
+    cudaStream_t si = (fan && i > 0) ? models[i]->stream : st;
+    if (si != st) EF_CUDA(cudaStreamWaitEvent(si, m0->fan_ev, 0));
+    EF_TRY(ef_model_recognize_device(models[i], m0->x_dev.as<uint8_t>(), m0->x_ld, n_boxes, threshold, &dev, si));
+    if (si != st) {
+      if (!models[i]->fan_ev) EF_CUDA(cudaEventCreateWithFlags(&models[i]->fan_ev, cudaEventDisableTiming));
+      EF_CUDA(cudaEventRecord(models[i]->fan_ev, si));
+    }
   }
+  if (fan)
+    for (int i = 1; i < n_models; ++i)
+      if (models[i]->stream != st) EF_CUDA(cudaStreamWaitEvent(st, models[i]->fan_ev, 0));
   EF_CUDA(cudaMemcpyAsync(m0->pinned, d, block, cudaMemcpyDeviceToHost, st));
   int32_t* h_status = reinterpret_cast<int32_t*>(reinterpret_cast<char*>(m0->pinned) + status_off);
   for (int i = 0; i < n_models; ++i)                                  // tcgen05 pipeline-timeout flags of the models
