@@ -315,7 +315,7 @@ finalize_slabs_kernel(const int32_t* __restrict__ part, int splits, long long sl
 __global__ void __launch_bounds__(256)
 finalize_slabs_hilo_kernel(const long long* __restrict__ part, int splits, long long slab_stride, int ld64, int B, int k,
                            int kq, const int32_t* __restrict__ col_exp, const double* __restrict__ bias,
-                           double* __restrict__ proj, int64_t ldp, double* __restrict__ xu_out) {
+                           double* __restrict__ proj, int64_t ldp, double* __restrict__ xu_out, const ef::TcTail tail) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   asm volatile("griddepcontrol.wait;" ::: "memory");
   const unsigned idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -323,11 +323,30 @@ finalize_slabs_hilo_kernel(const long long* __restrict__ part, int splits, long 
   const int c = (int)(idx - (unsigned)b * (unsigned)kq);
   if (b >= B) return;
   long long hi = 0, lo = 0;
-  for (int sp = 0; sp < splits; ++sp) {
-    const longlong2 v = __ldcg(reinterpret_cast<const longlong2*>(part + (size_t)sp * slab_stride + (size_t)b * ld64) + c);
-    hi += v.x;
-    lo += v.y;
+  bool in_tail = false;
+  if (tail.first >= 0) {
+    // tail split of the projection: the tiles of its last, partial wave hold `tail.splits` partial tiles in the compact
+    // region behind slab 0
+    const int n_tile = (8 * c) / tail.block_n, m_tile = b >> 7;
+    const int t = n_tile * tail.m_tiles + m_tile;
+    if (t >= tail.first) {
+      in_tail = true;
+      const long long tile64 = (long long)128 * tail.block_n / 4;                      // long longs per partial tile
+      const long long* base = part + tail.region / 4 + (long long)(t - tail.first) * tail.splits * tile64 +
+                              (long long)(b & 127) * (tail.block_n / 4) + (8 * c - n_tile * tail.block_n) / 4;
+      for (int sp = 0; sp < tail.splits; ++sp) {
+        const longlong2 v = __ldcg(reinterpret_cast<const longlong2*>(base + (long long)sp * tile64));
+        hi += v.x;
+        lo += v.y;
+      }
+    }
   }
+  if (!in_tail)
+    for (int sp = 0; sp < splits; ++sp) {
+      const longlong2 v = __ldcg(reinterpret_cast<const longlong2*>(part + (size_t)sp * slab_stride + (size_t)b * ld64) + c);
+      hi += v.x;
+      lo += v.y;
+    }
   double v = ldexp(ef::hilo_to_double(hi, lo), col_exp[c]);
   if (c < k) proj[(size_t)b * ldp + c] = v - bias[c];
   else if (xu_out) xu_out[b] = v;
@@ -392,15 +411,16 @@ int fused_epilogue(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, cons
 
 int project_finalize_slabs(const int32_t* part, int splits, int ld_part, int B, int k, int kq, int S,
                            const int32_t* col_exp, const double* bias, double* proj, int64_t ldp, double* resid2,
-                           cudaStream_t stream, bool combined) {
+                           cudaStream_t stream, bool combined, const TcTail* tail) {
   if (B <= 0) return EF_OK;
   if (S > 8 || (int64_t)B * kq >= (1ll << 31) - 256) return EF_ERR_INVALID;
   const unsigned grid = (unsigned)ceil_div((int64_t)B * kq, 256);
   if (combined) {
     if (S != 8 || (ld_part & 3)) return EF_ERR_INVALID;
+    const TcTail tl = tail ? *tail : TcTail{-1, 1, 0, 0, 0};
     EF_LAUNCH_PDL(finalize_slabs_hilo_kernel, grid, 256, 0, stream, reinterpret_cast<const long long*>(part), splits,
                   (long long)B * (ld_part / 4), ld_part / 4, B, k, kq, col_exp, bias, proj, (int64_t)ldp,
-                  (kq > k) ? resid2 : (double*)nullptr);
+                  (kq > k) ? resid2 : (double*)nullptr, tl);
     return EF_OK;
   }
   EF_LAUNCH_PDL(finalize_slabs_kernel, grid, 256, 0, stream, part, splits, (long long)B * ld_part, ld_part, B, k, kq, S,

@@ -50,6 +50,15 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
                int32_t* acc_t, int ld_acc, double* sumsq, int* status, cudaStream_t stream, int32_t* part = nullptr,
                bool combine = false);
 void project_tc_split_shape(int B, int D, int NC, int* splits, int* ld_part);
+// Tail split of the combined slabs (more tiles than SMs): tiles [0, first) are unsplit in slab 0, tile t >= first has
+// `splits` partial tiles at part + region + ((t - first) * splits + s) * 128 * block_n (int32 units, rows of block_n);
+// tile id = column tile * m_tiles + crop tile.  first < 0: no tail.
+struct TcTail {
+  int first, splits, block_n, m_tiles;
+  long long region;
+};
+bool project_tc_tail_shape(int B, int D, int NC, TcTail* t);
+size_t project_tc_part_elems(int B, int D, int NC);   // int32 elements of a slab buffer for batches of up to B crops
 size_t project_tc_part_bytes(int B, int D, int NC);
 
 // ef_recognize_cluster.cu -- single-kernel form (cluster of 4, DSMEM reduction, fused match); EF_ERR_UNSUPPORTED when
@@ -117,7 +126,7 @@ int project_finalize(int32_t* acc_t, int ld_acc, int B, int k, int kq, int S, co
 // split-K slabs of project_tc -> float64 features (and x . u~ into resid2 when kq > k); nothing to clear
 int project_finalize_slabs(const int32_t* part, int splits, int ld_part, int B, int k, int kq, int S,
                            const int32_t* col_exp, const double* bias, double* proj, int64_t ldp, double* resid2,
-                           cudaStream_t stream, bool combined = false);
+                           cudaStream_t stream, bool combined = false, const TcTail* tail = nullptr);
 
 int project_resid(const double* proj, int64_t ldp, int B, int k, double* sumsq, double c0, double* resid2,
                   cudaStream_t stream);

@@ -358,11 +358,8 @@ int ef_model_reserve(ef_model_t* m, int32_t max_batch) {
   EF_CUDA(cudaMemset(m->acc.p, 0, sizeof(int32_t) * (B + 32) * m->nc_pad));
   EF_TRY(m->proj.ensure(sizeof(double) * B * m->k));
   if (!ef::fused_epilogue_supported(m->k, m->n_gallery)) {
-    // splits x crops never exceeds max(batch, one wave of 128-crop tiles): see project_tc_split_shape
-    int splits = 1, ld_part = 0;
-    ef::project_tc_split_shape((int)B, m->D, m->NC, &splits, &ld_part);
-    const size_t rows = std::max(B, (size_t)ef::sm_count() * 128);
-    EF_TRY(m->part.ensure(sizeof(int32_t) * rows * ld_part));
+    // split-K slabs of the projection (+ the tail region of its last partial wave)
+    EF_TRY(m->part.ensure(sizeof(int32_t) * ef::project_tc_part_elems((int)B, m->D, m->NC)));
   }
   EF_TRY(m->sumsq.ensure(sizeof(double) * (B + 32)));
   EF_TRY(m->sumsq_w.ensure(sizeof(double) * (B + 32)));
@@ -484,7 +481,9 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
     if (m->last_used_tc && part) {
       int splits = 1, ld_part = 0;
       ef::project_tc_split_shape(B, m->D, m->NC, &splits, &ld_part);
-      if (small_tc && combine && m->k <= 191 && !getenv("EF_MST_NO_FUSED_FINALIZE")) {
+      ef::TcTail tail{};
+      const bool tailed = combine && ef::project_tc_tail_shape(B, m->D, m->NC, &tail);
+      if (small_tc && combine && !tailed && m->k <= 191 && !getenv("EF_MST_NO_FUSED_FINALIZE")) {
         // the matcher's query kernel forms the features from the (hi, lo) slabs itself: one launch less, the features
         // stay in its registers.  (With int32 plane slabs -- eight loads per component and split -- a warp per crop was
         // slower than the thread-per-component finalize: 15.6 us against 6.2 + 3.8.)
@@ -494,7 +493,7 @@ int ef_model_recognize_device(ef_model_t* m, const uint8_t* x, int64_t ldx, int3
       } else {
         EF_TRY(ef::project_finalize_slabs(part, splits, ld_part, B, m->k, m->kq, m->S, m->col_exp.as<int32_t>(),
                                           m->bias.as<double>(), proj, m->k, want_resid ? out->resid2 : nullptr, st,
-                                          combine));
+                                          combine, tailed ? &tail : nullptr));
         if (!small && want_resid)
           EF_TRY(ef::project_resid(proj, m->k, B, m->k, sumsq, m->c0, out->resid2, st));
       }

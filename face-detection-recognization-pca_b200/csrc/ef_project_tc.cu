@@ -45,6 +45,11 @@ struct Args {
   // 32, in slabs of long long [split][row][ld_part / 4]
   int combine;
   long long slab_stride;
+  // tail split (tail_first >= 0; combined slabs, more tiles than SMs): tiles [0, tail_first) are whole waves of one CTA
+  // per tile (full K range, slab 0); the tiles of the last, partial wave are split tail_splits ways along K so that the
+  // wave takes 1 / tail_splits of a tile's time.  Their partial tiles go to a compact region behind slab 0:
+  // [tile - tail_first][split][128 rows][block_n]
+  int tail_first, tail_splits;
   // split-K mode with mcast > 1: clusters of `mcast` consecutive crop tiles of the same (column tile, K range) share the
   // basis tile -- every CTA fetches 1/mcast of it and TMA-multicasts that part into the shared memory of all of them
   int mcast, m_tiles_pad;
@@ -123,16 +128,31 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
   // this CTA's contiguous range of (n tile, m tile, k block) units
   const long long total_units = (long long)a.n_tiles * a.m_tiles * a.kb_total;
   long long u_begin, u_end;
-  int split = 0;
+  int split = 0, tail_tile = -1;
   Seg fixed{0, 0, 0, 0};
   if (a.part) {
     // blockIdx = (column tile, K range, crop tile): the `mcast` CTAs of a cluster are consecutive crop tiles
-    const int grp = blockIdx.x / a.m_tiles_pad;
-    fixed.m_tile = blockIdx.x - grp * a.m_tiles_pad;         // may lie past the batch (cluster padding): loads zero fill
-    fixed.n_tile = grp / a.splits;
-    split = grp - fixed.n_tile * a.splits;
-    fixed.kb0 = (int)((long long)a.kb_total * split / a.splits);
-    fixed.kb1 = (int)((long long)a.kb_total * (split + 1) / a.splits);
+    if (a.tail_first >= 0) {
+      int t = (int)blockIdx.x, ways = 1;
+      if (t >= a.tail_first) {
+        const int i = t - a.tail_first;
+        t = a.tail_first + i / a.tail_splits;
+        split = i - (t - a.tail_first) * a.tail_splits;
+        ways = a.tail_splits;
+        tail_tile = t - a.tail_first;
+      }
+      fixed.n_tile = t / a.m_tiles_pad;
+      fixed.m_tile = t - fixed.n_tile * a.m_tiles_pad;
+      fixed.kb0 = (int)((long long)a.kb_total * split / ways);
+      fixed.kb1 = (int)((long long)a.kb_total * (split + 1) / ways);
+    } else {
+      const int grp = blockIdx.x / a.m_tiles_pad;
+      fixed.m_tile = blockIdx.x - grp * a.m_tiles_pad;       // may lie past the batch (cluster padding): loads zero fill
+      fixed.n_tile = grp / a.splits;
+      split = grp - fixed.n_tile * a.splits;
+      fixed.kb0 = (int)((long long)a.kb_total * split / a.splits);
+      fixed.kb1 = (int)((long long)a.kb_total * (split + 1) / a.splits);
+    }
     u_begin = 0;
     u_end = fixed.kb1 - fixed.kb0;
   } else {
@@ -270,9 +290,12 @@ project_tc_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_const
 #pragma unroll
             for (int j = 0; j < 8; ++j) pl[j] = (int32_t)v[8 + j];
             ef::planes_to_hilo(pl, h1, l1);
-            longlong2* dst = reinterpret_cast<longlong2*>(
-                reinterpret_cast<long long*>(a.part) + ((size_t)split * a.slab_stride + (size_t)row * a.ld_part) / 4 +
-                (size_t)((n_tile * a.block_n + c0) >> 2));
+            // int32-unit offset of (row, column c0) -- a multiple of 16 -- in slab `split`, or in the compact tail region
+            const size_t off = tail_tile < 0
+                ? (size_t)split * a.slab_stride + (size_t)row * a.ld_part + (size_t)(n_tile * a.block_n + c0)
+                : (size_t)a.slab_stride + ((size_t)tail_tile * a.tail_splits + split) * ((size_t)BLOCK_M * a.block_n) +
+                      (size_t)(row - m_tile * BLOCK_M) * a.block_n + (size_t)c0;
+            longlong2* dst = reinterpret_cast<longlong2*>(reinterpret_cast<long long*>(a.part) + off / 4);
             __stcg(dst, make_longlong2(h0, l0));
             __stcg(dst + 1, make_longlong2(h1, l1));
           }
@@ -388,6 +411,36 @@ static void split_shape(int B, int D, int NC, int* splits, int* ld_part, int* mc
   *ld_part = n_tiles * block_n;
 }
 
+// Tail split of the combined split-K slabs (see Args::tail_first): does it apply to this shape, and how.
+bool project_tc_tail_shape(int B, int D, int NC, TcTail* t) {
+  int splits, ld_part, mcast, m_tiles_pad, block_n, n_tiles;
+  split_shape(B, D, NC, &splits, &ld_part, &mcast, &m_tiles_pad);
+  tile_shape(NC, &block_n, &n_tiles);
+  const int sms = sm_count();
+  const int tiles = n_tiles * m_tiles_pad;
+  TcTail r{-1, 1, block_n, m_tiles_pad, 0};
+  if (t) *t = r;
+  if (mcast != 1 || tiles <= sms || getenv("EF_TC_NO_TAIL_SPLIT")) return false;
+  const int full = (tiles / sms) * sms, tail = tiles - full;
+  if (tail == 0) return false;
+  const int kb_total = (int)ceil_div(D, BLOCK_K);
+  const int ways = std::min(std::min(8, sms / tail), kb_total);
+  if (ways < 2) return false;
+  r.first = full;
+  r.splits = ways;
+  r.region = (long long)B * ld_part;                  // int32 units: the tail region starts behind slab 0
+  if (t) *t = r;
+  return true;
+}
+
+// int32 elements of the slab buffer for batches of up to B crops (slabs + the largest tail region any batch can ask for)
+size_t project_tc_part_elems(int B, int D, int NC) {
+  int splits, ld_part;
+  project_tc_split_shape(B, D, NC, &splits, &ld_part);
+  const size_t rows = std::max<size_t>((size_t)B, (size_t)sm_count() * BLOCK_M);
+  return rows * (size_t)ld_part + (size_t)sm_count() * BLOCK_M * 512;
+}
+
 void project_tc_split_shape(int B, int D, int NC, int* splits, int* ld_part) {
   int mcast, m_tiles_pad;
   split_shape(B, D, NC, splits, ld_part, &mcast, &m_tiles_pad);
@@ -439,6 +492,13 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
       a.n_loads = 1;
     }
   }
+  a.tail_first = -1;
+  a.tail_splits = 1;
+  TcTail tail{};
+  if (part && combine && project_tc_tail_shape(B, D, NC, &tail)) {
+    a.tail_first = tail.first;
+    a.tail_splits = tail.splits;
+  }
   a.sumsq = sumsq;
   a.status = status;
   a.probe = nullptr;
@@ -454,6 +514,7 @@ int project_tc(const uint8_t* X, int64_t ldx, int B, int D, const int8_t* Wq, in
   if (const char* e = getenv("EF_TC_GRID")) { const int v = atoi(e); if (v >= 1) grid = v; }
   if (grid > total_units) grid = (int)total_units;
   if (part) grid = a.n_tiles * a.m_tiles_pad * a.splits;
+  if (a.tail_first >= 0) grid = a.tail_first + (a.n_tiles * a.m_tiles_pad - a.tail_first) * a.tail_splits;
   static unsigned long long* probe_buf = nullptr;
   static int probe_grid = 0;
   const bool probing = getenv("EF_TC_PROBE") != nullptr;

@@ -556,6 +556,33 @@ def test_tensor_core_small_matcher_equals_float64_kernels(metric):
         rec.close()
 
 
+def test_projection_tail_split_is_bit_identical():
+    """More (crop tile, column tile) pairs than SMs: the tiles of the projection's last, partial wave are split along K and
+    their partial (hi, lo) tiles summed by the slab finalize.  Same features and answers as without the tail split
+    (EF_TC_NO_TAIL_SPLIT=1), as the int32 plane slabs and as the generic chain -- also for k <= 191, where the matcher's
+    query kernel otherwise reads the slabs itself."""
+    import os
+    require_gpu()
+    rng = np.random.default_rng(777)
+    for D, k, n, B in ((384, 300, 200, 4096), (512, 590, 300, 3000), (256, 178, 178, 8192)):
+        E = np.linalg.qr(rng.normal(size=(max(D, k), k)))[0][:D]
+        rec = ef.Recognizer(E, rng.uniform(40, 210, D), rng.normal(size=(n, k)) * 20, metric=ef.METRIC_COSINE_SK,
+                            labels=rng.integers(0, 9, n), scale=rng.uniform(5.0, 80.0, D), pca_mean=rng.normal(0, 1e-2, D))
+        X = rng.integers(0, 256, (B, D), dtype=np.uint8)
+        a = rec.recognize(X, 0.1)
+        for env in ("EF_TC_NO_TAIL_SPLIT", "EF_NO_SLAB_COMBINE", "EF_NO_MATCH_SMALL"):
+            os.environ[env] = "1"
+            try:
+                o = rec.recognize(X, 0.1)
+            finally:
+                os.environ.pop(env, None)
+            for f in ("features", "score", "index", "label", "resid2"):
+                assert np.array_equal(getattr(a, f), getattr(o, f)), (D, k, n, B, env, f)
+        few = rec.recognize(X[:130], 0.1)                          # no tail at this size, the same slab buffer
+        assert np.array_equal(few.index, a.index[:130]) and np.array_equal(few.features, a.features[:130])
+        rec.close()
+
+
 def test_split_k_slabs_equal_stream_k_atomics():
     """k > 32 on tensor cores: the split-K schedule that STORES partial tiles into slabs (default) against the stream-K
     schedule that merges them with int32 RED atomics (EF_NO_SLABS=1) and against the CUDA-core path (mode 0)."""
