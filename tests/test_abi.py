@@ -50,6 +50,21 @@ def test_argument_validation_needs_no_gpu():
     assert L.ef_eigh_work_bytes(0) == 0
 
 
+def test_matcher_image_sizes_are_host_arithmetic():
+    """Sizing functions of the tensor-core matchers are pure host arithmetic (callable without a device): 256-row tiles x
+    K slabs of 64 halfs (3 k halfs per row, 3 (k + 1) for the Euclidean metric) x 32 KB + a 256-byte trailer."""
+    L = ef._lib.lib()
+    tiles = -(-1_000_000 // 256)
+    assert L.ef_match_tc_image_bytes(1_000_000, 128) == tiles * 6 * 32768 + 256
+    assert L.ef_match_tc_image_bytes_metric(1_000_000, 128, ef.METRIC_COSINE_G1) == tiles * 6 * 32768 + 256
+    assert L.ef_match_tc_image_bytes_metric(1_000_000, 128, ef.METRIC_L2) == tiles * 7 * 32768 + 256
+    assert L.ef_match_tc_image_bytes_metric(229, 50, ef.METRIC_COSINE_SK) == 1 * 3 * 32768 + 256
+    assert L.ef_match_tc_image_bytes_metric(590, 590, ef.METRIC_COSINE_SK) == 3 * 28 * 32768 + 256
+    assert L.ef_match_tc_image_bytes_metric(0, 50, ef.METRIC_COSINE_SK) == 0
+    assert L.ef_match_tc_prepare_device(None, 0, None, 0, 0, 0, None, None) == ef._lib.EF_ERR_INVALID
+    assert L.ef_match_tc_device(None, 0, 0, 0, None, 0, None, None, 0, 0, 0, None, None, None, 0, None) == ef._lib.EF_ERR_INVALID
+
+
 def test_no_cpu_fallback_without_device():
     import torch
     if torch.cuda.is_available():
