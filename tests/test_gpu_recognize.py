@@ -556,6 +556,49 @@ def test_tensor_core_small_matcher_equals_float64_kernels(metric):
         rec.close()
 
 
+def test_back_to_back_batches_overlap_safely():
+    """Device-resident batches enqueued back to back, nothing synchronised in between: with the programmatic dependent
+    launches the projection of batch i + 1 runs while the matcher of batch i drains, and the row sums run beside the
+    projection.  Every batch of a 60-call run (two interleaved models, outputs kept per call) must equal the result of
+    the same call made alone without dependent launches (EF_NO_PDL=1)."""
+    import os
+    torch = require_gpu()
+    rng = np.random.default_rng(2024)
+    B = 2048
+    recs, xs = [], []
+    for D, k, n, metric, scaled in ((1024, 50, 229, ef.METRIC_COSINE_G1, False), (1024, 178, 178, ef.METRIC_COSINE_SK, True),
+                                    (768, 300, 300, ef.METRIC_COSINE_SK, True)):
+        E = np.linalg.qr(rng.normal(size=(D, k)))[0]
+        kw = dict(scale=rng.uniform(5.0, 80.0, D), pca_mean=rng.normal(0, 1e-2, D)) if scaled else {}
+        recs.append(ef.Recognizer(E, rng.uniform(40, 210, D), rng.normal(size=(n, k)) * 20, metric=metric,
+                                  labels=rng.integers(0, 9, n), **kw))
+        xs.append([torch.randint(0, 256, (B, D), dtype=torch.uint8, device="cuda") for _ in range(3)])
+    os.environ["EF_NO_PDL"] = "1"
+    try:
+        want = []
+        for m, rec in enumerate(recs):
+            row = []
+            for x in xs[m]:
+                o = rec.recognize_device(x, 0.1)
+                torch.cuda.synchronize()
+                row.append({f: v.clone() for f, v in o.items() if v is not None})
+            want.append(row)
+    finally:
+        os.environ.pop("EF_NO_PDL", None)
+    got = []
+    for i in range(60):
+        m = i % len(recs) if i % 7 else (i // 7) % len(recs)        # mostly alternating models, sometimes the same twice
+        j = i % 3
+        got.append((m, j, recs[m].recognize_device(xs[m][j], 0.1)))
+    torch.cuda.synchronize()
+    for m, j, o in got:
+        for f, v in want[m][j].items():
+            assert torch.equal(o[f], v), (m, j, f)
+    for rec in recs:
+        assert rec.pipeline_timeouts() == 0
+        rec.close()
+
+
 def test_projection_tail_split_is_bit_identical():
     """More (crop tile, column tile) pairs than SMs: the tiles of the projection's last, partial wave are split along K and
     their partial (hi, lo) tiles summed by the slab finalize.  Same features and answers as without the tail split
