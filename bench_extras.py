@@ -216,7 +216,9 @@ def template_section(ef, torch, dev):
 SHIPPED = (("gen1_k50_229rows_100x100", 10000, 50, 229, 1, False),
            ("trainv5_k178_178rows_64x64", 4096, 178, 178, 0, True),
            ("trainv4_k50_590rows_64x64", 4096, 50, 590, 0, True),
-           ("trainv5_fullk_k590_590rows_64x64", 4096, 590, 590, 0, True))   # train-v5 keeps k = N: its largest person
+           ("trainv5_fullk_k272_272rows_64x64", 4096, 272, 272, 0, True),   # train-v5 keeps k = N: the other shipped persons
+           ("trainv5_fullk_k308_308rows_64x64", 4096, 308, 308, 0, True),
+           ("trainv5_fullk_k590_590rows_64x64", 4096, 590, 590, 0, True))
 
 
 def shipped_shapes_section(ef, torch, dev):
